@@ -1,0 +1,285 @@
+"""ctypes binding of libcpelnano_b200.so — one Python function per symbol of include/cpelnano_b200.h.
+
+Arrays are numpy (host) arrays unless the function name ends in `_device`, in which case raw device
+addresses (ints, e.g. torch.Tensor.data_ptr()) are passed.  No computation happens in Python.
+"""
+import ctypes as C
+import os
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+MSTEP_FD, MSTEP_ANALYTIC = 0, 1
+
+# every exported symbol of include/cpelnano_b200.h (tests check the library exports exactly these)
+SYMBOLS = ["cpn_create", "cpn_destroy", "cpn_last_error", "cpn_version", "cpn_last_device_ms", "cpn_last_launches",
+           "cpn_measure_fp64_peak", "cpn_set_profile", "cpn_get_profile", "cpn_analyze_batch", "cpn_analyze_batch_device", "cpn_fit_batch", "cpn_fit_batch_device", "cpn_estep_batch", "cpn_mstep_batch",
+           "cpn_stat_sums_batch", "cpn_nls_reg_info", "cpn_cmd_batch", "cpn_grp_unmat_sweep", "cpn_grp_mat_sweep", "cpn_two_samp_pvals"]
+
+
+class CpnError(RuntimeError):
+    pass
+
+
+def lib_path():
+    return os.path.join(_HERE, "libcpelnano_b200.so")
+
+
+def _f64(a):
+    return np.ascontiguousarray(a, dtype=np.float64)
+
+
+def _i64(a):
+    return np.ascontiguousarray(a, dtype=np.int64)
+
+
+def _i32(a):
+    return np.ascontiguousarray(a, dtype=np.int32)
+
+
+def _ptr(a):
+    if a is None:
+        return None
+    if isinstance(a, int):
+        return C.c_void_p(a)
+    return a.ctypes.data_as(C.c_void_p)
+
+
+class Library:
+    """Loads the shared library (fails loudly if it has not been built) and owns one cpn_ctx per device."""
+
+    def __init__(self, path=None):
+        path = path or lib_path()
+        if not os.path.exists(path):
+            raise CpnError(f"{path} not found — build it with `python -c 'import __graft_entry__ as g; g.build()'` "
+                           "(nvcc, sm_100a). There is no CPU fallback.")
+        self.dll = C.CDLL(path)
+        d = self.dll
+        d.cpn_version.restype = C.c_char_p
+        d.cpn_last_error.restype = C.c_char_p
+        d.cpn_last_error.argtypes = [C.c_void_p]
+        d.cpn_last_device_ms.restype = C.c_double
+        d.cpn_last_device_ms.argtypes = [C.c_void_p]
+        d.cpn_last_launches.restype = C.c_int64
+        d.cpn_last_launches.argtypes = [C.c_void_p]
+        d.cpn_create.argtypes = [C.c_int, C.POINTER(C.c_void_p)]
+        d.cpn_destroy.argtypes = [C.c_void_p]
+        d.cpn_nls_reg_info.restype = C.c_int64
+        self._ctx = {}
+
+    def version(self):
+        return self.dll.cpn_version().decode()
+
+    def ctx(self, device=0):
+        if device not in self._ctx:
+            h = C.c_void_p()
+            rc = self.dll.cpn_create(int(device), C.byref(h))
+            if rc != 0 or not h.value:
+                raise CpnError(f"cpn_create(device={device}) failed with code {rc}: no usable sm_100 GPU (there is no CPU fallback)")
+            self._ctx[device] = h
+        return self._ctx[device]
+
+    def close(self):
+        for h in self._ctx.values():
+            self.dll.cpn_destroy(h)
+        self._ctx = {}
+
+    def _check(self, rc, ctx):
+        if rc != 0:
+            raise CpnError(f"libcpelnano_b200 error {rc}: {self.dll.cpn_last_error(ctx).decode()}")
+
+    def last_device_ms(self, device=0):
+        return self.dll.cpn_last_device_ms(self.ctx(device))
+
+    def last_launches(self, device=0):
+        return self.dll.cpn_last_launches(self.ctx(device))
+
+    def measure_fp64_peak(self, device=0):
+        v = C.c_double()
+        ctx = self.ctx(device)
+        self._check(self.dll.cpn_measure_fp64_peak(ctx, C.byref(v)), ctx)
+        return v.value
+
+    KERNEL_CLASSES = ("prep", "estep", "mstep", "score", "pick", "statsum", "cmd", "sweep")
+
+    def set_profile(self, enable, device=0):
+        ctx = self.ctx(device)
+        self._check(self.dll.cpn_set_profile(ctx, C.c_int(int(enable))), ctx)
+
+    def get_profile(self, device=0):
+        ms = np.zeros(8)
+        n = np.zeros(8, dtype=np.int64)
+        ctx = self.ctx(device)
+        self._check(self.dll.cpn_get_profile(ctx, _ptr(ms), _ptr(n)), ctx)
+        return {k: (float(ms[i]), int(n[i])) for i, k in enumerate(self.KERNEL_CLASSES)}
+
+    def analyze_batch_raw(self, R, grp_off, Nl, rho_l, d_l, read_off, lu, lm, phi0, n_init, max_em_iters, box, mstep_mode, cpg_off, rho_n,
+                          d_n, sub_off, sub_p, sub_q, phi_hat, Q, status, counters, logZ, ex, exx, log_g, e1, e2, mml, nme, on_device, device=0):
+        """Pointer-level cpn_analyze_batch[_device] (ints = raw addresses, or numpy arrays)."""
+        ctx = self.ctx(device)
+        fn = self.dll.cpn_analyze_batch_device if on_device else self.dll.cpn_analyze_batch
+        rc = fn(ctx, C.c_int64(R), _ptr(grp_off), _ptr(Nl), _ptr(rho_l), _ptr(d_l), _ptr(read_off), _ptr(lu), _ptr(lm), _ptr(phi0),
+                C.c_int32(n_init), C.c_int32(max_em_iters), C.c_double(box[0]), C.c_double(box[1]), C.c_double(box[2]), C.c_int32(mstep_mode),
+                _ptr(cpg_off), _ptr(rho_n), _ptr(d_n), _ptr(sub_off), _ptr(sub_p), _ptr(sub_q), _ptr(phi_hat), _ptr(Q), _ptr(status),
+                _ptr(counters), _ptr(logZ), _ptr(ex), _ptr(exx), _ptr(log_g), _ptr(e1), _ptr(e2), _ptr(mml), _ptr(nme))
+        self._check(rc, ctx)
+
+    def analyze_batch(self, grp_off, Nl, rho_l, d_l, read_off, log_pyx_u, log_pyx_m, phi0, n_init, cpg_off, rho_n, d_n, sub_off, sub_p, sub_q,
+                      max_em_iters=20, box=(20.0, 150.0, 50.0), mstep_mode=MSTEP_ANALYTIC, device=0):
+        grp_off, read_off, cpg_off, sub_off, sub_p, sub_q = (_i64(a) for a in (grp_off, read_off, cpg_off, sub_off, sub_p, sub_q))
+        Nl, rho_l, d_l, lu, lm, phi0, rho_n, d_n = (_f64(a) for a in (Nl, rho_l, d_l, log_pyx_u, log_pyx_m, phi0, rho_n, d_n))
+        R = len(grp_off) - 1
+        sN, sK = int(cpg_off[-1]), int(sub_off[-1])
+        out = dict(phi_hat=np.empty((R, 3)), Q=np.empty(R), pick=np.empty(R, dtype=np.int32), counters=np.empty((R, 4), dtype=np.int64),
+                   logZ=np.empty(R), ex=np.empty(sN), exx=np.empty(sN - R), log_g=np.empty((sK, 4)), e_log_g1=np.empty(sK),
+                   e_log_g2=np.empty(sK), mml=np.empty(sK), nme=np.empty(sK))
+        self.analyze_batch_raw(R, grp_off, Nl, rho_l, d_l, read_off, lu, lm, phi0, n_init, max_em_iters, box, mstep_mode, cpg_off, rho_n, d_n,
+                               sub_off, sub_p, sub_q, out["phi_hat"], out["Q"], out["pick"], out["counters"], out["logZ"], out["ex"], out["exx"],
+                               out["log_g"], out["e_log_g1"], out["e_log_g2"], out["mml"], out["nme"], False, device)
+        return out
+
+    # ---- EM -------------------------------------------------------------------------------------
+    def fit_batch(self, grp_off, Nl, rho_l, d_l, read_off, log_pyx_u, log_pyx_m, phi0, n_init, max_em_iters=20,
+                  box=(20.0, 150.0, 50.0), mstep_mode=MSTEP_ANALYTIC, per_start=False, device=0):
+        grp_off, read_off = _i64(grp_off), _i64(read_off)
+        Nl, rho_l, d_l, lu, lm, phi0 = _f64(Nl), _f64(rho_l), _f64(d_l), _f64(log_pyx_u), _f64(log_pyx_m), _f64(phi0)
+        R = len(grp_off) - 1
+        assert phi0.size == R * n_init * 3, "phi0 must be [R, n_init, 3]"
+        phi_hat, Q = np.empty((R, 3)), np.empty(R)
+        status = np.empty(R, dtype=np.int32)
+        counters = np.empty((R, 4), dtype=np.int64)
+        ps = np.empty((R, n_init, 3)) if per_start else None
+        qs = np.empty((R, n_init)) if per_start else None
+        ctx = self.ctx(device)
+        rc = self.dll.cpn_fit_batch(ctx, C.c_int64(R), _ptr(grp_off), _ptr(Nl), _ptr(rho_l), _ptr(d_l), _ptr(read_off), _ptr(lu), _ptr(lm),
+                                    _ptr(phi0), C.c_int32(n_init), C.c_int32(max_em_iters), C.c_double(box[0]), C.c_double(box[1]),
+                                    C.c_double(box[2]), C.c_int32(mstep_mode), _ptr(phi_hat), _ptr(Q), _ptr(status), _ptr(counters),
+                                    _ptr(ps), _ptr(qs))
+        self._check(rc, ctx)
+        out = dict(phi_hat=phi_hat, Q=Q, pick=status, counters=counters)
+        if per_start:
+            out.update(phi_starts=ps, Q_starts=qs)
+        return out
+
+    def fit_batch_raw(self, R, grp_off, Nl, rho_l, d_l, read_off, lu, lm, phi0, n_init, max_em_iters, box, mstep_mode, phi_hat, Q,
+                      status, counters, on_device, device=0):
+        """Pointer-level call (ints or numpy arrays) used by bench.py with pinned host or device buffers."""
+        ctx = self.ctx(device)
+        fn = self.dll.cpn_fit_batch_device if on_device else self.dll.cpn_fit_batch
+        rc = fn(ctx, C.c_int64(R), _ptr(grp_off), _ptr(Nl), _ptr(rho_l), _ptr(d_l), _ptr(read_off), _ptr(lu), _ptr(lm), _ptr(phi0),
+                C.c_int32(n_init), C.c_int32(max_em_iters), C.c_double(box[0]), C.c_double(box[1]), C.c_double(box[2]), C.c_int32(mstep_mode),
+                _ptr(phi_hat), _ptr(Q), _ptr(status), _ptr(counters), None, None)
+        self._check(rc, ctx)
+
+    def estep_batch(self, grp_off, Nl, rho_l, d_l, read_off, log_pyx_u, log_pyx_m, phi, with_logpy=True, device=0):
+        grp_off, read_off = _i64(grp_off), _i64(read_off)
+        Nl, rho_l, d_l, lu, lm, phi = _f64(Nl), _f64(rho_l), _f64(d_l), _f64(log_pyx_u), _f64(log_pyx_m), _f64(phi)
+        R = len(grp_off) - 1
+        ES = np.empty((R, 3))
+        lp = np.empty(R) if with_logpy else None
+        ctx = self.ctx(device)
+        rc = self.dll.cpn_estep_batch(ctx, C.c_int64(R), _ptr(grp_off), _ptr(Nl), _ptr(rho_l), _ptr(d_l), _ptr(read_off), _ptr(lu), _ptr(lm),
+                                      _ptr(phi), _ptr(ES), _ptr(lp))
+        self._check(rc, ctx)
+        return ES, lp
+
+    def mstep_batch(self, grp_off, Nl, rho_l, d_l, n_reads, ES, phi_init, mstep_mode=MSTEP_ANALYTIC, device=0):
+        grp_off, n_reads = _i64(grp_off), _i64(n_reads)
+        Nl, rho_l, d_l, ES, phi_init = _f64(Nl), _f64(rho_l), _f64(d_l), _f64(ES), _f64(phi_init)
+        R = len(grp_off) - 1
+        sol = np.empty((R, 3))
+        conv = np.empty(R, dtype=np.int32)
+        cnt = np.empty((R, 2), dtype=np.int64)
+        ctx = self.ctx(device)
+        rc = self.dll.cpn_mstep_batch(ctx, C.c_int64(R), _ptr(grp_off), _ptr(Nl), _ptr(rho_l), _ptr(d_l), _ptr(n_reads), _ptr(ES), _ptr(phi_init),
+                                      C.c_int32(mstep_mode), _ptr(sol), _ptr(conv), _ptr(cnt))
+        self._check(rc, ctx)
+        return sol, conv.astype(bool), cnt
+
+    # ---- summaries ------------------------------------------------------------------------------
+    def nls_reg_info(self, chrst, chrend, max_size_subreg, cpg_pos):
+        cpg_pos = _i64(cpg_pos)
+        N = len(cpg_pos)
+        K = self.dll.cpn_nls_reg_info(C.c_int64(chrst), C.c_int64(chrend), C.c_int64(max_size_subreg), _ptr(cpg_pos), C.c_int64(N), None, None, None, None)
+        if K < 0:
+            raise CpnError("cpn_nls_reg_info: bad arguments")
+        st, en, p, q = (np.empty(K, dtype=np.int64) for _ in range(4))
+        self.dll.cpn_nls_reg_info(C.c_int64(chrst), C.c_int64(chrend), C.c_int64(max_size_subreg), _ptr(cpg_pos), C.c_int64(N), _ptr(st), _ptr(en), _ptr(p), _ptr(q))
+        return st, en, p, q
+
+    def stat_sums_batch(self, phi, cpg_off, rho_n, d_n, sub_off, sub_p, sub_q, reg_of=None, device=0):
+        phi, rho_n, d_n = _f64(phi), _f64(rho_n), _f64(d_n)
+        cpg_off, sub_off, sub_p, sub_q = _i64(cpg_off), _i64(sub_off), _i64(sub_p), _i64(sub_q)
+        R = len(cpg_off) - 1
+        T = phi.size // 3
+        if reg_of is not None:
+            reg_of = _i64(reg_of)
+            ex_off = np.concatenate([[0], np.cumsum(np.diff(cpg_off)[reg_of])]).astype(np.int64)
+            k_off = np.concatenate([[0], np.cumsum(np.diff(sub_off)[reg_of])]).astype(np.int64)
+        else:
+            ex_off, k_off = cpg_off, sub_off
+        sN, sK = int(ex_off[-1]), int(k_off[-1])
+        out = dict(logZ=np.empty(T), ex=np.empty(sN), exx=np.empty(sN - T), log_g=np.empty((sK, 4)), e_log_g1=np.empty(sK),
+                   e_log_g2=np.empty(sK), mml=np.empty(sK), nme=np.empty(sK), ex_off=ex_off, k_off=k_off)
+        ctx = self.ctx(device)
+        rc = self.dll.cpn_stat_sums_batch(ctx, C.c_int64(T), _ptr(phi), _ptr(reg_of), _ptr(ex_off if reg_of is not None else None),
+                                          _ptr(k_off if reg_of is not None else None), C.c_int64(R), _ptr(cpg_off), _ptr(rho_n), _ptr(d_n),
+                                          _ptr(sub_off), _ptr(sub_p), _ptr(sub_q), _ptr(out["logZ"]), _ptr(out["ex"]), _ptr(out["exx"]),
+                                          _ptr(out["log_g"]), _ptr(out["e_log_g1"]), _ptr(out["e_log_g2"]), _ptr(out["mml"]), _ptr(out["nme"]))
+        self._check(rc, ctx)
+        return out
+
+    def cmd_batch(self, pair_a, pair_b, phi_tbl, reg_of, ex_off, ex_tbl, exx_tbl, nme_off, nme_tbl, cpg_off, rho_n, d_n, sub_off, sub_p,
+                  sub_q, device=0):
+        pair_a, pair_b, reg_of, ex_off, nme_off = _i64(pair_a), _i64(pair_b), _i64(reg_of), _i64(ex_off), _i64(nme_off)
+        phi_tbl, ex_tbl, exx_tbl, nme_tbl, rho_n, d_n = _f64(phi_tbl), _f64(ex_tbl), _f64(exx_tbl), _f64(nme_tbl), _f64(rho_n), _f64(d_n)
+        cpg_off, sub_off, sub_p, sub_q = _i64(cpg_off), _i64(sub_off), _i64(sub_p), _i64(sub_q)
+        P, T, R = len(pair_a), len(reg_of), len(cpg_off) - 1
+        Ks = np.diff(sub_off)[reg_of[pair_a]] if P else np.zeros(0, dtype=np.int64)
+        cmd_off = np.concatenate([[0], np.cumsum(Ks)]).astype(np.int64)
+        cmd = np.empty(int(cmd_off[-1]))
+        ctx = self.ctx(device)
+        rc = self.dll.cpn_cmd_batch(ctx, C.c_int64(P), _ptr(pair_a), _ptr(pair_b), C.c_int64(T), _ptr(phi_tbl), _ptr(reg_of), _ptr(ex_off),
+                                    _ptr(ex_tbl), _ptr(exx_tbl), _ptr(nme_off), _ptr(nme_tbl), C.c_int64(R), _ptr(cpg_off), _ptr(rho_n), _ptr(d_n),
+                                    _ptr(sub_off), _ptr(sub_p), _ptr(sub_q), _ptr(cmd_off), _ptr(cmd))
+        self._check(rc, ctx)
+        return cmd, cmd_off
+
+    # ---- sweeps ---------------------------------------------------------------------------------
+    def grp_unmat_sweep(self, n1, n2, tbl_off, mml, nme, cmd_tbl, labelings, exact, device=0):
+        tbl_off = _i64(tbl_off)
+        mml, nme, cmd_tbl = _f64(mml), _f64(nme), _f64(cmd_tbl)
+        labelings = _i32(labelings)
+        R, sK = len(tbl_off) - 1, int(tbl_off[-1])
+        P = labelings.shape[0] if labelings.ndim == 2 else labelings.size // max(n1, 1)
+        T, p = np.empty(3 * sK), np.empty(3 * sK)
+        cnt = np.empty(3 * sK, dtype=np.int64)
+        ctx = self.ctx(device)
+        rc = self.dll.cpn_grp_unmat_sweep(ctx, C.c_int64(R), C.c_int32(n1), C.c_int32(n2), _ptr(tbl_off), _ptr(mml), _ptr(nme), _ptr(cmd_tbl),
+                                          _ptr(labelings), C.c_int64(P), C.c_int32(int(exact)), _ptr(T), _ptr(cnt), _ptr(p))
+        self._check(rc, ctx)
+        return T, cnt, p
+
+    def grp_mat_sweep(self, n, tbl_off, mml1, mml2, nme1, nme2, js, exact, device=0):
+        tbl_off, js = _i64(tbl_off), _i64(js)
+        mml1, mml2, nme1, nme2 = _f64(mml1), _f64(mml2), _f64(nme1), _f64(nme2)
+        R, sK = len(tbl_off) - 1, int(tbl_off[-1])
+        T, p = np.empty(2 * sK), np.empty(2 * sK)
+        cnt = np.empty(2 * sK, dtype=np.int64)
+        ctx = self.ctx(device)
+        rc = self.dll.cpn_grp_mat_sweep(ctx, C.c_int64(R), C.c_int32(n), _ptr(tbl_off), _ptr(mml1), _ptr(mml2), _ptr(nme1), _ptr(nme2), _ptr(js),
+                                        C.c_int64(len(js)), C.c_int32(int(exact)), _ptr(T), _ptr(cnt), _ptr(p))
+        self._check(rc, ctx)
+        return T, cnt, p
+
+    def two_samp_pvals(self, tbl_off, P, T_obs, T_null, exact, device=0):
+        tbl_off = _i64(tbl_off)
+        T_obs, T_null = _f64(T_obs), _f64(T_null)
+        R, sK = len(tbl_off) - 1, int(tbl_off[-1])
+        cnt, nv = np.empty(3 * sK, dtype=np.int64), np.empty(3 * sK, dtype=np.int64)
+        p = np.empty(3 * sK)
+        ctx = self.ctx(device)
+        rc = self.dll.cpn_two_samp_pvals(ctx, C.c_int64(R), _ptr(tbl_off), C.c_int64(P), _ptr(T_obs), _ptr(T_null), C.c_int32(int(exact)), _ptr(cnt),
+                                         _ptr(nv), _ptr(p))
+        self._check(rc, ctx)
+        return cnt, nv, p

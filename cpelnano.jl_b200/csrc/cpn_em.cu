@@ -1,0 +1,1080 @@
+// cpn_em.cu — multi-start EM for batches of estimation regions (sm_100a).
+//
+// Reference path: get_ϕhat! → em_inst → em_iter   src/em_algorithm.jl:371/304/132
+//   E-step  get_cond_exs_log + get_ess             src/transfer_matrix.jl:944-965, src/em_algorithm.jl:99-113
+//   M-step  NLsolve on U(ϕ) = ∇logZ(ϕ) − ES/M       src/em_algorithm.jl:152-178, src/transfer_matrix.jl:1225-1246
+//   score   comp_ave_log_py → get_logpy_lgtrck      src/em_algorithm.jl:263-288, src/transfer_matrix.jl:843-870
+//
+// B200 design:
+//   * O(M·L) instead of the reference's O(M·L²): E[S(X)|y_m] = ∇_ϕ log Zc_m(ϕ), evaluated by ONE forward
+//     sweep of the 2-state chain that carries the 3 tangents (∂a,∂b,∂c) next to the message; no backward
+//     pass, no message storage.  Messages are kept in linear (not log) space as doubles renormalised by
+//     exact powers of two; potentials are expressed relative to their larger entry so nothing overflows.
+//   * E-step: one warp per (region,start) EM instance, lanes = reads; emission likelihood ratios are
+//     pre-packed once per call as [chunk][group][32 lanes] so every step is one coalesced 256 B load;
+//     per-group potentials of the instance are staged in shared memory by the warp (lanes = groups).
+//   * M-step: one lane per EM instance (the solve is a serial recursion along the chain); gradient AND
+//     Jacobian of log Z come from one forward sweep carrying first- and second-order tangents, feeding a
+//     restatement of NLsolve's trust-region dogleg.
+//   * The EM loop is a sequence of batched launches over a compacted list of still-active instances.
+#include <cmath>
+#include <cstring>
+#include <limits>
+#include <numeric>
+
+#include "cpn_common.cuh"
+
+namespace {
+
+constexpr int TILE = 128;          // groups staged per shared-memory tile
+constexpr int E_WARPS = 4;         // warps (EM instances) per E-step block
+constexpr int M_THREADS = 128;     // lanes (EM instances) per M-step block
+constexpr double LLR_CLAMP = 300.0;
+constexpr double CBRT_EPS = 6.0554544523933395e-6;
+
+struct RegionTables {
+    // per group (offsets grp_off): N_l, N_l·ρ_l and 1/d_l (coupling l→l+1; entry L-1 unused)
+    const int64_t* grp_off;
+    const double *na, *nb, *invd;
+    // emission likelihood ratios r = exp(log p(y|+1) − log p(y|−1)), 1 for unobserved / padding lanes
+    const int64_t* read_off;   // [R+1]
+    const int64_t* ew_off;     // [R] start of the region's block: [chunk][l][32]
+    const int64_t* rb_off;     // [R] start of the per-read base (Σ_obs log p(y|−1)) block: [chunk][32]
+    const double *ew, *rb;
+};
+
+struct SiteTile {
+    double wm[TILE], wp[TILE], t[TILE], na[TILE], nb[TILE], invd[TILE];
+};
+
+// ---------------------------------------------------------------------------------------------------
+// prep kernels
+// ---------------------------------------------------------------------------------------------------
+// link_functions.jl:16-25 inputs: α_l = a·N_l + b·(N_l ρ_l), β_l = c·(1/d_l)
+__global__ void k_prep_sites(int64_t R, const int64_t* __restrict__ grp_off, const double* __restrict__ Nl,
+                             const double* __restrict__ rho, const double* __restrict__ dl, double* __restrict__ na,
+                             double* __restrict__ nb, double* __restrict__ invd) {
+    int64_t warp = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5;
+    int lane = threadIdx.x & 31;
+    if (warp >= R) return;
+    int64_t g0 = grp_off[warp], g1 = grp_off[warp + 1];
+    int64_t L = g1 - g0;
+    for (int64_t l = lane; l < L; l += 32) {
+        double n = Nl[g0 + l];
+        na[g0 + l] = n;
+        nb[g0 + l] = n * rho[g0 + l];
+        invd[g0 + l] = (l < L - 1) ? 1.0 / dl[g0 - warp + l] : 0.0;
+    }
+}
+
+// Packs emissions (structures.jl:121-128: obs, log_pyx_u, log_pyx_m) as likelihood ratios, lanes = reads.
+// |LLR| is clamped at 300 with the dropped mass (< e^-300 relative) moved into the per-read base term.
+__global__ void k_prep_emis(int64_t R, const int64_t* __restrict__ grp_off, const int64_t* __restrict__ read_off,
+                            const int64_t* __restrict__ obs_off, const double* __restrict__ lu, const double* __restrict__ lm,
+                            const int64_t* __restrict__ ew_off, const int64_t* __restrict__ rb_off, double* __restrict__ ew,
+                            double* __restrict__ rb) {
+    int64_t warp = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5;
+    int lane = threadIdx.x & 31;
+    if (warp >= R) return;
+    int64_t L = grp_off[warp + 1] - grp_off[warp];
+    int64_t M = read_off[warp + 1] - read_off[warp];
+    int64_t nchunk = (M + 31) >> 5;
+    const double* lu_r = lu + obs_off[warp];
+    const double* lm_r = lm + obs_off[warp];
+    for (int64_t ch = 0; ch < nchunk; ++ch) {
+        int64_t m = ch * 32 + lane;
+        double base = 0.0;
+        double* dst = ew + ew_off[warp] + ch * L * 32 + lane;
+        for (int64_t l = 0; l < L; ++l) {
+            double r = 1.0;
+            if (m < M) {
+                double u = lu_r[m * L + l], v = lm_r[m * L + l];
+                if (u == u) {   // observed
+                    double d = v - u;
+                    if (d > LLR_CLAMP) { u = v - LLR_CLAMP; d = LLR_CLAMP; }
+                    else if (d < -LLR_CLAMP) { d = -LLR_CLAMP; }
+                    r = exp(d);
+                    base += u;
+                }
+            }
+            dst[l * 32] = r;
+        }
+        rb[rb_off[warp] + ch * 32 + lane] = base;
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------
+// shared: stage the per-group potentials of one instance for groups [l0, l0+n)
+// ---------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void fill_tile(SiteTile& st, int l0, int n, int lane, const double* __restrict__ na_g,
+                                          const double* __restrict__ nb_g, const double* __restrict__ invd_g, double a, double b,
+                                          double cabs) {
+    for (int j = lane; j < n; j += 32) {
+        int l = l0 + j;
+        double na = na_g[l], nb = nb_g[l];
+        double alpha = fma(b, nb, a * na);
+        double e = exp(-2.0 * fabs(alpha));
+        bool pos = alpha >= 0.0;
+        st.wm[j] = pos ? e : 1.0;      // φ(−1) relative to max(φ)
+        st.wp[j] = pos ? 1.0 : e;      // φ(+1) relative to max(φ)
+        st.na[j] = na;
+        st.nb[j] = nb;
+        double id = (l > 0) ? invd_g[l - 1] : 0.0;
+        st.invd[j] = id;
+        st.t[j] = exp(-2.0 * cabs * id);   // ψ(opposite)/ψ(aligned) for |β|
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------
+// E-step: ES = Σ_m ∇_ϕ log Zc_m(ϕ)   (≡ get_ess ∘ get_cond_exs_log)
+// ---------------------------------------------------------------------------------------------------
+// One forward sweep for the 32 reads of a chunk.  BPOS = (c ≥ 0).  (u,v) below are the source states that
+// enter x'=+1 with weight 1 and t respectively; for c<0 the roles of same/opposite swap.
+template <bool BPOS>
+__device__ __forceinline__ void estep_chunk(SiteTile& st, int L, int lane, const double* __restrict__ na_g,
+                                            const double* __restrict__ nb_g, const double* __restrict__ invd_g,
+                                            const double* __restrict__ ewc, double a, double b, double cabs, double out[3]) {
+    double fp = 0, fm = 0, gap = 0, gam = 0, gbp = 0, gbm = 0, gcp = 0, gcm = 0, sc = 1.0;
+    for (int l0 = 0; l0 < L; l0 += TILE) {
+        int n = min(TILE, L - l0);
+        __syncwarp();
+        fill_tile(st, l0, n, lane, na_g, nb_g, invd_g, a, b, cabs);
+        __syncwarp();
+        int j = 0;
+        if (l0 == 0) {
+            double r = ewc[lane];
+            double wp = st.wp[0] * r, wm = st.wm[0], na = st.na[0], nb = st.nb[0];
+            fp = wp; fm = wm;
+            gap = na * wp; gam = -na * wm;
+            gbp = nb * wp; gbm = -nb * wm;
+            gcp = 0.0; gcm = 0.0;
+            sc = cpn_inv_pow2_of(fp + fm);
+            j = 1;
+        }
+#pragma unroll 2
+        for (; j < n; ++j) {
+            double r = ewc[(size_t)(l0 + j) * 32 + lane];
+            double t = st.t[j], na = st.na[j], nb = st.nb[j];
+            double sinvd = BPOS ? st.invd[j] : -st.invd[j];
+            double phiP = (st.wp[j] * r) * sc, phiM = st.wm[j] * sc;
+            double u = BPOS ? fp : fm, v = BPOS ? fm : fp;
+            double Gp = fma(t, v, u), Gm = fma(t, u, v);
+            double ua = BPOS ? gap : gam, va = BPOS ? gam : gap;
+            double ub = BPOS ? gbp : gbm, vb = BPOS ? gbm : gbp;
+            double uc = BPOS ? gcp : gcm, vc = BPOS ? gcm : gcp;
+            double Hap = fma(t, va, ua), Ham = fma(t, ua, va);
+            double Hbp = fma(t, vb, ub), Hbm = fma(t, ub, vb);
+            double Hcp = fma(t, vc, uc), Hcm = fma(t, uc, vc);
+            double Dp = fma(2.0, u, -Gp), Dm = fma(2.0, v, -Gm);     // Σ_x (x x') ψ f, up to the sign in sinvd
+            gap = phiP * fma(na, Gp, Hap);
+            gam = phiM * fma(-na, Gm, Ham);
+            gbp = phiP * fma(nb, Gp, Hbp);
+            gbm = phiM * fma(-nb, Gm, Hbm);
+            gcp = phiP * fma(sinvd, Dp, Hcp);
+            gcm = phiM * fma(sinvd, Dm, Hcm);
+            fp = phiP * Gp;
+            fm = phiM * Gm;
+            sc = cpn_inv_pow2_of(fp + fm);
+        }
+    }
+    double inv = 1.0 / (fp + fm);
+    out[0] = (gap + gam) * inv;
+    out[1] = (gbp + gbm) * inv;
+    out[2] = (gcp + gcm) * inv;
+}
+
+__global__ void __launch_bounds__(E_WARPS * 32) k_estep(int n_items, const int* __restrict__ items, int n_init, RegionTables rt,
+                                                         const double* __restrict__ phi /*[3][NI]*/, int64_t NI,
+                                                         double* __restrict__ ES /*[3][NI]*/) {
+    __shared__ SiteTile tiles[E_WARPS];
+    int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    int item = blockIdx.x * E_WARPS + w;
+    if (item >= n_items) return;
+    int inst = items ? items[item] : item;
+    int64_t r = inst / n_init;
+    int64_t g0 = rt.grp_off[r];
+    int L = (int)(rt.grp_off[r + 1] - g0);
+    int64_t M = rt.read_off[r + 1] - rt.read_off[r];
+    double a = phi[inst], b = phi[NI + inst], c = phi[2 * NI + inst];
+    bool bpos = c >= 0.0;
+    double cabs = fabs(c);
+    const double* ew_r = rt.ew + rt.ew_off[r];
+    double acc0 = 0, acc1 = 0, acc2 = 0;
+    int nchunk = (int)((M + 31) >> 5);
+    for (int ch = 0; ch < nchunk; ++ch) {
+        double o[3];
+        const double* ewc = ew_r + (size_t)ch * L * 32;
+        if (bpos) estep_chunk<true>(tiles[w], L, lane, rt.na + g0, rt.nb + g0, rt.invd + g0, ewc, a, b, cabs, o);
+        else estep_chunk<false>(tiles[w], L, lane, rt.na + g0, rt.nb + g0, rt.invd + g0, ewc, a, b, cabs, o);
+        bool live = (int64_t)ch * 32 + lane < M;
+        acc0 += cpn_warp_sum(live ? o[0] : 0.0);
+        acc1 += cpn_warp_sum(live ? o[1] : 0.0);
+        acc2 += cpn_warp_sum(live ? o[2] : 0.0);
+    }
+    if (lane == 0) {
+        ES[inst] = acc0; ES[NI + inst] = acc1; ES[2 * NI + inst] = acc2;
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------
+// score: Q = (1/M) Σ_m log p(y_m; ϕ) = (1/M) Σ_m [base_m + log Zc_m,rel] − log Z_rel
+// (the |α|,|β| offsets of the relative potentials are identical in Zc and Z and cancel)
+// ---------------------------------------------------------------------------------------------------
+template <bool BPOS>
+__device__ __forceinline__ double logz_chunk(SiteTile& st, int L, int lane, const double* __restrict__ na_g,
+                                             const double* __restrict__ nb_g, const double* __restrict__ invd_g,
+                                             const double* __restrict__ ewc /*null → r = 1*/, double a, double b, double cabs) {
+    double fp = 0, fm = 0, sc = 1.0;
+    int esum = 0, e;
+    for (int l0 = 0; l0 < L; l0 += TILE) {
+        int n = min(TILE, L - l0);
+        __syncwarp();
+        fill_tile(st, l0, n, lane, na_g, nb_g, invd_g, a, b, cabs);
+        __syncwarp();
+        int j = 0;
+        if (l0 == 0) {
+            double r = ewc ? ewc[lane] : 1.0;
+            fp = st.wp[0] * r; fm = st.wm[0];
+            sc = cpn_inv_pow2_of(fp + fm, &e); esum += e;
+            j = 1;
+        }
+        for (; j < n; ++j) {
+            double r = ewc ? ewc[(size_t)(l0 + j) * 32 + lane] : 1.0;
+            double t = st.t[j];
+            double phiP = (st.wp[j] * r) * sc, phiM = st.wm[j] * sc;
+            double u = BPOS ? fp : fm, v = BPOS ? fm : fp;
+            fp = phiP * fma(t, v, u);
+            fm = phiM * fma(t, u, v);
+            sc = cpn_inv_pow2_of(fp + fm, &e); esum += e;
+        }
+    }
+    return log((fp + fm) * sc) + (double)esum * 0.6931471805599453;
+}
+
+// item → (instance); computes Q[inst] for instances whose flag[inst] == want (or all if flag == null)
+__global__ void __launch_bounds__(E_WARPS * 32) k_score(int n_items, const int* __restrict__ items, int n_init, RegionTables rt,
+                                                         const double* __restrict__ phi, int64_t NI, const int* __restrict__ flag,
+                                                         int want, double* __restrict__ Q) {
+    __shared__ SiteTile tiles[E_WARPS];
+    int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    int item = blockIdx.x * E_WARPS + w;
+    if (item >= n_items) return;
+    int inst = items ? items[item] : item;
+    if (flag && flag[inst] != want) {
+        if (lane == 0) Q[inst] = -cpn_inf();
+        return;
+    }
+    int64_t r = inst / n_init;
+    int64_t g0 = rt.grp_off[r];
+    int L = (int)(rt.grp_off[r + 1] - g0);
+    int64_t M = rt.read_off[r + 1] - rt.read_off[r];
+    double a = phi[inst], b = phi[NI + inst], c = phi[2 * NI + inst];
+    bool bpos = c >= 0.0;
+    double cabs = fabs(c);
+    const double* ew_r = rt.ew + rt.ew_off[r];
+    const double* rb_r = rt.rb + rt.rb_off[r];
+    int nchunk = (int)((M + 31) >> 5);
+    double acc = 0.0;
+    for (int ch = 0; ch < nchunk; ++ch) {
+        const double* ewc = ew_r + (size_t)ch * L * 32;
+        double lz = bpos ? logz_chunk<true>(tiles[w], L, lane, rt.na + g0, rt.nb + g0, rt.invd + g0, ewc, a, b, cabs)
+                         : logz_chunk<false>(tiles[w], L, lane, rt.na + g0, rt.nb + g0, rt.invd + g0, ewc, a, b, cabs);
+        bool live = (int64_t)ch * 32 + lane < M;
+        acc += cpn_warp_sum(live ? rb_r[ch * 32 + lane] + lz : 0.0);
+    }
+    // marginal chain (no data): every lane computes the same value
+    double lz0 = bpos ? logz_chunk<true>(tiles[w], L, lane, rt.na + g0, rt.nb + g0, rt.invd + g0, nullptr, a, b, cabs)
+                      : logz_chunk<false>(tiles[w], L, lane, rt.na + g0, rt.nb + g0, rt.invd + g0, nullptr, a, b, cabs);
+    if (lane == 0) Q[inst] = acc / (double)M - lz0;
+}
+
+// ---------------------------------------------------------------------------------------------------
+// M-step
+// ---------------------------------------------------------------------------------------------------
+// log Z_rel(ϕ) (value only) for the FD mode: serial sweep on one lane.
+__device__ double logz_serial(const double* __restrict__ na_g, const double* __restrict__ nb_g, const double* __restrict__ invd_g,
+                              int L, double a, double b, double c) {
+    // offsets Σ|α_l| + Σ|β_l| are NOT constant in ϕ here, so the FD mode needs the full log Z.
+    bool bpos = c >= 0.0;
+    double cabs = fabs(c);
+    double fp, fm, sc, off = 0.0;
+    int esum = 0, e;
+    {
+        double alpha = fma(b, nb_g[0], a * na_g[0]);
+        double ex = exp(-2.0 * fabs(alpha));
+        off += fabs(alpha);
+        fp = alpha >= 0 ? 1.0 : ex; fm = alpha >= 0 ? ex : 1.0;
+        sc = cpn_inv_pow2_of(fp + fm, &e); esum += e;
+    }
+    for (int l = 1; l < L; ++l) {
+        double alpha = fma(b, nb_g[l], a * na_g[l]);
+        double ex = exp(-2.0 * fabs(alpha));
+        double beta = cabs * invd_g[l - 1];
+        double t = exp(-2.0 * beta);
+        off += fabs(alpha) + beta;
+        double wp = (alpha >= 0 ? 1.0 : ex) * sc, wm = (alpha >= 0 ? ex : 1.0) * sc;
+        double u = bpos ? fp : fm, v = bpos ? fm : fp;
+        fp = wp * fma(t, v, u);
+        fm = wm * fma(t, u, v);
+        sc = cpn_inv_pow2_of(fp + fm, &e); esum += e;
+    }
+    return log((fp + fm) * sc) + (double)esum * 0.6931471805599453 + off;
+}
+
+// Gradient g[3] and Hessian H (aa,ab,ac,bb,bc,cc) of log Z(ϕ) by one forward sweep with first- and
+// second-order tangents.  c<0 is mapped onto c>0 by the gauge x_l → (−1)^l x_l (flips the sign of α_l,
+// N_l, N_lρ_l on odd sites and of 1/d_l everywhere), so the recursion always has ψ(aligned)=1, ψ(opposite)=t.
+__device__ void eval_grad_hess(const double* __restrict__ na_g, const double* __restrict__ nb_g, const double* __restrict__ invd_g,
+                               int L, double a, double b, double c, double g[3], double H[6]) {
+    const bool neg = c < 0.0;
+    const double cabs = fabs(c);
+    double f[2], ga[2], gb[2], gc[2], haa[2], hab[2], hac[2], hbb[2], hbc[2], hcc[2];
+    double sc;
+    {
+        double na = na_g[0], nb = nb_g[0];
+        double alpha = fma(b, nb, a * na);
+        double ex = exp(-2.0 * fabs(alpha));
+        double w[2];
+        w[0] = alpha >= 0 ? ex : 1.0; w[1] = alpha >= 0 ? 1.0 : ex;
+#pragma unroll
+        for (int x = 0; x < 2; ++x) {
+            double sg = x ? 1.0 : -1.0;
+            f[x] = w[x];
+            ga[x] = sg * na * w[x]; gb[x] = sg * nb * w[x]; gc[x] = 0.0;
+            haa[x] = na * na * w[x]; hab[x] = na * nb * w[x]; hbb[x] = nb * nb * w[x];
+            hac[x] = 0.0; hbc[x] = 0.0; hcc[x] = 0.0;
+        }
+        sc = cpn_inv_pow2_of(f[0] + f[1]);
+    }
+    for (int l = 1; l < L; ++l) {
+        double flip = (neg && (l & 1)) ? -1.0 : 1.0;
+        double na = flip * na_g[l], nb = flip * nb_g[l];
+        double id = invd_g[l - 1];
+        double invd = neg ? -id : id;
+        double alpha = fma(b, nb, a * na);
+        double ex = exp(-2.0 * fabs(alpha));
+        double t = exp(-2.0 * cabs * id);
+        double w[2];
+        w[0] = (alpha >= 0 ? ex : 1.0) * sc; w[1] = (alpha >= 0 ? 1.0 : ex) * sc;
+        double nf[2], nga[2], ngb[2], ngc[2], nhaa[2], nhab[2], nhac[2], nhbb[2], nhbc[2], nhcc[2];
+        const double invd2 = invd * invd, invd_2 = 2.0 * invd, nanb = na * nb, na2 = na * na, nb2 = nb * nb;
+#pragma unroll
+        for (int x = 0; x < 2; ++x) {
+            const int s = x, o = 1 - x;
+            const double sna = x ? na : -na, snb = x ? nb : -nb;
+            double S0 = fma(t, f[o], f[s]);
+            double Sa = fma(t, ga[o], ga[s]);
+            double Sb = fma(t, gb[o], gb[s]);
+            double gcl = fma(t, gc[o], gc[s]);
+            double D0 = fma(2.0, f[s], -S0);
+            double Sc = fma(invd, D0, gcl);
+            double Saa = fma(t, haa[o], haa[s]);
+            double Sab = fma(t, hab[o], hab[s]);
+            double Sbb = fma(t, hbb[o], hbb[s]);
+            double Sac = fma(invd, fma(2.0, ga[s], -Sa), fma(t, hac[o], hac[s]));
+            double Sbc = fma(invd, fma(2.0, gb[s], -Sb), fma(t, hbc[o], hbc[s]));
+            double Scc = fma(invd_2, fma(2.0, gc[s], -gcl), fma(invd2, S0, fma(t, hcc[o], hcc[s])));
+            double ph = w[x];
+            nf[x] = ph * S0;
+            nga[x] = ph * fma(sna, S0, Sa);
+            ngb[x] = ph * fma(snb, S0, Sb);
+            ngc[x] = ph * Sc;
+            nhaa[x] = ph * fma(na2, S0, fma(2.0 * sna, Sa, Saa));
+            nhab[x] = ph * fma(nanb, S0, fma(sna, Sb, fma(snb, Sa, Sab)));
+            nhbb[x] = ph * fma(nb2, S0, fma(2.0 * snb, Sb, Sbb));
+            nhac[x] = ph * fma(sna, Sc, Sac);
+            nhbc[x] = ph * fma(snb, Sc, Sbc);
+            nhcc[x] = ph * Scc;
+        }
+#pragma unroll
+        for (int x = 0; x < 2; ++x) {
+            f[x] = nf[x]; ga[x] = nga[x]; gb[x] = ngb[x]; gc[x] = ngc[x];
+            haa[x] = nhaa[x]; hab[x] = nhab[x]; hac[x] = nhac[x]; hbb[x] = nhbb[x]; hbc[x] = nhbc[x]; hcc[x] = nhcc[x];
+        }
+        sc = cpn_inv_pow2_of(f[0] + f[1]);
+    }
+    double inv = 1.0 / (f[0] + f[1]);
+    g[0] = (ga[0] + ga[1]) * inv; g[1] = (gb[0] + gb[1]) * inv; g[2] = (gc[0] + gc[1]) * inv;
+    H[0] = fma(-g[0], g[0], (haa[0] + haa[1]) * inv);
+    H[1] = fma(-g[0], g[1], (hab[0] + hab[1]) * inv);
+    H[2] = fma(-g[0], g[2], (hac[0] + hac[1]) * inv);
+    H[3] = fma(-g[1], g[1], (hbb[0] + hbb[1]) * inv);
+    H[4] = fma(-g[1], g[2], (hbc[0] + hbc[1]) * inv);
+    H[5] = fma(-g[2], g[2], (hcc[0] + hcc[1]) * inv);
+}
+
+struct MProblem {
+    const double *na, *nb, *invd;
+    int L;
+    double t0, t1, t2;     // ES/M
+    int mode;
+    int evals;             // log Z-equivalent evaluations (FD) / derivative sweeps (analytic)
+};
+
+// residual U(ϕ) = ∇logZ(ϕ) − ES/M  (em_algorithm.jl:152-157); FD mode: Calculus.gradient central rule.
+__device__ void residual_fd(MProblem& pb, double* x, double* U) {
+    for (int i = 0; i < 3; ++i) {
+        double epsilon = CBRT_EPS * fmax(1.0, fabs(x[i]));
+        double oldx = x[i];
+        x[i] = oldx + epsilon;
+        double fp = logz_serial(pb.na, pb.nb, pb.invd, pb.L, x[0], x[1], x[2]);
+        x[i] = oldx - epsilon;
+        double fm = logz_serial(pb.na, pb.nb, pb.invd, pb.L, x[0], x[1], x[2]);
+        x[i] = oldx;
+        U[i] = (fp - fm) / (epsilon + epsilon);
+    }
+    pb.evals += 6;
+    U[0] -= pb.t0; U[1] -= pb.t1; U[2] -= pb.t2;
+}
+// FiniteDiff central Jacobian of the residual: ε_k = max(cbrt(eps)|x_k|, cbrt(eps))
+__device__ void jacobian_fd(MProblem& pb, double* x, double J[3][3]) {
+    double x1[3] = {x[0], x[1], x[2]}, f1[3], f0[3];
+    for (int k = 0; k < 3; ++k) {
+        double x_save = x[k];
+        double epsilon = fmax(CBRT_EPS * fabs(x_save), CBRT_EPS);
+        x1[k] = x_save + epsilon; residual_fd(pb, x1, f1);
+        x[k] = x_save - epsilon;  residual_fd(pb, x, f0);
+        for (int i = 0; i < 3; ++i) J[i][k] = (f1[i] - f0[i]) / (2 * epsilon);
+        x1[k] = x_save; x[k] = x_save;
+    }
+}
+__device__ void value_jacobian(MProblem& pb, double* x, double* F, double J[3][3]) {
+    if (pb.mode == CPN_MSTEP_ANALYTIC) {
+        double g[3], H[6];
+        eval_grad_hess(pb.na, pb.nb, pb.invd, pb.L, x[0], x[1], x[2], g, H);
+        pb.evals += 1;
+        F[0] = g[0] - pb.t0; F[1] = g[1] - pb.t1; F[2] = g[2] - pb.t2;
+        J[0][0] = H[0]; J[0][1] = H[1]; J[0][2] = H[2];
+        J[1][0] = H[1]; J[1][1] = H[3]; J[1][2] = H[4];
+        J[2][0] = H[2]; J[2][1] = H[4]; J[2][2] = H[5];
+    } else {
+        residual_fd(pb, x, F);
+        jacobian_fd(pb, x, J);
+    }
+}
+
+__device__ __forceinline__ double wdot3(const double* wx, const double* x, const double* wy, const double* y) {
+    double out = 0.0;
+#pragma unroll
+    for (int i = 0; i < 3; ++i) out += wx[i] * x[i] * wy[i] * y[i];
+    return out;
+}
+__device__ __forceinline__ double wnorm3(const double* w, const double* x) { return sqrt(wdot3(w, x, w, x)); }
+__device__ __forceinline__ double sumabs2_3(const double* x) { return x[0] * x[0] + x[1] * x[1] + x[2] * x[2]; }
+__device__ __forceinline__ double norminf3(const double* x) { return fmax(fabs(x[0]), fmax(fabs(x[1]), fabs(x[2]))); }
+__device__ __forceinline__ bool anynan3(const double* x) { return x[0] != x[0] || x[1] != x[1] || x[2] != x[2]; }
+__device__ __forceinline__ bool allfinite3(const double* x) { return isfinite(x[0]) && isfinite(x[1]) && isfinite(x[2]); }
+
+// J \ r, LU with partial pivoting; false on an exactly singular pivot.
+__device__ bool lu_solve3(const double Jin[3][3], const double* r, double* out) {
+    double A[3][3], b[3] = {r[0], r[1], r[2]};
+#pragma unroll
+    for (int i = 0; i < 3; ++i)
+#pragma unroll
+        for (int j = 0; j < 3; ++j) A[i][j] = Jin[i][j];
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+        int piv = k; double best = fabs(A[k][k]);
+#pragma unroll
+        for (int i = k + 1; i < 3; ++i) if (fabs(A[i][k]) > best) { best = fabs(A[i][k]); piv = i; }
+        if (!(best > 0.0) && !(best != best)) return false;
+#pragma unroll
+        for (int i = k + 1; i < 3; ++i) {
+            if (piv == i) {
+#pragma unroll
+                for (int j = 0; j < 3; ++j) { double tmp = A[k][j]; A[k][j] = A[i][j]; A[i][j] = tmp; }
+                double tb = b[k]; b[k] = b[i]; b[i] = tb;
+            }
+        }
+#pragma unroll
+        for (int i = k + 1; i < 3; ++i) {
+            double m = A[i][k] / A[k][k];
+#pragma unroll
+            for (int j = k + 1; j < 3; ++j) A[i][j] -= m * A[k][j];
+            b[i] -= m * b[k];
+        }
+    }
+    out[2] = b[2] / A[2][2];
+    out[1] = (b[1] - A[1][2] * out[2]) / A[1][1];
+    out[0] = (b[0] - A[0][1] * out[1] - A[0][2] * out[2]) / A[0][0];
+    return true;
+}
+__device__ __forceinline__ void matvec3(const double J[3][3], const double* v, double* out) {
+#pragma unroll
+    for (int i = 0; i < 3; ++i) out[i] = J[i][0] * v[0] + J[i][1] * v[1] + J[i][2] * v[2];
+}
+// NLsolve dogleg! (trust_region.jl).  An exactly singular J (measure zero) takes the Cauchy branch.
+__device__ void dogleg3(double* p, const double* r, const double* d, const double J[3][3], double delta) {
+    double p_i[3], p_c[3];
+    bool ok = lu_solve3(J, r, p_i);
+    if (ok) {
+#pragma unroll
+        for (int i = 0; i < 3; ++i) p_i[i] = -p_i[i];
+        if (wnorm3(d, p_i) <= delta) { p[0] = p_i[0]; p[1] = p_i[1]; p[2] = p_i[2]; return; }
+    }
+    double g[3], Jg[3];
+#pragma unroll
+    for (int j = 0; j < 3; ++j) g[j] = (J[0][j] * r[0] + J[1][j] * r[1] + J[2][j] * r[2]) / (d[j] * d[j]);
+    matvec3(J, g, Jg);
+    double wg = wnorm3(d, g);
+    double coef = -(wg * wg) / sumabs2_3(Jg);
+#pragma unroll
+    for (int i = 0; i < 3; ++i) p_c[i] = coef * g[i];
+    if (!ok || wnorm3(d, p_c) >= delta) {
+        double s = -delta / wnorm3(d, g);
+#pragma unroll
+        for (int i = 0; i < 3; ++i) p[i] = g[i] * s;
+    } else {
+        double p_diff[3];
+#pragma unroll
+        for (int i = 0; i < 3; ++i) p_diff[i] = p_i[i] - p_c[i];
+        double b = 2 * wdot3(d, p_c, d, p_diff);
+        double wpd = wnorm3(d, p_diff), a = wpd * wpd, wpc = wnorm3(d, p_c);
+        double tau = (-b + sqrt(b * b - 4 * a * (wpc * wpc - delta * delta))) / (2 * a);
+#pragma unroll
+        for (int i = 0; i < 3; ++i) p[i] = p_c[i] + tau * p_diff[i];
+    }
+}
+// NLsolve.nlsolve(f!, x0; iterations=20, ftol=1e-3): trust region, autoscale, factor 1, xtol 0.
+// Returns converged(sol); *threw mirrors the IsFiniteException on a non-finite initial residual.
+__device__ bool trust_region_solve(MProblem& pb, const double* x0, double* x, int* n_iters, bool* threw) {
+    const double ftol = 1e-3, eta = 1e-4;
+    const int iterations = 20;
+    double r[3], J[3][3], fval[3], d[3], p[3], xold[3];
+    *threw = false;
+    x[0] = x0[0]; x[1] = x0[1]; x[2] = x0[2];
+    value_jacobian(pb, x, fval, J);
+    r[0] = fval[0]; r[1] = fval[1]; r[2] = fval[2];
+    *n_iters = 0;
+    if (!allfinite3(r)) { *threw = true; return false; }
+    bool x_conv = false, f_conv = norminf3(fval) <= ftol;
+    bool stopped = anynan3(x) || anynan3(fval);
+    bool conv = f_conv;
+    if (conv) return true;
+#pragma unroll
+    for (int j = 0; j < 3; ++j) {
+        d[j] = sqrt(J[0][j] * J[0][j] + J[1][j] * J[1][j] + J[2][j] * J[2][j]);
+        if (d[j] == 0.0) d[j] = 1.0;
+    }
+    double delta = wnorm3(d, x);
+    if (delta == 0.0) delta = 1.0;
+    int it = 0;
+    while (!stopped && !conv && it < iterations) {
+        ++it;
+        dogleg3(p, r, d, J, delta);
+#pragma unroll
+        for (int i = 0; i < 3; ++i) { xold[i] = x[i]; x[i] += p[i]; }
+        double Jn[3][3];
+        if (pb.mode == CPN_MSTEP_ANALYTIC) value_jacobian(pb, x, fval, Jn);   // F and J from the same sweep
+        else residual_fd(pb, x, fval);
+        double rp[3];
+        matvec3(J, p, rp);
+#pragma unroll
+        for (int i = 0; i < 3; ++i) rp[i] += r[i];
+        double rho = (sumabs2_3(r) - sumabs2_3(fval)) / (sumabs2_3(r) - sumabs2_3(rp));
+        if (rho > eta) {
+            r[0] = fval[0]; r[1] = fval[1]; r[2] = fval[2];
+            if (pb.mode == CPN_MSTEP_ANALYTIC) {
+#pragma unroll
+                for (int i = 0; i < 3; ++i)
+#pragma unroll
+                    for (int j = 0; j < 3; ++j) J[i][j] = Jn[i][j];
+            } else {
+                double Fd[3];
+                value_jacobian(pb, x, Fd, J);
+            }
+#pragma unroll
+            for (int j = 0; j < 3; ++j) {
+                double nj = sqrt(J[0][j] * J[0][j] + J[1][j] * J[1][j] + J[2][j] * J[2][j]);
+                d[j] = fmax(0.1 * d[j], nj);
+            }
+            double dx[3] = {x[0] - xold[0], x[1] - xold[1], x[2] - xold[2]};
+            x_conv = norminf3(dx) <= 0.0;
+            f_conv = norminf3(r) <= ftol;
+            conv = x_conv || f_conv;
+        } else {
+#pragma unroll
+            for (int i = 0; i < 3; ++i) x[i] -= p[i];
+            x_conv = false; conv = false;
+        }
+        if (rho < 0.1) delta = delta / 2;
+        else if (rho >= 0.9) delta = 2 * wnorm3(d, p);
+        else if (rho >= 0.5) delta = fmax(delta, 2 * wnorm3(d, p));
+        stopped = anynan3(x) || anynan3(fval);
+    }
+    *n_iters = it;
+    return x_conv || f_conv;
+}
+
+struct EmState {
+    double* phi;        // [3][NI] current iterate
+    double* ES;         // [3][NI]
+    int* iter;          // [NI] the reference's counter i (starts at 1)
+    int* status;        // [NI] 0 active, 1 converged, 2 not converged
+    int* cnt_em;        // [NI] EM iterations done
+    int* cnt_sol;       // [NI] solver iterations
+    int* cnt_eval;      // [NI] log Z evaluations / derivative sweeps
+    int64_t NI;
+};
+
+// One em_iter M-step + the em_inst bookkeeping (em_algorithm.jl:152-183, :317-341) for every active
+// instance; survivors are appended (block-ordered) to next_items.
+__global__ void __launch_bounds__(M_THREADS) k_mstep(int n_items, const int* __restrict__ items, int n_init, RegionTables rt,
+                                                      EmState st, int max_em_iters, double amax, double bmax, double cmax, int mode,
+                                                      int* __restrict__ next_items, int* __restrict__ n_next) {
+    int item = blockIdx.x * M_THREADS + threadIdx.x;
+    bool survive = false;
+    int inst = -1;
+    if (item < n_items) {
+        inst = items ? items[item] : item;
+        int64_t r = inst / n_init;
+        int64_t g0 = rt.grp_off[r];
+        MProblem pb;
+        pb.na = rt.na + g0; pb.nb = rt.nb + g0; pb.invd = rt.invd + g0;
+        pb.L = (int)(rt.grp_off[r + 1] - g0);
+        double Mr = (double)(rt.read_off[r + 1] - rt.read_off[r]);
+        int64_t NI = st.NI;
+        pb.t0 = st.ES[inst] / Mr; pb.t1 = st.ES[NI + inst] / Mr; pb.t2 = st.ES[2 * NI + inst] / Mr;
+        pb.mode = mode; pb.evals = 0;
+        double x0[3] = {st.phi[inst], st.phi[NI + inst], st.phi[2 * NI + inst]}, sol[3];
+        int nit; bool threw;
+        bool conv = trust_region_solve(pb, x0, sol, &nit, &threw);
+        double nx[3];
+        if (threw || !conv) { nx[0] = x0[0]; nx[1] = x0[1]; nx[2] = x0[2]; }
+        else {
+            nx[0] = fmax(-amax, fmin(sol[0], amax));
+            nx[1] = fmax(-bmax, fmin(sol[1], bmax));
+            nx[2] = fmax(-cmax, fmin(sol[2], cmax));
+        }
+        double d0 = x0[0] - nx[0], d1 = x0[1] - nx[1], d2 = x0[2] - nx[2];
+        bool cv = sqrt(d0 * d0 + d1 * d1 + d2 * d2) <= 3.0e-2;          // conv_check, em_algorithm.jl:18-23
+        int i = st.iter[inst];
+        bool hit = i >= max_em_iters;
+        i += 1;
+        st.phi[inst] = nx[0]; st.phi[NI + inst] = nx[1]; st.phi[2 * NI + inst] = nx[2];
+        st.iter[inst] = i;
+        st.cnt_em[inst] += 1; st.cnt_sol[inst] += nit; st.cnt_eval[inst] += pb.evals;
+        if (cv || hit) st.status[inst] = (cv && i > 2) ? 1 : 2;
+        else survive = true;
+    }
+    // ordered compaction inside the block, one atomic per block
+    __shared__ int warp_cnt[M_THREADS / 32];
+    __shared__ int base;
+    unsigned bal = __ballot_sync(0xffffffffu, survive);
+    int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    if (lane == 0) warp_cnt[w] = __popc(bal);
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        int tot = 0;
+        for (int k = 0; k < M_THREADS / 32; ++k) { int c = warp_cnt[k]; warp_cnt[k] = tot; tot += c; }
+        base = tot ? atomicAdd(n_next, tot) : 0;
+    }
+    __syncthreads();
+    if (survive) next_items[base + warp_cnt[w] + __popc(bal & ((1u << lane) - 1))] = inst;
+}
+
+// Single solve for the test hook cpn_mstep_batch.
+__global__ void k_mstep_once(int64_t R, RegionTables rt, const int64_t* __restrict__ n_reads, const double* __restrict__ ES,
+                             const double* __restrict__ phi_init, int mode, double* __restrict__ sol_out, int* __restrict__ conv_out,
+                             int64_t* __restrict__ counters) {
+    int64_t r = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (r >= R) return;
+    int64_t g0 = rt.grp_off[r];
+    MProblem pb;
+    pb.na = rt.na + g0; pb.nb = rt.nb + g0; pb.invd = rt.invd + g0;
+    pb.L = (int)(rt.grp_off[r + 1] - g0);
+    double Mr = (double)n_reads[r];
+    pb.t0 = ES[3 * r] / Mr; pb.t1 = ES[3 * r + 1] / Mr; pb.t2 = ES[3 * r + 2] / Mr;
+    pb.mode = mode; pb.evals = 0;
+    double x0[3] = {phi_init[3 * r], phi_init[3 * r + 1], phi_init[3 * r + 2]}, sol[3];
+    int nit; bool threw;
+    bool conv = trust_region_solve(pb, x0, sol, &nit, &threw);
+    sol_out[3 * r] = sol[0]; sol_out[3 * r + 1] = sol[1]; sol_out[3 * r + 2] = sol[2];
+    conv_out[r] = (conv && !threw) ? 1 : 0;
+    if (counters) { counters[2 * r] = nit; counters[2 * r + 1] = pb.evals; }
+}
+
+__global__ void k_init_state(int64_t NI, int n_init, const double* __restrict__ phi0 /*[NI][3]*/, EmState st, int* __restrict__ items,
+                             const int* __restrict__ order /*[R] region order or null*/) {
+    int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (i >= NI) return;
+    st.phi[i] = phi0[3 * i]; st.phi[st.NI + i] = phi0[3 * i + 1]; st.phi[2 * st.NI + i] = phi0[3 * i + 2];
+    st.iter[i] = 1; st.status[i] = 0; st.cnt_em[i] = 0; st.cnt_sol[i] = 0; st.cnt_eval[i] = 0;
+    if (order) {
+        int64_t slot = i / n_init, s = i % n_init;
+        items[i] = (int)((int64_t)order[slot] * n_init + s);
+    } else items[i] = (int)i;
+}
+
+// pick_ϕ (em_algorithm.jl:35-53): first start with the strictly largest Q; ϕ̂ = [] (NaN here) if all −Inf (:385)
+__global__ void k_pick(int64_t R, int n_init, EmState st, const double* __restrict__ Qs, double* __restrict__ phi_hat,
+                       double* __restrict__ Q, int* __restrict__ status, int64_t* __restrict__ counters,
+                       double* __restrict__ phi_starts, double* __restrict__ Q_starts) {
+    int64_t r = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (r >= R) return;
+    double best = -cpn_inf();
+    int bi = -1;
+    int64_t ce = 0, cs = 0, cv = 0;
+    for (int s = 0; s < n_init; ++s) {
+        int64_t i = r * n_init + s;
+        double q = Qs[i];
+        if (q > best) { best = q; bi = s; }
+        ce += st.cnt_em[i]; cs += st.cnt_sol[i]; cv += st.cnt_eval[i];
+        if (phi_starts) {
+            phi_starts[3 * i] = st.phi[i]; phi_starts[3 * i + 1] = st.phi[st.NI + i]; phi_starts[3 * i + 2] = st.phi[2 * st.NI + i];
+        }
+        if (Q_starts) Q_starts[i] = q;
+    }
+    if (bi >= 0) {
+        int64_t i = r * n_init + bi;
+        phi_hat[3 * r] = st.phi[i]; phi_hat[3 * r + 1] = st.phi[st.NI + i]; phi_hat[3 * r + 2] = st.phi[2 * st.NI + i];
+    } else {
+        phi_hat[3 * r] = phi_hat[3 * r + 1] = phi_hat[3 * r + 2] = cpn_nan();
+    }
+    Q[r] = best;
+    if (status) status[r] = bi;
+    if (counters) { counters[4 * r] = ce; counters[4 * r + 1] = cs; counters[4 * r + 2] = cv; counters[4 * r + 3] = ce; }
+}
+
+__global__ void k_pack_phi(int64_t R, const double* __restrict__ phi /*[R][3]*/, double* __restrict__ out /*[3][R]*/) {
+    int64_t r = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (r >= R) return;
+    out[r] = phi[3 * r]; out[R + r] = phi[3 * r + 1]; out[2 * R + r] = phi[3 * r + 2];
+}
+__global__ void k_unpack3(int64_t R, const double* __restrict__ in /*[3][R]*/, double* __restrict__ out /*[R][3]*/) {
+    int64_t r = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (r >= R) return;
+    out[3 * r] = in[r]; out[3 * r + 1] = in[R + r]; out[3 * r + 2] = in[2 * R + r];
+}
+
+// ---------------------------------------------------------------------------------------------------
+// host side
+// ---------------------------------------------------------------------------------------------------
+struct PackedRegions {
+    DevIn<int64_t> grp_off, read_off;
+    DevIn<double> Nl, rho, dl, lu, lm;
+    DevBuf<int64_t> obs_off, ew_off, rb_off;
+    DevBuf<double> na, nb, invd, ew, rb;
+    std::vector<int64_t> h_grp_off, h_read_off;
+    int64_t R = 0, sumL = 0, n_obs = 0;
+    RegionTables rt{};
+};
+
+inline unsigned blocks_for(int64_t n, int per_block) { return (unsigned)((n + per_block - 1) / per_block); }
+
+// Uploads (or borrows) the CSR inputs and builds the per-group and per-read device tables.
+int pack_regions(cpn_ctx* ctx, PackedRegions& pk, bool on_device, bool with_reads, int64_t R, const int64_t* grp_off,
+                 const double* Nl, const double* rho_l, const double* d_l, const int64_t* read_off, const double* lu, const double* lm) {
+    cudaStream_t s = ctx->stream;
+    pk.R = R;
+    pk.h_grp_off.resize(R + 1);
+    pk.h_read_off.assign(R + 1, 0);
+    if (on_device) {
+        CPN_CUDA(ctx, cudaMemcpyAsync(pk.h_grp_off.data(), grp_off, (R + 1) * sizeof(int64_t), cudaMemcpyDeviceToHost, s));
+        if (with_reads) CPN_CUDA(ctx, cudaMemcpyAsync(pk.h_read_off.data(), read_off, (R + 1) * sizeof(int64_t), cudaMemcpyDeviceToHost, s));
+        CPN_CUDA(ctx, cudaStreamSynchronize(s));
+    } else {
+        std::memcpy(pk.h_grp_off.data(), grp_off, (R + 1) * sizeof(int64_t));
+        if (with_reads) std::memcpy(pk.h_read_off.data(), read_off, (R + 1) * sizeof(int64_t));
+    }
+    CPN_ARG(ctx, pk.h_grp_off[0] == 0, "grp_off[0] must be 0");
+    std::vector<int64_t> h_obs(R + 1), h_ew(R + 1), h_rb(R + 1);
+    h_obs[0] = h_ew[0] = h_rb[0] = 0;
+    for (int64_t r = 0; r < R; ++r) {
+        int64_t L = pk.h_grp_off[r + 1] - pk.h_grp_off[r];
+        int64_t M = pk.h_read_off[r + 1] - pk.h_read_off[r];
+        CPN_ARG(ctx, L >= 2, "every region needs L >= 2 CpG groups (nanopore.jl:326)");
+        CPN_ARG(ctx, !with_reads || M >= 1, "every region needs at least one read");
+        int64_t nch = (M + 31) / 32;
+        h_obs[r + 1] = h_obs[r] + M * L;
+        h_ew[r + 1] = h_ew[r] + nch * L * 32;
+        h_rb[r + 1] = h_rb[r] + nch * 32;
+    }
+    pk.sumL = pk.h_grp_off[R];
+    pk.n_obs = h_obs[R];
+    CPN_CUDA(ctx, pk.grp_off.bind(grp_off, R + 1, on_device, s));
+    CPN_CUDA(ctx, pk.Nl.bind(Nl, pk.sumL, on_device, s));
+    CPN_CUDA(ctx, pk.rho.bind(rho_l, pk.sumL, on_device, s));
+    CPN_CUDA(ctx, pk.dl.bind(d_l, pk.sumL - R, on_device, s));
+    CPN_CUDA(ctx, pk.na.alloc(pk.sumL, s));
+    CPN_CUDA(ctx, pk.nb.alloc(pk.sumL, s));
+    CPN_CUDA(ctx, pk.invd.alloc(pk.sumL, s));
+    { KTimer kt(ctx, CPN_K_PREP);
+      k_prep_sites<<<blocks_for(R * 32, 256), 256, 0, s>>>(R, pk.grp_off.p, pk.Nl.p, pk.rho.p, pk.dl.p, pk.na.p, pk.nb.p, pk.invd.p); }
+    pk.rt.grp_off = pk.grp_off.p; pk.rt.na = pk.na.p; pk.rt.nb = pk.nb.p; pk.rt.invd = pk.invd.p;
+    if (with_reads) {
+        CPN_CUDA(ctx, pk.read_off.bind(read_off, R + 1, on_device, s));
+        CPN_CUDA(ctx, pk.lu.bind(lu, pk.n_obs, on_device, s));
+        CPN_CUDA(ctx, pk.lm.bind(lm, pk.n_obs, on_device, s));
+        CPN_CUDA(ctx, pk.obs_off.upload(h_obs.data(), R + 1, s));
+        CPN_CUDA(ctx, pk.ew_off.upload(h_ew.data(), R + 1, s));
+        CPN_CUDA(ctx, pk.rb_off.upload(h_rb.data(), R + 1, s));
+        CPN_CUDA(ctx, pk.ew.alloc(h_ew[R], s));
+        CPN_CUDA(ctx, pk.rb.alloc(h_rb[R], s));
+        { KTimer kt(ctx, CPN_K_PREP);
+          k_prep_emis<<<blocks_for(R * 32, 128), 128, 0, s>>>(R, pk.grp_off.p, pk.read_off.p, pk.obs_off.p, pk.lu.p, pk.lm.p, pk.ew_off.p,
+                                                              pk.rb_off.p, pk.ew.p, pk.rb.p); }
+        CPN_CUDA(ctx, cudaStreamSynchronize(s));   // h_* staging vectors go out of scope
+        pk.rt.read_off = pk.read_off.p; pk.rt.ew_off = pk.ew_off.p; pk.rt.rb_off = pk.rb_off.p; pk.rt.ew = pk.ew.p; pk.rt.rb = pk.rb.p;
+    }
+    CPN_CUDA(ctx, cudaGetLastError());
+    return CPN_OK;
+}
+
+// Optional second stage of cpn_analyze_batch: summaries of the fitted per-CpG chains.
+struct SummaryArgs {
+    const int64_t *cpg_off, *sub_off, *sub_p, *sub_q;
+    const double *rho_n, *d_n;
+    double *logZ, *ex, *exx, *log_g, *e_log_g1, *e_log_g2, *mml, *nme;
+};
+
+int fit_impl(cpn_ctx* ctx, bool on_device, int64_t R, const int64_t* grp_off, const double* Nl, const double* rho_l, const double* d_l,
+             const int64_t* read_off, const double* lu, const double* lm, const double* phi0, int32_t n_init, int32_t max_em_iters,
+             double amax, double bmax, double cmax, int32_t mstep_mode, double* phi_hat, double* Q, int32_t* status, int64_t* counters,
+             double* phi_starts, double* Q_starts, const SummaryArgs* sa = nullptr) {
+    CPN_ARG(ctx, R >= 0 && n_init >= 1 && max_em_iters >= 1, "R >= 0, n_init >= 1, max_em_iters >= 1");
+    CPN_ARG(ctx, grp_off && Nl && rho_l && d_l && read_off && lu && lm && phi0 && phi_hat && Q, "null pointer");
+    CPN_ARG(ctx, mstep_mode == CPN_MSTEP_FD || mstep_mode == CPN_MSTEP_ANALYTIC, "mstep_mode");
+    CPN_ARG(ctx, R * (int64_t)n_init < (int64_t)2147483647, "R*n_init must fit in int32");
+    CPN_CUDA(ctx, cudaSetDevice(ctx->device));
+    LaunchCounter lc(ctx);
+    if (R == 0) { ctx->last_ms = 0; return CPN_OK; }
+    cudaStream_t s = ctx->stream;
+    CPN_CUDA(ctx, cudaEventRecord(ctx->ev0, s));
+    {
+        PackedRegions pk;
+        int rc = pack_regions(ctx, pk, on_device, true, R, grp_off, Nl, rho_l, d_l, read_off, lu, lm);
+        if (rc) return rc;
+        const int64_t NI = R * n_init;
+        DevIn<double> d_phi0;
+        CPN_CUDA(ctx, d_phi0.bind(phi0, NI * 3, on_device, s));
+        DevBuf<double> phi, ES, Qs;
+        DevBuf<int> iter, stat, c_em, c_sol, c_ev, items_a, items_b, n_next, order;
+        CPN_CUDA(ctx, phi.alloc(3 * NI, s)); CPN_CUDA(ctx, ES.alloc(3 * NI, s)); CPN_CUDA(ctx, Qs.alloc(NI, s));
+        CPN_CUDA(ctx, iter.alloc(NI, s)); CPN_CUDA(ctx, stat.alloc(NI, s)); CPN_CUDA(ctx, c_em.alloc(NI, s));
+        CPN_CUDA(ctx, c_sol.alloc(NI, s)); CPN_CUDA(ctx, c_ev.alloc(NI, s));
+        CPN_CUDA(ctx, items_a.alloc(NI, s)); CPN_CUDA(ctx, items_b.alloc(NI, s)); CPN_CUDA(ctx, n_next.alloc(1, s));
+        // Regions ordered by group count (counting sort) so the 32 lanes of an M-step warp walk chains of
+        // similar length.
+        std::vector<int> h_order(R);
+        {
+            int64_t Lmax = 0;
+            for (int64_t r = 0; r < R; ++r) Lmax = std::max(Lmax, pk.h_grp_off[r + 1] - pk.h_grp_off[r]);
+            std::vector<int64_t> cnt(Lmax + 2, 0);
+            for (int64_t r = 0; r < R; ++r) cnt[pk.h_grp_off[r + 1] - pk.h_grp_off[r] + 1]++;
+            for (int64_t l = 0; l <= Lmax; ++l) cnt[l + 1] += cnt[l];
+            for (int64_t r = 0; r < R; ++r) h_order[cnt[pk.h_grp_off[r + 1] - pk.h_grp_off[r]]++] = (int)r;
+        }
+        CPN_CUDA(ctx, order.upload(h_order.data(), R, s));
+        EmState st{phi.p, ES.p, iter.p, stat.p, c_em.p, c_sol.p, c_ev.p, NI};
+        { KTimer kt(ctx, CPN_K_PREP);
+          k_init_state<<<blocks_for(NI, 256), 256, 0, s>>>(NI, n_init, d_phi0.p, st, items_a.p, order.p); }
+        int n_active = (int)NI;
+        int* cur = items_a.p;
+        int* nxt = items_b.p;
+        for (int it = 0; it < max_em_iters && n_active > 0; ++it) {
+            CPN_CUDA(ctx, cudaMemsetAsync(n_next.p, 0, sizeof(int), s));
+            { KTimer kt(ctx, CPN_K_ESTEP);
+              k_estep<<<blocks_for(n_active, E_WARPS), E_WARPS * 32, 0, s>>>(n_active, cur, n_init, pk.rt, phi.p, NI, ES.p); }
+            { KTimer kt(ctx, CPN_K_MSTEP);
+              k_mstep<<<blocks_for(n_active, M_THREADS), M_THREADS, 0, s>>>(n_active, cur, n_init, pk.rt, st, max_em_iters, amax, bmax, cmax,
+                                                                             mstep_mode, nxt, n_next.p); }
+            CPN_CUDA(ctx, cudaMemcpyAsync(&n_active, n_next.p, sizeof(int), cudaMemcpyDeviceToHost, s));
+            CPN_CUDA(ctx, cudaStreamSynchronize(s));
+            std::swap(cur, nxt);
+        }
+        // score converged instances (em_algorithm.jl:344), then pick per region
+        { KTimer kt(ctx, CPN_K_SCORE);
+          k_score<<<blocks_for(NI, E_WARPS), E_WARPS * 32, 0, s>>>((int)NI, nullptr, n_init, pk.rt, phi.p, NI, stat.p, 1, Qs.p); }
+        DevOut<double> o_phi, o_Q, o_ps, o_Qs;
+        DevOut<int32_t> o_status;
+        DevOut<int64_t> o_cnt;
+        CPN_CUDA(ctx, o_phi.bind(phi_hat, 3 * R, on_device, s));
+        CPN_CUDA(ctx, o_Q.bind(Q, R, on_device, s));
+        CPN_CUDA(ctx, o_status.bind(status, R, on_device, s));
+        CPN_CUDA(ctx, o_cnt.bind(counters, 4 * R, on_device, s));
+        if (phi_starts) CPN_CUDA(ctx, o_ps.bind(phi_starts, 3 * NI, on_device, s));
+        if (Q_starts) CPN_CUDA(ctx, o_Qs.bind(Q_starts, NI, on_device, s));
+        { KTimer kt(ctx, CPN_K_PICK);
+          k_pick<<<blocks_for(R, 128), 128, 0, s>>>(R, n_init, st, Qs.p, o_phi.p, o_Q.p, o_status.p, o_cnt.p, phi_starts ? o_ps.p : nullptr,
+                                                    Q_starts ? o_Qs.p : nullptr); }
+        CPN_CUDA(ctx, cudaGetLastError());
+        CPN_CUDA(ctx, o_phi.finish(s)); CPN_CUDA(ctx, o_Q.finish(s)); CPN_CUDA(ctx, o_status.finish(s)); CPN_CUDA(ctx, o_cnt.finish(s));
+        if (phi_starts) CPN_CUDA(ctx, o_ps.finish(s));
+        if (Q_starts) CPN_CUDA(ctx, o_Qs.finish(s));
+        if (sa) {
+            // rscle_grp_mod! + get_stat_sums! (nanopore.jl:338-343) on ϕ̂ straight from device memory; regions without a
+            // fit carry NaN ϕ̂ and produce NaN summaries (the host maps them to proc=false).
+            std::vector<int64_t> h_cpg(R + 1), h_sub(R + 1);
+            if (on_device) {
+                CPN_CUDA(ctx, cudaMemcpyAsync(h_cpg.data(), sa->cpg_off, (R + 1) * sizeof(int64_t), cudaMemcpyDeviceToHost, s));
+                CPN_CUDA(ctx, cudaMemcpyAsync(h_sub.data(), sa->sub_off, (R + 1) * sizeof(int64_t), cudaMemcpyDeviceToHost, s));
+                CPN_CUDA(ctx, cudaStreamSynchronize(s));
+            } else {
+                std::memcpy(h_cpg.data(), sa->cpg_off, (R + 1) * sizeof(int64_t));
+                std::memcpy(h_sub.data(), sa->sub_off, (R + 1) * sizeof(int64_t));
+            }
+            int64_t sumN = h_cpg[R], sumK = h_sub[R], Nmax = 0;
+            for (int64_t r = 0; r < R; ++r) {
+                CPN_ARG(ctx, h_cpg[r + 1] - h_cpg[r] >= 2, "every region needs N >= 2 CpG sites");
+                Nmax = std::max(Nmax, h_cpg[r + 1] - h_cpg[r]);
+            }
+            DevIn<int64_t> i_cpg, i_sub, i_sp, i_sq;
+            DevIn<double> i_rho, i_dn;
+            CPN_CUDA(ctx, i_cpg.bind(sa->cpg_off, R + 1, on_device, s)); CPN_CUDA(ctx, i_sub.bind(sa->sub_off, R + 1, on_device, s));
+            CPN_CUDA(ctx, i_sp.bind(sa->sub_p, sumK, on_device, s)); CPN_CUDA(ctx, i_sq.bind(sa->sub_q, sumK, on_device, s));
+            CPN_CUDA(ctx, i_rho.bind(sa->rho_n, sumN, on_device, s)); CPN_CUDA(ctx, i_dn.bind(sa->d_n, sumN - R, on_device, s));
+            DevOut<double> s_logZ, s_ex, s_exx, s_lg, s_e1, s_e2, s_mml, s_nme;
+            CPN_CUDA(ctx, s_logZ.bind(sa->logZ, R, on_device, s)); CPN_CUDA(ctx, s_ex.bind(sa->ex, sumN, on_device, s));
+            CPN_CUDA(ctx, s_exx.bind(sa->exx, sumN - R, on_device, s)); CPN_CUDA(ctx, s_lg.bind(sa->log_g, 4 * sumK, on_device, s));
+            CPN_CUDA(ctx, s_e1.bind(sa->e_log_g1, sumK, on_device, s)); CPN_CUDA(ctx, s_e2.bind(sa->e_log_g2, sumK, on_device, s));
+            CPN_CUDA(ctx, s_mml.bind(sa->mml, sumK, on_device, s)); CPN_CUDA(ctx, s_nme.bind(sa->nme, sumK, on_device, s));
+            int rc2 = cpn_stat_sums_launch(ctx, R, o_phi.p, nullptr, i_cpg.p, i_sub.p, i_cpg.p, i_rho.p, i_dn.p, i_sub.p, i_sp.p, i_sq.p, Nmax,
+                                           s_logZ.p, s_ex.p, s_exx.p, s_lg.p, s_e1.p, s_e2.p, s_mml.p, s_nme.p);
+            if (rc2) return rc2;
+            CPN_CUDA(ctx, s_logZ.finish(s)); CPN_CUDA(ctx, s_ex.finish(s)); CPN_CUDA(ctx, s_exx.finish(s)); CPN_CUDA(ctx, s_lg.finish(s));
+            CPN_CUDA(ctx, s_e1.finish(s)); CPN_CUDA(ctx, s_e2.finish(s)); CPN_CUDA(ctx, s_mml.finish(s)); CPN_CUDA(ctx, s_nme.finish(s));
+            CPN_CUDA(ctx, cudaEventRecord(ctx->ev1, s));
+            CPN_CUDA(ctx, cudaStreamSynchronize(s));
+        } else {
+            CPN_CUDA(ctx, cudaEventRecord(ctx->ev1, s));
+            CPN_CUDA(ctx, cudaStreamSynchronize(s));
+        }
+    }
+    float ms = 0;
+    CPN_CUDA(ctx, cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1));
+    ctx->last_ms = ms;
+    if (ctx->profile) cpn_profile_collect(ctx);
+    return CPN_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+int cpn_fit_batch(cpn_ctx* ctx, int64_t R, const int64_t* grp_off, const double* Nl, const double* rho_l, const double* d_l,
+                  const int64_t* read_off, const double* log_pyx_u, const double* log_pyx_m, const double* phi0, int32_t n_init,
+                  int32_t max_em_iters, double amax, double bmax, double cmax, int32_t mstep_mode, double* phi_hat, double* Q,
+                  int32_t* status, int64_t* counters, double* phi_starts, double* Q_starts) {
+    if (!ctx) return CPN_ERR_ARG;
+    return fit_impl(ctx, false, R, grp_off, Nl, rho_l, d_l, read_off, log_pyx_u, log_pyx_m, phi0, n_init, max_em_iters, amax, bmax, cmax,
+                    mstep_mode, phi_hat, Q, status, counters, phi_starts, Q_starts);
+}
+int cpn_fit_batch_device(cpn_ctx* ctx, int64_t R, const int64_t* grp_off, const double* Nl, const double* rho_l, const double* d_l,
+                         const int64_t* read_off, const double* log_pyx_u, const double* log_pyx_m, const double* phi0, int32_t n_init,
+                         int32_t max_em_iters, double amax, double bmax, double cmax, int32_t mstep_mode, double* phi_hat, double* Q,
+                         int32_t* status, int64_t* counters, double* phi_starts, double* Q_starts) {
+    if (!ctx) return CPN_ERR_ARG;
+    return fit_impl(ctx, true, R, grp_off, Nl, rho_l, d_l, read_off, log_pyx_u, log_pyx_m, phi0, n_init, max_em_iters, amax, bmax, cmax,
+                    mstep_mode, phi_hat, Q, status, counters, phi_starts, Q_starts);
+}
+
+static int analyze_common(cpn_ctx* ctx, bool dev, int64_t R, const int64_t* grp_off, const double* Nl, const double* rho_l, const double* d_l,
+                          const int64_t* read_off, const double* lu, const double* lm, const double* phi0, int32_t n_init, int32_t max_em_iters,
+                          double amax, double bmax, double cmax, int32_t mstep_mode, const int64_t* cpg_off, const double* rho_n,
+                          const double* d_n, const int64_t* sub_off, const int64_t* sub_p, const int64_t* sub_q, double* phi_hat, double* Q,
+                          int32_t* status, int64_t* counters, double* logZ, double* ex, double* exx, double* log_g, double* e_log_g1,
+                          double* e_log_g2, double* mml, double* nme) {
+    if (!ctx) return CPN_ERR_ARG;
+    CPN_ARG(ctx, cpg_off && rho_n && d_n && sub_off && sub_p && sub_q, "null per-CpG input pointer");
+    SummaryArgs sa{cpg_off, sub_off, sub_p, sub_q, rho_n, d_n, logZ, ex, exx, log_g, e_log_g1, e_log_g2, mml, nme};
+    return fit_impl(ctx, dev, R, grp_off, Nl, rho_l, d_l, read_off, lu, lm, phi0, n_init, max_em_iters, amax, bmax, cmax, mstep_mode, phi_hat,
+                    Q, status, counters, nullptr, nullptr, &sa);
+}
+
+int cpn_analyze_batch(cpn_ctx* ctx, int64_t R, const int64_t* grp_off, const double* Nl, const double* rho_l, const double* d_l,
+                      const int64_t* read_off, const double* log_pyx_u, const double* log_pyx_m, const double* phi0, int32_t n_init,
+                      int32_t max_em_iters, double amax, double bmax, double cmax, int32_t mstep_mode, const int64_t* cpg_off,
+                      const double* rho_n, const double* d_n, const int64_t* sub_off, const int64_t* sub_p, const int64_t* sub_q,
+                      double* phi_hat, double* Q, int32_t* status, int64_t* counters, double* logZ, double* ex, double* exx, double* log_g,
+                      double* e_log_g1, double* e_log_g2, double* mml, double* nme) {
+    return analyze_common(ctx, false, R, grp_off, Nl, rho_l, d_l, read_off, log_pyx_u, log_pyx_m, phi0, n_init, max_em_iters, amax, bmax, cmax,
+                          mstep_mode, cpg_off, rho_n, d_n, sub_off, sub_p, sub_q, phi_hat, Q, status, counters, logZ, ex, exx, log_g, e_log_g1,
+                          e_log_g2, mml, nme);
+}
+int cpn_analyze_batch_device(cpn_ctx* ctx, int64_t R, const int64_t* grp_off, const double* Nl, const double* rho_l, const double* d_l,
+                             const int64_t* read_off, const double* log_pyx_u, const double* log_pyx_m, const double* phi0, int32_t n_init,
+                             int32_t max_em_iters, double amax, double bmax, double cmax, int32_t mstep_mode, const int64_t* cpg_off,
+                             const double* rho_n, const double* d_n, const int64_t* sub_off, const int64_t* sub_p, const int64_t* sub_q,
+                             double* phi_hat, double* Q, int32_t* status, int64_t* counters, double* logZ, double* ex, double* exx,
+                             double* log_g, double* e_log_g1, double* e_log_g2, double* mml, double* nme) {
+    return analyze_common(ctx, true, R, grp_off, Nl, rho_l, d_l, read_off, log_pyx_u, log_pyx_m, phi0, n_init, max_em_iters, amax, bmax, cmax,
+                          mstep_mode, cpg_off, rho_n, d_n, sub_off, sub_p, sub_q, phi_hat, Q, status, counters, logZ, ex, exx, log_g, e_log_g1,
+                          e_log_g2, mml, nme);
+}
+
+int cpn_estep_batch(cpn_ctx* ctx, int64_t R, const int64_t* grp_off, const double* Nl, const double* rho_l, const double* d_l,
+                    const int64_t* read_off, const double* log_pyx_u, const double* log_pyx_m, const double* phi, double* ES,
+                    double* ave_logpy) {
+    if (!ctx) return CPN_ERR_ARG;
+    CPN_ARG(ctx, R >= 0 && grp_off && Nl && rho_l && d_l && read_off && log_pyx_u && log_pyx_m && phi && ES, "null pointer");
+    CPN_CUDA(ctx, cudaSetDevice(ctx->device));
+    LaunchCounter lc(ctx);
+    if (R == 0) return CPN_OK;
+    cudaStream_t s = ctx->stream;
+    CPN_CUDA(ctx, cudaEventRecord(ctx->ev0, s));
+    {
+        PackedRegions pk;
+        int rc = pack_regions(ctx, pk, false, true, R, grp_off, Nl, rho_l, d_l, read_off, log_pyx_u, log_pyx_m);
+        if (rc) return rc;
+        DevBuf<double> d_phi_in, d_phi, d_ES, d_ESo, d_Q;
+        CPN_CUDA(ctx, d_phi_in.upload(phi, 3 * R, s));
+        CPN_CUDA(ctx, d_phi.alloc(3 * R, s)); CPN_CUDA(ctx, d_ES.alloc(3 * R, s)); CPN_CUDA(ctx, d_ESo.alloc(3 * R, s));
+        CPN_CUDA(ctx, d_Q.alloc(R, s));
+        { KTimer kt(ctx, CPN_K_PREP); k_pack_phi<<<blocks_for(R, 256), 256, 0, s>>>(R, d_phi_in.p, d_phi.p); }
+        { KTimer kt(ctx, CPN_K_ESTEP); k_estep<<<blocks_for(R, E_WARPS), E_WARPS * 32, 0, s>>>((int)R, nullptr, 1, pk.rt, d_phi.p, R, d_ES.p); }
+        { KTimer kt(ctx, CPN_K_PREP); k_unpack3<<<blocks_for(R, 256), 256, 0, s>>>(R, d_ES.p, d_ESo.p); }
+        CPN_CUDA(ctx, d_ESo.download(ES, 3 * R, s));
+        if (ave_logpy) {
+            { KTimer kt(ctx, CPN_K_SCORE);
+              k_score<<<blocks_for(R, E_WARPS), E_WARPS * 32, 0, s>>>((int)R, nullptr, 1, pk.rt, d_phi.p, R, nullptr, 0, d_Q.p); }
+            CPN_CUDA(ctx, d_Q.download(ave_logpy, R, s));
+        }
+        CPN_CUDA(ctx, cudaGetLastError());
+        CPN_CUDA(ctx, cudaEventRecord(ctx->ev1, s));
+        CPN_CUDA(ctx, cudaStreamSynchronize(s));
+    }
+    float ms = 0;
+    CPN_CUDA(ctx, cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1));
+    ctx->last_ms = ms;
+    if (ctx->profile) cpn_profile_collect(ctx);
+    return CPN_OK;
+}
+
+int cpn_mstep_batch(cpn_ctx* ctx, int64_t R, const int64_t* grp_off, const double* Nl, const double* rho_l, const double* d_l,
+                    const int64_t* n_reads, const double* ES, const double* phi_init, int32_t mstep_mode, double* sol, int32_t* converged,
+                    int64_t* counters) {
+    if (!ctx) return CPN_ERR_ARG;
+    CPN_ARG(ctx, R >= 0 && grp_off && Nl && rho_l && d_l && n_reads && ES && phi_init && sol && converged, "null pointer");
+    CPN_ARG(ctx, mstep_mode == CPN_MSTEP_FD || mstep_mode == CPN_MSTEP_ANALYTIC, "mstep_mode");
+    CPN_CUDA(ctx, cudaSetDevice(ctx->device));
+    LaunchCounter lc(ctx);
+    if (R == 0) return CPN_OK;
+    cudaStream_t s = ctx->stream;
+    CPN_CUDA(ctx, cudaEventRecord(ctx->ev0, s));
+    {
+        PackedRegions pk;
+        int rc = pack_regions(ctx, pk, false, false, R, grp_off, Nl, rho_l, d_l, nullptr, nullptr, nullptr);
+        if (rc) return rc;
+        DevBuf<int64_t> d_nr, d_cnt;
+        DevBuf<double> d_ES, d_phi, d_sol;
+        DevBuf<int> d_conv;
+        CPN_CUDA(ctx, d_nr.upload(n_reads, R, s)); CPN_CUDA(ctx, d_ES.upload(ES, 3 * R, s)); CPN_CUDA(ctx, d_phi.upload(phi_init, 3 * R, s));
+        CPN_CUDA(ctx, d_sol.alloc(3 * R, s)); CPN_CUDA(ctx, d_conv.alloc(R, s)); CPN_CUDA(ctx, d_cnt.alloc(2 * R, s));
+        { KTimer kt(ctx, CPN_K_MSTEP);
+          k_mstep_once<<<blocks_for(R, 64), 64, 0, s>>>(R, pk.rt, d_nr.p, d_ES.p, d_phi.p, mstep_mode, d_sol.p, d_conv.p, d_cnt.p); }
+        CPN_CUDA(ctx, cudaGetLastError());
+        CPN_CUDA(ctx, d_sol.download(sol, 3 * R, s));
+        CPN_CUDA(ctx, d_conv.download(converged, R, s));
+        if (counters) CPN_CUDA(ctx, d_cnt.download(counters, 2 * R, s));
+        CPN_CUDA(ctx, cudaEventRecord(ctx->ev1, s));
+        CPN_CUDA(ctx, cudaStreamSynchronize(s));
+    }
+    float ms = 0;
+    CPN_CUDA(ctx, cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1));
+    ctx->last_ms = ms;
+    if (ctx->profile) cpn_profile_collect(ctx);
+    return CPN_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,368 @@
+"""Host-side mirror of the reference's Julia interface for the estimation hot path.
+
+Everything numeric is done by libcpelnano_b200.so; this module only packs `RegStruct`s into the CSR
+batches of include/cpelnano_b200.h and unpacks results, keeping the reference's names, argument meaning
+and failure behaviour (empty ϕ̂ ⇒ region skipped; NaN for empty sub-regions).
+"""
+import math
+from dataclasses import dataclass, field
+from itertools import combinations
+
+import numpy as np
+
+from .capi import Library, MSTEP_ANALYTIC
+
+LMAX = 1000                      # src/CpelNano.jl:50
+AMAX, BMAX, CMAX = 20.0, 150.0, 50.0   # src/CpelNano.jl:36-38 (non-const globals in the reference → passed by value)
+
+
+@dataclass
+class CpelNanoConfig:
+    """src/structures.jl:36-69 (fields used by the hot path; defaults of CpelNanoConfig())."""
+    min_cov: float = 10.0
+    min_grp_dist: int = 10
+    max_size_subreg: int = 350
+    size_est_reg: int = 3000
+    max_em_init: int = 10
+    max_em_iters: int = 20
+    matched: bool = False
+    verbose: bool = False
+    LMAX_TWO_SAMP: int = 100
+    pval_comp: bool = True
+    mstep_mode: int = MSTEP_ANALYTIC      # B200 extension: see include/cpelnano_b200.h
+
+    @classmethod
+    def five_arg(cls, min_cov, max_size_subreg, size_est_reg, max_em_init, max_em_iters):
+        """The 5-argument constructor silently stores max_size_subreg + 1 (src/structures.jl:65-68)."""
+        return cls(min_cov=min_cov, max_size_subreg=max_size_subreg + 1, size_est_reg=size_est_reg, max_em_init=max_em_init,
+                   max_em_iters=max_em_iters)
+
+
+@dataclass
+class AnalysisRegions:
+    """src/structures.jl:140-147 — closed genomic intervals and 1-based CpG index ranges (0 = empty)."""
+    num: int = 0
+    chr_st: np.ndarray = field(default_factory=lambda: np.zeros(0, dtype=np.int64))
+    chr_end: np.ndarray = field(default_factory=lambda: np.zeros(0, dtype=np.int64))
+    cpg_p: np.ndarray = field(default_factory=lambda: np.zeros(0, dtype=np.int64))
+    cpg_q: np.ndarray = field(default_factory=lambda: np.zeros(0, dtype=np.int64))
+
+
+def _empty():
+    return np.zeros(0)
+
+
+@dataclass
+class RegStruct:
+    """src/structures.jl:150-197.  `calls` is stored packed: lu/lm [m, L] with NaN = not observed."""
+    proc: bool = False
+    chr: str = ""
+    chrst: int = 0
+    chrend: int = 0
+    N: int = 0
+    L: int = 0
+    Nl: np.ndarray = field(default_factory=_empty)
+    rho_n: np.ndarray = field(default_factory=_empty)
+    rho_l: np.ndarray = field(default_factory=_empty)
+    dn: np.ndarray = field(default_factory=_empty)
+    dl: np.ndarray = field(default_factory=_empty)
+    cpg_pos: np.ndarray = field(default_factory=lambda: np.zeros(0, dtype=np.int64))
+    m: int = 0
+    log_pyx_u: np.ndarray = field(default_factory=lambda: np.zeros((0, 0)))
+    log_pyx_m: np.ndarray = field(default_factory=lambda: np.zeros((0, 0)))
+    nls_rgs: AnalysisRegions = field(default_factory=AnalysisRegions)
+    phihat: np.ndarray = field(default_factory=_empty)
+    logZ: float = math.nan
+    mml: np.ndarray = field(default_factory=_empty)
+    nme: np.ndarray = field(default_factory=_empty)
+    ex: np.ndarray = field(default_factory=_empty)
+    exx: np.ndarray = field(default_factory=_empty)
+    log_g1: np.ndarray = field(default_factory=_empty)       # E[log g1(X_p)]
+    log_g2: np.ndarray = field(default_factory=_empty)       # E[log g2(X_q)]
+    log_gs: np.ndarray = field(default_factory=lambda: np.zeros((0, 4)))   # pm, pp, qm, qp
+    Q: float = -math.inf
+
+    def set_calls(self, lu, lm):
+        self.log_pyx_u = np.ascontiguousarray(lu, dtype=np.float64)
+        self.log_pyx_m = np.ascontiguousarray(lm, dtype=np.float64)
+        self.m = self.log_pyx_u.shape[0]
+
+    # src/structures.jl:200-203
+    def get_ave_depth(self):
+        return float(np.sum(~np.isnan(self.log_pyx_u))) / self.L
+
+    def perc_gprs_obs(self):
+        return float(np.sum(np.any(~np.isnan(self.log_pyx_u), axis=0))) / self.L
+
+
+class Engine:
+    """One cpn_ctx on one GPU."""
+
+    def __init__(self, device=0, library=None):
+        self.lib = library or Library()
+        self.device = device
+        self.lib.ctx(device)          # fail now if there is no B200
+
+    # ---- packing -------------------------------------------------------------------------------
+    @staticmethod
+    def pack_groups(regs):
+        grp_off = np.concatenate([[0], np.cumsum([r.L for r in regs])]).astype(np.int64)
+        Nl = np.concatenate([np.asarray(r.Nl, dtype=np.float64) for r in regs])
+        rho_l = np.concatenate([np.asarray(r.rho_l, dtype=np.float64) for r in regs])
+        d_l = np.concatenate([np.asarray(r.dl, dtype=np.float64) for r in regs])
+        return grp_off, Nl, rho_l, d_l
+
+    @staticmethod
+    def pack_calls(regs):
+        read_off = np.concatenate([[0], np.cumsum([r.m for r in regs])]).astype(np.int64)
+        lu = np.concatenate([r.log_pyx_u.reshape(-1) for r in regs])
+        lm = np.concatenate([r.log_pyx_m.reshape(-1) for r in regs])
+        return read_off, lu, lm
+
+    @staticmethod
+    def pack_cpgs(regs):
+        cpg_off = np.concatenate([[0], np.cumsum([r.N for r in regs])]).astype(np.int64)
+        rho_n = np.concatenate([np.asarray(r.rho_n, dtype=np.float64) for r in regs])
+        d_n = np.concatenate([np.asarray(r.dn, dtype=np.float64) for r in regs])
+        sub_off = np.concatenate([[0], np.cumsum([r.nls_rgs.num for r in regs])]).astype(np.int64)
+        sub_p = np.concatenate([r.nls_rgs.cpg_p for r in regs]).astype(np.int64)
+        sub_q = np.concatenate([r.nls_rgs.cpg_q for r in regs]).astype(np.int64)
+        return cpg_off, rho_n, d_n, sub_off, sub_p, sub_q
+
+    # ---- get_ϕhat! -------------------------------------------------------------------------------
+    def get_phihat_batch(self, regs, config, phi0s=None, rng=None, per_start=False):
+        """get_ϕhat!(rs, config) for many regions in one call (src/em_algorithm.jl:371-390).
+        `phi0s` [R, max_em_init, 3] replaces gen_ϕ0s (:65-78); if None they are drawn from `rng`."""
+        if not regs:
+            return None
+        if phi0s is None:
+            from .simulations import gen_phi0s
+            phi0s = gen_phi0s(rng or np.random.default_rng(), len(regs), config.max_em_init)
+        grp_off, Nl, rho_l, d_l = self.pack_groups(regs)
+        read_off, lu, lm = self.pack_calls(regs)
+        out = self.lib.fit_batch(grp_off, Nl, rho_l, d_l, read_off, lu, lm, phi0s, config.max_em_init, config.max_em_iters,
+                                 (AMAX, BMAX, CMAX), config.mstep_mode, per_start=per_start, device=self.device)
+        for i, rs in enumerate(regs):
+            ok = out["pick"][i] >= 0
+            rs.phihat = out["phi_hat"][i].copy() if ok else np.zeros(0)     # rs.ϕhat = [] when Qhat == -Inf (:385)
+            rs.Q = float(out["Q"][i])
+        return out
+
+    # ---- get_nls_reg_info! + get_stat_sums! ---------------------------------------------------------
+    def get_nls_reg_info(self, rs, config):
+        st, en, p, q = self.lib.nls_reg_info(rs.chrst, rs.chrend, config.max_size_subreg, rs.cpg_pos)
+        rs.nls_rgs = AnalysisRegions(len(st), st, en, p, q)
+
+    def get_stat_sums_batch(self, regs, config):
+        """get_stat_sums!(rs, config) (src/statistical_summaries.jl:470-500) for regions that were rescaled with
+        rscle_grp_mod (per-CpG chain) and have a non-empty ϕ̂."""
+        if not regs:
+            return
+        for rs in regs:
+            assert len(rs.phihat) == 3, "get_stat_sums needs a fitted ϕ̂"
+            self.get_nls_reg_info(rs, config)
+        cpg_off, rho_n, d_n, sub_off, sub_p, sub_q = self.pack_cpgs(regs)
+        phi = np.array([rs.phihat for rs in regs])
+        out = self.lib.stat_sums_batch(phi, cpg_off, rho_n, d_n, sub_off, sub_p, sub_q, device=self.device)
+        for i, rs in enumerate(regs):
+            n0, n1, k0, k1 = cpg_off[i], cpg_off[i + 1], sub_off[i], sub_off[i + 1]
+            rs.logZ = float(out["logZ"][i])
+            rs.ex = out["ex"][n0:n1].copy(); rs.exx = out["exx"][n0 - i:n1 - i - 1].copy()
+            rs.log_gs = out["log_g"][k0:k1].copy()
+            rs.log_g1 = out["e_log_g1"][k0:k1].copy(); rs.log_g2 = out["e_log_g2"][k0:k1].copy()
+            rs.mml = out["mml"][k0:k1].copy(); rs.nme = out["nme"][k0:k1].copy()
+
+    # ---- comp_cmd ------------------------------------------------------------------------------------
+    def comp_cmd_pairs(self, models, pairs, regions=None):
+        """comp_cmd(models[a], models[b]) for every (a,b) in pairs (src/statistical_summaries.jl:512-570).
+        All models must already hold get_stat_sums outputs.  Models of a pair must share the region features."""
+        if not pairs:
+            return []
+        # unique genomic regions by identity of the feature arrays
+        key = {}
+        reg_of = np.zeros(len(models), dtype=np.int64)
+        reps = []
+        for t, m in enumerate(models):
+            kk = (m.chr, m.chrst, m.chrend, m.N)
+            if kk not in key:
+                key[kk] = len(reps); reps.append(m)
+            reg_of[t] = key[kk]
+        cpg_off, rho_n, d_n, sub_off, sub_p, sub_q = self.pack_cpgs(reps)
+        phi_tbl = np.array([m.phihat for m in models])
+        ex_off = np.concatenate([[0], np.cumsum([m.N for m in models])]).astype(np.int64)
+        nme_off = np.concatenate([[0], np.cumsum([m.nls_rgs.num for m in models])]).astype(np.int64)
+        ex_tbl = np.concatenate([m.ex for m in models]); exx_tbl = np.concatenate([m.exx for m in models])
+        nme_tbl = np.concatenate([m.nme for m in models])
+        pa = np.array([p[0] for p in pairs], dtype=np.int64); pb = np.array([p[1] for p in pairs], dtype=np.int64)
+        cmd, cmd_off = self.lib.cmd_batch(pa, pb, phi_tbl, reg_of, ex_off, ex_tbl, exx_tbl, nme_off, nme_tbl, cpg_off, rho_n, d_n, sub_off,
+                                          sub_p, sub_q, device=self.device)
+        return [cmd[cmd_off[i]:cmd_off[i + 1]].copy() for i in range(len(pairs))]
+
+    # ---- group tests -----------------------------------------------------------------------------------
+    def unmat_est_reg_test_batch(self, regions_g1, regions_g2, labelings=None, rng=None):
+        """unmat_est_reg_test(ms_g1, ms_g2) (src/grp_perm_tests.jl:200-291) for a list of regions; regions_g1[r] and
+        regions_g2[r] are the lists of fitted models of the two groups (same n1, n2 for every region of a call)."""
+        R = len(regions_g1)
+        n1, n2 = len(regions_g1[0]), len(regions_g2[0])
+        S = n1 + n2
+        L = math.comb(S, n1)
+        if L > 20:
+            exact = L < LMAX
+            if labelings is None:
+                allc = np.array(list(combinations(range(1, S + 1), n1)), dtype=np.int32)
+                if exact:
+                    labelings = allc
+                else:   # rand(1:L, LMAX) then keep the enumerated combinations whose index was drawn (:242-245)
+                    rng = rng or np.random.default_rng()
+                    idx = np.unique(rng.integers(0, L, size=LMAX))
+                    labelings = allc[idx]
+        else:
+            exact, labelings = True, np.zeros((0, n1), dtype=np.int32)
+        models, pairs, tbl_off = [], [], [0]
+        for r in range(R):
+            base = len(models)
+            models.extend(regions_g1[r]); models.extend(regions_g2[r])
+            pairs.extend((base + i, base + j) for i in range(S) for j in range(i + 1, S))
+            tbl_off.append(tbl_off[-1] + regions_g1[r][0].nls_rgs.num)
+        cmds = self.comp_cmd_pairs(models, pairs)
+        mml = np.concatenate([np.stack([m.mml for m in regions_g1[r] + regions_g2[r]]).reshape(-1) for r in range(R)])
+        nme = np.concatenate([np.stack([m.nme for m in regions_g1[r] + regions_g2[r]]).reshape(-1) for r in range(R)])
+        tbl = []
+        ci = 0
+        for r in range(R):
+            K = regions_g1[r][0].nls_rgs.num
+            t = np.full((S, S, K), np.nan)
+            for i in range(S):
+                for j in range(i + 1, S):
+                    t[i, j] = cmds[ci]; ci += 1
+            tbl.append(t.reshape(-1))
+        T, cnt, p = self.lib.grp_unmat_sweep(n1, n2, np.array(tbl_off), mml, nme, np.concatenate(tbl), labelings, exact, device=self.device)
+        out = []
+        for r in range(R):
+            K = tbl_off[r + 1] - tbl_off[r]
+            sl = slice(3 * tbl_off[r], 3 * tbl_off[r + 1])
+            out.append(dict(T=T[sl].reshape(3, K), cnt=cnt[sl].reshape(3, K), pval=p[sl].reshape(3, K), coords=regions_g1[r][0].nls_rgs))
+        return out
+
+    def mat_est_reg_test_batch(self, regions_g1, regions_g2, js=None, rng=None):
+        """mat_est_reg_test (src/grp_perm_tests.jl:432-499): Tmml, Tnme with sign-flip p-values; Tcmd = mean pair CMD, no p-value."""
+        R = len(regions_g1)
+        n = len(regions_g1[0])
+        if 0.5 ** n < 0.05:
+            exact = 2 ** n < LMAX
+            if js is None:
+                js = np.arange(2 ** n, dtype=np.int64) if exact else (rng or np.random.default_rng()).integers(0, 2 ** n, size=LMAX)
+        else:
+            exact, js = True, np.zeros(0, dtype=np.int64)
+        tbl_off = np.concatenate([[0], np.cumsum([regions_g1[r][0].nls_rgs.num for r in range(R)])]).astype(np.int64)
+        cat = lambda regs, f: np.concatenate([np.stack([getattr(m, f) for m in regs[r]]).reshape(-1) for r in range(R)])   # noqa: E731
+        T, cnt, p = self.lib.grp_mat_sweep(n, tbl_off, cat(regions_g1, "mml"), cat(regions_g2, "mml"), cat(regions_g1, "nme"),
+                                           cat(regions_g2, "nme"), js, exact, device=self.device)
+        models, pairs = [], []
+        for r in range(R):
+            base = len(models)
+            models.extend(regions_g1[r]); models.extend(regions_g2[r])
+            pairs.extend((base + s, base + n + s) for s in range(n))
+        cmds = self.comp_cmd_pairs(models, pairs)
+        out = []
+        for r in range(R):
+            K = tbl_off[r + 1] - tbl_off[r]
+            sl = slice(2 * tbl_off[r], 2 * tbl_off[r + 1])
+            pc = cmds[r * n:(r + 1) * n]
+            tc = pc[0].copy()
+            for s in range(1, n):
+                tc = tc + pc[s]                                        # sum(cmds)/n, left to right (:308-314)
+            out.append(dict(T=T[sl].reshape(2, K), cnt=cnt[sl].reshape(2, K), pval=p[sl].reshape(2, K), tcmd=tc / n,
+                            coords=regions_g1[r][0].nls_rgs))
+        return out
+
+
+_default = None
+
+
+def default_engine():
+    global _default
+    if _default is None:
+        _default = Engine(0)
+    return _default
+
+
+# ---- single-struct entry points with the reference's names -----------------------------------------------
+def get_phihat(rs, config, phi0s=None, rng=None, engine=None):
+    (engine or default_engine()).get_phihat_batch([rs], config, None if phi0s is None else np.asarray(phi0s)[None], rng)
+
+
+def rscle_grp_mod(rs):
+    """src/nanopore.jl:269-280 — redefine groups as singletons (per-CpG chain)."""
+    rs.L = rs.N
+    rs.dl = np.asarray(rs.dn, dtype=np.float64)
+    rs.rho_l = np.asarray(rs.rho_n, dtype=np.float64)
+    rs.Nl = np.ones(rs.N)
+
+
+def get_nls_reg_info(rs, config, engine=None):
+    (engine or default_engine()).get_nls_reg_info(rs, config)
+
+
+def get_stat_sums(rs, config, engine=None):
+    (engine or default_engine()).get_stat_sums_batch([rs], config)
+
+
+def comp_cmd(rs1, rs2, engine=None):
+    return (engine or default_engine()).comp_cmd_pairs([rs1, rs2], [(0, 1)])[0]
+
+
+def unmat_est_reg_test(ms_g1, ms_g2, engine=None, **kw):
+    return (engine or default_engine()).unmat_est_reg_test_batch([ms_g1], [ms_g2], **kw)[0]
+
+
+def mat_est_reg_test(ms_g1, ms_g2, engine=None, **kw):
+    return (engine or default_engine()).mat_est_reg_test_batch([ms_g1], [ms_g2], **kw)[0]
+
+
+def _copy_features(rs_ref):
+    """cp_rs_flds (src/two_samp_perm_tests.jl:11-30): keep the genomic features, reset the data and results."""
+    rs = RegStruct(chr=rs_ref.chr, chrst=rs_ref.chrst, chrend=rs_ref.chrend, N=rs_ref.N, L=rs_ref.L, Nl=np.array(rs_ref.Nl),
+                   rho_n=np.array(rs_ref.rho_n), rho_l=np.array(rs_ref.rho_l), dn=np.array(rs_ref.dn), dl=np.array(rs_ref.dl),
+                   cpg_pos=np.array(rs_ref.cpg_pos))
+    return rs
+
+
+def pmap_two_samp_null_stats(rs_ref, calls_s1, calls_s2, perm_ids, config, phi0s=None, rng=None, engine=None):
+    """src/two_samp_perm_tests.jl:41-87 for ONE permutation: pooled reads are split by `perm_ids` (ascending
+    1-based indices into vcat(calls_s1, calls_s2)), both halves are refitted, rescaled, summarised, compared.
+    calls_* are (lu, lm) tuples of [m, L] arrays; phi0s [2, max_em_init, 3] replaces the two gen_ϕ0s draws."""
+    eng = engine or default_engine()
+    lu = np.concatenate([calls_s1[0], calls_s2[0]]); lm = np.concatenate([calls_s1[1], calls_s2[1]])
+    idx = np.asarray(perm_ids, dtype=np.int64) - 1
+    rest = np.setdiff1d(np.arange(lu.shape[0]), idx)            # deleteat!(aux_calls, perm_ids): the rest, in order
+    a1, a2 = _copy_features(rs_ref), _copy_features(rs_ref)
+    a1.set_calls(lu[idx], lm[idx]); a2.set_calls(lu[rest], lm[rest])
+    K = rs_ref.nls_rgs.num
+    nan3 = (np.full(K, np.nan), np.full(K, np.nan), np.full(K, np.nan))
+    eng.get_phihat_batch([a1, a2], config, phi0s, rng)
+    if not (len(a1.phihat) > 0 and len(a2.phihat) > 0):
+        return nan3
+    rscle_grp_mod(a1); rscle_grp_mod(a2)
+    eng.get_stat_sums_batch([a1, a2], config)
+    return a1.mml - a2.mml, a1.nme - a2.nme, eng.comp_cmd_pairs([a1, a2], [(0, 1)])[0]
+
+
+def analyze_regions(regs, config, phi0s=None, rng=None, engine=None):
+    """The body of pmap_analyze_reg (src/nanopore.jl:292-352) for a whole chromosome's worth of regions at once —
+    the batch point that replaces `pmap` at src/nanopore.jl:406.  `regs` already carry genomic features and calls
+    (get_grp_info!/get_calls! stay on the Julia side).  Regions failing the reference's filters are left with proc=false."""
+    eng = engine or default_engine()
+    keep = [i for i, rs in enumerate(regs)
+            if len(rs.cpg_pos) > 9 and rs.m > 0 and rs.get_ave_depth() >= config.min_cov and rs.perc_gprs_obs() >= 0.66 and rs.L > 1]
+    if not keep:
+        return regs
+    sel = [regs[i] for i in keep]
+    eng.get_phihat_batch(sel, config, None if phi0s is None else np.asarray(phi0s)[keep], rng)
+    fitted = [rs for rs in sel if len(rs.phihat) > 0]
+    for rs in fitted:
+        rscle_grp_mod(rs)
+    eng.get_stat_sums_batch(fitted, config)
+    for rs in fitted:
+        rs.proc = True
+    return regs

@@ -1,0 +1,192 @@
+/* cpelnano_b200.h — C ABI of libcpelnano_b200.so (hand-written sm_100a CUDA kernels).
+ *
+ * Drop-in boundary for the per-region Ising estimation hot path of jordiabante/CpelNano.jl.
+ * The reference has no FFI; the boundary is cut at the Julia functions listed below, and each entry
+ * point here is what a `ccall` shim for that function binds (julia/CpelNanoB200.jl).
+ * Plain C: pointers and sizes only.  All host buffers are caller-owned; the library never keeps a host
+ * pointer after a call returns.  Return value 0 = ok, non-zero = error (text via cpn_last_error).
+ * Per-region numerical failures are NOT errors: they come back as status codes / NaN, mirroring the
+ * reference's "log and skip" behaviour (src/em_algorithm.jl:160-172,385).
+ *
+ * Conventions
+ *   - state index: x=-1 "unmethylated", x=+1 "methylated"
+ *   - CSR batches: `grp_off[R+1]` indexes per-group arrays (Nl, rho_l); d_l (L_r-1 entries per region)
+ *     starts at grp_off[r]-r.  `cpg_off[R+1]` / d_n likewise at CpG scale.
+ *   - emissions are read-major per region: element (m,l) of region r at obs_off[r] + m*L_r + l with
+ *     obs_off[r] = sum_{r'<r} M_r' L_r'; NaN in log_pyx_u marks "group not observed in this read"
+ *     (MethCallCpgGrp.obs == false, src/structures.jl:121-128).
+ *   - there is NO CPU fallback: every compute entry point fails with CPN_ERR_CUDA if no sm_100 device.
+ */
+#ifndef CPELNANO_B200_H
+#define CPELNANO_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct cpn_ctx cpn_ctx;
+
+enum {
+    CPN_OK = 0,
+    CPN_ERR_ARG = 1,      /* bad argument (null pointer, negative size, L<2, ...) */
+    CPN_ERR_CUDA = 2,     /* CUDA runtime error or no usable device */
+    CPN_ERR_NOMEM = 3
+};
+
+/* M-step evaluation mode (src/em_algorithm.jl:152-163 solves ∇logZ(ϕ) = ES/M with NLsolve):
+ *   CPN_MSTEP_ANALYTIC  gradient and Jacobian of log Z by forward-mode recursion along the chain (default)
+ *   CPN_MSTEP_FD        the reference's central finite differences of log Z (Calculus.gradient inside a
+ *                       FiniteDiff central Jacobian), same step sizes and evaluation order            */
+enum { CPN_MSTEP_FD = 0, CPN_MSTEP_ANALYTIC = 1 };
+
+/* per-start / per-region status of the EM fit (src/em_algorithm.jl:341-344,385) */
+enum { CPN_FIT_NONE = -1 /* all starts ended with Q=-Inf: rs.ϕhat = [] */ };
+
+/* ---- context ------------------------------------------------------------------------------- */
+int  cpn_create(int device_id, cpn_ctx** out);
+void cpn_destroy(cpn_ctx* ctx);
+const char* cpn_last_error(const cpn_ctx* ctx);           /* NUL-terminated, library-owned */
+const char* cpn_version(void);
+/* CUDA-event time (ms) of the device work of the last call on this ctx, and the number of kernels
+ * it launched (for bench.py's gpu_launches). */
+double  cpn_last_device_ms(const cpn_ctx* ctx);
+int64_t cpn_last_launches(const cpn_ctx* ctx);
+/* Measured FP64 FMA peak of this device (dependent-chain-free DFMA loop), TFLOP/s; and a DRAM copy
+ * bandwidth figure GB/s.  Used as roofline denominators when MEASURED_PEAKS.json has no FP64 entry. */
+int cpn_measure_fp64_peak(cpn_ctx* ctx, double* tflops);
+/* Optional per-launch profiler: when enabled, every kernel launch is bracketed by CUDA events on the
+ * launching stream and its time accumulated per kernel class (8 classes: 0 prep, 1 E-step, 2 M-step,
+ * 3 score, 4 pick, 5 summaries, 6 CMD, 7 sweeps).  cpn_set_profile resets the accumulators.          */
+int cpn_set_profile(cpn_ctx* ctx, int enable);
+int cpn_get_profile(const cpn_ctx* ctx, double* ms /*[8]*/, int64_t* launches /*[8]*/);
+
+/* ---- (b)+(c) multi-start EM: get_ϕhat!(rs, config)  src/em_algorithm.jl:371-390 -------------------
+ * For every region r: run n_init EM instances (em_inst, :304-350) from the given starts phi0 (the host
+ * RNG owns gen_ϕ0s, :65-78), keep the first start with maximal Q = mean_m log p(y_m; ϕ) (pick_ϕ, :35-53).
+ * Inputs are HOST pointers (copied to the device inside the call).
+ *   phi0        [R * n_init * 3]
+ *   phi_hat     [R * 3]   NaN when no start converged
+ *   Q           [R]       -Inf when no start converged
+ *   status      [R]       index of the picked start (0-based) or CPN_FIT_NONE
+ *   counters    [R * 4]   (em_iters, solver_iters, logZ_evals, estep_passes) summed over starts; may be NULL
+ *   phi_starts  [R * n_init * 3], Q_starts [R * n_init]  per-start results; may be NULL              */
+int cpn_fit_batch(cpn_ctx* ctx, int64_t R,
+                  const int64_t* grp_off, const double* Nl, const double* rho_l, const double* d_l,
+                  const int64_t* read_off, const double* log_pyx_u, const double* log_pyx_m,
+                  const double* phi0, int32_t n_init, int32_t max_em_iters,
+                  double amax, double bmax, double cmax, int32_t mstep_mode,
+                  double* phi_hat, double* Q, int32_t* status, int64_t* counters,
+                  double* phi_starts, double* Q_starts);
+
+/* Same computation with every buffer already resident in device memory (HBM) of ctx's device; used
+ * to measure device-only throughput and by callers that keep packed batches on the GPU.            */
+int cpn_fit_batch_device(cpn_ctx* ctx, int64_t R,
+                  const int64_t* grp_off, const double* Nl, const double* rho_l, const double* d_l,
+                  const int64_t* read_off, const double* log_pyx_u, const double* log_pyx_m,
+                  const double* phi0, int32_t n_init, int32_t max_em_iters,
+                  double amax, double bmax, double cmax, int32_t mstep_mode,
+                  double* phi_hat, double* Q, int32_t* status, int64_t* counters,
+                  double* phi_starts, double* Q_starts);
+
+/* ---- batched pmap_analyze_reg: fit → rscle_grp_mod! → get_stat_sums!  src/nanopore.jl:331-343 -------------
+ * One call per chromosome replaces the `pmap` at src/nanopore.jl:406.  Inputs of cpn_fit_batch plus the per-CpG
+ * features and sub-regions of cpn_stat_sums_batch (model r ↔ region r).  ϕ̂ goes from the EM kernels to the
+ * summaries kernel in device memory.  Regions without a converged start get NaN summaries (host: proc=false).
+ * The _device variant takes device pointers for every buffer.                                              */
+int cpn_analyze_batch(cpn_ctx* ctx, int64_t R,
+                  const int64_t* grp_off, const double* Nl, const double* rho_l, const double* d_l,
+                  const int64_t* read_off, const double* log_pyx_u, const double* log_pyx_m,
+                  const double* phi0, int32_t n_init, int32_t max_em_iters,
+                  double amax, double bmax, double cmax, int32_t mstep_mode,
+                  const int64_t* cpg_off, const double* rho_n, const double* d_n,
+                  const int64_t* sub_off, const int64_t* sub_p, const int64_t* sub_q,
+                  double* phi_hat, double* Q, int32_t* status, int64_t* counters,
+                  double* logZ, double* ex, double* exx, double* log_g,
+                  double* e_log_g1, double* e_log_g2, double* mml, double* nme);
+int cpn_analyze_batch_device(cpn_ctx* ctx, int64_t R,
+                  const int64_t* grp_off, const double* Nl, const double* rho_l, const double* d_l,
+                  const int64_t* read_off, const double* log_pyx_u, const double* log_pyx_m,
+                  const double* phi0, int32_t n_init, int32_t max_em_iters,
+                  double amax, double bmax, double cmax, int32_t mstep_mode,
+                  const int64_t* cpg_off, const double* rho_n, const double* d_n,
+                  const int64_t* sub_off, const int64_t* sub_p, const int64_t* sub_q,
+                  double* phi_hat, double* Q, int32_t* status, int64_t* counters,
+                  double* logZ, double* ex, double* exx, double* log_g,
+                  double* e_log_g1, double* e_log_g2, double* mml, double* nme);
+
+/* Building blocks of em_iter exposed for parity tests (host pointers):
+ *   cpn_estep_batch   ES[r] = get_ess(map(get_cond_exs_log))  src/em_algorithm.jl:142-146 at phi[r]
+ *                     and ave_logpy[r] = comp_ave_log_py (:263-288) at the same phi (may be NULL)
+ *   cpn_mstep_batch   one NLsolve-equivalent solve from phi_init[r] given ES[r] (:152-178, before clamp);
+ *                     converged[r] = converged(sol)                                                  */
+int cpn_estep_batch(cpn_ctx* ctx, int64_t R, const int64_t* grp_off, const double* Nl, const double* rho_l,
+                    const double* d_l, const int64_t* read_off, const double* log_pyx_u, const double* log_pyx_m,
+                    const double* phi /*[R*3]*/, double* ES /*[R*3]*/, double* ave_logpy /*[R] or NULL*/);
+int cpn_mstep_batch(cpn_ctx* ctx, int64_t R, const int64_t* grp_off, const double* Nl, const double* rho_l,
+                    const double* d_l, const int64_t* n_reads /*[R]*/, const double* ES /*[R*3]*/,
+                    const double* phi_init /*[R*3]*/, int32_t mstep_mode, double* sol /*[R*3]*/,
+                    int32_t* converged /*[R]*/, int64_t* counters /*[R*2] solver_iters, evals; or NULL*/);
+
+/* ---- (a)+(d) summaries of fitted per-CpG chains: get_stat_sums!(rs, config) -------------------------
+ * src/statistical_summaries.jl:470-500 after rscle_grp_mod! (src/nanopore.jl:269-280): N_l=1, ρ_l=ρ_n,
+ * d_l=d_n.  Sub-regions come from cpn_nls_reg_info (1-based CpG index ranges, 0 = empty).
+ * A table of T fitted models is summarised in one call; model t lives on genomic region reg_of[t] (several
+ * samples may share a region's features).  reg_of == NULL means T == R and model r ↔ region r, in which case
+ * ex_off/k_off may be NULL too (they default to cpg_off/sub_off).
+ *   phi [T*3]; reg_of [T]; ex_off [T+1] offsets of each model's E[X] block (E[XX] block at ex_off[t]-t);
+ *   k_off [T+1] offsets of each model's per-sub-region outputs;
+ *   cpg_off [R+1]; rho_n [ΣN]; d_n [ΣN - R]; sub_off [R+1]; sub_p, sub_q [ΣK]
+ *   logZ [T]; ex [ex_off[T]]; exx [ex_off[T]-T]; log_g [k_off[T]*4] (pm,pp,qm,qp); e_log_g1,e_log_g2,mml,nme [k_off[T]] */
+int cpn_stat_sums_batch(cpn_ctx* ctx, int64_t T, const double* phi, const int64_t* reg_of, const int64_t* ex_off, const int64_t* k_off,
+                        int64_t R, const int64_t* cpg_off, const double* rho_n, const double* d_n,
+                        const int64_t* sub_off, const int64_t* sub_p, const int64_t* sub_q,
+                        double* logZ, double* ex, double* exx, double* log_g,
+                        double* e_log_g1, double* e_log_g2, double* mml, double* nme);
+
+/* get_nls_reg_info!(rs, config)  src/genome_analysis.jl:472-538 — integer, host-only, bit-exact.
+ * Call with sub_st == NULL to obtain K only.  Returns K (number of analysis sub-regions) or -1.      */
+int64_t cpn_nls_reg_info(int64_t chrst, int64_t chrend, int64_t max_size_subreg, const int64_t* cpg_pos, int64_t N,
+                         int64_t* sub_st, int64_t* sub_end, int64_t* sub_p, int64_t* sub_q);
+
+/* comp_cmd(rs1, rs2)  src/statistical_summaries.jl:512-570 for P pairs of fitted models.
+ * Models live in a table of T models (phi_tbl [T*3]; ex_tbl/exx_tbl/nme_tbl are the outputs of
+ * cpn_stat_sums_batch for those models, laid out with the per-model offsets below); each model t belongs to
+ * genomic region reg_of[t] (features rho_n/d_n/sub_* indexed by region as in cpn_stat_sums_batch).
+ *   pair_a, pair_b [P] model indices (both must share the same region); cmd [Σ_pairs K_region] at cmd_off[P+1] */
+int cpn_cmd_batch(cpn_ctx* ctx, int64_t P, const int64_t* pair_a, const int64_t* pair_b,
+                  int64_t T, const double* phi_tbl, const int64_t* reg_of,
+                  const int64_t* ex_off /*[T+1] into ex_tbl; exx at ex_off[t]-t*/, const double* ex_tbl, const double* exx_tbl,
+                  const int64_t* nme_off /*[T+1] into nme_tbl*/, const double* nme_tbl,
+                  int64_t R, const int64_t* cpg_off, const double* rho_n, const double* d_n,
+                  const int64_t* sub_off, const int64_t* sub_p, const int64_t* sub_q,
+                  const int64_t* cmd_off /*[P+1]*/, double* cmd);
+
+/* ---- (e) permutation sweeps ---------------------------------------------------------------------------
+ * unmat_est_reg_test / mat_est_reg_test  src/grp_perm_tests.jl:200-291 / :432-499 for R regions that all
+ * have n1+n2 (unmatched) or n pairs (matched) fitted samples.  Statistic tables are inputs so that the
+ * integer counts are a pure function of them (accumulation order = the reference's, no FMA contraction).
+ *   tbl_off [R+1] offsets (in sub-regions) into the tables; K_r = tbl_off[r+1]-tbl_off[r]
+ *   mml,nme [Σ_r S*K_r] sample-major per region (group 1 samples first); cmd_tbl [Σ_r S*S*K_r], entry
+ *   (i*S+j)*K_r+k valid for i<j;  labelings [P*n1] ascending 1-based ids shared by all regions.
+ *   Outputs per region and sub-region: T [ΣK*3] (tmml,tnme,tcmd), cnt [ΣK*3], pval [ΣK*3] (NaN if P==0)  */
+int cpn_grp_unmat_sweep(cpn_ctx* ctx, int64_t R, int32_t n1, int32_t n2, const int64_t* tbl_off,
+                        const double* mml, const double* nme, const double* cmd_tbl,
+                        const int32_t* labelings, int64_t P, int32_t exact,
+                        double* T, int64_t* cnt, double* pval);
+/* matched: mml1,mml2,nme1,nme2 [Σ_r n*K_r]; js [P] sign words (bit s set = keep sign of pair s);
+ * outputs T [ΣK*2] (tmml,tnme), cnt [ΣK*2], pval [ΣK*2].                                                 */
+int cpn_grp_mat_sweep(cpn_ctx* ctx, int64_t R, int32_t n, const int64_t* tbl_off,
+                      const double* mml1, const double* mml2, const double* nme1, const double* nme2,
+                      const int64_t* js, int64_t P, int32_t exact,
+                      double* T, int64_t* cnt, double* pval);
+/* two-sample p-value counting  src/two_samp_perm_tests.jl:230-258: T_obs [ΣK*3] region-major (tmml,tnme,tcmd
+ * blocks of K_r), T_null [Σ_r P*3*K_r] permutation-major per region; NaN nulls are dropped, >20 valid needed. */
+int cpn_two_samp_pvals(cpn_ctx* ctx, int64_t R, const int64_t* tbl_off, int64_t P, const double* T_obs,
+                       const double* T_null, int32_t exact, int64_t* cnt, int64_t* n_valid, double* pval);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* CPELNANO_B200_H */

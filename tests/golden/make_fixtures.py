@@ -198,10 +198,11 @@ def main():
     np.savez_compressed(f"{OUT}/targeted_example.npz", **fx)
     print("targeted:", len(fx["chrst"]), "regions", len(fx["ex"]), "ex rows", len(fx["mml"]), "mml rows")
 
-    # ---- synthetic-workload layouts: every ≥10-CpG 3 kb region of the targeted BED interval ----
-    part = chr_part_targeted(seq_t, 155510, 255510)
+    # ---- synthetic-workload layouts: every ≥10-CpG 3 kb region of the whole targeted FASTA window ----
+    part_t = chr_part_targeted(seq_t, 155510, 255510)
     theta_set = {(int(a), int(b)) for a, b in zip(fx["chrst"], fx["chrend"])}
-    assert theta_set <= set(part), "theta-file regions must be a subset of the restated partition"
+    assert theta_set <= set(part_t), "theta-file regions must be a subset of the restated partition"
+    part = chr_part_full(seq_t)
     lay = {k: [] for k in ("chrst", "chrend", "cpg_pos", "rho_n", "d_n", "Nl", "rho_l", "d_l")}
     cpg_off, grp_off = [0], [0]
     for a, b in part:
