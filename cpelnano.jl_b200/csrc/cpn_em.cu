@@ -130,51 +130,67 @@ __device__ __forceinline__ void fill_tile(SiteTile& st, int l0, int n, int lane,
 // ---------------------------------------------------------------------------------------------------
 // One forward sweep for the 32 reads of a chunk.  BPOS = (c ≥ 0).  (u,v) below are the source states that
 // enter x'=+1 with weight 1 and t respectively; for c<0 the roles of same/opposite swap.
+constexpr int E_PF = 8;            // emission weights prefetched per lane (register double buffer)
+
 template <bool BPOS>
 __device__ __forceinline__ void estep_chunk(SiteTile& st, int L, int lane, const double* __restrict__ na_g,
                                             const double* __restrict__ nb_g, const double* __restrict__ invd_g,
                                             const double* __restrict__ ewc, double a, double b, double cabs, double out[3]) {
     double fp = 0, fm = 0, gap = 0, gam = 0, gbp = 0, gbm = 0, gcp = 0, gcm = 0, sc = 1.0;
+    const double* ew_lane = ewc + lane;
+    // The loop over groups is a serial dependency chain; the only long-latency operand is the emission weight, so the
+    // next E_PF of them are always in flight while the current E_PF are consumed.
+    double rn[E_PF];
+#pragma unroll
+    for (int u = 0; u < E_PF; ++u) rn[u] = (u < L) ? ew_lane[(size_t)u * 32] : 1.0;
     for (int l0 = 0; l0 < L; l0 += TILE) {
         int n = min(TILE, L - l0);
         __syncwarp();
         fill_tile(st, l0, n, lane, na_g, nb_g, invd_g, a, b, cabs);
         __syncwarp();
-        int j = 0;
-        if (l0 == 0) {
-            double r = ewc[lane];
-            double wp = st.wp[0] * r, wm = st.wm[0], na = st.na[0], nb = st.nb[0];
-            fp = wp; fm = wm;
-            gap = na * wp; gam = -na * wm;
-            gbp = nb * wp; gbm = -nb * wm;
-            gcp = 0.0; gcm = 0.0;
-            sc = cpn_inv_pow2_of(fp + fm);
-            j = 1;
-        }
-#pragma unroll 2
-        for (; j < n; ++j) {
-            double r = ewc[(size_t)(l0 + j) * 32 + lane];
-            double t = st.t[j], na = st.na[j], nb = st.nb[j];
-            double sinvd = BPOS ? st.invd[j] : -st.invd[j];
-            double phiP = (st.wp[j] * r) * sc, phiM = st.wm[j] * sc;
-            double u = BPOS ? fp : fm, v = BPOS ? fm : fp;
-            double Gp = fma(t, v, u), Gm = fma(t, u, v);
-            double ua = BPOS ? gap : gam, va = BPOS ? gam : gap;
-            double ub = BPOS ? gbp : gbm, vb = BPOS ? gbm : gbp;
-            double uc = BPOS ? gcp : gcm, vc = BPOS ? gcm : gcp;
-            double Hap = fma(t, va, ua), Ham = fma(t, ua, va);
-            double Hbp = fma(t, vb, ub), Hbm = fma(t, ub, vb);
-            double Hcp = fma(t, vc, uc), Hcm = fma(t, uc, vc);
-            double Dp = fma(2.0, u, -Gp), Dm = fma(2.0, v, -Gm);     // Σ_x (x x') ψ f, up to the sign in sinvd
-            gap = phiP * fma(na, Gp, Hap);
-            gam = phiM * fma(-na, Gm, Ham);
-            gbp = phiP * fma(nb, Gp, Hbp);
-            gbm = phiM * fma(-nb, Gm, Hbm);
-            gcp = phiP * fma(sinvd, Dp, Hcp);
-            gcm = phiM * fma(sinvd, Dm, Hcm);
-            fp = phiP * Gp;
-            fm = phiM * Gm;
-            sc = cpn_inv_pow2_of(fp + fm);
+        for (int j0 = 0; j0 < n; j0 += E_PF) {
+            double rc[E_PF];
+#pragma unroll
+            for (int u = 0; u < E_PF; ++u) rc[u] = rn[u];
+            const int lnext = l0 + j0 + E_PF;
+#pragma unroll
+            for (int u = 0; u < E_PF; ++u) rn[u] = (lnext + u < L) ? ew_lane[(size_t)(lnext + u) * 32] : 1.0;
+#pragma unroll
+            for (int u = 0; u < E_PF; ++u) {
+                const int j = j0 + u;
+                if (j < n) {
+                    double r = rc[u];
+                    if (l0 + j == 0) {
+                        double wp = st.wp[0] * r, wm = st.wm[0], na = st.na[0], nb = st.nb[0];
+                        fp = wp; fm = wm;
+                        gap = na * wp; gam = -na * wm;
+                        gbp = nb * wp; gbm = -nb * wm;
+                        gcp = 0.0; gcm = 0.0;
+                    } else {
+                        double t = st.t[j], na = st.na[j], nb = st.nb[j];
+                        double sinvd = BPOS ? st.invd[j] : -st.invd[j];
+                        double phiP = (st.wp[j] * r) * sc, phiM = st.wm[j] * sc;
+                        double u_ = BPOS ? fp : fm, v_ = BPOS ? fm : fp;
+                        double Gp = fma(t, v_, u_), Gm = fma(t, u_, v_);
+                        double ua = BPOS ? gap : gam, va = BPOS ? gam : gap;
+                        double ub = BPOS ? gbp : gbm, vb = BPOS ? gbm : gbp;
+                        double uc = BPOS ? gcp : gcm, vc = BPOS ? gcm : gcp;
+                        double Hap = fma(t, va, ua), Ham = fma(t, ua, va);
+                        double Hbp = fma(t, vb, ub), Hbm = fma(t, ub, vb);
+                        double Hcp = fma(t, vc, uc), Hcm = fma(t, uc, vc);
+                        double Dp = fma(2.0, u_, -Gp), Dm = fma(2.0, v_, -Gm);     // Σ_x (x x') ψ f, up to the sign in sinvd
+                        gap = phiP * fma(na, Gp, Hap);
+                        gam = phiM * fma(-na, Gm, Ham);
+                        gbp = phiP * fma(nb, Gp, Hbp);
+                        gbm = phiM * fma(-nb, Gm, Hbm);
+                        gcp = phiP * fma(sinvd, Dp, Hcp);
+                        gcm = phiM * fma(sinvd, Dm, Hcm);
+                        fp = phiP * Gp;
+                        fm = phiM * Gm;
+                    }
+                    sc = cpn_inv_pow2_of(fp + fm);
+                }
+            }
         }
     }
     double inv = 1.0 / (fp + fm);
@@ -673,6 +689,225 @@ __global__ void __launch_bounds__(M_THREADS) k_mstep(int n_items, const int* __r
     if (survive) next_items[base + warp_cnt[w] + __popc(bal & ((1u << lane) - 1))] = inst;
 }
 
+// Analytic-mode M-step with lane-level work stealing.  Every loop trip performs exactly one derivative sweep per busy
+// lane (the expensive, uniform part); the trust-region bookkeeping between sweeps is a small per-lane state machine
+// (NLsolve trust_region_: initial evaluation, then one evaluation per iteration).  A lane whose solve ends takes the
+// next EM instance from a global queue, so the 32 lanes of a warp stay busy regardless of how many solver iterations
+// their instances need.
+struct LaneSolve {
+    const double *na, *nb, *invd;
+    int L, inst, it, evals;
+    bool init_phase;
+    double t0, t1, t2;
+    double x0[3], x[3], xold[3], r[3], J[3][3], d[3], p[3], delta;
+};
+
+__device__ __forceinline__ void ws_next_step(LaneSolve& s) {
+    s.it += 1;
+    dogleg3(s.p, s.r, s.d, s.J, s.delta);
+#pragma unroll
+    for (int i = 0; i < 3; ++i) { s.xold[i] = s.x[i]; s.x[i] += s.p[i]; }
+}
+
+// Consumes F, J evaluated at s.x.  Returns 0 = continue (s.x holds the next trial point), 1 = converged, 2 = not converged.
+__device__ int ws_advance(LaneSolve& s, const double* fval, const double Jn[3][3]) {
+    const double ftol = 1e-3, eta = 1e-4;
+    if (s.init_phase) {
+        s.init_phase = false;
+#pragma unroll
+        for (int i = 0; i < 3; ++i) {
+            s.r[i] = fval[i];
+#pragma unroll
+            for (int j = 0; j < 3; ++j) s.J[i][j] = Jn[i][j];
+        }
+        if (!allfinite3(s.r)) return 2;                     // check_isfinite → exception → em_iter keeps ϕ (:160-172)
+        if (norminf3(fval) <= ftol) return 1;               // converged with 0 iterations
+        if (anynan3(s.x)) return 2;
+#pragma unroll
+        for (int j = 0; j < 3; ++j) {
+            s.d[j] = sqrt(s.J[0][j] * s.J[0][j] + s.J[1][j] * s.J[1][j] + s.J[2][j] * s.J[2][j]);
+            if (s.d[j] == 0.0) s.d[j] = 1.0;
+        }
+        s.delta = wnorm3(s.d, s.x);
+        if (s.delta == 0.0) s.delta = 1.0;
+        s.it = 0;
+        ws_next_step(s);
+        return 0;
+    }
+    double rp[3];
+    matvec3(s.J, s.p, rp);
+#pragma unroll
+    for (int i = 0; i < 3; ++i) rp[i] += s.r[i];
+    double rho = (sumabs2_3(s.r) - sumabs2_3(fval)) / (sumabs2_3(s.r) - sumabs2_3(rp));
+    bool conv = false;
+    if (rho > eta) {
+#pragma unroll
+        for (int i = 0; i < 3; ++i) {
+            s.r[i] = fval[i];
+#pragma unroll
+            for (int j = 0; j < 3; ++j) s.J[i][j] = Jn[i][j];
+        }
+#pragma unroll
+        for (int j = 0; j < 3; ++j) {
+            double nj = sqrt(s.J[0][j] * s.J[0][j] + s.J[1][j] * s.J[1][j] + s.J[2][j] * s.J[2][j]);
+            s.d[j] = fmax(0.1 * s.d[j], nj);
+        }
+        double dx[3] = {s.x[0] - s.xold[0], s.x[1] - s.xold[1], s.x[2] - s.xold[2]};
+        conv = (norminf3(dx) <= 0.0) || (norminf3(s.r) <= ftol);
+    } else {
+#pragma unroll
+        for (int i = 0; i < 3; ++i) s.x[i] -= s.p[i];
+    }
+    if (rho < 0.1) s.delta = s.delta / 2;
+    else if (rho >= 0.9) s.delta = 2 * wnorm3(s.d, s.p);
+    else if (rho >= 0.5) s.delta = fmax(s.delta, 2 * wnorm3(s.d, s.p));
+    bool stopped = anynan3(s.x) || anynan3(fval);
+    if (conv) return 1;
+    if (stopped || s.it >= 20) return 2;
+    ws_next_step(s);
+    return 0;
+}
+
+__global__ void __launch_bounds__(M_THREADS) k_mstep_ws(int n_items, const int* __restrict__ items, int n_init, RegionTables rt, EmState st,
+                                                         int max_em_iters, double amax, double bmax, double cmax, int* __restrict__ queue,
+                                                         unsigned char* __restrict__ alive /*[n_items] by list position*/) {
+    const int lane = threadIdx.x & 31;
+    int pos = -1;
+    const unsigned lt_mask = (1u << lane) - 1;
+    LaneSolve s;
+    bool have = false;
+    s.na = s.nb = s.invd = nullptr; s.L = 0; s.inst = -1; s.it = 0; s.evals = 0; s.init_phase = true;
+    bool drained = false;
+    for (;;) {
+        // ---- take work (warp-aggregated fetch from the global queue)
+        bool need = !have && !drained;
+        unsigned m = __ballot_sync(0xffffffffu, need);
+        if (m) {
+            int leader = __ffs(m) - 1, base = 0;
+            if (lane == leader) base = atomicAdd(queue, __popc(m));
+            base = __shfl_sync(0xffffffffu, base, leader);
+            if (need) {
+                int item = base + __popc(m & lt_mask);
+                if (item < n_items) {
+                    int inst = items ? items[item] : item;
+                    pos = item;
+                    int64_t r = inst / n_init;
+                    int64_t g0 = rt.grp_off[r];
+                    s.na = rt.na + g0; s.nb = rt.nb + g0; s.invd = rt.invd + g0;
+                    s.L = (int)(rt.grp_off[r + 1] - g0);
+                    double Mr = (double)(rt.read_off[r + 1] - rt.read_off[r]);
+                    int64_t NI = st.NI;
+                    s.t0 = st.ES[inst] / Mr; s.t1 = st.ES[NI + inst] / Mr; s.t2 = st.ES[2 * NI + inst] / Mr;
+                    s.inst = inst; s.evals = 0; s.it = 0; s.init_phase = true;
+#pragma unroll
+                    for (int i = 0; i < 3; ++i) { s.x0[i] = st.phi[i * NI + inst]; s.x[i] = s.x0[i]; }
+                    have = true;
+                } else drained = true;
+            }
+        }
+        if (!__any_sync(0xffffffffu, have)) break;
+        // ---- one derivative sweep at the current point of every busy lane
+        if (have) {
+            double g[3], H[6], fval[3], Jn[3][3];
+            eval_grad_hess(s.na, s.nb, s.invd, s.L, s.x[0], s.x[1], s.x[2], g, H);
+            s.evals += 1;
+            fval[0] = g[0] - s.t0; fval[1] = g[1] - s.t1; fval[2] = g[2] - s.t2;
+            Jn[0][0] = H[0]; Jn[0][1] = H[1]; Jn[0][2] = H[2];
+            Jn[1][0] = H[1]; Jn[1][1] = H[3]; Jn[1][2] = H[4];
+            Jn[2][0] = H[2]; Jn[2][1] = H[4]; Jn[2][2] = H[5];
+            int code = ws_advance(s, fval, Jn);
+            if (code != 0) {
+                // em_iter tail (:172-181) + em_inst bookkeeping (:327-341)
+                double nx[3];
+                if (code == 2) { nx[0] = s.x0[0]; nx[1] = s.x0[1]; nx[2] = s.x0[2]; }
+                else {
+                    nx[0] = fmax(-amax, fmin(s.x[0], amax));
+                    nx[1] = fmax(-bmax, fmin(s.x[1], bmax));
+                    nx[2] = fmax(-cmax, fmin(s.x[2], cmax));
+                }
+                double d0 = s.x0[0] - nx[0], d1 = s.x0[1] - nx[1], d2 = s.x0[2] - nx[2];
+                bool cv = sqrt(d0 * d0 + d1 * d1 + d2 * d2) <= 3.0e-2;
+                int inst = s.inst;
+                int64_t NI = st.NI;
+                int i = st.iter[inst];
+                bool hit = i >= max_em_iters;
+                i += 1;
+                st.phi[inst] = nx[0]; st.phi[NI + inst] = nx[1]; st.phi[2 * NI + inst] = nx[2];
+                st.iter[inst] = i;
+                st.cnt_em[inst] += 1; st.cnt_sol[inst] += s.it; st.cnt_eval[inst] += s.evals;
+                bool done = cv || hit;
+                if (done) st.status[inst] = (cv && i > 2) ? 1 : 2;
+                alive[pos] = done ? 0 : 1;
+                have = false;
+            }
+        }
+    }
+}
+
+// Order-preserving compaction of the active list (keeps instances sorted by chain length so that the lanes of an
+// M-step warp walk chains of similar length): per-block counts → scan of the counts → scatter.
+constexpr int CP_THREADS = 256, CP_ITEMS = 4, CP_TILE = CP_THREADS * CP_ITEMS;
+
+__global__ void __launch_bounds__(CP_THREADS) k_compact_count(int n, const unsigned char* __restrict__ alive, int* __restrict__ blk_cnt) {
+    __shared__ int wsum[CP_THREADS / 32];
+    int base = blockIdx.x * CP_TILE + threadIdx.x * CP_ITEMS;
+    int c = 0;
+#pragma unroll
+    for (int k = 0; k < CP_ITEMS; ++k) c += (base + k < n) ? alive[base + k] : 0;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) c += __shfl_xor_sync(0xffffffffu, c, o);
+    if ((threadIdx.x & 31) == 0) wsum[threadIdx.x >> 5] = c;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        int t = 0;
+        for (int k = 0; k < CP_THREADS / 32; ++k) t += wsum[k];
+        blk_cnt[blockIdx.x] = t;
+    }
+}
+__global__ void __launch_bounds__(1024) k_compact_scan(int nblk, int* __restrict__ blk_cnt /*in: counts, out: exclusive offsets*/,
+                                                        int* __restrict__ total) {
+    __shared__ int sm[1024];
+    __shared__ int carry;
+    if (threadIdx.x == 0) carry = 0;
+    __syncthreads();
+    for (int b0 = 0; b0 < nblk; b0 += 1024) {
+        int i = b0 + threadIdx.x;
+        int v = (i < nblk) ? blk_cnt[i] : 0;
+        sm[threadIdx.x] = v;
+        __syncthreads();
+        for (int o = 1; o < 1024; o <<= 1) {
+            int add = (threadIdx.x >= o) ? sm[threadIdx.x - o] : 0;
+            __syncthreads();
+            sm[threadIdx.x] += add;
+            __syncthreads();
+        }
+        if (i < nblk) blk_cnt[i] = carry + sm[threadIdx.x] - v;
+        __syncthreads();
+        if (threadIdx.x == 0) carry += sm[1023];
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) *total = carry;
+}
+__global__ void __launch_bounds__(CP_THREADS) k_compact_scatter(int n, const unsigned char* __restrict__ alive, const int* __restrict__ items,
+                                                                 const int* __restrict__ blk_off, int* __restrict__ out) {
+    __shared__ int wsum[CP_THREADS / 32];
+    int base = blockIdx.x * CP_TILE + threadIdx.x * CP_ITEMS;
+    int f[CP_ITEMS], c = 0;
+#pragma unroll
+    for (int k = 0; k < CP_ITEMS; ++k) { f[k] = (base + k < n) ? alive[base + k] : 0; c += f[k]; }
+    int incl = c;
+    int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) { int v = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += v; }
+    if (lane == 31) wsum[w] = incl;
+    __syncthreads();
+    int woff = 0;
+    for (int k = 0; k < w; ++k) woff += wsum[k];
+    int dst = blk_off[blockIdx.x] + woff + incl - c;
+#pragma unroll
+    for (int k = 0; k < CP_ITEMS; ++k) if (f[k]) out[dst++] = items[base + k];
+}
+
 // Single solve for the test hook cpn_mstep_batch.
 __global__ void k_mstep_once(int64_t R, RegionTables rt, const int64_t* __restrict__ n_reads, const double* __restrict__ ES,
                              const double* __restrict__ phi_init, int mode, double* __restrict__ sol_out, int* __restrict__ conv_out,
@@ -853,7 +1088,14 @@ int fit_impl(cpn_ctx* ctx, bool on_device, int64_t R, const int64_t* grp_off, co
         CPN_CUDA(ctx, phi.alloc(3 * NI, s)); CPN_CUDA(ctx, ES.alloc(3 * NI, s)); CPN_CUDA(ctx, Qs.alloc(NI, s));
         CPN_CUDA(ctx, iter.alloc(NI, s)); CPN_CUDA(ctx, stat.alloc(NI, s)); CPN_CUDA(ctx, c_em.alloc(NI, s));
         CPN_CUDA(ctx, c_sol.alloc(NI, s)); CPN_CUDA(ctx, c_ev.alloc(NI, s));
-        CPN_CUDA(ctx, items_a.alloc(NI, s)); CPN_CUDA(ctx, items_b.alloc(NI, s)); CPN_CUDA(ctx, n_next.alloc(1, s));
+        CPN_CUDA(ctx, items_a.alloc(NI, s)); CPN_CUDA(ctx, items_b.alloc(NI, s)); CPN_CUDA(ctx, n_next.alloc(2, s));
+        DevBuf<unsigned char> alive;
+        DevBuf<int> blk_cnt;
+        CPN_CUDA(ctx, alive.alloc(NI, s));
+        CPN_CUDA(ctx, blk_cnt.alloc((NI + CP_TILE - 1) / CP_TILE, s));
+        int ws_blocks_per_sm = 1;
+        CPN_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ws_blocks_per_sm, k_mstep_ws, M_THREADS, 0));
+        if (ws_blocks_per_sm < 1) ws_blocks_per_sm = 1;
         // Regions ordered by group count (counting sort) so the 32 lanes of an M-step warp walk chains of
         // similar length.
         std::vector<int> h_order(R);
@@ -873,12 +1115,24 @@ int fit_impl(cpn_ctx* ctx, bool on_device, int64_t R, const int64_t* grp_off, co
         int* cur = items_a.p;
         int* nxt = items_b.p;
         for (int it = 0; it < max_em_iters && n_active > 0; ++it) {
-            CPN_CUDA(ctx, cudaMemsetAsync(n_next.p, 0, sizeof(int), s));
+            CPN_CUDA(ctx, cudaMemsetAsync(n_next.p, 0, 2 * sizeof(int), s));     // [0] survivors, [1] work-queue head
             { KTimer kt(ctx, CPN_K_ESTEP);
               k_estep<<<blocks_for(n_active, E_WARPS), E_WARPS * 32, 0, s>>>(n_active, cur, n_init, pk.rt, phi.p, NI, ES.p); }
-            { KTimer kt(ctx, CPN_K_MSTEP);
-              k_mstep<<<blocks_for(n_active, M_THREADS), M_THREADS, 0, s>>>(n_active, cur, n_init, pk.rt, st, max_em_iters, amax, bmax, cmax,
-                                                                             mstep_mode, nxt, n_next.p); }
+            if (mstep_mode == CPN_MSTEP_ANALYTIC) {
+                unsigned grid = std::min<unsigned>(blocks_for(n_active, M_THREADS), (unsigned)(ctx->sm_count * ws_blocks_per_sm));
+                KTimer kt(ctx, CPN_K_MSTEP);
+                k_mstep_ws<<<grid, M_THREADS, 0, s>>>(n_active, cur, n_init, pk.rt, st, max_em_iters, amax, bmax, cmax, n_next.p + 1, alive.p);
+            }
+            if (mstep_mode == CPN_MSTEP_ANALYTIC) {
+                int nblk = (n_active + CP_TILE - 1) / CP_TILE;
+                { KTimer kt(ctx, CPN_K_PREP); k_compact_count<<<nblk, CP_THREADS, 0, s>>>(n_active, alive.p, blk_cnt.p); }
+                { KTimer kt(ctx, CPN_K_PREP); k_compact_scan<<<1, 1024, 0, s>>>(nblk, blk_cnt.p, n_next.p); }
+                { KTimer kt(ctx, CPN_K_PREP); k_compact_scatter<<<nblk, CP_THREADS, 0, s>>>(n_active, alive.p, cur, blk_cnt.p, nxt); }
+            } else {
+                KTimer kt(ctx, CPN_K_MSTEP);
+                k_mstep<<<blocks_for(n_active, M_THREADS), M_THREADS, 0, s>>>(n_active, cur, n_init, pk.rt, st, max_em_iters, amax, bmax, cmax,
+                                                                               mstep_mode, nxt, n_next.p);
+            }
             CPN_CUDA(ctx, cudaMemcpyAsync(&n_active, n_next.p, sizeof(int), cudaMemcpyDeviceToHost, s));
             CPN_CUDA(ctx, cudaStreamSynchronize(s));
             std::swap(cur, nxt);
