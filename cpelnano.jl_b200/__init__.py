@@ -23,7 +23,8 @@ from .capi import Library, CpnError, lib_path, MSTEP_FD, MSTEP_ANALYTIC   # noqa
 from .host import (CpelNanoConfig, RegStruct, Engine, get_phihat, rscle_grp_mod, get_nls_reg_info, get_stat_sums,   # noqa: F401
                    comp_cmd, unmat_est_reg_test, mat_est_reg_test, pmap_two_samp_null_stats, analyze_regions, default_engine)
 from . import simulations   # noqa: F401
+from . import sharding      # noqa: F401
 
 __all__ = ["Library", "CpnError", "Engine", "CpelNanoConfig", "RegStruct", "get_phihat", "rscle_grp_mod", "get_nls_reg_info",
            "get_stat_sums", "comp_cmd", "unmat_est_reg_test", "mat_est_reg_test", "pmap_two_samp_null_stats", "analyze_regions",
-           "simulations", "default_engine", "MSTEP_FD", "MSTEP_ANALYTIC"]
+           "simulations", "sharding", "default_engine", "MSTEP_FD", "MSTEP_ANALYTIC"]

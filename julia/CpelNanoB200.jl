@@ -1,0 +1,128 @@
+# CpelNanoB200.jl — ccall shim that routes CpelNano's estimation hot path to libcpelnano_b200.so.
+#
+# Delivered UNTESTED BY EXECUTION: this build image has no Julia.  The executable proof of the ABI is the Python host
+# (cpelnano.jl_b200/host.py) and tests/, which bind exactly the same symbols with the same argument order.
+#
+# Usage inside the package (after `include("nanopore.jl")` in src/CpelNano.jl):
+#     include("CpelNanoB200.jl")
+#     CpelNanoB200.enable!("/path/to/libcpelnano_b200.so"; device=0)
+# which redefines get_ϕhat!, get_stat_sums!, comp_cmd and replaces the pmap body of analyze_nano by one
+# cpn_analyze_batch call per chromosome.  Config struct, entry points and output files are unchanged.
+module CpelNanoB200
+
+using ..CpelNano: RegStruct, CpelNanoConfig, MethCallCpgGrp, AnalysisRegions, get_grp_info!, get_calls!, get_ave_depth,
+                  perc_gprs_obs, rscle_grp_mod!, gen_ϕ0s, print_log
+import ..CpelNano
+
+const LIB = Ref{String}("libcpelnano_b200")
+const CTX = Ref{Ptr{Cvoid}}(C_NULL)
+
+function enable!(lib::String; device::Int=0)
+    LIB[] = lib
+    ctx = Ref{Ptr{Cvoid}}(C_NULL)
+    rc = ccall((:cpn_create, LIB[]), Cint, (Cint, Ref{Ptr{Cvoid}}), device, ctx)
+    rc == 0 || error("cpn_create failed ($rc): no sm_100 GPU; there is no CPU fallback")
+    CTX[] = ctx[]
+    return nothing
+end
+
+check(rc) = rc == 0 || error(unsafe_string(ccall((:cpn_last_error, LIB[]), Cstring, (Ptr{Cvoid},), CTX[])))
+
+# ---- packing -------------------------------------------------------------------------------------------------
+# calls::Vector{Vector{MethCallCpgGrp}} (structures.jl:121-128,168) → read-major doubles, NaN = not observed
+function pack_calls(rss::Vector{RegStruct})
+    n = sum(rs -> rs.m * rs.L, rss)
+    lu = Vector{Float64}(undef, n); lm = Vector{Float64}(undef, n)
+    k = 0
+    for rs in rss, call in rs.calls, c in call
+        k += 1
+        lu[k] = c.obs ? c.log_pyx_u : NaN
+        lm[k] = c.obs ? c.log_pyx_m : NaN
+    end
+    read_off = Int64[0; cumsum([rs.m for rs in rss])]
+    return read_off, lu, lm
+end
+pack_groups(rss) = (Int64[0; cumsum([rs.L for rs in rss])], Float64.(vcat([rs.Nl for rs in rss]...)),
+                    Float64.(vcat([rs.ρl for rs in rss]...)), Float64.(vcat([rs.dl for rs in rss]...)))
+
+# get_nls_reg_info!(rs, config)  genome_analysis.jl:472
+function nls_reg_info!(rs::RegStruct, config::CpelNanoConfig)
+    K = ccall((:cpn_nls_reg_info, LIB[]), Int64, (Int64, Int64, Int64, Ptr{Int64}, Int64, Ptr{Int64}, Ptr{Int64}, Ptr{Int64}, Ptr{Int64}),
+              rs.chrst, rs.chrend, config.max_size_subreg, rs.cpg_pos, length(rs.cpg_pos), C_NULL, C_NULL, C_NULL, C_NULL)
+    st = Vector{Int64}(undef, K); en = similar(st); p = similar(st); q = similar(st)
+    ccall((:cpn_nls_reg_info, LIB[]), Int64, (Int64, Int64, Int64, Ptr{Int64}, Int64, Ptr{Int64}, Ptr{Int64}, Ptr{Int64}, Ptr{Int64}),
+          rs.chrst, rs.chrend, config.max_size_subreg, rs.cpg_pos, length(rs.cpg_pos), st, en, p, q)
+    rs.nls_rgs = AnalysisRegions([st[k]:en[k] for k = 1:K], [p[k]:q[k] for k = 1:K])
+    return p, q
+end
+
+# ---- get_ϕhat!(rs, config)  em_algorithm.jl:371 — batched --------------------------------------------------------
+function get_ϕhat_batch!(rss::Vector{RegStruct}, config::CpelNanoConfig)
+    R = length(rss)
+    grp_off, Nl, ρl, dl = pack_groups(rss)
+    read_off, lu, lm = pack_calls(rss)
+    ϕ0 = Float64.(vcat([vcat(gen_ϕ0s(config.max_em_init)...) for _ in 1:R]...))      # host RNG keeps ownership of the starts
+    ϕhat = Vector{Float64}(undef, 3R); Q = Vector{Float64}(undef, R); status = Vector{Int32}(undef, R)
+    GC.@preserve grp_off Nl ρl dl read_off lu lm ϕ0 ϕhat Q status begin
+        check(ccall((:cpn_fit_batch, LIB[]), Cint,
+            (Ptr{Cvoid}, Int64, Ptr{Int64}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Ptr{Int64}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64},
+             Int32, Int32, Float64, Float64, Float64, Int32, Ptr{Float64}, Ptr{Float64}, Ptr{Int32}, Ptr{Int64}, Ptr{Float64}, Ptr{Float64}),
+            CTX[], R, grp_off, Nl, ρl, dl, read_off, lu, lm, ϕ0, config.max_em_init, config.max_em_iters,
+            CpelNano.AMAX, CpelNano.BMAX, CpelNano.CMAX, 1, ϕhat, Q, status, C_NULL, C_NULL, C_NULL))
+    end
+    for (r, rs) in enumerate(rss)
+        rs.ϕhat = status[r] >= 0 ? ϕhat[(3r - 2):(3r)] : Vector{Float64}()          # rs.ϕhat = [] when no start converged (:385)
+    end
+    return nothing
+end
+CpelNano.get_ϕhat!(rs::RegStruct, config::CpelNanoConfig) = get_ϕhat_batch!([rs], config)
+
+# ---- get_stat_sums!(rs, config)  statistical_summaries.jl:470 — batched ---------------------------------------------
+function get_stat_sums_batch!(rss::Vector{RegStruct}, config::CpelNanoConfig)
+    T = length(rss)
+    pq = [nls_reg_info!(rs, config) for rs in rss]
+    cpg_off = Int64[0; cumsum([rs.N for rs in rss])]; sub_off = Int64[0; cumsum([length(x[1]) for x in pq])]
+    ρn = Float64.(vcat([rs.ρl for rs in rss]...)); dn = Float64.(vcat([rs.dl for rs in rss]...))       # after rscle_grp_mod!
+    sub_p = vcat([x[1] for x in pq]...); sub_q = vcat([x[2] for x in pq]...)
+    ϕ = Float64.(vcat([rs.ϕhat for rs in rss]...))
+    sN, sK = cpg_off[end], sub_off[end]
+    logZ = Vector{Float64}(undef, T); ex = Vector{Float64}(undef, sN); exx = Vector{Float64}(undef, sN - T)
+    lg = Vector{Float64}(undef, 4sK); e1 = Vector{Float64}(undef, sK); e2 = similar(e1); mml = similar(e1); nme = similar(e1)
+    GC.@preserve ϕ cpg_off ρn dn sub_off sub_p sub_q logZ ex exx lg e1 e2 mml nme begin
+        check(ccall((:cpn_stat_sums_batch, LIB[]), Cint,
+            (Ptr{Cvoid}, Int64, Ptr{Float64}, Ptr{Int64}, Ptr{Int64}, Ptr{Int64}, Int64, Ptr{Int64}, Ptr{Float64}, Ptr{Float64}, Ptr{Int64},
+             Ptr{Int64}, Ptr{Int64}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}),
+            CTX[], T, ϕ, C_NULL, C_NULL, C_NULL, T, cpg_off, ρn, dn, sub_off, sub_p, sub_q, logZ, ex, exx, lg, e1, e2, mml, nme))
+    end
+    for (t, rs) in enumerate(rss)
+        n = (cpg_off[t] + 1):cpg_off[t + 1]; k = (sub_off[t] + 1):sub_off[t + 1]
+        rs.logZ = logZ[t]; rs.exps.ex = ex[n]; rs.exps.exx = exx[(cpg_off[t] - t + 2):(cpg_off[t + 1] - t)]
+        rs.exps.log_g1 = e1[k]; rs.exps.log_g2 = e2[k]; rs.mml = mml[k]; rs.nme = nme[k]
+        rs.tm.log_gs.pm = lg[4 .* k .- 3]; rs.tm.log_gs.pp = lg[4 .* k .- 2]; rs.tm.log_gs.qm = lg[4 .* k .- 1]; rs.tm.log_gs.qp = lg[4 .* k]
+    end
+    return nothing
+end
+CpelNano.get_stat_sums!(rs::RegStruct, config::CpelNanoConfig) = get_stat_sums_batch!([rs], config)
+
+# ---- batch point: replaces `pmap(x -> pmap_analyze_reg(x, chr, nano, fa_rec, config), chr_part)`  nanopore.jl:406 -----
+function analyze_chr(chr_part, chr, nano, fa_rec, config::CpelNanoConfig)
+    rss = RegStruct[]
+    for reg_int in chr_part                                   # host side of pmap_analyze_reg (nanopore.jl:296-326), unchanged
+        rs = RegStruct(); rs.chr = chr; rs.chrst = minimum(reg_int); rs.chrend = maximum(reg_int)
+        get_grp_info!(rs, fa_rec, config.min_grp_dist)
+        push!(rss, rs)
+        length(rs.cpg_pos) > 9 || continue
+        get_calls!(rs, nano, config)
+    end
+    keep = [rs for rs in rss if length(rs.cpg_pos) > 9 && rs.m > 0 && get_ave_depth(rs) >= config.min_cov &&
+                                perc_gprs_obs(rs) >= 0.66 && rs.L > 1]
+    isempty(keep) && return rss
+    get_ϕhat_batch!(keep, config)
+    fitted = [rs for rs in keep if length(rs.ϕhat) > 0]
+    foreach(rscle_grp_mod!, fitted)
+    isempty(fitted) || get_stat_sums_batch!(fitted, config)
+    for rs in fitted; rs.proc = true; end
+    return rss                                                # → write_output(rss, config), unchanged
+end
+
+end # module
