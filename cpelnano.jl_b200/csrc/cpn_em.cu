@@ -29,13 +29,21 @@ namespace {
 constexpr int TILE = 128;          // groups staged per shared-memory tile
 constexpr int E_WARPS = 4;         // warps (EM instances) per E-step block
 constexpr int M_THREADS = 128;     // lanes (EM instances) per M-step block
+#ifndef WS_BLOCKS
+#define WS_BLOCKS 4                 // resident M-step blocks per SM the register budget is tuned for
+#endif
 constexpr double LLR_CLAMP = 300.0;
 constexpr double CBRT_EPS = 6.0554544523933395e-6;
+
+// One record per CpG group for the M-step sweep (ϕ-independent): N_l, N_lρ_l, 1/d and 1/d² of the coupling INTO the group
+// (0 for the first group), and the products N², N·Nρ, (Nρ)².  64 bytes → two 32-byte vector loads, prefetched one group ahead.
+struct __align__(64) SweepSite { double na, nb, id, id2, na2, nanb, nb2, pad; };
 
 struct RegionTables {
     // per group (offsets grp_off): N_l, N_l·ρ_l and 1/d_l (coupling l→l+1; entry L-1 unused)
     const int64_t* grp_off;
     const double *na, *nb, *invd;
+    const SweepSite* sq;       // per group: everything the second-order sweep of the M-step needs, one 64-byte record
     // emission likelihood ratios r = exp(log p(y|+1) − log p(y|−1)), 1 for unobserved / padding lanes
     const int64_t* read_off;   // [R+1]
     const int64_t* ew_off;     // [R] start of the region's block: [chunk][l][32]
@@ -43,8 +51,12 @@ struct RegionTables {
     const double *ew, *rb;
 };
 
+// Per-group potentials of one EM instance, staged in shared memory as three 16-byte pairs so that a chain step reads
+// them with three LDS.128 (all lanes read the same address: broadcast).
 struct SiteTile {
-    double wm[TILE], wp[TILE], t[TILE], na[TILE], nb[TILE], invd[TILE];
+    double2 w[TILE];     // (φ(−1), φ(+1)) relative to max(φ)
+    double2 tn[TILE];    // (t = ψ(opposite)/ψ(aligned) for |β| into this group, N_l)
+    double2 bd[TILE];    // (N_l·ρ_l, ±1/d_l of the coupling into this group; sign = sign(c))
 };
 
 // ---------------------------------------------------------------------------------------------------
@@ -53,7 +65,7 @@ struct SiteTile {
 // link_functions.jl:16-25 inputs: α_l = a·N_l + b·(N_l ρ_l), β_l = c·(1/d_l)
 __global__ void k_prep_sites(int64_t R, const int64_t* __restrict__ grp_off, const double* __restrict__ Nl,
                              const double* __restrict__ rho, const double* __restrict__ dl, double* __restrict__ na,
-                             double* __restrict__ nb, double* __restrict__ invd) {
+                             double* __restrict__ nb, double* __restrict__ invd, SweepSite* __restrict__ sq) {
     int64_t warp = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5;
     int lane = threadIdx.x & 31;
     if (warp >= R) return;
@@ -61,9 +73,15 @@ __global__ void k_prep_sites(int64_t R, const int64_t* __restrict__ grp_off, con
     int64_t L = g1 - g0;
     for (int64_t l = lane; l < L; l += 32) {
         double n = Nl[g0 + l];
+        double b = n * rho[g0 + l];
+        double id = (l < L - 1) ? 1.0 / dl[g0 - warp + l] : 0.0;
         na[g0 + l] = n;
-        nb[g0 + l] = n * rho[g0 + l];
-        invd[g0 + l] = (l < L - 1) ? 1.0 / dl[g0 - warp + l] : 0.0;
+        nb[g0 + l] = b;
+        invd[g0 + l] = id;
+        double idin = (l > 0) ? 1.0 / dl[g0 - warp + l - 1] : 0.0;
+        SweepSite ss;
+        ss.na = n; ss.nb = b; ss.id = idin; ss.id2 = idin * idin; ss.na2 = n * n; ss.nanb = n * b; ss.nb2 = b * b; ss.pad = 0.0;
+        sq[g0 + l] = ss;
     }
 }
 
@@ -108,20 +126,18 @@ __global__ void k_prep_emis(int64_t R, const int64_t* __restrict__ grp_off, cons
 // ---------------------------------------------------------------------------------------------------
 __device__ __forceinline__ void fill_tile(SiteTile& st, int l0, int n, int lane, const double* __restrict__ na_g,
                                           const double* __restrict__ nb_g, const double* __restrict__ invd_g, double a, double b,
-                                          double cabs) {
+                                          double cabs, bool bpos) {
     for (int j = lane; j < n; j += 32) {
         int l = l0 + j;
         double na = na_g[l], nb = nb_g[l];
         double alpha = fma(b, nb, a * na);
-        double e = exp(-2.0 * fabs(alpha));
-        bool pos = alpha >= 0.0;
-        st.wm[j] = pos ? e : 1.0;      // φ(−1) relative to max(φ)
-        st.wp[j] = pos ? 1.0 : e;      // φ(+1) relative to max(φ)
-        st.na[j] = na;
-        st.nb[j] = nb;
+        double e = cpn_exp_neg(-2.0 * fabs(alpha));
+        bool pos = __double2hiint(alpha) >= 0;
+        st.w[j] = make_double2(pos ? e : 1.0, pos ? 1.0 : e);
         double id = (l > 0) ? invd_g[l - 1] : 0.0;
-        st.invd[j] = id;
-        st.t[j] = exp(-2.0 * cabs * id);   // ψ(opposite)/ψ(aligned) for |β|
+        // group 0 has no incoming coupling: t = 0 makes the generic step reproduce f = φ_0 from the all-ones message
+        st.tn[j] = make_double2((l > 0) ? cpn_exp_neg(-2.0 * cabs * id) : 0.0, na);
+        st.bd[j] = make_double2(nb, bpos ? id : -id);
     }
 }
 
@@ -132,71 +148,84 @@ __device__ __forceinline__ void fill_tile(SiteTile& st, int l0, int n, int lane,
 // enter x'=+1 with weight 1 and t respectively; for c<0 the roles of same/opposite swap.
 constexpr int E_PF = 8;            // emission weights prefetched per lane (register double buffer)
 
+struct EState { double fp, fm, gap, gam, gbp, gbm, gcp, gcm; };
+
+// One chain step for one read.  (u,v) are the source states entering x'=+1 with weight 1 and t; for c<0 the roles of
+// aligned/opposite swap (BPOS=false).  `sc` is the power-of-two rescale computed from an earlier message.
+template <bool BPOS>
+__device__ __forceinline__ void estep_site(EState& s, const SiteTile& st, int j, double r, double sc) {
+    const double2 w = st.w[j], tn = st.tn[j], bd = st.bd[j];
+    const double t = tn.x, na = tn.y, nb = bd.x, sinvd = bd.y;
+    double phiP = (w.y * r) * sc, phiM = w.x * sc;
+    double u = BPOS ? s.fp : s.fm, v = BPOS ? s.fm : s.fp;
+    double Gp = fma(t, v, u), Gm = fma(t, u, v);
+    double ua = BPOS ? s.gap : s.gam, va = BPOS ? s.gam : s.gap;
+    double ub = BPOS ? s.gbp : s.gbm, vb = BPOS ? s.gbm : s.gbp;
+    double uc = BPOS ? s.gcp : s.gcm, vc = BPOS ? s.gcm : s.gcp;
+    double Hap = fma(t, va, ua), Ham = fma(t, ua, va);
+    double Hbp = fma(t, vb, ub), Hbm = fma(t, ub, vb);
+    double Hcp = fma(t, vc, uc), Hcm = fma(t, uc, vc);
+    double Dp = fma(2.0, u, -Gp), Dm = fma(2.0, v, -Gm);          // Σ_x (x x') ψ f, up to the sign carried by sinvd
+    s.gap = phiP * fma(na, Gp, Hap);
+    s.gam = phiM * fma(-na, Gm, Ham);
+    s.gbp = phiP * fma(nb, Gp, Hbp);
+    s.gbm = phiM * fma(-nb, Gm, Hbm);
+    s.gcp = phiP * fma(sinvd, Dp, Hcp);
+    s.gcm = phiM * fma(sinvd, Dm, Hcm);
+    s.fp = phiP * Gp;
+    s.fm = phiM * Gm;
+}
+
+// Forward sweep of the conditional chain for the 32 reads of a chunk, carrying the tangents (∂a,∂b,∂c).
+// Groups are processed E_PF at a time: the emission weights of the next E_PF groups are in flight (registers) while the
+// current ones are consumed; the message is rescaled every second group (|LLR| ≤ 300 keeps two steps inside the
+// double range).
 template <bool BPOS>
 __device__ __forceinline__ void estep_chunk(SiteTile& st, int L, int lane, const double* __restrict__ na_g,
                                             const double* __restrict__ nb_g, const double* __restrict__ invd_g,
                                             const double* __restrict__ ewc, double a, double b, double cabs, double out[3]) {
-    double fp = 0, fm = 0, gap = 0, gam = 0, gbp = 0, gbm = 0, gcp = 0, gcm = 0, sc = 1.0;
-    const double* ew_lane = ewc + lane;
-    // The loop over groups is a serial dependency chain; the only long-latency operand is the emission weight, so the
-    // next E_PF of them are always in flight while the current E_PF are consumed.
+    EState s{1.0, 1.0, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0};
+    double sc = 1.0;
+    const double* p = ewc + lane;                       // emission weight of (group l, this lane) at p[l*32]
+    const int Lfull = L & ~(E_PF - 1);
     double rn[E_PF];
+    if (Lfull > 0) {
 #pragma unroll
-    for (int u = 0; u < E_PF; ++u) rn[u] = (u < L) ? ew_lane[(size_t)u * 32] : 1.0;
+        for (int u = 0; u < E_PF; ++u) rn[u] = p[u * 32];
+    }
     for (int l0 = 0; l0 < L; l0 += TILE) {
-        int n = min(TILE, L - l0);
+        const int n = min(TILE, L - l0);
         __syncwarp();
-        fill_tile(st, l0, n, lane, na_g, nb_g, invd_g, a, b, cabs);
+        fill_tile(st, l0, n, lane, na_g, nb_g, invd_g, a, b, cabs, BPOS);
         __syncwarp();
-        for (int j0 = 0; j0 < n; j0 += E_PF) {
+        const int nfull = n & ~(E_PF - 1);
+        for (int j0 = 0; j0 < nfull; j0 += E_PF) {
             double rc[E_PF];
 #pragma unroll
             for (int u = 0; u < E_PF; ++u) rc[u] = rn[u];
-            const int lnext = l0 + j0 + E_PF;
+            p += E_PF * 32;
+            if (l0 + j0 + E_PF < Lfull) {
 #pragma unroll
-            for (int u = 0; u < E_PF; ++u) rn[u] = (lnext + u < L) ? ew_lane[(size_t)(lnext + u) * 32] : 1.0;
+                for (int u = 0; u < E_PF; ++u) rn[u] = p[u * 32];
+            }
 #pragma unroll
             for (int u = 0; u < E_PF; ++u) {
-                const int j = j0 + u;
-                if (j < n) {
-                    double r = rc[u];
-                    if (l0 + j == 0) {
-                        double wp = st.wp[0] * r, wm = st.wm[0], na = st.na[0], nb = st.nb[0];
-                        fp = wp; fm = wm;
-                        gap = na * wp; gam = -na * wm;
-                        gbp = nb * wp; gbm = -nb * wm;
-                        gcp = 0.0; gcm = 0.0;
-                    } else {
-                        double t = st.t[j], na = st.na[j], nb = st.nb[j];
-                        double sinvd = BPOS ? st.invd[j] : -st.invd[j];
-                        double phiP = (st.wp[j] * r) * sc, phiM = st.wm[j] * sc;
-                        double u_ = BPOS ? fp : fm, v_ = BPOS ? fm : fp;
-                        double Gp = fma(t, v_, u_), Gm = fma(t, u_, v_);
-                        double ua = BPOS ? gap : gam, va = BPOS ? gam : gap;
-                        double ub = BPOS ? gbp : gbm, vb = BPOS ? gbm : gbp;
-                        double uc = BPOS ? gcp : gcm, vc = BPOS ? gcm : gcp;
-                        double Hap = fma(t, va, ua), Ham = fma(t, ua, va);
-                        double Hbp = fma(t, vb, ub), Hbm = fma(t, ub, vb);
-                        double Hcp = fma(t, vc, uc), Hcm = fma(t, uc, vc);
-                        double Dp = fma(2.0, u_, -Gp), Dm = fma(2.0, v_, -Gm);     // Σ_x (x x') ψ f, up to the sign in sinvd
-                        gap = phiP * fma(na, Gp, Hap);
-                        gam = phiM * fma(-na, Gm, Ham);
-                        gbp = phiP * fma(nb, Gp, Hbp);
-                        gbm = phiM * fma(-nb, Gm, Hbm);
-                        gcp = phiP * fma(sinvd, Dp, Hcp);
-                        gcm = phiM * fma(sinvd, Dm, Hcm);
-                        fp = phiP * Gp;
-                        fm = phiM * Gm;
-                    }
-                    sc = cpn_inv_pow2_of(fp + fm);
-                }
+                estep_site<BPOS>(s, st, j0 + u, rc[u], sc);
+                if (u & 1) sc = cpn_inv_pow2_of(s.fp + s.fm); else sc = 1.0;
             }
         }
+        // tail of the chain (fewer than E_PF groups left): p already points at its first group
+        for (int j = nfull; j < n; ++j) {
+            double r = *p;
+            p += 32;
+            estep_site<BPOS>(s, st, j, r, sc);
+            sc = cpn_inv_pow2_of(s.fp + s.fm);
+        }
     }
-    double inv = 1.0 / (fp + fm);
-    out[0] = (gap + gam) * inv;
-    out[1] = (gbp + gbm) * inv;
-    out[2] = (gcp + gcm) * inv;
+    double inv = 1.0 / (s.fp + s.fm);
+    out[0] = (s.gap + s.gam) * inv;
+    out[1] = (s.gbp + s.gbm) * inv;
+    out[2] = (s.gcp + s.gcm) * inv;
 }
 
 __global__ void __launch_bounds__(E_WARPS * 32) k_estep(int n_items, const int* __restrict__ items, int n_init, RegionTables rt,
@@ -240,24 +269,18 @@ template <bool BPOS>
 __device__ __forceinline__ double logz_chunk(SiteTile& st, int L, int lane, const double* __restrict__ na_g,
                                              const double* __restrict__ nb_g, const double* __restrict__ invd_g,
                                              const double* __restrict__ ewc /*null → r = 1*/, double a, double b, double cabs) {
-    double fp = 0, fm = 0, sc = 1.0;
+    double fp = 1.0, fm = 1.0, sc = 1.0;           // all-ones message; group 0 carries t = 0 (see fill_tile)
     int esum = 0, e;
     for (int l0 = 0; l0 < L; l0 += TILE) {
         int n = min(TILE, L - l0);
         __syncwarp();
-        fill_tile(st, l0, n, lane, na_g, nb_g, invd_g, a, b, cabs);
+        fill_tile(st, l0, n, lane, na_g, nb_g, invd_g, a, b, cabs, BPOS);
         __syncwarp();
-        int j = 0;
-        if (l0 == 0) {
-            double r = ewc ? ewc[lane] : 1.0;
-            fp = st.wp[0] * r; fm = st.wm[0];
-            sc = cpn_inv_pow2_of(fp + fm, &e); esum += e;
-            j = 1;
-        }
-        for (; j < n; ++j) {
+        for (int j = 0; j < n; ++j) {
             double r = ewc ? ewc[(size_t)(l0 + j) * 32 + lane] : 1.0;
-            double t = st.t[j];
-            double phiP = (st.wp[j] * r) * sc, phiM = st.wm[j] * sc;
+            const double2 w = st.w[j];
+            double t = st.tn[j].x;
+            double phiP = (w.y * r) * sc, phiM = w.x * sc;
             double u = BPOS ? fp : fm, v = BPOS ? fm : fp;
             fp = phiP * fma(t, v, u);
             fm = phiM * fma(t, u, v);
@@ -340,44 +363,72 @@ __device__ double logz_serial(const double* __restrict__ na_g, const double* __r
 // Gradient g[3] and Hessian H (aa,ab,ac,bb,bc,cc) of log Z(ϕ) by one forward sweep with first- and
 // second-order tangents.  c<0 is mapped onto c>0 by the gauge x_l → (−1)^l x_l (flips the sign of α_l,
 // N_l, N_lρ_l on odd sites and of 1/d_l everywhere), so the recursion always has ψ(aligned)=1, ψ(opposite)=t.
-__device__ void eval_grad_hess(const double* __restrict__ na_g, const double* __restrict__ nb_g, const double* __restrict__ invd_g,
-                               int L, double a, double b, double c, double g[3], double H[6]) {
-    const bool neg = c < 0.0;
+struct SitePot { double na, nb, invd, invd2, na2, nanb, nb2, w0, w1, t; };
+
+__device__ __forceinline__ void prefetch_site(const SweepSite* p) {
+    asm volatile("prefetch.global.L1 [%0];" ::"l"(p));              // 64-byte record, 64-byte aligned: one line
+}
+__device__ __forceinline__ SweepSite load_site(const SweepSite* __restrict__ p) {
+    const double2* q = reinterpret_cast<const double2*>(p);
+    double2 x0 = __ldg(q), x1 = __ldg(q + 1), y0 = __ldg(q + 2), y1 = __ldg(q + 3);
+    SweepSite r;
+    r.na = x0.x; r.nb = x0.y; r.id = x1.x; r.id2 = x1.y; r.na2 = y0.x; r.nanb = y0.y; r.nb2 = y1.x; r.pad = 0.0;
+    return r;
+}
+// Potentials of group l at ϕ (gauge for c<0: sign flip of N_l, N_lρ_l on odd groups and of 1/d everywhere).
+__device__ __forceinline__ SitePot site_pot(const SweepSite& r, int l, bool neg, double a, double b, double cabs) {
+    const int flipbit = (neg && (l & 1)) ? (int)0x80000000 : 0;
+    const int negbit = neg ? (int)0x80000000 : 0;
+    SitePot p;
+    p.na = __hiloint2double(__double2hiint(r.na) ^ flipbit, __double2loint(r.na));
+    p.nb = __hiloint2double(__double2hiint(r.nb) ^ flipbit, __double2loint(r.nb));
+    p.invd = __hiloint2double(__double2hiint(r.id) ^ negbit, __double2loint(r.id));
+    p.invd2 = r.id2; p.na2 = r.na2; p.nanb = r.nanb; p.nb2 = r.nb2;
+    double alpha = fma(b, p.nb, a * p.na);
+    double ex = cpn_exp_neg(-2.0 * fabs(alpha));
+    const bool pos = __double2hiint(alpha) >= 0;
+    p.w0 = pos ? ex : 1.0; p.w1 = pos ? 1.0 : ex;
+    p.t = cpn_exp_neg(-2.0 * (cabs * r.id));
+    return p;
+}
+
+// The loop is software-pipelined by hand: while the recursion consumes group l, the record of group l+2 is being
+// loaded and the two exponentials of group l+1 are evaluated (they do not depend on the message), so the only serial
+// chain is the 2-state recursion itself.
+__device__ void eval_grad_hess(const SweepSite* __restrict__ tbl, int L, double a, double b, double c, double g[3], double H[6]) {
+    const bool neg = __double2hiint(c) < 0;
     const double cabs = fabs(c);
     double f[2], ga[2], gb[2], gc[2], haa[2], hab[2], hac[2], hbb[2], hbc[2], hcc[2];
     double sc;
+    SweepSite raw = load_site(tbl + (L > 1 ? 1 : 0));
     {
-        double na = na_g[0], nb = nb_g[0];
-        double alpha = fma(b, nb, a * na);
-        double ex = exp(-2.0 * fabs(alpha));
-        double w[2];
-        w[0] = alpha >= 0 ? ex : 1.0; w[1] = alpha >= 0 ? 1.0 : ex;
+        SitePot p0 = site_pot(load_site(tbl), 0, neg, a, b, cabs);
+        double w[2] = {p0.w0, p0.w1};
 #pragma unroll
         for (int x = 0; x < 2; ++x) {
             double sg = x ? 1.0 : -1.0;
             f[x] = w[x];
-            ga[x] = sg * na * w[x]; gb[x] = sg * nb * w[x]; gc[x] = 0.0;
-            haa[x] = na * na * w[x]; hab[x] = na * nb * w[x]; hbb[x] = nb * nb * w[x];
+            ga[x] = sg * p0.na * w[x]; gb[x] = sg * p0.nb * w[x]; gc[x] = 0.0;
+            haa[x] = p0.na2 * w[x]; hab[x] = p0.nanb * w[x]; hbb[x] = p0.nb2 * w[x];
             hac[x] = 0.0; hbc[x] = 0.0; hcc[x] = 0.0;
         }
         sc = cpn_inv_pow2_of(f[0] + f[1]);
     }
+    SitePot pot = site_pot(raw, 1, neg, a, b, cabs);
+    raw = load_site(tbl + (L > 2 ? 2 : 0));
     for (int l = 1; l < L; ++l) {
-        double flip = (neg && (l & 1)) ? -1.0 : 1.0;
-        double na = flip * na_g[l], nb = flip * nb_g[l];
-        double id = invd_g[l - 1];
-        double invd = neg ? -id : id;
-        double alpha = fma(b, nb, a * na);
-        double ex = exp(-2.0 * fabs(alpha));
-        double t = exp(-2.0 * cabs * id);
-        double w[2];
-        w[0] = (alpha >= 0 ? ex : 1.0) * sc; w[1] = (alpha >= 0 ? 1.0 : ex) * sc;
+        const SitePot p = pot;
+        const SweepSite rnext = raw;
+        prefetch_site(tbl + (l + 4 < L ? l + 4 : 0));               // pull the record of group l+4 into L1 (no register cost)
+        raw = load_site(tbl + (l + 2 < L ? l + 2 : 0));            // consumed by site_pot() in the next iteration
+        pot = site_pot(rnext, l + 1, neg, a, b, cabs);              // independent of the recursion below
+        const double t = p.t, invd = p.invd, invd2 = p.invd2, invd_2 = p.invd + p.invd;
+        double w[2] = {p.w0 * sc, p.w1 * sc};
         double nf[2], nga[2], ngb[2], ngc[2], nhaa[2], nhab[2], nhac[2], nhbb[2], nhbc[2], nhcc[2];
-        const double invd2 = invd * invd, invd_2 = 2.0 * invd, nanb = na * nb, na2 = na * na, nb2 = nb * nb;
 #pragma unroll
         for (int x = 0; x < 2; ++x) {
             const int s = x, o = 1 - x;
-            const double sna = x ? na : -na, snb = x ? nb : -nb;
+            const double sna = x ? p.na : -p.na, snb = x ? p.nb : -p.nb;
             double S0 = fma(t, f[o], f[s]);
             double Sa = fma(t, ga[o], ga[s]);
             double Sb = fma(t, gb[o], gb[s]);
@@ -395,9 +446,9 @@ __device__ void eval_grad_hess(const double* __restrict__ na_g, const double* __
             nga[x] = ph * fma(sna, S0, Sa);
             ngb[x] = ph * fma(snb, S0, Sb);
             ngc[x] = ph * Sc;
-            nhaa[x] = ph * fma(na2, S0, fma(2.0 * sna, Sa, Saa));
-            nhab[x] = ph * fma(nanb, S0, fma(sna, Sb, fma(snb, Sa, Sab)));
-            nhbb[x] = ph * fma(nb2, S0, fma(2.0 * snb, Sb, Sbb));
+            nhaa[x] = ph * fma(p.na2, S0, fma(sna, Sa + Sa, Saa));
+            nhab[x] = ph * fma(p.nanb, S0, fma(sna, Sb, fma(snb, Sa, Sab)));
+            nhbb[x] = ph * fma(p.nb2, S0, fma(snb, Sb + Sb, Sbb));
             nhac[x] = ph * fma(sna, Sc, Sac);
             nhbc[x] = ph * fma(snb, Sc, Sbc);
             nhcc[x] = ph * Scc;
@@ -421,6 +472,7 @@ __device__ void eval_grad_hess(const double* __restrict__ na_g, const double* __
 
 struct MProblem {
     const double *na, *nb, *invd;
+    const SweepSite* sq;
     int L;
     double t0, t1, t2;     // ES/M
     int mode;
@@ -457,7 +509,7 @@ __device__ void jacobian_fd(MProblem& pb, double* x, double J[3][3]) {
 __device__ void value_jacobian(MProblem& pb, double* x, double* F, double J[3][3]) {
     if (pb.mode == CPN_MSTEP_ANALYTIC) {
         double g[3], H[6];
-        eval_grad_hess(pb.na, pb.nb, pb.invd, pb.L, x[0], x[1], x[2], g, H);
+        eval_grad_hess(pb.sq, pb.L, x[0], x[1], x[2], g, H);
         pb.evals += 1;
         F[0] = g[0] - pb.t0; F[1] = g[1] - pb.t1; F[2] = g[2] - pb.t2;
         J[0][0] = H[0]; J[0][1] = H[1]; J[0][2] = H[2];
@@ -646,7 +698,7 @@ __global__ void __launch_bounds__(M_THREADS) k_mstep(int n_items, const int* __r
         int64_t r = inst / n_init;
         int64_t g0 = rt.grp_off[r];
         MProblem pb;
-        pb.na = rt.na + g0; pb.nb = rt.nb + g0; pb.invd = rt.invd + g0;
+        pb.na = rt.na + g0; pb.nb = rt.nb + g0; pb.invd = rt.invd + g0; pb.sq = rt.sq + g0;
         pb.L = (int)(rt.grp_off[r + 1] - g0);
         double Mr = (double)(rt.read_off[r + 1] - rt.read_off[r]);
         int64_t NI = st.NI;
@@ -690,94 +742,87 @@ __global__ void __launch_bounds__(M_THREADS) k_mstep(int n_items, const int* __r
 }
 
 // Analytic-mode M-step with lane-level work stealing.  Every loop trip performs exactly one derivative sweep per busy
-// lane (the expensive, uniform part); the trust-region bookkeeping between sweeps is a small per-lane state machine
-// (NLsolve trust_region_: initial evaluation, then one evaluation per iteration).  A lane whose solve ends takes the
-// next EM instance from a global queue, so the 32 lanes of a warp stay busy regardless of how many solver iterations
-// their instances need.
-struct LaneSolve {
-    const double *na, *nb, *invd;
-    int L, inst, it, evals;
-    bool init_phase;
-    double t0, t1, t2;
-    double x0[3], x[3], xold[3], r[3], J[3][3], d[3], p[3], delta;
-};
+// lane (the expensive, uniform part); the trust-region bookkeeping between sweeps is a per-lane state machine
+// (NLsolve trust_region_: initial evaluation, then one evaluation per iteration) written branch-light — both phases and
+// all three dogleg cases run the same instruction stream with selects — so lanes at different solver phases do not
+// serialise.  A lane whose solve ends takes the next EM instance from a global queue.  The solver state is cold during a
+// sweep and lives in shared memory ([field][thread], conflict-free), leaving the registers to the 20-value recursion.
+enum { C_X0 = 0, C_X = 3, C_XOLD = 6, C_R = 9, C_J = 12, C_D = 18, C_P = 21, C_DELTA = 24, C_T = 25, C_N = 28 };
 
-__device__ __forceinline__ void ws_next_step(LaneSolve& s) {
-    s.it += 1;
-    dogleg3(s.p, s.r, s.d, s.J, s.delta);
+// Solves the symmetric 3x3 system J p = r (J as aa,ab,ac,bb,bc,cc) by LU with partial pivoting; pivots are inverted once.
+__device__ __forceinline__ bool lu_solve3_sym(const double* Js, const double* r, double* out) {
+    double A[3][3] = {{Js[0], Js[1], Js[2]}, {Js[1], Js[3], Js[4]}, {Js[2], Js[4], Js[5]}};
+    double b[3] = {r[0], r[1], r[2]};
+    bool ok = true;
 #pragma unroll
-    for (int i = 0; i < 3; ++i) { s.xold[i] = s.x[i]; s.x[i] += s.p[i]; }
+    for (int k = 0; k < 3; ++k) {
+        // partial pivoting by conditional row swaps (selects)
+#pragma unroll
+        for (int i = k + 1; i < 3; ++i) {
+            bool sw = fabs(A[i][k]) > fabs(A[k][k]);
+#pragma unroll
+            for (int j = 0; j < 3; ++j) { double u = A[k][j], v = A[i][j]; A[k][j] = sw ? v : u; A[i][j] = sw ? u : v; }
+            double u = b[k], v = b[i]; b[k] = sw ? v : u; b[i] = sw ? u : v;
+        }
+        ok = ok && (A[k][k] != 0.0);
+        double inv = 1.0 / A[k][k];
+        A[k][k] = inv;
+#pragma unroll
+        for (int i = k + 1; i < 3; ++i) {
+            double m = A[i][k] * inv;
+#pragma unroll
+            for (int j = k + 1; j < 3; ++j) A[i][j] = fma(-m, A[k][j], A[i][j]);
+            b[i] = fma(-m, b[k], b[i]);
+        }
+    }
+    out[2] = b[2] * A[2][2];
+    out[1] = (b[1] - A[1][2] * out[2]) * A[1][1];
+    out[0] = (b[0] - A[0][1] * out[1] - A[0][2] * out[2]) * A[0][0];
+    return ok;
+}
+// NLsolve dogleg! with all three cases evaluated and selected (no divergent branches).
+__device__ __forceinline__ void dogleg3_sel(double* p, const double* r, const double* d, const double* Js, double delta) {
+    double p_i[3];
+    bool ok = lu_solve3_sym(Js, r, p_i);
+#pragma unroll
+    for (int i = 0; i < 3; ++i) p_i[i] = -p_i[i];
+    const bool case1 = ok && (wnorm3(d, p_i) <= delta);
+    double g[3], Jg[3], p_c[3];
+    g[0] = (Js[0] * r[0] + Js[1] * r[1] + Js[2] * r[2]) / (d[0] * d[0]);
+    g[1] = (Js[1] * r[0] + Js[3] * r[1] + Js[4] * r[2]) / (d[1] * d[1]);
+    g[2] = (Js[2] * r[0] + Js[4] * r[1] + Js[5] * r[2]) / (d[2] * d[2]);
+    Jg[0] = Js[0] * g[0] + Js[1] * g[1] + Js[2] * g[2];
+    Jg[1] = Js[1] * g[0] + Js[3] * g[1] + Js[4] * g[2];
+    Jg[2] = Js[2] * g[0] + Js[4] * g[1] + Js[5] * g[2];
+    const double wg2 = wdot3(d, g, d, g), wg = sqrt(wg2);
+    const double coef = -wg2 / sumabs2_3(Jg);
+#pragma unroll
+    for (int i = 0; i < 3; ++i) p_c[i] = coef * g[i];
+    const double wpc2 = wdot3(d, p_c, d, p_c);
+    const bool case2 = !ok || (sqrt(wpc2) >= delta);
+    const double s2 = -delta / wg;
+    double p_diff[3];
+#pragma unroll
+    for (int i = 0; i < 3; ++i) p_diff[i] = p_i[i] - p_c[i];
+    const double bq = 2 * wdot3(d, p_c, d, p_diff);
+    const double aq = wdot3(d, p_diff, d, p_diff);
+    const double tau = (-bq + sqrt(bq * bq - 4 * aq * (wpc2 - delta * delta))) / (2 * aq);
+#pragma unroll
+    for (int i = 0; i < 3; ++i) p[i] = case1 ? p_i[i] : (case2 ? g[i] * s2 : fma(tau, p_diff[i], p_c[i]));
 }
 
-// Consumes F, J evaluated at s.x.  Returns 0 = continue (s.x holds the next trial point), 1 = converged, 2 = not converged.
-__device__ int ws_advance(LaneSolve& s, const double* fval, const double Jn[3][3]) {
-    const double ftol = 1e-3, eta = 1e-4;
-    if (s.init_phase) {
-        s.init_phase = false;
-#pragma unroll
-        for (int i = 0; i < 3; ++i) {
-            s.r[i] = fval[i];
-#pragma unroll
-            for (int j = 0; j < 3; ++j) s.J[i][j] = Jn[i][j];
-        }
-        if (!allfinite3(s.r)) return 2;                     // check_isfinite → exception → em_iter keeps ϕ (:160-172)
-        if (norminf3(fval) <= ftol) return 1;               // converged with 0 iterations
-        if (anynan3(s.x)) return 2;
-#pragma unroll
-        for (int j = 0; j < 3; ++j) {
-            s.d[j] = sqrt(s.J[0][j] * s.J[0][j] + s.J[1][j] * s.J[1][j] + s.J[2][j] * s.J[2][j]);
-            if (s.d[j] == 0.0) s.d[j] = 1.0;
-        }
-        s.delta = wnorm3(s.d, s.x);
-        if (s.delta == 0.0) s.delta = 1.0;
-        s.it = 0;
-        ws_next_step(s);
-        return 0;
-    }
-    double rp[3];
-    matvec3(s.J, s.p, rp);
-#pragma unroll
-    for (int i = 0; i < 3; ++i) rp[i] += s.r[i];
-    double rho = (sumabs2_3(s.r) - sumabs2_3(fval)) / (sumabs2_3(s.r) - sumabs2_3(rp));
-    bool conv = false;
-    if (rho > eta) {
-#pragma unroll
-        for (int i = 0; i < 3; ++i) {
-            s.r[i] = fval[i];
-#pragma unroll
-            for (int j = 0; j < 3; ++j) s.J[i][j] = Jn[i][j];
-        }
-#pragma unroll
-        for (int j = 0; j < 3; ++j) {
-            double nj = sqrt(s.J[0][j] * s.J[0][j] + s.J[1][j] * s.J[1][j] + s.J[2][j] * s.J[2][j]);
-            s.d[j] = fmax(0.1 * s.d[j], nj);
-        }
-        double dx[3] = {s.x[0] - s.xold[0], s.x[1] - s.xold[1], s.x[2] - s.xold[2]};
-        conv = (norminf3(dx) <= 0.0) || (norminf3(s.r) <= ftol);
-    } else {
-#pragma unroll
-        for (int i = 0; i < 3; ++i) s.x[i] -= s.p[i];
-    }
-    if (rho < 0.1) s.delta = s.delta / 2;
-    else if (rho >= 0.9) s.delta = 2 * wnorm3(s.d, s.p);
-    else if (rho >= 0.5) s.delta = fmax(s.delta, 2 * wnorm3(s.d, s.p));
-    bool stopped = anynan3(s.x) || anynan3(fval);
-    if (conv) return 1;
-    if (stopped || s.it >= 20) return 2;
-    ws_next_step(s);
-    return 0;
-}
-
-__global__ void __launch_bounds__(M_THREADS) k_mstep_ws(int n_items, const int* __restrict__ items, int n_init, RegionTables rt, EmState st,
-                                                         int max_em_iters, double amax, double bmax, double cmax, int* __restrict__ queue,
-                                                         unsigned char* __restrict__ alive /*[n_items] by list position*/) {
+__global__ void __launch_bounds__(M_THREADS, WS_BLOCKS) k_mstep_ws(int n_items, const int* __restrict__ items, int n_init, RegionTables rt,
+                                                                    EmState st, int max_em_iters, double amax, double bmax, double cmax,
+                                                                    int* __restrict__ queue,
+                                                                    unsigned char* __restrict__ alive /*[n_items] by list position*/) {
+    __shared__ double cold[C_N][M_THREADS];
+#define CS(i) cold[(i)][threadIdx.x]
     const int lane = threadIdx.x & 31;
-    int pos = -1;
     const unsigned lt_mask = (1u << lane) - 1;
-    LaneSolve s;
-    bool have = false;
-    s.na = s.nb = s.invd = nullptr; s.L = 0; s.inst = -1; s.it = 0; s.evals = 0; s.init_phase = true;
-    bool drained = false;
+    const double ftol = 1e-3, eta = 1e-4;
+    const SweepSite* tbl = nullptr;
+    int L = 0, inst = -1, pos = -1, it = 0, evals = 0;
+    bool init = true, have = false, drained = false;
     for (;;) {
         // ---- take work (warp-aggregated fetch from the global queue)
         bool need = !have && !drained;
@@ -789,52 +834,105 @@ __global__ void __launch_bounds__(M_THREADS) k_mstep_ws(int n_items, const int* 
             if (need) {
                 int item = base + __popc(m & lt_mask);
                 if (item < n_items) {
-                    int inst = items ? items[item] : item;
+                    inst = items ? items[item] : item;
                     pos = item;
                     int64_t r = inst / n_init;
                     int64_t g0 = rt.grp_off[r];
-                    s.na = rt.na + g0; s.nb = rt.nb + g0; s.invd = rt.invd + g0;
-                    s.L = (int)(rt.grp_off[r + 1] - g0);
+                    tbl = rt.sq + g0;
+                    L = (int)(rt.grp_off[r + 1] - g0);
                     double Mr = (double)(rt.read_off[r + 1] - rt.read_off[r]);
                     int64_t NI = st.NI;
-                    s.t0 = st.ES[inst] / Mr; s.t1 = st.ES[NI + inst] / Mr; s.t2 = st.ES[2 * NI + inst] / Mr;
-                    s.inst = inst; s.evals = 0; s.it = 0; s.init_phase = true;
 #pragma unroll
-                    for (int i = 0; i < 3; ++i) { s.x0[i] = st.phi[i * NI + inst]; s.x[i] = s.x0[i]; }
-                    have = true;
+                    for (int i = 0; i < 3; ++i) {
+                        CS(C_T + i) = st.ES[i * NI + inst] / Mr;
+                        double v = st.phi[i * NI + inst];
+                        CS(C_X0 + i) = v; CS(C_X + i) = v;
+                    }
+                    evals = 0; it = 0; init = true; have = true;
                 } else drained = true;
             }
         }
         if (!__any_sync(0xffffffffu, have)) break;
-        // ---- one derivative sweep at the current point of every busy lane
         if (have) {
-            double g[3], H[6], fval[3], Jn[3][3];
-            eval_grad_hess(s.na, s.nb, s.invd, s.L, s.x[0], s.x[1], s.x[2], g, H);
-            s.evals += 1;
-            fval[0] = g[0] - s.t0; fval[1] = g[1] - s.t1; fval[2] = g[2] - s.t2;
-            Jn[0][0] = H[0]; Jn[0][1] = H[1]; Jn[0][2] = H[2];
-            Jn[1][0] = H[1]; Jn[1][1] = H[3]; Jn[1][2] = H[4];
-            Jn[2][0] = H[2]; Jn[2][1] = H[4]; Jn[2][2] = H[5];
-            int code = ws_advance(s, fval, Jn);
-            if (code != 0) {
-                // em_iter tail (:172-181) + em_inst bookkeeping (:327-341)
-                double nx[3];
-                if (code == 2) { nx[0] = s.x0[0]; nx[1] = s.x0[1]; nx[2] = s.x0[2]; }
-                else {
-                    nx[0] = fmax(-amax, fmin(s.x[0], amax));
-                    nx[1] = fmax(-bmax, fmin(s.x[1], bmax));
-                    nx[2] = fmax(-cmax, fmin(s.x[2], cmax));
+            // ---- one derivative sweep at the current point
+            double x[3] = {CS(C_X), CS(C_X + 1), CS(C_X + 2)};
+            double g[3], H[6];
+            eval_grad_hess(tbl, L, x[0], x[1], x[2], g, H);
+            evals += 1;
+            // ---- trust-region bookkeeping (NLsolve trust_region_), both phases in one instruction stream
+            double fval[3] = {g[0] - CS(C_T), g[1] - CS(C_T + 1), g[2] - CS(C_T + 2)};
+            double r[3] = {CS(C_R), CS(C_R + 1), CS(C_R + 2)};
+            double p[3] = {CS(C_P), CS(C_P + 1), CS(C_P + 2)};
+            double d[3] = {CS(C_D), CS(C_D + 1), CS(C_D + 2)};
+            double Js[6] = {CS(C_J), CS(C_J + 1), CS(C_J + 2), CS(C_J + 3), CS(C_J + 4), CS(C_J + 5)};
+            double delta = CS(C_DELTA);
+            double rp[3] = {Js[0] * p[0] + Js[1] * p[1] + Js[2] * p[2] + r[0], Js[1] * p[0] + Js[3] * p[1] + Js[4] * p[2] + r[1],
+                            Js[2] * p[0] + Js[4] * p[1] + Js[5] * p[2] + r[2]};
+            double rho = (sumabs2_3(r) - sumabs2_3(fval)) / (sumabs2_3(r) - sumabs2_3(rp));
+            const bool accept = init || (rho > eta);
+            bool x_conv = false;
+            if (accept) {
+#pragma unroll
+                for (int i = 0; i < 3; ++i) r[i] = fval[i];
+#pragma unroll
+                for (int i = 0; i < 6; ++i) Js[i] = H[i];
+                double n0 = sqrt(H[0] * H[0] + H[1] * H[1] + H[2] * H[2]);
+                double n1 = sqrt(H[1] * H[1] + H[3] * H[3] + H[4] * H[4]);
+                double n2 = sqrt(H[2] * H[2] + H[4] * H[4] + H[5] * H[5]);
+                d[0] = init ? (n0 == 0.0 ? 1.0 : n0) : fmax(0.1 * d[0], n0);
+                d[1] = init ? (n1 == 0.0 ? 1.0 : n1) : fmax(0.1 * d[1], n1);
+                d[2] = init ? (n2 == 0.0 ? 1.0 : n2) : fmax(0.1 * d[2], n2);
+                double dx[3] = {x[0] - CS(C_XOLD), x[1] - CS(C_XOLD + 1), x[2] - CS(C_XOLD + 2)};
+                x_conv = !init && (norminf3(dx) <= 0.0);
+            } else {
+#pragma unroll
+                for (int i = 0; i < 3; ++i) x[i] -= p[i];
+            }
+            if (init) {
+                delta = wnorm3(d, x);
+                if (delta == 0.0) delta = 1.0;
+            } else {
+                const double wdp = wnorm3(d, p);                     // with the scaling vector already updated (as NLsolve does)
+                if (rho < 0.1) delta = delta / 2;
+                else if (rho >= 0.9) delta = 2 * wdp;
+                else if (rho >= 0.5) delta = fmax(delta, 2 * wdp);
+            }
+            const bool threw = init && !allfinite3(fval);
+            const bool conv = accept && !threw && (x_conv || norminf3(r) <= ftol);
+            const bool stopped = anynan3(x) || anynan3(fval);
+            int code = 0;
+            if (threw) code = 2;
+            else if (conv) code = 1;
+            else if (stopped || (!init && it >= 20)) code = 2;
+            if (code == 0) {
+                it = init ? 1 : it + 1;
+                init = false;
+                dogleg3_sel(p, r, d, Js, delta);
+#pragma unroll
+                for (int i = 0; i < 3; ++i) {
+                    CS(C_XOLD + i) = x[i]; CS(C_X + i) = x[i] + p[i]; CS(C_P + i) = p[i]; CS(C_R + i) = r[i]; CS(C_D + i) = d[i];
                 }
-                double d0 = s.x0[0] - nx[0], d1 = s.x0[1] - nx[1], d2 = s.x0[2] - nx[2];
+#pragma unroll
+                for (int i = 0; i < 6; ++i) CS(C_J + i) = Js[i];
+                CS(C_DELTA) = delta;
+            } else {
+                // em_iter tail (:172-181) + em_inst bookkeeping (:327-341)
+                double x0[3] = {CS(C_X0), CS(C_X0 + 1), CS(C_X0 + 2)}, nx[3];
+                if (code == 2) { nx[0] = x0[0]; nx[1] = x0[1]; nx[2] = x0[2]; }
+                else {
+                    nx[0] = fmax(-amax, fmin(x[0], amax));
+                    nx[1] = fmax(-bmax, fmin(x[1], bmax));
+                    nx[2] = fmax(-cmax, fmin(x[2], cmax));
+                }
+                double d0 = x0[0] - nx[0], d1 = x0[1] - nx[1], d2 = x0[2] - nx[2];
                 bool cv = sqrt(d0 * d0 + d1 * d1 + d2 * d2) <= 3.0e-2;
-                int inst = s.inst;
                 int64_t NI = st.NI;
                 int i = st.iter[inst];
                 bool hit = i >= max_em_iters;
                 i += 1;
                 st.phi[inst] = nx[0]; st.phi[NI + inst] = nx[1]; st.phi[2 * NI + inst] = nx[2];
                 st.iter[inst] = i;
-                st.cnt_em[inst] += 1; st.cnt_sol[inst] += s.it; st.cnt_eval[inst] += s.evals;
+                st.cnt_em[inst] += 1; st.cnt_sol[inst] += init ? 0 : it; st.cnt_eval[inst] += evals;
                 bool done = cv || hit;
                 if (done) st.status[inst] = (cv && i > 2) ? 1 : 2;
                 alive[pos] = done ? 0 : 1;
@@ -842,6 +940,7 @@ __global__ void __launch_bounds__(M_THREADS) k_mstep_ws(int n_items, const int* 
             }
         }
     }
+#undef CS
 }
 
 // Order-preserving compaction of the active list (keeps instances sorted by chain length so that the lanes of an
@@ -916,7 +1015,7 @@ __global__ void k_mstep_once(int64_t R, RegionTables rt, const int64_t* __restri
     if (r >= R) return;
     int64_t g0 = rt.grp_off[r];
     MProblem pb;
-    pb.na = rt.na + g0; pb.nb = rt.nb + g0; pb.invd = rt.invd + g0;
+    pb.na = rt.na + g0; pb.nb = rt.nb + g0; pb.invd = rt.invd + g0; pb.sq = rt.sq + g0;
     pb.L = (int)(rt.grp_off[r + 1] - g0);
     double Mr = (double)n_reads[r];
     pb.t0 = ES[3 * r] / Mr; pb.t1 = ES[3 * r + 1] / Mr; pb.t2 = ES[3 * r + 2] / Mr;
@@ -990,6 +1089,7 @@ struct PackedRegions {
     DevIn<double> Nl, rho, dl, lu, lm;
     DevBuf<int64_t> obs_off, ew_off, rb_off;
     DevBuf<double> na, nb, invd, ew, rb;
+    DevBuf<SweepSite> sq;
     std::vector<int64_t> h_grp_off, h_read_off;
     int64_t R = 0, sumL = 0, n_obs = 0;
     RegionTables rt{};
@@ -1034,9 +1134,10 @@ int pack_regions(cpn_ctx* ctx, PackedRegions& pk, bool on_device, bool with_read
     CPN_CUDA(ctx, pk.na.alloc(pk.sumL, s));
     CPN_CUDA(ctx, pk.nb.alloc(pk.sumL, s));
     CPN_CUDA(ctx, pk.invd.alloc(pk.sumL, s));
+    CPN_CUDA(ctx, pk.sq.alloc(pk.sumL, s));
     { KTimer kt(ctx, CPN_K_PREP);
-      k_prep_sites<<<blocks_for(R * 32, 256), 256, 0, s>>>(R, pk.grp_off.p, pk.Nl.p, pk.rho.p, pk.dl.p, pk.na.p, pk.nb.p, pk.invd.p); }
-    pk.rt.grp_off = pk.grp_off.p; pk.rt.na = pk.na.p; pk.rt.nb = pk.nb.p; pk.rt.invd = pk.invd.p;
+      k_prep_sites<<<blocks_for(R * 32, 256), 256, 0, s>>>(R, pk.grp_off.p, pk.Nl.p, pk.rho.p, pk.dl.p, pk.na.p, pk.nb.p, pk.invd.p, pk.sq.p); }
+    pk.rt.grp_off = pk.grp_off.p; pk.rt.na = pk.na.p; pk.rt.nb = pk.nb.p; pk.rt.invd = pk.invd.p; pk.rt.sq = pk.sq.p;
     if (with_reads) {
         CPN_CUDA(ctx, pk.read_off.bind(read_off, R + 1, on_device, s));
         CPN_CUDA(ctx, pk.lu.bind(lu, pk.n_obs, on_device, s));
