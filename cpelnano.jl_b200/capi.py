@@ -22,7 +22,8 @@ class CpnError(RuntimeError):
 
 
 def lib_path():
-    return os.path.join(_HERE, "libcpelnano_b200.so")
+    """In-tree library; CPN_LIB overrides it (kernel-tuning builds under build/variants/)."""
+    return os.environ.get("CPN_LIB") or os.path.join(_HERE, "libcpelnano_b200.so")
 
 
 def _f64(a):

@@ -35,9 +35,9 @@ constexpr int M_THREADS = 128;     // lanes (EM instances) per M-step block
 constexpr double LLR_CLAMP = 300.0;
 constexpr double CBRT_EPS = 6.0554544523933395e-6;
 
-// One record per CpG group for the M-step sweep (ϕ-independent): N_l, N_lρ_l, 1/d and 1/d² of the coupling INTO the group
-// (0 for the first group), and the products N², N·Nρ, (Nρ)².  64 bytes → two 32-byte vector loads, prefetched one group ahead.
-struct __align__(64) SweepSite { double na, nb, id, id2, na2, nanb, nb2, pad; };
+// One 32-byte record per CpG group for the M-step sweep (ϕ-independent): N_l, N_lρ_l, 1/d and 1/d² of the coupling INTO
+// the group (0 for the first group).  Small on purpose: the records of all chains resident on an SM must stay in L1.
+struct __align__(32) SweepSite { double na, nb, id, id2; };
 
 struct RegionTables {
     // per group (offsets grp_off): N_l, N_l·ρ_l and 1/d_l (coupling l→l+1; entry L-1 unused)
@@ -80,7 +80,7 @@ __global__ void k_prep_sites(int64_t R, const int64_t* __restrict__ grp_off, con
         invd[g0 + l] = id;
         double idin = (l > 0) ? 1.0 / dl[g0 - warp + l - 1] : 0.0;
         SweepSite ss;
-        ss.na = n; ss.nb = b; ss.id = idin; ss.id2 = idin * idin; ss.na2 = n * n; ss.nanb = n * b; ss.nb2 = b * b; ss.pad = 0.0;
+        ss.na = n; ss.nb = b; ss.id = idin; ss.id2 = idin * idin;
         sq[g0 + l] = ss;
     }
 }
@@ -146,7 +146,10 @@ __device__ __forceinline__ void fill_tile(SiteTile& st, int l0, int n, int lane,
 // ---------------------------------------------------------------------------------------------------
 // One forward sweep for the 32 reads of a chunk.  BPOS = (c ≥ 0).  (u,v) below are the source states that
 // enter x'=+1 with weight 1 and t respectively; for c<0 the roles of same/opposite swap.
-constexpr int E_PF = 8;            // emission weights prefetched per lane (register double buffer)
+#ifndef E_PF_N
+#define E_PF_N 8
+#endif
+constexpr int E_PF = E_PF_N;       // emission weights prefetched per lane (register double buffer)
 
 struct EState { double fp, fm, gap, gam, gbp, gbm, gcp, gcm; };
 
@@ -228,7 +231,10 @@ __device__ __forceinline__ void estep_chunk(SiteTile& st, int L, int lane, const
     out[2] = (s.gcp + s.gcm) * inv;
 }
 
-__global__ void __launch_bounds__(E_WARPS * 32) k_estep(int n_items, const int* __restrict__ items, int n_init, RegionTables rt,
+#ifndef E_BLOCKS
+#define E_BLOCKS 4
+#endif
+__global__ void __launch_bounds__(E_WARPS * 32, E_BLOCKS) k_estep(int n_items, const int* __restrict__ items, int n_init, RegionTables rt,
                                                          const double* __restrict__ phi /*[3][NI]*/, int64_t NI,
                                                          double* __restrict__ ES /*[3][NI]*/) {
     __shared__ SiteTile tiles[E_WARPS];
@@ -366,13 +372,13 @@ __device__ double logz_serial(const double* __restrict__ na_g, const double* __r
 struct SitePot { double na, nb, invd, invd2, na2, nanb, nb2, w0, w1, t; };
 
 __device__ __forceinline__ void prefetch_site(const SweepSite* p) {
-    asm volatile("prefetch.global.L1 [%0];" ::"l"(p));              // 64-byte record, 64-byte aligned: one line
+    asm volatile("prefetch.global.L1 [%0];" ::"l"(p));              // 32-byte record, 32-byte aligned: one sector
 }
 __device__ __forceinline__ SweepSite load_site(const SweepSite* __restrict__ p) {
     const double2* q = reinterpret_cast<const double2*>(p);
-    double2 x0 = __ldg(q), x1 = __ldg(q + 1), y0 = __ldg(q + 2), y1 = __ldg(q + 3);
+    double2 x0 = __ldg(q), x1 = __ldg(q + 1);
     SweepSite r;
-    r.na = x0.x; r.nb = x0.y; r.id = x1.x; r.id2 = x1.y; r.na2 = y0.x; r.nanb = y0.y; r.nb2 = y1.x; r.pad = 0.0;
+    r.na = x0.x; r.nb = x0.y; r.id = x1.x; r.id2 = x1.y;
     return r;
 }
 // Potentials of group l at ϕ (gauge for c<0: sign flip of N_l, N_lρ_l on odd groups and of 1/d everywhere).
@@ -383,7 +389,7 @@ __device__ __forceinline__ SitePot site_pot(const SweepSite& r, int l, bool neg,
     p.na = __hiloint2double(__double2hiint(r.na) ^ flipbit, __double2loint(r.na));
     p.nb = __hiloint2double(__double2hiint(r.nb) ^ flipbit, __double2loint(r.nb));
     p.invd = __hiloint2double(__double2hiint(r.id) ^ negbit, __double2loint(r.id));
-    p.invd2 = r.id2; p.na2 = r.na2; p.nanb = r.nanb; p.nb2 = r.nb2;
+    p.invd2 = r.id2; p.na2 = r.na * r.na; p.nanb = r.na * r.nb; p.nb2 = r.nb * r.nb;
     double alpha = fma(b, p.nb, a * p.na);
     double ex = cpn_exp_neg(-2.0 * fabs(alpha));
     const bool pos = __double2hiint(alpha) >= 0;
