@@ -127,17 +127,29 @@ __global__ void k_prep_emis(int64_t R, const int64_t* __restrict__ grp_off, cons
 __device__ __forceinline__ void fill_tile(SiteTile& st, int l0, int n, int lane, const double* __restrict__ na_g,
                                           const double* __restrict__ nb_g, const double* __restrict__ invd_g, double a, double b,
                                           double cabs, bool bpos) {
-    for (int j = lane; j < n; j += 32) {
-        int l = l0 + j;
-        double na = na_g[l], nb = nb_g[l];
-        double alpha = fma(b, nb, a * na);
-        double e = cpn_exp_neg(-2.0 * fabs(alpha));
-        bool pos = __double2hiint(alpha) >= 0;
-        st.w[j] = make_double2(pos ? e : 1.0, pos ? 1.0 : e);
-        double id = (l > 0) ? invd_g[l - 1] : 0.0;
-        // group 0 has no incoming coupling: t = 0 makes the generic step reproduce f = φ_0 from the all-ones message
-        st.tn[j] = make_double2((l > 0) ? cpn_exp_neg(-2.0 * cabs * id) : 0.0, na);
-        st.bd[j] = make_double2(nb, bpos ? id : -id);
+    // lanes are strided over the groups of the tile; all loads of a lane are issued before any exponential
+    constexpr int K = TILE / 32;
+    double na[K], nb[K], id[K];
+#pragma unroll
+    for (int k = 0; k < K; ++k) {
+        const int j = lane + 32 * k, l = l0 + j;
+        const bool in = j < n;
+        na[k] = in ? na_g[l] : 0.0;
+        nb[k] = in ? nb_g[l] : 0.0;
+        id[k] = (in && l > 0) ? invd_g[l - 1] : 0.0;
+    }
+#pragma unroll
+    for (int k = 0; k < K; ++k) {
+        const int j = lane + 32 * k, l = l0 + j;
+        if (j < n) {
+            double alpha = fma(b, nb[k], a * na[k]);
+            double e = cpn_exp_neg(-2.0 * fabs(alpha));
+            bool pos = __double2hiint(alpha) >= 0;
+            st.w[j] = make_double2(pos ? e : 1.0, pos ? 1.0 : e);
+            // group 0 has no incoming coupling: t = 0 makes the generic step reproduce f = φ_0 from the all-ones message
+            st.tn[j] = make_double2((l > 0) ? cpn_exp_neg(-2.0 * (cabs * id[k])) : 0.0, na[k]);
+            st.bd[j] = make_double2(nb[k], bpos ? id[k] : -id[k]);
+        }
     }
 }
 
@@ -196,6 +208,13 @@ __device__ __forceinline__ void estep_chunk(SiteTile& st, int L, int lane, const
 #pragma unroll
         for (int u = 0; u < E_PF; ++u) rn[u] = p[u * 32];
     }
+    // the last L mod E_PF groups: loaded up front as well, so the tail loop never waits on memory
+    double rt_[E_PF - 1];
+    {
+        const double* pt = p + (size_t)Lfull * 32;
+#pragma unroll
+        for (int u = 0; u < E_PF - 1; ++u) rt_[u] = (Lfull + u < L) ? pt[u * 32] : 1.0;
+    }
     for (int l0 = 0; l0 < L; l0 += TILE) {
         const int n = min(TILE, L - l0);
         __syncwarp();
@@ -217,12 +236,14 @@ __device__ __forceinline__ void estep_chunk(SiteTile& st, int L, int lane, const
                 if (u & 1) sc = cpn_inv_pow2_of(s.fp + s.fm); else sc = 1.0;
             }
         }
-        // tail of the chain (fewer than E_PF groups left): p already points at its first group
-        for (int j = nfull; j < n; ++j) {
-            double r = *p;
-            p += 32;
-            estep_site<BPOS>(s, st, j, r, sc);
-            sc = cpn_inv_pow2_of(s.fp + s.fm);
+        // tail of the chain (fewer than E_PF groups left; only the last tile has one)
+#pragma unroll
+        for (int u = 0; u < E_PF - 1; ++u) {
+            const int j = nfull + u;
+            if (j < n) {
+                estep_site<BPOS>(s, st, j, rt_[u], sc);
+                sc = cpn_inv_pow2_of(s.fp + s.fm);
+            }
         }
     }
     double inv = 1.0 / (s.fp + s.fm);
@@ -689,6 +710,8 @@ struct EmState {
     int* cnt_sol;       // [NI] solver iterations
     int* cnt_eval;      // [NI] log Z evaluations / derivative sweeps
     int64_t NI;
+    double* gh;                 // [9][NI] ∇logZ (3) and its Hessian (6) at the instance's CURRENT ϕ, when gh_valid
+    unsigned char* gh_valid;    // [NI]
 };
 
 // One em_iter M-step + the em_inst bookkeeping (em_algorithm.jl:152-183, :317-341) for every active
@@ -817,6 +840,11 @@ __device__ __forceinline__ void dogleg3_sel(double* p, const double* r, const do
     for (int i = 0; i < 3; ++i) p[i] = case1 ? p_i[i] : (case2 ? g[i] * s2 : fma(tau, p_diff[i], p_c[i]));
 }
 
+// Loop trip of a lane:  [take work] → [B: consume the pending (∇logZ, Hessian): accept/reject, radius, convergence, next
+// trial point] → [S: one derivative sweep at the trial point].  ∇logZ and its Hessian at the final iterate of one M-step
+// are exactly what the next M-step of the same instance needs first (they do not depend on the E-step), so they are kept
+// in `gh` and the first sweep of every later M-step is skipped (bit-identical to recomputing).  A lane whose instance ends
+// in B immediately takes the next one (two rounds per trip), so no sweep slot is wasted.
 __global__ void __launch_bounds__(M_THREADS, WS_BLOCKS) k_mstep_ws(int n_items, const int* __restrict__ items, int n_init, RegionTables rt,
                                                                     EmState st, int max_em_iters, double amax, double bmax, double cmax,
                                                                     int* __restrict__ queue,
@@ -826,124 +854,149 @@ __global__ void __launch_bounds__(M_THREADS, WS_BLOCKS) k_mstep_ws(int n_items, 
     const int lane = threadIdx.x & 31;
     const unsigned lt_mask = (1u << lane) - 1;
     const double ftol = 1e-3, eta = 1e-4;
+    const int64_t NI = st.NI;
     const SweepSite* tbl = nullptr;
     int L = 0, inst = -1, pos = -1, it = 0, evals = 0;
-    bool init = true, have = false, drained = false;
+    bool init = true, have = false, drained = false, pending = false;
+    double g[3], H[6];
     for (;;) {
-        // ---- take work (warp-aggregated fetch from the global queue)
-        bool need = !have && !drained;
-        unsigned m = __ballot_sync(0xffffffffu, need);
-        if (m) {
-            int leader = __ffs(m) - 1, base = 0;
-            if (lane == leader) base = atomicAdd(queue, __popc(m));
-            base = __shfl_sync(0xffffffffu, base, leader);
-            if (need) {
-                int item = base + __popc(m & lt_mask);
-                if (item < n_items) {
-                    inst = items ? items[item] : item;
-                    pos = item;
-                    int64_t r = inst / n_init;
-                    int64_t g0 = rt.grp_off[r];
-                    tbl = rt.sq + g0;
-                    L = (int)(rt.grp_off[r + 1] - g0);
-                    double Mr = (double)(rt.read_off[r + 1] - rt.read_off[r]);
-                    int64_t NI = st.NI;
+#pragma unroll 1
+        for (int round = 0; round < 2; ++round) {
+            // ---- take work (warp-aggregated fetch from the global queue)
+            bool need = !have && !drained;
+            unsigned m = __ballot_sync(0xffffffffu, need);
+            if (m) {
+                int leader = __ffs(m) - 1, base = 0;
+                if (lane == leader) base = atomicAdd(queue, __popc(m));
+                base = __shfl_sync(0xffffffffu, base, leader);
+                if (need) {
+                    int item = base + __popc(m & lt_mask);
+                    if (item < n_items) {
+                        inst = items ? items[item] : item;
+                        pos = item;
+                        int64_t r = inst / n_init;
+                        int64_t g0 = rt.grp_off[r];
+                        tbl = rt.sq + g0;
+                        L = (int)(rt.grp_off[r + 1] - g0);
+                        double Mr = (double)(rt.read_off[r + 1] - rt.read_off[r]);
+#pragma unroll
+                        for (int i = 0; i < 3; ++i) {
+                            CS(C_T + i) = st.ES[i * NI + inst] / Mr;
+                            double v = st.phi[i * NI + inst];
+                            CS(C_X0 + i) = v; CS(C_X + i) = v;
+                        }
+                        evals = 0; it = 0; init = true; have = true;
+                        pending = st.gh_valid[inst] != 0;
+                        if (pending) {
+#pragma unroll
+                            for (int i = 0; i < 3; ++i) g[i] = st.gh[i * NI + inst];
+#pragma unroll
+                            for (int i = 0; i < 6; ++i) H[i] = st.gh[(3 + i) * NI + inst];
+                        }
+                    } else drained = true;
+                }
+            }
+            // ---- B: trust-region bookkeeping (NLsolve trust_region_), both phases in one instruction stream
+            if (have && pending) {
+                pending = false;
+                double x[3] = {CS(C_X), CS(C_X + 1), CS(C_X + 2)};
+                double fval[3] = {g[0] - CS(C_T), g[1] - CS(C_T + 1), g[2] - CS(C_T + 2)};
+                double r[3] = {CS(C_R), CS(C_R + 1), CS(C_R + 2)};
+                double p[3] = {CS(C_P), CS(C_P + 1), CS(C_P + 2)};
+                double d[3] = {CS(C_D), CS(C_D + 1), CS(C_D + 2)};
+                double Js[6] = {CS(C_J), CS(C_J + 1), CS(C_J + 2), CS(C_J + 3), CS(C_J + 4), CS(C_J + 5)};
+                double delta = CS(C_DELTA);
+                double rp[3] = {Js[0] * p[0] + Js[1] * p[1] + Js[2] * p[2] + r[0], Js[1] * p[0] + Js[3] * p[1] + Js[4] * p[2] + r[1],
+                                Js[2] * p[0] + Js[4] * p[1] + Js[5] * p[2] + r[2]};
+                double rho = (sumabs2_3(r) - sumabs2_3(fval)) / (sumabs2_3(r) - sumabs2_3(rp));
+                const bool accept = init || (rho > eta);
+                bool x_conv = false;
+                if (accept) {
+#pragma unroll
+                    for (int i = 0; i < 3; ++i) r[i] = fval[i];
+#pragma unroll
+                    for (int i = 0; i < 6; ++i) Js[i] = H[i];
+                    double n0 = sqrt(H[0] * H[0] + H[1] * H[1] + H[2] * H[2]);
+                    double n1 = sqrt(H[1] * H[1] + H[3] * H[3] + H[4] * H[4]);
+                    double n2 = sqrt(H[2] * H[2] + H[4] * H[4] + H[5] * H[5]);
+                    d[0] = init ? (n0 == 0.0 ? 1.0 : n0) : fmax(0.1 * d[0], n0);
+                    d[1] = init ? (n1 == 0.0 ? 1.0 : n1) : fmax(0.1 * d[1], n1);
+                    d[2] = init ? (n2 == 0.0 ? 1.0 : n2) : fmax(0.1 * d[2], n2);
+                    double dx[3] = {x[0] - CS(C_XOLD), x[1] - CS(C_XOLD + 1), x[2] - CS(C_XOLD + 2)};
+                    x_conv = !init && (norminf3(dx) <= 0.0);
+                    if (!init || evals > 0) {          // remember the evaluation at the accepted point (unless it came from gh)
+#pragma unroll
+                        for (int i = 0; i < 3; ++i) st.gh[i * NI + inst] = g[i];
+#pragma unroll
+                        for (int i = 0; i < 6; ++i) st.gh[(3 + i) * NI + inst] = H[i];
+                    }
+                } else {
+#pragma unroll
+                    for (int i = 0; i < 3; ++i) x[i] -= p[i];
+                }
+                if (init) {
+                    delta = wnorm3(d, x);
+                    if (delta == 0.0) delta = 1.0;
+                } else {
+                    const double wdp = wnorm3(d, p);                 // with the scaling vector already updated (as NLsolve does)
+                    if (rho < 0.1) delta = delta / 2;
+                    else if (rho >= 0.9) delta = 2 * wdp;
+                    else if (rho >= 0.5) delta = fmax(delta, 2 * wdp);
+                }
+                const bool threw = init && !allfinite3(fval);
+                const bool conv = accept && !threw && (x_conv || norminf3(r) <= ftol);
+                const bool stopped = anynan3(x) || anynan3(fval);
+                int code = 0;
+                if (threw) code = 2;
+                else if (conv) code = 1;
+                else if (stopped || (!init && it >= 20)) code = 2;
+                if (code == 0) {
+                    it = init ? 1 : it + 1;
+                    init = false;
+                    dogleg3_sel(p, r, d, Js, delta);
 #pragma unroll
                     for (int i = 0; i < 3; ++i) {
-                        CS(C_T + i) = st.ES[i * NI + inst] / Mr;
-                        double v = st.phi[i * NI + inst];
-                        CS(C_X0 + i) = v; CS(C_X + i) = v;
+                        CS(C_XOLD + i) = x[i]; CS(C_X + i) = x[i] + p[i]; CS(C_P + i) = p[i]; CS(C_R + i) = r[i]; CS(C_D + i) = d[i];
                     }
-                    evals = 0; it = 0; init = true; have = true;
-                } else drained = true;
+#pragma unroll
+                    for (int i = 0; i < 6; ++i) CS(C_J + i) = Js[i];
+                    CS(C_DELTA) = delta;
+                } else {
+                    // em_iter tail (:172-181) + em_inst bookkeeping (:327-341)
+                    double x0[3] = {CS(C_X0), CS(C_X0 + 1), CS(C_X0 + 2)}, nx[3];
+                    bool gh_ok;
+                    if (code == 2) {
+                        nx[0] = x0[0]; nx[1] = x0[1]; nx[2] = x0[2];
+                        gh_ok = init && !threw;               // ϕ stays at x0: gh still describes it only if no step was accepted
+                    } else {
+                        nx[0] = fmax(-amax, fmin(x[0], amax));
+                        nx[1] = fmax(-bmax, fmin(x[1], bmax));
+                        nx[2] = fmax(-cmax, fmin(x[2], cmax));
+                        gh_ok = (nx[0] == x[0]) && (nx[1] == x[1]) && (nx[2] == x[2]);   // gh was evaluated at x, not at the clamped point
+                    }
+                    double d0 = x0[0] - nx[0], d1 = x0[1] - nx[1], d2 = x0[2] - nx[2];
+                    bool cv = sqrt(d0 * d0 + d1 * d1 + d2 * d2) <= 3.0e-2;
+                    int i = st.iter[inst];
+                    bool hit = i >= max_em_iters;
+                    i += 1;
+                    st.phi[inst] = nx[0]; st.phi[NI + inst] = nx[1]; st.phi[2 * NI + inst] = nx[2];
+                    st.iter[inst] = i;
+                    st.cnt_em[inst] += 1; st.cnt_sol[inst] += init ? 0 : it; st.cnt_eval[inst] += evals;
+                    st.gh_valid[inst] = gh_ok ? 1 : 0;
+                    bool done = cv || hit;
+                    if (done) st.status[inst] = (cv && i > 2) ? 1 : 2;
+                    alive[pos] = done ? 0 : 1;
+                    have = false;
+                }
             }
+            if (!__any_sync(0xffffffffu, !have && !drained)) break;
         }
         if (!__any_sync(0xffffffffu, have)) break;
+        // ---- S: one derivative sweep at the current (trial) point of every busy lane
         if (have) {
-            // ---- one derivative sweep at the current point
-            double x[3] = {CS(C_X), CS(C_X + 1), CS(C_X + 2)};
-            double g[3], H[6];
-            eval_grad_hess(tbl, L, x[0], x[1], x[2], g, H);
+            eval_grad_hess(tbl, L, CS(C_X), CS(C_X + 1), CS(C_X + 2), g, H);
             evals += 1;
-            // ---- trust-region bookkeeping (NLsolve trust_region_), both phases in one instruction stream
-            double fval[3] = {g[0] - CS(C_T), g[1] - CS(C_T + 1), g[2] - CS(C_T + 2)};
-            double r[3] = {CS(C_R), CS(C_R + 1), CS(C_R + 2)};
-            double p[3] = {CS(C_P), CS(C_P + 1), CS(C_P + 2)};
-            double d[3] = {CS(C_D), CS(C_D + 1), CS(C_D + 2)};
-            double Js[6] = {CS(C_J), CS(C_J + 1), CS(C_J + 2), CS(C_J + 3), CS(C_J + 4), CS(C_J + 5)};
-            double delta = CS(C_DELTA);
-            double rp[3] = {Js[0] * p[0] + Js[1] * p[1] + Js[2] * p[2] + r[0], Js[1] * p[0] + Js[3] * p[1] + Js[4] * p[2] + r[1],
-                            Js[2] * p[0] + Js[4] * p[1] + Js[5] * p[2] + r[2]};
-            double rho = (sumabs2_3(r) - sumabs2_3(fval)) / (sumabs2_3(r) - sumabs2_3(rp));
-            const bool accept = init || (rho > eta);
-            bool x_conv = false;
-            if (accept) {
-#pragma unroll
-                for (int i = 0; i < 3; ++i) r[i] = fval[i];
-#pragma unroll
-                for (int i = 0; i < 6; ++i) Js[i] = H[i];
-                double n0 = sqrt(H[0] * H[0] + H[1] * H[1] + H[2] * H[2]);
-                double n1 = sqrt(H[1] * H[1] + H[3] * H[3] + H[4] * H[4]);
-                double n2 = sqrt(H[2] * H[2] + H[4] * H[4] + H[5] * H[5]);
-                d[0] = init ? (n0 == 0.0 ? 1.0 : n0) : fmax(0.1 * d[0], n0);
-                d[1] = init ? (n1 == 0.0 ? 1.0 : n1) : fmax(0.1 * d[1], n1);
-                d[2] = init ? (n2 == 0.0 ? 1.0 : n2) : fmax(0.1 * d[2], n2);
-                double dx[3] = {x[0] - CS(C_XOLD), x[1] - CS(C_XOLD + 1), x[2] - CS(C_XOLD + 2)};
-                x_conv = !init && (norminf3(dx) <= 0.0);
-            } else {
-#pragma unroll
-                for (int i = 0; i < 3; ++i) x[i] -= p[i];
-            }
-            if (init) {
-                delta = wnorm3(d, x);
-                if (delta == 0.0) delta = 1.0;
-            } else {
-                const double wdp = wnorm3(d, p);                     // with the scaling vector already updated (as NLsolve does)
-                if (rho < 0.1) delta = delta / 2;
-                else if (rho >= 0.9) delta = 2 * wdp;
-                else if (rho >= 0.5) delta = fmax(delta, 2 * wdp);
-            }
-            const bool threw = init && !allfinite3(fval);
-            const bool conv = accept && !threw && (x_conv || norminf3(r) <= ftol);
-            const bool stopped = anynan3(x) || anynan3(fval);
-            int code = 0;
-            if (threw) code = 2;
-            else if (conv) code = 1;
-            else if (stopped || (!init && it >= 20)) code = 2;
-            if (code == 0) {
-                it = init ? 1 : it + 1;
-                init = false;
-                dogleg3_sel(p, r, d, Js, delta);
-#pragma unroll
-                for (int i = 0; i < 3; ++i) {
-                    CS(C_XOLD + i) = x[i]; CS(C_X + i) = x[i] + p[i]; CS(C_P + i) = p[i]; CS(C_R + i) = r[i]; CS(C_D + i) = d[i];
-                }
-#pragma unroll
-                for (int i = 0; i < 6; ++i) CS(C_J + i) = Js[i];
-                CS(C_DELTA) = delta;
-            } else {
-                // em_iter tail (:172-181) + em_inst bookkeeping (:327-341)
-                double x0[3] = {CS(C_X0), CS(C_X0 + 1), CS(C_X0 + 2)}, nx[3];
-                if (code == 2) { nx[0] = x0[0]; nx[1] = x0[1]; nx[2] = x0[2]; }
-                else {
-                    nx[0] = fmax(-amax, fmin(x[0], amax));
-                    nx[1] = fmax(-bmax, fmin(x[1], bmax));
-                    nx[2] = fmax(-cmax, fmin(x[2], cmax));
-                }
-                double d0 = x0[0] - nx[0], d1 = x0[1] - nx[1], d2 = x0[2] - nx[2];
-                bool cv = sqrt(d0 * d0 + d1 * d1 + d2 * d2) <= 3.0e-2;
-                int64_t NI = st.NI;
-                int i = st.iter[inst];
-                bool hit = i >= max_em_iters;
-                i += 1;
-                st.phi[inst] = nx[0]; st.phi[NI + inst] = nx[1]; st.phi[2 * NI + inst] = nx[2];
-                st.iter[inst] = i;
-                st.cnt_em[inst] += 1; st.cnt_sol[inst] += init ? 0 : it; st.cnt_eval[inst] += evals;
-                bool done = cv || hit;
-                if (done) st.status[inst] = (cv && i > 2) ? 1 : 2;
-                alive[pos] = done ? 0 : 1;
-                have = false;
-            }
+            pending = true;
         }
     }
 #undef CS
@@ -1215,7 +1268,12 @@ int fit_impl(cpn_ctx* ctx, bool on_device, int64_t R, const int64_t* grp_off, co
             for (int64_t r = 0; r < R; ++r) h_order[cnt[pk.h_grp_off[r + 1] - pk.h_grp_off[r]]++] = (int)r;
         }
         CPN_CUDA(ctx, order.upload(h_order.data(), R, s));
-        EmState st{phi.p, ES.p, iter.p, stat.p, c_em.p, c_sol.p, c_ev.p, NI};
+        DevBuf<double> gh;
+        DevBuf<unsigned char> gh_valid;
+        CPN_CUDA(ctx, gh.alloc(9 * NI, s));
+        CPN_CUDA(ctx, gh_valid.alloc(NI, s));
+        CPN_CUDA(ctx, cudaMemsetAsync(gh_valid.p, 0, NI, s));
+        EmState st{phi.p, ES.p, iter.p, stat.p, c_em.p, c_sol.p, c_ev.p, NI, gh.p, gh_valid.p};
         { KTimer kt(ctx, CPN_K_PREP);
           k_init_state<<<blocks_for(NI, 256), 256, 0, s>>>(NI, n_init, d_phi0.p, st, items_a.p, order.p); }
         int n_active = (int)NI;
