@@ -82,6 +82,8 @@ class RegStruct:
     log_gs: np.ndarray = field(default_factory=lambda: np.zeros((0, 4)))   # pm, pp, qm, qp
     Q: float = -math.inf
 
+    group_view: object = None     # get_grp_info!-scale copy (N_l, ρ_l, d_l) kept when the struct is rescaled to the per-CpG chain
+
     def set_calls(self, lu, lm):
         self.log_pyx_u = np.ascontiguousarray(lu, dtype=np.float64)
         self.log_pyx_m = np.ascontiguousarray(lm, dtype=np.float64)
@@ -277,6 +279,78 @@ class Engine:
         return out
 
 
+    # ---- two-sample test ---------------------------------------------------------------------------------
+    def two_samp_null_stats_batch(self, rs_ref, calls_s1, calls_s2, perms, config, phi0s=None, rng=None):
+        """pmap_two_samp_null_stats (src/two_samp_perm_tests.jl:41-87) for ALL permutations of a region in one batch.
+        perms [P, n1]: ascending 1-based indices into vcat(calls_s1, calls_s2) that form sample 1; the rest, in order, is
+        sample 2.  Every (permutation, half) becomes one row of a CSR batch: 2P multi-start EM fits, 2P summaries, P CMDs.
+        phi0s [P, 2, max_em_init, 3] replaces the 2P gen_ϕ0s draws.  Returns T_null [P, 3, K] (NaN where a fit failed)."""
+        perms = np.asarray(perms, dtype=np.int64)
+        P, n1 = perms.shape
+        lu = np.concatenate([calls_s1[0], calls_s2[0]]); lm = np.concatenate([calls_s1[1], calls_s2[1]])
+        n, L = lu.shape
+        n2 = n - n1
+        mask = np.ones((P, n), dtype=bool)
+        mask[np.arange(P)[:, None], perms - 1] = False
+        rest = np.nonzero(mask)[1].reshape(P, n2)                          # deleteat!(aux_calls, perm_ids): the rest, in order
+        order = np.concatenate([perms - 1, rest], axis=1)                  # [P, n]: rows of half 1 then rows of half 2
+        lu_b = lu[order].reshape(-1); lm_b = lm[order].reshape(-1)
+        R2 = 2 * P
+        grp_off = (np.arange(R2 + 1) * L).astype(np.int64)
+        Nl = np.tile(np.asarray(rs_ref.Nl, dtype=np.float64), R2); rho_l = np.tile(np.asarray(rs_ref.rho_l, dtype=np.float64), R2)
+        d_l = np.tile(np.asarray(rs_ref.dl, dtype=np.float64), R2)
+        reads = np.tile(np.array([n1, n2], dtype=np.int64), P)
+        read_off = np.concatenate([[0], np.cumsum(reads)]).astype(np.int64)
+        if phi0s is None:
+            from .simulations import gen_phi0s
+            phi0s = gen_phi0s(rng or np.random.default_rng(), R2, config.max_em_init)
+        fit = self.lib.fit_batch(grp_off, Nl, rho_l, d_l, read_off, lu_b, lm_b, np.asarray(phi0s).reshape(R2, config.max_em_init, 3),
+                                 config.max_em_init, config.max_em_iters, (AMAX, BMAX, CMAX), config.mstep_mode, device=self.device)
+        K = rs_ref.nls_rgs.num
+        N = rs_ref.N
+        cpg_off = np.array([0, N], dtype=np.int64); sub_off = np.array([0, K], dtype=np.int64)
+        ss = self.lib.stat_sums_batch(fit["phi_hat"], cpg_off, rs_ref.rho_n, rs_ref.dn, sub_off, rs_ref.nls_rgs.cpg_p, rs_ref.nls_rgs.cpg_q,
+                                      reg_of=np.zeros(R2, dtype=np.int64), device=self.device)
+        pa = np.arange(0, R2, 2, dtype=np.int64)
+        cmd, _ = self.lib.cmd_batch(pa, pa + 1, fit["phi_hat"], np.zeros(R2, dtype=np.int64), ss["ex_off"], ss["ex"], ss["exx"], ss["k_off"],
+                                    ss["nme"], cpg_off, rs_ref.rho_n, rs_ref.dn, sub_off, rs_ref.nls_rgs.cpg_p, rs_ref.nls_rgs.cpg_q,
+                                    device=self.device)
+        mml = ss["mml"].reshape(P, 2, K); nme = ss["nme"].reshape(P, 2, K)
+        T = np.stack([mml[:, 0] - mml[:, 1], nme[:, 0] - nme[:, 1], cmd.reshape(P, K)], axis=1)
+        bad = (fit["pick"].reshape(P, 2) < 0).any(axis=1)                 # either ϕ̂ empty → all three statistics NaN (:65)
+        T[bad] = np.nan
+        return T
+
+    def diff_two_samp_comp_region(self, mod_s1, mod_s2, calls_s1, calls_s2, config, rng=None, perms=None, phi0s=None):
+        """pmap_diff_two_samp_comp (src/two_samp_perm_tests.jl:157-273) for one region: observed statistics from the two fitted
+        models (per-CpG scale, with summaries), null statistics from refits of permuted reads (group scale features are taken
+        from `calls`' owner mod_s1: Nl, rho_l, dl must describe the CpG groups), p-values by counting."""
+        K = mod_s1.nls_rgs.num
+        T_obs = np.stack([mod_s1.mml - mod_s2.mml, mod_s1.nme - mod_s2.nme, self.comp_cmd_pairs([mod_s1, mod_s2], [(0, 1)])[0]])
+        pval = np.full((3, K), np.nan)
+        out = dict(T=T_obs, pval=pval, cnt=None, n_valid=None, exact=None)
+        if not config.pval_comp:
+            return out
+        n1, n2 = calls_s1[0].shape[0], calls_s2[0].shape[0]
+        Lc = math.comb(n1 + n2, n1)
+        if Lc <= 20:
+            return out
+        exact = Lc < config.LMAX_TWO_SAMP
+        if perms is None:
+            if exact:
+                perms = np.array(list(combinations(range(1, n1 + n2 + 1), n1)), dtype=np.int64)
+            else:    # sort!(StatsBase.sample(1:n, n1; replace=false)) LMAX_TWO_SAMP times (:211-214)
+                rng = rng or np.random.default_rng()
+                perms = np.stack([np.sort(rng.choice(np.arange(1, n1 + n2 + 1), n1, replace=False)) for _ in range(config.LMAX_TWO_SAMP)])
+        import copy
+        ref = copy.copy(mod_s1.group_view if mod_s1.group_view is not None else mod_s1)    # "back to group scale" (:198-199)
+        ref.nls_rgs, ref.rho_n, ref.dn, ref.N = mod_s1.nls_rgs, mod_s1.rho_n, mod_s1.dn, mod_s1.N
+        T_null = self.two_samp_null_stats_batch(ref, calls_s1, calls_s2, perms, config, phi0s, rng)
+        cnt, nv, p = self.lib.two_samp_pvals(np.array([0, K]), len(perms), T_obs.reshape(-1), T_null.reshape(-1), exact, device=self.device)
+        out.update(pval=p.reshape(3, K), cnt=cnt.reshape(3, K), n_valid=nv.reshape(3, K), exact=exact, T_null=T_null)
+        return out
+
+
 _default = None
 
 
@@ -293,7 +367,14 @@ def get_phihat(rs, config, phi0s=None, rng=None, engine=None):
 
 
 def rscle_grp_mod(rs):
-    """src/nanopore.jl:269-280 — redefine groups as singletons (per-CpG chain)."""
+    """src/nanopore.jl:269-280 — redefine groups as singletons (per-CpG chain).  The group-scale features are remembered in
+    rs.group_view (the reference recomputes them with get_grp_info! when it goes "back to group scale",
+    src/two_samp_perm_tests.jl:198-199)."""
+    if rs.group_view is None and rs.L != rs.N:
+        import copy
+        gv = copy.copy(rs)
+        gv.Nl, gv.rho_l, gv.dl = np.array(rs.Nl), np.array(rs.rho_l), np.array(rs.dl)
+        rs.group_view = gv
     rs.L = rs.N
     rs.dl = np.asarray(rs.dn, dtype=np.float64)
     rs.rho_l = np.asarray(rs.rho_n, dtype=np.float64)

@@ -415,6 +415,43 @@ def test_two_sample_null_stats_pipeline(engine, orc, cpn):
     assert np.all((np.isnan(tc)) | ((tc > -1e-6) & (tc < 1.0)))
 
 
+def test_two_sample_batched_permutations(engine, orc, cpn):
+    """All permutations of a region in one batch == the one-permutation entry point, and p-value counting on the result
+    == the oracle's counting (two_samp_perm_tests.jl:230-258)."""
+    nb = cpn.simulations.make_nano_batch(1, M=16, seed=77)
+    rg = nb.region(0)
+    cfg = cpn.CpelNanoConfig(max_em_init=2, LMAX_TWO_SAMP=30)
+    ref = cpn.RegStruct(chr="c", chrst=int(nb.chrst[0]), chrend=int(nb.chrend[0]), N=int(nb.cpg_off[1]), L=rg["L"], Nl=rg["Nl"], rho_l=rg["rho_l"],
+                        dl=rg["d_l"], rho_n=nb.rho_n, dn=nb.d_n, cpg_pos=nb.cpg_pos)
+    engine.get_nls_reg_info(ref, cfg)
+    rng = np.random.default_rng(2)
+    P = 30
+    perms = np.stack([np.sort(rng.choice(np.arange(1, 17), 8, replace=False)) for _ in range(P)])
+    phi0 = cpn.simulations.gen_phi0s(rng, 2 * P, 2).reshape(P, 2, 2, 3)
+    s1, s2 = (rg["lu"][:8], rg["lm"][:8]), (rg["lu"][8:], rg["lm"][8:])
+    T = engine.two_samp_null_stats_batch(ref, s1, s2, perms, cfg, phi0s=phi0)
+    assert T.shape == (P, 3, ref.nls_rgs.num)
+    for pi in (0, 7, 29):
+        tm, tn, tc = cpn.pmap_two_samp_null_stats(ref, s1, s2, perms[pi], cfg, phi0s=phi0[pi], engine=engine)
+        assert np.array_equal(T[pi, 0], tm, equal_nan=True) and np.array_equal(T[pi, 1], tn, equal_nan=True)
+        assert np.array_equal(T[pi, 2], tc, equal_nan=True)
+    # full region test: two fitted models (here: fits of the two halves), then permutation p-values
+    m1, m2 = cpn.RegStruct(**{k: getattr(ref, k) for k in ("chr", "chrst", "chrend", "N", "L", "Nl", "rho_l", "dl", "rho_n", "dn", "cpg_pos")}), None
+    import copy
+    m2 = copy.copy(m1)
+    m1.set_calls(*s1); m2.set_calls(*s2)
+    engine.get_phihat_batch([m1, m2], cpn.CpelNanoConfig(max_em_init=4), rng=np.random.default_rng(5))
+    if len(m1.phihat) == 3 and len(m2.phihat) == 3:
+        cpn.rscle_grp_mod(m1); cpn.rscle_grp_mod(m2)
+        engine.get_stat_sums_batch([m1, m2], cfg)
+        out = engine.diff_two_samp_comp_region(m1, m2, s1, s2, cfg, perms=perms, phi0s=phi0)
+        c_o, nv_o, p_o = orc.two_samp_pvals(out["T"], out["T_null"], out["exact"])
+        assert np.array_equal(out["cnt"], c_o) and np.array_equal(out["n_valid"], nv_o) and np.array_equal(out["pval"], p_o, equal_nan=True)
+        assert out["exact"] is False
+        ok = ~np.isnan(out["pval"][0])
+        assert np.all((out["pval"][:, ok] > 0) & (out["pval"][:, ok] <= 1))
+
+
 def test_analyze_regions_filters(engine, cpn):
     """pmap_analyze_reg's data filters (nanopore.jl:309,322-326): regions failing them keep proc == false."""
     nb = cpn.simulations.make_nano_batch(5, M=30, seed=3)
