@@ -321,7 +321,11 @@ def main():
             ok = (fit_c["pick"] >= 0) & (pick[:n_s] >= 0)
             if ok.any():
                 dq = np.abs(fit_c["Q"][ok] - host_out["Q"].numpy()[:n_s][ok]) / np.abs(fit_c["Q"][ok])
-                line["cpu_baseline"]["parity_on_sample"] = {"regions": int(ok.sum()), "max_rel_dQ": float(dq.max())}
+                dphi = np.abs(fit_c["phi_hat"][ok] - host_out["phi_hat"].numpy().reshape(R, 3)[:n_s][ok])
+                line["cpu_baseline"]["parity_on_sample"] = {
+                    "regions": int(ok.sum()), "median_rel_dQ": float(np.median(dq)), "p99_rel_dQ": float(np.percentile(dq, 99)),
+                    "median_abs_dphi": [float(v) for v in np.median(dphi, axis=0)],
+                    "note": "picked optimum; EM output of the reference algorithm itself moves by this much under a 1-ulp input change (DESIGN.md §6)"}
         print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()

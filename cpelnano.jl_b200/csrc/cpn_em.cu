@@ -32,6 +32,9 @@ constexpr int M_THREADS = 128;     // lanes (EM instances) per M-step block
 #ifndef WS_BLOCKS
 #define WS_BLOCKS 4                 // resident M-step blocks per SM the register budget is tuned for
 #endif
+#ifndef WS_ROUNDS
+#define WS_ROUNDS 2                 // take-work + bookkeeping rounds per loop trip of the M-step
+#endif
 constexpr double LLR_CLAMP = 300.0;
 constexpr double CBRT_EPS = 6.0554544523933395e-6;
 
@@ -861,7 +864,7 @@ __global__ void __launch_bounds__(M_THREADS, WS_BLOCKS) k_mstep_ws(int n_items, 
     double g[3], H[6];
     for (;;) {
 #pragma unroll 1
-        for (int round = 0; round < 2; ++round) {
+        for (int round = 0; round < WS_ROUNDS; ++round) {
             // ---- take work (warp-aggregated fetch from the global queue)
             bool need = !have && !drained;
             unsigned m = __ballot_sync(0xffffffffu, need);
@@ -1209,6 +1212,9 @@ int pack_regions(cpn_ctx* ctx, PackedRegions& pk, bool on_device, bool with_read
         { KTimer kt(ctx, CPN_K_PREP);
           k_prep_emis<<<blocks_for(R * 32, 128), 128, 0, s>>>(R, pk.grp_off.p, pk.read_off.p, pk.obs_off.p, pk.lu.p, pk.lm.p, pk.ew_off.p,
                                                               pk.rb_off.p, pk.ew.p, pk.rb.p); }
+        // the raw emissions are not needed once packed: give the (stream-ordered) memory back before the EM loop
+        pk.lu.own.release();
+        pk.lm.own.release();
         CPN_CUDA(ctx, cudaStreamSynchronize(s));   // h_* staging vectors go out of scope
         pk.rt.read_off = pk.read_off.p; pk.rt.ew_off = pk.ew_off.p; pk.rt.rb_off = pk.rb_off.p; pk.rt.ew = pk.ew.p; pk.rt.rb = pk.rb.p;
     }
