@@ -42,11 +42,18 @@ constexpr double CBRT_EPS = 6.0554544523933395e-6;
 // the group (0 for the first group).  Small on purpose: the records of all chains resident on an SM must stay in L1.
 struct __align__(32) SweepSite { double na, nb, id, id2; };
 
+// What an E-step warp needs to know about its EM instance, stored by POSITION in the active list (written by
+// k_init_state / k_compact_scatter) so that the warp's first loads do not depend on each other:
+// instance id, region geometry, start of the packed emissions, and the instance's current ϕ.
+struct __align__(32) ItemDesc { int inst, L, M, pad; int64_t g0, ew_off; };
+struct __align__(32) RegionDesc { int64_t g0, ew_off; int32_t L, M; int64_t pad; };
+
 struct RegionTables {
     // per group (offsets grp_off): N_l, N_l·ρ_l and 1/d_l (coupling l→l+1; entry L-1 unused)
     const int64_t* grp_off;
     const double *na, *nb, *invd;
-    const SweepSite* sq;       // per group: everything the second-order sweep of the M-step needs, one 64-byte record
+    const SweepSite* sq;       // per group: what the second-order sweep of the M-step needs, one 32-byte record
+    const RegionDesc* rdesc;   // [R]
     // emission likelihood ratios r = exp(log p(y|+1) − log p(y|−1)), 1 for unobserved / padding lanes
     const int64_t* read_off;   // [R+1]
     const int64_t* ew_off;     // [R] start of the region's block: [chunk][l][32]
@@ -258,30 +265,31 @@ __device__ __forceinline__ void estep_chunk(SiteTile& st, int L, int lane, const
 #ifndef E_BLOCKS
 #define E_BLOCKS 4
 #endif
-__global__ void __launch_bounds__(E_WARPS * 32, E_BLOCKS) k_estep(int n_items, const int* __restrict__ items, int n_init, RegionTables rt,
-                                                         const double* __restrict__ phi /*[3][NI]*/, int64_t NI,
-                                                         double* __restrict__ ES /*[3][NI]*/) {
+__global__ void __launch_bounds__(E_WARPS * 32, E_BLOCKS) k_estep(int n_items, const ItemDesc* __restrict__ desc,
+                                                                   const double* __restrict__ phil /*[3][cap] by list position*/, int64_t cap,
+                                                                   RegionTables rt, int64_t NI, double* __restrict__ ES /*[3][NI]*/) {
     __shared__ SiteTile tiles[E_WARPS];
     int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
     int item = blockIdx.x * E_WARPS + w;
     if (item >= n_items) return;
-    int inst = items ? items[item] : item;
-    int64_t r = inst / n_init;
-    int64_t g0 = rt.grp_off[r];
-    int L = (int)(rt.grp_off[r + 1] - g0);
-    int64_t M = rt.read_off[r + 1] - rt.read_off[r];
-    double a = phi[inst], b = phi[NI + inst], c = phi[2 * NI + inst];
-    bool bpos = c >= 0.0;
+    // one round of independent loads: descriptor (two 16-byte vectors) and ϕ
+    const int4* dq = reinterpret_cast<const int4*>(desc + item);
+    const int4 d0 = __ldg(dq);
+    const longlong2 d1 = __ldg(reinterpret_cast<const longlong2*>(dq + 1));
+    double a = phil[item], b = phil[cap + item], c = phil[2 * cap + item];
+    const int inst = d0.x, L = d0.y, M = d0.z;
+    const int64_t g0 = d1.x;
+    bool bpos = __double2hiint(c) >= 0;
     double cabs = fabs(c);
-    const double* ew_r = rt.ew + rt.ew_off[r];
+    const double* ew_r = rt.ew + d1.y;
     double acc0 = 0, acc1 = 0, acc2 = 0;
-    int nchunk = (int)((M + 31) >> 5);
+    int nchunk = (M + 31) >> 5;
     for (int ch = 0; ch < nchunk; ++ch) {
         double o[3];
         const double* ewc = ew_r + (size_t)ch * L * 32;
         if (bpos) estep_chunk<true>(tiles[w], L, lane, rt.na + g0, rt.nb + g0, rt.invd + g0, ewc, a, b, cabs, o);
         else estep_chunk<false>(tiles[w], L, lane, rt.na + g0, rt.nb + g0, rt.invd + g0, ewc, a, b, cabs, o);
-        bool live = (int64_t)ch * 32 + lane < M;
+        bool live = ch * 32 + lane < M;
         acc0 += cpn_warp_sum(live ? o[0] : 0.0);
         acc1 += cpn_warp_sum(live ? o[1] : 0.0);
         acc2 += cpn_warp_sum(live ? o[2] : 0.0);
@@ -289,6 +297,20 @@ __global__ void __launch_bounds__(E_WARPS * 32, E_BLOCKS) k_estep(int n_items, c
     if (lane == 0) {
         ES[inst] = acc0; ES[NI + inst] = acc1; ES[2 * NI + inst] = acc2;
     }
+}
+
+// Builds the position-indexed descriptors for a list of instances (items == null: identity list).
+__global__ void k_make_desc(int n_items, const int* __restrict__ items, int n_init, const RegionDesc* __restrict__ rdesc,
+                            const double* __restrict__ phi /*[3][NI]*/, int64_t NI, ItemDesc* __restrict__ desc, double* __restrict__ phil,
+                            int64_t cap) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n_items) return;
+    int inst = items ? items[i] : i;
+    RegionDesc rd = rdesc[inst / n_init];
+    ItemDesc d;
+    d.inst = inst; d.L = rd.L; d.M = rd.M; d.pad = 0; d.g0 = rd.g0; d.ew_off = rd.ew_off;
+    desc[i] = d;
+    phil[i] = phi[inst]; phil[cap + i] = phi[NI + inst]; phil[2 * cap + i] = phi[2 * NI + inst];
 }
 
 // ---------------------------------------------------------------------------------------------------
@@ -1152,6 +1174,7 @@ struct PackedRegions {
     DevBuf<int64_t> obs_off, ew_off, rb_off;
     DevBuf<double> na, nb, invd, ew, rb;
     DevBuf<SweepSite> sq;
+    DevBuf<RegionDesc> rdesc;
     std::vector<int64_t> h_grp_off, h_read_off;
     int64_t R = 0, sumL = 0, n_obs = 0;
     RegionTables rt{};
@@ -1212,6 +1235,14 @@ int pack_regions(cpn_ctx* ctx, PackedRegions& pk, bool on_device, bool with_read
         { KTimer kt(ctx, CPN_K_PREP);
           k_prep_emis<<<blocks_for(R * 32, 128), 128, 0, s>>>(R, pk.grp_off.p, pk.read_off.p, pk.obs_off.p, pk.lu.p, pk.lm.p, pk.ew_off.p,
                                                               pk.rb_off.p, pk.ew.p, pk.rb.p); }
+        std::vector<RegionDesc> h_desc(R);
+        for (int64_t r = 0; r < R; ++r) {
+            h_desc[r].g0 = pk.h_grp_off[r]; h_desc[r].ew_off = h_ew[r];
+            h_desc[r].L = (int32_t)(pk.h_grp_off[r + 1] - pk.h_grp_off[r]); h_desc[r].M = (int32_t)(pk.h_read_off[r + 1] - pk.h_read_off[r]);
+            h_desc[r].pad = 0;
+        }
+        CPN_CUDA(ctx, pk.rdesc.upload(h_desc.data(), R, s));
+        pk.rt.rdesc = pk.rdesc.p;
         // the raw emissions are not needed once packed: give the (stream-ordered) memory back before the EM loop
         pk.lu.own.release();
         pk.lm.own.release();
@@ -1257,6 +1288,10 @@ int fit_impl(cpn_ctx* ctx, bool on_device, int64_t R, const int64_t* grp_off, co
         CPN_CUDA(ctx, items_a.alloc(NI, s)); CPN_CUDA(ctx, items_b.alloc(NI, s)); CPN_CUDA(ctx, n_next.alloc(2, s));
         DevBuf<unsigned char> alive;
         DevBuf<int> blk_cnt;
+        DevBuf<ItemDesc> idesc;
+        DevBuf<double> phil;
+        CPN_CUDA(ctx, idesc.alloc(NI, s));
+        CPN_CUDA(ctx, phil.alloc(3 * NI, s));
         CPN_CUDA(ctx, alive.alloc(NI, s));
         CPN_CUDA(ctx, blk_cnt.alloc((NI + CP_TILE - 1) / CP_TILE, s));
         int ws_blocks_per_sm = 1;
@@ -1287,8 +1322,10 @@ int fit_impl(cpn_ctx* ctx, bool on_device, int64_t R, const int64_t* grp_off, co
         int* nxt = items_b.p;
         for (int it = 0; it < max_em_iters && n_active > 0; ++it) {
             CPN_CUDA(ctx, cudaMemsetAsync(n_next.p, 0, 2 * sizeof(int), s));     // [0] survivors, [1] work-queue head
+            { KTimer kt(ctx, CPN_K_PREP);
+              k_make_desc<<<blocks_for(n_active, 256), 256, 0, s>>>(n_active, cur, n_init, pk.rt.rdesc, phi.p, NI, idesc.p, phil.p, NI); }
             { KTimer kt(ctx, CPN_K_ESTEP);
-              k_estep<<<blocks_for(n_active, E_WARPS), E_WARPS * 32, 0, s>>>(n_active, cur, n_init, pk.rt, phi.p, NI, ES.p); }
+              k_estep<<<blocks_for(n_active, E_WARPS), E_WARPS * 32, 0, s>>>(n_active, idesc.p, phil.p, NI, pk.rt, NI, ES.p); }
             if (mstep_mode == CPN_MSTEP_ANALYTIC) {
                 unsigned grid = std::min<unsigned>(blocks_for(n_active, M_THREADS), (unsigned)(ctx->sm_count * ws_blocks_per_sm));
                 KTimer kt(ctx, CPN_K_MSTEP);
@@ -1447,7 +1484,12 @@ int cpn_estep_batch(cpn_ctx* ctx, int64_t R, const int64_t* grp_off, const doubl
         CPN_CUDA(ctx, d_phi.alloc(3 * R, s)); CPN_CUDA(ctx, d_ES.alloc(3 * R, s)); CPN_CUDA(ctx, d_ESo.alloc(3 * R, s));
         CPN_CUDA(ctx, d_Q.alloc(R, s));
         { KTimer kt(ctx, CPN_K_PREP); k_pack_phi<<<blocks_for(R, 256), 256, 0, s>>>(R, d_phi_in.p, d_phi.p); }
-        { KTimer kt(ctx, CPN_K_ESTEP); k_estep<<<blocks_for(R, E_WARPS), E_WARPS * 32, 0, s>>>((int)R, nullptr, 1, pk.rt, d_phi.p, R, d_ES.p); }
+        DevBuf<ItemDesc> idesc;
+        DevBuf<double> phil;
+        CPN_CUDA(ctx, idesc.alloc(R, s)); CPN_CUDA(ctx, phil.alloc(3 * R, s));
+        { KTimer kt(ctx, CPN_K_PREP);
+          k_make_desc<<<blocks_for(R, 256), 256, 0, s>>>((int)R, nullptr, 1, pk.rt.rdesc, d_phi.p, R, idesc.p, phil.p, R); }
+        { KTimer kt(ctx, CPN_K_ESTEP); k_estep<<<blocks_for(R, E_WARPS), E_WARPS * 32, 0, s>>>((int)R, idesc.p, phil.p, R, pk.rt, R, d_ES.p); }
         { KTimer kt(ctx, CPN_K_PREP); k_unpack3<<<blocks_for(R, 256), 256, 0, s>>>(R, d_ES.p, d_ESo.p); }
         CPN_CUDA(ctx, d_ESo.download(ES, 3 * R, s));
         if (ave_logpy) {
