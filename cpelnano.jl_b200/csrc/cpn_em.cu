@@ -447,12 +447,42 @@ __device__ __forceinline__ SitePot site_pot(const SweepSite& r, int l, bool neg,
 // The loop is software-pipelined by hand: while the recursion consumes group l, the record of group l+2 is being
 // loaded and the two exponentials of group l+1 are evaluated (they do not depend on the message), so the only serial
 // chain is the 2-state recursion itself.
-__device__ void eval_grad_hess(const SweepSite* __restrict__ tbl, int L, double a, double b, double c, double g[3], double H[6]) {
+// RING = true (work-stealing kernel): the records travel global → shared memory with cp.async into a private 4-slot ring
+// per lane, issued three groups ahead.  An asynchronous copy has no destination register, so the compiler cannot sink it
+// next to its use the way it does with an ordinary load whose value is only needed one iteration later.
+constexpr int RING_SLOTS = 4;
+__device__ __forceinline__ void ring_issue(double2* ring, int slot, const SweepSite* src) {
+    // two 16-byte halves of the 32-byte record → ring[(slot*2 + half) * M_THREADS + tid]
+    unsigned d0 = (unsigned)__cvta_generic_to_shared(ring + (slot * 2 + 0) * M_THREADS + threadIdx.x);
+    unsigned d1 = (unsigned)__cvta_generic_to_shared(ring + (slot * 2 + 1) * M_THREADS + threadIdx.x);
+    const char* g = reinterpret_cast<const char*>(src);
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" ::"r"(d0), "l"(g));
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" ::"r"(d1), "l"(g + 16));
+    asm volatile("cp.async.commit_group;");
+}
+__device__ __forceinline__ SweepSite ring_read(const double2* ring, int slot) {
+    double2 x0 = ring[(slot * 2 + 0) * M_THREADS + threadIdx.x], x1 = ring[(slot * 2 + 1) * M_THREADS + threadIdx.x];
+    SweepSite r;
+    r.na = x0.x; r.nb = x0.y; r.id = x1.x; r.id2 = x1.y;
+    return r;
+}
+
+template <bool RING>
+__device__ void eval_grad_hess(const SweepSite* __restrict__ tbl, int L, double a, double b, double c, double g[3], double H[6],
+                               double2* ring = nullptr) {
     const bool neg = __double2hiint(c) < 0;
     const double cabs = fabs(c);
     double f[2], ga[2], gb[2], gc[2], haa[2], hab[2], hac[2], hbb[2], hbc[2], hcc[2];
     double sc;
-    SweepSite raw = load_site(tbl + (L > 1 ? 1 : 0));
+    SweepSite raw;
+    if (RING) {
+        // prologue: records 1, 2, 3 in flight (slots 1, 2, 3); record 0 is read directly
+        ring_issue(ring, 1, tbl + (L > 1 ? 1 : 0));
+        ring_issue(ring, 2, tbl + (L > 2 ? 2 : 0));
+        ring_issue(ring, 3, tbl + (L > 3 ? 3 : 0));
+    } else {
+        raw = load_site(tbl + (L > 1 ? 1 : 0));
+    }
     {
         SitePot p0 = site_pot(load_site(tbl), 0, neg, a, b, cabs);
         double w[2] = {p0.w0, p0.w1};
@@ -466,13 +496,26 @@ __device__ void eval_grad_hess(const SweepSite* __restrict__ tbl, int L, double 
         }
         sc = cpn_inv_pow2_of(f[0] + f[1]);
     }
+    if (RING) {
+        asm volatile("cp.async.wait_group 2;");                     // record 1 has landed
+        raw = ring_read(ring, 1);
+    }
     SitePot pot = site_pot(raw, 1, neg, a, b, cabs);
-    raw = load_site(tbl + (L > 2 ? 2 : 0));
+    if (!RING) raw = load_site(tbl + (L > 2 ? 2 : 0));
     for (int l = 1; l < L; ++l) {
         const SitePot p = pot;
-        const SweepSite rnext = raw;
-        prefetch_site(tbl + (l + 4 < L ? l + 4 : 0));               // pull the record of group l+4 into L1 (no register cost)
-        raw = load_site(tbl + (l + 2 < L ? l + 2 : 0));            // consumed by site_pot() in the next iteration
+        SweepSite rnext;
+        if (RING) {
+            // in flight during this trip: records l+1, l+2, l+3 (the new one goes to the slot record l-1 vacated);
+            // waiting until at most two groups are pending guarantees record l+1 has landed
+            ring_issue(ring, (l + 3) & (RING_SLOTS - 1), tbl + (l + 3 < L ? l + 3 : 0));
+            asm volatile("cp.async.wait_group 2;");
+            rnext = ring_read(ring, (l + 1) & (RING_SLOTS - 1));
+        } else {
+            rnext = raw;
+            prefetch_site(tbl + (l + 4 < L ? l + 4 : 0));           // pull the record of group l+4 into L1 (no register cost)
+            raw = load_site(tbl + (l + 2 < L ? l + 2 : 0));        // consumed by site_pot() in the next iteration
+        }
         pot = site_pot(rnext, l + 1, neg, a, b, cabs);              // independent of the recursion below
         const double t = p.t, invd = p.invd, invd2 = p.invd2, invd_2 = p.invd + p.invd;
         double w[2] = {p.w0 * sc, p.w1 * sc};
@@ -520,6 +563,7 @@ __device__ void eval_grad_hess(const SweepSite* __restrict__ tbl, int L, double 
     H[3] = fma(-g[1], g[1], (hbb[0] + hbb[1]) * inv);
     H[4] = fma(-g[1], g[2], (hbc[0] + hbc[1]) * inv);
     H[5] = fma(-g[2], g[2], (hcc[0] + hcc[1]) * inv);
+    if (RING) asm volatile("cp.async.wait_group 0;");               // drain before the ring is reused by the next sweep
 }
 
 struct MProblem {
@@ -561,7 +605,7 @@ __device__ void jacobian_fd(MProblem& pb, double* x, double J[3][3]) {
 __device__ void value_jacobian(MProblem& pb, double* x, double* F, double J[3][3]) {
     if (pb.mode == CPN_MSTEP_ANALYTIC) {
         double g[3], H[6];
-        eval_grad_hess(pb.sq, pb.L, x[0], x[1], x[2], g, H);
+        eval_grad_hess<false>(pb.sq, pb.L, x[0], x[1], x[2], g, H);
         pb.evals += 1;
         F[0] = g[0] - pb.t0; F[1] = g[1] - pb.t1; F[2] = g[2] - pb.t2;
         J[0][0] = H[0]; J[0][1] = H[1]; J[0][2] = H[2];
@@ -875,6 +919,7 @@ __global__ void __launch_bounds__(M_THREADS, WS_BLOCKS) k_mstep_ws(int n_items, 
                                                                     int* __restrict__ queue,
                                                                     unsigned char* __restrict__ alive /*[n_items] by list position*/) {
     __shared__ double cold[C_N][M_THREADS];
+    __shared__ double2 ring[RING_SLOTS * 2 * M_THREADS];
 #define CS(i) cold[(i)][threadIdx.x]
     const int lane = threadIdx.x & 31;
     const unsigned lt_mask = (1u << lane) - 1;
@@ -1019,7 +1064,7 @@ __global__ void __launch_bounds__(M_THREADS, WS_BLOCKS) k_mstep_ws(int n_items, 
         if (!__any_sync(0xffffffffu, have)) break;
         // ---- S: one derivative sweep at the current (trial) point of every busy lane
         if (have) {
-            eval_grad_hess(tbl, L, CS(C_X), CS(C_X + 1), CS(C_X + 2), g, H);
+            eval_grad_hess<true>(tbl, L, CS(C_X), CS(C_X + 1), CS(C_X + 2), g, H, ring);
             evals += 1;
             pending = true;
         }
