@@ -26,7 +26,7 @@
 
 namespace {
 
-constexpr int TILE = 128;          // groups staged per shared-memory tile
+constexpr int TILE = 64;           // groups staged per shared-memory tile
 constexpr int E_WARPS = 4;         // warps (EM instances) per E-step block
 constexpr int M_THREADS = 128;     // lanes (EM instances) per M-step block
 #ifndef WS_BLOCKS
@@ -201,61 +201,70 @@ __device__ __forceinline__ void estep_site(EState& s, const SiteTile& st, int j,
     s.fm = phiM * Gm;
 }
 
+// Emission weights of a warp travel global → shared memory with cp.async (8 bytes per lane and group) into a private
+// ring: two slots of E_PF groups plus one slot for the chain tail.  A lane only ever reads what it copied itself, so no
+// warp synchronisation is needed; and because an asynchronous copy has no destination register, the deep prefetch costs
+// no registers (the register file is what limits the number of resident E-step warps).
+struct EmisRing { double r[3][E_PF][32]; };
+
+__device__ __forceinline__ void ering_issue(EmisRing& ring, int slot, const double* __restrict__ src /*row 0, this lane*/, int nrows, int lane) {
+#pragma unroll
+    for (int u = 0; u < E_PF; ++u) {
+        if (u < nrows) {
+            unsigned d = (unsigned)__cvta_generic_to_shared(&ring.r[slot][u][lane]);
+            asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(d), "l"(src + u * 32));
+        }
+    }
+    asm volatile("cp.async.commit_group;");
+}
+
 // Forward sweep of the conditional chain for the 32 reads of a chunk, carrying the tangents (∂a,∂b,∂c).
-// Groups are processed E_PF at a time: the emission weights of the next E_PF groups are in flight (registers) while the
-// current ones are consumed; the message is rescaled every second group (|LLR| ≤ 300 keeps two steps inside the
-// double range).
+// Groups are processed E_PF at a time: while one block of E_PF emission rows is consumed from the ring the next one is in
+// flight; the message is rescaled every second group (|LLR| ≤ 300 keeps two steps inside the double range).
 template <bool BPOS>
-__device__ __forceinline__ void estep_chunk(SiteTile& st, int L, int lane, const double* __restrict__ na_g,
+__device__ __forceinline__ void estep_chunk(SiteTile& st, EmisRing& ring, int L, int lane, const double* __restrict__ na_g,
                                             const double* __restrict__ nb_g, const double* __restrict__ invd_g,
                                             const double* __restrict__ ewc, double a, double b, double cabs, double out[3]) {
     EState s{1.0, 1.0, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0};
     double sc = 1.0;
     const double* p = ewc + lane;                       // emission weight of (group l, this lane) at p[l*32]
     const int Lfull = L & ~(E_PF - 1);
-    double rn[E_PF];
-    if (Lfull > 0) {
-#pragma unroll
-        for (int u = 0; u < E_PF; ++u) rn[u] = p[u * 32];
-    }
-    // the last L mod E_PF groups: loaded up front as well, so the tail loop never waits on memory
-    double rt_[E_PF - 1];
-    {
-        const double* pt = p + (size_t)Lfull * 32;
-#pragma unroll
-        for (int u = 0; u < E_PF - 1; ++u) rt_[u] = (Lfull + u < L) ? pt[u * 32] : 1.0;
-    }
+    const int ngrp = Lfull / E_PF;
+    // in flight from the start: the first block of rows (slot 0) and the chain tail (slot 2)
+    ering_issue(ring, 0, p, Lfull > 0 ? E_PF : 0, lane);
+    ering_issue(ring, 2, p + (size_t)Lfull * 32, L - Lfull, lane);
+    int g = 0;                                          // index of the block of E_PF groups being consumed
     for (int l0 = 0; l0 < L; l0 += TILE) {
         const int n = min(TILE, L - l0);
         __syncwarp();
         fill_tile(st, l0, n, lane, na_g, nb_g, invd_g, a, b, cabs, BPOS);
         __syncwarp();
         const int nfull = n & ~(E_PF - 1);
-        for (int j0 = 0; j0 < nfull; j0 += E_PF) {
-            double rc[E_PF];
-#pragma unroll
-            for (int u = 0; u < E_PF; ++u) rc[u] = rn[u];
-            p += E_PF * 32;
-            if (l0 + j0 + E_PF < Lfull) {
-#pragma unroll
-                for (int u = 0; u < E_PF; ++u) rn[u] = p[u * 32];
-            }
+        for (int j0 = 0; j0 < nfull; j0 += E_PF, ++g) {
+            // next block in flight, then wait until at most that one is pending: block g (and the tail) have landed
+            ering_issue(ring, (g + 1) & 1, p + (size_t)(g + 1) * E_PF * 32, (g + 1 < ngrp) ? E_PF : 0, lane);
+            asm volatile("cp.async.wait_group 1;");
+            const int slot = g & 1;
 #pragma unroll
             for (int u = 0; u < E_PF; ++u) {
-                estep_site<BPOS>(s, st, j0 + u, rc[u], sc);
+                estep_site<BPOS>(s, st, j0 + u, ring.r[slot][u][lane], sc);
                 if (u & 1) sc = cpn_inv_pow2_of(s.fp + s.fm); else sc = 1.0;
             }
         }
         // tail of the chain (fewer than E_PF groups left; only the last tile has one)
+        if (nfull < n) {
+            asm volatile("cp.async.wait_group 0;");
 #pragma unroll
-        for (int u = 0; u < E_PF - 1; ++u) {
-            const int j = nfull + u;
-            if (j < n) {
-                estep_site<BPOS>(s, st, j, rt_[u], sc);
-                sc = cpn_inv_pow2_of(s.fp + s.fm);
+            for (int u = 0; u < E_PF - 1; ++u) {
+                const int j = nfull + u;
+                if (j < n) {
+                    estep_site<BPOS>(s, st, j, ring.r[2][u][lane], sc);
+                    sc = cpn_inv_pow2_of(s.fp + s.fm);
+                }
             }
         }
     }
+    asm volatile("cp.async.wait_group 0;");
     double inv = 1.0 / (s.fp + s.fm);
     out[0] = (s.gap + s.gam) * inv;
     out[1] = (s.gbp + s.gbm) * inv;
@@ -263,12 +272,13 @@ __device__ __forceinline__ void estep_chunk(SiteTile& st, int L, int lane, const
 }
 
 #ifndef E_BLOCKS
-#define E_BLOCKS 4
+#define E_BLOCKS 5
 #endif
 __global__ void __launch_bounds__(E_WARPS * 32, E_BLOCKS) k_estep(int n_items, const ItemDesc* __restrict__ desc,
                                                                    const double* __restrict__ phil /*[3][cap] by list position*/, int64_t cap,
                                                                    RegionTables rt, int64_t NI, double* __restrict__ ES /*[3][NI]*/) {
     __shared__ SiteTile tiles[E_WARPS];
+    __shared__ EmisRing rings[E_WARPS];
     int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
     int item = blockIdx.x * E_WARPS + w;
     if (item >= n_items) return;
@@ -287,8 +297,8 @@ __global__ void __launch_bounds__(E_WARPS * 32, E_BLOCKS) k_estep(int n_items, c
     for (int ch = 0; ch < nchunk; ++ch) {
         double o[3];
         const double* ewc = ew_r + (size_t)ch * L * 32;
-        if (bpos) estep_chunk<true>(tiles[w], L, lane, rt.na + g0, rt.nb + g0, rt.invd + g0, ewc, a, b, cabs, o);
-        else estep_chunk<false>(tiles[w], L, lane, rt.na + g0, rt.nb + g0, rt.invd + g0, ewc, a, b, cabs, o);
+        if (bpos) estep_chunk<true>(tiles[w], rings[w], L, lane, rt.na + g0, rt.nb + g0, rt.invd + g0, ewc, a, b, cabs, o);
+        else estep_chunk<false>(tiles[w], rings[w], L, lane, rt.na + g0, rt.nb + g0, rt.invd + g0, ewc, a, b, cabs, o);
         bool live = ch * 32 + lane < M;
         acc0 += cpn_warp_sum(live ? o[0] : 0.0);
         acc1 += cpn_warp_sum(live ? o[1] : 0.0);
