@@ -452,6 +452,51 @@ def test_two_sample_batched_permutations(engine, orc, cpn):
         assert np.all((out["pval"][:, ok] > 0) & (out["pval"][:, ok] <= 1))
 
 
+def test_analyze_batch_equals_fit_plus_stat_sums(engine, cpn):
+    """cpn_analyze_batch (ϕ̂ stays on the device between the EM kernels and the summaries kernel) is bit-identical to
+    cpn_fit_batch followed by cpn_stat_sums_batch, for host and for device pointers; regions without a fit get NaN."""
+    import torch
+    nb = cpn.simulations.make_nano_batch(40, M=30, seed=13)
+    n_init = 3
+    phi0 = cpn.simulations.gen_phi0s(np.random.default_rng(8), nb.R, n_init)
+    subs = [engine.lib.nls_reg_info(int(nb.chrst[r]), int(nb.chrend[r]), 350, nb.cpg_pos[nb.cpg_off[r]:nb.cpg_off[r + 1]]) for r in range(nb.R)]
+    sub_off = np.concatenate([[0], np.cumsum([len(s[0]) for s in subs])]).astype(np.int64)
+    sub_p, sub_q = np.concatenate([s[2] for s in subs]), np.concatenate([s[3] for s in subs])
+    fit = engine.lib.fit_batch(nb.grp_off, nb.Nl, nb.rho_l, nb.d_l, nb.read_off, nb.log_pyx_u, nb.log_pyx_m, phi0, n_init, 20)
+    ss = engine.lib.stat_sums_batch(fit["phi_hat"], nb.cpg_off, nb.rho_n, nb.d_n, sub_off, sub_p, sub_q)
+    out = engine.lib.analyze_batch(nb.grp_off, nb.Nl, nb.rho_l, nb.d_l, nb.read_off, nb.log_pyx_u, nb.log_pyx_m, phi0, n_init, nb.cpg_off, nb.rho_n,
+                                   nb.d_n, sub_off, sub_p, sub_q)
+    for k in ("phi_hat", "Q", "pick", "counters"):
+        assert np.array_equal(out[k], fit[k], equal_nan=True), k
+    for k in ("logZ", "ex", "exx", "log_g", "e_log_g1", "e_log_g2", "mml", "nme"):
+        assert np.array_equal(out[k], ss[k], equal_nan=True), k
+    bad = np.where(out["pick"] < 0)[0]
+    for r in bad:
+        assert np.all(np.isnan(out["mml"][sub_off[r]:sub_off[r + 1]])) and np.isnan(out["logZ"][r])
+    assert (out["pick"] >= 0).sum() >= nb.R // 2
+    # device-pointer variant
+    ins = dict(grp_off=nb.grp_off, Nl=nb.Nl, rho_l=nb.rho_l, d_l=nb.d_l, read_off=nb.read_off, lu=nb.log_pyx_u, lm=nb.log_pyx_m,
+               phi0=phi0.reshape(-1), cpg_off=nb.cpg_off, rho_n=nb.rho_n, d_n=nb.d_n, sub_off=sub_off, sub_p=sub_p, sub_q=sub_q)
+    dev = {k: torch.from_numpy(np.ascontiguousarray(v)).cuda() for k, v in ins.items()}
+    sN, sK, R = int(nb.cpg_off[-1]), int(sub_off[-1]), nb.R
+    outs = dict(phi_hat=torch.empty(3 * R, dtype=torch.float64, device="cuda"), Q=torch.empty(R, dtype=torch.float64, device="cuda"),
+                status=torch.empty(R, dtype=torch.int32, device="cuda"), counters=torch.empty(4 * R, dtype=torch.int64, device="cuda"),
+                logZ=torch.empty(R, dtype=torch.float64, device="cuda"), ex=torch.empty(sN, dtype=torch.float64, device="cuda"),
+                exx=torch.empty(sN - R, dtype=torch.float64, device="cuda"), log_g=torch.empty(4 * sK, dtype=torch.float64, device="cuda"),
+                e1=torch.empty(sK, dtype=torch.float64, device="cuda"), e2=torch.empty(sK, dtype=torch.float64, device="cuda"),
+                mml=torch.empty(sK, dtype=torch.float64, device="cuda"), nme=torch.empty(sK, dtype=torch.float64, device="cuda"))
+    torch.cuda.synchronize()
+    p = {k: v.data_ptr() for k, v in dev.items()}
+    o = {k: v.data_ptr() for k, v in outs.items()}
+    engine.lib.analyze_batch_raw(R, p["grp_off"], p["Nl"], p["rho_l"], p["d_l"], p["read_off"], p["lu"], p["lm"], p["phi0"], n_init, 20,
+                                 (20.0, 150.0, 50.0), cpn.MSTEP_ANALYTIC, p["cpg_off"], p["rho_n"], p["d_n"], p["sub_off"], p["sub_p"], p["sub_q"],
+                                 o["phi_hat"], o["Q"], o["status"], o["counters"], o["logZ"], o["ex"], o["exx"], o["log_g"], o["e1"], o["e2"],
+                                 o["mml"], o["nme"], True)
+    torch.cuda.synchronize()
+    assert np.array_equal(outs["phi_hat"].cpu().numpy().reshape(R, 3), fit["phi_hat"], equal_nan=True)
+    assert np.array_equal(outs["nme"].cpu().numpy(), ss["nme"], equal_nan=True) and np.array_equal(outs["ex"].cpu().numpy(), ss["ex"], equal_nan=True)
+
+
 def test_analyze_regions_filters(engine, cpn):
     """pmap_analyze_reg's data filters (nanopore.jl:309,322-326): regions failing them keep proc == false."""
     nb = cpn.simulations.make_nano_batch(5, M=30, seed=3)
