@@ -261,8 +261,11 @@ def main():
         run_step(lib, R, p_host_in, p_host_out, args.n_init, args.max_em_iters, mode, False, local_rank)
     barrier()
     t0 = time.perf_counter()
+    e2e_steps = []
     for _ in range(args.steps):
+        t1 = time.perf_counter()
         run_step(lib, R, p_host_in, p_host_out, args.n_init, args.max_em_iters, mode, False, local_rank)
+        e2e_steps.append(round((time.perf_counter() - t1) * 1e3, 2))
     barrier()
     t_e2e = time.perf_counter() - t0
 
@@ -293,7 +296,7 @@ def main():
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
                 "ms_per_step": dev_ms / args.steps, "wall_ms_per_step": 1e3 * t_dev / args.steps, "higher_is_better": True, "scaling": "weak",
                 "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": config,
-                "e2e": {"value": e2e, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
+                "e2e": {"value": e2e, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "ms_steps_rank0": e2e_steps},
                 "gpu_launches": int(launches),
                 "clocks": clocks,
                 "roofline": {"bound": "fp64", "kernel": "k_" + dom, "achieved": achieved, "peak": fp64_peak, "unit": "TFLOP/s",

@@ -13,6 +13,70 @@
 enum { CPN_K_PREP = 0, CPN_K_ESTEP = 1, CPN_K_MSTEP = 2, CPN_K_SCORE = 3, CPN_K_PICK = 4, CPN_K_STATSUM = 5, CPN_K_CMD = 6, CPN_K_SWEEP = 7,
        CPN_K_NCLASS = 8 };
 
+// Grow-only device workspace with stack discipline.  The fit path allocates the same sequence of (large) buffers on every
+// call; taking them from the stream-ordered pool made the driver defragment the pool under multi-stream use (stalls of
+// hundreds of ms), so they come from one persistent block instead.  A request that does not fit falls back to the pool and
+// raises the size the block is re-created with at the next reset().
+struct CpnArena {
+    char* base = nullptr;
+    size_t cap = 0, vtop = 0, high = 0;
+    struct Spill { void* p; size_t voff, bytes; cudaStream_t s; };
+    std::vector<Spill> spill;
+    static size_t round_up(size_t b) { return (b + 511) & ~(size_t)511; }
+    cudaError_t alloc(void** out, size_t bytes, cudaStream_t s) {
+        size_t b = round_up(bytes ? bytes : 1), voff = vtop;
+        vtop += b;
+        if (vtop > high) high = vtop;
+        if (voff + b <= cap) { *out = base + voff; return cudaSuccess; }
+        cudaError_t e = cudaMallocAsync(out, b, s);
+        if (e == cudaSuccess) spill.push_back({*out, voff, b, s});
+        return e;
+    }
+    void release(void* p, size_t bytes) {
+        size_t b = round_up(bytes ? bytes : 1);
+        if (base && (char*)p >= base && (char*)p < base + cap) {
+            size_t voff = (size_t)((char*)p - base);
+            if (voff + b == vtop) vtop = voff;          // top of the stack: reusable right away (same stream)
+            return;
+        }
+        for (size_t i = 0; i < spill.size(); ++i)
+            if (spill[i].p == p) {
+                if (spill[i].voff + spill[i].bytes == vtop) vtop = spill[i].voff;
+                cudaFreeAsync(p, spill[i].s);
+                spill.erase(spill.begin() + i);
+                return;
+            }
+    }
+    // Call only when no stream still uses memory handed out earlier.
+    cudaError_t reset() {
+        for (auto& sp : spill) cudaFreeAsync(sp.p, sp.s);
+        spill.clear();
+        vtop = 0;
+        if (high > cap) {
+            if (base) cudaFree(base);
+            base = nullptr; cap = 0;
+            size_t want = (high + high / 8 + ((size_t)2 << 20) - 1) & ~(((size_t)2 << 20) - 1);
+            cudaError_t e = cudaMalloc((void**)&base, want);
+            if (e != cudaSuccess) { cudaGetLastError(); return cudaSuccess; }   // keep spilling to the pool
+            cap = want;
+        }
+        return cudaSuccess;
+    }
+    void destroy() {
+        for (auto& sp : spill) cudaFreeAsync(sp.p, sp.s);
+        spill.clear();
+        if (base) cudaFree(base);
+        base = nullptr; cap = vtop = high = 0;
+    }
+};
+// The arena DevBuf allocations of the calling thread come from (null: the stream-ordered pool).
+inline CpnArena*& cpn_tl_arena() { static thread_local CpnArena* a = nullptr; return a; }
+struct CpnArenaScope {
+    CpnArena* prev;
+    explicit CpnArenaScope(CpnArena* a) : prev(cpn_tl_arena()) { cpn_tl_arena() = a; }
+    ~CpnArenaScope() { cpn_tl_arena() = prev; }
+};
+
 struct cpn_ctx {
     int device = 0;
     int sm_count = 148;
@@ -28,6 +92,15 @@ struct cpn_ctx {
     size_t pev_used = 0;
     double prof_ms[CPN_K_NCLASS] = {0};
     int64_t prof_launches[CPN_K_NCLASS] = {0};
+    // worker sub-contexts (own stream/events) used by the host-pointer entry points to run chunks of a batch concurrently
+    std::vector<cpn_ctx*> children;
+    // EM loop: pinned mailbox for the per-iteration active counts and the events that say when each has arrived
+    int* h_counts = nullptr;
+    int h_counts_cap = 0;
+    std::vector<cudaEvent_t> it_ev;
+    // persistent workspaces of the fit path: EM state / outputs, staged inputs, and the staging slots of a chunked host call
+    CpnArena arena, stage_arena;
+    std::vector<CpnArena*> slot_arenas;
 };
 
 // Brackets one launch with events when profiling is on.  Usage: { KTimer t(ctx, CPN_K_ESTEP); kernel<<<...>>>(...); }
@@ -84,18 +157,24 @@ struct DevBuf {
     T* p = nullptr;
     size_t n = 0;
     cudaStream_t s = nullptr;
+    CpnArena* ar = nullptr;
     DevBuf() = default;
     DevBuf(const DevBuf&) = delete;
     DevBuf& operator=(const DevBuf&) = delete;
     ~DevBuf() { release(); }
     void release() {
-        if (p) cudaFreeAsync(p, s);
-        p = nullptr; n = 0;
+        if (p) {
+            if (ar) ar->release(p, (n ? n : 1) * sizeof(T));
+            else cudaFreeAsync(p, s);
+        }
+        p = nullptr; n = 0; ar = nullptr;
     }
     cudaError_t alloc(size_t count, cudaStream_t stream) {
         release();
         s = stream; n = count;
         if (count == 0) count = 1;
+        ar = cpn_tl_arena();
+        if (ar) return ar->alloc((void**)&p, count * sizeof(T), stream);
         return cudaMallocAsync((void**)&p, count * sizeof(T), stream);
     }
     cudaError_t upload(const T* host, size_t count, cudaStream_t stream) {

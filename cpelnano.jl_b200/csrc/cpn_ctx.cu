@@ -57,6 +57,12 @@ void cpn_destroy(cpn_ctx* ctx) {
     if (ctx->ev0) cudaEventDestroy(ctx->ev0);
     if (ctx->ev1) cudaEventDestroy(ctx->ev1);
     for (cudaEvent_t e : ctx->pev) cudaEventDestroy(e);
+    for (cpn_ctx* c : ctx->children) cpn_destroy(c);
+    for (cudaEvent_t e : ctx->it_ev) cudaEventDestroy(e);
+    ctx->arena.destroy();
+    ctx->stage_arena.destroy();
+    for (CpnArena* a : ctx->slot_arenas) { a->destroy(); delete a; }
+    if (ctx->h_counts) cudaFreeHost(ctx->h_counts);
     delete ctx;
 }
 

@@ -17,6 +17,13 @@
 //     Jacobian of log Z come from one forward sweep carrying first- and second-order tangents, feeding a
 //     restatement of NLsolve's trust-region dogleg.
 //   * The EM loop is a sequence of batched launches over a compacted list of still-active instances.
+#include <algorithm>
+#include <condition_variable>
+#include <memory>
+#include <mutex>
+#include <chrono>
+#include <cstdlib>
+#include <thread>
 #include <cmath>
 #include <cstring>
 #include <limits>
@@ -276,11 +283,13 @@ __device__ __forceinline__ void estep_chunk(SiteTile& st, EmisRing& ring, int L,
 #endif
 __global__ void __launch_bounds__(E_WARPS * 32, E_BLOCKS) k_estep(int n_items, const ItemDesc* __restrict__ desc,
                                                                    const double* __restrict__ phil /*[3][cap] by list position*/, int64_t cap,
-                                                                   RegionTables rt, int64_t NI, double* __restrict__ ES /*[3][NI]*/) {
+                                                                   RegionTables rt, int64_t NI, double* __restrict__ ES /*[3][NI]*/,
+                                                                   const int* __restrict__ n_dev /*null, or the true item count*/) {
     __shared__ SiteTile tiles[E_WARPS];
     __shared__ EmisRing rings[E_WARPS];
     int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
     int item = blockIdx.x * E_WARPS + w;
+    if (n_dev) n_items = __ldg(n_dev);
     if (item >= n_items) return;
     // one round of independent loads: descriptor (two 16-byte vectors) and ϕ
     const int4* dq = reinterpret_cast<const int4*>(desc + item);
@@ -312,8 +321,9 @@ __global__ void __launch_bounds__(E_WARPS * 32, E_BLOCKS) k_estep(int n_items, c
 // Builds the position-indexed descriptors for a list of instances (items == null: identity list).
 __global__ void k_make_desc(int n_items, const int* __restrict__ items, int n_init, const RegionDesc* __restrict__ rdesc,
                             const double* __restrict__ phi /*[3][NI]*/, int64_t NI, ItemDesc* __restrict__ desc, double* __restrict__ phil,
-                            int64_t cap) {
+                            int64_t cap, const int* __restrict__ n_dev) {
     int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (n_dev) n_items = __ldg(n_dev);
     if (i >= n_items) return;
     int inst = items ? items[i] : i;
     RegionDesc rd = rdesc[inst / n_init];
@@ -797,8 +807,10 @@ struct EmState {
 // instance; survivors are appended (block-ordered) to next_items.
 __global__ void __launch_bounds__(M_THREADS) k_mstep(int n_items, const int* __restrict__ items, int n_init, RegionTables rt,
                                                       EmState st, int max_em_iters, double amax, double bmax, double cmax, int mode,
-                                                      int* __restrict__ next_items, int* __restrict__ n_next) {
+                                                      int* __restrict__ next_items, int* __restrict__ n_next,
+                                                      const int* __restrict__ n_dev) {
     int item = blockIdx.x * M_THREADS + threadIdx.x;
+    if (n_dev) n_items = __ldg(n_dev);
     bool survive = false;
     int inst = -1;
     if (item < n_items) {
@@ -927,7 +939,9 @@ __device__ __forceinline__ void dogleg3_sel(double* p, const double* r, const do
 __global__ void __launch_bounds__(M_THREADS, WS_BLOCKS) k_mstep_ws(int n_items, const int* __restrict__ items, int n_init, RegionTables rt,
                                                                     EmState st, int max_em_iters, double amax, double bmax, double cmax,
                                                                     int* __restrict__ queue,
-                                                                    unsigned char* __restrict__ alive /*[n_items] by list position*/) {
+                                                                    unsigned char* __restrict__ alive /*[n_items] by list position*/,
+                                                                    const int* __restrict__ n_dev) {
+    if (n_dev) n_items = __ldg(n_dev);
     __shared__ double cold[C_N][M_THREADS];
     __shared__ double2 ring[RING_SLOTS * 2 * M_THREADS];
 #define CS(i) cold[(i)][threadIdx.x]
@@ -1086,8 +1100,10 @@ __global__ void __launch_bounds__(M_THREADS, WS_BLOCKS) k_mstep_ws(int n_items, 
 // M-step warp walk chains of similar length): per-block counts → scan of the counts → scatter.
 constexpr int CP_THREADS = 256, CP_ITEMS = 4, CP_TILE = CP_THREADS * CP_ITEMS;
 
-__global__ void __launch_bounds__(CP_THREADS) k_compact_count(int n, const unsigned char* __restrict__ alive, int* __restrict__ blk_cnt) {
+__global__ void __launch_bounds__(CP_THREADS) k_compact_count(int n, const unsigned char* __restrict__ alive, int* __restrict__ blk_cnt,
+                                                               const int* __restrict__ n_dev) {
     __shared__ int wsum[CP_THREADS / 32];
+    if (n_dev) n = __ldg(n_dev);
     int base = blockIdx.x * CP_TILE + threadIdx.x * CP_ITEMS;
     int c = 0;
 #pragma unroll
@@ -1127,8 +1143,10 @@ __global__ void __launch_bounds__(1024) k_compact_scan(int nblk, int* __restrict
     if (threadIdx.x == 0) *total = carry;
 }
 __global__ void __launch_bounds__(CP_THREADS) k_compact_scatter(int n, const unsigned char* __restrict__ alive, const int* __restrict__ items,
-                                                                 const int* __restrict__ blk_off, int* __restrict__ out) {
+                                                                 const int* __restrict__ blk_off, int* __restrict__ out,
+                                                                 const int* __restrict__ n_dev) {
     __shared__ int wsum[CP_THREADS / 32];
+    if (n_dev) n = __ldg(n_dev);
     int base = blockIdx.x * CP_TILE + threadIdx.x * CP_ITEMS;
     int f[CP_ITEMS], c = 0;
 #pragma unroll
@@ -1237,6 +1255,22 @@ struct PackedRegions {
 
 inline unsigned blocks_for(int64_t n, int per_block) { return (unsigned)((n + per_block - 1) / per_block); }
 
+// CPN_TRACE=1 prints host-side phase timestamps (ms since the first traced event) to stderr.
+static void trace(const cpn_ctx* ctx, const char* what) {
+    static const bool on = getenv("CPN_TRACE") != nullptr;
+    if (!on) return;
+    static const auto epoch = std::chrono::steady_clock::now();
+    double t = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - epoch).count();
+    uint64_t reserved = 0, used = 0;
+    cudaMemPool_t pool;
+    if (cudaDeviceGetDefaultMemPool(&pool, ctx->device) == cudaSuccess) {
+        cudaMemPoolGetAttribute(pool, cudaMemPoolAttrReservedMemCurrent, &reserved);
+        cudaMemPoolGetAttribute(pool, cudaMemPoolAttrUsedMemCurrent, &used);
+    }
+    fprintf(stderr, "[cpn trace] %p %-10s %9.2f  pool reserved %7.1f MB used %7.1f MB\n", (const void*)ctx, what, t, reserved / 1048576.0,
+            used / 1048576.0);
+}
+
 // Uploads (or borrows) the CSR inputs and builds the per-group and per-read device tables.
 int pack_regions(cpn_ctx* ctx, PackedRegions& pk, bool on_device, bool with_reads, int64_t R, const int64_t* grp_off,
                  const double* Nl, const double* rho_l, const double* d_l, const int64_t* read_off, const double* lu, const double* lm) {
@@ -1267,6 +1301,7 @@ int pack_regions(cpn_ctx* ctx, PackedRegions& pk, bool on_device, bool with_read
     }
     pk.sumL = pk.h_grp_off[R];
     pk.n_obs = h_obs[R];
+    trace(ctx, "pk-begin");
     CPN_CUDA(ctx, pk.grp_off.bind(grp_off, R + 1, on_device, s));
     CPN_CUDA(ctx, pk.Nl.bind(Nl, pk.sumL, on_device, s));
     CPN_CUDA(ctx, pk.rho.bind(rho_l, pk.sumL, on_device, s));
@@ -1279,29 +1314,35 @@ int pack_regions(cpn_ctx* ctx, PackedRegions& pk, bool on_device, bool with_read
       k_prep_sites<<<blocks_for(R * 32, 256), 256, 0, s>>>(R, pk.grp_off.p, pk.Nl.p, pk.rho.p, pk.dl.p, pk.na.p, pk.nb.p, pk.invd.p, pk.sq.p); }
     pk.rt.grp_off = pk.grp_off.p; pk.rt.na = pk.na.p; pk.rt.nb = pk.nb.p; pk.rt.invd = pk.invd.p; pk.rt.sq = pk.sq.p;
     if (with_reads) {
-        CPN_CUDA(ctx, pk.read_off.bind(read_off, R + 1, on_device, s));
-        CPN_CUDA(ctx, pk.lu.bind(lu, pk.n_obs, on_device, s));
-        CPN_CUDA(ctx, pk.lm.bind(lm, pk.n_obs, on_device, s));
-        CPN_CUDA(ctx, pk.obs_off.upload(h_obs.data(), R + 1, s));
-        CPN_CUDA(ctx, pk.ew_off.upload(h_ew.data(), R + 1, s));
-        CPN_CUDA(ctx, pk.rb_off.upload(h_rb.data(), R + 1, s));
-        CPN_CUDA(ctx, pk.ew.alloc(h_ew[R], s));
-        CPN_CUDA(ctx, pk.rb.alloc(h_rb[R], s));
-        { KTimer kt(ctx, CPN_K_PREP);
-          k_prep_emis<<<blocks_for(R * 32, 128), 128, 0, s>>>(R, pk.grp_off.p, pk.read_off.p, pk.obs_off.p, pk.lu.p, pk.lm.p, pk.ew_off.p,
-                                                              pk.rb_off.p, pk.ew.p, pk.rb.p); }
+        trace(ctx, "pk-sites");
+        // tables first, raw emissions last: they sit on top of the workspace stack and are popped once packed
         std::vector<RegionDesc> h_desc(R);
         for (int64_t r = 0; r < R; ++r) {
             h_desc[r].g0 = pk.h_grp_off[r]; h_desc[r].ew_off = h_ew[r];
             h_desc[r].L = (int32_t)(pk.h_grp_off[r + 1] - pk.h_grp_off[r]); h_desc[r].M = (int32_t)(pk.h_read_off[r + 1] - pk.h_read_off[r]);
             h_desc[r].pad = 0;
         }
+        CPN_CUDA(ctx, pk.read_off.bind(read_off, R + 1, on_device, s));
+        CPN_CUDA(ctx, pk.obs_off.upload(h_obs.data(), R + 1, s));
+        CPN_CUDA(ctx, pk.ew_off.upload(h_ew.data(), R + 1, s));
+        CPN_CUDA(ctx, pk.rb_off.upload(h_rb.data(), R + 1, s));
         CPN_CUDA(ctx, pk.rdesc.upload(h_desc.data(), R, s));
         pk.rt.rdesc = pk.rdesc.p;
-        // the raw emissions are not needed once packed: give the (stream-ordered) memory back before the EM loop
-        pk.lu.own.release();
+        CPN_CUDA(ctx, pk.ew.alloc(h_ew[R], s));
+        CPN_CUDA(ctx, pk.rb.alloc(h_rb[R], s));
+        CPN_CUDA(ctx, pk.lu.bind(lu, pk.n_obs, on_device, s));
+        trace(ctx, "pk-lu");
+        CPN_CUDA(ctx, pk.lm.bind(lm, pk.n_obs, on_device, s));
+        trace(ctx, "pk-lm");
+        { KTimer kt(ctx, CPN_K_PREP);
+          k_prep_emis<<<blocks_for(R * 32, 128), 128, 0, s>>>(R, pk.grp_off.p, pk.read_off.p, pk.obs_off.p, pk.lu.p, pk.lm.p, pk.ew_off.p,
+                                                              pk.rb_off.p, pk.ew.p, pk.rb.p); }
+        // the raw emissions are not needed once packed: hand the memory back (stream-ordered) before the EM loop
         pk.lm.own.release();
+        pk.lu.own.release();
+        trace(ctx, "pk-enq");
         CPN_CUDA(ctx, cudaStreamSynchronize(s));   // h_* staging vectors go out of scope
+        trace(ctx, "pk-sync");
         pk.rt.read_off = pk.read_off.p; pk.rt.ew_off = pk.ew_off.p; pk.rt.rb_off = pk.rb_off.p; pk.rt.ew = pk.ew.p; pk.rt.rb = pk.rb.p;
     }
     CPN_CUDA(ctx, cudaGetLastError());
@@ -1315,12 +1356,46 @@ struct SummaryArgs {
     double *logZ, *ex, *exx, *log_g, *e_log_g1, *e_log_g2, *mml, *nme;
 };
 
+// Pinned count mailbox and one event per EM iteration, owned by the context and grown on demand.
+static int ctx_iter_resources(cpn_ctx* ctx, int n) {
+    if (ctx->h_counts_cap < n) {
+        if (ctx->h_counts) cudaFreeHost(ctx->h_counts);
+        ctx->h_counts = nullptr; ctx->h_counts_cap = 0;
+        CPN_CUDA(ctx, cudaHostAlloc((void**)&ctx->h_counts, (size_t)n * sizeof(int), cudaHostAllocDefault));
+        ctx->h_counts_cap = n;
+    }
+    while ((int)ctx->it_ev.size() < n) {
+        cudaEvent_t e;
+        CPN_CUDA(ctx, cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+        ctx->it_ev.push_back(e);
+    }
+    return CPN_OK;
+}
+
+// Inputs of one batch (or one chunk of a batch) resident on the device: the packed region tables and the EM starts.
+struct StagedBatch {
+    CpnArena* arena = nullptr;   // workspace the tables live in (reset by whoever hands it out)
+    PackedRegions pk;
+    DevIn<double> phi0;
+};
+
+int fit_stage(cpn_ctx* ctx, StagedBatch& sb, bool on_device, int64_t R, const int64_t* grp_off, const double* Nl, const double* rho_l,
+              const double* d_l, const int64_t* read_off, const double* lu, const double* lm, const double* phi0, int32_t n_init) {
+    CPN_CUDA(ctx, cudaSetDevice(ctx->device));
+    CpnArenaScope scope(sb.arena);
+    // ϕ0 first: the raw emissions must stay on top of the workspace stack
+    CPN_CUDA(ctx, sb.phi0.bind(phi0, R * n_init * 3, on_device, ctx->stream));
+    return pack_regions(ctx, sb.pk, on_device, true, R, grp_off, Nl, rho_l, d_l, read_off, lu, lm);
+}
+
+// `pre` = inputs staged earlier (possibly on another context's stream, already synchronised); the input pointers are then unused.
 int fit_impl(cpn_ctx* ctx, bool on_device, int64_t R, const int64_t* grp_off, const double* Nl, const double* rho_l, const double* d_l,
              const int64_t* read_off, const double* lu, const double* lm, const double* phi0, int32_t n_init, int32_t max_em_iters,
              double amax, double bmax, double cmax, int32_t mstep_mode, double* phi_hat, double* Q, int32_t* status, int64_t* counters,
-             double* phi_starts, double* Q_starts, const SummaryArgs* sa = nullptr) {
+             double* phi_starts, double* Q_starts, const SummaryArgs* sa = nullptr, StagedBatch* pre = nullptr) {
     CPN_ARG(ctx, R >= 0 && n_init >= 1 && max_em_iters >= 1, "R >= 0, n_init >= 1, max_em_iters >= 1");
-    CPN_ARG(ctx, grp_off && Nl && rho_l && d_l && read_off && lu && lm && phi0 && phi_hat && Q, "null pointer");
+    CPN_ARG(ctx, pre || (grp_off && Nl && rho_l && d_l && read_off && lu && lm && phi0), "null pointer");
+    CPN_ARG(ctx, phi_hat && Q, "null pointer");
     CPN_ARG(ctx, mstep_mode == CPN_MSTEP_FD || mstep_mode == CPN_MSTEP_ANALYTIC, "mstep_mode");
     CPN_ARG(ctx, R * (int64_t)n_init < (int64_t)2147483647, "R*n_init must fit in int32");
     CPN_CUDA(ctx, cudaSetDevice(ctx->device));
@@ -1329,18 +1404,26 @@ int fit_impl(cpn_ctx* ctx, bool on_device, int64_t R, const int64_t* grp_off, co
     cudaStream_t s = ctx->stream;
     CPN_CUDA(ctx, cudaEventRecord(ctx->ev0, s));
     {
-        PackedRegions pk;
-        int rc = pack_regions(ctx, pk, on_device, true, R, grp_off, Nl, rho_l, d_l, read_off, lu, lm);
-        if (rc) return rc;
+        StagedBatch local;
+        StagedBatch* sb = pre ? pre : &local;
+        trace(ctx, "begin");
+        CPN_CUDA(ctx, ctx->arena.reset());
+        if (!pre) {
+            CPN_CUDA(ctx, ctx->stage_arena.reset());
+            local.arena = &ctx->stage_arena;
+            int rc = fit_stage(ctx, local, on_device, R, grp_off, Nl, rho_l, d_l, read_off, lu, lm, phi0, n_init);
+            if (rc) return rc;
+        }
+        PackedRegions& pk = sb->pk;
+        DevIn<double>& d_phi0 = sb->phi0;
+        CpnArenaScope scope(&ctx->arena);
         const int64_t NI = R * n_init;
-        DevIn<double> d_phi0;
-        CPN_CUDA(ctx, d_phi0.bind(phi0, NI * 3, on_device, s));
         DevBuf<double> phi, ES, Qs;
-        DevBuf<int> iter, stat, c_em, c_sol, c_ev, items_a, items_b, n_next, order;
+        DevBuf<int> iter, stat, c_em, c_sol, c_ev, items_a, items_b, order;
         CPN_CUDA(ctx, phi.alloc(3 * NI, s)); CPN_CUDA(ctx, ES.alloc(3 * NI, s)); CPN_CUDA(ctx, Qs.alloc(NI, s));
         CPN_CUDA(ctx, iter.alloc(NI, s)); CPN_CUDA(ctx, stat.alloc(NI, s)); CPN_CUDA(ctx, c_em.alloc(NI, s));
         CPN_CUDA(ctx, c_sol.alloc(NI, s)); CPN_CUDA(ctx, c_ev.alloc(NI, s));
-        CPN_CUDA(ctx, items_a.alloc(NI, s)); CPN_CUDA(ctx, items_b.alloc(NI, s)); CPN_CUDA(ctx, n_next.alloc(2, s));
+        CPN_CUDA(ctx, items_a.alloc(NI, s)); CPN_CUDA(ctx, items_b.alloc(NI, s));
         DevBuf<unsigned char> alive;
         DevBuf<int> blk_cnt;
         DevBuf<ItemDesc> idesc;
@@ -1372,34 +1455,54 @@ int fit_impl(cpn_ctx* ctx, bool on_device, int64_t R, const int64_t* grp_off, co
         EmState st{phi.p, ES.p, iter.p, stat.p, c_em.p, c_sol.p, c_ev.p, NI, gh.p, gh_valid.p};
         { KTimer kt(ctx, CPN_K_PREP);
           k_init_state<<<blocks_for(NI, 256), 256, 0, s>>>(NI, n_init, d_phi0.p, st, items_a.p, order.p); }
-        int n_active = (int)NI;
+        trace(ctx, "em-start");
+        // The host never waits for the device inside the EM loop.  The number of instances still active after iteration i
+        // lives in counts[i+1] on the device (kernels of iteration i+1 read it there); the host sizes its grids from the
+        // newest count that has already arrived in pinned memory — an upper bound, since the active list only shrinks —
+        // and runs at most EM_LAG iterations ahead.  Launch and read-back latencies (which grow several-fold while another
+        // stream saturates PCIe with uploads) stay off the critical path.
+        constexpr int EM_LAG = 2;
+        DevBuf<int> counts;                                  // [max_em_iters + 1][2]: {active count, M-step queue head}
+        CPN_CUDA(ctx, counts.alloc(2 * ((size_t)max_em_iters + 1), s));
+        CPN_CUDA(ctx, cudaMemsetAsync(counts.p, 0, 2 * ((size_t)max_em_iters + 1) * sizeof(int), s));
+        int rc_h = ctx_iter_resources(ctx, max_em_iters + 1);
+        if (rc_h) return rc_h;
+        volatile int* h_counts = ctx->h_counts;
+        h_counts[0] = (int)NI;
+        CPN_CUDA(ctx, cudaMemcpyAsync(counts.p, (const void*)ctx->h_counts, sizeof(int), cudaMemcpyHostToDevice, s));
+        int known = 0;
         int* cur = items_a.p;
         int* nxt = items_b.p;
-        for (int it = 0; it < max_em_iters && n_active > 0; ++it) {
-            CPN_CUDA(ctx, cudaMemsetAsync(n_next.p, 0, 2 * sizeof(int), s));     // [0] survivors, [1] work-queue head
+        for (int it = 0; it < max_em_iters; ++it) {
+            if (it - EM_LAG > known) { CPN_CUDA(ctx, cudaEventSynchronize(ctx->it_ev[it - EM_LAG])); known = it - EM_LAG; }
+            while (known < it && cudaEventQuery(ctx->it_ev[known + 1]) == cudaSuccess) ++known;
+            const int ub = h_counts[known];
+            if (ub <= 0) break;
+            const int* n_dev = counts.p + 2 * it;
+            int* queue = counts.p + 2 * it + 1;
+            int* n_out = counts.p + 2 * (it + 1);
             { KTimer kt(ctx, CPN_K_PREP);
-              k_make_desc<<<blocks_for(n_active, 256), 256, 0, s>>>(n_active, cur, n_init, pk.rt.rdesc, phi.p, NI, idesc.p, phil.p, NI); }
+              k_make_desc<<<blocks_for(ub, 256), 256, 0, s>>>(ub, cur, n_init, pk.rt.rdesc, phi.p, NI, idesc.p, phil.p, NI, n_dev); }
             { KTimer kt(ctx, CPN_K_ESTEP);
-              k_estep<<<blocks_for(n_active, E_WARPS), E_WARPS * 32, 0, s>>>(n_active, idesc.p, phil.p, NI, pk.rt, NI, ES.p); }
+              k_estep<<<blocks_for(ub, E_WARPS), E_WARPS * 32, 0, s>>>(ub, idesc.p, phil.p, NI, pk.rt, NI, ES.p, n_dev); }
             if (mstep_mode == CPN_MSTEP_ANALYTIC) {
-                unsigned grid = std::min<unsigned>(blocks_for(n_active, M_THREADS), (unsigned)(ctx->sm_count * ws_blocks_per_sm));
-                KTimer kt(ctx, CPN_K_MSTEP);
-                k_mstep_ws<<<grid, M_THREADS, 0, s>>>(n_active, cur, n_init, pk.rt, st, max_em_iters, amax, bmax, cmax, n_next.p + 1, alive.p);
-            }
-            if (mstep_mode == CPN_MSTEP_ANALYTIC) {
-                int nblk = (n_active + CP_TILE - 1) / CP_TILE;
-                { KTimer kt(ctx, CPN_K_PREP); k_compact_count<<<nblk, CP_THREADS, 0, s>>>(n_active, alive.p, blk_cnt.p); }
-                { KTimer kt(ctx, CPN_K_PREP); k_compact_scan<<<1, 1024, 0, s>>>(nblk, blk_cnt.p, n_next.p); }
-                { KTimer kt(ctx, CPN_K_PREP); k_compact_scatter<<<nblk, CP_THREADS, 0, s>>>(n_active, alive.p, cur, blk_cnt.p, nxt); }
+                unsigned grid = std::min<unsigned>(blocks_for(ub, M_THREADS), (unsigned)(ctx->sm_count * ws_blocks_per_sm));
+                { KTimer kt(ctx, CPN_K_MSTEP);
+                  k_mstep_ws<<<grid, M_THREADS, 0, s>>>(ub, cur, n_init, pk.rt, st, max_em_iters, amax, bmax, cmax, queue, alive.p, n_dev); }
+                int nblk = (ub + CP_TILE - 1) / CP_TILE;
+                { KTimer kt(ctx, CPN_K_PREP); k_compact_count<<<nblk, CP_THREADS, 0, s>>>(ub, alive.p, blk_cnt.p, n_dev); }
+                { KTimer kt(ctx, CPN_K_PREP); k_compact_scan<<<1, 1024, 0, s>>>(nblk, blk_cnt.p, n_out); }
+                { KTimer kt(ctx, CPN_K_PREP); k_compact_scatter<<<nblk, CP_THREADS, 0, s>>>(ub, alive.p, cur, blk_cnt.p, nxt, n_dev); }
             } else {
                 KTimer kt(ctx, CPN_K_MSTEP);
-                k_mstep<<<blocks_for(n_active, M_THREADS), M_THREADS, 0, s>>>(n_active, cur, n_init, pk.rt, st, max_em_iters, amax, bmax, cmax,
-                                                                               mstep_mode, nxt, n_next.p);
+                k_mstep<<<blocks_for(ub, M_THREADS), M_THREADS, 0, s>>>(ub, cur, n_init, pk.rt, st, max_em_iters, amax, bmax, cmax, mstep_mode,
+                                                                         nxt, n_out, n_dev);
             }
-            CPN_CUDA(ctx, cudaMemcpyAsync(&n_active, n_next.p, sizeof(int), cudaMemcpyDeviceToHost, s));
-            CPN_CUDA(ctx, cudaStreamSynchronize(s));
+            CPN_CUDA(ctx, cudaMemcpyAsync((void*)(ctx->h_counts + it + 1), n_out, sizeof(int), cudaMemcpyDeviceToHost, s));
+            CPN_CUDA(ctx, cudaEventRecord(ctx->it_ev[it + 1], s));
             std::swap(cur, nxt);
         }
+        trace(ctx, "em-done");
         // score converged instances (em_algorithm.jl:344), then pick per region
         { KTimer kt(ctx, CPN_K_SCORE);
           k_score<<<blocks_for(NI, E_WARPS), E_WARPS * 32, 0, s>>>((int)NI, nullptr, n_init, pk.rt, phi.p, NI, stat.p, 1, Qs.p); }
@@ -1458,6 +1561,7 @@ int fit_impl(cpn_ctx* ctx, bool on_device, int64_t R, const int64_t* grp_off, co
             CPN_CUDA(ctx, cudaStreamSynchronize(s));
         }
     }
+    trace(ctx, "end");
     float ms = 0;
     CPN_CUDA(ctx, cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1));
     ctx->last_ms = ms;
@@ -1469,13 +1573,180 @@ int fit_impl(cpn_ctx* ctx, bool on_device, int64_t R, const int64_t* grp_off, co
 
 extern "C" {
 
+// Host-pointer entry points split a large batch into contiguous chunks of regions (balanced by M·L) and run them on worker
+// threads, each with its own stream: the host→device copy of chunk k+1 overlaps the EM kernels of chunk k, and the tail of
+// one chunk's kernels overlaps the head of the other's.  Regions are independent, so results do not depend on the split.
+static int env_int(const char* name, int dflt) { const char* e = getenv(name); return e ? atoi(e) : dflt; }
+
+static int fit_host_chunked(cpn_ctx* ctx, int64_t R, const int64_t* grp_off, const double* Nl, const double* rho_l, const double* d_l,
+                            const int64_t* read_off, const double* lu, const double* lm, const double* phi0, int32_t n_init,
+                            int32_t max_em_iters, double amax, double bmax, double cmax, int32_t mstep_mode, double* phi_hat, double* Q,
+                            int32_t* status, int64_t* counters, double* phi_starts, double* Q_starts, const SummaryArgs* sa) {
+    // Chunk plan: K chunks whose costs (M·L summed over regions) grow geometrically, so the first upload — the only one that
+    // nothing overlaps — is short, while later chunks are big enough to keep the EM kernels' late, sparsely populated
+    // iterations amortised.  CPN_WORKERS=0 disables chunking; CPN_CHUNKS / CPN_CHUNK_RATIO / CPN_CHUNK_REGIONS tune the plan.
+    const int n_workers = std::max(0, env_int("CPN_WORKERS", 2));
+    const int64_t chunk_regions = std::max(1, env_int("CPN_CHUNK_REGIONS", 12500));
+    int C = (int)((R > 0 && grp_off && read_off && n_workers >= 1) ? std::min<int64_t>(R / chunk_regions, 4) : 0);
+    if (C > 1 && getenv("CPN_CHUNKS")) C = (int)std::min<int64_t>(std::max(1, env_int("CPN_CHUNKS", C)), R);
+    if (C <= 1)
+        return fit_impl(ctx, false, R, grp_off, Nl, rho_l, d_l, read_off, lu, lm, phi0, n_init, max_em_iters, amax, bmax, cmax, mstep_mode,
+                        phi_hat, Q, status, counters, phi_starts, Q_starts, sa);
+    CPN_ARG(ctx, Nl && rho_l && d_l && lu && lm && phi0 && phi_hat && Q, "null pointer");
+    CPN_ARG(ctx, n_init >= 1, "n_init >= 1");
+    auto t0 = std::chrono::steady_clock::now();
+    const double ratio = getenv("CPN_CHUNK_RATIO") ? std::max(1.0, atof(getenv("CPN_CHUNK_RATIO"))) : 1.3;
+    std::vector<int64_t> obs(R + 1);       // emission offsets = cumulative cost
+    obs[0] = 0;
+    for (int64_t r = 0; r < R; ++r) obs[r + 1] = obs[r] + (grp_off[r + 1] - grp_off[r]) * (read_off[r + 1] - read_off[r]);
+    std::vector<int64_t> bnd(C + 1, R);
+    bnd[0] = 0;
+    {
+        double total = 0, acc = 0, w = 1;
+        for (int c = 0; c < C; ++c, w *= ratio) total += w;
+        w = 1;
+        for (int c = 1; c < C; ++c, w *= ratio) {
+            acc += w;
+            int64_t target = (int64_t)((double)obs[R] * (acc / total));
+            bnd[c] = std::lower_bound(obs.begin(), obs.end(), target) - obs.begin();
+            bnd[c] = std::min(std::max(bnd[c], bnd[c - 1]), R);
+        }
+    }
+    // children[0] stages chunks (host→device copies and the packing kernels) ahead of the W compute workers children[1..W]
+    const int W = std::min(n_workers, C);
+    while ((int)ctx->children.size() < W + 1) {
+        cpn_ctx* ch = nullptr;
+        if (cpn_create(ctx->device, &ch) != CPN_OK) { ctx->err = "could not create a worker context"; return CPN_ERR_CUDA; }
+        if (ctx->children.empty() && env_int("CPN_UPLOAD_PRIO", 1)) {
+            // the staging stream outranks the compute streams: its packing kernels take SM slots as soon as EM blocks retire
+            int lo = 0, hi = 0;
+            cudaStream_t ps = nullptr;
+            if (cudaDeviceGetStreamPriorityRange(&lo, &hi) == cudaSuccess &&
+                cudaStreamCreateWithPriority(&ps, cudaStreamNonBlocking, hi) == cudaSuccess) {
+                cudaStreamDestroy(ch->stream);
+                ch->stream = ps;
+            }
+        }
+        ctx->children.push_back(ch);
+    }
+    for (int i = 0; i <= W; ++i) cpn_set_profile(ctx->children[i], ctx->profile ? 1 : 0);
+    const int depth = 2;                   // chunks staged ahead of the ones being computed
+    while ((int)ctx->slot_arenas.size() < depth + W + 1) ctx->slot_arenas.push_back(new CpnArena());
+    std::vector<CpnArena*> free_arenas(ctx->slot_arenas.begin(), ctx->slot_arenas.begin() + depth + W + 1);
+    std::vector<std::unique_ptr<StagedBatch>> slot(C);
+    std::vector<int> state(C, 0);          // 0 pending, 1 staged, -1 failed
+    std::vector<int> rc(W + 1, CPN_OK);
+    std::vector<int64_t> launches(W + 1, 0);
+    std::mutex mu;
+    std::condition_variable cv;
+    int taken = 0;
+    bool abort_all = false;
+    std::vector<std::thread> th;
+    th.emplace_back([&]() {
+        cpn_ctx* u = ctx->children[0];
+        u->last_launches = 0;
+        std::vector<int64_t> g, rd;
+        for (int c = 0; c < C; ++c) {
+            {
+                std::unique_lock<std::mutex> lk(mu);
+                cv.wait(lk, [&] { return abort_all || (c < taken + depth && !free_arenas.empty()); });
+                if (abort_all) return;
+            }
+            const int64_t r0 = bnd[c], Rc = bnd[c + 1] - r0;
+            int r = CPN_OK;
+            if (Rc > 0) {
+                CpnArena* ar;
+                { std::lock_guard<std::mutex> lk(mu); ar = free_arenas.back(); free_arenas.pop_back(); }
+                ar->reset();
+                g.resize(Rc + 1); rd.resize(Rc + 1);
+                for (int64_t i = 0; i <= Rc; ++i) { g[i] = grp_off[r0 + i] - grp_off[r0]; rd[i] = read_off[r0 + i] - read_off[r0]; }
+                const int64_t g0 = grp_off[r0];
+                slot[c].reset(new StagedBatch());
+                slot[c]->arena = ar;
+                trace(u, "stage");
+                r = fit_stage(u, *slot[c], false, Rc, g.data(), Nl + g0, rho_l + g0, d_l + (g0 - r0), rd.data(), lu + obs[r0], lm + obs[r0],
+                              phi0 + r0 * n_init * 3, n_init);
+                if (r == CPN_OK && cudaStreamSynchronize(u->stream) != cudaSuccess) { u->err = "stream synchronize failed"; r = CPN_ERR_CUDA; }
+                launches[0] = u->last_launches;
+                trace(u, "staged");
+            }
+            std::lock_guard<std::mutex> lk(mu);
+            state[c] = r == CPN_OK ? 1 : -1;
+            if (r != CPN_OK) { rc[0] = r; abort_all = true; }
+            cv.notify_all();
+            if (r != CPN_OK) return;
+        }
+    });
+    for (int wi = 1; wi <= W; ++wi) {
+        th.emplace_back([&, wi]() {
+            cpn_ctx* w = ctx->children[wi];
+            std::vector<int64_t> cp, sb;
+            for (;;) {
+                int c;
+                {
+                    std::unique_lock<std::mutex> lk(mu);
+                    if (abort_all || taken >= C) return;
+                    c = taken++;
+                    cv.notify_all();
+                    cv.wait(lk, [&] { return abort_all || state[c] != 0; });
+                    if (state[c] != 1) return;
+                }
+                const int64_t r0 = bnd[c], Rc = bnd[c + 1] - r0;
+                if (Rc <= 0) continue;
+                SummaryArgs sc{};
+                if (sa) {
+                    cp.resize(Rc + 1); sb.resize(Rc + 1);
+                    for (int64_t i = 0; i <= Rc; ++i) { cp[i] = sa->cpg_off[r0 + i] - sa->cpg_off[r0]; sb[i] = sa->sub_off[r0 + i] - sa->sub_off[r0]; }
+                    const int64_t n0 = sa->cpg_off[r0], k0 = sa->sub_off[r0];
+                    sc = SummaryArgs{cp.data(), sb.data(), sa->sub_p + k0, sa->sub_q + k0, sa->rho_n + n0, sa->d_n + (n0 - r0),
+                                     sa->logZ + r0, sa->ex + n0, sa->exx + (n0 - r0), sa->log_g + 4 * k0, sa->e_log_g1 + k0, sa->e_log_g2 + k0,
+                                     sa->mml + k0, sa->nme + k0};
+                }
+                int r = fit_impl(w, false, Rc, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, n_init, max_em_iters,
+                                 amax, bmax, cmax, mstep_mode, phi_hat + 3 * r0, Q + r0, status ? status + r0 : nullptr,
+                                 counters ? counters + 4 * r0 : nullptr, phi_starts ? phi_starts + r0 * n_init * 3 : nullptr,
+                                 Q_starts ? Q_starts + r0 * n_init : nullptr, sa ? &sc : nullptr, slot[c].get());
+                launches[wi] += w->last_launches;
+                {   // the worker's stream is idle: the staging slot can be reused
+                    CpnArena* ar = slot[c]->arena;
+                    slot[c].reset();
+                    std::lock_guard<std::mutex> lk(mu);
+                    free_arenas.push_back(ar);
+                    cv.notify_all();
+                }
+                if (r != CPN_OK) {
+                    std::lock_guard<std::mutex> lk(mu);
+                    rc[wi] = r; abort_all = true;
+                    cv.notify_all();
+                    return;
+                }
+            }
+        });
+    }
+    for (auto& t : th) t.join();
+    slot.clear();
+    ctx->last_launches = 0;
+    int ret = CPN_OK;
+    for (int wi = 0; wi <= W; ++wi) {
+        cpn_ctx* w = ctx->children[wi];
+        ctx->last_launches += launches[wi];
+        for (int k = 0; k < CPN_K_NCLASS; ++k) {
+            ctx->prof_ms[k] += w->prof_ms[k]; ctx->prof_launches[k] += w->prof_launches[k];
+            w->prof_ms[k] = 0; w->prof_launches[k] = 0;
+        }
+        if (rc[wi] != CPN_OK && ret == CPN_OK) { ret = rc[wi]; ctx->err = w->err; }
+    }
+    ctx->last_ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
+    return ret;
+}
+
 int cpn_fit_batch(cpn_ctx* ctx, int64_t R, const int64_t* grp_off, const double* Nl, const double* rho_l, const double* d_l,
                   const int64_t* read_off, const double* log_pyx_u, const double* log_pyx_m, const double* phi0, int32_t n_init,
                   int32_t max_em_iters, double amax, double bmax, double cmax, int32_t mstep_mode, double* phi_hat, double* Q,
                   int32_t* status, int64_t* counters, double* phi_starts, double* Q_starts) {
     if (!ctx) return CPN_ERR_ARG;
-    return fit_impl(ctx, false, R, grp_off, Nl, rho_l, d_l, read_off, log_pyx_u, log_pyx_m, phi0, n_init, max_em_iters, amax, bmax, cmax,
-                    mstep_mode, phi_hat, Q, status, counters, phi_starts, Q_starts);
+    return fit_host_chunked(ctx, R, grp_off, Nl, rho_l, d_l, read_off, log_pyx_u, log_pyx_m, phi0, n_init, max_em_iters, amax, bmax, cmax,
+                            mstep_mode, phi_hat, Q, status, counters, phi_starts, Q_starts, nullptr);
 }
 int cpn_fit_batch_device(cpn_ctx* ctx, int64_t R, const int64_t* grp_off, const double* Nl, const double* rho_l, const double* d_l,
                          const int64_t* read_off, const double* log_pyx_u, const double* log_pyx_m, const double* phi0, int32_t n_init,
@@ -1495,6 +1766,11 @@ static int analyze_common(cpn_ctx* ctx, bool dev, int64_t R, const int64_t* grp_
     if (!ctx) return CPN_ERR_ARG;
     CPN_ARG(ctx, cpg_off && rho_n && d_n && sub_off && sub_p && sub_q, "null per-CpG input pointer");
     SummaryArgs sa{cpg_off, sub_off, sub_p, sub_q, rho_n, d_n, logZ, ex, exx, log_g, e_log_g1, e_log_g2, mml, nme};
+    if (!dev) {
+        CPN_ARG(ctx, logZ && ex && exx && log_g && e_log_g1 && e_log_g2 && mml && nme, "null output pointer");
+        return fit_host_chunked(ctx, R, grp_off, Nl, rho_l, d_l, read_off, lu, lm, phi0, n_init, max_em_iters, amax, bmax, cmax, mstep_mode,
+                                phi_hat, Q, status, counters, nullptr, nullptr, &sa);
+    }
     return fit_impl(ctx, dev, R, grp_off, Nl, rho_l, d_l, read_off, lu, lm, phi0, n_init, max_em_iters, amax, bmax, cmax, mstep_mode, phi_hat,
                     Q, status, counters, nullptr, nullptr, &sa);
 }
@@ -1543,8 +1819,8 @@ int cpn_estep_batch(cpn_ctx* ctx, int64_t R, const int64_t* grp_off, const doubl
         DevBuf<double> phil;
         CPN_CUDA(ctx, idesc.alloc(R, s)); CPN_CUDA(ctx, phil.alloc(3 * R, s));
         { KTimer kt(ctx, CPN_K_PREP);
-          k_make_desc<<<blocks_for(R, 256), 256, 0, s>>>((int)R, nullptr, 1, pk.rt.rdesc, d_phi.p, R, idesc.p, phil.p, R); }
-        { KTimer kt(ctx, CPN_K_ESTEP); k_estep<<<blocks_for(R, E_WARPS), E_WARPS * 32, 0, s>>>((int)R, idesc.p, phil.p, R, pk.rt, R, d_ES.p); }
+          k_make_desc<<<blocks_for(R, 256), 256, 0, s>>>((int)R, nullptr, 1, pk.rt.rdesc, d_phi.p, R, idesc.p, phil.p, R, nullptr); }
+        { KTimer kt(ctx, CPN_K_ESTEP); k_estep<<<blocks_for(R, E_WARPS), E_WARPS * 32, 0, s>>>((int)R, idesc.p, phil.p, R, pk.rt, R, d_ES.p, nullptr); }
         { KTimer kt(ctx, CPN_K_PREP); k_unpack3<<<blocks_for(R, 256), 256, 0, s>>>(R, d_ES.p, d_ESo.p); }
         CPN_CUDA(ctx, d_ESo.download(ES, 3 * R, s));
         if (ave_logpy) {
@@ -1556,6 +1832,7 @@ int cpn_estep_batch(cpn_ctx* ctx, int64_t R, const int64_t* grp_off, const doubl
         CPN_CUDA(ctx, cudaEventRecord(ctx->ev1, s));
         CPN_CUDA(ctx, cudaStreamSynchronize(s));
     }
+    trace(ctx, "end");
     float ms = 0;
     CPN_CUDA(ctx, cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1));
     ctx->last_ms = ms;
@@ -1592,6 +1869,7 @@ int cpn_mstep_batch(cpn_ctx* ctx, int64_t R, const int64_t* grp_off, const doubl
         CPN_CUDA(ctx, cudaEventRecord(ctx->ev1, s));
         CPN_CUDA(ctx, cudaStreamSynchronize(s));
     }
+    trace(ctx, "end");
     float ms = 0;
     CPN_CUDA(ctx, cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1));
     ctx->last_ms = ms;

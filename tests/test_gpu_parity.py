@@ -497,6 +497,38 @@ def test_analyze_batch_equals_fit_plus_stat_sums(engine, cpn):
     assert np.array_equal(outs["nme"].cpu().numpy(), ss["nme"], equal_nan=True) and np.array_equal(outs["ex"].cpu().numpy(), ss["ex"], equal_nan=True)
 
 
+def test_host_entry_points_chunked_equals_single_stream(engine, cpn, monkeypatch):
+    """The host-pointer entry points split big batches into chunks of regions that run on worker streams (H2D of one chunk
+    overlapping the kernels of another).  Regions are independent, so any split gives bit-identical results."""
+    nb = cpn.simulations.make_nano_batch(90, M=20, seed=21)
+    n_init = 3
+    phi0 = cpn.simulations.gen_phi0s(np.random.default_rng(4), nb.R, n_init)
+    subs = [engine.lib.nls_reg_info(int(nb.chrst[r]), int(nb.chrend[r]), 350, nb.cpg_pos[nb.cpg_off[r]:nb.cpg_off[r + 1]]) for r in range(nb.R)]
+    sub_off = np.concatenate([[0], np.cumsum([len(s[0]) for s in subs])]).astype(np.int64)
+    sub_p, sub_q = np.concatenate([s[2] for s in subs]), np.concatenate([s[3] for s in subs])
+
+    def run():
+        fit = engine.lib.fit_batch(nb.grp_off, nb.Nl, nb.rho_l, nb.d_l, nb.read_off, nb.log_pyx_u, nb.log_pyx_m, phi0, n_init, 20)
+        out = engine.lib.analyze_batch(nb.grp_off, nb.Nl, nb.rho_l, nb.d_l, nb.read_off, nb.log_pyx_u, nb.log_pyx_m, phi0, n_init, nb.cpg_off,
+                                       nb.rho_n, nb.d_n, sub_off, sub_p, sub_q)
+        return fit, out
+
+    monkeypatch.setenv("CPN_WORKERS", "0")
+    fit1, out1 = run()
+    for workers, chunk, chunks, ratio in ((1, 10, None, None), (2, 20, 3, 1.0), (3, 5, 7, 2.0), (1, 1, 90, 1.0), (2, 1, 200, 1.3)):
+        monkeypatch.setenv("CPN_WORKERS", str(workers))
+        monkeypatch.setenv("CPN_CHUNK_REGIONS", str(chunk))
+        if chunks is not None:
+            monkeypatch.setenv("CPN_CHUNKS", str(chunks))
+            monkeypatch.setenv("CPN_CHUNK_RATIO", str(ratio))
+        fit2, out2 = run()
+        for k in fit1:
+            assert np.array_equal(np.asarray(fit1[k]), np.asarray(fit2[k]), equal_nan=True), (workers, k)
+        for k in out1:
+            assert np.array_equal(np.asarray(out1[k]), np.asarray(out2[k]), equal_nan=True), (workers, k)
+    assert engine.lib.last_launches() > 0
+
+
 def test_analyze_regions_filters(engine, cpn):
     """pmap_analyze_reg's data filters (nanopore.jl:309,322-326): regions failing them keep proc == false."""
     nb = cpn.simulations.make_nano_batch(5, M=30, seed=3)
