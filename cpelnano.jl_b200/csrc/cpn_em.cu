@@ -1273,12 +1273,14 @@ static void trace(const cpn_ctx* ctx, const char* what) {
 
 // Uploads (or borrows) the CSR inputs and builds the per-group and per-read device tables.
 int pack_regions(cpn_ctx* ctx, PackedRegions& pk, bool on_device, bool with_reads, int64_t R, const int64_t* grp_off,
-                 const double* Nl, const double* rho_l, const double* d_l, const int64_t* read_off, const double* lu, const double* lm) {
+                 const double* Nl, const double* rho_l, const double* d_l, const int64_t* read_off, const double* lu, const double* lm,
+                 int offs_mode = -1 /*-1: offsets live where the data lives; 0: offsets on the host, data per on_device*/) {
     cudaStream_t s = ctx->stream;
+    const bool offs_dev = offs_mode < 0 ? on_device : offs_mode != 0;
     pk.R = R;
     pk.h_grp_off.resize(R + 1);
     pk.h_read_off.assign(R + 1, 0);
-    if (on_device) {
+    if (offs_dev) {
         CPN_CUDA(ctx, cudaMemcpyAsync(pk.h_grp_off.data(), grp_off, (R + 1) * sizeof(int64_t), cudaMemcpyDeviceToHost, s));
         if (with_reads) CPN_CUDA(ctx, cudaMemcpyAsync(pk.h_read_off.data(), read_off, (R + 1) * sizeof(int64_t), cudaMemcpyDeviceToHost, s));
         CPN_CUDA(ctx, cudaStreamSynchronize(s));
@@ -1302,7 +1304,7 @@ int pack_regions(cpn_ctx* ctx, PackedRegions& pk, bool on_device, bool with_read
     pk.sumL = pk.h_grp_off[R];
     pk.n_obs = h_obs[R];
     trace(ctx, "pk-begin");
-    CPN_CUDA(ctx, pk.grp_off.bind(grp_off, R + 1, on_device, s));
+    CPN_CUDA(ctx, pk.grp_off.bind(grp_off, R + 1, offs_dev, s));
     CPN_CUDA(ctx, pk.Nl.bind(Nl, pk.sumL, on_device, s));
     CPN_CUDA(ctx, pk.rho.bind(rho_l, pk.sumL, on_device, s));
     CPN_CUDA(ctx, pk.dl.bind(d_l, pk.sumL - R, on_device, s));
@@ -1322,7 +1324,7 @@ int pack_regions(cpn_ctx* ctx, PackedRegions& pk, bool on_device, bool with_read
             h_desc[r].L = (int32_t)(pk.h_grp_off[r + 1] - pk.h_grp_off[r]); h_desc[r].M = (int32_t)(pk.h_read_off[r + 1] - pk.h_read_off[r]);
             h_desc[r].pad = 0;
         }
-        CPN_CUDA(ctx, pk.read_off.bind(read_off, R + 1, on_device, s));
+        CPN_CUDA(ctx, pk.read_off.bind(read_off, R + 1, offs_dev, s));
         CPN_CUDA(ctx, pk.obs_off.upload(h_obs.data(), R + 1, s));
         CPN_CUDA(ctx, pk.ew_off.upload(h_ew.data(), R + 1, s));
         CPN_CUDA(ctx, pk.rb_off.upload(h_rb.data(), R + 1, s));
@@ -1380,19 +1382,21 @@ struct StagedBatch {
 };
 
 int fit_stage(cpn_ctx* ctx, StagedBatch& sb, bool on_device, int64_t R, const int64_t* grp_off, const double* Nl, const double* rho_l,
-              const double* d_l, const int64_t* read_off, const double* lu, const double* lm, const double* phi0, int32_t n_init) {
+              const double* d_l, const int64_t* read_off, const double* lu, const double* lm, const double* phi0, int32_t n_init,
+              int offs_mode = -1) {
     CPN_CUDA(ctx, cudaSetDevice(ctx->device));
     CpnArenaScope scope(sb.arena);
     // ϕ0 first: the raw emissions must stay on top of the workspace stack
     CPN_CUDA(ctx, sb.phi0.bind(phi0, R * n_init * 3, on_device, ctx->stream));
-    return pack_regions(ctx, sb.pk, on_device, true, R, grp_off, Nl, rho_l, d_l, read_off, lu, lm);
+    return pack_regions(ctx, sb.pk, on_device, true, R, grp_off, Nl, rho_l, d_l, read_off, lu, lm, offs_mode);
 }
 
 // `pre` = inputs staged earlier (possibly on another context's stream, already synchronised); the input pointers are then unused.
 int fit_impl(cpn_ctx* ctx, bool on_device, int64_t R, const int64_t* grp_off, const double* Nl, const double* rho_l, const double* d_l,
              const int64_t* read_off, const double* lu, const double* lm, const double* phi0, int32_t n_init, int32_t max_em_iters,
              double amax, double bmax, double cmax, int32_t mstep_mode, double* phi_hat, double* Q, int32_t* status, int64_t* counters,
-             double* phi_starts, double* Q_starts, const SummaryArgs* sa = nullptr, StagedBatch* pre = nullptr) {
+             double* phi_starts, double* Q_starts, const SummaryArgs* sa = nullptr, StagedBatch* pre = nullptr, int offs_mode = -1) {
+    const bool offs_dev = offs_mode < 0 ? on_device : offs_mode != 0;
     CPN_ARG(ctx, R >= 0 && n_init >= 1 && max_em_iters >= 1, "R >= 0, n_init >= 1, max_em_iters >= 1");
     CPN_ARG(ctx, pre || (grp_off && Nl && rho_l && d_l && read_off && lu && lm && phi0), "null pointer");
     CPN_ARG(ctx, phi_hat && Q, "null pointer");
@@ -1526,7 +1530,7 @@ int fit_impl(cpn_ctx* ctx, bool on_device, int64_t R, const int64_t* grp_off, co
             // rscle_grp_mod! + get_stat_sums! (nanopore.jl:338-343) on ϕ̂ straight from device memory; regions without a
             // fit carry NaN ϕ̂ and produce NaN summaries (the host maps them to proc=false).
             std::vector<int64_t> h_cpg(R + 1), h_sub(R + 1);
-            if (on_device) {
+            if (offs_dev) {
                 CPN_CUDA(ctx, cudaMemcpyAsync(h_cpg.data(), sa->cpg_off, (R + 1) * sizeof(int64_t), cudaMemcpyDeviceToHost, s));
                 CPN_CUDA(ctx, cudaMemcpyAsync(h_sub.data(), sa->sub_off, (R + 1) * sizeof(int64_t), cudaMemcpyDeviceToHost, s));
                 CPN_CUDA(ctx, cudaStreamSynchronize(s));
@@ -1541,7 +1545,7 @@ int fit_impl(cpn_ctx* ctx, bool on_device, int64_t R, const int64_t* grp_off, co
             }
             DevIn<int64_t> i_cpg, i_sub, i_sp, i_sq;
             DevIn<double> i_rho, i_dn;
-            CPN_CUDA(ctx, i_cpg.bind(sa->cpg_off, R + 1, on_device, s)); CPN_CUDA(ctx, i_sub.bind(sa->sub_off, R + 1, on_device, s));
+            CPN_CUDA(ctx, i_cpg.bind(sa->cpg_off, R + 1, offs_dev, s)); CPN_CUDA(ctx, i_sub.bind(sa->sub_off, R + 1, offs_dev, s));
             CPN_CUDA(ctx, i_sp.bind(sa->sub_p, sumK, on_device, s)); CPN_CUDA(ctx, i_sq.bind(sa->sub_q, sumK, on_device, s));
             CPN_CUDA(ctx, i_rho.bind(sa->rho_n, sumN, on_device, s)); CPN_CUDA(ctx, i_dn.bind(sa->d_n, sumN - R, on_device, s));
             DevOut<double> s_logZ, s_ex, s_exx, s_lg, s_e1, s_e2, s_mml, s_nme;
@@ -1578,24 +1582,46 @@ extern "C" {
 // one chunk's kernels overlaps the head of the other's.  Regions are independent, so results do not depend on the split.
 static int env_int(const char* name, int dflt) { const char* e = getenv(name); return e ? atoi(e) : dflt; }
 
-static int fit_host_chunked(cpn_ctx* ctx, int64_t R, const int64_t* grp_off, const double* Nl, const double* rho_l, const double* d_l,
-                            const int64_t* read_off, const double* lu, const double* lm, const double* phi0, int32_t n_init,
-                            int32_t max_em_iters, double amax, double bmax, double cmax, int32_t mstep_mode, double* phi_hat, double* Q,
-                            int32_t* status, int64_t* counters, double* phi_starts, double* Q_starts, const SummaryArgs* sa) {
+static int fit_chunked(cpn_ctx* ctx, bool on_device, int64_t R, const int64_t* grp_off_in, const double* Nl, const double* rho_l,
+                       const double* d_l, const int64_t* read_off_in, const double* lu, const double* lm, const double* phi0, int32_t n_init,
+                       int32_t max_em_iters, double amax, double bmax, double cmax, int32_t mstep_mode, double* phi_hat, double* Q,
+                       int32_t* status, int64_t* counters, double* phi_starts, double* Q_starts, const SummaryArgs* sa_in) {
     // Chunk plan: K chunks whose costs (M·L summed over regions) grow geometrically, so the first upload — the only one that
     // nothing overlaps — is short, while later chunks are big enough to keep the EM kernels' late, sparsely populated
-    // iterations amortised.  CPN_WORKERS=0 disables chunking; CPN_CHUNKS / CPN_CHUNK_RATIO / CPN_CHUNK_REGIONS tune the plan.
+    // iterations amortised.  Device-resident inputs have nothing to upload and run as one batch unless CPN_DEVICE_CHUNKS asks
+    // for equal parts (kept for experiments and tests).
+    // CPN_WORKERS=0 disables chunking; CPN_CHUNKS / CPN_CHUNK_RATIO / CPN_CHUNK_REGIONS tune the plan.
     const int n_workers = std::max(0, env_int("CPN_WORKERS", 2));
     const int64_t chunk_regions = std::max(1, env_int("CPN_CHUNK_REGIONS", 12500));
-    int C = (int)((R > 0 && grp_off && read_off && n_workers >= 1) ? std::min<int64_t>(R / chunk_regions, 4) : 0);
-    if (C > 1 && getenv("CPN_CHUNKS")) C = (int)std::min<int64_t>(std::max(1, env_int("CPN_CHUNKS", C)), R);
+    int C = (int)((R > 0 && grp_off_in && read_off_in && n_workers >= 1) ? std::min<int64_t>(R / chunk_regions, 4) : 0);
+    if (on_device) C = std::min(C, 1);     // measured: concurrent chunks do not beat one full-width batch (97.3 vs 97.1 ms per 1e5 regions)
+    const char* cvar = on_device ? "CPN_DEVICE_CHUNKS" : "CPN_CHUNKS";
+    if (R / chunk_regions > 1 && n_workers >= 1 && getenv(cvar)) C = (int)std::min<int64_t>(std::max(1, env_int(cvar, C)), R);
     if (C <= 1)
-        return fit_impl(ctx, false, R, grp_off, Nl, rho_l, d_l, read_off, lu, lm, phi0, n_init, max_em_iters, amax, bmax, cmax, mstep_mode,
-                        phi_hat, Q, status, counters, phi_starts, Q_starts, sa);
+        return fit_impl(ctx, on_device, R, grp_off_in, Nl, rho_l, d_l, read_off_in, lu, lm, phi0, n_init, max_em_iters, amax, bmax, cmax,
+                        mstep_mode, phi_hat, Q, status, counters, phi_starts, Q_starts, sa_in);
     CPN_ARG(ctx, Nl && rho_l && d_l && lu && lm && phi0 && phi_hat && Q, "null pointer");
     CPN_ARG(ctx, n_init >= 1, "n_init >= 1");
     auto t0 = std::chrono::steady_clock::now();
-    const double ratio = getenv("CPN_CHUNK_RATIO") ? std::max(1.0, atof(getenv("CPN_CHUNK_RATIO"))) : 1.3;
+    // the CSR offsets are needed on the host to cut the batch; device-resident ones are fetched once
+    std::vector<int64_t> h_off[4];
+    const int64_t* grp_off = grp_off_in;
+    const int64_t* read_off = read_off_in;
+    SummaryArgs sa_host{};
+    const SummaryArgs* sa = sa_in;
+    if (on_device) {
+        CPN_CUDA(ctx, cudaSetDevice(ctx->device));
+        const int64_t* src[4] = {grp_off_in, read_off_in, sa_in ? sa_in->cpg_off : nullptr, sa_in ? sa_in->sub_off : nullptr};
+        for (int k = 0; k < 4; ++k)
+            if (src[k]) {
+                h_off[k].resize(R + 1);
+                CPN_CUDA(ctx, cudaMemcpyAsync(h_off[k].data(), src[k], (R + 1) * sizeof(int64_t), cudaMemcpyDeviceToHost, ctx->stream));
+            }
+        CPN_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+        grp_off = h_off[0].data(); read_off = h_off[1].data();
+        if (sa_in) { sa_host = *sa_in; sa_host.cpg_off = h_off[2].data(); sa_host.sub_off = h_off[3].data(); sa = &sa_host; }
+    }
+    const double ratio = on_device ? 1.0 : (getenv("CPN_CHUNK_RATIO") ? std::max(1.0, atof(getenv("CPN_CHUNK_RATIO"))) : 1.3);
     std::vector<int64_t> obs(R + 1);       // emission offsets = cumulative cost
     obs[0] = 0;
     for (int64_t r = 0; r < R; ++r) obs[r + 1] = obs[r] + (grp_off[r + 1] - grp_off[r]) * (read_off[r + 1] - read_off[r]);
@@ -1630,6 +1656,9 @@ static int fit_host_chunked(cpn_ctx* ctx, int64_t R, const int64_t* grp_off, con
         ctx->children.push_back(ch);
     }
     for (int i = 0; i <= W; ++i) cpn_set_profile(ctx->children[i], ctx->profile ? 1 : 0);
+    // device-side bracket of the whole call: ev0 precedes every worker stream's work, ev1 follows all of it
+    CPN_CUDA(ctx, cudaEventRecord(ctx->ev0, ctx->stream));
+    for (int i = 0; i <= W; ++i) CPN_CUDA(ctx, cudaStreamWaitEvent(ctx->children[i]->stream, ctx->ev0, 0));
     const int depth = 2;                   // chunks staged ahead of the ones being computed
     while ((int)ctx->slot_arenas.size() < depth + W + 1) ctx->slot_arenas.push_back(new CpnArena());
     std::vector<CpnArena*> free_arenas(ctx->slot_arenas.begin(), ctx->slot_arenas.begin() + depth + W + 1);
@@ -1664,8 +1693,8 @@ static int fit_host_chunked(cpn_ctx* ctx, int64_t R, const int64_t* grp_off, con
                 slot[c].reset(new StagedBatch());
                 slot[c]->arena = ar;
                 trace(u, "stage");
-                r = fit_stage(u, *slot[c], false, Rc, g.data(), Nl + g0, rho_l + g0, d_l + (g0 - r0), rd.data(), lu + obs[r0], lm + obs[r0],
-                              phi0 + r0 * n_init * 3, n_init);
+                r = fit_stage(u, *slot[c], on_device, Rc, g.data(), Nl + g0, rho_l + g0, d_l + (g0 - r0), rd.data(), lu + obs[r0], lm + obs[r0],
+                              phi0 + r0 * n_init * 3, n_init, 0);
                 if (r == CPN_OK && cudaStreamSynchronize(u->stream) != cudaSuccess) { u->err = "stream synchronize failed"; r = CPN_ERR_CUDA; }
                 launches[0] = u->last_launches;
                 trace(u, "staged");
@@ -1702,10 +1731,10 @@ static int fit_host_chunked(cpn_ctx* ctx, int64_t R, const int64_t* grp_off, con
                                      sa->logZ + r0, sa->ex + n0, sa->exx + (n0 - r0), sa->log_g + 4 * k0, sa->e_log_g1 + k0, sa->e_log_g2 + k0,
                                      sa->mml + k0, sa->nme + k0};
                 }
-                int r = fit_impl(w, false, Rc, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, n_init, max_em_iters,
+                int r = fit_impl(w, on_device, Rc, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, n_init, max_em_iters,
                                  amax, bmax, cmax, mstep_mode, phi_hat + 3 * r0, Q + r0, status ? status + r0 : nullptr,
                                  counters ? counters + 4 * r0 : nullptr, phi_starts ? phi_starts + r0 * n_init * 3 : nullptr,
-                                 Q_starts ? Q_starts + r0 * n_init : nullptr, sa ? &sc : nullptr, slot[c].get());
+                                 Q_starts ? Q_starts + r0 * n_init : nullptr, sa ? &sc : nullptr, slot[c].get(), 0);
                 launches[wi] += w->last_launches;
                 {   // the worker's stream is idle: the staging slot can be reused
                     CpnArena* ar = slot[c]->arena;
@@ -1737,6 +1766,17 @@ static int fit_host_chunked(cpn_ctx* ctx, int64_t R, const int64_t* grp_off, con
         if (rc[wi] != CPN_OK && ret == CPN_OK) { ret = rc[wi]; ctx->err = w->err; }
     }
     ctx->last_ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
+    if (ret == CPN_OK) {
+        for (int i = 0; i <= W; ++i) {
+            CPN_CUDA(ctx, cudaEventRecord(ctx->children[i]->ev1, ctx->children[i]->stream));
+            CPN_CUDA(ctx, cudaStreamWaitEvent(ctx->stream, ctx->children[i]->ev1, 0));
+        }
+        CPN_CUDA(ctx, cudaEventRecord(ctx->ev1, ctx->stream));
+        CPN_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+        float ms = 0;
+        CPN_CUDA(ctx, cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1));
+        ctx->last_ms = ms;
+    }
     return ret;
 }
 
@@ -1745,7 +1785,7 @@ int cpn_fit_batch(cpn_ctx* ctx, int64_t R, const int64_t* grp_off, const double*
                   int32_t max_em_iters, double amax, double bmax, double cmax, int32_t mstep_mode, double* phi_hat, double* Q,
                   int32_t* status, int64_t* counters, double* phi_starts, double* Q_starts) {
     if (!ctx) return CPN_ERR_ARG;
-    return fit_host_chunked(ctx, R, grp_off, Nl, rho_l, d_l, read_off, log_pyx_u, log_pyx_m, phi0, n_init, max_em_iters, amax, bmax, cmax,
+    return fit_chunked(ctx, false, R, grp_off, Nl, rho_l, d_l, read_off, log_pyx_u, log_pyx_m, phi0, n_init, max_em_iters, amax, bmax, cmax,
                             mstep_mode, phi_hat, Q, status, counters, phi_starts, Q_starts, nullptr);
 }
 int cpn_fit_batch_device(cpn_ctx* ctx, int64_t R, const int64_t* grp_off, const double* Nl, const double* rho_l, const double* d_l,
@@ -1753,8 +1793,8 @@ int cpn_fit_batch_device(cpn_ctx* ctx, int64_t R, const int64_t* grp_off, const 
                          int32_t max_em_iters, double amax, double bmax, double cmax, int32_t mstep_mode, double* phi_hat, double* Q,
                          int32_t* status, int64_t* counters, double* phi_starts, double* Q_starts) {
     if (!ctx) return CPN_ERR_ARG;
-    return fit_impl(ctx, true, R, grp_off, Nl, rho_l, d_l, read_off, log_pyx_u, log_pyx_m, phi0, n_init, max_em_iters, amax, bmax, cmax,
-                    mstep_mode, phi_hat, Q, status, counters, phi_starts, Q_starts);
+    return fit_chunked(ctx, true, R, grp_off, Nl, rho_l, d_l, read_off, log_pyx_u, log_pyx_m, phi0, n_init, max_em_iters, amax, bmax, cmax,
+                       mstep_mode, phi_hat, Q, status, counters, phi_starts, Q_starts, nullptr);
 }
 
 static int analyze_common(cpn_ctx* ctx, bool dev, int64_t R, const int64_t* grp_off, const double* Nl, const double* rho_l, const double* d_l,
@@ -1768,11 +1808,11 @@ static int analyze_common(cpn_ctx* ctx, bool dev, int64_t R, const int64_t* grp_
     SummaryArgs sa{cpg_off, sub_off, sub_p, sub_q, rho_n, d_n, logZ, ex, exx, log_g, e_log_g1, e_log_g2, mml, nme};
     if (!dev) {
         CPN_ARG(ctx, logZ && ex && exx && log_g && e_log_g1 && e_log_g2 && mml && nme, "null output pointer");
-        return fit_host_chunked(ctx, R, grp_off, Nl, rho_l, d_l, read_off, lu, lm, phi0, n_init, max_em_iters, amax, bmax, cmax, mstep_mode,
+        return fit_chunked(ctx, false, R, grp_off, Nl, rho_l, d_l, read_off, lu, lm, phi0, n_init, max_em_iters, amax, bmax, cmax, mstep_mode,
                                 phi_hat, Q, status, counters, nullptr, nullptr, &sa);
     }
-    return fit_impl(ctx, dev, R, grp_off, Nl, rho_l, d_l, read_off, lu, lm, phi0, n_init, max_em_iters, amax, bmax, cmax, mstep_mode, phi_hat,
-                    Q, status, counters, nullptr, nullptr, &sa);
+    return fit_chunked(ctx, true, R, grp_off, Nl, rho_l, d_l, read_off, lu, lm, phi0, n_init, max_em_iters, amax, bmax, cmax, mstep_mode,
+                       phi_hat, Q, status, counters, nullptr, nullptr, &sa);
 }
 
 int cpn_analyze_batch(cpn_ctx* ctx, int64_t R, const int64_t* grp_off, const double* Nl, const double* rho_l, const double* d_l,

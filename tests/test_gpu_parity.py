@@ -452,6 +452,32 @@ def test_two_sample_batched_permutations(engine, orc, cpn):
         assert np.all((out["pval"][:, ok] > 0) & (out["pval"][:, ok] <= 1))
 
 
+def _analyze_device(engine, cpn, nb, phi0, n_init, sub_off, sub_p, sub_q):
+    """cpn_analyze_batch_device on torch-owned device buffers; returns the outputs as numpy arrays."""
+    import torch
+    ins = dict(grp_off=nb.grp_off, Nl=nb.Nl, rho_l=nb.rho_l, d_l=nb.d_l, read_off=nb.read_off, lu=nb.log_pyx_u, lm=nb.log_pyx_m,
+               phi0=phi0.reshape(-1), cpg_off=nb.cpg_off, rho_n=nb.rho_n, d_n=nb.d_n, sub_off=sub_off, sub_p=sub_p, sub_q=sub_q)
+    dev = {k: torch.from_numpy(np.ascontiguousarray(v)).cuda() for k, v in ins.items()}
+    sN, sK, R = int(nb.cpg_off[-1]), int(sub_off[-1]), nb.R
+    outs = dict(phi_hat=torch.empty(3 * R, dtype=torch.float64, device="cuda"), Q=torch.empty(R, dtype=torch.float64, device="cuda"),
+                status=torch.empty(R, dtype=torch.int32, device="cuda"), counters=torch.empty(4 * R, dtype=torch.int64, device="cuda"),
+                logZ=torch.empty(R, dtype=torch.float64, device="cuda"), ex=torch.empty(sN, dtype=torch.float64, device="cuda"),
+                exx=torch.empty(sN - R, dtype=torch.float64, device="cuda"), log_g=torch.empty(4 * sK, dtype=torch.float64, device="cuda"),
+                e1=torch.empty(sK, dtype=torch.float64, device="cuda"), e2=torch.empty(sK, dtype=torch.float64, device="cuda"),
+                mml=torch.empty(sK, dtype=torch.float64, device="cuda"), nme=torch.empty(sK, dtype=torch.float64, device="cuda"))
+    torch.cuda.synchronize()
+    p = {k: v.data_ptr() for k, v in dev.items()}
+    o = {k: v.data_ptr() for k, v in outs.items()}
+    engine.lib.analyze_batch_raw(R, p["grp_off"], p["Nl"], p["rho_l"], p["d_l"], p["read_off"], p["lu"], p["lm"], p["phi0"], n_init, 20,
+                                 (20.0, 150.0, 50.0), cpn.MSTEP_ANALYTIC, p["cpg_off"], p["rho_n"], p["d_n"], p["sub_off"], p["sub_p"], p["sub_q"],
+                                 o["phi_hat"], o["Q"], o["status"], o["counters"], o["logZ"], o["ex"], o["exx"], o["log_g"], o["e1"], o["e2"],
+                                 o["mml"], o["nme"], True)
+    torch.cuda.synchronize()
+    res = {k: v.cpu().numpy() for k, v in outs.items()}
+    res["phi_hat"] = res["phi_hat"].reshape(R, 3)
+    return res
+
+
 def test_analyze_batch_equals_fit_plus_stat_sums(engine, cpn):
     """cpn_analyze_batch (ϕ̂ stays on the device between the EM kernels and the summaries kernel) is bit-identical to
     cpn_fit_batch followed by cpn_stat_sums_batch, for host and for device pointers; regions without a fit get NaN."""
@@ -475,26 +501,10 @@ def test_analyze_batch_equals_fit_plus_stat_sums(engine, cpn):
         assert np.all(np.isnan(out["mml"][sub_off[r]:sub_off[r + 1]])) and np.isnan(out["logZ"][r])
     assert (out["pick"] >= 0).sum() >= nb.R // 2
     # device-pointer variant
-    ins = dict(grp_off=nb.grp_off, Nl=nb.Nl, rho_l=nb.rho_l, d_l=nb.d_l, read_off=nb.read_off, lu=nb.log_pyx_u, lm=nb.log_pyx_m,
-               phi0=phi0.reshape(-1), cpg_off=nb.cpg_off, rho_n=nb.rho_n, d_n=nb.d_n, sub_off=sub_off, sub_p=sub_p, sub_q=sub_q)
-    dev = {k: torch.from_numpy(np.ascontiguousarray(v)).cuda() for k, v in ins.items()}
-    sN, sK, R = int(nb.cpg_off[-1]), int(sub_off[-1]), nb.R
-    outs = dict(phi_hat=torch.empty(3 * R, dtype=torch.float64, device="cuda"), Q=torch.empty(R, dtype=torch.float64, device="cuda"),
-                status=torch.empty(R, dtype=torch.int32, device="cuda"), counters=torch.empty(4 * R, dtype=torch.int64, device="cuda"),
-                logZ=torch.empty(R, dtype=torch.float64, device="cuda"), ex=torch.empty(sN, dtype=torch.float64, device="cuda"),
-                exx=torch.empty(sN - R, dtype=torch.float64, device="cuda"), log_g=torch.empty(4 * sK, dtype=torch.float64, device="cuda"),
-                e1=torch.empty(sK, dtype=torch.float64, device="cuda"), e2=torch.empty(sK, dtype=torch.float64, device="cuda"),
-                mml=torch.empty(sK, dtype=torch.float64, device="cuda"), nme=torch.empty(sK, dtype=torch.float64, device="cuda"))
-    torch.cuda.synchronize()
-    p = {k: v.data_ptr() for k, v in dev.items()}
-    o = {k: v.data_ptr() for k, v in outs.items()}
-    engine.lib.analyze_batch_raw(R, p["grp_off"], p["Nl"], p["rho_l"], p["d_l"], p["read_off"], p["lu"], p["lm"], p["phi0"], n_init, 20,
-                                 (20.0, 150.0, 50.0), cpn.MSTEP_ANALYTIC, p["cpg_off"], p["rho_n"], p["d_n"], p["sub_off"], p["sub_p"], p["sub_q"],
-                                 o["phi_hat"], o["Q"], o["status"], o["counters"], o["logZ"], o["ex"], o["exx"], o["log_g"], o["e1"], o["e2"],
-                                 o["mml"], o["nme"], True)
-    torch.cuda.synchronize()
-    assert np.array_equal(outs["phi_hat"].cpu().numpy().reshape(R, 3), fit["phi_hat"], equal_nan=True)
-    assert np.array_equal(outs["nme"].cpu().numpy(), ss["nme"], equal_nan=True) and np.array_equal(outs["ex"].cpu().numpy(), ss["ex"], equal_nan=True)
+    outs = _analyze_device(engine, cpn, nb, phi0, n_init, sub_off, sub_p, sub_q)
+    R = nb.R
+    assert np.array_equal(outs["phi_hat"], fit["phi_hat"], equal_nan=True)
+    assert np.array_equal(outs["nme"], ss["nme"], equal_nan=True) and np.array_equal(outs["ex"], ss["ex"], equal_nan=True)
 
 
 def test_host_entry_points_chunked_equals_single_stream(engine, cpn, monkeypatch):
@@ -527,6 +537,13 @@ def test_host_entry_points_chunked_equals_single_stream(engine, cpn, monkeypatch
         for k in out1:
             assert np.array_equal(np.asarray(out1[k]), np.asarray(out2[k]), equal_nan=True), (workers, k)
     assert engine.lib.last_launches() > 0
+    # device-resident inputs are cut into chunks too (offsets fetched to the host once)
+    monkeypatch.setenv("CPN_DEVICE_CHUNKS", "3")
+    dev = _analyze_device(engine, cpn, nb, phi0, n_init, sub_off, sub_p, sub_q)
+    for k, k1 in (("phi_hat", "phi_hat"), ("Q", "Q"), ("status", "pick"), ("logZ", "logZ"), ("ex", "ex"), ("exx", "exx"), ("log_g", "log_g"),
+                  ("e1", "e_log_g1"), ("e2", "e_log_g2"), ("mml", "mml"), ("nme", "nme")):
+        assert np.array_equal(dev[k].reshape(-1), np.asarray(out1[k1]).reshape(-1), equal_nan=True), k
+    assert np.array_equal(dev["counters"].reshape(-1), np.asarray(out1["counters"]).reshape(-1))
 
 
 def test_analyze_regions_filters(engine, cpn):
