@@ -1255,6 +1255,8 @@ struct PackedRegions {
 
 inline unsigned blocks_for(int64_t n, int per_block) { return (unsigned)((n + per_block - 1) / per_block); }
 
+static int env_int(const char* name, int dflt) { const char* e = getenv(name); return e ? atoi(e) : dflt; }
+
 // CPN_TRACE=1 prints host-side phase timestamps (ms since the first traced event) to stderr.
 static void trace(const cpn_ctx* ctx, const char* what) {
     static const bool on = getenv("CPN_TRACE") != nullptr;
@@ -1448,7 +1450,11 @@ int fit_impl(cpn_ctx* ctx, bool on_device, int64_t R, const int64_t* grp_off, co
             std::vector<int64_t> cnt(Lmax + 2, 0);
             for (int64_t r = 0; r < R; ++r) cnt[pk.h_grp_off[r + 1] - pk.h_grp_off[r] + 1]++;
             for (int64_t l = 0; l <= Lmax; ++l) cnt[l + 1] += cnt[l];
-            for (int64_t r = 0; r < R; ++r) h_order[cnt[pk.h_grp_off[r + 1] - pk.h_grp_off[r]]++] = (int)r;
+            const bool desc = env_int("CPN_ORDER_DESC", 1) != 0;
+            for (int64_t r = 0; r < R; ++r) {
+                int64_t pos = cnt[pk.h_grp_off[r + 1] - pk.h_grp_off[r]]++;
+                h_order[desc ? R - 1 - pos : pos] = (int)r;     // longest chains first: the kernels' tails are made of short ones
+            }
         }
         CPN_CUDA(ctx, order.upload(h_order.data(), R, s));
         DevBuf<double> gh;
@@ -1580,7 +1586,6 @@ extern "C" {
 // Host-pointer entry points split a large batch into contiguous chunks of regions (balanced by M·L) and run them on worker
 // threads, each with its own stream: the host→device copy of chunk k+1 overlaps the EM kernels of chunk k, and the tail of
 // one chunk's kernels overlaps the head of the other's.  Regions are independent, so results do not depend on the split.
-static int env_int(const char* name, int dflt) { const char* e = getenv(name); return e ? atoi(e) : dflt; }
 
 static int fit_chunked(cpn_ctx* ctx, bool on_device, int64_t R, const int64_t* grp_off_in, const double* Nl, const double* rho_l,
                        const double* d_l, const int64_t* read_off_in, const double* lu, const double* lm, const double* phi0, int32_t n_init,
