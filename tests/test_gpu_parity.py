@@ -546,6 +546,73 @@ def test_host_entry_points_chunked_equals_single_stream(engine, cpn, monkeypatch
     assert np.array_equal(dev["counters"].reshape(-1), np.asarray(out1["counters"]).reshape(-1))
 
 
+def test_full_size_batch_properties(engine, orc, cpn):
+    """BASELINE.json config 2 size (1e5 regions × 30 reads × 10 starts, ≤ 20 EM iterations) through cpn_analyze_batch.
+    Size-independent properties: (1) position independence — the batch is five copies of the same 20 000 regions and every
+    copy must come out bit-identical although the copies sit in different chunks, thread blocks and work-queue positions;
+    (2) a slice run on its own equals the same slice of the full run; (3) ranges of every output; (4) NaN exactly where no
+    start converged; (5) a handful of regions against the oracle's full multi-start EM."""
+    base_R, copies, n_init = 20000, 5, 10
+    nb = cpn.simulations.make_nano_batch(base_R, M=30, seed=17)
+    phi0 = cpn.simulations.gen_phi0s(np.random.default_rng(18), base_R, n_init)
+    lib = engine.lib
+    subs = [lib.nls_reg_info(int(nb.chrst[r]), int(nb.chrend[r]), 350, nb.cpg_pos[nb.cpg_off[r]:nb.cpg_off[r + 1]]) for r in range(base_R)]
+    K = np.array([len(s[0]) for s in subs])
+    sub_p, sub_q = np.concatenate([s[2] for s in subs]), np.concatenate([s[3] for s in subs])
+
+    def tile_off(off):
+        d = np.diff(off)
+        return np.concatenate([[0], np.cumsum(np.tile(d, copies))]).astype(np.int64)
+
+    R = base_R * copies
+    t = lambda a: np.tile(a, copies)                                                    # noqa: E731
+    out = lib.analyze_batch(tile_off(nb.grp_off), t(nb.Nl), t(nb.rho_l), t(nb.d_l), tile_off(nb.read_off), t(nb.log_pyx_u), t(nb.log_pyx_m),
+                            np.tile(phi0, (copies, 1, 1)), n_init, tile_off(nb.cpg_off), t(nb.rho_n), t(nb.d_n),
+                            tile_off(np.concatenate([[0], np.cumsum(K)])), t(sub_p), t(sub_q))
+    assert out["phi_hat"].shape == (R, 3)
+    # (1) position independence
+    for k in ("phi_hat", "Q", "pick", "counters", "logZ", "ex", "exx", "mml", "nme", "e_log_g1", "e_log_g2", "log_g"):
+        a = np.asarray(out[k])
+        a = a.reshape(copies, -1)
+        for c in range(1, copies):
+            assert np.array_equal(a[0], a[c], equal_nan=True), (k, c)
+    # (2) a slice on its own
+    r0, r1 = 7000, 9000
+    g0, g1 = nb.grp_off[r0], nb.grp_off[r1]; o0, o1 = nb.obs_off[r0], nb.obs_off[r1]; n0, n1 = nb.cpg_off[r0], nb.cpg_off[r1]
+    koff = np.concatenate([[0], np.cumsum(K)])
+    part = lib.analyze_batch(nb.grp_off[r0:r1 + 1] - g0, nb.Nl[g0:g1], nb.rho_l[g0:g1], nb.d_l[g0 - r0:g1 - r1], nb.read_off[r0:r1 + 1] - nb.read_off[r0],
+                             nb.log_pyx_u[o0:o1], nb.log_pyx_m[o0:o1], phi0[r0:r1], n_init, nb.cpg_off[r0:r1 + 1] - n0, nb.rho_n[n0:n1],
+                             nb.d_n[n0 - r0:n1 - r1], koff[r0:r1 + 1] - koff[r0], sub_p[koff[r0]:koff[r1]], sub_q[koff[r0]:koff[r1]])
+    assert np.array_equal(part["phi_hat"], out["phi_hat"][r0:r1], equal_nan=True)
+    assert np.array_equal(part["nme"], out["nme"][koff[r0]:koff[r1]], equal_nan=True)
+    assert np.array_equal(part["ex"], out["ex"][n0:n1], equal_nan=True)
+    # (3) ranges, (4) NaN pattern
+    ok = out["pick"][:base_R] >= 0
+    assert ok.mean() > 0.9
+    ph = out["phi_hat"][:base_R]
+    assert np.all(np.isnan(ph[~ok])) and np.all(np.isfinite(ph[ok]))
+    assert np.all(np.abs(ph[ok]) <= np.array([20.0, 150.0, 50.0]))
+    assert np.all(out["Q"][:base_R][ok] < 0) and np.all(np.isneginf(out["Q"][:base_R][~ok]))
+    okn = np.repeat(ok, np.diff(nb.cpg_off))
+    ex = out["ex"][:nb.cpg_off[-1]]
+    assert np.all(np.abs(ex[okn]) <= 1.0) and np.all(np.isnan(ex[~okn]))
+    okk = np.repeat(ok, K)
+    mml, nme = out["mml"][:koff[-1]], out["nme"][:koff[-1]]
+    has = np.tile(sub_p, 1)[:koff[-1]] > 0                                           # sub-regions with at least one CpG
+    assert np.all((mml[okk & has] >= 0) & (mml[okk & has] <= 1))
+    assert np.all((nme[okk & has] >= -1e-12) & (nme[okk & has] <= 1 + 1e-9))
+    cnt = out["counters"][:base_R]
+    assert np.all(cnt[:, 0] == cnt[:, 3]) and np.all(cnt[:, 0] <= n_init * 20) and np.all(cnt[:, 0] >= n_init)
+    # (5) oracle on a few regions
+    idx = np.array([3, 4999, 12345, 19999])
+    sub = nb.subset(idx)
+    ref = orc.fit_batch(sub.grp_off, sub.Nl, sub.rho_l, sub.d_l, sub.read_off, sub.log_pyx_u, sub.log_pyx_m, phi0[idx], n_init, 20, n_threads=4)
+    both = (ref["pick"] >= 0) & ok[idx]
+    assert both.sum() >= 3
+    rel = np.abs(ref["Q"][both] - out["Q"][idx][both]) / np.abs(ref["Q"][both])
+    assert np.median(rel) < 1e-7 and rel.max() < 1e-3, rel      # picked optimum; see DESIGN.md §6 for why not tighter
+
+
 def test_analyze_regions_filters(engine, cpn):
     """pmap_analyze_reg's data filters (nanopore.jl:309,322-326): regions failing them keep proc == false."""
     nb = cpn.simulations.make_nano_batch(5, M=30, seed=3)
