@@ -14,7 +14,7 @@ MSTEP_FD, MSTEP_ANALYTIC = 0, 1
 # every exported symbol of include/cpelnano_b200.h (tests check the library exports exactly these)
 SYMBOLS = ["cpn_create", "cpn_destroy", "cpn_last_error", "cpn_version", "cpn_last_device_ms", "cpn_last_launches",
            "cpn_measure_fp64_peak", "cpn_set_profile", "cpn_get_profile", "cpn_analyze_batch", "cpn_analyze_batch_device", "cpn_fit_batch", "cpn_fit_batch_device", "cpn_estep_batch", "cpn_mstep_batch",
-           "cpn_stat_sums_batch", "cpn_nls_reg_info", "cpn_cmd_batch", "cpn_grp_unmat_sweep", "cpn_grp_mat_sweep", "cpn_two_samp_pvals"]
+           "cpn_stat_sums_batch", "cpn_nls_reg_info", "cpn_cmd_batch", "cpn_grp_unmat_sweep", "cpn_grp_mat_sweep", "cpn_two_samp_pvals", "cpn_two_samp_null_batch"]
 
 
 class CpnError(RuntimeError):
@@ -272,6 +272,25 @@ class Library:
                                         C.c_int64(len(js)), C.c_int32(int(exact)), _ptr(T), _ptr(cnt), _ptr(p))
         self._check(rc, ctx)
         return T, cnt, p
+
+    def two_samp_null_batch(self, grp_off, Nl, rho_l, d_l, read_off, lu, lm, perm_off, n1, perm_ids, phi0, n_init, cpg_off, rho_n, d_n,
+                            sub_off, sub_p, sub_q, max_em_iters=20, box=(20.0, 150.0, 50.0), mstep_mode=MSTEP_ANALYTIC, device=0):
+        """cpn_two_samp_null_batch: returns (T_null flat [Σ P_r·3·K_r], fit_status [Σ P_r·2])."""
+        grp_off, read_off, perm_off, n1 = _i64(grp_off), _i64(read_off), _i64(perm_off), _i64(n1)
+        Nl, rho_l, d_l, lu, lm, phi0 = _f64(Nl), _f64(rho_l), _f64(d_l), _f64(lu), _f64(lm), _f64(phi0)
+        perm_ids = _i32(perm_ids)
+        cpg_off, sub_off, sub_p, sub_q, rho_n, d_n = _i64(cpg_off), _i64(sub_off), _i64(sub_p), _i64(sub_q), _f64(rho_n), _f64(d_n)
+        R = len(grp_off) - 1
+        P_r = np.diff(perm_off)
+        T = np.empty(int((3 * P_r * np.diff(sub_off)).sum()))
+        status = np.empty(int(2 * perm_off[-1]), dtype=np.int32)
+        ctx = self.ctx(device)
+        rc = self.dll.cpn_two_samp_null_batch(ctx, C.c_int64(R), _ptr(grp_off), _ptr(Nl), _ptr(rho_l), _ptr(d_l), _ptr(read_off), _ptr(lu), _ptr(lm),
+                                              _ptr(perm_off), _ptr(n1), _ptr(perm_ids), _ptr(phi0), C.c_int32(n_init), C.c_int32(max_em_iters),
+                                              C.c_double(box[0]), C.c_double(box[1]), C.c_double(box[2]), C.c_int32(mstep_mode), _ptr(cpg_off),
+                                              _ptr(rho_n), _ptr(d_n), _ptr(sub_off), _ptr(sub_p), _ptr(sub_q), _ptr(T), _ptr(status))
+        self._check(rc, ctx)
+        return T, status
 
     def two_samp_pvals(self, tbl_off, P, T_obs, T_null, exact, device=0):
         tbl_off = _i64(tbl_off)

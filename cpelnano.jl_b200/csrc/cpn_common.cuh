@@ -228,6 +228,12 @@ int cpn_stat_sums_launch(cpn_ctx* ctx, int64_t T, const double* phi, const int64
                          const int64_t* sub_q, int64_t Nmax, double* logZ, double* ex, double* exx, double* log_g, double* e_log_g1,
                          double* e_log_g2, double* mml, double* nme);
 
+// Launch-only entry of the CMD kernel (all pointers on the device); defined in cpn_summaries.cu.
+int cpn_cmd_launch(cpn_ctx* ctx, int64_t P, const int64_t* pair_a, const int64_t* pair_b, const double* phi_tbl, const int64_t* reg_of,
+                   const int64_t* ex_off, const double* ex_tbl, const double* exx_tbl, const int64_t* nme_off, const double* nme_tbl,
+                   const int64_t* cpg_off, const double* rho_n, const double* d_n, const int64_t* sub_off, const int64_t* sub_p,
+                   const int64_t* sub_q, int64_t Nmax, const int64_t* cmd_off, double* cmd);
+
 struct LaunchCounter {
     cpn_ctx* ctx;
     explicit LaunchCounter(cpn_ctx* c) : ctx(c) { ctx->last_launches = 0; }

@@ -52,8 +52,11 @@ struct __align__(32) SweepSite { double na, nb, id, id2; };
 // What an E-step warp needs to know about its EM instance, stored by POSITION in the active list (written by
 // k_init_state / k_compact_scatter) so that the warp's first loads do not depend on each other:
 // instance id, region geometry, start of the packed emissions, and the instance's current ϕ.
-struct __align__(32) ItemDesc { int inst, L, M, pad; int64_t g0, ew_off; };
-struct __align__(32) RegionDesc { int64_t g0, ew_off; int32_t L, M; int64_t pad; };
+struct __align__(32) ItemDesc { int inst, L, M, ridx; int64_t g0, ew_off; };
+// A "region" of the EM kernels.  Normally one estimation region with its own reads.  A VIEW (two-sample permutation
+// refits) shares the group tables and the packed emissions of a base region and names its reads through an index table:
+// ridx ≥ 0 is the first row (32 int32 read ids, one per lane and chunk) of the view in RegionTables::ridx; −1 = all reads.
+struct __align__(16) RegionDesc { int64_t g0, ew_off, rb_off; int32_t L, M, ridx, pad; };
 
 struct RegionTables {
     // per group (offsets grp_off): N_l, N_l·ρ_l and 1/d_l (coupling l→l+1; entry L-1 unused)
@@ -66,6 +69,7 @@ struct RegionTables {
     const int64_t* ew_off;     // [R] start of the region's block: [chunk][l][32]
     const int64_t* rb_off;     // [R] start of the per-read base (Σ_obs log p(y|−1)) block: [chunk][32]
     const double *ew, *rb;
+    const int32_t* ridx;       // read-id rows of views (null when there are none)
 };
 
 // Per-group potentials of one EM instance, staged in shared memory as three 16-byte pairs so that a chain step reads
@@ -231,10 +235,10 @@ __device__ __forceinline__ void ering_issue(EmisRing& ring, int slot, const doub
 template <bool BPOS>
 __device__ __forceinline__ void estep_chunk(SiteTile& st, EmisRing& ring, int L, int lane, const double* __restrict__ na_g,
                                             const double* __restrict__ nb_g, const double* __restrict__ invd_g,
-                                            const double* __restrict__ ewc, double a, double b, double cabs, double out[3]) {
+                                            const double* __restrict__ p /*emission weight of (group l, this lane's read) at p[l*32]*/,
+                                            double a, double b, double cabs, double out[3]) {
     EState s{1.0, 1.0, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0};
     double sc = 1.0;
-    const double* p = ewc + lane;                       // emission weight of (group l, this lane) at p[l*32]
     const int Lfull = L & ~(E_PF - 1);
     const int ngrp = Lfull / E_PF;
     // in flight from the start: the first block of rows (slot 0) and the chain tail (slot 2)
@@ -296,7 +300,7 @@ __global__ void __launch_bounds__(E_WARPS * 32, E_BLOCKS) k_estep(int n_items, c
     const int4 d0 = __ldg(dq);
     const longlong2 d1 = __ldg(reinterpret_cast<const longlong2*>(dq + 1));
     double a = phil[item], b = phil[cap + item], c = phil[2 * cap + item];
-    const int inst = d0.x, L = d0.y, M = d0.z;
+    const int inst = d0.x, L = d0.y, M = d0.z, ridx = d0.w;
     const int64_t g0 = d1.x;
     bool bpos = __double2hiint(c) >= 0;
     double cabs = fabs(c);
@@ -305,9 +309,12 @@ __global__ void __launch_bounds__(E_WARPS * 32, E_BLOCKS) k_estep(int n_items, c
     int nchunk = (M + 31) >> 5;
     for (int ch = 0; ch < nchunk; ++ch) {
         double o[3];
-        const double* ewc = ew_r + (size_t)ch * L * 32;
-        if (bpos) estep_chunk<true>(tiles[w], rings[w], L, lane, rt.na + g0, rt.nb + g0, rt.invd + g0, ewc, a, b, cabs, o);
-        else estep_chunk<false>(tiles[w], rings[w], L, lane, rt.na + g0, rt.nb + g0, rt.invd + g0, ewc, a, b, cabs, o);
+        // this lane's read: lane of chunk ch, or — in a view — the pooled read the view's index row names
+        int q = ch * 32 + lane;
+        if (ridx >= 0) q = __ldg(rt.ridx + ((size_t)(ridx + ch) << 5) + lane);
+        const double* p = ew_r + (size_t)(q >> 5) * L * 32 + (q & 31);
+        if (bpos) estep_chunk<true>(tiles[w], rings[w], L, lane, rt.na + g0, rt.nb + g0, rt.invd + g0, p, a, b, cabs, o);
+        else estep_chunk<false>(tiles[w], rings[w], L, lane, rt.na + g0, rt.nb + g0, rt.invd + g0, p, a, b, cabs, o);
         bool live = ch * 32 + lane < M;
         acc0 += cpn_warp_sum(live ? o[0] : 0.0);
         acc1 += cpn_warp_sum(live ? o[1] : 0.0);
@@ -328,7 +335,7 @@ __global__ void k_make_desc(int n_items, const int* __restrict__ items, int n_in
     int inst = items ? items[i] : i;
     RegionDesc rd = rdesc[inst / n_init];
     ItemDesc d;
-    d.inst = inst; d.L = rd.L; d.M = rd.M; d.pad = 0; d.g0 = rd.g0; d.ew_off = rd.ew_off;
+    d.inst = inst; d.L = rd.L; d.M = rd.M; d.ridx = rd.ridx; d.g0 = rd.g0; d.ew_off = rd.ew_off;
     desc[i] = d;
     phil[i] = phi[inst]; phil[cap + i] = phi[NI + inst]; phil[2 * cap + i] = phi[2 * NI + inst];
 }
@@ -340,7 +347,8 @@ __global__ void k_make_desc(int n_items, const int* __restrict__ items, int n_in
 template <bool BPOS>
 __device__ __forceinline__ double logz_chunk(SiteTile& st, int L, int lane, const double* __restrict__ na_g,
                                              const double* __restrict__ nb_g, const double* __restrict__ invd_g,
-                                             const double* __restrict__ ewc /*null → r = 1*/, double a, double b, double cabs) {
+                                             const double* __restrict__ p /*this lane's read, row stride 32; null → r = 1*/, double a,
+                                             double b, double cabs) {
     double fp = 1.0, fm = 1.0, sc = 1.0;           // all-ones message; group 0 carries t = 0 (see fill_tile)
     int esum = 0, e;
     for (int l0 = 0; l0 < L; l0 += TILE) {
@@ -349,7 +357,7 @@ __device__ __forceinline__ double logz_chunk(SiteTile& st, int L, int lane, cons
         fill_tile(st, l0, n, lane, na_g, nb_g, invd_g, a, b, cabs, BPOS);
         __syncwarp();
         for (int j = 0; j < n; ++j) {
-            double r = ewc ? ewc[(size_t)(l0 + j) * 32 + lane] : 1.0;
+            double r = p ? p[(size_t)(l0 + j) * 32] : 1.0;
             const double2 w = st.w[j];
             double t = st.tn[j].x;
             double phiP = (w.y * r) * sc, phiM = w.x * sc;
@@ -375,23 +383,25 @@ __global__ void __launch_bounds__(E_WARPS * 32) k_score(int n_items, const int* 
         if (lane == 0) Q[inst] = -cpn_inf();
         return;
     }
-    int64_t r = inst / n_init;
-    int64_t g0 = rt.grp_off[r];
-    int L = (int)(rt.grp_off[r + 1] - g0);
-    int64_t M = rt.read_off[r + 1] - rt.read_off[r];
+    const RegionDesc rd = rt.rdesc[inst / n_init];
+    const int64_t g0 = rd.g0;
+    const int L = rd.L;
+    const int64_t M = rd.M;
     double a = phi[inst], b = phi[NI + inst], c = phi[2 * NI + inst];
     bool bpos = c >= 0.0;
     double cabs = fabs(c);
-    const double* ew_r = rt.ew + rt.ew_off[r];
-    const double* rb_r = rt.rb + rt.rb_off[r];
+    const double* ew_r = rt.ew + rd.ew_off;
+    const double* rb_r = rt.rb + rd.rb_off;
     int nchunk = (int)((M + 31) >> 5);
     double acc = 0.0;
     for (int ch = 0; ch < nchunk; ++ch) {
-        const double* ewc = ew_r + (size_t)ch * L * 32;
-        double lz = bpos ? logz_chunk<true>(tiles[w], L, lane, rt.na + g0, rt.nb + g0, rt.invd + g0, ewc, a, b, cabs)
-                         : logz_chunk<false>(tiles[w], L, lane, rt.na + g0, rt.nb + g0, rt.invd + g0, ewc, a, b, cabs);
+        int q = ch * 32 + lane;
+        if (rd.ridx >= 0) q = __ldg(rt.ridx + ((size_t)(rd.ridx + ch) << 5) + lane);
+        const double* p = ew_r + (size_t)(q >> 5) * L * 32 + (q & 31);
+        double lz = bpos ? logz_chunk<true>(tiles[w], L, lane, rt.na + g0, rt.nb + g0, rt.invd + g0, p, a, b, cabs)
+                         : logz_chunk<false>(tiles[w], L, lane, rt.na + g0, rt.nb + g0, rt.invd + g0, p, a, b, cabs);
         bool live = (int64_t)ch * 32 + lane < M;
-        acc += cpn_warp_sum(live ? rb_r[ch * 32 + lane] + lz : 0.0);
+        acc += cpn_warp_sum(live ? rb_r[q] + lz : 0.0);
     }
     // marginal chain (no data): every lane computes the same value
     double lz0 = bpos ? logz_chunk<true>(tiles[w], L, lane, rt.na + g0, rt.nb + g0, rt.invd + g0, nullptr, a, b, cabs)
@@ -815,12 +825,12 @@ __global__ void __launch_bounds__(M_THREADS) k_mstep(int n_items, const int* __r
     int inst = -1;
     if (item < n_items) {
         inst = items ? items[item] : item;
-        int64_t r = inst / n_init;
-        int64_t g0 = rt.grp_off[r];
+        const RegionDesc rd = rt.rdesc[inst / n_init];
+        int64_t g0 = rd.g0;
         MProblem pb;
         pb.na = rt.na + g0; pb.nb = rt.nb + g0; pb.invd = rt.invd + g0; pb.sq = rt.sq + g0;
-        pb.L = (int)(rt.grp_off[r + 1] - g0);
-        double Mr = (double)(rt.read_off[r + 1] - rt.read_off[r]);
+        pb.L = rd.L;
+        double Mr = (double)rd.M;
         int64_t NI = st.NI;
         pb.t0 = st.ES[inst] / Mr; pb.t1 = st.ES[NI + inst] / Mr; pb.t2 = st.ES[2 * NI + inst] / Mr;
         pb.mode = mode; pb.evals = 0;
@@ -968,11 +978,10 @@ __global__ void __launch_bounds__(M_THREADS, WS_BLOCKS) k_mstep_ws(int n_items, 
                     if (item < n_items) {
                         inst = items ? items[item] : item;
                         pos = item;
-                        int64_t r = inst / n_init;
-                        int64_t g0 = rt.grp_off[r];
-                        tbl = rt.sq + g0;
-                        L = (int)(rt.grp_off[r + 1] - g0);
-                        double Mr = (double)(rt.read_off[r + 1] - rt.read_off[r]);
+                        const RegionDesc rd = rt.rdesc[inst / n_init];
+                        tbl = rt.sq + rd.g0;
+                        L = rd.L;
+                        double Mr = (double)rd.M;
 #pragma unroll
                         for (int i = 0; i < 3; ++i) {
                             CS(C_T + i) = st.ES[i * NI + inst] / Mr;
@@ -1322,9 +1331,9 @@ int pack_regions(cpn_ctx* ctx, PackedRegions& pk, bool on_device, bool with_read
         // tables first, raw emissions last: they sit on top of the workspace stack and are popped once packed
         std::vector<RegionDesc> h_desc(R);
         for (int64_t r = 0; r < R; ++r) {
-            h_desc[r].g0 = pk.h_grp_off[r]; h_desc[r].ew_off = h_ew[r];
+            h_desc[r].g0 = pk.h_grp_off[r]; h_desc[r].ew_off = h_ew[r]; h_desc[r].rb_off = h_rb[r];
             h_desc[r].L = (int32_t)(pk.h_grp_off[r + 1] - pk.h_grp_off[r]); h_desc[r].M = (int32_t)(pk.h_read_off[r + 1] - pk.h_read_off[r]);
-            h_desc[r].pad = 0;
+            h_desc[r].ridx = -1; h_desc[r].pad = 0;
         }
         CPN_CUDA(ctx, pk.read_off.bind(read_off, R + 1, offs_dev, s));
         CPN_CUDA(ctx, pk.obs_off.upload(h_obs.data(), R + 1, s));
@@ -1381,15 +1390,20 @@ struct StagedBatch {
     CpnArena* arena = nullptr;   // workspace the tables live in (reset by whoever hands it out)
     PackedRegions pk;
     DevIn<double> phi0;
+    // optional views (two-sample permutation refits): the EM runs over V views of the staged regions instead of the regions
+    int64_t V = 0;
+    DevBuf<RegionDesc> vdesc;    // [V]
+    DevBuf<int32_t> ridx;        // read-id rows
+    std::vector<int32_t> h_vL;   // chain length per view (ordering)
 };
 
 int fit_stage(cpn_ctx* ctx, StagedBatch& sb, bool on_device, int64_t R, const int64_t* grp_off, const double* Nl, const double* rho_l,
               const double* d_l, const int64_t* read_off, const double* lu, const double* lm, const double* phi0, int32_t n_init,
-              int offs_mode = -1) {
+              int offs_mode = -1, int64_t n_units = -1 /*EM units the starts are for; default: the R regions*/) {
     CPN_CUDA(ctx, cudaSetDevice(ctx->device));
     CpnArenaScope scope(sb.arena);
     // ϕ0 first: the raw emissions must stay on top of the workspace stack
-    CPN_CUDA(ctx, sb.phi0.bind(phi0, R * n_init * 3, on_device, ctx->stream));
+    CPN_CUDA(ctx, sb.phi0.bind(phi0, (n_units < 0 ? R : n_units) * n_init * 3, on_device, ctx->stream));
     return pack_regions(ctx, sb.pk, on_device, true, R, grp_off, Nl, rho_l, d_l, read_off, lu, lm, offs_mode);
 }
 
@@ -1423,7 +1437,13 @@ int fit_impl(cpn_ctx* ctx, bool on_device, int64_t R, const int64_t* grp_off, co
         PackedRegions& pk = sb->pk;
         DevIn<double>& d_phi0 = sb->phi0;
         CpnArenaScope scope(&ctx->arena);
-        const int64_t NI = R * n_init;
+        // EM units: the staged regions, or views of them
+        const bool views = sb->V > 0;
+        CPN_ARG(ctx, !(views && sa), "summaries of views are computed by the caller");
+        const int64_t U = views ? sb->V : R;
+        RegionTables rt = pk.rt;
+        if (views) { rt.rdesc = sb->vdesc.p; rt.ridx = sb->ridx.p; }
+        const int64_t NI = U * n_init;
         DevBuf<double> phi, ES, Qs;
         DevBuf<int> iter, stat, c_em, c_sol, c_ev, items_a, items_b, order;
         CPN_CUDA(ctx, phi.alloc(3 * NI, s)); CPN_CUDA(ctx, ES.alloc(3 * NI, s)); CPN_CUDA(ctx, Qs.alloc(NI, s));
@@ -1443,20 +1463,21 @@ int fit_impl(cpn_ctx* ctx, bool on_device, int64_t R, const int64_t* grp_off, co
         if (ws_blocks_per_sm < 1) ws_blocks_per_sm = 1;
         // Regions ordered by group count (counting sort) so the 32 lanes of an M-step warp walk chains of
         // similar length.
-        std::vector<int> h_order(R);
+        std::vector<int> h_order(U);
         {
+            auto len = [&](int64_t u) -> int64_t { return views ? sb->h_vL[u] : pk.h_grp_off[u + 1] - pk.h_grp_off[u]; };
             int64_t Lmax = 0;
-            for (int64_t r = 0; r < R; ++r) Lmax = std::max(Lmax, pk.h_grp_off[r + 1] - pk.h_grp_off[r]);
+            for (int64_t u = 0; u < U; ++u) Lmax = std::max(Lmax, len(u));
             std::vector<int64_t> cnt(Lmax + 2, 0);
-            for (int64_t r = 0; r < R; ++r) cnt[pk.h_grp_off[r + 1] - pk.h_grp_off[r] + 1]++;
+            for (int64_t u = 0; u < U; ++u) cnt[len(u) + 1]++;
             for (int64_t l = 0; l <= Lmax; ++l) cnt[l + 1] += cnt[l];
             const bool desc = env_int("CPN_ORDER_DESC", 1) != 0;
-            for (int64_t r = 0; r < R; ++r) {
-                int64_t pos = cnt[pk.h_grp_off[r + 1] - pk.h_grp_off[r]]++;
-                h_order[desc ? R - 1 - pos : pos] = (int)r;     // longest chains first: the kernels' tails are made of short ones
+            for (int64_t u = 0; u < U; ++u) {
+                int64_t pos = cnt[len(u)]++;
+                h_order[desc ? U - 1 - pos : pos] = (int)u;     // longest chains first: the kernels' tails are made of short ones
             }
         }
-        CPN_CUDA(ctx, order.upload(h_order.data(), R, s));
+        CPN_CUDA(ctx, order.upload(h_order.data(), U, s));
         DevBuf<double> gh;
         DevBuf<unsigned char> gh_valid;
         CPN_CUDA(ctx, gh.alloc(9 * NI, s));
@@ -1492,20 +1513,20 @@ int fit_impl(cpn_ctx* ctx, bool on_device, int64_t R, const int64_t* grp_off, co
             int* queue = counts.p + 2 * it + 1;
             int* n_out = counts.p + 2 * (it + 1);
             { KTimer kt(ctx, CPN_K_PREP);
-              k_make_desc<<<blocks_for(ub, 256), 256, 0, s>>>(ub, cur, n_init, pk.rt.rdesc, phi.p, NI, idesc.p, phil.p, NI, n_dev); }
+              k_make_desc<<<blocks_for(ub, 256), 256, 0, s>>>(ub, cur, n_init, rt.rdesc, phi.p, NI, idesc.p, phil.p, NI, n_dev); }
             { KTimer kt(ctx, CPN_K_ESTEP);
-              k_estep<<<blocks_for(ub, E_WARPS), E_WARPS * 32, 0, s>>>(ub, idesc.p, phil.p, NI, pk.rt, NI, ES.p, n_dev); }
+              k_estep<<<blocks_for(ub, E_WARPS), E_WARPS * 32, 0, s>>>(ub, idesc.p, phil.p, NI, rt, NI, ES.p, n_dev); }
             if (mstep_mode == CPN_MSTEP_ANALYTIC) {
                 unsigned grid = std::min<unsigned>(blocks_for(ub, M_THREADS), (unsigned)(ctx->sm_count * ws_blocks_per_sm));
                 { KTimer kt(ctx, CPN_K_MSTEP);
-                  k_mstep_ws<<<grid, M_THREADS, 0, s>>>(ub, cur, n_init, pk.rt, st, max_em_iters, amax, bmax, cmax, queue, alive.p, n_dev); }
+                  k_mstep_ws<<<grid, M_THREADS, 0, s>>>(ub, cur, n_init, rt, st, max_em_iters, amax, bmax, cmax, queue, alive.p, n_dev); }
                 int nblk = (ub + CP_TILE - 1) / CP_TILE;
                 { KTimer kt(ctx, CPN_K_PREP); k_compact_count<<<nblk, CP_THREADS, 0, s>>>(ub, alive.p, blk_cnt.p, n_dev); }
                 { KTimer kt(ctx, CPN_K_PREP); k_compact_scan<<<1, 1024, 0, s>>>(nblk, blk_cnt.p, n_out); }
                 { KTimer kt(ctx, CPN_K_PREP); k_compact_scatter<<<nblk, CP_THREADS, 0, s>>>(ub, alive.p, cur, blk_cnt.p, nxt, n_dev); }
             } else {
                 KTimer kt(ctx, CPN_K_MSTEP);
-                k_mstep<<<blocks_for(ub, M_THREADS), M_THREADS, 0, s>>>(ub, cur, n_init, pk.rt, st, max_em_iters, amax, bmax, cmax, mstep_mode,
+                k_mstep<<<blocks_for(ub, M_THREADS), M_THREADS, 0, s>>>(ub, cur, n_init, rt, st, max_em_iters, amax, bmax, cmax, mstep_mode,
                                                                          nxt, n_out, n_dev);
             }
             CPN_CUDA(ctx, cudaMemcpyAsync((void*)(ctx->h_counts + it + 1), n_out, sizeof(int), cudaMemcpyDeviceToHost, s));
@@ -1515,18 +1536,18 @@ int fit_impl(cpn_ctx* ctx, bool on_device, int64_t R, const int64_t* grp_off, co
         trace(ctx, "em-done");
         // score converged instances (em_algorithm.jl:344), then pick per region
         { KTimer kt(ctx, CPN_K_SCORE);
-          k_score<<<blocks_for(NI, E_WARPS), E_WARPS * 32, 0, s>>>((int)NI, nullptr, n_init, pk.rt, phi.p, NI, stat.p, 1, Qs.p); }
+          k_score<<<blocks_for(NI, E_WARPS), E_WARPS * 32, 0, s>>>((int)NI, nullptr, n_init, rt, phi.p, NI, stat.p, 1, Qs.p); }
         DevOut<double> o_phi, o_Q, o_ps, o_Qs;
         DevOut<int32_t> o_status;
         DevOut<int64_t> o_cnt;
-        CPN_CUDA(ctx, o_phi.bind(phi_hat, 3 * R, on_device, s));
-        CPN_CUDA(ctx, o_Q.bind(Q, R, on_device, s));
-        CPN_CUDA(ctx, o_status.bind(status, R, on_device, s));
-        CPN_CUDA(ctx, o_cnt.bind(counters, 4 * R, on_device, s));
+        CPN_CUDA(ctx, o_phi.bind(phi_hat, 3 * U, on_device, s));
+        CPN_CUDA(ctx, o_Q.bind(Q, U, on_device, s));
+        CPN_CUDA(ctx, o_status.bind(status, U, on_device, s));
+        CPN_CUDA(ctx, o_cnt.bind(counters, 4 * U, on_device, s));
         if (phi_starts) CPN_CUDA(ctx, o_ps.bind(phi_starts, 3 * NI, on_device, s));
         if (Q_starts) CPN_CUDA(ctx, o_Qs.bind(Q_starts, NI, on_device, s));
         { KTimer kt(ctx, CPN_K_PICK);
-          k_pick<<<blocks_for(R, 128), 128, 0, s>>>(R, n_init, st, Qs.p, o_phi.p, o_Q.p, o_status.p, o_cnt.p, phi_starts ? o_ps.p : nullptr,
+          k_pick<<<blocks_for(U, 128), 128, 0, s>>>(U, n_init, st, Qs.p, o_phi.p, o_Q.p, o_status.p, o_cnt.p, phi_starts ? o_ps.p : nullptr,
                                                     Q_starts ? o_Qs.p : nullptr); }
         CPN_CUDA(ctx, cudaGetLastError());
         CPN_CUDA(ctx, o_phi.finish(s)); CPN_CUDA(ctx, o_Q.finish(s)); CPN_CUDA(ctx, o_status.finish(s)); CPN_CUDA(ctx, o_cnt.finish(s));
@@ -1572,11 +1593,32 @@ int fit_impl(cpn_ctx* ctx, bool on_device, int64_t R, const int64_t* grp_off, co
         }
     }
     trace(ctx, "end");
-    float ms = 0;
-    CPN_CUDA(ctx, cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1));
-    ctx->last_ms = ms;
+    if (!pre) {
+        float ms = 0;
+        CPN_CUDA(ctx, cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1));
+        ctx->last_ms = ms;
+    }
     if (ctx->profile) cpn_profile_collect(ctx);
     return CPN_OK;
+}
+
+
+// Null statistics of the two-sample test (two_samp_perm_tests.jl:65-86): for permutation i (models 2i and 2i+1) and
+// sub-region k: Tmml = mml1 − mml2, Tnme = nme1 − nme2, Tcmd; all NaN when either refit found no optimum.
+__global__ void k_two_samp_T(int64_t P, const int64_t* __restrict__ k_off /*[2P+1] per model*/, const int64_t* __restrict__ cmd_off /*[P+1]*/,
+                             const double* __restrict__ mml, const double* __restrict__ nme, const double* __restrict__ cmd,
+                             const int32_t* __restrict__ status, double* __restrict__ T) {
+    int64_t i = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5;
+    int lane = threadIdx.x & 31;
+    if (i >= P) return;
+    const int64_t c0 = cmd_off[i], K = cmd_off[i + 1] - c0, ka = k_off[2 * i], kb = k_off[2 * i + 1];
+    const bool bad = status[2 * i] < 0 || status[2 * i + 1] < 0;
+    const double nan = __longlong_as_double(0x7ff8000000000000LL);
+    for (int64_t k = lane; k < K; k += 32) {
+        T[3 * c0 + k] = bad ? nan : mml[ka + k] - mml[kb + k];
+        T[3 * c0 + K + k] = bad ? nan : nme[ka + k] - nme[kb + k];
+        T[3 * c0 + 2 * K + k] = bad ? nan : cmd[c0 + k];
+    }
 }
 
 }  // namespace
@@ -1877,7 +1919,6 @@ int cpn_estep_batch(cpn_ctx* ctx, int64_t R, const int64_t* grp_off, const doubl
         CPN_CUDA(ctx, cudaEventRecord(ctx->ev1, s));
         CPN_CUDA(ctx, cudaStreamSynchronize(s));
     }
-    trace(ctx, "end");
     float ms = 0;
     CPN_CUDA(ctx, cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1));
     ctx->last_ms = ms;
@@ -1914,7 +1955,129 @@ int cpn_mstep_batch(cpn_ctx* ctx, int64_t R, const int64_t* grp_off, const doubl
         CPN_CUDA(ctx, cudaEventRecord(ctx->ev1, s));
         CPN_CUDA(ctx, cudaStreamSynchronize(s));
     }
-    trace(ctx, "end");
+    float ms = 0;
+    CPN_CUDA(ctx, cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1));
+    ctx->last_ms = ms;
+    if (ctx->profile) cpn_profile_collect(ctx);
+    return CPN_OK;
+}
+
+int cpn_two_samp_null_batch(cpn_ctx* ctx, int64_t R, const int64_t* grp_off, const double* Nl, const double* rho_l, const double* d_l,
+                            const int64_t* read_off, const double* log_pyx_u, const double* log_pyx_m, const int64_t* perm_off,
+                            const int64_t* n1, const int32_t* perm_ids, const double* phi0, int32_t n_init, int32_t max_em_iters,
+                            double amax, double bmax, double cmax, int32_t mstep_mode, const int64_t* cpg_off, const double* rho_n,
+                            const double* d_n, const int64_t* sub_off, const int64_t* sub_p, const int64_t* sub_q, double* T_null,
+                            int32_t* fit_status) {
+    if (!ctx) return CPN_ERR_ARG;
+    CPN_ARG(ctx, R >= 0 && n_init >= 1 && max_em_iters >= 1, "R >= 0, n_init >= 1, max_em_iters >= 1");
+    CPN_ARG(ctx, grp_off && Nl && rho_l && d_l && read_off && log_pyx_u && log_pyx_m && perm_off && n1 && perm_ids && phi0, "null pointer");
+    CPN_ARG(ctx, cpg_off && rho_n && d_n && sub_off && sub_p && sub_q && T_null, "null pointer");
+    CPN_CUDA(ctx, cudaSetDevice(ctx->device));
+    ctx->last_launches = 0;
+    if (R == 0 || perm_off[R] == 0) { ctx->last_ms = 0; return CPN_OK; }
+    cudaStream_t s = ctx->stream;
+    const int64_t Pt = perm_off[R], V = 2 * Pt;
+    CPN_ARG(ctx, V * (int64_t)n_init < (int64_t)2147483647, "2·ΣP·n_init must fit in int32");
+    // ---- host: the views.  View 2i is sample 1 of permutation i (the reads perm_ids names), view 2i+1 the rest, in order
+    // (deleteat!, two_samp_perm_tests.jl:57-59).  Row layout of ridx: 32 read ids per chunk, padding lanes point at read 0.
+    std::vector<RegionDesc> vd(V);
+    std::vector<int32_t> ridx;
+    std::vector<int64_t> reg_of(V), ex_off(V + 1), k_off(V + 1), cmd_off(Pt + 1), pa(Pt), pb(Pt);
+    std::vector<int64_t> h_ew(R + 1), h_rb(R + 1);
+    h_ew[0] = h_rb[0] = 0;
+    int64_t Nmax = 0;
+    for (int64_t r = 0; r < R; ++r) {
+        const int64_t L = grp_off[r + 1] - grp_off[r], n = read_off[r + 1] - read_off[r], nch = (n + 31) / 32;
+        h_ew[r + 1] = h_ew[r] + nch * L * 32;                      // same arithmetic as pack_regions
+        h_rb[r + 1] = h_rb[r] + nch * 32;
+        CPN_ARG(ctx, n1[r] >= 1 && n1[r] < n, "each sample needs at least one read");
+        CPN_ARG(ctx, cpg_off[r + 1] - cpg_off[r] >= 2, "every region needs N >= 2 CpG sites");
+        Nmax = std::max(Nmax, cpg_off[r + 1] - cpg_off[r]);
+    }
+    ex_off[0] = k_off[0] = cmd_off[0] = 0;
+    {
+        std::vector<char> in1;
+        int64_t ip = 0;                                            // cursor in perm_ids
+        for (int64_t r = 0; r < R; ++r) {
+            const int64_t L = grp_off[r + 1] - grp_off[r], n = read_off[r + 1] - read_off[r], m1 = n1[r], m2 = n - m1;
+            const int64_t N = cpg_off[r + 1] - cpg_off[r], K = sub_off[r + 1] - sub_off[r];
+            in1.assign(n, 0);
+            for (int64_t i = perm_off[r]; i < perm_off[r + 1]; ++i, ip += m1) {
+                std::fill(in1.begin(), in1.end(), 0);
+                int32_t prev = 0;
+                for (int64_t j = 0; j < m1; ++j) {
+                    int32_t id = perm_ids[ip + j];
+                    CPN_ARG(ctx, id > prev && id <= n, "perm_ids must be ascending 1-based read indices");
+                    prev = id; in1[id - 1] = 1;
+                }
+                for (int h = 0; h < 2; ++h) {
+                    const int64_t v = 2 * i + h, mv = h ? m2 : m1, rows = (mv + 31) / 32;
+                    RegionDesc& d = vd[v];
+                    d.g0 = grp_off[r]; d.ew_off = h_ew[r]; d.rb_off = h_rb[r]; d.L = (int32_t)L; d.M = (int32_t)mv;
+                    d.ridx = (int32_t)(ridx.size() / 32); d.pad = 0;
+                    size_t base = ridx.size();
+                    ridx.resize(base + rows * 32, 0);
+                    int64_t c = 0;
+                    if (h == 0) for (int64_t j = 0; j < m1; ++j) ridx[base + c++] = perm_ids[ip + j] - 1;
+                    else for (int64_t q = 0; q < n; ++q) if (!in1[q]) ridx[base + c++] = (int32_t)q;
+                    reg_of[v] = r; ex_off[v + 1] = ex_off[v] + N; k_off[v + 1] = k_off[v] + K;
+                }
+                pa[i] = 2 * i; pb[i] = 2 * i + 1; cmd_off[i + 1] = cmd_off[i] + K;
+            }
+        }
+    }
+    CPN_CUDA(ctx, cudaEventRecord(ctx->ev0, s));
+    int rc = CPN_OK;
+    {
+        CPN_CUDA(ctx, ctx->stage_arena.reset());
+        StagedBatch sb;
+        sb.arena = &ctx->stage_arena;
+        rc = fit_stage(ctx, sb, false, R, grp_off, Nl, rho_l, d_l, read_off, log_pyx_u, log_pyx_m, phi0, n_init, -1, V);
+        if (rc) return rc;
+        const int64_t sumN = cpg_off[R], sumK = sub_off[R], sK = k_off[V], sN = ex_off[V];
+        DevBuf<int64_t> d_reg, d_exo, d_ko, d_co, d_pa, d_pb, d_cpg, d_so, d_sp, d_sq;
+        DevBuf<double> d_rho, d_dn, d_phi, d_Q, logZ, ex, exx, lg, e1, e2, mml, nme, cmd, T;
+        DevBuf<int32_t> d_stat;
+        {
+            CpnArenaScope scope(&ctx->stage_arena);
+            sb.V = V;
+            sb.h_vL.resize(V);
+            for (int64_t v = 0; v < V; ++v) sb.h_vL[v] = vd[v].L;
+            CPN_CUDA(ctx, sb.vdesc.upload(vd.data(), V, s));
+            CPN_CUDA(ctx, sb.ridx.upload(ridx.data(), ridx.size(), s));
+            CPN_CUDA(ctx, d_reg.upload(reg_of.data(), V, s)); CPN_CUDA(ctx, d_exo.upload(ex_off.data(), V + 1, s));
+            CPN_CUDA(ctx, d_ko.upload(k_off.data(), V + 1, s)); CPN_CUDA(ctx, d_co.upload(cmd_off.data(), Pt + 1, s));
+            CPN_CUDA(ctx, d_pa.upload(pa.data(), Pt, s)); CPN_CUDA(ctx, d_pb.upload(pb.data(), Pt, s));
+            CPN_CUDA(ctx, d_cpg.upload(cpg_off, R + 1, s)); CPN_CUDA(ctx, d_so.upload(sub_off, R + 1, s));
+            CPN_CUDA(ctx, d_sp.upload(sub_p, sumK, s)); CPN_CUDA(ctx, d_sq.upload(sub_q, sumK, s));
+            CPN_CUDA(ctx, d_rho.upload(rho_n, sumN, s)); CPN_CUDA(ctx, d_dn.upload(d_n, sumN - R, s));
+            CPN_CUDA(ctx, d_phi.alloc(3 * V, s)); CPN_CUDA(ctx, d_Q.alloc(V, s)); CPN_CUDA(ctx, d_stat.alloc(V, s));
+            CPN_CUDA(ctx, logZ.alloc(V, s)); CPN_CUDA(ctx, ex.alloc(sN, s)); CPN_CUDA(ctx, exx.alloc(sN - V, s)); CPN_CUDA(ctx, lg.alloc(4 * sK, s));
+            CPN_CUDA(ctx, e1.alloc(sK, s)); CPN_CUDA(ctx, e2.alloc(sK, s)); CPN_CUDA(ctx, mml.alloc(sK, s)); CPN_CUDA(ctx, nme.alloc(sK, s));
+            CPN_CUDA(ctx, cmd.alloc(cmd_off[Pt], s)); CPN_CUDA(ctx, T.alloc(3 * cmd_off[Pt], s));
+            CPN_CUDA(ctx, cudaStreamSynchronize(s));               // the host staging vectors may go
+        }
+        // 2·ΣP multi-start EM fits over the views; results stay on the device
+        const int64_t keep_launches = ctx->last_launches;
+        rc = fit_impl(ctx, true, R, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, n_init, max_em_iters, amax, bmax, cmax,
+                      mstep_mode, d_phi.p, d_Q.p, d_stat.p, nullptr, nullptr, nullptr, nullptr, &sb);
+        if (rc) return rc;
+        ctx->last_launches += keep_launches;
+        // per-CpG summaries of every refit, CMD of the two halves of every permutation, then the three statistics
+        rc = cpn_stat_sums_launch(ctx, V, d_phi.p, d_reg.p, d_exo.p, d_ko.p, d_cpg.p, d_rho.p, d_dn.p, d_so.p, d_sp.p, d_sq.p, Nmax, logZ.p, ex.p,
+                                  exx.p, lg.p, e1.p, e2.p, mml.p, nme.p);
+        if (rc) return rc;
+        rc = cpn_cmd_launch(ctx, Pt, d_pa.p, d_pb.p, d_phi.p, d_reg.p, d_exo.p, ex.p, exx.p, d_ko.p, nme.p, d_cpg.p, d_rho.p, d_dn.p, d_so.p, d_sp.p,
+                            d_sq.p, Nmax, d_co.p, cmd.p);
+        if (rc) return rc;
+        { KTimer kt(ctx, CPN_K_SWEEP);
+          k_two_samp_T<<<blocks_for(Pt * 32, 256), 256, 0, s>>>(Pt, d_ko.p, d_co.p, mml.p, nme.p, cmd.p, d_stat.p, T.p); }
+        CPN_CUDA(ctx, cudaGetLastError());
+        CPN_CUDA(ctx, T.download(T_null, 3 * cmd_off[Pt], s));
+        if (fit_status) CPN_CUDA(ctx, d_stat.download(fit_status, V, s));
+        CPN_CUDA(ctx, cudaEventRecord(ctx->ev1, s));
+        CPN_CUDA(ctx, cudaStreamSynchronize(s));
+    }
     float ms = 0;
     CPN_CUDA(ctx, cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1));
     ctx->last_ms = ms;
@@ -1923,3 +2086,4 @@ int cpn_mstep_batch(cpn_ctx* ctx, int64_t R, const int64_t* grp_off, const doubl
 }
 
 }  // extern "C"
+

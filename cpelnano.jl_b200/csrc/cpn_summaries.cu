@@ -334,6 +334,24 @@ int cpn_stat_sums_launch(cpn_ctx* ctx, int64_t T, const double* phi, const int64
     return CPN_OK;
 }
 
+int cpn_cmd_launch(cpn_ctx* ctx, int64_t P, const int64_t* pair_a, const int64_t* pair_b, const double* phi_tbl, const int64_t* reg_of,
+                   const int64_t* ex_off, const double* ex_tbl, const double* exx_tbl, const int64_t* nme_off, const double* nme_tbl,
+                   const int64_t* cpg_off, const double* rho_n, const double* d_n, const int64_t* sub_off, const int64_t* sub_p,
+                   const int64_t* sub_q, int64_t Nmax, const int64_t* cmd_off, double* cmd) {
+    int stride = (int)((Nmax + 1) | 1);
+    size_t smem = (size_t)S_WARPS * S_ARR * stride * sizeof(double);
+    CPN_ARG(ctx, smem <= 200 * 1024, "region with too many CpG sites for the shared-memory staging (N > ~500)");
+    CPN_CUDA(ctx, cudaFuncSetAttribute(k_cmd, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    {
+        KTimer kt(ctx, CPN_K_CMD);
+        k_cmd<<<blocks_for(P, S_WARPS), S_WARPS * 32, smem, ctx->stream>>>(P, stride, pair_a, pair_b, phi_tbl, reg_of, ex_off, ex_tbl, exx_tbl,
+                                                                            nme_off, nme_tbl, cpg_off, rho_n, d_n, sub_off, sub_p, sub_q, cmd_off,
+                                                                            cmd);
+    }
+    CPN_CUDA(ctx, cudaGetLastError());
+    return CPN_OK;
+}
+
 extern "C" {
 
 int cpn_stat_sums_batch(cpn_ctx* ctx, int64_t T, const double* phi, const int64_t* reg_of, const int64_t* ex_off, const int64_t* k_off,

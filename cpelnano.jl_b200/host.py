@@ -285,41 +285,92 @@ class Engine:
         perms [P, n1]: ascending 1-based indices into vcat(calls_s1, calls_s2) that form sample 1; the rest, in order, is
         sample 2.  Every (permutation, half) becomes one row of a CSR batch: 2P multi-start EM fits, 2P summaries, P CMDs.
         phi0s [P, 2, max_em_init, 3] replaces the 2P gen_ϕ0s draws.  Returns T_null [P, 3, K] (NaN where a fit failed)."""
-        perms = np.asarray(perms, dtype=np.int64)
-        P, n1 = perms.shape
-        lu = np.concatenate([calls_s1[0], calls_s2[0]]); lm = np.concatenate([calls_s1[1], calls_s2[1]])
-        n, L = lu.shape
-        n2 = n - n1
-        mask = np.ones((P, n), dtype=bool)
-        mask[np.arange(P)[:, None], perms - 1] = False
-        rest = np.nonzero(mask)[1].reshape(P, n2)                          # deleteat!(aux_calls, perm_ids): the rest, in order
-        order = np.concatenate([perms - 1, rest], axis=1)                  # [P, n]: rows of half 1 then rows of half 2
-        lu_b = lu[order].reshape(-1); lm_b = lm[order].reshape(-1)
-        R2 = 2 * P
-        grp_off = (np.arange(R2 + 1) * L).astype(np.int64)
-        Nl = np.tile(np.asarray(rs_ref.Nl, dtype=np.float64), R2); rho_l = np.tile(np.asarray(rs_ref.rho_l, dtype=np.float64), R2)
-        d_l = np.tile(np.asarray(rs_ref.dl, dtype=np.float64), R2)
-        reads = np.tile(np.array([n1, n2], dtype=np.int64), P)
-        read_off = np.concatenate([[0], np.cumsum(reads)]).astype(np.int64)
+        return self.two_samp_null_stats_regions([(rs_ref, calls_s1, calls_s2, perms)], config, None if phi0s is None else [phi0s], rng)[0]
+
+    def two_samp_null_stats_regions(self, items, config, phi0s=None, rng=None):
+        """The same for several regions in ONE device batch (the pmap over regions of two_samp_perm_tests.jl:220): items is a
+        list of (rs_ref, calls_s1, calls_s2, perms); row order = region, permutation, half.  A region contributes only
+        2·P fits, which alone cannot fill a B200 — batching regions is what brings the throughput of the EM kernels.
+        Returns one T_null [P_r, 3, K_r] per region."""
+        lus, lms, Nls, rhos, dls, reads, grp_len, reg_rows = [], [], [], [], [], [], [], []
+        for (rs_ref, calls_s1, calls_s2, perms) in items:
+            perms = np.asarray(perms, dtype=np.int64)
+            P, n1 = perms.shape
+            lu = np.concatenate([calls_s1[0], calls_s2[0]]); lm = np.concatenate([calls_s1[1], calls_s2[1]])
+            n, L = lu.shape
+            n2 = n - n1
+            mask = np.ones((P, n), dtype=bool)
+            mask[np.arange(P)[:, None], perms - 1] = False
+            rest = np.nonzero(mask)[1].reshape(P, n2)                      # deleteat!(aux_calls, perm_ids): the rest, in order
+            order = np.concatenate([perms - 1, rest], axis=1)              # [P, n]: rows of half 1 then rows of half 2
+            lus.append(lu[order].reshape(-1)); lms.append(lm[order].reshape(-1))
+            R2 = 2 * P
+            Nls.append(np.tile(np.asarray(rs_ref.Nl, dtype=np.float64), R2)); rhos.append(np.tile(np.asarray(rs_ref.rho_l, dtype=np.float64), R2))
+            dls.append(np.tile(np.asarray(rs_ref.dl, dtype=np.float64), R2))
+            reads.append(np.tile(np.array([n1, n2], dtype=np.int64), P))
+            grp_len.append(np.full(R2, L, dtype=np.int64))
+            reg_rows.append(R2)
+        rows = int(sum(reg_rows))
+        grp_off = np.concatenate([[0], np.cumsum(np.concatenate(grp_len))]).astype(np.int64)
+        read_off = np.concatenate([[0], np.cumsum(np.concatenate(reads))]).astype(np.int64)
         if phi0s is None:
             from .simulations import gen_phi0s
-            phi0s = gen_phi0s(rng or np.random.default_rng(), R2, config.max_em_init)
-        fit = self.lib.fit_batch(grp_off, Nl, rho_l, d_l, read_off, lu_b, lm_b, np.asarray(phi0s).reshape(R2, config.max_em_init, 3),
-                                 config.max_em_init, config.max_em_iters, (AMAX, BMAX, CMAX), config.mstep_mode, device=self.device)
-        K = rs_ref.nls_rgs.num
-        N = rs_ref.N
-        cpg_off = np.array([0, N], dtype=np.int64); sub_off = np.array([0, K], dtype=np.int64)
-        ss = self.lib.stat_sums_batch(fit["phi_hat"], cpg_off, rs_ref.rho_n, rs_ref.dn, sub_off, rs_ref.nls_rgs.cpg_p, rs_ref.nls_rgs.cpg_q,
-                                      reg_of=np.zeros(R2, dtype=np.int64), device=self.device)
-        pa = np.arange(0, R2, 2, dtype=np.int64)
-        cmd, _ = self.lib.cmd_batch(pa, pa + 1, fit["phi_hat"], np.zeros(R2, dtype=np.int64), ss["ex_off"], ss["ex"], ss["exx"], ss["k_off"],
-                                    ss["nme"], cpg_off, rs_ref.rho_n, rs_ref.dn, sub_off, rs_ref.nls_rgs.cpg_p, rs_ref.nls_rgs.cpg_q,
-                                    device=self.device)
-        mml = ss["mml"].reshape(P, 2, K); nme = ss["nme"].reshape(P, 2, K)
-        T = np.stack([mml[:, 0] - mml[:, 1], nme[:, 0] - nme[:, 1], cmd.reshape(P, K)], axis=1)
-        bad = (fit["pick"].reshape(P, 2) < 0).any(axis=1)                 # either ϕ̂ empty → all three statistics NaN (:65)
-        T[bad] = np.nan
-        return T
+            phi0 = gen_phi0s(rng or np.random.default_rng(), rows, config.max_em_init)
+        else:
+            phi0 = np.concatenate([np.asarray(p).reshape(-1, config.max_em_init, 3) for p in phi0s])
+        fit = self.lib.fit_batch(grp_off, np.concatenate(Nls), np.concatenate(rhos), np.concatenate(dls), read_off, np.concatenate(lus),
+                                 np.concatenate(lms), phi0.reshape(rows, config.max_em_init, 3), config.max_em_init, config.max_em_iters,
+                                 (AMAX, BMAX, CMAX), config.mstep_mode, device=self.device)
+        refs = [it[0] for it in items]
+        cpg_off, rho_n, d_n, sub_off, sub_p, sub_q = self.pack_cpgs(refs)
+        reg_of = np.repeat(np.arange(len(items), dtype=np.int64), reg_rows)
+        ss = self.lib.stat_sums_batch(fit["phi_hat"], cpg_off, rho_n, d_n, sub_off, sub_p, sub_q, reg_of=reg_of, device=self.device)
+        pa = np.arange(0, rows, 2, dtype=np.int64)
+        cmd, cmd_off = self.lib.cmd_batch(pa, pa + 1, fit["phi_hat"], reg_of, ss["ex_off"], ss["ex"], ss["exx"], ss["k_off"], ss["nme"], cpg_off,
+                                          rho_n, d_n, sub_off, sub_p, sub_q, device=self.device)
+        out, row0, pair0 = [], 0, 0
+        for i, (rs_ref, _, _, perms) in enumerate(items):
+            P, K = len(perms), rs_ref.nls_rgs.num
+            k0 = ss["k_off"][row0]
+            mml = ss["mml"][k0:k0 + 2 * P * K].reshape(P, 2, K); nme = ss["nme"][k0:k0 + 2 * P * K].reshape(P, 2, K)
+            c0 = cmd_off[pair0]
+            T = np.stack([mml[:, 0] - mml[:, 1], nme[:, 0] - nme[:, 1], cmd[c0:c0 + P * K].reshape(P, K)], axis=1)
+            bad = (fit["pick"][row0:row0 + 2 * P].reshape(P, 2) < 0).any(axis=1)     # either ϕ̂ empty → all three statistics NaN (:65)
+            T[bad] = np.nan
+            out.append(T)
+            row0 += 2 * P; pair0 += P
+        return out
+
+    def two_samp_null_stats_device(self, items, config, phi0s=None, rng=None):
+        """Same contract as two_samp_null_stats_regions through cpn_two_samp_null_batch: the pooled reads of each region are
+        uploaded once and the 2·P refits are views of them (no per-permutation copies on the host or over PCIe); summaries,
+        CMD and the three statistics stay on the device.  Bit-identical to the materialised path."""
+        refs = [it[0] for it in items]
+        grp_off = np.concatenate([[0], np.cumsum([len(r.Nl) for r in refs])]).astype(np.int64)
+        Nl = np.concatenate([np.asarray(r.Nl, dtype=np.float64) for r in refs]); rho_l = np.concatenate([np.asarray(r.rho_l, dtype=np.float64) for r in refs])
+        d_l = np.concatenate([np.asarray(r.dl, dtype=np.float64) for r in refs])
+        lu = np.concatenate([np.concatenate([it[1][0], it[2][0]]).reshape(-1) for it in items])
+        lm = np.concatenate([np.concatenate([it[1][1], it[2][1]]).reshape(-1) for it in items])
+        read_off = np.concatenate([[0], np.cumsum([it[1][0].shape[0] + it[2][0].shape[0] for it in items])]).astype(np.int64)
+        perms = [np.asarray(it[3], dtype=np.int32) for it in items]
+        perm_off = np.concatenate([[0], np.cumsum([p.shape[0] for p in perms])]).astype(np.int64)
+        n1 = np.array([p.shape[1] for p in perms], dtype=np.int64)
+        rows = 2 * int(perm_off[-1])
+        if phi0s is None:
+            from .simulations import gen_phi0s
+            phi0 = gen_phi0s(rng or np.random.default_rng(), rows, config.max_em_init)
+        else:
+            phi0 = np.concatenate([np.asarray(p).reshape(-1, config.max_em_init, 3) for p in phi0s])
+        cpg_off, rho_n, d_n, sub_off, sub_p, sub_q = self.pack_cpgs(refs)
+        T, status = self.lib.two_samp_null_batch(grp_off, Nl, rho_l, d_l, read_off, lu, lm, perm_off, n1, np.concatenate([p.reshape(-1) for p in perms]),
+                                                 phi0, config.max_em_init, cpg_off, rho_n, d_n, sub_off, sub_p, sub_q, config.max_em_iters,
+                                                 (AMAX, BMAX, CMAX), config.mstep_mode, device=self.device)
+        out, t0 = [], 0
+        for r, p in zip(refs, perms):
+            n = p.shape[0] * 3 * r.nls_rgs.num
+            out.append(T[t0:t0 + n].reshape(p.shape[0], 3, r.nls_rgs.num))
+            t0 += n
+        return out
 
     def diff_two_samp_comp_region(self, mod_s1, mod_s2, calls_s1, calls_s2, config, rng=None, perms=None, phi0s=None):
         """pmap_diff_two_samp_comp (src/two_samp_perm_tests.jl:157-273) for one region: observed statistics from the two fitted
@@ -345,7 +396,7 @@ class Engine:
         import copy
         ref = copy.copy(mod_s1.group_view if mod_s1.group_view is not None else mod_s1)    # "back to group scale" (:198-199)
         ref.nls_rgs, ref.rho_n, ref.dn, ref.N = mod_s1.nls_rgs, mod_s1.rho_n, mod_s1.dn, mod_s1.N
-        T_null = self.two_samp_null_stats_batch(ref, calls_s1, calls_s2, perms, config, phi0s, rng)
+        T_null = self.two_samp_null_stats_device([(ref, calls_s1, calls_s2, perms)], config, None if phi0s is None else [phi0s], rng)[0]
         cnt, nv, p = self.lib.two_samp_pvals(np.array([0, K]), len(perms), T_obs.reshape(-1), T_null.reshape(-1), exact, device=self.device)
         out.update(pval=p.reshape(3, K), cnt=cnt.reshape(3, K), n_valid=nv.reshape(3, K), exact=exact, T_null=T_null)
         return out

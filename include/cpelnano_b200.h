@@ -181,6 +181,26 @@ int cpn_grp_mat_sweep(cpn_ctx* ctx, int64_t R, int32_t n, const int64_t* tbl_off
                       const double* mml1, const double* mml2, const double* nme1, const double* nme2,
                       const int64_t* js, int64_t P, int32_t exact,
                       double* T, int64_t* cnt, double* pval);
+/* two-sample null statistics, all on the device  src/two_samp_perm_tests.jl:41-87 (pmap_two_samp_null_stats) over the
+ * pmap of :220: for every region r and every permutation i of its pooled reads, refit both halves (multi-start EM),
+ * summarise both fits (rscle_grp_mod! + get_stat_sums!) and return Tmml = mml1-mml2, Tnme = nme1-nme2, Tcmd = comp_cmd.
+ * The pooled reads cross PCIe once: the 2*P_r refits of a region are VIEWS of its packed emissions (a read-index row per
+ * lane), so nothing is materialised per permutation.
+ *   grp_off ... log_pyx_m  as in cpn_fit_batch; the reads of region r are vcat(calls_s1, calls_s2) (:54)
+ *   perm_off [R+1]         permutations per region;  n1 [R] reads of sample 1
+ *   perm_ids               for region r, P_r rows of n1[r] ascending 1-based indices into the pooled reads = sample 1 (:57);
+ *                          sample 2 is the rest, in order (deleteat!, :58-59)
+ *   phi0 [sum P_r*2*n_init*3]  EM starts, ordered region, permutation, half, start
+ *   cpg_off ... sub_q      per-CpG tables as in cpn_stat_sums_batch
+ *   T_null [sum_r P_r*3*K_r]   region-major, then permutation, statistic (mml, nme, cmd), sub-region: the layout
+ *                          cpn_two_samp_pvals reads; NaN for a permutation when either refit has no optimum (:65)
+ *   fit_status [sum P_r*2] optional: picked start per refit, -1 = none                                              */
+int cpn_two_samp_null_batch(cpn_ctx* ctx, int64_t R, const int64_t* grp_off, const double* Nl, const double* rho_l,
+                            const double* d_l, const int64_t* read_off, const double* log_pyx_u, const double* log_pyx_m,
+                            const int64_t* perm_off, const int64_t* n1, const int32_t* perm_ids, const double* phi0,
+                            int32_t n_init, int32_t max_em_iters, double amax, double bmax, double cmax, int32_t mstep_mode,
+                            const int64_t* cpg_off, const double* rho_n, const double* d_n, const int64_t* sub_off,
+                            const int64_t* sub_p, const int64_t* sub_q, double* T_null, int32_t* fit_status);
 /* two-sample p-value counting  src/two_samp_perm_tests.jl:230-258: T_obs [ΣK*3] region-major (tmml,tnme,tcmd
  * blocks of K_r), T_null [Σ_r P*3*K_r] permutation-major per region; NaN nulls are dropped, >20 valid needed. */
 int cpn_two_samp_pvals(cpn_ctx* ctx, int64_t R, const int64_t* tbl_off, int64_t P, const double* T_obs,

@@ -478,6 +478,35 @@ def _analyze_device(engine, cpn, nb, phi0, n_init, sub_off, sub_p, sub_q):
     return res
 
 
+def test_two_sample_regions_in_one_batch(engine, cpn):
+    """Several regions' permutations in one device batch (the pmap over regions, two_samp_perm_tests.jl:220) give exactly
+    what one call per region gives; regions differ in L, N, K and read counts.  The device-side path (views of the pooled
+    reads, summaries/CMD/statistics on the device) is bit-identical to the path that materialises every permuted sample."""
+    nb = cpn.simulations.make_nano_batch(3, M=14, seed=78)
+    cfg = cpn.CpelNanoConfig(max_em_init=2)
+    rng = np.random.default_rng(3)
+    items, phi0s = [], []
+    for r in range(nb.R):
+        rg = nb.region(r)
+        n0, n1 = nb.cpg_off[r], nb.cpg_off[r + 1]
+        ref = cpn.RegStruct(chr="c", chrst=int(nb.chrst[r]), chrend=int(nb.chrend[r]), N=int(n1 - n0), L=rg["L"], Nl=rg["Nl"], rho_l=rg["rho_l"],
+                            dl=rg["d_l"], rho_n=nb.rho_n[n0:n1], dn=nb.d_n[n0 - r:n1 - r - 1], cpg_pos=nb.cpg_pos[n0:n1])
+        engine.get_nls_reg_info(ref, cfg)
+        h = 6 + r                                                           # sample 1 has 6, 7, 8 reads
+        P = 5 + 2 * r
+        perms = np.stack([np.sort(rng.choice(np.arange(1, 15), h, replace=False)) for _ in range(P)])
+        items.append((ref, (rg["lu"][:h], rg["lm"][:h]), (rg["lu"][h:], rg["lm"][h:]), perms))
+        phi0s.append(cpn.simulations.gen_phi0s(rng, 2 * P, 2).reshape(P, 2, 2, 3))
+    together = engine.two_samp_null_stats_regions(items, cfg, phi0s=phi0s)
+    device = engine.two_samp_null_stats_device(items, cfg, phi0s=phi0s)      # cpn_two_samp_null_batch: refits are views of the pooled reads
+    for it, p0, T, Td in zip(items, phi0s, together, device):
+        alone = engine.two_samp_null_stats_batch(*it, cfg, phi0s=p0)
+        assert T.shape == (len(it[3]), 3, it[0].nls_rgs.num)
+        assert np.array_equal(T, alone, equal_nan=True)
+        assert np.array_equal(Td, T, equal_nan=True)
+        assert np.isfinite(Td).any()
+
+
 def test_analyze_batch_equals_fit_plus_stat_sums(engine, cpn):
     """cpn_analyze_batch (ϕ̂ stays on the device between the EM kernels and the summaries kernel) is bit-identical to
     cpn_fit_batch followed by cpn_stat_sums_batch, for host and for device pointers; regions without a fit get NaN."""
