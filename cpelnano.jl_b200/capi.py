@@ -14,7 +14,7 @@ MSTEP_FD, MSTEP_ANALYTIC = 0, 1
 # every exported symbol of include/cpelnano_b200.h (tests check the library exports exactly these)
 SYMBOLS = ["cpn_create", "cpn_destroy", "cpn_last_error", "cpn_version", "cpn_last_device_ms", "cpn_last_launches",
            "cpn_measure_fp64_peak", "cpn_set_profile", "cpn_get_profile", "cpn_analyze_batch", "cpn_analyze_batch_device", "cpn_fit_batch", "cpn_fit_batch_device", "cpn_estep_batch", "cpn_mstep_batch",
-           "cpn_stat_sums_batch", "cpn_nls_reg_info", "cpn_cmd_batch", "cpn_grp_unmat_sweep", "cpn_grp_mat_sweep", "cpn_two_samp_pvals", "cpn_two_samp_null_batch"]
+           "cpn_stat_sums_batch", "cpn_nls_reg_info", "cpn_cmd_batch", "cpn_grp_unmat_sweep", "cpn_grp_mat_sweep", "cpn_two_samp_pvals", "cpn_two_samp_null_batch", "cpn_grp_test_batch"]
 
 
 class CpnError(RuntimeError):
@@ -272,6 +272,23 @@ class Library:
                                         C.c_int64(len(js)), C.c_int32(int(exact)), _ptr(T), _ptr(cnt), _ptr(p))
         self._check(rc, ctx)
         return T, cnt, p
+
+    def grp_test_batch(self, n1, n2, matched, phi, cpg_off, rho_n, d_n, sub_off, sub_p, sub_q, labelings, exact, device=0):
+        """cpn_grp_test_batch: phi [R, S, 3] → unmatched (T, cnt, p) [ΣK·3]; matched (T, cnt, p) [ΣK·2] and tcmd [ΣK]."""
+        phi, rho_n, d_n = _f64(phi), _f64(rho_n), _f64(d_n)
+        cpg_off, sub_off, sub_p, sub_q = _i64(cpg_off), _i64(sub_off), _i64(sub_p), _i64(sub_q)
+        labelings = _i64(labelings) if matched else _i32(labelings)
+        R, sK = len(cpg_off) - 1, int(sub_off[-1])
+        P = len(labelings) if matched else (labelings.shape[0] if labelings.ndim == 2 else labelings.size // max(n1, 1))
+        ns = 2 if matched else 3
+        T, p, cnt = np.empty(ns * sK), np.empty(ns * sK), np.empty(ns * sK, dtype=np.int64)
+        tcmd = np.empty(sK)
+        ctx = self.ctx(device)
+        rc = self.dll.cpn_grp_test_batch(ctx, C.c_int64(R), C.c_int32(n1), C.c_int32(n2), C.c_int32(int(matched)), _ptr(phi), _ptr(cpg_off),
+                                         _ptr(rho_n), _ptr(d_n), _ptr(sub_off), _ptr(sub_p), _ptr(sub_q), _ptr(labelings), C.c_int64(P),
+                                         C.c_int32(int(exact)), _ptr(T), _ptr(cnt), _ptr(p), _ptr(tcmd))
+        self._check(rc, ctx)
+        return (T, cnt, p, tcmd) if matched else (T, cnt, p)
 
     def two_samp_null_batch(self, grp_off, Nl, rho_l, d_l, read_off, lu, lm, perm_off, n1, perm_ids, phi0, n_init, cpg_off, rho_n, d_n,
                             sub_off, sub_p, sub_q, max_em_iters=20, box=(20.0, 150.0, 50.0), mstep_mode=MSTEP_ANALYTIC, device=0):

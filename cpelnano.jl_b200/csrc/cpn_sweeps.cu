@@ -11,21 +11,35 @@
 // operation of a statistic uses the explicitly rounded intrinsics (__dadd_rn, __ddiv_rn, …) in the
 // reference's accumulation order, so nvcc cannot contract or re-associate them: given bit-identical
 // tables the counts equal the reference's.
+#include <algorithm>
 #include <cmath>
+#include <cstdlib>
+#include <vector>
 
 #include "cpn_common.cuh"
 
 namespace {
 
 constexpr int SW_THREADS = 256;
+inline unsigned blocks_for(int64_t n, int per_block) { return (unsigned)((n + per_block - 1) / per_block); }
 
-// sum(vector of K-vectors)/n with Julia's left-to-right `+` (grp_perm_tests.jl:121-125)
-__device__ __forceinline__ double mean_ids(const double* tab, int K, int k, const int* ids, int n) {
-    double s = tab[(ids[0] - 1) * K + k];
-    for (int i = 1; i < n; ++i) s = __dadd_rn(s, tab[(ids[i] - 1) * K + k]);
-    return __ddiv_rn(s, (double)n);
+// a / n for a small positive integer n, correctly rounded, in three FP64 instructions instead of the ≈ 25 of the generic
+// division: q0 = RN(a·y) with y = RN(1/n), r = a − n·q0 (exact in an FMA), q = RN(q0 + r·y) (Markstein's final correction;
+// checked bit-for-bit against a/n on 4·10⁸ values for every n ≤ 1024).  Outside the range where neither step can
+// underflow or overflow — and for NaN — the generic division runs.
+__device__ __forceinline__ double div_small(double a, double n, double y) {
+    const double aa = fabs(a);
+    if (!(aa >= 1e-290 && aa <= 1e290) && a != 0.0) return __ddiv_rn(a, n);
+    const double q0 = __dmul_rn(a, y);
+    const double r = __fma_rn(-n, q0, a);
+    return __fma_rn(r, y, q0);
 }
 
+// Unmatched sweep.  A thread owns labelings; for each it keeps the group membership as two bit masks and KB sub-regions'
+// worth of running sums in registers, so the index arithmetic of a sample (or pair of samples) is paid once per KB
+// sub-regions and the inner loops are LDS + DADD.  Sums run over ascending sample ids — the order of the reference's id
+// vectors (grp_perm_tests.jl:121-125, :86-107; combinations are ascending, and so is their complement).
+template <int KB>
 __global__ void __launch_bounds__(SW_THREADS) k_unmat_sweep(int n1, int n2, int Kmax, const int64_t* __restrict__ tbl_off,
                                                              const double* __restrict__ mml, const double* __restrict__ nme,
                                                              const double* __restrict__ cmd_tbl, const int32_t* __restrict__ labelings,
@@ -40,7 +54,7 @@ __global__ void __launch_bounds__(SW_THREADS) k_unmat_sweep(int n1, int n2, int 
     double* s_nme = s_mml + S * Kmax;            // [S][K]
     double* s_cmd = s_nme + S * Kmax;            // [S*S][K]
     double* s_T = s_cmd + S * S * Kmax;          // [3][K]
-    int* s_cnt = (int*)(s_T + 3 * Kmax);         // [3][K]
+    int* s_cnt = (int*)(s_T + 3 * Kmax);         // [3][K]  (+ 16 doubles of slack: row tails are read unguarded below)
     for (int i = threadIdx.x; i < S * K; i += blockDim.x) { s_mml[i] = mml[k0 * S + i]; s_nme[i] = nme[k0 * S + i]; }
     for (int i = threadIdx.x; i < S * S * K; i += blockDim.x) s_cmd[i] = cmd_tbl[k0 * S * S + i];
     for (int i = threadIdx.x; i < 3 * K; i += blockDim.x) s_cnt[i] = 0;
@@ -60,28 +74,67 @@ __global__ void __launch_bounds__(SW_THREADS) k_unmat_sweep(int n1, int n2, int 
         s_T[2 * K + k] = __ddiv_rn(acc, (double)(n1 * n2));
     }
     __syncthreads();
-    int g1[32], g2[32];
+    const unsigned long long all = (S >= 64) ? ~0ull : ((1ull << S) - 1ull);
+    const double d1 = (double)n1, d2 = (double)n2, d12 = (double)(n1 * n2);
+    const double y1 = __ddiv_rn(1.0, d1), y2 = __ddiv_rn(1.0, d2), y12 = __ddiv_rn(1.0, d12);
     for (int64_t pi = threadIdx.x; pi < P; pi += blockDim.x) {
         const int32_t* lab = labelings + pi * n1;
-        for (int i = 0; i < n1; ++i) g1[i] = lab[i];
-        int a = 0, c = 0;
-        for (int s = 1; s <= S; ++s) { if (a < n1 && g1[a] == s) ++a; else g2[c++] = s; }
-        for (int k = 0; k < K; ++k) {
-            double tobs = s_T[k];
-            if (tobs != tobs) continue;                                          // isnan(tmml_obs[k]) && continue (:260)
-            double tm = __dsub_rn(mean_ids(s_mml, K, k, g1, n1), mean_ids(s_mml, K, k, g2, n2));
-            double tn = __dsub_rn(mean_ids(s_nme, K, k, g1, n1), mean_ids(s_nme, K, k, g2, n2));
-            double tc = 0.0;                                                     // comp_unmat_perm_stat_cmd :86-107
-            for (int i = 0; i < n1; ++i)
-                for (int j = 0; j < n2; ++j) {
-                    int ii = g1[i] - 1, jj = g2[j] - 1;
-                    int lo = min(ii, jj), hi = max(ii, jj);
-                    tc = __dadd_rn(tc, s_cmd[(lo * S + hi) * K + k]);
+        unsigned long long m1 = 0;
+        for (int i = 0; i < n1; ++i) m1 |= 1ull << (lab[i] - 1);
+        const unsigned long long m2 = all & ~m1;
+        for (int kb = 0; kb < K; kb += KB) {
+            double tm[KB], tn[KB], tc[KB];
+            {   // Tmml, Tnme: mean over group 1 − mean over group 2
+                double a[KB], b[KB];
+                unsigned long long m = m1;
+                const double *pm = s_mml + (__ffsll((long long)m) - 1) * K + kb, *pn = s_nme + (__ffsll((long long)m) - 1) * K + kb;
+#pragma unroll
+                for (int u = 0; u < KB; ++u) { a[u] = pm[u]; b[u] = pn[u]; }
+                for (m &= m - 1; m; m &= m - 1) {
+                    const int o = (__ffsll((long long)m) - 1) * K + kb;
+#pragma unroll
+                    for (int u = 0; u < KB; ++u) { a[u] = __dadd_rn(a[u], s_mml[o + u]); b[u] = __dadd_rn(b[u], s_nme[o + u]); }
                 }
-            tc = __ddiv_rn(tc, (double)(n1 * n2));
-            if (fabs(tm) >= fabs(tobs)) atomicAdd(&s_cnt[k], 1);                 // :268-270
-            if (fabs(tn) >= fabs(s_T[K + k])) atomicAdd(&s_cnt[K + k], 1);
-            if (tc >= s_T[2 * K + k]) atomicAdd(&s_cnt[2 * K + k], 1);
+#pragma unroll
+                for (int u = 0; u < KB; ++u) { tm[u] = div_small(a[u], d1, y1); tn[u] = div_small(b[u], d1, y1); }
+                m = m2;
+                pm = s_mml + (__ffsll((long long)m) - 1) * K + kb; pn = s_nme + (__ffsll((long long)m) - 1) * K + kb;
+#pragma unroll
+                for (int u = 0; u < KB; ++u) { a[u] = pm[u]; b[u] = pn[u]; }
+                for (m &= m - 1; m; m &= m - 1) {
+                    const int o = (__ffsll((long long)m) - 1) * K + kb;
+#pragma unroll
+                    for (int u = 0; u < KB; ++u) { a[u] = __dadd_rn(a[u], s_mml[o + u]); b[u] = __dadd_rn(b[u], s_nme[o + u]); }
+                }
+#pragma unroll
+                for (int u = 0; u < KB; ++u) {
+                    tm[u] = __dsub_rn(tm[u], div_small(a[u], d2, y2));
+                    tn[u] = __dsub_rn(tn[u], div_small(b[u], d2, y2));
+                }
+            }
+#pragma unroll
+            for (int u = 0; u < KB; ++u) tc[u] = 0.0;                            // comp_unmat_perm_stat_cmd :86-107
+            for (unsigned long long a = m1; a; a &= a - 1) {
+                const int ii = __ffsll((long long)a) - 1;
+                for (unsigned long long b = m2; b; b &= b - 1) {
+                    const int jj = __ffsll((long long)b) - 1;
+                    const int o = (min(ii, jj) * S + max(ii, jj)) * K + kb;
+#pragma unroll
+                    for (int u = 0; u < KB; ++u) tc[u] = __dadd_rn(tc[u], s_cmd[o + u]);
+                }
+            }
+#pragma unroll
+            for (int u = 0; u < KB; ++u) {
+                const int k = kb + u;
+                if (k < K) {
+                    const double tobs = s_T[k];
+                    if (tobs == tobs) {                                          // isnan(tmml_obs[k]) && continue (:260)
+                        if (fabs(tm[u]) >= fabs(tobs)) atomicAdd(&s_cnt[k], 1);  // :268-270
+                        if (fabs(tn[u]) >= fabs(s_T[K + k])) atomicAdd(&s_cnt[K + k], 1);
+                        if (div_small(tc[u], d12, y12) >= s_T[2 * K + k]) atomicAdd(&s_cnt[2 * K + k], 1);
+                    }
+                }
+            }
         }
     }
     __syncthreads();
@@ -98,11 +151,26 @@ __global__ void __launch_bounds__(SW_THREADS) k_unmat_sweep(int n1, int n2, int 
     }
 }
 
+typedef void (*unmat_kernel_t)(int, int, int, const int64_t*, const double*, const double*, const double*, const int32_t*, int64_t, int, double*,
+                               int64_t*, double*);
+// Sub-regions per pass: the fewest passes of at most 8, split evenly (K = 9 → 5 + 4), so the accumulators stay in ≈ 100
+// registers and two blocks fit on an SM.  CPN_SWEEP_KB overrides (4, 5, 6, 8, 12, 16) for experiments.
+inline unmat_kernel_t unmat_kernel_for(int Kmax) {
+    int chunks = (Kmax + 7) / 8, kb = (Kmax + chunks - 1) / chunks;
+    if (const char* e = getenv("CPN_SWEEP_KB")) kb = atoi(e);
+    return kb <= 4 ? k_unmat_sweep<4> : kb == 5 ? k_unmat_sweep<5> : kb == 6 ? k_unmat_sweep<6> : kb <= 8 ? k_unmat_sweep<8>
+         : kb <= 12 ? k_unmat_sweep<12> : k_unmat_sweep<16>;
+}
+inline size_t unmat_smem(int S, int Kmax) {
+    return (size_t)(2 * S + S * S + 3) * Kmax * sizeof(double) + (size_t)3 * Kmax * sizeof(int) + 16 * sizeof(double);
+}
+
 __global__ void __launch_bounds__(SW_THREADS) k_mat_sweep(int n, int Kmax, const int64_t* __restrict__ tbl_off, const double* __restrict__ mml1,
                                                            const double* __restrict__ mml2, const double* __restrict__ nme1,
                                                            const double* __restrict__ nme2, const int64_t* __restrict__ js, int64_t P,
                                                            int exact, double* __restrict__ T, int64_t* __restrict__ cnt,
-                                                           double* __restrict__ pval) {
+                                                           double* __restrict__ pval, int rstride /*values per sub-region and region: n, or S
+                                                           when both groups share one [R][S][K] table*/, int g2off /*0, or n*/) {
     extern __shared__ double sm[];
     int64_t r = blockIdx.x;
     int64_t k0 = tbl_off[r];
@@ -112,8 +180,8 @@ __global__ void __launch_bounds__(SW_THREADS) k_mat_sweep(int n, int Kmax, const
     double* s_T = s_dn + n * Kmax;              // [2][K]
     int* s_cnt = (int*)(s_T + 2 * Kmax);
     for (int i = threadIdx.x; i < n * K; i += blockDim.x) {
-        s_dm[i] = __dsub_rn(mml1[k0 * n + i], mml2[k0 * n + i]);
-        s_dn[i] = __dsub_rn(nme1[k0 * n + i], nme2[k0 * n + i]);
+        s_dm[i] = __dsub_rn(mml1[k0 * rstride + i], mml2[k0 * rstride + g2off * K + i]);
+        s_dn[i] = __dsub_rn(nme1[k0 * rstride + i], nme2[k0 * rstride + g2off * K + i]);
     }
     for (int i = threadIdx.x; i < 2 * K; i += blockDim.x) s_cnt[i] = 0;
     __syncthreads();
@@ -124,6 +192,7 @@ __global__ void __launch_bounds__(SW_THREADS) k_mat_sweep(int n, int Kmax, const
         s_T[K + k] = __ddiv_rn(b, (double)n);
     }
     __syncthreads();
+    const double dn_ = (double)n, yn = __ddiv_rn(1.0, (double)n);
     for (int64_t pi = threadIdx.x; pi < P; pi += blockDim.x) {
         int64_t j = js[pi];
         for (int k = 0; k < K; ++k) {
@@ -137,7 +206,7 @@ __global__ void __launch_bounds__(SW_THREADS) k_mat_sweep(int n, int Kmax, const
                 b = __dadd_rn(b, bit ? s_dn[s * K + k] : -s_dn[s * K + k]);
                 jk >>= 1;
             }
-            a = __ddiv_rn(a, (double)n); b = __ddiv_rn(b, (double)n);
+            a = div_small(a, dn_, yn); b = div_small(b, dn_, yn);
             if (fabs(a) >= fabs(tobs)) atomicAdd(&s_cnt[k], 1);
             if (fabs(b) >= fabs(s_T[K + k])) atomicAdd(&s_cnt[K + k], 1);
         }
@@ -192,6 +261,45 @@ __global__ void __launch_bounds__(SW_THREADS) k_two_samp_pvals(int Kmax, const i
     }
 }
 
+// Fused group test: index tables of the R·S models (model t = r·S + s shares region r's features).
+__global__ void k_grp_models(int64_t T, int S, const int64_t* __restrict__ cpg_off, const int64_t* __restrict__ sub_off,
+                             int64_t* __restrict__ reg_of, int64_t* __restrict__ ex_off, int64_t* __restrict__ k_off) {
+    int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (t > T) return;
+    if (t == T) { int64_t R = T / S; ex_off[T] = S * cpg_off[R]; k_off[T] = S * sub_off[R]; return; }
+    int64_t r = t / S, sidx = t - r * S;
+    reg_of[t] = r;
+    ex_off[t] = S * cpg_off[r] + sidx * (cpg_off[r + 1] - cpg_off[r]);
+    k_off[t] = S * sub_off[r] + sidx * (sub_off[r + 1] - sub_off[r]);
+}
+// Pairs of a region and where their CMD vectors go.  Unmatched: all i<j, written straight into the [S][S][K] table the
+// sweep reads; matched: (s, n+s), written as [n][K].
+__global__ void k_grp_pairs(int64_t R, int S, int npair, const int* __restrict__ pi, const int* __restrict__ pj, int matched,
+                            const int64_t* __restrict__ sub_off, int64_t* __restrict__ pa, int64_t* __restrict__ pb,
+                            int64_t* __restrict__ cmd_off) {
+    int64_t q = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (q >= R * npair) return;
+    int64_t r = q / npair;
+    int loc = (int)(q - r * npair);
+    int i = pi[loc], j = pj[loc];
+    int64_t k0 = sub_off[r], K = sub_off[r + 1] - k0;
+    pa[q] = r * S + i; pb[q] = r * S + j;
+    cmd_off[q] = matched ? (int64_t)npair * k0 + (int64_t)loc * K : (int64_t)S * S * k0 + (int64_t)(i * S + j) * K;
+}
+// Tcmd of the matched test: sum(cmds)/n, left to right (grp_perm_tests.jl:308-314).
+__global__ void k_mat_tcmd(int64_t R, int n, const int64_t* __restrict__ sub_off, const double* __restrict__ cmd /*[R][n][K]*/,
+                           double* __restrict__ tcmd) {
+    int64_t r = blockIdx.x;
+    int64_t k0 = sub_off[r];
+    int K = (int)(sub_off[r + 1] - k0);
+    for (int k = threadIdx.x; k < K; k += blockDim.x) {
+        const double* c = cmd + (int64_t)n * k0;
+        double a = c[k];
+        for (int s = 1; s < n; ++s) a = __dadd_rn(a, c[(int64_t)s * K + k]);
+        tcmd[k0 + k] = __ddiv_rn(a, (double)n);
+    }
+}
+
 int kmax_of(const int64_t* tbl_off, int64_t R) {
     int64_t k = 1;
     for (int64_t r = 0; r < R; ++r) k = std::max(k, tbl_off[r + 1] - tbl_off[r]);
@@ -213,11 +321,12 @@ int cpn_grp_unmat_sweep(cpn_ctx* ctx, int64_t R, int32_t n1, int32_t n2, const i
     const int S = n1 + n2;
     const int Kmax = kmax_of(tbl_off, R);
     const int64_t sumK = tbl_off[R];
-    size_t smem = (size_t)(2 * S + S * S + 3) * Kmax * sizeof(double) + (size_t)3 * Kmax * sizeof(int);
+    size_t smem = unmat_smem(S, Kmax);
     CPN_ARG(ctx, smem <= 200 * 1024, "statistic tables of one region do not fit in shared memory");
     for (int64_t i = 0; i < P * n1; ++i) CPN_ARG(ctx, labelings[i] >= 1 && labelings[i] <= S, "labeling id out of range");
     cudaStream_t s = ctx->stream;
-    CPN_CUDA(ctx, cudaFuncSetAttribute(k_unmat_sweep, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    unmat_kernel_t kern = unmat_kernel_for(Kmax);
+    CPN_CUDA(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     CPN_CUDA(ctx, cudaEventRecord(ctx->ev0, s));
     {
         DevBuf<int64_t> d_off, o_cnt;
@@ -226,7 +335,7 @@ int cpn_grp_unmat_sweep(cpn_ctx* ctx, int64_t R, int32_t n1, int32_t n2, const i
         CPN_CUDA(ctx, d_off.upload(tbl_off, R + 1, s)); CPN_CUDA(ctx, d_mml.upload(mml, sumK * S, s)); CPN_CUDA(ctx, d_nme.upload(nme, sumK * S, s));
         CPN_CUDA(ctx, d_cmd.upload(cmd_tbl, sumK * S * S, s)); CPN_CUDA(ctx, d_lab.upload(labelings, P * n1, s));
         CPN_CUDA(ctx, o_T.alloc(3 * sumK, s)); CPN_CUDA(ctx, o_cnt.alloc(3 * sumK, s)); CPN_CUDA(ctx, o_p.alloc(3 * sumK, s));
-        { KTimer kt(ctx, CPN_K_SWEEP); k_unmat_sweep<<<(unsigned)R, SW_THREADS, smem, s>>>(n1, n2, Kmax, d_off.p, d_mml.p, d_nme.p, d_cmd.p, d_lab.p, P, exact, o_T.p, o_cnt.p, o_p.p); }
+        { KTimer kt(ctx, CPN_K_SWEEP); kern<<<(unsigned)R, SW_THREADS, smem, s>>>(n1, n2, Kmax, d_off.p, d_mml.p, d_nme.p, d_cmd.p, d_lab.p, P, exact, o_T.p, o_cnt.p, o_p.p); }
         CPN_CUDA(ctx, cudaGetLastError());
         CPN_CUDA(ctx, o_T.download(T, 3 * sumK, s)); CPN_CUDA(ctx, o_cnt.download(cnt, 3 * sumK, s)); CPN_CUDA(ctx, o_p.download(pval, 3 * sumK, s));
         CPN_CUDA(ctx, cudaEventRecord(ctx->ev1, s));
@@ -261,7 +370,7 @@ int cpn_grp_mat_sweep(cpn_ctx* ctx, int64_t R, int32_t n, const int64_t* tbl_off
         CPN_CUDA(ctx, d_m1.upload(mml1, sumK * n, s)); CPN_CUDA(ctx, d_m2.upload(mml2, sumK * n, s));
         CPN_CUDA(ctx, d_n1.upload(nme1, sumK * n, s)); CPN_CUDA(ctx, d_n2.upload(nme2, sumK * n, s));
         CPN_CUDA(ctx, o_T.alloc(2 * sumK, s)); CPN_CUDA(ctx, o_cnt.alloc(2 * sumK, s)); CPN_CUDA(ctx, o_p.alloc(2 * sumK, s));
-        { KTimer kt(ctx, CPN_K_SWEEP); k_mat_sweep<<<(unsigned)R, SW_THREADS, smem, s>>>(n, Kmax, d_off.p, d_m1.p, d_m2.p, d_n1.p, d_n2.p, d_js.p, P, exact, o_T.p, o_cnt.p, o_p.p); }
+        { KTimer kt(ctx, CPN_K_SWEEP); k_mat_sweep<<<(unsigned)R, SW_THREADS, smem, s>>>(n, Kmax, d_off.p, d_m1.p, d_m2.p, d_n1.p, d_n2.p, d_js.p, P, exact, o_T.p, o_cnt.p, o_p.p, n, 0); }
         CPN_CUDA(ctx, cudaGetLastError());
         CPN_CUDA(ctx, o_T.download(T, 2 * sumK, s)); CPN_CUDA(ctx, o_cnt.download(cnt, 2 * sumK, s)); CPN_CUDA(ctx, o_p.download(pval, 2 * sumK, s));
         CPN_CUDA(ctx, cudaEventRecord(ctx->ev1, s));
@@ -295,6 +404,96 @@ int cpn_two_samp_pvals(cpn_ctx* ctx, int64_t R, const int64_t* tbl_off, int64_t 
         { KTimer kt(ctx, CPN_K_SWEEP); k_two_samp_pvals<<<(unsigned)R, SW_THREADS, smem, s>>>(Kmax, d_off.p, P, d_T.p, d_null.p, exact, o_cnt.p, o_nv.p, o_p.p); }
         CPN_CUDA(ctx, cudaGetLastError());
         CPN_CUDA(ctx, o_cnt.download(cnt, 3 * sumK, s)); CPN_CUDA(ctx, o_nv.download(n_valid, 3 * sumK, s)); CPN_CUDA(ctx, o_p.download(pval, 3 * sumK, s));
+        CPN_CUDA(ctx, cudaEventRecord(ctx->ev1, s));
+        CPN_CUDA(ctx, cudaStreamSynchronize(s));
+    }
+    float ms = 0;
+    CPN_CUDA(ctx, cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1));
+    ctx->last_ms = ms;
+    if (ctx->profile) cpn_profile_collect(ctx);
+    return CPN_OK;
+}
+
+int cpn_grp_test_batch(cpn_ctx* ctx, int64_t R, int32_t n1, int32_t n2, int32_t matched, const double* phi, const int64_t* cpg_off,
+                       const double* rho_n, const double* d_n, const int64_t* sub_off, const int64_t* sub_p, const int64_t* sub_q,
+                       const void* labelings, int64_t P, int32_t exact, double* T, int64_t* cnt, double* pval, double* tcmd) {
+    if (!ctx) return CPN_ERR_ARG;
+    CPN_ARG(ctx, R >= 0 && n1 >= 1 && n2 >= 1 && n1 <= 32 && n2 <= 32 && P >= 0, "sizes (n1,n2 in 1..32)");
+    CPN_ARG(ctx, !matched || n1 == n2, "the matched test needs n1 == n2");
+    CPN_ARG(ctx, phi && cpg_off && rho_n && d_n && sub_off && sub_p && sub_q && (labelings || P == 0) && T && cnt && pval, "null pointer");
+    CPN_ARG(ctx, !matched || tcmd, "tcmd is required for the matched test");
+    CPN_CUDA(ctx, cudaSetDevice(ctx->device));
+    LaunchCounter lc(ctx);
+    if (R == 0) return CPN_OK;
+    const int S = n1 + n2, n = n1;
+    const int64_t Tm = R * S, sumN = cpg_off[R], sumK = sub_off[R];
+    const int Kmax = kmax_of(sub_off, R);
+    int64_t Nmax = 0;
+    for (int64_t r = 0; r < R; ++r) {
+        CPN_ARG(ctx, cpg_off[r + 1] - cpg_off[r] >= 2, "every region needs N >= 2 CpG sites");
+        Nmax = std::max(Nmax, cpg_off[r + 1] - cpg_off[r]);
+    }
+    std::vector<int> pi, pj;
+    if (matched) for (int s = 0; s < n; ++s) { pi.push_back(s); pj.push_back(n + s); }
+    else for (int i = 0; i < S; ++i) for (int j = i + 1; j < S; ++j) { pi.push_back(i); pj.push_back(j); }
+    const int npair = (int)pi.size();
+    const int nstat = matched ? 2 : 3;
+    size_t smem = matched ? (size_t)(2 * n + 2) * Kmax * sizeof(double) + (size_t)2 * Kmax * sizeof(int) : unmat_smem(S, Kmax);
+    CPN_ARG(ctx, smem <= 200 * 1024, "statistic tables of one region do not fit in shared memory");
+    if (!matched) {
+        const int32_t* lab = (const int32_t*)labelings;
+        for (int64_t i = 0; i < P * n1; ++i) CPN_ARG(ctx, lab[i] >= 1 && lab[i] <= S, "labeling id out of range");
+    }
+    cudaStream_t s = ctx->stream;
+    if (matched) CPN_CUDA(ctx, cudaFuncSetAttribute(k_mat_sweep, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    unmat_kernel_t kern = unmat_kernel_for(Kmax);
+    if (!matched) CPN_CUDA(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    CPN_CUDA(ctx, cudaEventRecord(ctx->ev0, s));
+    {
+        DevBuf<double> d_phi, d_rho, d_dn, logZ, ex, exx, lg, e1, e2, mml, nme, cmd, o_T, o_p, o_tc;
+        DevBuf<int64_t> d_cpg, d_so, d_sp, d_sq, reg_of, ex_off, k_off, pa, pb, cmd_off, d_js, o_cnt;
+        DevBuf<int32_t> d_lab;
+        DevBuf<int> d_pi, d_pj;
+        CPN_CUDA(ctx, d_phi.upload(phi, 3 * Tm, s));
+        CPN_CUDA(ctx, d_cpg.upload(cpg_off, R + 1, s)); CPN_CUDA(ctx, d_rho.upload(rho_n, sumN, s)); CPN_CUDA(ctx, d_dn.upload(d_n, sumN - R, s));
+        CPN_CUDA(ctx, d_so.upload(sub_off, R + 1, s)); CPN_CUDA(ctx, d_sp.upload(sub_p, sumK, s)); CPN_CUDA(ctx, d_sq.upload(sub_q, sumK, s));
+        CPN_CUDA(ctx, d_pi.upload(pi.data(), npair, s)); CPN_CUDA(ctx, d_pj.upload(pj.data(), npair, s));
+        if (matched) CPN_CUDA(ctx, d_js.upload((const int64_t*)labelings, P, s));
+        else CPN_CUDA(ctx, d_lab.upload((const int32_t*)labelings, P * n1, s));
+        CPN_CUDA(ctx, reg_of.alloc(Tm, s)); CPN_CUDA(ctx, ex_off.alloc(Tm + 1, s)); CPN_CUDA(ctx, k_off.alloc(Tm + 1, s));
+        CPN_CUDA(ctx, logZ.alloc(Tm, s)); CPN_CUDA(ctx, ex.alloc(S * sumN, s)); CPN_CUDA(ctx, exx.alloc(S * (sumN - R), s));
+        CPN_CUDA(ctx, lg.alloc(4 * S * sumK, s)); CPN_CUDA(ctx, e1.alloc(S * sumK, s)); CPN_CUDA(ctx, e2.alloc(S * sumK, s));
+        CPN_CUDA(ctx, mml.alloc(S * sumK, s)); CPN_CUDA(ctx, nme.alloc(S * sumK, s));
+        const int64_t ncmd = matched ? (int64_t)n * sumK : (int64_t)S * S * sumK;
+        CPN_CUDA(ctx, cmd.alloc(ncmd, s));
+        CPN_CUDA(ctx, pa.alloc(R * npair, s)); CPN_CUDA(ctx, pb.alloc(R * npair, s)); CPN_CUDA(ctx, cmd_off.alloc(R * npair, s));
+        CPN_CUDA(ctx, o_T.alloc(nstat * sumK, s)); CPN_CUDA(ctx, o_cnt.alloc(nstat * sumK, s)); CPN_CUDA(ctx, o_p.alloc(nstat * sumK, s));
+        if (matched) CPN_CUDA(ctx, o_tc.alloc(sumK, s));
+        CPN_CUDA(ctx, cudaMemsetAsync(cmd.p, 0xFF, ncmd * sizeof(double), s));        // NaN outside the pairs that exist
+        { KTimer kt(ctx, CPN_K_PREP);
+          k_grp_models<<<blocks_for(Tm + 1, 256), 256, 0, s>>>(Tm, S, d_cpg.p, d_so.p, reg_of.p, ex_off.p, k_off.p); }
+        { KTimer kt(ctx, CPN_K_PREP);
+          k_grp_pairs<<<blocks_for(R * npair, 256), 256, 0, s>>>(R, S, npair, d_pi.p, d_pj.p, matched, d_so.p, pa.p, pb.p, cmd_off.p); }
+        // get_stat_sums! of every sample's model, comp_cmd of every pair, then the labelings
+        int rc = cpn_stat_sums_launch(ctx, Tm, d_phi.p, reg_of.p, ex_off.p, k_off.p, d_cpg.p, d_rho.p, d_dn.p, d_so.p, d_sp.p, d_sq.p, Nmax, logZ.p,
+                                      ex.p, exx.p, lg.p, e1.p, e2.p, mml.p, nme.p);
+        if (rc) return rc;
+        rc = cpn_cmd_launch(ctx, R * npair, pa.p, pb.p, d_phi.p, reg_of.p, ex_off.p, ex.p, exx.p, k_off.p, nme.p, d_cpg.p, d_rho.p, d_dn.p, d_so.p,
+                            d_sp.p, d_sq.p, Nmax, cmd_off.p, cmd.p);
+        if (rc) return rc;
+        if (matched) {
+            { KTimer kt(ctx, CPN_K_SWEEP); k_mat_tcmd<<<(unsigned)R, 32, 0, s>>>(R, n, d_so.p, cmd.p, o_tc.p); }
+            { KTimer kt(ctx, CPN_K_SWEEP);
+              k_mat_sweep<<<(unsigned)R, SW_THREADS, smem, s>>>(n, Kmax, d_so.p, mml.p, mml.p, nme.p, nme.p, d_js.p, P, exact, o_T.p, o_cnt.p, o_p.p,
+                                                                S, n); }
+            CPN_CUDA(ctx, o_tc.download(tcmd, sumK, s));
+        } else {
+            KTimer kt(ctx, CPN_K_SWEEP);
+            kern<<<(unsigned)R, SW_THREADS, smem, s>>>(n1, n2, Kmax, d_so.p, mml.p, nme.p, cmd.p, d_lab.p, P, exact, o_T.p, o_cnt.p, o_p.p);
+        }
+        CPN_CUDA(ctx, cudaGetLastError());
+        CPN_CUDA(ctx, o_T.download(T, nstat * sumK, s)); CPN_CUDA(ctx, o_cnt.download(cnt, nstat * sumK, s));
+        CPN_CUDA(ctx, o_p.download(pval, nstat * sumK, s));
         CPN_CUDA(ctx, cudaEventRecord(ctx->ev1, s));
         CPN_CUDA(ctx, cudaStreamSynchronize(s));
     }

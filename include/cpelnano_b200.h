@@ -181,6 +181,20 @@ int cpn_grp_mat_sweep(cpn_ctx* ctx, int64_t R, int32_t n, const int64_t* tbl_off
                       const double* mml1, const double* mml2, const double* nme1, const double* nme2,
                       const int64_t* js, int64_t P, int32_t exact,
                       double* T, int64_t* cnt, double* pval);
+/* group comparison, all on the device  src/grp_perm_tests.jl:200-291 (unmatched) / :432-499 (matched) over the pmap of
+ * :674: from the fitted parameters of the S = n1+n2 samples of every region to (T, counts, p-values) in one call —
+ * get_stat_sums! of the R*S models, comp_cmd of every pair (all i<j unmatched; (s, n1+s) matched) and the labeling sweep.
+ * Only phi goes in and only the statistics come out; E[X], E[XX], MML, NME and the CMD table never leave the GPU.
+ *   phi [R][S][3]      group 1 first; every sample must have a model (the caller drops regions that do not, :646-655)
+ *   cpg_off ... sub_q  per-CpG tables as in cpn_stat_sums_batch
+ *   matched == 0:      labelings int32 [P][n1] ascending 1-based ids of group 1 (combinations); outputs T, cnt, pval
+ *                      [sumK*3] as cpn_grp_unmat_sweep; tcmd unused
+ *   matched != 0:      n1 == n2; labelings int64 js[P] sign words; outputs T, cnt, pval [sumK*2] as cpn_grp_mat_sweep and
+ *                      tcmd [sumK] = sum of the pair CMDs / n (:308-314)                                               */
+int cpn_grp_test_batch(cpn_ctx* ctx, int64_t R, int32_t n1, int32_t n2, int32_t matched, const double* phi,
+                       const int64_t* cpg_off, const double* rho_n, const double* d_n, const int64_t* sub_off,
+                       const int64_t* sub_p, const int64_t* sub_q, const void* labelings, int64_t P, int32_t exact,
+                       double* T, int64_t* cnt, double* pval, double* tcmd);
 /* two-sample null statistics, all on the device  src/two_samp_perm_tests.jl:41-87 (pmap_two_samp_null_stats) over the
  * pmap of :220: for every region r and every permutation i of its pooled reads, refit both halves (multi-start EM),
  * summarise both fits (rscle_grp_mod! + get_stat_sums!) and return Tmml = mml1-mml2, Tnme = nme1-nme2, Tcmd = comp_cmd.

@@ -305,6 +305,20 @@ def test_cmd_and_group_tests_vs_oracle_and_goldens(engine, orc, cpn):
             assert round(ma[r]["T"][1, k], 4) == G["mat_tnme"][key][0] and abs(ma[r]["pval"][1, k] - G["mat_tnme"][key][1]) < 1e-15
             assert round(max(0.0, ma[r]["tcmd"][k]), 4) == G["mat_tcmd"][key][0]
     assert n_rows == 225 and n_tie < 120
+    # the fused device pipeline (ϕ̂ of the 12 samples in, statistics out) gives exactly the staged results
+    reps = [g1s[r][0] for r in range(R)]
+    cpg_off, rho_n, d_n, sub_off, sub_p, sub_q = engine.pack_cpgs(reps)
+    phi = np.array([[m.phihat for m in g1s[r] + g2s[r]] for r in range(R)])
+    T, cnt, pv = engine.lib.grp_test_batch(6, 6, False, phi, cpg_off, rho_n, d_n, sub_off, sub_p, sub_q, labs, True)
+    Tm, cntm, pm, tcmd = engine.lib.grp_test_batch(6, 6, True, phi, cpg_off, rho_n, d_n, sub_off, sub_p, sub_q, np.arange(64), True)
+    for r in range(R):
+        K = sub_off[r + 1] - sub_off[r]
+        sl3, sl2 = slice(3 * sub_off[r], 3 * sub_off[r + 1]), slice(2 * sub_off[r], 2 * sub_off[r + 1])
+        assert np.array_equal(T[sl3].reshape(3, K), un[r]["T"], equal_nan=True) and np.array_equal(cnt[sl3].reshape(3, K), un[r]["cnt"])
+        assert np.array_equal(pv[sl3].reshape(3, K), un[r]["pval"], equal_nan=True)
+        assert np.array_equal(Tm[sl2].reshape(2, K), ma[r]["T"], equal_nan=True) and np.array_equal(cntm[sl2].reshape(2, K), ma[r]["cnt"])
+        assert np.array_equal(pm[sl2].reshape(2, K), ma[r]["pval"], equal_nan=True)
+        assert np.array_equal(tcmd[sub_off[r]:sub_off[r + 1]], ma[r]["tcmd"], equal_nan=True)
 
 
 def test_summaries_vs_60_digit_reference(engine, orc, cpn):

@@ -87,10 +87,33 @@ def group(args):
     dev = sum(v["device_ms"] for v in stages.values())
     wall = sum(v["wall_ms"] for v in stages.values())
     sig = float(np.nanmean(p[: 3 * int(sub_off[-1])] < 0.05))
+    # the same through the fused entry point (ϕ̂ in, statistics out)
+    fused = {}
+    for rep in range(2):                                                     # first pass warms the pool up
+        lib.set_profile(True)
+        t0 = time.perf_counter()
+        Tf, cf, pf = lib.grp_test_batch(n1, n2, False, phi, nb.cpg_off, nb.rho_n, nb.d_n, sub_off, sub_p, sub_q, labelings, True)
+        fused["unmatched"] = {"wall_ms": (time.perf_counter() - t0) * 1e3, "device_ms": lib.last_device_ms(),
+                              "kernel_ms": {k: round(v[0], 3) for k, v in lib.get_profile().items() if v[1]}}
+        lib.set_profile(True)
+        t0 = time.perf_counter()
+        Tg, cg, pg, tcg = lib.grp_test_batch(n1, n2, True, phi, nb.cpg_off, nb.rho_n, nb.d_n, sub_off, sub_p, sub_q, np.arange(64), True)
+        fused["matched"] = {"wall_ms": (time.perf_counter() - t0) * 1e3, "device_ms": lib.last_device_ms(),
+                            "kernel_ms": {k: round(v[0], 3) for k, v in lib.get_profile().items() if v[1]}}
+        lib.set_profile(False)
+    same = bool(np.array_equal(Tf, T, equal_nan=True) and np.array_equal(cf, cnt) and np.array_equal(Tg, Tm, equal_nan=True) and np.array_equal(cg, cm))
+    fw = fused["unmatched"]["wall_ms"] + fused["matched"]["wall_ms"]
+    fd = fused["unmatched"]["device_ms"] + fused["matched"]["device_ms"]
     print(json.dumps({"workload": "group 6 vs 6, unmatched (924 labelings) + matched (64 sign patterns)", "regions": R, "models": R * S,
-                      "pairs": int(len(pa)), "sub_regions": int(sub_off[-1]), "stages": stages, "device_ms": dev, "wall_ms": wall,
-                      "regions_per_s_device": R / (dev * 1e-3), "regions_per_s_wall": R / (wall * 1e-3), "frac_p_lt_0.05": sig,
-                      "note": "wall includes numpy packing and pageable host↔device copies of the Python harness"}))
+                      "pairs": int(len(pa)), "sub_regions": int(sub_off[-1]),
+                      "staged": {"stages": stages, "device_ms": dev, "wall_ms": wall, "regions_per_s_device": R / (dev * 1e-3),
+                                 "regions_per_s_wall": R / (wall * 1e-3),
+                                 "note": "one C-ABI call per stage; wall includes numpy packing and pageable host↔device copies"},
+                      "fused": {"calls": fused, "device_ms": fd, "wall_ms": fw, "regions_per_s_device": R / (fd * 1e-3),
+                                "regions_per_s_wall": R / (fw * 1e-3), "identical_to_staged": same,
+                                "unmatched_only_regions_per_s_wall": R / (fused["unmatched"]["wall_ms"] * 1e-3),
+                                "note": "cpn_grp_test_batch: phi in, (T, cnt, p) out; device_ms includes the copies"},
+                      "frac_p_lt_0.05": sig}))
 
 
 def two_sample(args):
@@ -128,8 +151,9 @@ def two_sample(args):
             fits += 2 * P * len(grp)
     print(json.dumps({"workload": "two-sample permutation test, 30+30 reads", "regions": R, "perms": P, "em_fits": fits,
                       "starts_per_fit": cfg.max_em_init, "regions_per_call": G, "device_views": bool(args.device_views), "wall_s": t_all, "regions_per_s_wall": R / t_all, "fits_per_s_wall": fits / t_all,
-                      "note": "one cpn_fit_batch + cpn_stat_sums_batch + cpn_cmd_batch per call of regions_per_call regions (2P fits each), "
-                              "pageable host buffers through the Python harness"}))
+                      "note": ("cpn_two_samp_null_batch: pooled reads uploaded once, refits are views" if args.device_views else
+                               "permuted samples materialised on the host: cpn_fit_batch + cpn_stat_sums_batch + cpn_cmd_batch") +
+                              "; regions_per_call regions per call; pageable host buffers; wall includes drawing the EM starts"}))
 
 
 if __name__ == "__main__":
