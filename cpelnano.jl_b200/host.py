@@ -246,6 +246,39 @@ class Engine:
             out.append(dict(T=T[sl].reshape(3, K), cnt=cnt[sl].reshape(3, K), pval=p[sl].reshape(3, K), coords=regions_g1[r][0].nls_rgs))
         return out
 
+    def grp_comp_batch(self, regions_g1, regions_g2, matched=False, labelings=None, js=None, rng=None):
+        """The body of the region loop of the group comparison (grp_perm_tests.jl:599 / :618) for a list of regions in one
+        device call: the models only need ϕ̂ and the region features — get_stat_sums!, comp_cmd for every pair and the
+        labeling sweep all run inside cpn_grp_test_batch.  Returns the same dicts as unmat_/mat_est_reg_test_batch."""
+        R = len(regions_g1)
+        n1, n2 = len(regions_g1[0]), len(regions_g2[0])
+        S = n1 + n2
+        reps = [regions_g1[r][0] for r in range(R)]
+        cpg_off, rho_n, d_n, sub_off, sub_p, sub_q = self.pack_cpgs(reps)
+        phi = np.array([[m.phihat for m in regions_g1[r] + regions_g2[r]] for r in range(R)], dtype=np.float64)
+        if matched:
+            if 0.5 ** n1 < 0.05:
+                exact = 2 ** n1 < LMAX
+                if js is None:
+                    js = np.arange(2 ** n1, dtype=np.int64) if exact else (rng or np.random.default_rng()).integers(0, 2 ** n1, size=LMAX)
+            else:
+                exact, js = True, np.zeros(0, dtype=np.int64)
+            T, cnt, p, tcmd = self.lib.grp_test_batch(n1, n2, True, phi, cpg_off, rho_n, d_n, sub_off, sub_p, sub_q, js, exact, device=self.device)
+            return [dict(T=T[2 * sub_off[r]:2 * sub_off[r + 1]].reshape(2, -1), cnt=cnt[2 * sub_off[r]:2 * sub_off[r + 1]].reshape(2, -1),
+                         pval=p[2 * sub_off[r]:2 * sub_off[r + 1]].reshape(2, -1), tcmd=tcmd[sub_off[r]:sub_off[r + 1]], coords=reps[r].nls_rgs)
+                    for r in range(R)]
+        L = math.comb(S, n1)
+        if L > 20:
+            exact = L < LMAX
+            if labelings is None:
+                allc = np.array(list(combinations(range(1, S + 1), n1)), dtype=np.int32)
+                labelings = allc if exact else allc[np.unique((rng or np.random.default_rng()).integers(0, L, size=LMAX))]
+        else:
+            exact, labelings = True, np.zeros((0, n1), dtype=np.int32)
+        T, cnt, p = self.lib.grp_test_batch(n1, n2, False, phi, cpg_off, rho_n, d_n, sub_off, sub_p, sub_q, labelings, exact, device=self.device)
+        return [dict(T=T[3 * sub_off[r]:3 * sub_off[r + 1]].reshape(3, -1), cnt=cnt[3 * sub_off[r]:3 * sub_off[r + 1]].reshape(3, -1),
+                     pval=p[3 * sub_off[r]:3 * sub_off[r + 1]].reshape(3, -1), coords=reps[r].nls_rgs) for r in range(R)]
+
     def mat_est_reg_test_batch(self, regions_g1, regions_g2, js=None, rng=None):
         """mat_est_reg_test (src/grp_perm_tests.jl:432-499): Tmml, Tnme with sign-flip p-values; Tcmd = mean pair CMD, no p-value."""
         R = len(regions_g1)

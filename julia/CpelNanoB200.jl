@@ -104,6 +104,32 @@ function get_stat_sums_batch!(rss::Vector{RegStruct}, config::CpelNanoConfig)
 end
 CpelNano.get_stat_sums!(rs::RegStruct, config::CpelNanoConfig) = get_stat_sums_batch!([rs], config)
 
+# ---- region loop of the group comparison  grp_perm_tests.jl:599 (unmatched) / :618 (matched), pmap at :674 ---------
+# ms_g1[r], ms_g2[r]: the fitted models (ϕ̂ and region features; no summaries needed) of the two groups for region r.
+# Returns (T, cnt, p[, tcmd]) flat, sub-regions of region r at sub_off[r]+1:sub_off[r+1] inside blocks of 3 (or 2) statistics.
+function grp_test_batch(ms_g1::Vector{Vector{RegStruct}}, ms_g2::Vector{Vector{RegStruct}}, config::CpelNanoConfig; matched::Bool=false)
+    R = length(ms_g1); n1 = length(ms_g1[1]); n2 = length(ms_g2[1]); S = n1 + n2
+    reps = [ms_g1[r][1] for r in 1:R]
+    pq = [nls_reg_info!(rs, config) for rs in reps]
+    cpg_off = Int64[0; cumsum([rs.N for rs in reps])]; sub_off = Int64[0; cumsum([length(x[1]) for x in pq])]
+    ρn = Float64.(vcat([rs.ρn for rs in reps]...)); dn = Float64.(vcat([rs.dn for rs in reps]...))
+    sub_p = vcat([x[1] for x in pq]...); sub_q = vcat([x[2] for x in pq]...)
+    ϕ = Float64.(vcat([vcat([m.ϕhat for m in vcat(ms_g1[r], ms_g2[r])]...) for r in 1:R]...))
+    exact = matched ? 2^n1 < CpelNano.LMAX : binomial(S, n1) < CpelNano.LMAX
+    lab = matched ? (exact ? collect(Int64, 0:(2^n1 - 1)) : rand(0:(2^n1 - 1), CpelNano.LMAX)) :
+                    Int32.(vcat((exact ? collect(combinations(1:S, n1)) : collect(combinations(1:S, n1))[unique(rand(1:binomial(S, n1), CpelNano.LMAX))])...))
+    P = matched ? length(lab) : div(length(lab), n1)
+    ns = matched ? 2 : 3; sK = sub_off[end]
+    T = Vector{Float64}(undef, ns * sK); p = similar(T); cnt = Vector{Int64}(undef, ns * sK); tcmd = Vector{Float64}(undef, sK)
+    GC.@preserve ϕ cpg_off ρn dn sub_off sub_p sub_q lab T cnt p tcmd begin
+        check(ccall((:cpn_grp_test_batch, LIB[]), Cint,
+            (Ptr{Cvoid}, Int64, Int32, Int32, Int32, Ptr{Float64}, Ptr{Int64}, Ptr{Float64}, Ptr{Float64}, Ptr{Int64}, Ptr{Int64}, Ptr{Int64},
+             Ptr{Cvoid}, Int64, Int32, Ptr{Float64}, Ptr{Int64}, Ptr{Float64}, Ptr{Float64}),
+            CTX[], R, n1, n2, matched ? 1 : 0, ϕ, cpg_off, ρn, dn, sub_off, sub_p, sub_q, lab, P, exact ? 1 : 0, T, cnt, p, tcmd))
+    end
+    return matched ? (T, cnt, p, tcmd, sub_off) : (T, cnt, p, sub_off)
+end
+
 # ---- batch point: replaces `pmap(x -> pmap_analyze_reg(x, chr, nano, fa_rec, config), chr_part)`  nanopore.jl:406 -----
 function analyze_chr(chr_part, chr, nano, fa_rec, config::CpelNanoConfig)
     rss = RegStruct[]

@@ -311,8 +311,10 @@ def test_cmd_and_group_tests_vs_oracle_and_goldens(engine, orc, cpn):
     phi = np.array([[m.phihat for m in g1s[r] + g2s[r]] for r in range(R)])
     T, cnt, pv = engine.lib.grp_test_batch(6, 6, False, phi, cpg_off, rho_n, d_n, sub_off, sub_p, sub_q, labs, True)
     Tm, cntm, pm, tcmd = engine.lib.grp_test_batch(6, 6, True, phi, cpg_off, rho_n, d_n, sub_off, sub_p, sub_q, np.arange(64), True)
+    un2, ma2 = engine.grp_comp_batch(g1s, g2s), engine.grp_comp_batch(g1s, g2s, matched=True)
     for r in range(R):
         K = sub_off[r + 1] - sub_off[r]
+        assert np.array_equal(un2[r]["pval"], un[r]["pval"], equal_nan=True) and np.array_equal(ma2[r]["tcmd"], ma[r]["tcmd"], equal_nan=True)
         sl3, sl2 = slice(3 * sub_off[r], 3 * sub_off[r + 1]), slice(2 * sub_off[r], 2 * sub_off[r + 1])
         assert np.array_equal(T[sl3].reshape(3, K), un[r]["T"], equal_nan=True) and np.array_equal(cnt[sl3].reshape(3, K), un[r]["cnt"])
         assert np.array_equal(pv[sl3].reshape(3, K), un[r]["pval"], equal_nan=True)
