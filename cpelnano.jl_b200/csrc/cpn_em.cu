@@ -1649,6 +1649,7 @@ static int fit_chunked(cpn_ctx* ctx, bool on_device, int64_t R, const int64_t* g
                         mstep_mode, phi_hat, Q, status, counters, phi_starts, Q_starts, sa_in);
     CPN_ARG(ctx, Nl && rho_l && d_l && lu && lm && phi0 && phi_hat && Q, "null pointer");
     CPN_ARG(ctx, n_init >= 1, "n_init >= 1");
+    CPN_CUDA(ctx, cudaSetDevice(ctx->device));
     auto t0 = std::chrono::steady_clock::now();
     // the CSR offsets are needed on the host to cut the batch; device-resident ones are fetched once
     std::vector<int64_t> h_off[4];
@@ -1720,6 +1721,7 @@ static int fit_chunked(cpn_ctx* ctx, bool on_device, int64_t R, const int64_t* g
     std::vector<std::thread> th;
     th.emplace_back([&]() {
         cpn_ctx* u = ctx->children[0];
+        cudaSetDevice(ctx->device);                    // a new thread starts on device 0
         u->last_launches = 0;
         std::vector<int64_t> g, rd;
         for (int c = 0; c < C; ++c) {
@@ -1756,6 +1758,7 @@ static int fit_chunked(cpn_ctx* ctx, bool on_device, int64_t R, const int64_t* g
     for (int wi = 1; wi <= W; ++wi) {
         th.emplace_back([&, wi]() {
             cpn_ctx* w = ctx->children[wi];
+            cudaSetDevice(ctx->device);
             std::vector<int64_t> cp, sb;
             for (;;) {
                 int c;

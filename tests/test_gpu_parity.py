@@ -658,6 +658,23 @@ def test_full_size_batch_properties(engine, orc, cpn):
     assert np.median(rel) < 1e-7 and rel.max() < 1e-3, rel      # picked optimum; see DESIGN.md §6 for why not tighter
 
 
+def test_second_device_worker_threads(engine, cpn, monkeypatch):
+    """On a multi-GPU box a context on device 1 must do all its work there — including the staging and worker threads of
+    the chunked host path, which start with device 0 current (this crashed with an illegal address once)."""
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs two GPUs")
+    nb = cpn.simulations.make_nano_batch(60, M=20, seed=31)
+    n_init = 2
+    phi0 = cpn.simulations.gen_phi0s(np.random.default_rng(5), nb.R, n_init)
+    monkeypatch.setenv("CPN_WORKERS", "2"); monkeypatch.setenv("CPN_CHUNK_REGIONS", "5"); monkeypatch.setenv("CPN_CHUNKS", "4")
+    outs = [engine.lib.fit_batch(nb.grp_off, nb.Nl, nb.rho_l, nb.d_l, nb.read_off, nb.log_pyx_u, nb.log_pyx_m, phi0, n_init, 20, device=d)
+            for d in (0, 1, 1)]
+    for k in outs[0]:
+        assert np.array_equal(np.asarray(outs[0][k]), np.asarray(outs[1][k]), equal_nan=True), k
+        assert np.array_equal(np.asarray(outs[1][k]), np.asarray(outs[2][k]), equal_nan=True), k
+
+
 def test_analyze_regions_filters(engine, cpn):
     """pmap_analyze_reg's data filters (nanopore.jl:309,322-326): regions failing them keep proc == false."""
     nb = cpn.simulations.make_nano_batch(5, M=30, seed=3)
