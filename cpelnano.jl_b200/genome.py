@@ -1,0 +1,153 @@
+"""Genome-side inputs of the estimation path: FASTA → estimation regions → CpG sites, CpG groups and densities.
+
+Host-side mirror of ("next" row):
+
+    get_genome_info / get_chr_fa_rec      src/genome_analysis.jl:19-61, :283-312   → read_fasta
+    get_cpg_grps                          src/genome_analysis.jl:63-111            → cpg_groups
+    get_ρn                                src/genome_analysis.jl:122-140           → inside grp_info (prefix counts, not regex)
+    get_grp_info!                         src/genome_analysis.jl:226-277           → grp_info / region_features
+    get_chr_part (whole chr / BED)        src/genome_analysis.jl:327-390, :391-458 → chr_part
+
+Integer work, bit-exact by construction: CpG positions are found once per chromosome on the byte array and every
+window count of the reference (one regex scan of a 1 kb window per CpG) becomes two binary searches into that array.
+Outputs are pinned by the reference's golden theta files (α, β reproduce exactly; tests/test_host_inputs.py).
+Coordinates are 1-based closed, as in the reference.
+"""
+import gzip
+
+import numpy as np
+
+from .host import RegStruct
+
+
+def read_fasta(path):
+    """{record name: upper/lower-case sequence string as bytes array (uint8)} in file order."""
+    opener = gzip.open if str(path).endswith(".gz") else open
+    recs, name, chunks = {}, None, []
+    with opener(path, "rt") as f:
+        for line in f:
+            if line.startswith(">"):
+                if name is not None:
+                    recs[name] = np.frombuffer("".join(chunks).encode(), dtype=np.uint8)
+                name, chunks = line[1:].split()[0], []
+            else:
+                chunks.append(line.strip())
+    if name is not None:
+        recs[name] = np.frombuffer("".join(chunks).encode(), dtype=np.uint8)
+    return recs
+
+
+def cpg_starts(seq):
+    """1-based positions of the C of every CG dinucleotide (the regex r"[Cc][Gg]" of the reference; matches cannot overlap)."""
+    up = seq & 0xDF                                              # ASCII upper-case
+    return (np.nonzero((up[:-1] == ord("C")) & (up[1:] == ord("G")))[0] + 1).astype(np.int64)
+
+
+def cpg_groups(cpg_pos, min_grp_dist):
+    """get_cpg_grps (genome_analysis.jl:63-111): consecutive CpGs closer than or at min_grp_dist share a group.
+    Returns (first, last) 0-based inclusive index arrays; the group interval is [pos[first]-5, pos[last]+5]."""
+    cpg_pos = np.asarray(cpg_pos, dtype=np.int64)
+    if len(cpg_pos) == 0:
+        return np.zeros(0, dtype=np.int64), np.zeros(0, dtype=np.int64)
+    brk = np.nonzero(np.diff(cpg_pos) > min_grp_dist)[0]
+    first = np.concatenate([[0], brk + 1]).astype(np.int64)
+    last = np.concatenate([brk, [len(cpg_pos) - 1]]).astype(np.int64)
+    return first, last
+
+
+class Chromosome:
+    """One FASTA record with its CpG index."""
+
+    def __init__(self, name, seq):
+        self.name, self.seq, self.size = name, seq, len(seq)
+        self.cg = cpg_starts(seq)
+
+    def cpgs_in(self, st, end):
+        """CG matches lying completely inside seq[st..end] (what a regex scan of that substring finds)."""
+        lo = np.searchsorted(self.cg, st, side="left")
+        hi = np.searchsorted(self.cg, end - 1, side="right")
+        return lo, max(lo, hi)
+
+    # ---- get_chr_part ---------------------------------------------------------------------------------------------------
+    def chr_part(self, size_est_reg=3000, min_grp_dist=10, targets=None):
+        """Estimation regions of the chromosome (targets=None, :327-390) or of BED intervals [(st, end), …] (:391-458):
+        windows of size_est_reg whose right boundary is moved off any CpG group it would split."""
+        spans = [(1, self.size)] if targets is None else list(targets)
+        part = []
+        for (reg_st, reg_end) in spans:
+            i = reg_st
+            while i < reg_end:
+                bndy = i + size_est_reg - 1
+                if bndy >= reg_end:
+                    part.append((i, reg_end))
+                    break
+                lo, hi = self.cpgs_in(bndy - 1000, min(self.size, bndy + 1000))
+                if hi > lo:
+                    pos = self.cg[lo:hi]
+                    first, last = cpg_groups(pos, min_grp_dist)
+                    a, b = pos[first] - 5, pos[last] + 5
+                    hit = np.nonzero((a <= bndy) & (bndy <= b))[0]
+                    if len(hit):
+                        a0, b0 = int(a[hit[0]]), int(b[hit[0]])
+                        bndy = b0 + 2 if 2 * bndy - a0 > b0 else a0 - 1
+                part.append((i, bndy))
+                i = bndy + 1
+        return part
+
+    # ---- get_grp_info! ---------------------------------------------------------------------------------------------------
+    def grp_info(self, chrst, chrend, min_grp_dist=10):
+        """CpG sites of [chrst, chrend], their densities ρ_n (CpGs per bp in a ±500 bp window clipped to the region's ±500 bp
+        context, :122-140, :249-255), distances, and the CpG groups with N_l, ρ_l (mean of ρ_n, sum then divide) and d_l."""
+        lo, hi = self.cpgs_in(chrst, chrend)
+        cpg_pos = self.cg[lo:hi].copy()
+        out = dict(cpg_pos=cpg_pos, N=len(cpg_pos))
+        if len(cpg_pos) <= 1:
+            return out
+        cont_st, cont_end = max(1, chrst - 500), min(self.size, chrend + 500)
+        clen = cont_end - cont_st + 1
+        o = cpg_pos - cont_st                                   # the offset the reference hands to get_ρn
+        win_st = np.maximum(1, o - 500) + cont_st - 1           # window in chromosome coordinates
+        win_end = np.minimum(clen, o + 500) + cont_st - 1
+        cnt = np.searchsorted(self.cg, win_end - 1, side="right") - np.searchsorted(self.cg, win_st, side="left")
+        rho_n = np.maximum(cnt, 0) / 1000
+        first, last = cpg_groups(cpg_pos, min_grp_dist)
+        Nl = (last - first + 1).astype(np.float64)
+        # sum(ρ_n[first:last]) / N_l with the reference's left-to-right sum (cumulative-sum differences are not bit-identical);
+        # groups are short, so add one column of group members at a time
+        rho_l = rho_n[first].copy()
+        for k in range(1, int(Nl.max())):
+            more = Nl > k
+            rho_l[more] += rho_n[first[more] + k]
+        rho_l /= Nl
+        d_l = (cpg_pos[first[1:]] - cpg_pos[last[:-1]]).astype(np.float64)
+        out.update(rho_n=rho_n, d_n=np.diff(cpg_pos).astype(np.float64), Nl=Nl, rho_l=rho_l, d_l=d_l, grp_first=first, grp_last=last,
+                   grp_st=cpg_pos[first] - 5, grp_end=cpg_pos[last] + 5)
+        return out
+
+    def region_struct(self, chrst, chrend, min_grp_dist=10):
+        """RegStruct with the genomic fields get_grp_info! fills (group scale); calls are added by nanopolish.attach_calls."""
+        gi = self.grp_info(chrst, chrend, min_grp_dist)
+        rs = RegStruct(chr=self.name, chrst=int(chrst), chrend=int(chrend), N=int(gi["N"]), cpg_pos=gi["cpg_pos"])
+        if gi["N"] > 1:
+            rs.L = len(gi["Nl"])
+            rs.Nl, rs.rho_l, rs.dl, rs.rho_n, rs.dn = gi["Nl"], gi["rho_l"], gi["d_l"], gi["rho_n"], gi["d_n"]
+            rs.grp_st, rs.grp_end = gi["grp_st"], gi["grp_end"]
+        return rs
+
+
+def read_bed(path):
+    """read_bed_reg (src/input_output.jl:494-525): {chr: [(st, end), …]} in file order; lines with end < st are dropped."""
+    regs = {}
+    with open(path) as f:
+        for line in f:
+            v = line.rstrip("\n").split("\t")
+            if len(v) < 3:
+                continue
+            st, end = int(v[1]), int(v[2])
+            if end >= st:
+                regs.setdefault(v[0], []).append((st, end))
+    return regs
+
+
+def load_genome(path):
+    return {name: Chromosome(name, seq) for name, seq in read_fasta(path).items()}
