@@ -1,0 +1,110 @@
+"""User entry points of the reference, file in → file out, with the per-region `pmap` bodies replaced by one device batch
+per chromosome (SURVEY.md §8b "batch points"):
+
+    analyze_nano(nano, fasta, config)                          src/nanopore.jl:362-416
+    diff_grp_comp(mod_fls_g1, mod_fls_g2, fasta, config)       src/grp_perm_tests.jl:637-687
+
+Same arguments, same output files (outputs.py restates Julia's number formatting).  Two documented differences, both about
+ORDER only: the reference iterates Julia `Dict`s (reads of a region in get_calls_nanopolish!, common regions in
+find_comm_regs), whose order depends on the Julia build; here reads follow their first appearance in the calls file and
+common regions are written in coordinate order.  Host work (FASTA scan, calls parsing) is genome.py / nanopolish.py; every
+number comes from libcpelnano_b200.so.
+"""
+import os
+
+import numpy as np
+
+from . import genome, outputs
+from .host import default_engine, analyze_regions
+from .nanopolish import NanopolishCalls
+
+
+def _print_log(config, msg):
+    if getattr(config, "verbose", False):
+        print(f"[cpelnano_b200] {msg}", flush=True)
+
+
+def _outputs_exist(paths):
+    """check_output_exists / check_diff_output_exists (src/input_output.jl:36-88): any existing output file stops the run."""
+    return any(os.path.exists(p) for p in paths)
+
+
+def analyze_nano(nano, fasta, config, out_dir, out_prefix, bed_reg=None, mod_nse=True, rng=None, phi0_fn=None, engine=None):
+    """Estimate ϕ̂ for every estimation region of every chromosome and write theta / ex / exx / mml / nme files.
+    out_dir, out_prefix, bed_reg, mod_nse are fields of the reference's config struct (src/structures.jl:36-69) passed
+    explicitly here.  phi0_fn(n_regions) → [n, max_em_init, 3] replaces the unseeded gen_ϕ0s draws (tests); default: rng.
+    Returns the list of processed RegStructs (the reference returns nothing)."""
+    eng = engine or default_engine()
+    chroms = genome.load_genome(fasta)
+    os.makedirs(out_dir, exist_ok=True)
+    files = outputs.OutputFiles(out_dir, out_prefix)
+    if _outputs_exist(files.all()):
+        return None
+    targets = genome.read_bed(bed_reg) if bed_reg else None
+    calls = NanopolishCalls(nano)
+    done = []
+    for name, chrom in chroms.items():
+        if targets is not None and name not in targets:
+            continue
+        part = chrom.chr_part(config.size_est_reg, config.min_grp_dist, None if targets is None else targets[name])
+        _print_log(config, f"chr {name}: {len(part)} estimation regions")
+        regs = []
+        for (st, end) in part:
+            rs = chrom.region_struct(st, end, config.min_grp_dist)
+            if len(rs.cpg_pos) > 9:                      # pmap_analyze_reg returns before get_calls! otherwise (:308)
+                calls.attach_calls(rs, mod_nse)
+            regs.append(rs)
+        cand = [rs for rs in regs if len(rs.cpg_pos) > 9]
+        phi0s = None
+        if phi0_fn is not None:
+            phi0s = phi0_fn(len(cand))
+        analyze_regions(cand, config, phi0s=phi0s, rng=rng, engine=eng)
+        # write_output_ϕ runs after rscle_grp_mod!, so the theta file holds the per-CpG α, β (as the reference's does)
+        outputs.write_output(regs, files)
+        done.extend(rs for rs in regs if rs.proc)
+    return done
+
+
+def _find_comm_regs(ms_g1, ms_g2):
+    """find_comm_regs (src/grp_perm_tests.jl:527-556): region ids present in at least one sample of each group."""
+    k1 = set().union(*[set(d) for d in ms_g1]) if ms_g1 else set()
+    k2 = set().union(*[set(d) for d in ms_g2]) if ms_g2 else set()
+    return k1 & k2
+
+
+def diff_grp_comp(mod_fls_g1, mod_fls_g2, fasta, config, out_dir, out_prefix, rng=None, engine=None):
+    """Group comparison from model (theta) files: per chromosome read every sample's ϕ̂, find the common regions, run
+    unmat_est_reg_test / mat_est_reg_test (config.matched) for all of them on the device, write tmml / tnme / tcmd and add BH
+    q-values.  Regions are batched by their (n1, n2) sample counts (one cpn_grp_test_batch call per distinct pair)."""
+    eng = engine or default_engine()
+    chroms = genome.load_genome(fasta)
+    os.makedirs(out_dir, exist_ok=True)
+    files = outputs.OutputDiffFiles(out_dir, out_prefix)
+    if _outputs_exist(files.all()):
+        return None
+    for name, chrom in chroms.items():
+        ms_g1 = [outputs.read_mod_file_chr(f, chrom, config, eng, summaries=False) for f in mod_fls_g1]
+        ms_g2 = [outputs.read_mod_file_chr(f, chrom, config, eng, summaries=False) for f in mod_fls_g2]
+        comm = _find_comm_regs(ms_g1, ms_g2)
+        if not comm:
+            continue
+        batches = {}
+        for rid in comm:
+            if config.matched:                           # pairs present in both groups (:576-586)
+                reps = [i for i in range(min(len(ms_g1), len(ms_g2))) if rid in ms_g1[i] and rid in ms_g2[i]]
+                g1, g2 = [ms_g1[i][rid] for i in reps], [ms_g2[i][rid] for i in reps]
+            else:
+                g1, g2 = [d[rid] for d in ms_g1 if rid in d], [d[rid] for d in ms_g2 if rid in d]
+            if not g1 or not g2:
+                continue
+            batches.setdefault((len(g1), len(g2)), []).append((g1[0].chrst, g1[0].chrend, g1, g2))
+        tests, keys = [], []
+        for (n1, n2), items in batches.items():
+            items.sort(key=lambda t: (t[0], t[1]))
+            out = eng.grp_comp_batch([t[2] for t in items], [t[3] for t in items], matched=config.matched, rng=rng)
+            tests.extend(out); keys.extend((t[0], t[1]) for t in items)
+        order = sorted(range(len(tests)), key=lambda i: keys[i])
+        tests = [tests[i] for i in order]
+        outputs.write_diff_output([name] * len(tests), tests, files, matched=config.matched)
+    outputs.mult_hyp_corr(files, matched=config.matched)
+    return files

@@ -1,0 +1,110 @@
+"""Output text and BH correction against the reference's own golden files.
+
+The golden files were written by Julia: every floating-point token in them is Julia's `string(::Float64)`.  Parsing a token
+and printing it with outputs.julia_str must give the token back; BH q-values recomputed from the golden p columns must
+print to the golden q columns.  GPU-side end-to-end file comparisons are in test_pipeline_gpu.py.
+"""
+import io
+import os
+import tarfile
+
+import numpy as np
+import pytest
+
+import cpelnano_b200 as cpn
+from cpelnano_b200 import outputs
+
+INP = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "inputs")
+
+
+@pytest.fixture(scope="module")
+def golden():
+    out = {}
+    with tarfile.open(os.path.join(INP, "golden_outputs.tar.gz")) as tar:
+        for m in tar.getmembers():
+            out[m.name] = tar.extractfile(m).read().decode()
+    return out
+
+
+def _float_tokens(text, first_col):
+    for line in text.splitlines():
+        for field in line.split("\t")[first_col:]:
+            for tok in field.split(","):
+                yield tok
+
+
+def test_julia_float_text_round_trips_every_golden_number(golden):
+    n = 0
+    for name, text in golden.items():
+        for tok in _float_tokens(text, 3):
+            assert outputs.julia_str(float(tok)) == tok, (name, tok)
+            n += 1
+    assert n > 20_000
+
+
+def test_julia_float_text_special_cases():
+    cases = {1.0: "1.0", 100000.0: "100000.0", 1e6: "1.0e6", 1234567.0: "1.234567e6", 1e-5: "1.0e-5", 0.0001: "0.0001",
+             -3.25e-7: "-3.25e-7", 1e22: "1.0e22", 5e-324: "5.0e-324", 0.1 + 0.2: "0.30000000000000004", -0.0: "-0.0",
+             float("inf"): "Inf", float("-inf"): "-Inf", 2.0 ** 70: "1.1805916207174113e21", 999999.9: "999999.9"}
+    for x, s in cases.items():
+        assert outputs.julia_str(x) == s
+    assert outputs.julia_str(float("nan")) == "NaN"
+
+
+def test_julia_round_ties_to_even_on_the_scaled_value():
+    assert outputs.julia_round(0.00005) == np.rint(0.00005 * 1e4) / 1e4
+    assert outputs.julia_round(2.5, 0) == 2.0 and outputs.julia_round(3.5, 0) == 4.0
+    assert outputs.julia_round(-0.93145) == -0.9314 or outputs.julia_round(-0.93145) == -0.9315   # whichever x·1e4 rounds to
+    assert outputs.julia_round(0.12344999) == 0.1234
+
+
+@pytest.mark.parametrize("name", ["unmat_tmml", "unmat_tnme", "unmat_tcmd", "mat_tmml", "mat_tnme"])
+def test_bh_qvalues_reprint_the_golden_q_column(golden, name):
+    rows = [l.split("\t") for l in golden[f"grp_comp_example/tests/cpelnano_grp_comp_{name}.txt"].splitlines()]
+    p = np.array([float(r[4]) for r in rows])
+    q = outputs.bh_adjust(p)
+    assert [outputs.julia_str(v) for v in q] == [r[5] for r in rows]
+
+
+def test_bh_properties():
+    rng = np.random.default_rng(1)
+    p = rng.random(1000)
+    q = outputs.bh_adjust(p)
+    o = np.argsort(p)
+    assert np.all(np.diff(q[o]) >= 0) and np.all(q >= p) and q.max() <= 1.0
+    assert np.array_equal(outputs.bh_adjust([0.2]), [0.2]) and len(outputs.bh_adjust([])) == 0
+
+
+def test_add_qvalues_rewrites_file_like_the_reference(golden, tmp_path):
+    """Strip the q column of a golden file, run add_qvalues_to_path: the file must come back byte-identical (NaN p-values of
+    the matched Tcmd file are never corrected: mult_hyp_corr skips it, src/multiple_hypothesis.jl:60)."""
+    text = golden["grp_comp_example/tests/cpelnano_grp_comp_unmat_tnme.txt"]
+    path = tmp_path / "t_tnme.txt"
+    path.write_text("".join("\t".join(l.split("\t")[:5]) + "\n" for l in text.splitlines()))
+    outputs.add_qvalues_to_path(str(path))
+    assert path.read_text() == text
+    empty = tmp_path / "empty.txt"
+    empty.write_text("")
+    outputs.add_qvalues_to_path(str(empty))
+    assert empty.read_text() == ""
+
+
+def test_theta_reader_and_alpha_beta_print_identically(golden, tmp_path):
+    """read_theta_lines + genome features + get_αβ_from_ϕ + julia_str reproduce the golden theta file byte for byte
+    (the α, β columns are per-CpG: write_output_ϕ runs after rscle_grp_mod!)."""
+    from cpelnano_b200 import genome
+    text = golden["full_example/cpelnano/full_example_mod_nse_true_theta.txt"]
+    src = tmp_path / "theta.txt"
+    src.write_text(text)
+    chrom = genome.load_genome(os.path.join(INP, "full_example.fa.gz"))["hg38_dna"]
+    regs = []
+    for (c, st, end, phi) in outputs.read_theta_lines(str(src), "hg38_dna"):
+        rs = chrom.region_struct(st, end)
+        rs.phihat = phi
+        cpn.rscle_grp_mod(rs)
+        rs.proc = True
+        regs.append(rs)
+    assert len(regs) == 27
+    dst = tmp_path / "out_theta.txt"
+    outputs.write_output_phi(str(dst), regs)
+    assert dst.read_text() == text

@@ -1,0 +1,120 @@
+"""File-in → file-out entry points on the GPU against the reference's golden output FILES (run with -m gpu).
+
+  * diff_grp_comp on the bundled 6 vs 6 model files (recipe: calls/GeneralTesting/permutation_tests_tests.jl:118-156) must
+    write the golden tmml / tnme rows character for character (T at 4 dp, exact p from the full 924-labeling / 64-sign sweeps, BH q)
+    and the golden T column of tcmd; unmatched Tcmd p-values may differ by one count of 924 where complementary labelings tie
+    at the last ulp (the reference's own result there depends on its summation order).
+  * summaries recomputed from the golden theta file must re-write the golden ex / exx / mml / nme files: mml / nme (rounded
+    to 4 dp) byte for byte, E[X] / E[XX] (full precision) to 1e-12.
+  * analyze_nano on the bundled full_example calls selects exactly the golden file's 27 regions (integer filters, bit-exact),
+    converges on all of them, and lands on the golden ϕ̂ as closely as the reference's stopping rule (‖Δϕ‖ ≤ 3e-2, random
+    unseeded starts) allows.
+"""
+import os
+import tarfile
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+INP = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "inputs")
+
+
+@pytest.fixture(scope="module")
+def golden_dir(tmp_path_factory):
+    d = tmp_path_factory.mktemp("golden_outputs")
+    with tarfile.open(os.path.join(INP, "golden_outputs.tar.gz")) as tar:
+        tar.extractall(d, filter="data")
+    return str(d)
+
+
+@pytest.fixture(scope="module")
+def fasta_full(tmp_path_factory):
+    return os.path.join(INP, "full_example.fa.gz")
+
+
+def _rows(path, sort=False):
+    rows = [l.rstrip("\n").split("\t") for l in open(path)]
+    return sorted(rows, key=lambda r: (int(r[1]), int(r[2]))) if sort else rows
+
+
+@pytest.mark.parametrize("matched", [False, True])
+def test_diff_grp_comp_writes_the_golden_files(engine, cpn, golden_dir, fasta_full, tmp_path, matched):
+    g1 = [f"{golden_dir}/grp_comp_example/mod_files/g1_rep{i}.txt" for i in range(1, 7)]
+    g2 = [f"{golden_dir}/grp_comp_example/mod_files/g2_rep{i}.txt" for i in range(1, 7)]
+    cfg = cpn.CpelNanoConfig(matched=matched)
+    kind = "mat" if matched else "unmat"
+    files = cpn.diff_grp_comp(g1, g2, fasta_full, cfg, str(tmp_path), f"cpelnano_grp_comp_{kind}", engine=engine)
+    gold = f"{golden_dir}/grp_comp_example/tests/cpelnano_grp_comp_{kind}"
+    for stat in ("tmml", "tnme"):
+        # the reference writes regions in Julia Dict order (find_comm_regs); rows are compared in coordinate order, as text
+        assert _rows(getattr(files, stat + "_file")) == _rows(f"{gold}_{stat}.txt", sort=True), stat
+    got, ref = _rows(files.tcmd_file), _rows(f"{gold}_tcmd.txt", sort=True)
+    assert len(got) == len(ref) == 225
+    if matched:
+        assert got == ref                                     # T only, p = NaN, no q column
+    else:
+        assert [r[:4] for r in got] == [r[:4] for r in ref]   # coordinates and T
+        dp = np.array([float(a[4]) - float(b[4]) for a, b in zip(got, ref)]) * 924
+        assert np.all(np.abs(dp) <= 1.0 + 1e-9), np.abs(dp).max()
+    # an existing output stops a second run (check_diff_output_exists)
+    assert cpn.diff_grp_comp(g1, g2, fasta_full, cfg, str(tmp_path), f"cpelnano_grp_comp_{kind}", engine=engine) is None
+
+
+@pytest.mark.parametrize("example,fa,prefix,mss", [
+    ("targeted_example", "targeted_example.fa.gz", "targeted_example/cpelnano/targeted_example", 351),
+])
+def test_summaries_from_golden_theta_rewrite_the_golden_files(engine, cpn, golden_dir, tmp_path, example, fa, prefix, mss):
+    from cpelnano_b200 import genome, outputs
+    chrom = genome.load_genome(os.path.join(INP, fa))["hg38_dna"]
+    cfg = cpn.CpelNanoConfig(max_size_subreg=mss)             # 5-argument ctor of the example stores 350 + 1
+    regs = outputs.read_mod_file_chr(f"{golden_dir}/{prefix}_theta.txt", chrom, cfg, engine)
+    regs = sorted(regs.values(), key=lambda r: r.chrst)
+    files = outputs.OutputFiles(str(tmp_path), example)
+    outputs.write_output(regs, files)
+    assert open(files.theta_file).read() == open(f"{golden_dir}/{prefix}_theta.txt").read()
+    assert open(files.mml_file).read() == open(f"{golden_dir}/{prefix}_mml.txt").read()
+    assert open(files.nme_file).read() == open(f"{golden_dir}/{prefix}_nme.txt").read()
+    # the golden ex / exx files hold four appended runs of the example (open(path, "a")), only the last of which belongs to the
+    # golden theta file: a row written here must equal one of the golden rows with the same coordinates
+    for stat in ("ex", "exx"):
+        ref = {}
+        for r in _rows(f"{golden_dir}/{prefix}_{stat}.txt"):
+            ref.setdefault((r[0], r[1], r[2]), []).append(float(r[3]))
+        got = _rows(getattr(files, stat + "_file"))
+        assert len(got) == sum(r.N - (stat == "exx") for r in regs) and {tuple(r[:3]) for r in got} <= set(ref)
+        d = np.array([min(abs(float(r[3]) - v) for v in ref[tuple(r[:3])]) for r in got])
+        assert d.max() <= 1e-12, d.max()
+
+
+def test_analyze_nano_full_example(engine, cpn, golden_dir, fasta_full, tmp_path):
+    from cpelnano_b200 import outputs
+    cfg = cpn.CpelNanoConfig()                                # defaults: min_cov 10, 10 starts, ≤ 20 EM iterations
+    rng = np.random.default_rng(20211111)
+    done = cpn.analyze_nano(os.path.join(INP, "full_example_calls.tsv.gz"), fasta_full, cfg, str(tmp_path), "full_example", rng=rng,
+                            engine=engine)
+    gold = outputs.read_theta_lines(f"{golden_dir}/full_example/cpelnano/full_example_mod_nse_true_theta.txt")
+    mine = outputs.read_theta_lines(str(tmp_path / "full_example_theta.txt"))
+    assert [(g[1], g[2]) for g in mine] == [(g[1], g[2]) for g in gold]          # the same 27 regions, in order
+    assert len(done) == 27
+    dphi = np.array([m[3] - g[3] for m, g in zip(mine, gold)])
+    # the golden run used different (unseeded) starts: same optimum up to the EM stopping rule on most regions
+    med = np.median(np.abs(dphi), axis=0)
+    assert med[0] <= 0.02 and med[1] <= 1.0 and med[2] <= 0.5, med
+    # outputs are internally consistent: mml file has one row per non-empty sub-region, all within [0, 1]
+    mml = np.array([float(r[3]) for r in _rows(tmp_path / "full_example_mml.txt")])
+    nme = np.array([float(r[3]) for r in _rows(tmp_path / "full_example_nme.txt")])
+    assert len(mml) == len(nme) > 200 and mml.min() >= 0.0 and mml.max() <= 1.0 and nme.min() >= 0.0 and nme.max() <= 1.0
+    # the MML of the golden model and of this fit agree closely (MML is a smooth function of the optimum)
+    with open(tmp_path / "gold_theta.txt", "w") as f:
+        f.write(open(f"{golden_dir}/full_example/cpelnano/full_example_mod_nse_true_theta.txt").read())
+    from cpelnano_b200 import genome
+    chrom = genome.load_genome(fasta_full)["hg38_dna"]
+    gregs = sorted(outputs.read_mod_file_chr(str(tmp_path / "gold_theta.txt"), chrom, cfg, engine).values(), key=lambda r: r.chrst)
+    gm = np.concatenate([r.mml[~np.isnan(r.mml)] for r in gregs])
+    assert len(gm) == len(mml) and np.median(np.abs(gm - mml)) <= 0.01, np.median(np.abs(gm - mml))
+    # mod_nse = false: hard emissions (0, −50) go through the same kernels (the WGBS-style likelihood, src/CpelNano.jl:32-33)
+    done2 = cpn.analyze_nano(os.path.join(INP, "full_example_calls.tsv.gz"), fasta_full, cfg, str(tmp_path), "full_example_hard",
+                             mod_nse=False, rng=np.random.default_rng(1), engine=engine)
+    assert len(done2) >= 20
