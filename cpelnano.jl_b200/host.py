@@ -434,6 +434,62 @@ class Engine:
         out.update(pval=p.reshape(3, K), cnt=cnt.reshape(3, K), n_valid=nv.reshape(3, K), exact=exact, T_null=T_null)
         return out
 
+    def diff_two_samp_comp_batch(self, items, config, rng=None, perms=None, phi0s=None):
+        """pmap_diff_two_samp_comp for many regions: items = [(mod_s1, mod_s2, calls_s1, calls_s2)], models at per-CpG scale with
+        summaries.  Observed CMDs in one call, the null refits of ALL regions in one cpn_two_samp_null_batch call, p-value counts
+        in one cpn_two_samp_pvals call per distinct (number of permutations, exact) pair.  perms / phi0s: optional per-region
+        lists (tests); default: all C(n, n1) splits when fewer than config.LMAX_TWO_SAMP, else LMAX_TWO_SAMP sorted samples."""
+        import copy
+        R = len(items)
+        if R == 0:
+            return []
+        models, pairs = [], []
+        for (m1, m2, _, _) in items:
+            pairs.append((len(models), len(models) + 1)); models.extend([m1, m2])
+        cmds = self.comp_cmd_pairs(models, pairs)
+        outs, todo = [], []
+        for i, (m1, m2, c1, c2) in enumerate(items):
+            K = m1.nls_rgs.num
+            T_obs = np.stack([m1.mml - m2.mml, m1.nme - m2.nme, cmds[i]])
+            outs.append(dict(T=T_obs, pval=np.full((3, K), np.nan), cnt=None, n_valid=None, exact=None, coords=m1.nls_rgs))
+            if not config.pval_comp:
+                continue
+            n1, n2 = c1[0].shape[0], c2[0].shape[0]
+            if n1 == 0 or n2 == 0:
+                continue
+            Lc = math.comb(n1 + n2, n1)
+            if Lc <= 20:
+                continue
+            exact = Lc < config.LMAX_TWO_SAMP
+            if perms is not None and perms[i] is not None:
+                pr = np.asarray(perms[i], dtype=np.int64)
+            elif exact:
+                pr = np.array(list(combinations(range(1, n1 + n2 + 1), n1)), dtype=np.int64)
+            else:    # sort!(StatsBase.sample(1:n, n1; replace=false)) LMAX_TWO_SAMP times (:211-214)
+                rng = rng or np.random.default_rng()
+                pr = np.stack([np.sort(rng.choice(np.arange(1, n1 + n2 + 1), n1, replace=False)) for _ in range(config.LMAX_TWO_SAMP)])
+            ref = copy.copy(m1.group_view if m1.group_view is not None else m1)    # "back to group scale" (:198-199)
+            ref.nls_rgs, ref.rho_n, ref.dn, ref.N = m1.nls_rgs, m1.rho_n, m1.dn, m1.N
+            todo.append((i, ref, pr, exact))
+        if not todo:
+            return outs
+        T_nulls = self.two_samp_null_stats_device([(ref, items[i][2], items[i][3], pr) for (i, ref, pr, _) in todo], config,
+                                                  None if phi0s is None else [phi0s[i] for (i, _, _, _) in todo], rng)
+        groups = {}
+        for j, (i, ref, pr, exact) in enumerate(todo):
+            groups.setdefault((len(pr), exact), []).append(j)
+        for (P, exact), js in groups.items():
+            Ks = [outs[todo[j][0]]["T"].shape[1] for j in js]
+            tbl_off = np.concatenate([[0], np.cumsum(Ks)]).astype(np.int64)
+            T_obs = np.concatenate([outs[todo[j][0]]["T"].reshape(-1) for j in js])
+            T_null = np.concatenate([T_nulls[j].reshape(-1) for j in js])
+            cnt, nv, p = self.lib.two_samp_pvals(tbl_off, P, T_obs, T_null, exact, device=self.device)
+            for a, j in enumerate(js):
+                i, K = todo[j][0], Ks[a]
+                sl = slice(3 * tbl_off[a], 3 * tbl_off[a + 1])
+                outs[i].update(pval=p[sl].reshape(3, K), cnt=cnt[sl].reshape(3, K), n_valid=nv[sl].reshape(3, K), exact=exact, T_null=T_nulls[j])
+        return outs
+
 
 _default = None
 

@@ -3,6 +3,7 @@ per chromosome (SURVEY.md §8b "batch points"):
 
     analyze_nano(nano, fasta, config)                          src/nanopore.jl:362-416
     diff_grp_comp(mod_fls_g1, mod_fls_g2, fasta, config)       src/grp_perm_tests.jl:637-687
+    diff_two_samp_comp(mod1, mod2, nano1, nano2, fasta, config) src/two_samp_perm_tests.jl:408-460
 
 Same arguments, same output files (outputs.py restates Julia's number formatting).  Two documented differences, both about
 ORDER only: the reference iterates Julia `Dict`s (reads of a region in get_calls_nanopolish!, common regions in
@@ -107,4 +108,41 @@ def diff_grp_comp(mod_fls_g1, mod_fls_g2, fasta, config, out_dir, out_prefix, rn
         tests = [tests[i] for i in order]
         outputs.write_diff_output([name] * len(tests), tests, files, matched=config.matched)
     outputs.mult_hyp_corr(files, matched=config.matched)
+    return files
+
+
+def diff_two_samp_comp(mods_path_s1, mods_path_s2, nano_s1, nano_s2, fasta, config, out_dir, out_prefix, mod_nse=True, rng=None,
+                       engine=None):
+    """Two-sample comparison from two model files and the two samples' calls: observed Tmml / Tnme / Tcmd per sub-region, and
+    (config.pval_comp) permutation p-values from refits of the pooled reads — every region of a chromosome in one device
+    batch (the reference maps serially over regions and pmaps over permutations, :445 / :220).  BH q-values only when
+    p-values were computed (:452-455)."""
+    eng = engine or default_engine()
+    chroms = genome.load_genome(fasta)
+    os.makedirs(out_dir, exist_ok=True)
+    files = outputs.OutputDiffFiles(out_dir, out_prefix)
+    if _outputs_exist(files.all()):
+        return None
+    calls1 = NanopolishCalls(nano_s1) if config.pval_comp else None
+    calls2 = (calls1 if nano_s2 == nano_s1 else NanopolishCalls(nano_s2)) if config.pval_comp else None
+    for name, chrom in chroms.items():
+        m1 = outputs.read_mod_file_chr(mods_path_s1, chrom, config, eng)
+        m2 = outputs.read_mod_file_chr(mods_path_s2, chrom, config, eng)
+        comm = sorted(set(m1) & set(m2), key=lambda k: (m1[k].chrst, m1[k].chrend))
+        if not comm:
+            continue
+        items = []
+        for rid in comm:
+            a, b = m1[rid], m2[rid]
+            if config.pval_comp:                         # get_calls! on the GROUP intervals of the region (:187-188)
+                ga, gb = a.group_view or a, b.group_view or b
+                c1 = calls1.region_calls(a.chr, a.chrst, a.chrend, ga.grp_st, ga.grp_end, mod_nse)[:2]
+                c2 = calls2.region_calls(b.chr, b.chrst, b.chrend, gb.grp_st, gb.grp_end, mod_nse)[:2]
+            else:
+                c1 = c2 = (np.zeros((0, 0)), np.zeros((0, 0)))
+            items.append((a, b, c1, c2))
+        tests = eng.diff_two_samp_comp_batch(items, config, rng=rng)
+        outputs.write_diff_output([name] * len(tests), tests, files, matched=False)
+    if config.pval_comp:
+        outputs.mult_hyp_corr(files, matched=False)
     return files

@@ -118,3 +118,25 @@ def test_analyze_nano_full_example(engine, cpn, golden_dir, fasta_full, tmp_path
     done2 = cpn.analyze_nano(os.path.join(INP, "full_example_calls.tsv.gz"), fasta_full, cfg, str(tmp_path), "full_example_hard",
                              mod_nse=False, rng=np.random.default_rng(1), engine=engine)
     assert len(done2) >= 20
+
+
+def test_diff_two_samp_comp_same_sample_reproduces_the_golden_files(engine, cpn, golden_dir, fasta_full, tmp_path):
+    """Recipe of calls/GeneralTesting/permutation_tests_tests.jl:160-190: a sample against itself (4 regions of the full
+    example, 4 starts, ≤ 25 EM iterations).  T = 0 for every statistic, every valid permutation statistic is ≥ 0 in absolute
+    value, so p = (1+n)/(1+n) = 1 and q = 1: the golden files are fully determined and must be reproduced as text."""
+    theta = tmp_path / "two_samp_theta.txt"
+    lines = open(f"{golden_dir}/full_example/cpelnano/full_example_mod_nse_true_theta.txt").read().splitlines()[:4]
+    theta.write_text("".join("\t".join(l.split("\t")[:4]) + "\n" for l in lines))      # model files may omit α, β (4 columns)
+    nano = os.path.join(INP, "full_example_calls.tsv.gz")
+    cfg = cpn.CpelNanoConfig(max_em_iters=25, max_em_init=4, pval_comp=True)
+    files = cpn.diff_two_samp_comp(str(theta), str(theta), nano, nano, fasta_full, cfg, str(tmp_path), "cpelnano_two_samp",
+                                   rng=np.random.default_rng(5), engine=engine)
+    for stat in ("tmml", "tnme", "tcmd"):
+        got = _rows(getattr(files, stat + "_file"))
+        ref = _rows(f"{golden_dir}/two_samp_example/tests/cpelnano_two_samp_{stat}.txt", sort=True)
+        assert got == ref, stat
+    # without p-values: T columns only, p = NaN, no q column (two_samp_perm_tests.jl:452)
+    cfg2 = cpn.CpelNanoConfig(pval_comp=False)
+    files2 = cpn.diff_two_samp_comp(str(theta), str(theta), nano, nano, fasta_full, cfg2, str(tmp_path), "no_pvals", engine=engine)
+    rows = _rows(files2.tmml_file)
+    assert len(rows) == 34 and all(r[3] == "0.0" and r[4] == "NaN" and len(r) == 5 for r in rows)
