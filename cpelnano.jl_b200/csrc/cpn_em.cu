@@ -1640,6 +1640,9 @@ static int fit_chunked(cpn_ctx* ctx, bool on_device, int64_t R, const int64_t* g
     // CPN_WORKERS=0 disables chunking; CPN_CHUNKS / CPN_CHUNK_RATIO / CPN_CHUNK_REGIONS tune the plan.
     const int n_workers = std::max(0, env_int("CPN_WORKERS", 2));
     const int64_t chunk_regions = std::max(1, env_int("CPN_CHUNK_REGIONS", 12500));
+    // no chunk holds more than CPN_MAX_CHUNK_REGIONS regions: the staging arenas (one per chunk in flight, ≈ 33 KB per region)
+    // stay bounded however large the batch is — a whole genome (3·10⁶ regions) runs as 12 chunks through the same five arenas
+    const int64_t max_chunk_regions = std::max(1, env_int("CPN_MAX_CHUNK_REGIONS", 250000));
     int C = (int)((R > 0 && grp_off_in && read_off_in && n_workers >= 1) ? std::min<int64_t>(R / chunk_regions, 4) : 0);
     if (on_device) C = std::min(C, 1);     // measured: concurrent chunks do not beat one full-width batch (97.3 vs 97.1 ms per 1e5 regions)
     const char* cvar = on_device ? "CPN_DEVICE_CHUNKS" : "CPN_CHUNKS";
@@ -1684,6 +1687,21 @@ static int fit_chunked(cpn_ctx* ctx, bool on_device, int64_t R, const int64_t* g
             int64_t target = (int64_t)((double)obs[R] * (acc / total));
             bnd[c] = std::lower_bound(obs.begin(), obs.end(), target) - obs.begin();
             bnd[c] = std::min(std::max(bnd[c], bnd[c - 1]), R);
+        }
+    }
+    {   // enforce the region cap: the geometric plan is kept while it respects it; from the first chunk that would exceed it on,
+        // chunks of exactly the cap follow until the batch is covered
+        bool over = false;
+        for (int c = 0; c < C; ++c) over = over || (bnd[c + 1] - bnd[c] > max_chunk_regions);
+        if (over) {
+            std::vector<int64_t> nb{0};
+            for (int c = 0; c < C && nb.back() < R; ++c) {
+                if (bnd[c + 1] - nb.back() > max_chunk_regions) break;
+                if (bnd[c + 1] > nb.back()) nb.push_back(bnd[c + 1]);
+            }
+            while (nb.back() < R) nb.push_back(std::min(R, nb.back() + max_chunk_regions));
+            bnd = nb;
+            C = (int)bnd.size() - 1;
         }
     }
     // children[0] stages chunks (host→device copies and the packing kernels) ahead of the W compute workers children[1..W]

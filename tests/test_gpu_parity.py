@@ -582,6 +582,14 @@ def test_host_entry_points_chunked_equals_single_stream(engine, cpn, monkeypatch
         for k in out1:
             assert np.array_equal(np.asarray(out1[k]), np.asarray(out2[k]), equal_nan=True), (workers, k)
     assert engine.lib.last_launches() > 0
+    # the region cap on a chunk (whole-genome batches): plan of 3 chunks over 90 regions, no chunk may exceed 7 → the geometric
+    # head is dropped and 13 capped chunks run through the same arenas
+    monkeypatch.setenv("CPN_WORKERS", "2"); monkeypatch.setenv("CPN_CHUNK_REGIONS", "20"); monkeypatch.setenv("CPN_CHUNKS", "3")
+    monkeypatch.setenv("CPN_CHUNK_RATIO", "1.3"); monkeypatch.setenv("CPN_MAX_CHUNK_REGIONS", "7")
+    fit3, out3 = run()
+    for k in out1:
+        assert np.array_equal(np.asarray(out1[k]), np.asarray(out3[k]), equal_nan=True), ("cap", k)
+    monkeypatch.delenv("CPN_MAX_CHUNK_REGIONS")
     # device-resident inputs are cut into chunks too (offsets fetched to the host once)
     monkeypatch.setenv("CPN_DEVICE_CHUNKS", "3")
     dev = _analyze_device(engine, cpn, nb, phi0, n_init, sub_off, sub_p, sub_q)
