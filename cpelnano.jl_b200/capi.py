@@ -14,7 +14,9 @@ MSTEP_FD, MSTEP_ANALYTIC = 0, 1
 # every exported symbol of include/cpelnano_b200.h (tests check the library exports exactly these)
 SYMBOLS = ["cpn_create", "cpn_destroy", "cpn_last_error", "cpn_version", "cpn_last_device_ms", "cpn_last_launches",
            "cpn_measure_fp64_peak", "cpn_set_profile", "cpn_get_profile", "cpn_analyze_batch", "cpn_analyze_batch_device", "cpn_fit_batch", "cpn_fit_batch_device", "cpn_estep_batch", "cpn_mstep_batch",
-           "cpn_stat_sums_batch", "cpn_nls_reg_info", "cpn_cmd_batch", "cpn_grp_unmat_sweep", "cpn_grp_mat_sweep", "cpn_two_samp_pvals", "cpn_two_samp_null_batch", "cpn_grp_test_batch"]
+           "cpn_stat_sums_batch", "cpn_nls_reg_info", "cpn_cmd_batch", "cpn_grp_unmat_sweep", "cpn_grp_mat_sweep", "cpn_two_samp_pvals", "cpn_two_samp_null_batch", "cpn_grp_test_batch",
+           "cpn_calls_open", "cpn_calls_close", "cpn_calls_open_error", "cpn_calls_error", "cpn_calls_num_lines", "cpn_calls_num_reads", "cpn_calls_num_chr",
+           "cpn_calls_chr_name", "cpn_calls_chr_lines", "cpn_calls_read_name", "cpn_calls_count_reads", "cpn_calls_fill"]
 
 
 class CpnError(RuntimeError):
@@ -66,6 +68,15 @@ class Library:
         d.cpn_create.argtypes = [C.c_int, C.POINTER(C.c_void_p)]
         d.cpn_destroy.argtypes = [C.c_void_p]
         d.cpn_nls_reg_info.restype = C.c_int64
+        for f in ("cpn_calls_open_error", "cpn_calls_error", "cpn_calls_chr_name", "cpn_calls_read_name"):
+            getattr(d, f).restype = C.c_char_p
+        for f in ("cpn_calls_num_lines", "cpn_calls_num_reads", "cpn_calls_num_chr", "cpn_calls_chr_lines"):
+            getattr(d, f).restype = C.c_int64
+        d.cpn_calls_open.argtypes = [C.c_char_p, C.c_int32, C.POINTER(C.c_void_p)]
+        d.cpn_calls_close.argtypes = [C.c_void_p]
+        d.cpn_calls_error.argtypes = [C.c_void_p]
+        d.cpn_calls_num_lines.argtypes = d.cpn_calls_num_reads.argtypes = d.cpn_calls_num_chr.argtypes = [C.c_void_p]
+        d.cpn_calls_chr_name.argtypes = d.cpn_calls_chr_lines.argtypes = d.cpn_calls_read_name.argtypes = [C.c_void_p, C.c_int64]
         self._ctx = {}
 
     def version(self):
@@ -320,3 +331,59 @@ class Library:
                                          _ptr(nv), _ptr(p))
         self._check(rc, ctx)
         return cnt, nv, p
+
+
+class CallsHandle:
+    """cpn_calls: a nanopolish calls file parsed once by the native loader (csrc/cpn_calls.cpp).  Host-only — works without a GPU."""
+
+    def __init__(self, lib, path, n_threads=0):
+        self.lib = lib
+        h = C.c_void_p()
+        rc = lib.dll.cpn_calls_open(str(path).encode(), C.c_int32(n_threads), C.byref(h))
+        if rc != 0 or not h.value:
+            raise CpnError(f"cpn_calls_open failed with code {rc}: {lib.dll.cpn_calls_open_error().decode()}")
+        self.h = h
+        d = lib.dll
+        self.n_lines = int(d.cpn_calls_num_lines(h))
+        self.n_reads = int(d.cpn_calls_num_reads(h))
+        self.chromosomes = {d.cpn_calls_chr_name(h, C.c_int64(i)).decode(): int(d.cpn_calls_chr_lines(h, C.c_int64(i)))
+                            for i in range(int(d.cpn_calls_num_chr(h)))}
+
+    def close(self):
+        if self.h is not None:
+            self.lib.dll.cpn_calls_close(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def read_name(self, read_id):
+        return self.lib.dll.cpn_calls_read_name(self.h, C.c_int64(int(read_id))).decode()
+
+    def count_reads(self, chrom, chrst, chrend, n_threads=0):
+        chrst, chrend = _i64(chrst), _i64(chrend)
+        n = np.empty(len(chrst), dtype=np.int64)
+        rc = self.lib.dll.cpn_calls_count_reads(self.h, chrom.encode(), C.c_int64(len(chrst)), _ptr(chrst), _ptr(chrend), C.c_int32(n_threads), _ptr(n))
+        if rc != 0:
+            raise CpnError(f"cpn_calls_count_reads error {rc}: {self.lib.dll.cpn_calls_error(self.h).decode()}")
+        return n
+
+    def fill(self, chrom, chrst, chrend, grp_off, grp_st, grp_end, mod_nse=True, read_off=None, n_threads=0, want_ids=False):
+        """→ (read_off [R+1], log_pyx_u, log_pyx_m[, read_ids]) in the CSR layout of cpn_fit_batch."""
+        chrst, chrend, grp_off, grp_st, grp_end = _i64(chrst), _i64(chrend), _i64(grp_off), _i64(grp_st), _i64(grp_end)
+        R = len(chrst)
+        if read_off is None:
+            read_off = np.concatenate([[0], np.cumsum(self.count_reads(chrom, chrst, chrend, n_threads))]).astype(np.int64)
+        read_off = _i64(read_off)
+        n_obs = int(np.sum(np.diff(read_off) * np.diff(grp_off))) if R else 0
+        lu, lm = np.empty(n_obs), np.empty(n_obs)
+        ids = np.empty(int(read_off[-1]) if R else 0, dtype=np.int64)
+        rc = self.lib.dll.cpn_calls_fill(self.h, chrom.encode(), C.c_int64(R), _ptr(chrst), _ptr(chrend), _ptr(grp_off), _ptr(grp_st), _ptr(grp_end),
+                                         C.c_int32(int(bool(mod_nse))), _ptr(read_off), C.c_int32(n_threads), _ptr(lu), _ptr(lm),
+                                         _ptr(ids) if want_ids else None)
+        if rc != 0:
+            raise CpnError(f"cpn_calls_fill error {rc}: {self.lib.dll.cpn_calls_error(self.h).decode()}")
+        return (read_off, lu, lm, ids) if want_ids else (read_off, lu, lm)

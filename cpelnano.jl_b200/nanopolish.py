@@ -43,8 +43,9 @@ class NanopolishCalls:
                 g = g.iloc[np.argsort(start, kind="stable")]
                 start = g["start"].to_numpy()
             codes, names = pd.factorize(g["read"], sort=False)
-            self.by_chr[name] = dict(start=start, end=g["end"].to_numpy(), read=codes.astype(np.int64), names=np.asarray(names),
-                                     lm=g["lm"].to_numpy(), lu=g["lu"].to_numpy())
+            end = g["end"].to_numpy()
+            self.by_chr[name] = dict(start=start, end=end, read=codes.astype(np.int64), names=np.asarray(names),
+                                     lm=g["lm"].to_numpy(), lu=g["lu"].to_numpy(), max_span=int((end - start).max()) if len(end) else 0)
 
     def region_calls(self, chrom, chrst, chrend, grp_st, grp_end, mod_nse=True):
         """(lu, lm, read_names): [m, L] matrices with NaN where a group is not observed in a read."""
@@ -53,7 +54,8 @@ class NanopolishCalls:
         if c is None:
             return np.zeros((0, L)), np.zeros((0, L)), np.zeros(0, dtype=object)
         hi = np.searchsorted(c["start"], chrend, side="right")            # start ≤ chrend (file sorted by start)
-        sel = np.nonzero(c["end"][:hi] >= chrst)[0]                        # end ≥ chrst
+        lo = np.searchsorted(c["start"], chrst - c["max_span"], side="left")   # end ≥ chrst needs start ≥ chrst − longest call
+        sel = lo + np.nonzero(c["end"][lo:hi] >= chrst)[0]                 # end ≥ chrst
         if len(sel) == 0:
             return np.zeros((0, L)), np.zeros((0, L)), np.zeros(0, dtype=object)
         reads = c["read"][sel]
@@ -83,6 +85,48 @@ class NanopolishCalls:
         rs.set_calls(lu, lm)
         rs.read_names = names
         return rs
+
+
+class NativeCalls:
+    """Same contract as NanopolishCalls on top of the native loader (csrc/cpn_calls.cpp through the C ABI: cpn_calls_open /
+    cpn_calls_count_reads / cpn_calls_fill): the file is parsed once by all host threads, and the calls of ALL regions of a
+    chromosome are written in one call, directly in the CSR layout cpn_fit_batch takes."""
+
+    def __init__(self, path, library=None, n_threads=0):
+        from .capi import Library, CallsHandle
+        self.handle = CallsHandle(library or Library(), path, n_threads)
+        self.n_lines = self.handle.n_lines
+        self.n_threads = n_threads
+
+    def region_calls(self, chrom, chrst, chrend, grp_st, grp_end, mod_nse=True):
+        L = len(grp_st)
+        read_off, lu, lm, ids = self.handle.fill(chrom, [chrst], [chrend], [0, L], grp_st, grp_end, mod_nse, n_threads=1, want_ids=True)
+        m = int(read_off[1])
+        return lu.reshape(m, L), lm.reshape(m, L), np.array([self.handle.read_name(i) for i in ids], dtype=object)
+
+    def attach_calls(self, rs, mod_nse=True):
+        lu, lm, names = self.region_calls(rs.chr, rs.chrst, rs.chrend, rs.grp_st, rs.grp_end, mod_nse)
+        rs.set_calls(lu, lm)
+        rs.read_names = names
+        return rs
+
+    def attach_calls_batch(self, regs, mod_nse=True):
+        """get_calls! for a list of RegStructs of ONE chromosome (group-scale features set) in two native calls."""
+        if not regs:
+            return regs
+        chrom = regs[0].chr
+        assert all(r.chr == chrom for r in regs)
+        Ls = [len(r.grp_st) for r in regs]
+        grp_off = np.concatenate([[0], np.cumsum(Ls)]).astype(np.int64)
+        read_off, lu, lm = self.handle.fill(chrom, [r.chrst for r in regs], [r.chrend for r in regs], grp_off,
+                                            np.concatenate([r.grp_st for r in regs]), np.concatenate([r.grp_end for r in regs]), mod_nse,
+                                            n_threads=self.n_threads)
+        o = 0
+        for i, r in enumerate(regs):
+            m, L = int(read_off[i + 1] - read_off[i]), Ls[i]
+            r.set_calls(lu[o:o + m * L].reshape(m, L), lm[o:o + m * L].reshape(m, L))
+            o += m * L
+        return regs
 
 
 def region_calls_reference(path, chrom, chrst, chrend, grp_st, grp_end, mod_nse=True):

@@ -8,8 +8,8 @@ per chromosome (SURVEY.md §8b "batch points"):
 Same arguments, same output files (outputs.py restates Julia's number formatting).  Two documented differences, both about
 ORDER only: the reference iterates Julia `Dict`s (reads of a region in get_calls_nanopolish!, common regions in
 find_comm_regs), whose order depends on the Julia build; here reads follow their first appearance in the calls file and
-common regions are written in coordinate order.  Host work (FASTA scan, calls parsing) is genome.py / nanopolish.py; every
-number comes from libcpelnano_b200.so.
+common regions are written in coordinate order.  Host work: FASTA scan in genome.py, calls parsing by the native loader (csrc/cpn_calls.cpp via
+nanopolish.NativeCalls); every number comes from libcpelnano_b200.so.
 """
 import os
 
@@ -17,7 +17,7 @@ import numpy as np
 
 from . import genome, outputs
 from .host import default_engine, analyze_regions
-from .nanopolish import NanopolishCalls
+from .nanopolish import NativeCalls
 
 
 def _print_log(config, msg):
@@ -42,20 +42,16 @@ def analyze_nano(nano, fasta, config, out_dir, out_prefix, bed_reg=None, mod_nse
     if _outputs_exist(files.all()):
         return None
     targets = genome.read_bed(bed_reg) if bed_reg else None
-    calls = NanopolishCalls(nano)
+    calls = NativeCalls(nano, eng.lib)
     done = []
     for name, chrom in chroms.items():
         if targets is not None and name not in targets:
             continue
         part = chrom.chr_part(config.size_est_reg, config.min_grp_dist, None if targets is None else targets[name])
         _print_log(config, f"chr {name}: {len(part)} estimation regions")
-        regs = []
-        for (st, end) in part:
-            rs = chrom.region_struct(st, end, config.min_grp_dist)
-            if len(rs.cpg_pos) > 9:                      # pmap_analyze_reg returns before get_calls! otherwise (:308)
-                calls.attach_calls(rs, mod_nse)
-            regs.append(rs)
-        cand = [rs for rs in regs if len(rs.cpg_pos) > 9]
+        regs = [chrom.region_struct(st, end, config.min_grp_dist) for (st, end) in part]
+        cand = [rs for rs in regs if len(rs.cpg_pos) > 9]      # pmap_analyze_reg returns before get_calls! otherwise (:308)
+        calls.attach_calls_batch(cand, mod_nse)
         phi0s = None
         if phi0_fn is not None:
             phi0s = phi0_fn(len(cand))
@@ -123,8 +119,8 @@ def diff_two_samp_comp(mods_path_s1, mods_path_s2, nano_s1, nano_s2, fasta, conf
     files = outputs.OutputDiffFiles(out_dir, out_prefix)
     if _outputs_exist(files.all()):
         return None
-    calls1 = NanopolishCalls(nano_s1) if config.pval_comp else None
-    calls2 = (calls1 if nano_s2 == nano_s1 else NanopolishCalls(nano_s2)) if config.pval_comp else None
+    calls1 = NativeCalls(nano_s1, eng.lib) if config.pval_comp else None
+    calls2 = (calls1 if nano_s2 == nano_s1 else NativeCalls(nano_s2, eng.lib)) if config.pval_comp else None
     for name, chrom in chroms.items():
         m1 = outputs.read_mod_file_chr(mods_path_s1, chrom, config, eng)
         m2 = outputs.read_mod_file_chr(mods_path_s2, chrom, config, eng)

@@ -220,6 +220,40 @@ int cpn_two_samp_null_batch(cpn_ctx* ctx, int64_t R, const int64_t* grp_off, con
 int cpn_two_samp_pvals(cpn_ctx* ctx, int64_t R, const int64_t* tbl_off, int64_t P, const double* T_obs,
                        const double* T_null, int32_t exact, int64_t* cnt, int64_t* n_valid, double* pval);
 
+/* ---- calls ingestion (host only, no GPU needed) ---------------------------------------------------------------------
+ * Replaces get_dic_nanopolish (src/input_output.jl:536-570: the TSV is re-read from the top for every region) and
+ * get_calls_nanopolish! (src/nanopore.jl:172-230: linear findfirst over the CpG groups per call) — i.e. get_calls!
+ * (src/nanopore.jl:241-257) for ALL regions of a chromosome in two calls.  cpn_calls_open parses a nanopolish
+ * call-methylation TSV (plain or .gz; first line = header; columns 1 chr, 3 start, 4 end, 5 read name, 7 log_lik_methylated,
+ * 8 log_lik_unmethylated) once, with n_threads threads (0 = all), into columns per chromosome.  Decimal text is converted
+ * correctly rounded, as parse(Float64, ·).  The handle is read-only afterwards and may be shared by threads.
+ *   cpn_calls_count_reads  n_reads[r] = reads with at least one line on `chr` with start <= chrend[r] and end >= chrst[r]
+ *                          (every such read becomes a row, rs.m, even if none of its lines matches a group)
+ *   cpn_calls_fill         read_off [R+1] = exclusive cumulative sum of n_reads; grp_off/grp_st/grp_end: CSR of the regions'
+ *                          CpG-group intervals (grp_int = [first CpG - 5, last CpG + 5], src/genome_analysis.jl:63-111);
+ *                          writes log_pyx_u / log_pyx_m in the layout cpn_fit_batch takes (read-major [m_r x L_r] per region,
+ *                          NaN = not observed); a line's group is the one with grp_st == start+1-5 and grp_end == end+1+5;
+ *                          later lines overwrite earlier ones; mod_nse == 0 stores (0, -50) for the likelier state
+ *                          (src/CpelNano.jl:32-33).  Rows are in order of first appearance in the file (the reference: Julia
+ *                          Dict order).  read_ids (optional) [sum m_r]: index of each row's read for cpn_calls_read_name.
+ * Errors: cpn_calls_open returns non-zero and leaves the text in cpn_calls_open_error() (thread-local).               */
+typedef struct cpn_calls cpn_calls;
+int  cpn_calls_open(const char* path, int32_t n_threads, cpn_calls** out);
+void cpn_calls_close(cpn_calls* calls);
+const char* cpn_calls_open_error(void);
+const char* cpn_calls_error(const cpn_calls* calls);
+int64_t cpn_calls_num_lines(const cpn_calls* calls);
+int64_t cpn_calls_num_reads(const cpn_calls* calls);
+int64_t cpn_calls_num_chr(const cpn_calls* calls);
+const char* cpn_calls_chr_name(const cpn_calls* calls, int64_t i);
+int64_t cpn_calls_chr_lines(const cpn_calls* calls, int64_t i);
+const char* cpn_calls_read_name(const cpn_calls* calls, int64_t read_id);
+int cpn_calls_count_reads(const cpn_calls* calls, const char* chr, int64_t R, const int64_t* chrst, const int64_t* chrend,
+                          int32_t n_threads, int64_t* n_reads);
+int cpn_calls_fill(const cpn_calls* calls, const char* chr, int64_t R, const int64_t* chrst, const int64_t* chrend,
+                   const int64_t* grp_off, const int64_t* grp_st, const int64_t* grp_end, int32_t mod_nse,
+                   const int64_t* read_off, int32_t n_threads, double* log_pyx_u, double* log_pyx_m, int64_t* read_ids);
+
 #ifdef __cplusplus
 }
 #endif
