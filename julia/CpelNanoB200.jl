@@ -130,6 +130,53 @@ function grp_test_batch(ms_g1::Vector{Vector{RegStruct}}, ms_g2::Vector{Vector{R
     return matched ? (T, cnt, p, tcmd, sub_off) : (T, cnt, p, sub_off)
 end
 
+# ---- calls ingestion: get_calls!(rs, nano, config) (nanopore.jl:241-257) for all regions of a chromosome --------------------
+# get_dic_nanopolish re-reads the TSV for every region (input_output.jl:536-570); the native loader parses it once
+# (cpn_calls_open, all threads) and fills every region's calls in two calls.  CALLS caches the handle per file.
+const CALLS = Dict{String,Ptr{Cvoid}}()
+function calls_handle(nano::String)
+    haskey(CALLS, nano) && return CALLS[nano]
+    h = Ref{Ptr{Cvoid}}(C_NULL)
+    rc = ccall((:cpn_calls_open, LIB[]), Cint, (Cstring, Int32, Ref{Ptr{Cvoid}}), nano, 0, h)
+    rc == 0 || error(unsafe_string(ccall((:cpn_calls_open_error, LIB[]), Cstring, ())))
+    CALLS[nano] = h[]
+end
+
+function get_calls_batch!(rss::Vector{RegStruct}, nano::String, config::CpelNanoConfig)
+    isempty(rss) && return nothing
+    h = calls_handle(nano)
+    R = length(rss)
+    chrst = Int64[rs.chrst for rs in rss]; chrend = Int64[rs.chrend for rs in rss]
+    grp_off = cumsum(vcat(0, [length(rs.cpg_grps) for rs in rss]))
+    grp_st = Int64[minimum(g.grp_int) for rs in rss for g in rs.cpg_grps]
+    grp_end = Int64[maximum(g.grp_int) for rs in rss for g in rs.cpg_grps]
+    n_reads = Vector{Int64}(undef, R)
+    chr = rss[1].chr
+    rc = ccall((:cpn_calls_count_reads, LIB[]), Cint, (Ptr{Cvoid}, Cstring, Int64, Ptr{Int64}, Ptr{Int64}, Int32, Ptr{Int64}),
+               h, chr, R, chrst, chrend, 0, n_reads)
+    rc == 0 || error(unsafe_string(ccall((:cpn_calls_error, LIB[]), Cstring, (Ptr{Cvoid},), h)))
+    read_off = cumsum(vcat(0, n_reads))
+    n_obs = sum(n_reads .* diff(grp_off))
+    lu = Vector{Float64}(undef, n_obs); lm = Vector{Float64}(undef, n_obs)
+    rc = ccall((:cpn_calls_fill, LIB[]), Cint,
+               (Ptr{Cvoid}, Cstring, Int64, Ptr{Int64}, Ptr{Int64}, Ptr{Int64}, Ptr{Int64}, Ptr{Int64}, Int32, Ptr{Int64}, Int32,
+                Ptr{Float64}, Ptr{Float64}, Ptr{Int64}),
+               h, chr, R, chrst, chrend, grp_off, grp_st, grp_end, config.mod_nse ? 1 : 0, read_off, 0, lu, lm, C_NULL)
+    rc == 0 || error(unsafe_string(ccall((:cpn_calls_error, LIB[]), Cstring, (Ptr{Cvoid},), h)))
+    # (lu, lm, read_off, grp_off) are already the arrays cpn_fit_batch takes; RegStruct.calls is rebuilt only for callers that
+    # still walk the boxed objects (get_ave_depth, perc_gprs_obs: structures.jl:200-203)
+    o = 0
+    for (i, rs) in enumerate(rss)
+        L = grp_off[i+1] - grp_off[i]; rs.m = n_reads[i]
+        rs.calls = [[begin
+                         u = lu[o + (m-1)*L + l]
+                         isnan(u) ? MethCallCpgGrp() : MethCallCpgGrp(u, lm[o + (m-1)*L + l])     # (log_pyx_u, log_pyx_m) ctor, structures.jl:127
+                     end for l in 1:L] for m in 1:rs.m]
+        o += rs.m * L
+    end
+    return nothing
+end
+
 # ---- batch point: replaces `pmap(x -> pmap_analyze_reg(x, chr, nano, fa_rec, config), chr_part)`  nanopore.jl:406 -----
 function analyze_chr(chr_part, chr, nano, fa_rec, config::CpelNanoConfig)
     rss = RegStruct[]
@@ -137,9 +184,8 @@ function analyze_chr(chr_part, chr, nano, fa_rec, config::CpelNanoConfig)
         rs = RegStruct(); rs.chr = chr; rs.chrst = minimum(reg_int); rs.chrend = maximum(reg_int)
         get_grp_info!(rs, fa_rec, config.min_grp_dist)
         push!(rss, rs)
-        length(rs.cpg_pos) > 9 || continue
-        get_calls!(rs, nano, config)
     end
+    get_calls_batch!([rs for rs in rss if length(rs.cpg_pos) > 9], nano, config)     # was: get_calls!(rs, nano, config) per region
     keep = [rs for rs in rss if length(rs.cpg_pos) > 9 && rs.m > 0 && get_ave_depth(rs) >= config.min_cov &&
                                 perc_gprs_obs(rs) >= 0.66 && rs.L > 1]
     isempty(keep) && return rss
