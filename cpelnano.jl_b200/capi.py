@@ -16,7 +16,8 @@ SYMBOLS = ["cpn_create", "cpn_destroy", "cpn_last_error", "cpn_version", "cpn_la
            "cpn_measure_fp64_peak", "cpn_set_profile", "cpn_get_profile", "cpn_analyze_batch", "cpn_analyze_batch_device", "cpn_fit_batch", "cpn_fit_batch_device", "cpn_estep_batch", "cpn_mstep_batch",
            "cpn_stat_sums_batch", "cpn_nls_reg_info", "cpn_cmd_batch", "cpn_grp_unmat_sweep", "cpn_grp_mat_sweep", "cpn_two_samp_pvals", "cpn_two_samp_null_batch", "cpn_grp_test_batch",
            "cpn_calls_open", "cpn_calls_close", "cpn_calls_open_error", "cpn_calls_error", "cpn_calls_num_lines", "cpn_calls_num_reads", "cpn_calls_num_chr",
-           "cpn_calls_chr_name", "cpn_calls_chr_lines", "cpn_calls_read_name", "cpn_calls_count_reads", "cpn_calls_fill"]
+           "cpn_calls_chr_name", "cpn_calls_chr_lines", "cpn_calls_read_name", "cpn_calls_count_reads", "cpn_calls_fill",
+           "cpn_cpg_scan", "cpn_chr_part", "cpn_grp_info_count", "cpn_grp_info_fill"]
 
 
 class CpnError(RuntimeError):
@@ -72,6 +73,7 @@ class Library:
             getattr(d, f).restype = C.c_char_p
         for f in ("cpn_calls_num_lines", "cpn_calls_num_reads", "cpn_calls_num_chr", "cpn_calls_chr_lines"):
             getattr(d, f).restype = C.c_int64
+        d.cpn_cpg_scan.restype = d.cpn_chr_part.restype = C.c_int64
         d.cpn_calls_open.argtypes = [C.c_char_p, C.c_int32, C.POINTER(C.c_void_p)]
         d.cpn_calls_close.argtypes = [C.c_void_p]
         d.cpn_calls_error.argtypes = [C.c_void_p]
@@ -331,6 +333,51 @@ class Library:
                                          _ptr(nv), _ptr(p))
         self._check(rc, ctx)
         return cnt, nv, p
+
+
+# ---- genome features (host only) ------------------------------------------------------------------------------------------
+def cpg_scan(lib, seq, n_threads=0):
+    """1-based positions of every CG in a uint8 sequence array (cpn_cpg_scan)."""
+    seq = np.ascontiguousarray(seq, dtype=np.uint8)
+    n = lib.dll.cpn_cpg_scan(_ptr(seq), C.c_int64(len(seq)), C.c_int32(n_threads), None, C.c_int64(0))
+    out = np.empty(max(int(n), 0), dtype=np.int64)
+    if n > 0:
+        lib.dll.cpn_cpg_scan(_ptr(seq), C.c_int64(len(seq)), C.c_int32(n_threads), _ptr(out), C.c_int64(len(out)))
+    return out
+
+
+def chr_part(lib, cg, chr_size, reg_st, reg_end, size_est_reg=3000, min_grp_dist=10):
+    cg = _i64(cg)
+    a = (_ptr(cg), C.c_int64(len(cg)), C.c_int64(chr_size), C.c_int64(reg_st), C.c_int64(reg_end), C.c_int64(size_est_reg), C.c_int64(min_grp_dist))
+    k = int(lib.dll.cpn_chr_part(*a, None, None, C.c_int64(0)))
+    st, en = np.empty(k, dtype=np.int64), np.empty(k, dtype=np.int64)
+    if k > 0:
+        lib.dll.cpn_chr_part(*a, _ptr(st), _ptr(en), C.c_int64(k))
+    return st, en
+
+
+def grp_info_batch(lib, cg, chr_size, chrst, chrend, min_grp_dist=10, n_threads=0):
+    """get_grp_info! for R regions: dict of CSR arrays (cpg_off, grp_off, cpg_pos, rho_n, d_n, Nl, rho_l, d_l, grp_st, grp_end)."""
+    cg, chrst, chrend = _i64(cg), _i64(chrst), _i64(chrend)
+    R = len(chrst)
+    N, L = np.empty(R, dtype=np.int64), np.empty(R, dtype=np.int64)
+    rc = lib.dll.cpn_grp_info_count(_ptr(cg), C.c_int64(len(cg)), C.c_int64(R), _ptr(chrst), _ptr(chrend), C.c_int64(min_grp_dist), C.c_int32(n_threads),
+                                    _ptr(N), _ptr(L))
+    if rc != 0:
+        raise CpnError(f"cpn_grp_info_count error {rc}")
+    cpg_off = np.concatenate([[0], np.cumsum(N)]).astype(np.int64); grp_off = np.concatenate([[0], np.cumsum(L)]).astype(np.int64)
+    sN, sL = int(cpg_off[-1]), int(grp_off[-1])
+    o = dict(cpg_off=cpg_off, grp_off=grp_off, cpg_pos=np.empty(sN, dtype=np.int64), rho_n=np.empty(sN), d_n=np.empty(int(np.maximum(N - 1, 0).sum())),
+             Nl=np.empty(sL), rho_l=np.empty(sL), d_l=np.empty(int(np.maximum(L - 1, 0).sum())), grp_st=np.empty(sL, dtype=np.int64),
+             grp_end=np.empty(sL, dtype=np.int64))
+    rc = lib.dll.cpn_grp_info_fill(_ptr(cg), C.c_int64(len(cg)), C.c_int64(chr_size), C.c_int64(R), _ptr(chrst), _ptr(chrend), C.c_int64(min_grp_dist),
+                                   _ptr(cpg_off), _ptr(grp_off), C.c_int32(n_threads), _ptr(o["cpg_pos"]), _ptr(o["rho_n"]), _ptr(o["d_n"]), _ptr(o["Nl"]),
+                                   _ptr(o["rho_l"]), _ptr(o["d_l"]), _ptr(o["grp_st"]), _ptr(o["grp_end"]))
+    if rc != 0:
+        raise CpnError(f"cpn_grp_info_fill error {rc}")
+    o["dn_off"] = np.concatenate([[0], np.cumsum(np.maximum(N - 1, 0))]).astype(np.int64)
+    o["dl_off"] = np.concatenate([[0], np.cumsum(np.maximum(L - 1, 0))]).astype(np.int64)
+    return o
 
 
 class CallsHandle:

@@ -58,9 +58,13 @@ def cpg_groups(cpg_pos, min_grp_dist):
 class Chromosome:
     """One FASTA record with its CpG index."""
 
-    def __init__(self, name, seq):
+    def __init__(self, name, seq, lib=None):
         self.name, self.seq, self.size = name, seq, len(seq)
-        self.cg = cpg_starts(seq)
+        if lib is not None:
+            from . import capi
+            self.cg = capi.cpg_scan(lib, seq)       # native, multi-threaded (cpn_cpg_scan)
+        else:
+            self.cg = cpg_starts(seq)
 
     def cpgs_in(self, st, end):
         """CG matches lying completely inside seq[st..end] (what a regex scan of that substring finds)."""
@@ -85,7 +89,8 @@ class Chromosome:
                 if hi > lo:
                     pos = self.cg[lo:hi]
                     first, last = cpg_groups(pos, min_grp_dist)
-                    a, b = pos[first] - 5, pos[last] + 5
+                    pad = 0 if len(pos) == 1 else 5          # a lone CpG's interval is returned unpadded (early return, :67)
+                    a, b = pos[first] - pad, pos[last] + pad
                     hit = np.nonzero((a <= bndy) & (bndy <= b))[0]
                     if len(hit):
                         a0, b0 = int(a[hit[0]]), int(b[hit[0]])
@@ -135,6 +140,36 @@ class Chromosome:
         return rs
 
 
+    # ---- native batch path (csrc/cpn_genome.cpp through the C ABI) --------------------------------------------------------
+    def chr_part_native(self, lib, size_est_reg=3000, min_grp_dist=10, targets=None):
+        from . import capi
+        spans = [(1, self.size)] if targets is None else list(targets)
+        part = []
+        for (a, b) in spans:
+            st, en = capi.chr_part(lib, self.cg, self.size, a, b, size_est_reg, min_grp_dist)
+            part.extend(zip(st.tolist(), en.tolist()))
+        return part
+
+    def region_structs(self, lib, part, min_grp_dist=10, n_threads=0):
+        """region_struct for every (chrst, chrend) of `part` in two native calls (cpn_grp_info_count / _fill)."""
+        from . import capi
+        if not part:
+            return []
+        st = np.array([p[0] for p in part], dtype=np.int64); en = np.array([p[1] for p in part], dtype=np.int64)
+        o = capi.grp_info_batch(lib, self.cg, self.size, st, en, min_grp_dist, n_threads)
+        regs = []
+        for r in range(len(part)):
+            n0, n1, g0, g1 = o["cpg_off"][r], o["cpg_off"][r + 1], o["grp_off"][r], o["grp_off"][r + 1]
+            rs = RegStruct(chr=self.name, chrst=int(st[r]), chrend=int(en[r]), N=int(n1 - n0), cpg_pos=o["cpg_pos"][n0:n1])
+            if n1 - n0 > 1:
+                rs.L = int(g1 - g0)
+                rs.Nl, rs.rho_l, rs.rho_n = o["Nl"][g0:g1], o["rho_l"][g0:g1], o["rho_n"][n0:n1]
+                rs.dn, rs.dl = o["d_n"][o["dn_off"][r]:o["dn_off"][r + 1]], o["d_l"][o["dl_off"][r]:o["dl_off"][r + 1]]
+                rs.grp_st, rs.grp_end = o["grp_st"][g0:g1], o["grp_end"][g0:g1]
+            regs.append(rs)
+        return regs
+
+
 def read_bed(path):
     """read_bed_reg (src/input_output.jl:494-525): {chr: [(st, end), …]} in file order; lines with end < st are dropped."""
     regs = {}
@@ -149,5 +184,5 @@ def read_bed(path):
     return regs
 
 
-def load_genome(path):
-    return {name: Chromosome(name, seq) for name, seq in read_fasta(path).items()}
+def load_genome(path, lib=None):
+    return {name: Chromosome(name, seq, lib) for name, seq in read_fasta(path).items()}

@@ -8,8 +8,8 @@ per chromosome (SURVEY.md §8b "batch points"):
 Same arguments, same output files (outputs.py restates Julia's number formatting).  Two documented differences, both about
 ORDER only: the reference iterates Julia `Dict`s (reads of a region in get_calls_nanopolish!, common regions in
 find_comm_regs), whose order depends on the Julia build; here reads follow their first appearance in the calls file and
-common regions are written in coordinate order.  Host work: FASTA scan in genome.py, calls parsing by the native loader (csrc/cpn_calls.cpp via
-nanopolish.NativeCalls); every number comes from libcpelnano_b200.so.
+common regions are written in coordinate order.  Host work is native and batched per chromosome: CpG index, partition and region features (csrc/cpn_genome.cpp), calls
+parsing and binning (csrc/cpn_calls.cpp); every number comes from libcpelnano_b200.so.
 """
 import os
 
@@ -36,7 +36,7 @@ def analyze_nano(nano, fasta, config, out_dir, out_prefix, bed_reg=None, mod_nse
     explicitly here.  phi0_fn(n_regions) → [n, max_em_init, 3] replaces the unseeded gen_ϕ0s draws (tests); default: rng.
     Returns the list of processed RegStructs (the reference returns nothing)."""
     eng = engine or default_engine()
-    chroms = genome.load_genome(fasta)
+    chroms = genome.load_genome(fasta, eng.lib)
     os.makedirs(out_dir, exist_ok=True)
     files = outputs.OutputFiles(out_dir, out_prefix)
     if _outputs_exist(files.all()):
@@ -47,9 +47,9 @@ def analyze_nano(nano, fasta, config, out_dir, out_prefix, bed_reg=None, mod_nse
     for name, chrom in chroms.items():
         if targets is not None and name not in targets:
             continue
-        part = chrom.chr_part(config.size_est_reg, config.min_grp_dist, None if targets is None else targets[name])
+        part = chrom.chr_part_native(eng.lib, config.size_est_reg, config.min_grp_dist, None if targets is None else targets[name])
         _print_log(config, f"chr {name}: {len(part)} estimation regions")
-        regs = [chrom.region_struct(st, end, config.min_grp_dist) for (st, end) in part]
+        regs = chrom.region_structs(eng.lib, part, config.min_grp_dist)
         cand = [rs for rs in regs if len(rs.cpg_pos) > 9]      # pmap_analyze_reg returns before get_calls! otherwise (:308)
         calls.attach_calls_batch(cand, mod_nse)
         phi0s = None

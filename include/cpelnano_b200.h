@@ -254,6 +254,28 @@ int cpn_calls_fill(const cpn_calls* calls, const char* chr, int64_t R, const int
                    const int64_t* grp_off, const int64_t* grp_st, const int64_t* grp_end, int32_t mod_nse,
                    const int64_t* read_off, int32_t n_threads, double* log_pyx_u, double* log_pyx_m, int64_t* read_ids);
 
+/* ---- genome features (host only, no GPU needed) -----------------------------------------------------------------------
+ * get_grp_info! (src/genome_analysis.jl:226-277: regex scan of the region, get_grps_from_cgs :63-111, get_ρn :122-140 — a regex
+ * scan of a <= 1 kb window per CpG —, get_ρl/get_dn/get_dl :150-216) and get_chr_part (:327-458) for ALL regions of a chromosome,
+ * from one index of the chromosome's CG dinucleotides.
+ *   cpn_cpg_scan        1-based positions of the C of every CG (case-insensitive) in seq[0..n); returns the count; call with
+ *                       cpg_pos = NULL (or cap too small) to size the output
+ *   cpn_chr_part        estimation regions of [reg_st, reg_end] (whole chromosome: 1, chr_size; BED interval: its ends):
+ *                       windows of size_est_reg whose right boundary is moved off the CpG group containing it; returns the
+ *                       number of regions (call with NULL outputs to size)
+ *   cpn_grp_info_count  N[r] CpG sites and L[r] CpG groups of region r (L = 0 when N <= 1: the reference stops there)
+ *   cpn_grp_info_fill   cpg_off / grp_off = exclusive cumulative sums of N / L; writes cpg_pos, rho_n [sum N], Nl, rho_l, grp_st,
+ *                       grp_end [sum L], d_n [sum max(N-1,0)], d_l [sum max(L-1,0)] — for batches of regions with N > 1 these
+ *                       are exactly the CSR arrays (d_* at off[r]-r) of cpn_fit_batch / cpn_stat_sums_batch.               */
+int64_t cpn_cpg_scan(const char* seq, int64_t n, int32_t n_threads, int64_t* cpg_pos, int64_t cap);
+int64_t cpn_chr_part(const int64_t* cg, int64_t ncg, int64_t chr_size, int64_t reg_st, int64_t reg_end, int64_t size_est_reg,
+                     int64_t min_grp_dist, int64_t* out_st, int64_t* out_end, int64_t cap);
+int cpn_grp_info_count(const int64_t* cg, int64_t ncg, int64_t R, const int64_t* chrst, const int64_t* chrend, int64_t min_grp_dist,
+                       int32_t n_threads, int64_t* N, int64_t* L);
+int cpn_grp_info_fill(const int64_t* cg, int64_t ncg, int64_t chr_size, int64_t R, const int64_t* chrst, const int64_t* chrend,
+                      int64_t min_grp_dist, const int64_t* cpg_off, const int64_t* grp_off, int32_t n_threads, int64_t* cpg_pos,
+                      double* rho_n, double* d_n, double* Nl, double* rho_l, double* d_l, int64_t* grp_st, int64_t* grp_end);
+
 #ifdef __cplusplus
 }
 #endif
