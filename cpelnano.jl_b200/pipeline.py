@@ -30,35 +30,54 @@ def _outputs_exist(paths):
     return any(os.path.exists(p) for p in paths)
 
 
-def analyze_nano(nano, fasta, config, out_dir, out_prefix, bed_reg=None, mod_nse=True, rng=None, phi0_fn=None, engine=None):
+def analyze_nano(nano, fasta, config, out_dir, out_prefix, bed_reg=None, mod_nse=True, rng=None, phi0_fn=None, engine=None, timings=None):
     """Estimate ϕ̂ for every estimation region of every chromosome and write theta / ex / exx / mml / nme files.
     out_dir, out_prefix, bed_reg, mod_nse are fields of the reference's config struct (src/structures.jl:36-69) passed
     explicitly here.  phi0_fn(n_regions) → [n, max_em_init, 3] replaces the unseeded gen_ϕ0s draws (tests); default: rng.
-    Returns the list of processed RegStructs (the reference returns nothing)."""
+    timings: optional dict that receives the wall seconds of each stage.  Returns the list of processed RegStructs (the
+    reference returns nothing)."""
+    import time
+    tm = timings if timings is not None else {}
+
+    def lap(key, t0):
+        tm[key] = tm.get(key, 0.0) + time.perf_counter() - t0
+        return time.perf_counter()
+
     eng = engine or default_engine()
+    t = time.perf_counter()
     chroms = genome.load_genome(fasta, eng.lib)
+    t = lap("fasta_and_cpg_index_s", t)
     os.makedirs(out_dir, exist_ok=True)
     files = outputs.OutputFiles(out_dir, out_prefix)
     if _outputs_exist(files.all()):
         return None
     targets = genome.read_bed(bed_reg) if bed_reg else None
+    t = time.perf_counter()
     calls = NativeCalls(nano, eng.lib)
+    t = lap("calls_parse_s", t)
     done = []
     for name, chrom in chroms.items():
         if targets is not None and name not in targets:
             continue
+        t = time.perf_counter()
         part = chrom.chr_part_native(eng.lib, config.size_est_reg, config.min_grp_dist, None if targets is None else targets[name])
         _print_log(config, f"chr {name}: {len(part)} estimation regions")
         regs = chrom.region_structs(eng.lib, part, config.min_grp_dist)
+        t = lap("partition_and_features_s", t)
         cand = [rs for rs in regs if len(rs.cpg_pos) > 9]      # pmap_analyze_reg returns before get_calls! otherwise (:308)
         calls.attach_calls_batch(cand, mod_nse)
+        t = lap("calls_fill_s", t)
         phi0s = None
         if phi0_fn is not None:
             phi0s = phi0_fn(len(cand))
         analyze_regions(cand, config, phi0s=phi0s, rng=rng, engine=eng)
+        t = lap("fit_and_summaries_s", t)
         # write_output_ϕ runs after rscle_grp_mod!, so the theta file holds the per-CpG α, β (as the reference's does)
         outputs.write_output(regs, files)
+        t = lap("write_outputs_s", t)
         done.extend(rs for rs in regs if rs.proc)
+        tm["regions"] = tm.get("regions", 0) + len(part)
+        tm["regions_fitted"] = tm.get("regions_fitted", 0) + sum(1 for rs in regs if rs.proc)
     return done
 
 

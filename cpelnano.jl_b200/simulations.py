@@ -174,3 +174,40 @@ def gen_grp_phis(rng, phi1, phi2, s1, s2, nse_sc=1.0):
                          rng.integers(0, 21, size=(S, R)) / 100.0], axis=-1)
 
     return phi1[None] + nse_sc * noise(s1), phi2[None] + nse_sc * noise(s2)
+
+
+def layouts_from_fasta(lib, chromosome, size_est_reg=3000, min_grp_dist=10, targets=None):
+    """Layout tables (the `layouts=` argument of make_nano_batch) for every estimation region of a chromosome that passes the
+    N > 9, L > 1 filters of pmap_analyze_reg, from the native feature extraction; also returns the regions' group intervals."""
+    from . import capi
+    part = chromosome.chr_part_native(lib, size_est_reg, min_grp_dist, targets)
+    st = np.array([p[0] for p in part], dtype=np.int64); en = np.array([p[1] for p in part], dtype=np.int64)
+    o = capi.grp_info_batch(lib, chromosome.cg, chromosome.size, st, en, min_grp_dist)
+    N, L = np.diff(o["cpg_off"]), np.diff(o["grp_off"])
+    keep = np.nonzero((N > 9) & (L > 1))[0]
+    cat = lambda v, off: np.concatenate([v[off[r]:off[r + 1]] for r in keep])      # noqa: E731
+    lay = dict(chrst=st[keep], chrend=en[keep], cpg_off=np.concatenate([[0], np.cumsum(N[keep])]).astype(np.int64),
+               grp_off=np.concatenate([[0], np.cumsum(L[keep])]).astype(np.int64), cpg_pos=cat(o["cpg_pos"], o["cpg_off"]),
+               rho_n=cat(o["rho_n"], o["cpg_off"]), d_n=cat(o["d_n"], o["dn_off"]), Nl=cat(o["Nl"], o["grp_off"]),
+               rho_l=cat(o["rho_l"], o["grp_off"]), d_l=cat(o["d_l"], o["dl_off"]))
+    return lay, cat(o["grp_st"], o["grp_off"]), cat(o["grp_end"], o["grp_off"])
+
+
+def write_nanopolish_tsv(path, nb, chrom_name, grp_st, grp_end, fmt=repr):
+    """A NanoBatch as a nanopolish call-methylation file: one line per observed (read, group), sorted by start; reads are
+    region-local and named r<region>_<read>.  grp_st / grp_end are the group intervals of the batch's regions in order (group
+    interval = [first CpG − 5, last CpG + 5], so the 0-based nanopolish start / end are grp_st + 4 / grp_end − 6).  fmt = repr
+    writes doubles that parse back bit-identically; fmt = "{:.2f}".format gives nanopolish's two decimals."""
+    with open(path, "w") as f:
+        f.write("chromosome\tstrand\tstart\tend\tread_name\tlog_lik_ratio\tlog_lik_methylated\tlog_lik_unmethylated\tnum_calling_strands\t"
+                "num_motifs\tsequence\n")
+        for r in range(nb.R):
+            g0, g1 = int(nb.grp_off[r]), int(nb.grp_off[r + 1])
+            L, M = g1 - g0, int(nb.read_off[r + 1] - nb.read_off[r])
+            lu = nb.log_pyx_u[nb.obs_off[r]:nb.obs_off[r + 1]].reshape(M, L); lm = nb.log_pyx_m[nb.obs_off[r]:nb.obs_off[r + 1]].reshape(M, L)
+            for l in range(L):
+                st, en = int(grp_st[g0 + l]) + 4, int(grp_end[g0 + l]) - 6
+                for m in range(M):
+                    if lu[m, l] == lu[m, l]:
+                        f.write(f"{chrom_name}\t+\t{st}\t{en}\tr{r:06d}_{m:03d}\t{fmt(float(lm[m, l] - lu[m, l]))}\t{fmt(float(lm[m, l]))}\t"
+                                f"{fmt(float(lu[m, l]))}\t1\t1\tNNNNNCGNNNNN\n")

@@ -140,3 +140,42 @@ def test_diff_two_samp_comp_same_sample_reproduces_the_golden_files(engine, cpn,
     files2 = cpn.diff_two_samp_comp(str(theta), str(theta), nano, nano, fasta_full, cfg2, str(tmp_path), "no_pvals", engine=engine)
     rows = _rows(files2.tmml_file)
     assert len(rows) == 34 and all(r[3] == "0.0" and r[4] == "NaN" and len(r) == 5 for r in rows)
+
+
+def test_file_pipeline_equals_the_csr_api_bit_for_bit(engine, cpn, tmp_path):
+    """FASTA + calls file → analyze_nano (native CpG index, partition, features, calls loader, batched GPU fit, writers) against
+    cpn_analyze_batch on the arrays the file was written from.  Every group is observed (pobs = 1) so that the file's read
+    order (first appearance) is the batch's read order; doubles are written with 17 significant digits.  Equality is exact."""
+    from cpelnano_b200 import genome, simulations, outputs
+    fa = os.path.join(INP, "targeted_example.fa.gz")
+    chrom = genome.load_genome(fa, engine.lib)["hg38_dna"]
+    lay, grp_st, grp_end = simulations.layouts_from_fasta(engine.lib, chrom)
+    ref = simulations.load_layouts()
+    assert all(np.array_equal(lay[k], ref[k]) for k in ref)                      # native features = the committed, golden-pinned layouts
+    R, n_init = len(lay["chrst"]), 3
+    nb = simulations.make_nano_batch(R, M=20, seed=5, pobs=1.0, layouts=lay)
+    tsv = tmp_path / "calls.tsv"
+    simulations.write_nanopolish_tsv(str(tsv), nb, "hg38_dna", grp_st, grp_end)
+    phi0 = simulations.gen_phi0s(np.random.default_rng(9), R, n_init)
+    cfg = cpn.CpelNanoConfig(max_em_init=n_init)
+    subs = [engine.lib.nls_reg_info(int(nb.chrst[r]), int(nb.chrend[r]), cfg.max_size_subreg, nb.cpg_pos[nb.cpg_off[r]:nb.cpg_off[r + 1]]) for r in range(R)]
+    sub_off = np.concatenate([[0], np.cumsum([len(s[0]) for s in subs])]).astype(np.int64)
+    direct = engine.lib.analyze_batch(nb.grp_off, nb.Nl, nb.rho_l, nb.d_l, nb.read_off, nb.log_pyx_u, nb.log_pyx_m, phi0, n_init, nb.cpg_off,
+                                      nb.rho_n, nb.d_n, sub_off, np.concatenate([s[2] for s in subs]), np.concatenate([s[3] for s in subs]))
+
+    def starts(n):
+        assert n == R
+        return phi0
+
+    done = cpn.analyze_nano(str(tsv), fa, cfg, str(tmp_path), "sim", phi0_fn=starts, engine=engine)
+    ok = np.nonzero(direct["pick"] >= 0)[0]
+    assert len(done) == len(ok) > 100
+    for rs, r in zip(done, ok):
+        assert (rs.chrst, rs.chrend) == (int(nb.chrst[r]), int(nb.chrend[r]))
+        assert np.array_equal(rs.phihat, direct["phi_hat"][r])
+        assert np.array_equal(rs.mml, direct["mml"][sub_off[r]:sub_off[r + 1]], equal_nan=True)
+        assert np.array_equal(rs.nme, direct["nme"][sub_off[r]:sub_off[r + 1]], equal_nan=True)
+        assert np.array_equal(rs.ex, direct["ex"][nb.cpg_off[r]:nb.cpg_off[r + 1]])
+    # and the theta file holds exactly those fits, as text
+    lines = outputs.read_theta_lines(str(tmp_path / "sim_theta.txt"))
+    assert len(lines) == len(ok) and all(np.array_equal(l[3], direct["phi_hat"][r]) for l, r in zip(lines, ok))
