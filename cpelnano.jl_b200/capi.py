@@ -17,7 +17,7 @@ SYMBOLS = ["cpn_create", "cpn_destroy", "cpn_last_error", "cpn_version", "cpn_la
            "cpn_stat_sums_batch", "cpn_nls_reg_info", "cpn_cmd_batch", "cpn_grp_unmat_sweep", "cpn_grp_mat_sweep", "cpn_two_samp_pvals", "cpn_two_samp_null_batch", "cpn_grp_test_batch",
            "cpn_calls_open", "cpn_calls_close", "cpn_calls_open_error", "cpn_calls_error", "cpn_calls_num_lines", "cpn_calls_num_reads", "cpn_calls_num_chr",
            "cpn_calls_chr_name", "cpn_calls_chr_lines", "cpn_calls_read_name", "cpn_calls_count_reads", "cpn_calls_fill",
-           "cpn_cpg_scan", "cpn_chr_part", "cpn_grp_info_count", "cpn_grp_info_fill"]
+           "cpn_cpg_scan", "cpn_chr_part", "cpn_grp_info_count", "cpn_grp_info_fill", "cpn_format_f64", "cpn_write_rows", "cpn_write_theta"]
 
 
 class CpnError(RuntimeError):
@@ -73,7 +73,7 @@ class Library:
             getattr(d, f).restype = C.c_char_p
         for f in ("cpn_calls_num_lines", "cpn_calls_num_reads", "cpn_calls_num_chr", "cpn_calls_chr_lines"):
             getattr(d, f).restype = C.c_int64
-        d.cpn_cpg_scan.restype = d.cpn_chr_part.restype = C.c_int64
+        d.cpn_cpg_scan.restype = d.cpn_chr_part.restype = d.cpn_format_f64.restype = C.c_int64
         d.cpn_calls_open.argtypes = [C.c_char_p, C.c_int32, C.POINTER(C.c_void_p)]
         d.cpn_calls_close.argtypes = [C.c_void_p]
         d.cpn_calls_error.argtypes = [C.c_void_p]
@@ -378,6 +378,34 @@ def grp_info_batch(lib, cg, chr_size, chrst, chrend, min_grp_dist=10, n_threads=
     o["dn_off"] = np.concatenate([[0], np.cumsum(np.maximum(N - 1, 0))]).astype(np.int64)
     o["dl_off"] = np.concatenate([[0], np.cumsum(np.maximum(L - 1, 0))]).astype(np.int64)
     return o
+
+
+# ---- output text (host only) ------------------------------------------------------------------------------------------------
+def format_f64(lib, x, sep=",", digits=-1):
+    """Julia's text of the doubles in x, joined by sep (cpn_format_f64)."""
+    x = _f64(np.atleast_1d(x))
+    n = lib.dll.cpn_format_f64(_ptr(x), C.c_int64(len(x)), C.c_char(sep.encode()), C.c_int32(digits), None, C.c_int64(0))
+    buf = C.create_string_buffer(int(n) + 1)
+    lib.dll.cpn_format_f64(_ptr(x), C.c_int64(len(x)), C.c_char(sep.encode()), C.c_int32(digits), buf, C.c_int64(n))
+    return buf.raw[:n].decode()
+
+
+def write_rows(lib, path, chrom, a, b, v, digits=-1, clamp0=False, w=None):
+    a, b, v = _i64(a), _i64(b), _f64(v)
+    w = None if w is None else _f64(w)
+    rc = lib.dll.cpn_write_rows(str(path).encode(), chrom.encode(), C.c_int64(len(v)), _ptr(a), _ptr(b), _ptr(v), C.c_int32(digits), C.c_int32(int(clamp0)),
+                                _ptr(w))
+    if rc != 0:
+        raise CpnError(f"cpn_write_rows({path}) failed with code {rc}")
+
+
+def write_theta(lib, path, chrom, chrst, chrend, phi, grp_off, Nl, rho_l, d_l):
+    chrst, chrend, grp_off, phi, rho_l, d_l = _i64(chrst), _i64(chrend), _i64(grp_off), _f64(phi), _f64(rho_l), _f64(d_l)
+    Nl = None if Nl is None else _f64(Nl)
+    rc = lib.dll.cpn_write_theta(str(path).encode(), chrom.encode(), C.c_int64(len(chrst)), _ptr(chrst), _ptr(chrend), _ptr(phi), _ptr(grp_off), _ptr(Nl),
+                                 _ptr(rho_l), _ptr(d_l))
+    if rc != 0:
+        raise CpnError(f"cpn_write_theta({path}) failed with code {rc}")
 
 
 class CallsHandle:

@@ -1,0 +1,145 @@
+// cpn_text.cpp — output text of the path, native (host only).
+//
+// The reference writes its result files with Julia string interpolation (src/input_output.jl:95-462): every Float64 is printed
+// by Base.show → shortest round-trip digits (Grisu/Ryu), positional when the decimal point position pt satisfies -4 < pt <= 6
+// (i.e. 1e-5 <= |x| < 1e6: "0.0001", "123456.7", "100000.0"), otherwise d.ddde±x ("1.0e-5", "1.234567e6"); NaN, Inf, -Inf, -0.0.
+// round(x, digits=4) is round-half-even of x·10⁴ divided by 10⁴ (Base/floatfuncs.jl).  std::to_chars gives the same shortest
+// digit string; this file only re-arranges it.  Pinned by re-printing every number of the reference's golden files and by
+// re-writing the golden theta / mml / nme files byte for byte (tests/test_outputs.py, tests/test_pipeline_gpu.py).
+//
+//   write_output_ex / _exx / _mml / _nme, write_output_tmml / _tnme / _tcmd   → cpn_write_rows
+//   write_output_ϕ (with get_αβ_from_ϕ, src/link_functions.jl:16-25)          → cpn_write_theta
+#include <charconv>
+#include <cmath>
+#include <cstdint>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "../../include/cpelnano_b200.h"
+
+namespace {
+
+// appends Julia's text of x to s
+inline void put_f64(std::string& s, double x) {
+    if (x != x) { s += "NaN"; return; }
+    if (std::isinf(x)) { s += x > 0 ? "Inf" : "-Inf"; return; }
+    if (x == 0.0) { s += std::signbit(x) ? "-0.0" : "0.0"; return; }
+    char buf[40];
+    auto r = std::to_chars(buf, buf + sizeof buf, std::fabs(x), std::chars_format::scientific);      // d[.ddd]e±XX, shortest digits
+    const char* e = (const char*)memchr(buf, 'e', r.ptr - buf);
+    char digits[24];
+    int n = 0;
+    for (const char* p = buf; p < e; ++p)
+        if (*p != '.') digits[n++] = *p;
+    int ex = 0;
+    std::from_chars(e + 1 + (e[1] == '+'), r.ptr, ex);
+    const int pt = ex + 1;                                    // |x| = 0.DIGITS × 10^pt
+    if (x < 0) s += '-';
+    if (pt <= -4 || pt > 6) {
+        s += digits[0];
+        s += '.';
+        if (n > 1) s.append(digits + 1, n - 1); else s += '0';
+        s += 'e';
+        s += std::to_string(pt - 1);
+    } else if (pt <= 0) {
+        s += "0.";
+        s.append((size_t)(-pt), '0');
+        s.append(digits, n);
+    } else if (pt >= n) {
+        s.append(digits, n);
+        s.append((size_t)(pt - n), '0');
+        s += ".0";
+    } else {
+        s.append(digits, pt);
+        s += '.';
+        s.append(digits + pt, n - pt);
+    }
+}
+
+inline double round_digits(double x, int d) {
+    if (d < 0) return x;
+    double og = 1.0;
+    for (int i = 0; i < d; ++i) og *= 10.0;
+    return std::nearbyint(x * og) / og;                       // default rounding mode: to nearest, ties to even
+}
+
+inline void put_i64(std::string& s, int64_t v) {
+    char buf[24];
+    auto r = std::to_chars(buf, buf + sizeof buf, v);
+    s.append(buf, r.ptr - buf);
+}
+
+bool append_file(const char* path, const std::string& s) {
+    FILE* f = fopen(path, "ab");
+    if (!f) return false;
+    const bool ok = s.empty() || fwrite(s.data(), 1, s.size(), f) == s.size();
+    return fclose(f) == 0 && ok;
+}
+
+}  // namespace
+
+extern "C" {
+
+int64_t cpn_format_f64(const double* x, int64_t n, char sep, int32_t digits, char* out, int64_t cap) {
+    if (n < 0 || (n > 0 && !x)) return -1;
+    std::string s;
+    s.reserve((size_t)n * 20);
+    for (int64_t i = 0; i < n; ++i) {
+        if (i) s += sep;
+        put_f64(s, round_digits(x[i], digits));
+    }
+    if (out && cap >= (int64_t)s.size()) memcpy(out, s.data(), s.size());
+    return (int64_t)s.size();
+}
+
+int cpn_write_rows(const char* path, const char* chr, int64_t n, const int64_t* a, const int64_t* b, const double* v, int32_t digits,
+                   int32_t clamp0, const double* w) {
+    if (!path || !chr || n < 0 || (n > 0 && (!a || !b || !v))) return CPN_ERR_ARG;
+    std::string s;
+    s.reserve((size_t)n * 48);
+    for (int64_t i = 0; i < n; ++i) {
+        if (v[i] != v[i]) continue;                            // isnan(x) && continue
+        s += chr; s += '\t';
+        put_i64(s, a[i]); s += '\t';
+        put_i64(s, b[i]); s += '\t';
+        double x = v[i];
+        if (clamp0 && !(x > 0.0)) x = 0.0;                     // max(0.0, tcmd) before rounding (input_output.jl:427)
+        put_f64(s, round_digits(x, digits));
+        if (w) { s += '\t'; put_f64(s, w[i]); }
+        s += '\n';
+    }
+    return append_file(path, s) ? CPN_OK : CPN_ERR_ARG;
+}
+
+int cpn_write_theta(const char* path, const char* chr, int64_t R, const int64_t* chrst, const int64_t* chrend, const double* phi,
+                    const int64_t* grp_off, const double* Nl, const double* rho_l, const double* d_l) {
+    if (!path || !chr || R < 0 || (R > 0 && (!chrst || !chrend || !phi || !grp_off || !rho_l || !d_l))) return CPN_ERR_ARG;
+    std::string s;
+    for (int64_t r = 0; r < R; ++r) {
+        const double pa = phi[3 * r], pb = phi[3 * r + 1], pc = phi[3 * r + 2];
+        const int64_t g0 = grp_off[r], L = grp_off[r + 1] - g0;
+        s += chr; s += '\t';
+        put_i64(s, chrst[r]); s += '\t';
+        put_i64(s, chrend[r]); s += '\t';
+        put_f64(s, pa); s += ','; put_f64(s, pb); s += ','; put_f64(s, pc); s += '\t';
+        for (int64_t l = 0; l < L; ++l) {                      // α = (a .+ b .* ρ) .* N, no fused multiply-add (link_functions.jl:19)
+            if (l) s += ',';
+            volatile double t = pb * rho_l[g0 + l];
+            volatile double u = pa + t;
+            put_f64(s, Nl ? u * Nl[g0 + l] : u);
+        }
+        s += '\t';
+        const double* d = d_l + (g0 - r);
+        for (int64_t l = 0; l + 1 < L; ++l) {                  // β = c ./ d
+            if (l) s += ',';
+            put_f64(s, pc / d[l]);
+        }
+        s += '\n';
+        if (s.size() > (1u << 24)) { if (!append_file(path, s)) return CPN_ERR_ARG; s.clear(); }
+    }
+    return append_file(path, s) ? CPN_OK : CPN_ERR_ARG;
+}
+
+}  // extern "C"

@@ -140,13 +140,45 @@ def write_output_nme(path, regs):
     _write_sub(path, regs, "nme")
 
 
-def write_output(regs, files):
-    """write_output (src/input_output.jl:314-333): theta, exx, ex, mml, nme — all opened in append mode."""
+def write_output(regs, files, lib=None):
+    """write_output (src/input_output.jl:314-333): theta, exx, ex, mml, nme — all opened in append mode.  With `lib` the text
+    is produced by the native writers (cpn_write_theta / cpn_write_rows: same bytes, no per-number Python work)."""
+    if lib is not None:
+        return _write_output_native(regs, files, lib)
     write_output_phi(files.theta_file, regs)
     write_output_exx(files.exx_file, regs)
     write_output_ex(files.ex_file, regs)
     write_output_mml(files.mml_file, regs)
     write_output_nme(files.nme_file, regs)
+
+
+def _by_chr(items, key):
+    """Consecutive runs of items sharing a chromosome name (files are written in region order)."""
+    run, name = [], None
+    for it in items:
+        k = key(it)
+        if run and k != name:
+            yield name, run
+            run = []
+        name = k
+        run.append(it)
+    if run:
+        yield name, run
+
+
+def _write_output_native(regs, files, lib):
+    from . import capi
+    done = [rs for rs in regs if rs.proc]
+    for name, rr in _by_chr(done, lambda rs: rs.chr):
+        cat = lambda f: np.concatenate([np.asarray(f(rs)) for rs in rr])      # noqa: E731
+        grp_off = np.concatenate([[0], np.cumsum([rs.L for rs in rr])]).astype(np.int64)
+        capi.write_theta(lib, files.theta_file, name, [rs.chrst for rs in rr], [rs.chrend for rs in rr], np.array([rs.phihat for rs in rr]), grp_off,
+                         cat(lambda rs: rs.Nl), cat(lambda rs: rs.rho_l), cat(lambda rs: rs.dl))
+        capi.write_rows(lib, files.exx_file, name, cat(lambda rs: rs.cpg_pos[:rs.L - 1]), cat(lambda rs: rs.cpg_pos[1:rs.L]), cat(lambda rs: rs.exx[:rs.L - 1]))
+        capi.write_rows(lib, files.ex_file, name, cat(lambda rs: rs.cpg_pos[:rs.L]), cat(lambda rs: rs.cpg_pos[:rs.L]), cat(lambda rs: rs.ex[:rs.L]))
+        st, en = cat(lambda rs: rs.nls_rgs.chr_st), cat(lambda rs: rs.nls_rgs.chr_end)
+        capi.write_rows(lib, files.mml_file, name, st, en, cat(lambda rs: rs.mml), digits=4)
+        capi.write_rows(lib, files.nme_file, name, st, en, cat(lambda rs: rs.nme), digits=4)
 
 
 # ---- differential outputs --------------------------------------------------------------------------------------------------
@@ -166,8 +198,21 @@ def _write_test(path, chrom, tests, row, clamp=False):
                 io.write(f"{chr_name}\t{co.chr_st[k]}\t{co.chr_end[k]}\t{julia_str(julia_round(t))}\t{julia_str(p[k])}\n")
 
 
-def write_diff_output(chrom, tests, files, matched=False):
+def write_diff_output(chrom, tests, files, matched=False, lib=None):
     """write_diff_output (src/input_output.jl:448-462).  `chrom[i]` is the chromosome name of tests[i]."""
+    if lib is not None:
+        from . import capi
+        for name, run in _by_chr(list(zip(chrom, tests)), lambda ct: ct[0]):
+            ts = [t for _, t in run]
+            st = np.concatenate([t["coords"].chr_st for t in ts]); en = np.concatenate([t["coords"].chr_end for t in ts])
+            capi.write_rows(lib, files.tmml_file, name, st, en, np.concatenate([t["T"][0] for t in ts]), 4, False, np.concatenate([t["pval"][0] for t in ts]))
+            capi.write_rows(lib, files.tnme_file, name, st, en, np.concatenate([t["T"][1] for t in ts]), 4, False, np.concatenate([t["pval"][1] for t in ts]))
+            if matched:
+                tc = np.concatenate([t["tcmd"] for t in ts]); pc = np.full(len(tc), np.nan)
+            else:
+                tc = np.concatenate([t["T"][2] for t in ts]); pc = np.concatenate([t["pval"][2] for t in ts])
+            capi.write_rows(lib, files.tcmd_file, name, st, en, tc, 4, True, pc)
+        return
     _write_test(files.tmml_file, chrom, tests, 0)
     _write_test(files.tnme_file, chrom, tests, 1)
     _write_test(files.tcmd_file, chrom, tests, "tcmd_matched" if matched else 2, clamp=True)

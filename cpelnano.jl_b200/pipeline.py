@@ -73,7 +73,7 @@ def analyze_nano(nano, fasta, config, out_dir, out_prefix, bed_reg=None, mod_nse
         analyze_regions(cand, config, phi0s=phi0s, rng=rng, engine=eng)
         t = lap("fit_and_summaries_s", t)
         # write_output_ϕ runs after rscle_grp_mod!, so the theta file holds the per-CpG α, β (as the reference's does)
-        outputs.write_output(regs, files)
+        outputs.write_output(regs, files, eng.lib)
         t = lap("write_outputs_s", t)
         done.extend(rs for rs in regs if rs.proc)
         tm["regions"] = tm.get("regions", 0) + len(part)
@@ -121,7 +121,7 @@ def diff_grp_comp(mod_fls_g1, mod_fls_g2, fasta, config, out_dir, out_prefix, rn
             tests.extend(out); keys.extend((t[0], t[1]) for t in items)
         order = sorted(range(len(tests)), key=lambda i: keys[i])
         tests = [tests[i] for i in order]
-        outputs.write_diff_output([name] * len(tests), tests, files, matched=config.matched)
+        outputs.write_diff_output([name] * len(tests), tests, files, matched=config.matched, lib=eng.lib)
     outputs.mult_hyp_corr(files, matched=config.matched)
     return files
 
@@ -157,7 +157,7 @@ def diff_two_samp_comp(mods_path_s1, mods_path_s2, nano_s1, nano_s2, fasta, conf
                 c1 = c2 = (np.zeros((0, 0)), np.zeros((0, 0)))
             items.append((a, b, c1, c2))
         tests = eng.diff_two_samp_comp_batch(items, config, rng=rng)
-        outputs.write_diff_output([name] * len(tests), tests, files, matched=False)
+        outputs.write_diff_output([name] * len(tests), tests, files, matched=False, lib=eng.lib)
     if config.pval_comp:
         outputs.mult_hyp_corr(files, matched=False)
     return files

@@ -276,6 +276,21 @@ int cpn_grp_info_fill(const int64_t* cg, int64_t ncg, int64_t chr_size, int64_t 
                       int64_t min_grp_dist, const int64_t* cpg_off, const int64_t* grp_off, int32_t n_threads, int64_t* cpg_pos,
                       double* rho_n, double* d_n, double* Nl, double* rho_l, double* d_l, int64_t* grp_st, int64_t* grp_end);
 
+/* ---- output text (host only, no GPU needed) -----------------------------------------------------------------------------
+ * The reference's writers (src/input_output.jl:95-462) print with Julia string interpolation; these entry points produce the
+ * same bytes: Float64 as Julia's shortest round-trip text ("0.0001", "1.0e-5", "1.234567e6", "NaN"), round(x, digits=d) as
+ * round-half-even of x*10^d divided back.
+ *   cpn_format_f64  n values joined by sep (digits < 0: no rounding); returns the byte count (call with out = NULL to size)
+ *   cpn_write_rows  appends "chr \t a[i] \t b[i] \t v[i] [\t w[i]] \n" for every i with non-NaN v[i] (write_output_ex/_exx: digits -1;
+ *                   _mml/_nme and _tmml/_tnme: digits 4, w = p-values; _tcmd: digits 4, clamp0 = 1: max(0, v) first)
+ *   cpn_write_theta appends write_output_ϕ rows: chr, chrst, chrend, "a,b,c", α list, β list with α = (a + b*rho_l)*Nl and
+ *                   β = c/d_l (get_αβ_from_ϕ, src/link_functions.jl:16-25; Nl = NULL means all ones, the per-CpG chain)      */
+int64_t cpn_format_f64(const double* x, int64_t n, char sep, int32_t digits, char* out, int64_t cap);
+int cpn_write_rows(const char* path, const char* chr, int64_t n, const int64_t* a, const int64_t* b, const double* v, int32_t digits,
+                   int32_t clamp0, const double* w);
+int cpn_write_theta(const char* path, const char* chr, int64_t R, const int64_t* chrst, const int64_t* chrend, const double* phi,
+                    const int64_t* grp_off, const double* Nl, const double* rho_l, const double* d_l);
+
 #ifdef __cplusplus
 }
 #endif

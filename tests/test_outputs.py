@@ -108,3 +108,73 @@ def test_theta_reader_and_alpha_beta_print_identically(golden, tmp_path):
     dst = tmp_path / "out_theta.txt"
     outputs.write_output_phi(str(dst), regs)
     assert dst.read_text() == text
+
+
+# ---- native writers (csrc/cpn_text.cpp) ------------------------------------------------------------------------------------------
+def test_native_float_text_equals_julia_text_on_every_golden_number(golden):
+    from cpelnano_b200 import capi
+    lib = cpn.Library()
+    for name, text in golden.items():
+        toks = list(_float_tokens(text, 3))
+        vals = np.array([float(t) for t in toks])
+        assert capi.format_f64(lib, vals, sep="\n").split("\n") == toks, name
+    rng = np.random.default_rng(0)
+    x = np.concatenate([rng.standard_normal(20000) * 10.0 ** rng.integers(-12, 12, 20000), [0.0, -0.0, np.nan, np.inf, -np.inf, 1e-5, 1e6, 999999.9,
+                        5e-324, 1.7976931348623157e308, 0.1 + 0.2, 100000.0, 123456.7, 1e22, 2.0 ** 70]])
+    assert capi.format_f64(lib, x, sep=";").split(";") == [outputs.julia_str(v) for v in x]
+    r4 = capi.format_f64(lib, x[:20000], sep=";", digits=4).split(";")
+    assert r4 == [outputs.julia_str(outputs.julia_round(v)) for v in x[:20000]]
+
+
+def test_native_writers_reproduce_golden_theta_and_python_writers(golden, tmp_path):
+    from cpelnano_b200 import genome
+    lib = cpn.Library()
+    text = golden["full_example/cpelnano/full_example_mod_nse_true_theta.txt"]
+    src = tmp_path / "theta.txt"
+    src.write_text(text)
+    chrom = genome.load_genome(os.path.join(INP, "full_example.fa.gz"), lib)["hg38_dna"]
+    lines = outputs.read_theta_lines(str(src), "hg38_dna")
+    regs = chrom.region_structs(lib, [(l[1], l[2]) for l in lines])
+    rng = np.random.default_rng(3)
+    for rs, l in zip(regs, lines):
+        rs.phihat = l[3]
+        cpn.rscle_grp_mod(rs)
+        rs.proc = True
+        # summaries are the GPU's job; here any doubles will do to compare the two writers (NaN rows must be skipped by both)
+        rs.ex, rs.exx = rng.uniform(-1, 1, rs.N), rng.uniform(-1, 1, rs.N - 1)
+        K = 9
+        rs.nls_rgs = cpn.host.AnalysisRegions(K, np.arange(K) * 300 + rs.chrst, np.arange(K) * 300 + rs.chrst + 299, np.zeros(K, dtype=np.int64),
+                                              np.zeros(K, dtype=np.int64))
+        rs.mml, rs.nme = rng.uniform(0, 1, K), rng.uniform(0, 1, K)
+        rs.mml[rng.integers(0, K)] = np.nan; rs.nme[np.isnan(rs.mml)] = np.nan
+        rs.ex[0] = np.nan
+    regs[3].proc = False
+    fa, fb = outputs.OutputFiles(str(tmp_path), "py"), outputs.OutputFiles(str(tmp_path), "native")
+    outputs.write_output(regs, fa)
+    outputs.write_output(regs, fb, lib)
+    for a, b in zip(fa.all(), fb.all()):
+        assert open(a).read() == open(b).read() and os.path.getsize(a) > 0, a
+    regs[3].proc = True
+    fc = outputs.OutputFiles(str(tmp_path), "native_all")
+    outputs.write_output(regs, fc, lib)
+    assert open(fc.theta_file).read() == text                                  # the reference's own theta file, byte for byte
+
+
+def test_native_diff_writer_equals_python_writer(tmp_path):
+    lib = cpn.Library()
+    rng = np.random.default_rng(2)
+    tests, chrom = [], []
+    for r in range(40):
+        K = int(rng.integers(1, 10))
+        co = cpn.host.AnalysisRegions(K, np.arange(K) * 350 + 1000 * r, np.arange(K) * 350 + 1000 * r + 349, np.zeros(K, dtype=np.int64), np.zeros(K, dtype=np.int64))
+        T = rng.standard_normal((3, K)); T[2] = np.abs(T[2]) - 0.05                  # some Tcmd slightly negative: clamped to 0.0
+        T[:, rng.integers(0, K)] = np.nan
+        p = rng.integers(0, 925, (3, K)) / 924.0
+        p[rng.random((3, K)) < 0.1] = np.nan
+        tests.append(dict(T=T, pval=p, tcmd=np.abs(T[2]), coords=co)); chrom.append("chrA" if r < 25 else "chrB")
+    for matched in (False, True):
+        fa, fb = outputs.OutputDiffFiles(str(tmp_path), f"py{matched}"), outputs.OutputDiffFiles(str(tmp_path), f"nat{matched}")
+        outputs.write_diff_output(chrom, tests, fa, matched)
+        outputs.write_diff_output(chrom, tests, fb, matched, lib)
+        for a, b in zip(fa.all(), fb.all()):
+            assert open(a).read() == open(b).read() and os.path.getsize(a) > 0
