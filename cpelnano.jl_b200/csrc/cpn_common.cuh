@@ -4,6 +4,7 @@
 
 #include <cstdint>
 #include <cstdio>
+#include <cstdlib>
 #include <string>
 #include <vector>
 
@@ -82,6 +83,7 @@ struct cpn_ctx {
     int sm_count = 148;
     cudaStream_t stream = nullptr;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    cudaEvent_t ev_wait = nullptr;           // blocking-sync event behind cpn_wait_stream
     std::string err;
     double last_ms = 0.0;
     int64_t last_launches = 0;
@@ -102,6 +104,23 @@ struct cpn_ctx {
     CpnArena arena, stage_arena;
     std::vector<CpnArena*> slot_arenas;
 };
+
+// Host waits sleep instead of spinning (cudaEventBlockingSync): a host-pointer call keeps a staging thread and two workers
+// waiting on the GPU most of the time, and with one process per GPU on a shared host (8 ranks × 3 threads on 16 cores) spinning
+// waiters take the cores the launching threads need.  The wake-up latency (tens of µs) is off the critical path: the EM loop
+// runs two iterations ahead of the device.  CPN_SPIN_WAIT=1 restores cudaStreamSynchronize.
+inline bool cpn_spin_wait() {
+    static const bool spin = getenv("CPN_SPIN_WAIT") != nullptr && atoi(getenv("CPN_SPIN_WAIT")) != 0;
+    return spin;
+}
+inline cudaError_t cpn_wait_stream(cpn_ctx* ctx, cudaStream_t s) {
+    if (cpn_spin_wait()) return cudaStreamSynchronize(s);
+    cudaError_t e = cudaSuccess;
+    if (!ctx->ev_wait) e = cudaEventCreateWithFlags(&ctx->ev_wait, cudaEventBlockingSync | cudaEventDisableTiming);
+    if (e == cudaSuccess) e = cudaEventRecord(ctx->ev_wait, s);
+    if (e == cudaSuccess) e = cudaEventSynchronize(ctx->ev_wait);
+    return e;
+}
 
 // Brackets one launch with events when profiling is on.  Usage: { KTimer t(ctx, CPN_K_ESTEP); kernel<<<...>>>(...); }
 struct KTimer {

@@ -56,6 +56,7 @@ void cpn_destroy(cpn_ctx* ctx) {
     if (ctx->stream) { cudaStreamSynchronize(ctx->stream); cudaStreamDestroy(ctx->stream); }
     if (ctx->ev0) cudaEventDestroy(ctx->ev0);
     if (ctx->ev1) cudaEventDestroy(ctx->ev1);
+    if (ctx->ev_wait) cudaEventDestroy(ctx->ev_wait);
     for (cudaEvent_t e : ctx->pev) cudaEventDestroy(e);
     for (cpn_ctx* c : ctx->children) cpn_destroy(c);
     for (cudaEvent_t e : ctx->it_ev) cudaEventDestroy(e);

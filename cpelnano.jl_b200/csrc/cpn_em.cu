@@ -1294,7 +1294,7 @@ int pack_regions(cpn_ctx* ctx, PackedRegions& pk, bool on_device, bool with_read
     if (offs_dev) {
         CPN_CUDA(ctx, cudaMemcpyAsync(pk.h_grp_off.data(), grp_off, (R + 1) * sizeof(int64_t), cudaMemcpyDeviceToHost, s));
         if (with_reads) CPN_CUDA(ctx, cudaMemcpyAsync(pk.h_read_off.data(), read_off, (R + 1) * sizeof(int64_t), cudaMemcpyDeviceToHost, s));
-        CPN_CUDA(ctx, cudaStreamSynchronize(s));
+        CPN_CUDA(ctx, cpn_wait_stream(ctx, s));
     } else {
         std::memcpy(pk.h_grp_off.data(), grp_off, (R + 1) * sizeof(int64_t));
         if (with_reads) std::memcpy(pk.h_read_off.data(), read_off, (R + 1) * sizeof(int64_t));
@@ -1354,7 +1354,7 @@ int pack_regions(cpn_ctx* ctx, PackedRegions& pk, bool on_device, bool with_read
         pk.lm.own.release();
         pk.lu.own.release();
         trace(ctx, "pk-enq");
-        CPN_CUDA(ctx, cudaStreamSynchronize(s));   // h_* staging vectors go out of scope
+        CPN_CUDA(ctx, cpn_wait_stream(ctx, s));   // h_* staging vectors go out of scope
         trace(ctx, "pk-sync");
         pk.rt.read_off = pk.read_off.p; pk.rt.ew_off = pk.ew_off.p; pk.rt.rb_off = pk.rb_off.p; pk.rt.ew = pk.ew.p; pk.rt.rb = pk.rb.p;
     }
@@ -1379,7 +1379,7 @@ static int ctx_iter_resources(cpn_ctx* ctx, int n) {
     }
     while ((int)ctx->it_ev.size() < n) {
         cudaEvent_t e;
-        CPN_CUDA(ctx, cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+        CPN_CUDA(ctx, cudaEventCreateWithFlags(&e, cudaEventDisableTiming | (cpn_spin_wait() ? 0 : cudaEventBlockingSync)));
         ctx->it_ev.push_back(e);
     }
     return CPN_OK;
@@ -1560,7 +1560,7 @@ int fit_impl(cpn_ctx* ctx, bool on_device, int64_t R, const int64_t* grp_off, co
             if (offs_dev) {
                 CPN_CUDA(ctx, cudaMemcpyAsync(h_cpg.data(), sa->cpg_off, (R + 1) * sizeof(int64_t), cudaMemcpyDeviceToHost, s));
                 CPN_CUDA(ctx, cudaMemcpyAsync(h_sub.data(), sa->sub_off, (R + 1) * sizeof(int64_t), cudaMemcpyDeviceToHost, s));
-                CPN_CUDA(ctx, cudaStreamSynchronize(s));
+                CPN_CUDA(ctx, cpn_wait_stream(ctx, s));
             } else {
                 std::memcpy(h_cpg.data(), sa->cpg_off, (R + 1) * sizeof(int64_t));
                 std::memcpy(h_sub.data(), sa->sub_off, (R + 1) * sizeof(int64_t));
@@ -1586,10 +1586,10 @@ int fit_impl(cpn_ctx* ctx, bool on_device, int64_t R, const int64_t* grp_off, co
             CPN_CUDA(ctx, s_logZ.finish(s)); CPN_CUDA(ctx, s_ex.finish(s)); CPN_CUDA(ctx, s_exx.finish(s)); CPN_CUDA(ctx, s_lg.finish(s));
             CPN_CUDA(ctx, s_e1.finish(s)); CPN_CUDA(ctx, s_e2.finish(s)); CPN_CUDA(ctx, s_mml.finish(s)); CPN_CUDA(ctx, s_nme.finish(s));
             CPN_CUDA(ctx, cudaEventRecord(ctx->ev1, s));
-            CPN_CUDA(ctx, cudaStreamSynchronize(s));
+            CPN_CUDA(ctx, cpn_wait_stream(ctx, s));
         } else {
             CPN_CUDA(ctx, cudaEventRecord(ctx->ev1, s));
-            CPN_CUDA(ctx, cudaStreamSynchronize(s));
+            CPN_CUDA(ctx, cpn_wait_stream(ctx, s));
         }
     }
     trace(ctx, "end");
@@ -1668,7 +1668,7 @@ static int fit_chunked(cpn_ctx* ctx, bool on_device, int64_t R, const int64_t* g
                 h_off[k].resize(R + 1);
                 CPN_CUDA(ctx, cudaMemcpyAsync(h_off[k].data(), src[k], (R + 1) * sizeof(int64_t), cudaMemcpyDeviceToHost, ctx->stream));
             }
-        CPN_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+        CPN_CUDA(ctx, cpn_wait_stream(ctx, ctx->stream));
         grp_off = h_off[0].data(); read_off = h_off[1].data();
         if (sa_in) { sa_host = *sa_in; sa_host.cpg_off = h_off[2].data(); sa_host.sub_off = h_off[3].data(); sa = &sa_host; }
     }
@@ -1762,7 +1762,7 @@ static int fit_chunked(cpn_ctx* ctx, bool on_device, int64_t R, const int64_t* g
                 trace(u, "stage");
                 r = fit_stage(u, *slot[c], on_device, Rc, g.data(), Nl + g0, rho_l + g0, d_l + (g0 - r0), rd.data(), lu + obs[r0], lm + obs[r0],
                               phi0 + r0 * n_init * 3, n_init, 0);
-                if (r == CPN_OK && cudaStreamSynchronize(u->stream) != cudaSuccess) { u->err = "stream synchronize failed"; r = CPN_ERR_CUDA; }
+                if (r == CPN_OK && cpn_wait_stream(u, u->stream) != cudaSuccess) { u->err = "stream synchronize failed"; r = CPN_ERR_CUDA; }
                 launches[0] = u->last_launches;
                 trace(u, "staged");
             }
@@ -1840,7 +1840,7 @@ static int fit_chunked(cpn_ctx* ctx, bool on_device, int64_t R, const int64_t* g
             CPN_CUDA(ctx, cudaStreamWaitEvent(ctx->stream, ctx->children[i]->ev1, 0));
         }
         CPN_CUDA(ctx, cudaEventRecord(ctx->ev1, ctx->stream));
-        CPN_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+        CPN_CUDA(ctx, cpn_wait_stream(ctx, ctx->stream));
         float ms = 0;
         CPN_CUDA(ctx, cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1));
         ctx->last_ms = ms;
@@ -1938,7 +1938,7 @@ int cpn_estep_batch(cpn_ctx* ctx, int64_t R, const int64_t* grp_off, const doubl
         }
         CPN_CUDA(ctx, cudaGetLastError());
         CPN_CUDA(ctx, cudaEventRecord(ctx->ev1, s));
-        CPN_CUDA(ctx, cudaStreamSynchronize(s));
+        CPN_CUDA(ctx, cpn_wait_stream(ctx, s));
     }
     float ms = 0;
     CPN_CUDA(ctx, cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1));
@@ -1974,7 +1974,7 @@ int cpn_mstep_batch(cpn_ctx* ctx, int64_t R, const int64_t* grp_off, const doubl
         CPN_CUDA(ctx, d_conv.download(converged, R, s));
         if (counters) CPN_CUDA(ctx, d_cnt.download(counters, 2 * R, s));
         CPN_CUDA(ctx, cudaEventRecord(ctx->ev1, s));
-        CPN_CUDA(ctx, cudaStreamSynchronize(s));
+        CPN_CUDA(ctx, cpn_wait_stream(ctx, s));
     }
     float ms = 0;
     CPN_CUDA(ctx, cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1));
@@ -2076,7 +2076,7 @@ int cpn_two_samp_null_batch(cpn_ctx* ctx, int64_t R, const int64_t* grp_off, con
             CPN_CUDA(ctx, logZ.alloc(V, s)); CPN_CUDA(ctx, ex.alloc(sN, s)); CPN_CUDA(ctx, exx.alloc(sN - V, s)); CPN_CUDA(ctx, lg.alloc(4 * sK, s));
             CPN_CUDA(ctx, e1.alloc(sK, s)); CPN_CUDA(ctx, e2.alloc(sK, s)); CPN_CUDA(ctx, mml.alloc(sK, s)); CPN_CUDA(ctx, nme.alloc(sK, s));
             CPN_CUDA(ctx, cmd.alloc(cmd_off[Pt], s)); CPN_CUDA(ctx, T.alloc(3 * cmd_off[Pt], s));
-            CPN_CUDA(ctx, cudaStreamSynchronize(s));               // the host staging vectors may go
+            CPN_CUDA(ctx, cpn_wait_stream(ctx, s));               // the host staging vectors may go
         }
         // 2·ΣP multi-start EM fits over the views; results stay on the device
         const int64_t keep_launches = ctx->last_launches;
@@ -2097,7 +2097,7 @@ int cpn_two_samp_null_batch(cpn_ctx* ctx, int64_t R, const int64_t* grp_off, con
         CPN_CUDA(ctx, T.download(T_null, 3 * cmd_off[Pt], s));
         if (fit_status) CPN_CUDA(ctx, d_stat.download(fit_status, V, s));
         CPN_CUDA(ctx, cudaEventRecord(ctx->ev1, s));
-        CPN_CUDA(ctx, cudaStreamSynchronize(s));
+        CPN_CUDA(ctx, cpn_wait_stream(ctx, s));
     }
     float ms = 0;
     CPN_CUDA(ctx, cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1));
