@@ -127,38 +127,3 @@ class NativeCalls:
             r.set_calls(lu[o:o + m * L].reshape(m, L), lm[o:o + m * L].reshape(m, L))
             o += m * L
         return regs
-
-
-def region_calls_reference(path, chrom, chrst, chrend, grp_st, grp_end, mod_nse=True):
-    """Line-by-line restatement of get_dic_nanopolish + get_calls_nanopolish! for ONE region (test oracle: O(file) per
-    region like the reference).  Returns {read name: (lu[L], lm[L])}."""
-    opener = gzip.open if str(path).endswith(".gz") else open
-    dic = {}
-    with opener(path, "rt") as f:
-        for i, line in enumerate(f):
-            if i == 0:
-                continue
-            v = line.rstrip("\n").split("\t")
-            if v[0] != chrom:
-                continue
-            if not int(v[2]) <= chrend:
-                continue
-            if not int(v[3]) >= chrst:
-                continue
-            dic.setdefault(v[4], []).append(v)
-    out = {}
-    L = len(grp_st)
-    for name, lines in dic.items():
-        lu = [float("nan")] * L; lm = [float("nan")] * L
-        for v in lines:
-            st, en = int(v[2]) + 1 - 5, int(v[3]) + 1 + 5
-            i_st = next((i for i in range(L) if grp_st[i] == st), None)
-            i_en = next((i for i in range(L) if grp_end[i] == en), None)
-            if i_st is None or i_en is None or i_st != i_en:
-                continue
-            m, u = float(v[6]), float(v[7])
-            if not mod_nse:
-                m, u = (LOG_PYX_RIGHT_X, LOG_PYX_WRONG_X) if m > u else (LOG_PYX_WRONG_X, LOG_PYX_RIGHT_X)
-            lm[i_st], lu[i_st] = m, u
-        out[name] = (np.array(lu), np.array(lm))
-    return out

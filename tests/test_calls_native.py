@@ -12,6 +12,7 @@ import os
 import numpy as np
 import pytest
 
+import calls_ref            # oracle/calls_ref.py (conftest puts oracle/ on sys.path)
 import cpelnano_b200 as cpn
 from cpelnano_b200 import genome, nanopolish
 
@@ -46,7 +47,7 @@ def test_native_equals_numpy_and_restatement_on_bundled_calls(lib, regions, mod_
     for i in (7, 20):
         rs = regions[i]
         a = nat.region_calls(rs.chr, rs.chrst, rs.chrend, rs.grp_st, rs.grp_end, mod_nse)
-        line = nanopolish.region_calls_reference(TSV, rs.chr, rs.chrst, rs.chrend, rs.grp_st, rs.grp_end, mod_nse)
+        line = calls_ref.region_calls_reference(TSV, rs.chr, rs.chrst, rs.chrend, rs.grp_st, rs.grp_end, mod_nse)
         assert set(a[2]) == set(line)
         for k, nm in enumerate(a[2]):
             assert np.array_equal(a[0][k], line[nm][0], equal_nan=True) and np.array_equal(a[1][k], line[nm][1], equal_nan=True)

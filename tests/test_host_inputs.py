@@ -3,7 +3,7 @@
 Pins: the committed fixtures tests/golden/{targeted,full}_example.npz were produced by a regex-per-window restatement of the
 reference (tests/golden/make_fixtures.py) and reproduce the golden theta files' α, β bit-exactly (test_oracle_golden.py); the
 vectorised implementation in cpelnano.jl_b200/genome.py must give the same integers and the same doubles.  Calls ingestion is
-checked against a line-by-line restatement of get_dic_nanopolish + get_calls_nanopolish! (src/input_output.jl:536-570,
+checked against the line-by-line restatement in oracle/calls_ref.py of get_dic_nanopolish + get_calls_nanopolish! (src/input_output.jl:536-570,
 src/nanopore.jl:172-230) on the bundled full_example calls.
 """
 import os
@@ -11,6 +11,7 @@ import os
 import numpy as np
 import pytest
 
+import calls_ref            # oracle/calls_ref.py (conftest puts oracle/ on sys.path)
 import cpelnano_b200 as cpn
 from cpelnano_b200 import genome, nanopolish
 
@@ -104,7 +105,7 @@ def test_calls_ingestion_matches_line_by_line_restatement(chr_full, calls_full, 
     for r in (0, 5, 13, 26):
         rs = chr_full.region_struct(int(fx["chrst"][r]), int(fx["chrend"][r]))
         lu, lm, names = calls_full.region_calls(rs.chr, rs.chrst, rs.chrend, rs.grp_st, rs.grp_end, mod_nse)
-        ref = nanopolish.region_calls_reference(path, rs.chr, rs.chrst, rs.chrend, rs.grp_st, rs.grp_end, mod_nse)
+        ref = calls_ref.region_calls_reference(path, rs.chr, rs.chrst, rs.chrend, rs.grp_st, rs.grp_end, mod_nse)
         assert set(names) == set(ref) and len(names) == len(ref)
         for i, nm in enumerate(names):
             assert np.array_equal(lu[i], ref[nm][0], equal_nan=True)

@@ -17,6 +17,8 @@ import numpy as np
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "oracle"))
+import calls_ref  # noqa: E402  (test oracle)
 
 
 def main():
@@ -85,7 +87,7 @@ def main():
     t = time.perf_counter()
     for r in range(args.ref_sample):
         a, b = grp_off[r], grp_off[r + 1]
-        nanopolish.region_calls_reference(path, "chrS", int(chrst[r]), int(chrend[r]), gs[a:b], ge[a:b])
+        calls_ref.region_calls_reference(path, "chrS", int(chrst[r]), int(chrend[r]), gs[a:b], ge[a:b])
     t_ref = (time.perf_counter() - t) / args.ref_sample
     out["reference_access_pattern"] = {"s_per_region": t_ref, "regions_per_s": 1 / t_ref,
                                        "note": "whole file re-read for every region (src/input_output.jl:536-570), Python restatement; Julia would be faster per line, the O(regions x file) shape is the point"}
