@@ -356,15 +356,25 @@ __device__ __forceinline__ double logz_chunk(SiteTile& st, int L, int lane, cons
         __syncwarp();
         fill_tile(st, l0, n, lane, na_g, nb_g, invd_g, a, b, cabs, BPOS);
         __syncwarp();
-        for (int j = 0; j < n; ++j) {
-            double r = p ? p[(size_t)(l0 + j) * 32] : 1.0;
-            const double2 w = st.w[j];
-            double t = st.tn[j].x;
-            double phiP = (w.y * r) * sc, phiM = w.x * sc;
-            double u = BPOS ? fp : fm, v = BPOS ? fm : fp;
-            fp = phiP * fma(t, v, u);
-            fm = phiM * fma(t, u, v);
-            sc = cpn_inv_pow2_of(fp + fm, &e); esum += e;
+        // emission weights of 8 groups are loaded before they are used: the chain step is a handful of dependent FP64
+        // instructions, so a load per step sat on the critical path (same arithmetic, same order: results unchanged)
+        for (int j0 = 0; j0 < n; j0 += 8) {
+            double rr[8];
+#pragma unroll
+            for (int k = 0; k < 8; ++k) rr[k] = (p && j0 + k < n) ? __ldg(p + (size_t)(l0 + j0 + k) * 32) : 1.0;
+#pragma unroll
+            for (int k = 0; k < 8; ++k) {
+                const int j = j0 + k;
+                if (j < n) {
+                    const double2 w = st.w[j];
+                    double t = st.tn[j].x;
+                    double phiP = (w.y * rr[k]) * sc, phiM = w.x * sc;
+                    double u = BPOS ? fp : fm, v = BPOS ? fm : fp;
+                    fp = phiP * fma(t, v, u);
+                    fm = phiM * fma(t, u, v);
+                    sc = cpn_inv_pow2_of(fp + fm, &e); esum += e;
+                }
+            }
         }
     }
     return log((fp + fm) * sc) + (double)esum * 0.6931471805599453;
@@ -394,18 +404,24 @@ __global__ void __launch_bounds__(E_WARPS * 32) k_score(int n_items, const int* 
     const double* rb_r = rt.rb + rd.rb_off;
     int nchunk = (int)((M + 31) >> 5);
     double acc = 0.0;
+    // The data-free chain log Z(ϕ) rides in lane 31 of the last chunk whenever that lane has no read (M not a multiple of 32):
+    // same instructions as a read with all emission weights 1, so the separate pass (a whole warp computing one chain) goes.
+    const bool spare = (M & 31) != 0;
+    double lz0 = 0.0;
     for (int ch = 0; ch < nchunk; ++ch) {
         int q = ch * 32 + lane;
+        const bool live = (int64_t)ch * 32 + lane < M;
         if (rd.ridx >= 0) q = __ldg(rt.ridx + ((size_t)(rd.ridx + ch) << 5) + lane);
         const double* p = ew_r + (size_t)(q >> 5) * L * 32 + (q & 31);
+        if (spare && ch == nchunk - 1 && lane == 31) p = nullptr;
         double lz = bpos ? logz_chunk<true>(tiles[w], L, lane, rt.na + g0, rt.nb + g0, rt.invd + g0, p, a, b, cabs)
                          : logz_chunk<false>(tiles[w], L, lane, rt.na + g0, rt.nb + g0, rt.invd + g0, p, a, b, cabs);
-        bool live = (int64_t)ch * 32 + lane < M;
         acc += cpn_warp_sum(live ? rb_r[q] + lz : 0.0);
+        if (spare && ch == nchunk - 1) lz0 = __shfl_sync(0xffffffffu, lz, 31);
     }
-    // marginal chain (no data): every lane computes the same value
-    double lz0 = bpos ? logz_chunk<true>(tiles[w], L, lane, rt.na + g0, rt.nb + g0, rt.invd + g0, nullptr, a, b, cabs)
-                      : logz_chunk<false>(tiles[w], L, lane, rt.na + g0, rt.nb + g0, rt.invd + g0, nullptr, a, b, cabs);
+    if (!spare)      // every lane of the last chunk holds a read: the marginal chain needs its own pass (all lanes compute the same value)
+        lz0 = bpos ? logz_chunk<true>(tiles[w], L, lane, rt.na + g0, rt.nb + g0, rt.invd + g0, nullptr, a, b, cabs)
+                   : logz_chunk<false>(tiles[w], L, lane, rt.na + g0, rt.nb + g0, rt.invd + g0, nullptr, a, b, cabs);
     if (lane == 0) Q[inst] = acc / (double)M - lz0;
 }
 
