@@ -169,6 +169,8 @@ def _by_chr(items, key):
 def _write_output_native(regs, files, lib):
     from . import capi
     done = [rs for rs in regs if rs.proc]
+    for f in files.all():                      # open(path, "a") of the reference creates every file, even when no region was processed
+        open(f, "a").close()
     for name, rr in _by_chr(done, lambda rs: rs.chr):
         cat = lambda f: np.concatenate([np.asarray(f(rs)) for rs in rr])      # noqa: E731
         grp_off = np.concatenate([[0], np.cumsum([rs.L for rs in rr])]).astype(np.int64)
@@ -202,6 +204,8 @@ def write_diff_output(chrom, tests, files, matched=False, lib=None):
     """write_diff_output (src/input_output.jl:448-462).  `chrom[i]` is the chromosome name of tests[i]."""
     if lib is not None:
         from . import capi
+        for f in files.all():
+            open(f, "a").close()
         for name, run in _by_chr(list(zip(chrom, tests)), lambda ct: ct[0]):
             ts = [t for _, t in run]
             st = np.concatenate([t["coords"].chr_st for t in ts]); en = np.concatenate([t["coords"].chr_end for t in ts])

@@ -178,3 +178,16 @@ def test_native_diff_writer_equals_python_writer(tmp_path):
         outputs.write_diff_output(chrom, tests, fb, matched, lib)
         for a, b in zip(fa.all(), fb.all()):
             assert open(a).read() == open(b).read() and os.path.getsize(a) > 0
+
+
+def test_writers_create_empty_files_when_nothing_was_processed(tmp_path):
+    """open(path, "a") in the reference creates all five files even if every region was skipped; both writers do the same."""
+    lib = cpn.Library()
+    for tag, l in (("py", None), ("nat", lib)):
+        f = outputs.OutputFiles(str(tmp_path), tag)
+        outputs.write_output([cpn.RegStruct(chr="c", chrst=1, chrend=10)], f, l)
+        assert all(os.path.exists(p) and os.path.getsize(p) == 0 for p in f.all())
+        d = outputs.OutputDiffFiles(str(tmp_path), tag)
+        outputs.write_diff_output([], [], d, False, l)
+        assert all(os.path.exists(p) and os.path.getsize(p) == 0 for p in d.all())
+        outputs.mult_hyp_corr(d)
