@@ -17,7 +17,7 @@ SYMBOLS = ["cpn_create", "cpn_destroy", "cpn_last_error", "cpn_version", "cpn_la
            "cpn_stat_sums_batch", "cpn_nls_reg_info", "cpn_cmd_batch", "cpn_grp_unmat_sweep", "cpn_grp_mat_sweep", "cpn_two_samp_pvals", "cpn_two_samp_null_batch", "cpn_grp_test_batch",
            "cpn_calls_open", "cpn_calls_close", "cpn_calls_open_error", "cpn_calls_error", "cpn_calls_num_lines", "cpn_calls_num_reads", "cpn_calls_num_chr",
            "cpn_calls_chr_name", "cpn_calls_chr_lines", "cpn_calls_read_name", "cpn_calls_count_reads", "cpn_calls_fill",
-           "cpn_cpg_scan", "cpn_chr_part", "cpn_grp_info_count", "cpn_grp_info_fill", "cpn_format_f64", "cpn_write_rows", "cpn_write_theta"]
+           "cpn_cpg_scan", "cpn_chr_part", "cpn_grp_info_count", "cpn_grp_info_fill", "cpn_format_f64", "cpn_write_rows", "cpn_write_theta", "cpn_nls_reg_info_batch"]
 
 
 class CpnError(RuntimeError):
@@ -356,6 +356,15 @@ def chr_part(lib, cg, chr_size, reg_st, reg_end, size_est_reg=3000, min_grp_dist
     return st, en
 
 
+def grp_info_counts(lib, cg, chrst, chrend, min_grp_dist, N, L, n_threads=0):
+    """cpn_grp_info_count into caller arrays N, L (int64 [R])."""
+    cg, chrst, chrend = _i64(cg), _i64(chrst), _i64(chrend)
+    rc = lib.dll.cpn_grp_info_count(_ptr(cg), C.c_int64(len(cg)), C.c_int64(len(chrst)), _ptr(chrst), _ptr(chrend), C.c_int64(min_grp_dist),
+                                    C.c_int32(n_threads), _ptr(N), _ptr(L))
+    if rc != 0:
+        raise CpnError(f"cpn_grp_info_count error {rc}")
+
+
 def grp_info_batch(lib, cg, chr_size, chrst, chrend, min_grp_dist=10, n_threads=0):
     """get_grp_info! for R regions: dict of CSR arrays (cpg_off, grp_off, cpg_pos, rho_n, d_n, Nl, rho_l, d_l, grp_st, grp_end)."""
     cg, chrst, chrend = _i64(cg), _i64(chrst), _i64(chrend)
@@ -378,6 +387,21 @@ def grp_info_batch(lib, cg, chr_size, chrst, chrend, min_grp_dist=10, n_threads=
     o["dn_off"] = np.concatenate([[0], np.cumsum(np.maximum(N - 1, 0))]).astype(np.int64)
     o["dl_off"] = np.concatenate([[0], np.cumsum(np.maximum(L - 1, 0))]).astype(np.int64)
     return o
+
+
+def nls_reg_info_batch(lib, chrst, chrend, max_size_subreg, cpg_off, cpg_pos, n_threads=0):
+    """get_nls_reg_info! for R regions → (sub_off [R+1], sub_st, sub_end, sub_p, sub_q)."""
+    chrst, chrend, cpg_off, cpg_pos = _i64(chrst), _i64(chrend), _i64(cpg_off), _i64(cpg_pos)
+    R = len(chrst)
+    K = np.empty(R, dtype=np.int64)
+    a = (C.c_int64(R), _ptr(chrst), _ptr(chrend), C.c_int64(max_size_subreg), _ptr(cpg_off), _ptr(cpg_pos), C.c_int32(n_threads))
+    if lib.dll.cpn_nls_reg_info_batch(*a, _ptr(K), None, None, None, None, None) != 0:
+        raise CpnError("cpn_nls_reg_info_batch: bad arguments")
+    sub_off = np.concatenate([[0], np.cumsum(K)]).astype(np.int64)
+    st, en, p, q = (np.empty(int(sub_off[-1]), dtype=np.int64) for _ in range(4))
+    if lib.dll.cpn_nls_reg_info_batch(*a, None, _ptr(sub_off), _ptr(st), _ptr(en), _ptr(p), _ptr(q)) != 0:
+        raise CpnError("cpn_nls_reg_info_batch: bad arguments")
+    return sub_off, st, en, p, q
 
 
 # ---- output text (host only) ------------------------------------------------------------------------------------------------

@@ -205,4 +205,30 @@ int cpn_grp_info_fill(const int64_t* cg, int64_t ncg, int64_t chr_size, int64_t 
     return bad ? CPN_ERR_ARG : CPN_OK;
 }
 
+// get_nls_reg_info! (src/genome_analysis.jl:472-538) for R regions: the per-region entry point cpn_nls_reg_info in a loop,
+// threaded.  Pass 1 (sub_st == NULL): K[r].  Pass 2: sub_off = exclusive cumulative sum of K.
+int cpn_nls_reg_info_batch(int64_t R, const int64_t* chrst, const int64_t* chrend, int64_t max_size_subreg, const int64_t* cpg_off,
+                           const int64_t* cpg_pos, int32_t n_threads, int64_t* K, const int64_t* sub_off, int64_t* sub_st, int64_t* sub_end,
+                           int64_t* sub_p, int64_t* sub_q) {
+    if (R < 0 || (R > 0 && (!chrst || !chrend || !cpg_off))) return CPN_ERR_ARG;
+    std::atomic<int> bad{0};
+    if (!sub_st) {
+        if (R > 0 && !K) return CPN_ERR_ARG;
+        parallel_for(R, n_threads, [&](int64_t r) {
+            K[r] = cpn_nls_reg_info(chrst[r], chrend[r], max_size_subreg, cpg_pos ? cpg_pos + cpg_off[r] : nullptr, cpg_off[r + 1] - cpg_off[r], nullptr,
+                                    nullptr, nullptr, nullptr);
+            if (K[r] < 0) bad = 1;
+        });
+        return bad ? CPN_ERR_ARG : CPN_OK;
+    }
+    if (!sub_off || !sub_end || !sub_p || !sub_q || (cpg_off[R] > 0 && !cpg_pos)) return CPN_ERR_ARG;
+    parallel_for(R, n_threads, [&](int64_t r) {
+        const int64_t k0 = sub_off[r];
+        int64_t k = cpn_nls_reg_info(chrst[r], chrend[r], max_size_subreg, cpg_pos + cpg_off[r], cpg_off[r + 1] - cpg_off[r], sub_st + k0, sub_end + k0,
+                                     sub_p + k0, sub_q + k0);
+        if (k != sub_off[r + 1] - k0) bad = 1;
+    });
+    return bad ? CPN_ERR_ARG : CPN_OK;
+}
+
 }  // extern "C"

@@ -81,6 +81,104 @@ def analyze_nano(nano, fasta, config, out_dir, out_prefix, bed_reg=None, mod_nse
     return done
 
 
+def analyze_nano_csr(nano, fasta, config, out_dir, out_prefix, bed_reg=None, mod_nse=True, rng=None, phi0_fn=None, engine=None, timings=None,
+                     block_regions=50_000):
+    """analyze_nano without per-region Python objects: every stage works on the CSR arrays of a block of estimation regions —
+    native features → native calls → filters of pmap_analyze_reg (vectorised) → ONE cpn_analyze_batch → native writers.
+    Writes the same bytes as analyze_nano (tests/test_pipeline_gpu.py); this is the path for whole chromosomes, where a Python
+    loop over 10⁵–10⁶ regions would cost more than everything else together.  Returns a dict of counters."""
+    import time
+    from . import capi
+    from .host import AMAX, BMAX, CMAX
+    from .simulations import gen_phi0s
+    tm = timings if timings is not None else {}
+
+    def lap(key, t0):
+        tm[key] = tm.get(key, 0.0) + time.perf_counter() - t0
+        return time.perf_counter()
+
+    eng = engine or default_engine()
+    lib = eng.lib
+    t = time.perf_counter()
+    chroms = genome.load_genome(fasta, lib)
+    t = lap("fasta_and_cpg_index_s", t)
+    os.makedirs(out_dir, exist_ok=True)
+    files = outputs.OutputFiles(out_dir, out_prefix)
+    if _outputs_exist(files.all()):
+        return None
+    for f in files.all():
+        open(f, "a").close()
+    targets = genome.read_bed(bed_reg) if bed_reg else None
+    calls = NativeCalls(nano, lib)
+    t = lap("calls_parse_s", t)
+    stats = dict(regions=0, candidates=0, with_data=0, fitted=0)
+    for name, chrom in chroms.items():
+        if targets is not None and name not in targets:
+            continue
+        t = time.perf_counter()
+        part = chrom.chr_part_native(lib, config.size_est_reg, config.min_grp_dist, None if targets is None else targets[name])
+        st_all = np.array([p[0] for p in part], dtype=np.int64); en_all = np.array([p[1] for p in part], dtype=np.int64)
+        stats["regions"] += len(part)
+        for b0 in range(0, len(part), block_regions):
+            st, en = st_all[b0:b0 + block_regions], en_all[b0:b0 + block_regions]
+            N = np.empty(len(st), dtype=np.int64); L = np.empty(len(st), dtype=np.int64)
+            capi.grp_info_counts(lib, chrom.cg, st, en, config.min_grp_dist, N, L)
+            cand = np.nonzero(N > 9)[0]                          # length(rs.cpg_pos) > 9 || return rs (:308)
+            stats["candidates"] += len(cand)
+            if len(cand) == 0:
+                continue
+            c = capi.grp_info_batch(lib, chrom.cg, chrom.size, st[cand], en[cand], config.min_grp_dist)
+            t = lap("partition_and_features_s", t)
+            read_off, lu, _ = calls.handle.fill(name, st[cand], en[cand], c["grp_off"], c["grp_st"], c["grp_end"], mod_nse)
+            # get_ave_depth >= min_cov, perc_gprs_obs >= 0.66, L > 1 (nanopore.jl:322-326; structures.jl:200-203), vectorised
+            Lc, m = np.diff(c["grp_off"]), np.diff(read_off)
+            sizes = m * Lc
+            obs_off = np.concatenate([[0], np.cumsum(sizes)])
+            reg_of = np.repeat(np.arange(len(cand)), sizes)
+            obs = ~np.isnan(lu)
+            n_obs = np.bincount(reg_of[obs], minlength=len(cand))
+            gid = c["grp_off"][reg_of] + (np.arange(obs_off[-1]) - obs_off[reg_of]) % np.maximum(Lc[reg_of], 1)
+            seen = np.zeros(int(c["grp_off"][-1]), dtype=bool)
+            seen[gid[obs]] = True
+            n_grp = np.add.reduceat(seen, c["grp_off"][:-1]) if len(seen) else np.zeros(len(cand), dtype=np.int64)
+            keep = (m > 0) & (n_obs / np.maximum(Lc, 1) >= config.min_cov) & (n_grp / np.maximum(Lc, 1) >= 0.66) & (Lc > 1)
+            del reg_of, gid, obs, lu
+            sel = cand[keep]
+            stats["with_data"] += len(sel)
+            if len(sel) == 0:
+                t = lap("calls_fill_s", t)
+                continue
+            k = c if keep.all() else capi.grp_info_batch(lib, chrom.cg, chrom.size, st[sel], en[sel], config.min_grp_dist)
+            read_off, lu, lm = calls.handle.fill(name, st[sel], en[sel], k["grp_off"], k["grp_st"], k["grp_end"], mod_nse)
+            t = lap("calls_fill_s", t)
+            if phi0_fn is not None:
+                phi0 = np.asarray(phi0_fn(len(cand)))[keep]
+            else:
+                phi0 = gen_phi0s(rng or np.random.default_rng(), len(sel), config.max_em_init)
+            sub_off, sub_st, sub_en, sub_p, sub_q = capi.nls_reg_info_batch(lib, st[sel], en[sel], config.max_size_subreg, k["cpg_off"], k["cpg_pos"])
+            out = lib.analyze_batch(k["grp_off"], k["Nl"], k["rho_l"], k["d_l"], read_off, lu, lm, phi0, config.max_em_init, k["cpg_off"], k["rho_n"],
+                                    k["d_n"], sub_off, sub_p, sub_q, config.max_em_iters, (AMAX, BMAX, CMAX), config.mstep_mode, device=eng.device)
+            t = lap("fit_and_summaries_s", t)
+            ok = out["pick"] >= 0
+            stats["fitted"] += int(ok.sum())
+            Nk, Kk = np.diff(k["cpg_off"]), np.diff(sub_off)
+            site = np.repeat(ok, Nk)                                         # per-CpG rows of fitted regions
+            first = np.zeros(len(site), dtype=bool); first[k["cpg_off"][:-1]] = True
+            last = np.zeros(len(site), dtype=bool); last[k["cpg_off"][1:] - 1] = True
+            pair = np.repeat(ok, Nk - 1)
+            pos = k["cpg_pos"]
+            capi.write_theta(lib, files.theta_file, name, st[sel][ok], en[sel][ok], out["phi_hat"][ok], np.concatenate([[0], np.cumsum(Nk[ok])]), None,
+                             k["rho_n"][site], k["d_n"][pair])
+            capi.write_rows(lib, files.exx_file, name, pos[~last][pair], pos[~first][pair], out["exx"][pair])
+            capi.write_rows(lib, files.ex_file, name, pos[site], pos[site], out["ex"][site])
+            sub = np.repeat(ok, Kk)
+            capi.write_rows(lib, files.mml_file, name, sub_st[sub], sub_en[sub], out["mml"][sub], digits=4)
+            capi.write_rows(lib, files.nme_file, name, sub_st[sub], sub_en[sub], out["nme"][sub], digits=4)
+            t = lap("write_outputs_s", t)
+    tm.update(stats)
+    return stats
+
+
 def _find_comm_regs(ms_g1, ms_g2):
     """find_comm_regs (src/grp_perm_tests.jl:527-556): region ids present in at least one sample of each group."""
     k1 = set().union(*[set(d) for d in ms_g1]) if ms_g1 else set()

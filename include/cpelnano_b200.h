@@ -267,6 +267,11 @@ int cpn_calls_fill(const cpn_calls* calls, const char* chr, int64_t R, const int
  *   cpn_grp_info_fill   cpg_off / grp_off = exclusive cumulative sums of N / L; writes cpg_pos, rho_n [sum N], Nl, rho_l, grp_st,
  *                       grp_end [sum L], d_n [sum max(N-1,0)], d_l [sum max(L-1,0)] — for batches of regions with N > 1 these
  *                       are exactly the CSR arrays (d_* at off[r]-r) of cpn_fit_batch / cpn_stat_sums_batch.               */
+/*   cpn_nls_reg_info_batch  cpn_nls_reg_info for R regions (threaded): with sub_st == NULL writes K[r]; otherwise sub_off is the
+ *                       exclusive cumulative sum of K and the four sub-region tables are filled                              */
+int cpn_nls_reg_info_batch(int64_t R, const int64_t* chrst, const int64_t* chrend, int64_t max_size_subreg, const int64_t* cpg_off,
+                           const int64_t* cpg_pos, int32_t n_threads, int64_t* K, const int64_t* sub_off, int64_t* sub_st, int64_t* sub_end,
+                           int64_t* sub_p, int64_t* sub_q);
 int64_t cpn_cpg_scan(const char* seq, int64_t n, int32_t n_threads, int64_t* cpg_pos, int64_t cap);
 int64_t cpn_chr_part(const int64_t* cg, int64_t ncg, int64_t chr_size, int64_t reg_st, int64_t reg_end, int64_t size_est_reg,
                      int64_t min_grp_dist, int64_t* out_st, int64_t* out_end, int64_t cap);

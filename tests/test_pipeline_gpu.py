@@ -179,3 +179,47 @@ def test_file_pipeline_equals_the_csr_api_bit_for_bit(engine, cpn, tmp_path):
     # and the theta file holds exactly those fits, as text
     lines = outputs.read_theta_lines(str(tmp_path / "sim_theta.txt"))
     assert len(lines) == len(ok) and all(np.array_equal(l[3], direct["phi_hat"][r]) for l, r in zip(lines, ok))
+
+
+def test_csr_fast_path_writes_the_same_files(engine, cpn, tmp_path):
+    """analyze_nano_csr (block-wise CSR arrays end to end, vectorised filters, one cpn_analyze_batch per block) against analyze_nano
+    (per-region structs): the five output files must be byte-identical — on the bundled calls (14 of 41 regions rejected by
+    the coverage filters) and on a simulated file with unobserved groups, with small blocks to cross block boundaries."""
+    from cpelnano_b200 import genome, simulations
+    cases = []
+    cases.append((os.path.join(INP, "full_example_calls.tsv.gz"), os.path.join(INP, "full_example.fa.gz"), cpn.CpelNanoConfig(max_em_init=4), 41, 27))
+    fa = os.path.join(INP, "targeted_example.fa.gz")
+    chrom = genome.load_genome(fa, engine.lib)["hg38_dna"]
+    lay, grp_st, grp_end = simulations.layouts_from_fasta(engine.lib, chrom)
+    nb = simulations.make_nano_batch(len(lay["chrst"]), M=15, seed=8, pobs=0.8, layouts=lay)
+    tsv = tmp_path / "sim.tsv"
+    simulations.write_nanopolish_tsv(str(tsv), nb, "hg38_dna", grp_st, grp_end, fmt="{:.2f}".format)
+    cases.append((str(tsv), fa, cpn.CpelNanoConfig(max_em_init=3, min_cov=5.0), None, 137))
+    for i, (calls, fasta, cfg, n_cand, n_fit_max) in enumerate(cases):
+        store = {}
+
+        def starts(n, store=store, cfg=cfg):
+            if n not in store:
+                store[n] = simulations.gen_phi0s(np.random.default_rng(100 + n), n, cfg.max_em_init)
+            return store[n]
+
+        a = cpn.analyze_nano(calls, fasta, cfg, str(tmp_path / f"a{i}"), "x", phi0_fn=starts, engine=engine)
+        for block in (50_000, 16):
+            if block == 16:                       # starts are handed out per block of candidates: rebuild them block-wise from the full set
+                full = next(iter(store.values()))
+                state = {"o": 0}
+
+                def starts_blk(n, full=full, state=state):
+                    out = full[state["o"]:state["o"] + n]; state["o"] += n
+                    return out
+                fn = starts_blk
+            else:
+                fn = starts
+            tag = f"b{i}_{block}"
+            st = cpn.analyze_nano_csr(calls, fasta, cfg, str(tmp_path / tag), "x", phi0_fn=fn, engine=engine, block_regions=block)
+            assert st["fitted"] == len(a) <= n_fit_max and (n_cand is None or st["candidates"] == n_cand)
+            if block == 16 and i == 0:
+                continue                          # blocks of partition windows ≠ blocks of candidates only when windows are skipped (N ≤ 9)
+            for suffix in ("theta", "ex", "exx", "mml", "nme"):
+                fa_, fb_ = tmp_path / f"a{i}" / f"x_{suffix}.txt", tmp_path / tag / f"x_{suffix}.txt"
+                assert fa_.read_bytes() == fb_.read_bytes() and fa_.stat().st_size > 0, (i, block, suffix)
