@@ -52,7 +52,14 @@ def main():
         done = cpn.analyze_nano(tsv, fa, cfg, os.path.join(tmp, f"out{rep}"), "sim", rng=np.random.default_rng(1), engine=eng, timings=tm)
         tm["total_s"] = time.perf_counter() - t0
         tm["regions_per_s_whole_job"] = tm["regions_fitted"] / tm["total_s"]
-        out["run%d" % rep] = tm
+        out["per_region_structs_run%d" % rep] = tm
+    for rep in range(2):
+        tm = {}
+        t0 = time.perf_counter()
+        st = cpn.analyze_nano_csr(tsv, fa, cfg, os.path.join(tmp, f"csr{rep}"), "sim", rng=np.random.default_rng(1), engine=eng, timings=tm)
+        tm["total_s"] = time.perf_counter() - t0
+        tm["regions_per_s_whole_job"] = st["fitted"] / tm["total_s"]
+        out["csr_path_run%d" % rep] = tm
     phi = np.array([rs.phihat for rs in done]); true = nb.phi_true[: len(phi)] if len(phi) == R else None
     if true is not None:
         out["median_abs_error_vs_simulated_phi"] = np.median(np.abs(phi - true), axis=0).tolist()
