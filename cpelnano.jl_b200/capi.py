@@ -17,7 +17,7 @@ SYMBOLS = ["cpn_create", "cpn_destroy", "cpn_last_error", "cpn_version", "cpn_la
            "cpn_stat_sums_batch", "cpn_nls_reg_info", "cpn_cmd_batch", "cpn_grp_unmat_sweep", "cpn_grp_mat_sweep", "cpn_two_samp_pvals", "cpn_two_samp_null_batch", "cpn_grp_test_batch",
            "cpn_calls_open", "cpn_calls_close", "cpn_calls_open_error", "cpn_calls_error", "cpn_calls_num_lines", "cpn_calls_num_reads", "cpn_calls_num_chr",
            "cpn_calls_chr_name", "cpn_calls_chr_lines", "cpn_calls_read_name", "cpn_calls_count_reads", "cpn_calls_fill",
-           "cpn_cpg_scan", "cpn_chr_part", "cpn_grp_info_count", "cpn_grp_info_fill", "cpn_format_f64", "cpn_write_rows", "cpn_write_theta", "cpn_nls_reg_info_batch"]
+           "cpn_cpg_scan", "cpn_chr_part", "cpn_grp_info_count", "cpn_grp_info_fill", "cpn_format_f64", "cpn_write_rows", "cpn_write_theta", "cpn_nls_reg_info_batch", "cpn_calls_coverage"]
 
 
 class CpnError(RuntimeError):
@@ -333,6 +333,16 @@ class Library:
                                          _ptr(nv), _ptr(p))
         self._check(rc, ctx)
         return cnt, nv, p
+
+
+def calls_coverage(lib, grp_off, read_off, log_pyx_u, n_threads=0):
+    """(n_obs, n_grp_obs) per region of an emission batch: numerators of get_ave_depth / perc_gprs_obs (cpn_calls_coverage)."""
+    grp_off, read_off, lu = _i64(grp_off), _i64(read_off), _f64(log_pyx_u)
+    R = len(grp_off) - 1
+    a, b = np.empty(R, dtype=np.int64), np.empty(R, dtype=np.int64)
+    if lib.dll.cpn_calls_coverage(C.c_int64(R), _ptr(grp_off), _ptr(read_off), _ptr(lu), C.c_int32(n_threads), _ptr(a), _ptr(b)) != 0:
+        raise CpnError("cpn_calls_coverage: bad arguments")
+    return a, b
 
 
 # ---- genome features (host only) ------------------------------------------------------------------------------------------

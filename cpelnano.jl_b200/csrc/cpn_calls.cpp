@@ -418,4 +418,31 @@ int cpn_calls_fill(const cpn_calls* c, const char* chr, int64_t R, const int64_t
     return CPN_OK;
 }
 
+// Numerators of get_ave_depth and perc_gprs_obs (src/structures.jl:200-203) for every region of an emission batch:
+// n_obs[r] = observed (read, group) cells, n_grp_obs[r] = groups observed in at least one read.  Works on any CSR emission
+// arrays in the layout of cpn_fit_batch (NaN in log_pyx_u = not observed).
+int cpn_calls_coverage(int64_t R, const int64_t* grp_off, const int64_t* read_off, const double* log_pyx_u, int32_t n_threads,
+                       int64_t* n_obs, int64_t* n_grp_obs) {
+    if (R < 0 || (R > 0 && (!grp_off || !read_off || !n_obs || !n_grp_obs))) return CPN_ERR_ARG;
+    if (R == 0) return CPN_OK;
+    std::vector<int64_t> obs(R + 1);
+    obs[0] = 0;
+    for (int64_t r = 0; r < R; ++r) obs[r + 1] = obs[r] + (read_off[r + 1] - read_off[r]) * (grp_off[r + 1] - grp_off[r]);
+    if (obs[R] > 0 && !log_pyx_u) return CPN_ERR_ARG;
+    for_regions(R, n_threads, [&](int64_t r, RowMap&) {
+        const int64_t L = grp_off[r + 1] - grp_off[r], m = read_off[r + 1] - read_off[r];
+        const double* lu = log_pyx_u + obs[r];
+        int64_t cells = 0, groups = 0;
+        for (int64_t l = 0; l < L; ++l) {
+            int64_t c = 0;
+            for (int64_t k = 0; k < m; ++k) c += (lu[k * L + l] == lu[k * L + l]);
+            cells += c;
+            groups += (c > 0);
+        }
+        n_obs[r] = cells;
+        n_grp_obs[r] = groups;
+    });
+    return CPN_OK;
+}
+
 }  // extern "C"

@@ -132,17 +132,9 @@ def analyze_nano_csr(nano, fasta, config, out_dir, out_prefix, bed_reg=None, mod
             read_off, lu, _ = calls.handle.fill(name, st[cand], en[cand], c["grp_off"], c["grp_st"], c["grp_end"], mod_nse)
             # get_ave_depth >= min_cov, perc_gprs_obs >= 0.66, L > 1 (nanopore.jl:322-326; structures.jl:200-203), vectorised
             Lc, m = np.diff(c["grp_off"]), np.diff(read_off)
-            sizes = m * Lc
-            obs_off = np.concatenate([[0], np.cumsum(sizes)])
-            reg_of = np.repeat(np.arange(len(cand)), sizes)
-            obs = ~np.isnan(lu)
-            n_obs = np.bincount(reg_of[obs], minlength=len(cand))
-            gid = c["grp_off"][reg_of] + (np.arange(obs_off[-1]) - obs_off[reg_of]) % np.maximum(Lc[reg_of], 1)
-            seen = np.zeros(int(c["grp_off"][-1]), dtype=bool)
-            seen[gid[obs]] = True
-            n_grp = np.add.reduceat(seen, c["grp_off"][:-1]) if len(seen) else np.zeros(len(cand), dtype=np.int64)
+            n_obs, n_grp = capi.calls_coverage(lib, c["grp_off"], read_off, lu)
             keep = (m > 0) & (n_obs / np.maximum(Lc, 1) >= config.min_cov) & (n_grp / np.maximum(Lc, 1) >= 0.66) & (Lc > 1)
-            del reg_of, gid, obs, lu
+            del lu
             sel = cand[keep]
             stats["with_data"] += len(sel)
             if len(sel) == 0:

@@ -250,6 +250,10 @@ int64_t cpn_calls_chr_lines(const cpn_calls* calls, int64_t i);
 const char* cpn_calls_read_name(const cpn_calls* calls, int64_t read_id);
 int cpn_calls_count_reads(const cpn_calls* calls, const char* chr, int64_t R, const int64_t* chrst, const int64_t* chrend,
                           int32_t n_threads, int64_t* n_reads);
+/*   cpn_calls_coverage    numerators of get_ave_depth / perc_gprs_obs (src/structures.jl:200-203) for every region of an emission batch:
+ *                          n_obs[r] observed (read, group) cells, n_grp_obs[r] groups observed in at least one read               */
+int cpn_calls_coverage(int64_t R, const int64_t* grp_off, const int64_t* read_off, const double* log_pyx_u, int32_t n_threads,
+                       int64_t* n_obs, int64_t* n_grp_obs);
 int cpn_calls_fill(const cpn_calls* calls, const char* chr, int64_t R, const int64_t* chrst, const int64_t* chrend,
                    const int64_t* grp_off, const int64_t* grp_st, const int64_t* grp_end, int32_t mod_nse,
                    const int64_t* read_off, int32_t n_threads, double* log_pyx_u, double* log_pyx_m, int64_t* read_ids);
