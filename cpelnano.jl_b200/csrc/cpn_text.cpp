@@ -15,6 +15,7 @@
 #include <cstdio>
 #include <cstring>
 #include <string>
+#include <thread>
 #include <vector>
 
 #include "../../include/cpelnano_b200.h"
@@ -71,10 +72,23 @@ inline void put_i64(std::string& s, int64_t v) {
     s.append(buf, r.ptr - buf);
 }
 
-bool append_file(const char* path, const std::string& s) {
+// formats the index range [0, n) in contiguous slices on all host threads; slices are written in order
+template <class F>
+bool format_parallel(const char* path, int64_t n, int64_t min_per_thread, F&& fmt) {
+    int T = (int)std::max(1u, std::thread::hardware_concurrency());
+    T = (int)std::max<int64_t>(1, std::min<int64_t>(T, n / std::max<int64_t>(1, min_per_thread)));
+    std::vector<std::string> parts(T);
+    if (T == 1) {
+        fmt((int64_t)0, n, parts[0]);
+    } else {
+        std::vector<std::thread> th;
+        for (int t = 0; t < T; ++t) th.emplace_back([&, t] { fmt(n * t / T, n * (t + 1) / T, parts[t]); });
+        for (auto& x : th) x.join();
+    }
     FILE* f = fopen(path, "ab");
     if (!f) return false;
-    const bool ok = s.empty() || fwrite(s.data(), 1, s.size(), f) == s.size();
+    bool ok = true;
+    for (const std::string& s : parts) ok = ok && (s.empty() || fwrite(s.data(), 1, s.size(), f) == s.size());
     return fclose(f) == 0 && ok;
 }
 
@@ -97,49 +111,50 @@ int64_t cpn_format_f64(const double* x, int64_t n, char sep, int32_t digits, cha
 int cpn_write_rows(const char* path, const char* chr, int64_t n, const int64_t* a, const int64_t* b, const double* v, int32_t digits,
                    int32_t clamp0, const double* w) {
     if (!path || !chr || n < 0 || (n > 0 && (!a || !b || !v))) return CPN_ERR_ARG;
-    std::string s;
-    s.reserve((size_t)n * 48);
-    for (int64_t i = 0; i < n; ++i) {
-        if (v[i] != v[i]) continue;                            // isnan(x) && continue
-        s += chr; s += '\t';
-        put_i64(s, a[i]); s += '\t';
-        put_i64(s, b[i]); s += '\t';
-        double x = v[i];
-        if (clamp0 && !(x > 0.0)) x = 0.0;                     // max(0.0, tcmd) before rounding (input_output.jl:427)
-        put_f64(s, round_digits(x, digits));
-        if (w) { s += '\t'; put_f64(s, w[i]); }
-        s += '\n';
-    }
-    return append_file(path, s) ? CPN_OK : CPN_ERR_ARG;
+    const bool ok = format_parallel(path, n, 20000, [&](int64_t i0, int64_t i1, std::string& s) {
+        s.reserve((size_t)(i1 - i0) * 48);
+        for (int64_t i = i0; i < i1; ++i) {
+            if (v[i] != v[i]) continue;                        // isnan(x) && continue
+            s += chr; s += '\t';
+            put_i64(s, a[i]); s += '\t';
+            put_i64(s, b[i]); s += '\t';
+            double x = v[i];
+            if (clamp0 && !(x > 0.0)) x = 0.0;                 // max(0.0, tcmd) before rounding (input_output.jl:427)
+            put_f64(s, round_digits(x, digits));
+            if (w) { s += '\t'; put_f64(s, w[i]); }
+            s += '\n';
+        }
+    });
+    return ok ? CPN_OK : CPN_ERR_ARG;
 }
 
 int cpn_write_theta(const char* path, const char* chr, int64_t R, const int64_t* chrst, const int64_t* chrend, const double* phi,
                     const int64_t* grp_off, const double* Nl, const double* rho_l, const double* d_l) {
     if (!path || !chr || R < 0 || (R > 0 && (!chrst || !chrend || !phi || !grp_off || !rho_l || !d_l))) return CPN_ERR_ARG;
-    std::string s;
-    for (int64_t r = 0; r < R; ++r) {
-        const double pa = phi[3 * r], pb = phi[3 * r + 1], pc = phi[3 * r + 2];
-        const int64_t g0 = grp_off[r], L = grp_off[r + 1] - g0;
-        s += chr; s += '\t';
-        put_i64(s, chrst[r]); s += '\t';
-        put_i64(s, chrend[r]); s += '\t';
-        put_f64(s, pa); s += ','; put_f64(s, pb); s += ','; put_f64(s, pc); s += '\t';
-        for (int64_t l = 0; l < L; ++l) {                      // α = (a .+ b .* ρ) .* N, no fused multiply-add (link_functions.jl:19)
-            if (l) s += ',';
-            volatile double t = pb * rho_l[g0 + l];
-            volatile double u = pa + t;
-            put_f64(s, Nl ? u * Nl[g0 + l] : u);
+    const bool ok = format_parallel(path, R, 500, [&](int64_t r0, int64_t r1, std::string& s) {
+        for (int64_t r = r0; r < r1; ++r) {
+            const double pa = phi[3 * r], pb = phi[3 * r + 1], pc = phi[3 * r + 2];
+            const int64_t g0 = grp_off[r], L = grp_off[r + 1] - g0;
+            s += chr; s += '\t';
+            put_i64(s, chrst[r]); s += '\t';
+            put_i64(s, chrend[r]); s += '\t';
+            put_f64(s, pa); s += ','; put_f64(s, pb); s += ','; put_f64(s, pc); s += '\t';
+            for (int64_t l = 0; l < L; ++l) {                  // α = (a .+ b .* ρ) .* N, no fused multiply-add (link_functions.jl:19)
+                if (l) s += ',';
+                volatile double t = pb * rho_l[g0 + l];
+                volatile double u = pa + t;
+                put_f64(s, Nl ? u * Nl[g0 + l] : u);
+            }
+            s += '\t';
+            const double* d = d_l + (g0 - r);
+            for (int64_t l = 0; l + 1 < L; ++l) {              // β = c ./ d
+                if (l) s += ',';
+                put_f64(s, pc / d[l]);
+            }
+            s += '\n';
         }
-        s += '\t';
-        const double* d = d_l + (g0 - r);
-        for (int64_t l = 0; l + 1 < L; ++l) {                  // β = c ./ d
-            if (l) s += ',';
-            put_f64(s, pc / d[l]);
-        }
-        s += '\n';
-        if (s.size() > (1u << 24)) { if (!append_file(path, s)) return CPN_ERR_ARG; s.clear(); }
-    }
-    return append_file(path, s) ? CPN_OK : CPN_ERR_ARG;
+    });
+    return ok ? CPN_OK : CPN_ERR_ARG;
 }
 
 }  // extern "C"
