@@ -17,7 +17,8 @@ SYMBOLS = ["cpn_create", "cpn_destroy", "cpn_last_error", "cpn_version", "cpn_la
            "cpn_stat_sums_batch", "cpn_nls_reg_info", "cpn_cmd_batch", "cpn_grp_unmat_sweep", "cpn_grp_mat_sweep", "cpn_two_samp_pvals", "cpn_two_samp_null_batch", "cpn_grp_test_batch",
            "cpn_calls_open", "cpn_calls_close", "cpn_calls_open_error", "cpn_calls_error", "cpn_calls_num_lines", "cpn_calls_num_reads", "cpn_calls_num_chr",
            "cpn_calls_chr_name", "cpn_calls_chr_lines", "cpn_calls_read_name", "cpn_calls_count_reads", "cpn_calls_fill",
-           "cpn_cpg_scan", "cpn_chr_part", "cpn_grp_info_count", "cpn_grp_info_fill", "cpn_format_f64", "cpn_write_rows", "cpn_write_theta", "cpn_nls_reg_info_batch", "cpn_calls_coverage"]
+           "cpn_cpg_scan", "cpn_chr_part", "cpn_grp_info_count", "cpn_grp_info_fill", "cpn_format_f64", "cpn_write_rows", "cpn_write_theta", "cpn_nls_reg_info_batch", "cpn_calls_coverage", "cpn_fasta_open", "cpn_fasta_close", "cpn_fasta_open_error",
+           "cpn_fasta_num_records", "cpn_fasta_name", "cpn_fasta_length", "cpn_fasta_seq"]
 
 
 class CpnError(RuntimeError):
@@ -343,6 +344,47 @@ def calls_coverage(lib, grp_off, read_off, log_pyx_u, n_threads=0):
     if lib.dll.cpn_calls_coverage(C.c_int64(R), _ptr(grp_off), _ptr(read_off), _ptr(lu), C.c_int32(n_threads), _ptr(a), _ptr(b)) != 0:
         raise CpnError("cpn_calls_coverage: bad arguments")
     return a, b
+
+
+class FastaHandle:
+    """cpn_fasta: records of a FASTA file (plain / .gz) read by the native loader; sequences are zero-copy uint8 views that keep
+    the handle alive."""
+
+    def __init__(self, lib, path):
+        d = lib.dll
+        d.cpn_fasta_open.argtypes = [C.c_char_p, C.POINTER(C.c_void_p)]
+        d.cpn_fasta_close.argtypes = [C.c_void_p]
+        d.cpn_fasta_open_error.restype = C.c_char_p
+        for f in ("cpn_fasta_num_records", "cpn_fasta_length"):
+            getattr(d, f).restype = C.c_int64
+        d.cpn_fasta_num_records.argtypes = [C.c_void_p]
+        d.cpn_fasta_name.restype = C.c_char_p
+        d.cpn_fasta_seq.restype = C.c_void_p
+        d.cpn_fasta_name.argtypes = d.cpn_fasta_length.argtypes = d.cpn_fasta_seq.argtypes = [C.c_void_p, C.c_int64]
+        h = C.c_void_p()
+        rc = d.cpn_fasta_open(str(path).encode(), C.byref(h))
+        if rc != 0 or not h.value:
+            raise CpnError(f"cpn_fasta_open failed with code {rc}: {d.cpn_fasta_open_error().decode()}")
+        self.lib, self.h = lib, h
+        self.records = {}
+        for i in range(int(d.cpn_fasta_num_records(h))):
+            n = int(d.cpn_fasta_length(h, i))
+            ptr = d.cpn_fasta_seq(h, i)
+            arr = np.ctypeslib.as_array(C.cast(ptr, C.POINTER(C.c_uint8)), shape=(n,)) if n > 0 else np.zeros(0, dtype=np.uint8)
+            arr.flags.writeable = False
+            self.records[d.cpn_fasta_name(h, i).decode()] = arr
+
+    def close(self):
+        if self.h is not None:
+            self.records = {}
+            self.lib.dll.cpn_fasta_close(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
 
 
 # ---- genome features (host only) ------------------------------------------------------------------------------------------

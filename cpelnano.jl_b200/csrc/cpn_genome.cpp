@@ -15,8 +15,15 @@
 #include <atomic>
 #include <cstdint>
 #include <cstring>
+#include <string>
 #include <thread>
 #include <vector>
+
+#include <fcntl.h>
+#include <sys/mman.h>
+#include <sys/stat.h>
+#include <unistd.h>
+#include <zlib.h>
 
 #include "../../include/cpelnano_b200.h"
 
@@ -230,5 +237,90 @@ int cpn_nls_reg_info_batch(int64_t R, const int64_t* chrst, const int64_t* chren
     });
     return bad ? CPN_ERR_ARG : CPN_OK;
 }
+
+// ---- FASTA (get_genome_info / get_chr_fa_rec, src/genome_analysis.jl:19-61,283-312) ----------------------------------------------
+// Records are held in memory with line breaks removed; the name is the identifier (text after '>' up to the first blank).
+struct cpn_fasta {
+    std::vector<std::string> names;
+    std::vector<std::string> seqs;
+};
+static thread_local std::string g_fasta_err;
+
+const char* cpn_fasta_open_error(void) { return g_fasta_err.c_str(); }
+
+int cpn_fasta_open(const char* path, cpn_fasta** out) {
+    if (!path || !out) { g_fasta_err = "null argument"; return CPN_ERR_ARG; }
+    *out = nullptr;
+    std::vector<char> zbuf;
+    const char* data = nullptr;
+    size_t size = 0;
+    void* map = nullptr;
+    const size_t plen = strlen(path);
+    if (plen > 3 && strcmp(path + plen - 3, ".gz") == 0) {
+        gzFile g = gzopen(path, "rb");
+        if (!g) { g_fasta_err = std::string("cannot open ") + path; return CPN_ERR_ARG; }
+        gzbuffer(g, 1 << 20);
+        zbuf.resize(1 << 24);
+        for (;;) {
+            if (zbuf.size() - size < (1 << 22)) zbuf.resize(zbuf.size() * 2);
+            int k = gzread(g, zbuf.data() + size, (unsigned)std::min<size_t>(zbuf.size() - size, 1u << 30));
+            if (k < 0) { gzclose(g); g_fasta_err = "gzread failed"; return CPN_ERR_ARG; }
+            if (k == 0) break;
+            size += (size_t)k;
+        }
+        gzclose(g);
+        data = zbuf.data();
+    } else {
+        int fd = open(path, O_RDONLY);
+        if (fd < 0) { g_fasta_err = std::string("cannot open ") + path; return CPN_ERR_ARG; }
+        struct stat st;
+        if (fstat(fd, &st) != 0) { close(fd); g_fasta_err = "fstat failed"; return CPN_ERR_ARG; }
+        size = (size_t)st.st_size;
+        if (size > 0) {
+            map = mmap(nullptr, size, PROT_READ, MAP_PRIVATE, fd, 0);
+            if (map == MAP_FAILED) { close(fd); g_fasta_err = "mmap failed"; return CPN_ERR_NOMEM; }
+            data = (const char*)map;
+        }
+        close(fd);
+    }
+    cpn_fasta* f = new cpn_fasta();
+    // pass 1: record names and exact lengths; pass 2: copy the lines (one exact allocation per record)
+    std::vector<size_t> len;
+    for (int pass = 0; pass < 2; ++pass) {
+        const char* p = data;
+        const char* end = data + size;
+        int64_t rec = -1;
+        while (p < end) {
+            const char* nl = (const char*)memchr(p, '\n', end - p);
+            const char* le = nl ? nl : end;
+            const char* line = p;
+            p = nl ? nl + 1 : end;
+            if (le > line && le[-1] == '\r') --le;
+            if (le == line) continue;
+            if (*line == '>') {
+                ++rec;
+                if (pass == 0) {
+                    const char* q = line + 1;
+                    while (q < le && *q != ' ' && *q != '\t') ++q;
+                    f->names.emplace_back(line + 1, q - (line + 1));
+                    len.push_back(0);
+                } else {
+                    f->seqs[rec].reserve(len[rec]);
+                }
+            } else if (rec >= 0) {
+                if (pass == 0) len[rec] += (size_t)(le - line); else f->seqs[rec].append(line, le - line);
+            }
+        }
+        if (pass == 0) f->seqs.resize(f->names.size());
+    }
+    if (map) munmap(map, size);
+    *out = f;
+    return CPN_OK;
+}
+void cpn_fasta_close(cpn_fasta* f) { delete f; }
+int64_t cpn_fasta_num_records(const cpn_fasta* f) { return f ? (int64_t)f->names.size() : 0; }
+const char* cpn_fasta_name(const cpn_fasta* f, int64_t i) { return (f && i >= 0 && i < (int64_t)f->names.size()) ? f->names[i].c_str() : ""; }
+int64_t cpn_fasta_length(const cpn_fasta* f, int64_t i) { return (f && i >= 0 && i < (int64_t)f->seqs.size()) ? (int64_t)f->seqs[i].size() : -1; }
+const char* cpn_fasta_seq(const cpn_fasta* f, int64_t i) { return (f && i >= 0 && i < (int64_t)f->seqs.size()) ? f->seqs[i].data() : nullptr; }
 
 }  // extern "C"

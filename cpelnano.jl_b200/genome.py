@@ -185,4 +185,15 @@ def read_bed(path):
 
 
 def load_genome(path, lib=None):
-    return {name: Chromosome(name, seq, lib) for name, seq in read_fasta(path).items()}
+    """{record name: Chromosome}.  With `lib` the file is read by the native FASTA loader (cpn_fasta_open) and scanned by
+    cpn_cpg_scan; the Chromosome objects keep the loader's memory alive."""
+    if lib is None:
+        return {name: Chromosome(name, seq) for name, seq in read_fasta(path).items()}
+    from . import capi
+    fa = capi.FastaHandle(lib, path)
+    out = {}
+    for name, seq in fa.records.items():
+        ch = Chromosome(name, seq, lib)
+        ch._fasta = fa
+        out[name] = ch
+    return out

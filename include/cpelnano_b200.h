@@ -276,6 +276,17 @@ int cpn_calls_fill(const cpn_calls* calls, const char* chr, int64_t R, const int
 int cpn_nls_reg_info_batch(int64_t R, const int64_t* chrst, const int64_t* chrend, int64_t max_size_subreg, const int64_t* cpg_off,
                            const int64_t* cpg_pos, int32_t n_threads, int64_t* K, const int64_t* sub_off, int64_t* sub_st, int64_t* sub_end,
                            int64_t* sub_p, int64_t* sub_q);
+/*   cpn_fasta_*         FASTA file (plain or .gz) held in memory, line breaks removed (get_genome_info / get_chr_fa_rec,
+ *                       src/genome_analysis.jl:19-61,283-312); name = identifier up to the first blank; cpn_fasta_seq returns a
+ *                       library-owned pointer to cpn_fasta_length bytes, valid until cpn_fasta_close                          */
+typedef struct cpn_fasta cpn_fasta;
+int  cpn_fasta_open(const char* path, cpn_fasta** out);
+void cpn_fasta_close(cpn_fasta* fa);
+const char* cpn_fasta_open_error(void);
+int64_t cpn_fasta_num_records(const cpn_fasta* fa);
+const char* cpn_fasta_name(const cpn_fasta* fa, int64_t i);
+int64_t cpn_fasta_length(const cpn_fasta* fa, int64_t i);
+const char* cpn_fasta_seq(const cpn_fasta* fa, int64_t i);
 int64_t cpn_cpg_scan(const char* seq, int64_t n, int32_t n_threads, int64_t* cpg_pos, int64_t cap);
 int64_t cpn_chr_part(const int64_t* cg, int64_t ncg, int64_t chr_size, int64_t reg_st, int64_t reg_end, int64_t size_est_reg,
                      int64_t min_grp_dist, int64_t* out_st, int64_t* out_end, int64_t cap);

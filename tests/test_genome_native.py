@@ -118,3 +118,18 @@ def test_scan_edge_cases(lib):
     assert np.array_equal(got, genome.cpg_starts(big)) and len(got) == 1_000_003
     o = capi.grp_info_batch(lib, got[:0], 100, [1], [50])                         # chromosome without CpGs
     assert o["cpg_off"].tolist() == [0, 0] and o["grp_off"].tolist() == [0, 0]
+
+
+def test_native_fasta_loader_equals_python_reader(lib, tmp_path):
+    for fa in ("full_example.fa.gz", "targeted_example.fa.gz"):
+        p = os.path.join(INP, fa)
+        a, b = genome.read_fasta(p), genome.load_genome(p, lib)
+        assert list(a) == list(b) and all(np.array_equal(a[k], b[k].seq) for k in a)
+    p = tmp_path / "multi.fa"
+    p.write_bytes(b">chr1 some description\r\nACGT\r\nacgn\r\n>chr2\tx\nCG\n\nCGCG\n>empty\n>last\nTTTT")      # CRLF, blank line, no final newline
+    a, b = genome.read_fasta(str(p)), genome.load_genome(str(p), lib)
+    assert {k: v.tobytes() for k, v in a.items()} == {k: v.seq.tobytes() for k, v in b.items()} == \
+        {"chr1": b"ACGTacgn", "chr2": b"CGCGCG", "empty": b"", "last": b"TTTT"}
+    assert b["chr2"].cg.tolist() == [1, 3, 5] and b["empty"].cg.tolist() == []
+    with pytest.raises(cpn.CpnError, match="cannot open"):
+        capi.FastaHandle(lib, str(tmp_path / "missing.fa"))
