@@ -82,11 +82,17 @@ def analyze_nano(nano, fasta, config, out_dir, out_prefix, bed_reg=None, mod_nse
 
 
 def analyze_nano_csr(nano, fasta, config, out_dir, out_prefix, bed_reg=None, mod_nse=True, rng=None, phi0_fn=None, engine=None, timings=None,
-                     block_regions=50_000):
+                     block_regions=50_000, rank=0, world=1, phi0_by_region=None):
     """analyze_nano without per-region Python objects: every stage works on the CSR arrays of a block of estimation regions —
     native features → native calls → filters of pmap_analyze_reg (vectorised) → ONE cpn_analyze_batch → native writers.
     Writes the same bytes as analyze_nano (tests/test_pipeline_gpu.py); this is the path for whole chromosomes, where a Python
-    loop over 10⁵–10⁶ regions would cost more than everything else together.  Returns a dict of counters."""
+    loop over 10⁵–10⁶ regions would cost more than everything else together.  Returns a dict of counters.
+
+    Multi-GPU (one process per GPU): with world > 1 rank k analyses the k-th contiguous slice of every
+    chromosome's estimation regions on its own device and writes part files; after a barrier one rank calls merge_shards,
+    which concatenates the parts in (chromosome, rank) order — the bytes of a single-process run.  No collective is needed.
+    phi0_by_region(chr_name, chrst[n]) → [n, max_em_init, 3] makes the starts a function of the region (used by tests so that
+    sharded and unsharded runs see the same starts)."""
     import time
     from . import capi
     from .host import AMAX, BMAX, CMAX
@@ -103,23 +109,33 @@ def analyze_nano_csr(nano, fasta, config, out_dir, out_prefix, bed_reg=None, mod
     chroms = genome.load_genome(fasta, lib)
     t = lap("fasta_and_cpg_index_s", t)
     os.makedirs(out_dir, exist_ok=True)
-    files = outputs.OutputFiles(out_dir, out_prefix)
-    if _outputs_exist(files.all()):
+    final = outputs.OutputFiles(out_dir, out_prefix)
+    if _outputs_exist(final.all()):
         return None
-    for f in files.all():
-        open(f, "a").close()
+    if world == 1:
+        files = final
+        for f in files.all():
+            open(f, "a").close()
+    else:
+        os.makedirs(os.path.join(out_dir, SHARD_DIR), exist_ok=True)
     targets = genome.read_bed(bed_reg) if bed_reg else None
     calls = NativeCalls(nano, lib)
     t = lap("calls_parse_s", t)
     stats = dict(regions=0, candidates=0, with_data=0, fitted=0)
-    for name, chrom in chroms.items():
+    for ci, (name, chrom) in enumerate(chroms.items()):
         if targets is not None and name not in targets:
             continue
         t = time.perf_counter()
         part = chrom.chr_part_native(lib, config.size_est_reg, config.min_grp_dist, None if targets is None else targets[name])
         st_all = np.array([p[0] for p in part], dtype=np.int64); en_all = np.array([p[1] for p in part], dtype=np.int64)
-        stats["regions"] += len(part)
-        for b0 in range(0, len(part), block_regions):
+        if world > 1:                                           # this rank's contiguous slice of the chromosome's regions
+            b = (len(part) * np.arange(world + 1)) // world
+            st_all, en_all = st_all[b[rank]:b[rank + 1]], en_all[b[rank]:b[rank + 1]]
+            files = outputs.OutputFiles(os.path.join(out_dir, SHARD_DIR), _shard_prefix(out_prefix, ci, rank))
+            for f in files.all():
+                open(f, "w").close()
+        stats["regions"] += len(st_all)
+        for b0 in range(0, len(st_all), block_regions):
             st, en = st_all[b0:b0 + block_regions], en_all[b0:b0 + block_regions]
             N = np.empty(len(st), dtype=np.int64); L = np.empty(len(st), dtype=np.int64)
             capi.grp_info_counts(lib, chrom.cg, st, en, config.min_grp_dist, N, L)
@@ -143,7 +159,9 @@ def analyze_nano_csr(nano, fasta, config, out_dir, out_prefix, bed_reg=None, mod
             k = c if keep.all() else capi.grp_info_batch(lib, chrom.cg, chrom.size, st[sel], en[sel], config.min_grp_dist)
             read_off, lu, lm = calls.handle.fill(name, st[sel], en[sel], k["grp_off"], k["grp_st"], k["grp_end"], mod_nse)
             t = lap("calls_fill_s", t)
-            if phi0_fn is not None:
+            if phi0_by_region is not None:
+                phi0 = np.asarray(phi0_by_region(name, st[sel]))
+            elif phi0_fn is not None:
                 phi0 = np.asarray(phi0_fn(len(cand)))[keep]
             else:
                 phi0 = gen_phi0s(rng or np.random.default_rng(), len(sel), config.max_em_init)
@@ -169,6 +187,40 @@ def analyze_nano_csr(nano, fasta, config, out_dir, out_prefix, bed_reg=None, mod
             t = lap("write_outputs_s", t)
     tm.update(stats)
     return stats
+
+
+SHARD_DIR = "_shards"
+
+
+def _shard_prefix(out_prefix, ci, rank):
+    return f"{out_prefix}.c{ci:05d}.r{rank:04d}"
+
+
+def merge_shards(out_dir, out_prefix, world, n_chr=None):
+    """Concatenate the part files the ranks of a sharded analyze_nano_csr run wrote, in (chromosome, rank) order, into the five
+    output files, and remove the parts.  Call on one rank after all ranks have finished."""
+    import glob
+    import shutil
+    final = outputs.OutputFiles(out_dir, out_prefix)
+    sd = os.path.join(out_dir, SHARD_DIR)
+    if n_chr is None:
+        found = glob.glob(os.path.join(sd, f"{out_prefix}.c*.r0000_theta.txt"))
+        cis = sorted(int(os.path.basename(f).split(".c")[-1].split(".r")[0]) for f in found)
+    else:
+        cis = list(range(n_chr))
+    for suffix, dst in zip(("theta", "ex", "exx", "mml", "nme"), final.all()):
+        with open(dst, "ab") as out:
+            for ci in cis:
+                for r in range(world):
+                    src = os.path.join(sd, f"{_shard_prefix(out_prefix, ci, r)}_{suffix}.txt")
+                    if not os.path.exists(src):
+                        if os.path.exists(os.path.join(sd, f"{_shard_prefix(out_prefix, ci, 0)}_{suffix}.txt")):
+                            raise FileNotFoundError(f"shard of rank {r} missing: {src}")
+                        continue
+                    with open(src, "rb") as f:
+                        shutil.copyfileobj(f, out, 1 << 24)
+    shutil.rmtree(sd, ignore_errors=True)
+    return final
 
 
 def _find_comm_regs(ms_g1, ms_g2):

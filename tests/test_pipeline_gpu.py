@@ -223,3 +223,23 @@ def test_csr_fast_path_writes_the_same_files(engine, cpn, tmp_path):
             for suffix in ("theta", "ex", "exx", "mml", "nme"):
                 fa_, fb_ = tmp_path / f"a{i}" / f"x_{suffix}.txt", tmp_path / tag / f"x_{suffix}.txt"
                 assert fa_.read_bytes() == fb_.read_bytes() and fa_.stat().st_size > 0, (i, block, suffix)
+
+
+def test_sharded_run_merges_to_the_single_process_files(engine, cpn, tmp_path):
+    """analyze_nano_csr(rank, world = 3) run shard by shard on this GPU with the real fit, merged: the bytes of the unsharded
+    run (regions are independent and the starts are a function of the region)."""
+    nano, fasta = os.path.join(INP, "full_example_calls.tsv.gz"), os.path.join(INP, "full_example.fa.gz")
+    cfg = cpn.CpelNanoConfig(max_em_init=3)
+
+    def starts(name, st):
+        from cpelnano_b200 import simulations
+        return np.stack([simulations.gen_phi0s(np.random.default_rng(int(s)), 1, 3)[0] for s in st])
+
+    s1 = cpn.analyze_nano_csr(nano, fasta, cfg, str(tmp_path / "one"), "x", engine=engine, phi0_by_region=starts)
+    tot = 0
+    for r in range(3):
+        tot += cpn.analyze_nano_csr(nano, fasta, cfg, str(tmp_path / "three"), "x", engine=engine, phi0_by_region=starts, rank=r, world=3)["fitted"]
+    cpn.merge_shards(str(tmp_path / "three"), "x", 3)
+    assert tot == s1["fitted"] == 27
+    for suffix in ("theta", "ex", "exx", "mml", "nme"):
+        assert (tmp_path / "one" / f"x_{suffix}.txt").read_bytes() == (tmp_path / "three" / f"x_{suffix}.txt").read_bytes()
