@@ -268,6 +268,129 @@ def diff_grp_comp(mod_fls_g1, mod_fls_g2, fasta, config, out_dir, out_prefix, rn
     return files
 
 
+def _read_theta_columns(path):
+    """{chr: (chrst[n], chrend[n], phi[n, 3])} of a model file; only the first four tab-separated fields of a line are split
+    (the α, β lists that follow are kilobytes long and are not needed: read_mod_file_chr recomputes everything from ϕ̂)."""
+    cols = {}
+    with open(path) as f:
+        for line in f:
+            v = line.split("\t", 4)
+            if len(v) < 4:
+                continue
+            c = cols.setdefault(v[0], ([], [], []))
+            c[0].append(int(v[1])); c[1].append(int(v[2])); c[2].append(v[3].rstrip("\n"))
+    out = {}
+    for name, (a, b, p) in cols.items():
+        out[name] = (np.array(a, dtype=np.int64), np.array(b, dtype=np.int64),
+                     np.array([t.split(",") for t in p], dtype=np.float64).reshape(len(p), 3))
+    return out
+
+
+def diff_grp_comp_csr(mod_fls_g1, mod_fls_g2, fasta, config, out_dir, out_prefix, rng=None, engine=None, block_regions=200_000):
+    """diff_grp_comp on arrays: model files → (chrst, chrend, ϕ̂) columns; the features of the common regions come from ONE native
+    feature batch per block (they depend on the region, not on the sample); one cpn_grp_test_batch per distinct (n1, n2) and block;
+    native writers.  Writes the same bytes as diff_grp_comp (tests/test_pipeline_gpu.py)."""
+    from itertools import combinations
+    import math
+    from . import capi
+    from .host import LMAX
+    eng = engine or default_engine()
+    lib = eng.lib
+    chroms = genome.load_genome(fasta, lib)
+    os.makedirs(out_dir, exist_ok=True)
+    files = outputs.OutputDiffFiles(out_dir, out_prefix)
+    if _outputs_exist(files.all()):
+        return None
+    for f in files.all():
+        open(f, "a").close()
+    cols = [[_read_theta_columns(f) for f in grp] for grp in (mod_fls_g1, mod_fls_g2)]
+    matched = bool(config.matched)
+    for name, chrom in chroms.items():
+        # union of the regions of all samples, in coordinate order, and each sample's row for every region (−1 = absent)
+        keys = set()
+        for grp in cols:
+            for c in grp:
+                if name in c:
+                    keys.update(zip(c[name][0].tolist(), c[name][1].tolist()))
+        if not keys:
+            continue
+        regs = sorted(keys)
+        index = {k: i for i, k in enumerate(regs)}
+        rows = []
+        for grp in cols:
+            rg = np.full((len(grp), len(regs)), -1, dtype=np.int64)
+            for s_i, c in enumerate(grp):
+                if name in c:
+                    rg[s_i, [index[k] for k in zip(c[name][0].tolist(), c[name][1].tolist())]] = np.arange(len(c[name][0]))
+            rows.append(rg)
+        if matched:                                          # replicate i of both groups must hold the region (:576-586)
+            n = min(len(rows[0]), len(rows[1]))
+            both = (rows[0][:n] >= 0) & (rows[1][:n] >= 0)
+            pres = [both, both]
+            rows = [rows[0][:n], rows[1][:n]]
+        else:
+            pres = [rows[0] >= 0, rows[1] >= 0]
+        n1s, n2s = pres[0].sum(axis=0), pres[1].sum(axis=0)
+        st_all = np.array([k[0] for k in regs], dtype=np.int64); en_all = np.array([k[1] for k in regs], dtype=np.int64)
+        results = []                                         # (region indices, T, p[, tcmd], sub_off, sub_st, sub_en) per batch
+        for (n1, n2) in sorted(set(zip(n1s.tolist(), n2s.tolist()))):
+            if n1 == 0 or n2 == 0:
+                continue
+            ridx_all = np.nonzero((n1s == n1) & (n2s == n2))[0]
+            S = n1 + n2
+            if matched:
+                if 0.5 ** n1 < 0.05:
+                    exact = 2 ** n1 < LMAX
+                    lab = np.arange(2 ** n1, dtype=np.int64) if exact else (rng or np.random.default_rng()).integers(0, 2 ** n1, size=LMAX)
+                else:
+                    exact, lab = True, np.zeros(0, dtype=np.int64)
+            else:
+                Lc = math.comb(S, n1)
+                if Lc > 20:
+                    exact = Lc < LMAX
+                    allc = np.array(list(combinations(range(1, S + 1), n1)), dtype=np.int32)
+                    lab = allc if exact else allc[np.unique((rng or np.random.default_rng()).integers(0, Lc, size=LMAX))]
+                else:
+                    exact, lab = True, np.zeros((0, n1), dtype=np.int32)
+            for b0 in range(0, len(ridx_all), block_regions):
+                ridx = ridx_all[b0:b0 + block_regions]
+                phi = np.empty((len(ridx), S, 3))
+                for g, (grp, off) in enumerate(((cols[0], 0), (cols[1], n1))):
+                    # samples holding each region, in file order (the reference pushes them in that order, :590-597)
+                    order = np.argsort(~pres[g][:, ridx], axis=0, kind="stable")[: (n1 if g == 0 else n2)]       # [n_g, R] sample ids
+                    for j in range(order.shape[0]):
+                        smp = order[j]
+                        for s_i in np.unique(smp):
+                            m = smp == s_i
+                            phi[m, off + j] = grp[s_i][name][2][rows[g][s_i, ridx[m]]]
+                k = capi.grp_info_batch(lib, chrom.cg, chrom.size, st_all[ridx], en_all[ridx], config.min_grp_dist)
+                sub_off, sub_st, sub_en, sub_p, sub_q = capi.nls_reg_info_batch(lib, st_all[ridx], en_all[ridx], config.max_size_subreg, k["cpg_off"],
+                                                                                 k["cpg_pos"])
+                out = lib.grp_test_batch(n1, n2, matched, phi, k["cpg_off"], k["rho_n"], k["d_n"], sub_off, sub_p, sub_q, lab, exact, device=eng.device)
+                results.append((ridx, out, sub_off, sub_st, sub_en))
+        if not results:
+            continue
+        # rows of all batches in coordinate order of their regions
+        ns = 2 if matched else 3
+        reg_of_row, st_r, en_r, Ts, Ps = [], [], [], [[] for _ in range(3)], [[] for _ in range(3)]
+        for (ridx, out, sub_off, sub_st, sub_en) in results:
+            K = np.diff(sub_off)
+            within = np.arange(sub_off[-1]) - np.repeat(sub_off[:-1], K)
+            reg_of_row.append(np.repeat(ridx, K)); st_r.append(sub_st); en_r.append(sub_en)
+            for j in range(ns):
+                idx = np.repeat(ns * sub_off[:-1] + j * K, K) + within
+                Ts[j].append(out[0][idx]); Ps[j].append(out[2][idx])
+            if matched:
+                Ts[2].append(out[3]); Ps[2].append(np.full(len(out[3]), np.nan))
+        reg_of_row = np.concatenate(reg_of_row)
+        o = np.argsort(reg_of_row, kind="stable")
+        st_r, en_r = np.concatenate(st_r)[o], np.concatenate(en_r)[o]
+        for j, (path, clamp) in enumerate(((files.tmml_file, False), (files.tnme_file, False), (files.tcmd_file, True))):
+            capi.write_rows(lib, path, name, st_r, en_r, np.concatenate(Ts[j])[o], 4, clamp, np.concatenate(Ps[j])[o])
+    outputs.mult_hyp_corr(files, matched=matched)
+    return files
+
+
 def diff_two_samp_comp(mods_path_s1, mods_path_s2, nano_s1, nano_s2, fasta, config, out_dir, out_prefix, mod_nse=True, rng=None,
                        engine=None):
     """Two-sample comparison from two model files and the two samples' calls: observed Tmml / Tnme / Tcmd per sub-region, and

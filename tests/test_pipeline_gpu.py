@@ -60,6 +60,10 @@ def test_diff_grp_comp_writes_the_golden_files(engine, cpn, golden_dir, fasta_fu
         assert np.all(np.abs(dp) <= 1.0 + 1e-9), np.abs(dp).max()
     # an existing output stops a second run (check_diff_output_exists)
     assert cpn.diff_grp_comp(g1, g2, fasta_full, cfg, str(tmp_path), f"cpelnano_grp_comp_{kind}", engine=engine) is None
+    # the array path writes the same bytes
+    files2 = cpn.diff_grp_comp_csr(g1, g2, fasta_full, cfg, str(tmp_path / "csr"), f"cpelnano_grp_comp_{kind}", engine=engine)
+    for a, b in zip(files.all(), files2.all()):
+        assert open(a).read() == open(b).read()
 
 
 @pytest.mark.parametrize("example,fa,prefix,mss", [
