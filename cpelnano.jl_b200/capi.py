@@ -18,7 +18,7 @@ SYMBOLS = ["cpn_create", "cpn_destroy", "cpn_last_error", "cpn_version", "cpn_la
            "cpn_calls_open", "cpn_calls_close", "cpn_calls_open_error", "cpn_calls_error", "cpn_calls_num_lines", "cpn_calls_num_reads", "cpn_calls_num_chr",
            "cpn_calls_chr_name", "cpn_calls_chr_lines", "cpn_calls_read_name", "cpn_calls_count_reads", "cpn_calls_fill",
            "cpn_cpg_scan", "cpn_chr_part", "cpn_grp_info_count", "cpn_grp_info_fill", "cpn_format_f64", "cpn_write_rows", "cpn_write_theta", "cpn_nls_reg_info_batch", "cpn_calls_coverage", "cpn_fasta_open", "cpn_fasta_close", "cpn_fasta_open_error",
-           "cpn_fasta_num_records", "cpn_fasta_name", "cpn_fasta_length", "cpn_fasta_seq"]
+           "cpn_fasta_num_records", "cpn_fasta_name", "cpn_fasta_length", "cpn_fasta_seq", "cpn_add_qvalues"]
 
 
 class CpnError(RuntimeError):
@@ -473,6 +473,12 @@ def write_rows(lib, path, chrom, a, b, v, digits=-1, clamp0=False, w=None):
                                 _ptr(w))
     if rc != 0:
         raise CpnError(f"cpn_write_rows({path}) failed with code {rc}")
+
+
+def add_qvalues(lib, path):
+    rc = lib.dll.cpn_add_qvalues(str(path).encode())
+    if rc != 0:
+        raise CpnError(f"cpn_add_qvalues({path}) failed with code {rc}")
 
 
 def write_theta(lib, path, chrom, chrst, chrend, phi, grp_off, Nl, rho_l, d_l):

@@ -9,12 +9,14 @@
 //
 //   write_output_ex / _exx / _mml / _nme, write_output_tmml / _tnme / _tcmd   → cpn_write_rows
 //   write_output_ϕ (with get_αβ_from_ϕ, src/link_functions.jl:16-25)          → cpn_write_theta
+#include <algorithm>
 #include <charconv>
 #include <cmath>
 #include <cstdint>
 #include <cstdio>
 #include <cstring>
 #include <string>
+#include <string_view>
 #include <thread>
 #include <vector>
 
@@ -155,6 +157,86 @@ int cpn_write_theta(const char* path, const char* chr, int64_t R, const int64_t*
         }
     });
     return ok ? CPN_OK : CPN_ERR_ARG;
+}
+
+// add_qvalues_to_path (src/multiple_hypothesis.jl:14-49): Benjamini–Hochberg q-values of the p column (5th field) appended as
+// a 6th column, NaN where p is NaN; the file is re-written through readdlm / writedlm in the reference, i.e. the float fields
+// are re-printed (shortest text: unchanged for text Julia wrote itself) and integer fields stay integers.
+// MultipleTesting.BenjaminiHochberg: sorted p, p_(i)·(n/i), running minimum from the largest rank down, capped at 1.
+int cpn_add_qvalues(const char* path) {
+    if (!path) return CPN_ERR_ARG;
+    FILE* f = fopen(path, "rb");
+    if (!f) return CPN_OK;                                   // nothing to do (the reference checks filesize(path) > 0)
+    std::string buf;
+    {
+        char tmp[1 << 16];
+        size_t k;
+        while ((k = fread(tmp, 1, sizeof tmp, f)) > 0) buf.append(tmp, k);
+    }
+    fclose(f);
+    if (buf.empty()) return CPN_OK;
+    struct Row { const char *b, *e; double t, p; const char *f3e; };
+    std::vector<Row> rows;
+    const char* p0 = buf.data();
+    const char* end = p0 + buf.size();
+    while (p0 < end) {
+        const char* nl = (const char*)memchr(p0, '\n', end - p0);
+        const char* le = nl ? nl : end;
+        if (le > p0) {
+            const char* fld[6];
+            int nf = 0;
+            fld[nf++] = p0;
+            for (const char* q = p0; q < le && nf < 6; ++q)
+                if (*q == '\t') fld[nf++] = q + 1;
+            if (nf < 5) return CPN_ERR_ARG;
+            auto parse = [&](const char* b, const char* e, double& v) {
+                std::string_view sv(b, e - b);
+                if (sv == "NaN") { v = std::nan(""); return true; }
+                if (sv == "Inf") { v = INFINITY; return true; }
+                if (sv == "-Inf") { v = -INFINITY; return true; }
+                auto r = std::from_chars(b, e, v);
+                return r.ec == std::errc() && r.ptr == e;
+            };
+            Row r;
+            r.b = p0; r.e = le; r.f3e = fld[3] - 1;
+            const char* pe = (nf > 5) ? fld[5] - 1 : le;
+            if (!parse(fld[3], fld[4] - 1, r.t) || !parse(fld[4], pe, r.p)) return CPN_ERR_ARG;
+            rows.push_back(r);
+        }
+        p0 = nl ? nl + 1 : end;
+    }
+    const size_t n_all = rows.size();
+    std::vector<uint32_t> ord;
+    ord.reserve(n_all);
+    for (size_t i = 0; i < n_all; ++i)
+        if (rows[i].p == rows[i].p) ord.push_back((uint32_t)i);
+    std::vector<double> q(n_all, std::nan(""));
+    const size_t n = ord.size();
+    if (n == 1) q[ord[0]] = rows[ord[0]].p;
+    if (n > 1) {
+        std::stable_sort(ord.begin(), ord.end(), [&](uint32_t a, uint32_t b) { return rows[a].p < rows[b].p; });
+        double run = INFINITY;
+        for (size_t k = n; k-- > 0;) {
+            const double v = rows[ord[k]].p * ((double)n / (double)(k + 1));
+            run = std::min(run, v);
+            q[ord[k]] = std::min(1.0, run);
+        }
+    }
+    std::string out;
+    out.reserve(buf.size() + n_all * 24);
+    for (size_t i = 0; i < n_all; ++i) {
+        out.append(rows[i].b, rows[i].f3e - rows[i].b);      // chr, start, end (integers are written back as integers)
+        out += '\t'; put_f64(out, rows[i].t);
+        out += '\t'; put_f64(out, rows[i].p);
+        out += '\t'; put_f64(out, q[i]);
+        out += '\n';
+    }
+    const std::string tmp = std::string(path) + ".tmp";
+    FILE* g = fopen(tmp.c_str(), "wb");
+    if (!g) return CPN_ERR_ARG;
+    const bool ok = fwrite(out.data(), 1, out.size(), g) == out.size();
+    if (fclose(g) != 0 || !ok) return CPN_ERR_ARG;
+    return rename(tmp.c_str(), path) == 0 ? CPN_OK : CPN_ERR_ARG;
 }
 
 }  // extern "C"

@@ -254,11 +254,17 @@ def add_qvalues_to_path(path):
     os.replace(tmp, path)
 
 
-def mult_hyp_corr(files, matched=False):
-    add_qvalues_to_path(files.tmml_file)
-    add_qvalues_to_path(files.tnme_file)
+def mult_hyp_corr(files, matched=False, lib=None):
+    """mult_hyp_corr (src/multiple_hypothesis.jl:55-63); with `lib` through the native cpn_add_qvalues (same bytes)."""
+    if lib is not None:
+        from . import capi
+        add = lambda p: capi.add_qvalues(lib, p)      # noqa: E731
+    else:
+        add = add_qvalues_to_path
+    add(files.tmml_file)
+    add(files.tnme_file)
     if not matched:
-        add_qvalues_to_path(files.tcmd_file)
+        add(files.tcmd_file)
 
 
 # ---- model files ---------------------------------------------------------------------------------------------------------------

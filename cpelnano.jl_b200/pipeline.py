@@ -387,7 +387,7 @@ def diff_grp_comp_csr(mod_fls_g1, mod_fls_g2, fasta, config, out_dir, out_prefix
         st_r, en_r = np.concatenate(st_r)[o], np.concatenate(en_r)[o]
         for j, (path, clamp) in enumerate(((files.tmml_file, False), (files.tnme_file, False), (files.tcmd_file, True))):
             capi.write_rows(lib, path, name, st_r, en_r, np.concatenate(Ts[j])[o], 4, clamp, np.concatenate(Ps[j])[o])
-    outputs.mult_hyp_corr(files, matched=matched)
+    outputs.mult_hyp_corr(files, matched=matched, lib=lib)
     return files
 
 

@@ -308,6 +308,9 @@ int cpn_grp_info_fill(const int64_t* cg, int64_t ncg, int64_t chr_size, int64_t 
 int64_t cpn_format_f64(const double* x, int64_t n, char sep, int32_t digits, char* out, int64_t cap);
 int cpn_write_rows(const char* path, const char* chr, int64_t n, const int64_t* a, const int64_t* b, const double* v, int32_t digits,
                    int32_t clamp0, const double* w);
+/*   cpn_add_qvalues  add_qvalues_to_path (src/multiple_hypothesis.jl:14-49): appends the Benjamini-Hochberg q-value of the p column
+ *                   (NaN where p is NaN) to every row of a tmml / tnme / tcmd file, re-printing the float fields as writedlm does     */
+int cpn_add_qvalues(const char* path);
 int cpn_write_theta(const char* path, const char* chr, int64_t R, const int64_t* chrst, const int64_t* chrend, const double* phi,
                     const int64_t* grp_off, const double* Nl, const double* rho_l, const double* d_l);
 

@@ -191,3 +191,34 @@ def test_writers_create_empty_files_when_nothing_was_processed(tmp_path):
         outputs.write_diff_output([], [], d, False, l)
         assert all(os.path.exists(p) and os.path.getsize(p) == 0 for p in d.all())
         outputs.mult_hyp_corr(d)
+
+
+def test_native_qvalues_equal_python_and_golden(golden, tmp_path):
+    from cpelnano_b200 import capi
+    lib = cpn.Library()
+    for name in ("unmat_tmml", "unmat_tnme", "unmat_tcmd", "mat_tmml", "mat_tnme"):
+        text = golden[f"grp_comp_example/tests/cpelnano_grp_comp_{name}.txt"]
+        stripped = "".join("\t".join(l.split("\t")[:5]) + "\n" for l in text.splitlines())
+        a, b = tmp_path / f"{name}_py.txt", tmp_path / f"{name}_nat.txt"
+        a.write_text(stripped); b.write_text(stripped)
+        outputs.add_qvalues_to_path(str(a))
+        capi.add_qvalues(lib, str(b))
+        assert a.read_text() == b.read_text() == text, name           # the reference's file, byte for byte
+    # NaN p-values, ties, a single row, empty and missing files
+    rng = np.random.default_rng(4)
+    rows = []
+    for i in range(500):
+        p = rng.integers(0, 30) / 29.0 if rng.random() > 0.1 else float("nan")
+        rows.append(f"chr1\t{100 * i}\t{100 * i + 99}\t{outputs.julia_str(outputs.julia_round(rng.standard_normal()))}\t{outputs.julia_str(p)}\n")
+    a, b = tmp_path / "r_py.txt", tmp_path / "r_nat.txt"
+    a.write_text("".join(rows)); b.write_text("".join(rows))
+    outputs.add_qvalues_to_path(str(a)); capi.add_qvalues(lib, str(b))
+    assert a.read_text() == b.read_text() and "NaN\tNaN" in a.read_text()
+    one = tmp_path / "one.txt"
+    one.write_text("chr1\t1\t2\t0.5\t0.25\n")
+    capi.add_qvalues(lib, str(one))
+    assert one.read_text() == "chr1\t1\t2\t0.5\t0.25\t0.25\n"
+    empty = tmp_path / "empty.txt"
+    empty.write_text("")
+    capi.add_qvalues(lib, str(empty)); capi.add_qvalues(lib, str(tmp_path / "missing.txt"))
+    assert empty.read_text() == "" and not (tmp_path / "missing.txt").exists()
