@@ -286,7 +286,7 @@ def _read_theta_columns(path):
     return out
 
 
-def diff_grp_comp_csr(mod_fls_g1, mod_fls_g2, fasta, config, out_dir, out_prefix, rng=None, engine=None, block_regions=200_000):
+def diff_grp_comp_csr(mod_fls_g1, mod_fls_g2, fasta, config, out_dir, out_prefix, rng=None, engine=None, block_regions=200_000, timings=None):
     """diff_grp_comp on arrays: model files → (chrst, chrend, ϕ̂) columns; the features of the common regions come from ONE native
     feature batch per block (they depend on the region, not on the sample); one cpn_grp_test_batch per distinct (n1, n2) and block;
     native writers.  Writes the same bytes as diff_grp_comp (tests/test_pipeline_gpu.py)."""
@@ -294,9 +294,18 @@ def diff_grp_comp_csr(mod_fls_g1, mod_fls_g2, fasta, config, out_dir, out_prefix
     import math
     from . import capi
     from .host import LMAX
+    import time
+    tm = timings if timings is not None else {}
+
+    def lap(key, t0):
+        tm[key] = tm.get(key, 0.0) + time.perf_counter() - t0
+        return time.perf_counter()
+
     eng = engine or default_engine()
     lib = eng.lib
+    t = time.perf_counter()
     chroms = genome.load_genome(fasta, lib)
+    t = lap("fasta_and_cpg_index_s", t)
     os.makedirs(out_dir, exist_ok=True)
     files = outputs.OutputDiffFiles(out_dir, out_prefix)
     if _outputs_exist(files.all()):
@@ -304,6 +313,7 @@ def diff_grp_comp_csr(mod_fls_g1, mod_fls_g2, fasta, config, out_dir, out_prefix
     for f in files.all():
         open(f, "a").close()
     cols = [[_read_theta_columns(f) for f in grp] for grp in (mod_fls_g1, mod_fls_g2)]
+    t = lap("read_model_files_s", t)
     matched = bool(config.matched)
     for name, chrom in chroms.items():
         # union of the regions of all samples, in coordinate order, and each sample's row for every region (−1 = absent)
@@ -363,10 +373,14 @@ def diff_grp_comp_csr(mod_fls_g1, mod_fls_g2, fasta, config, out_dir, out_prefix
                         for s_i in np.unique(smp):
                             m = smp == s_i
                             phi[m, off + j] = grp[s_i][name][2][rows[g][s_i, ridx[m]]]
+                t = lap("match_regions_and_samples_s", t)
                 k = capi.grp_info_batch(lib, chrom.cg, chrom.size, st_all[ridx], en_all[ridx], config.min_grp_dist)
                 sub_off, sub_st, sub_en, sub_p, sub_q = capi.nls_reg_info_batch(lib, st_all[ridx], en_all[ridx], config.max_size_subreg, k["cpg_off"],
                                                                                  k["cpg_pos"])
+                t = lap("features_s", t)
                 out = lib.grp_test_batch(n1, n2, matched, phi, k["cpg_off"], k["rho_n"], k["d_n"], sub_off, sub_p, sub_q, lab, exact, device=eng.device)
+                t = lap("summaries_cmd_and_sweep_gpu_s", t)
+                tm["regions"] = tm.get("regions", 0) + len(ridx)
                 results.append((ridx, out, sub_off, sub_st, sub_en))
         if not results:
             continue
@@ -387,7 +401,10 @@ def diff_grp_comp_csr(mod_fls_g1, mod_fls_g2, fasta, config, out_dir, out_prefix
         st_r, en_r = np.concatenate(st_r)[o], np.concatenate(en_r)[o]
         for j, (path, clamp) in enumerate(((files.tmml_file, False), (files.tnme_file, False), (files.tcmd_file, True))):
             capi.write_rows(lib, path, name, st_r, en_r, np.concatenate(Ts[j])[o], 4, clamp, np.concatenate(Ps[j])[o])
+        t = lap("write_outputs_s", t)
+    t = time.perf_counter()
     outputs.mult_hyp_corr(files, matched=matched, lib=lib)
+    lap("bh_qvalues_s", t)
     return files
 
 
