@@ -303,9 +303,9 @@ def main():
                 "clocks": clocks,
                 "roofline": {"bound": "fp64", "kernel": "k_" + dom, "achieved": achieved, "peak": fp64_peak, "unit": "TFLOP/s",
                              "frac": achieved / fp64_peak if fp64_peak else None,
-                             "traffic": (1.320146e9 + 31.36e6) if (dom == "estep" and R == 100_000) else None,
+                             "traffic": (1.317404e9 + 29.185536e6) if (dom == "estep" and R == 100_000) else None,
                              "traffic_note": "ncu dram__bytes_read.sum+write.sum of the FIRST k_estep launch (10^6 instances) of this configuration, "
-                                             "profiles/r01_ncu_summary.md capture C; algorithmic bytes of that launch = 1.13e9 (packed emissions read once)",
+                                             "profiles/r01_ncu_summary.md capture E (profiles/r01_ncu_capture_E_final.json); algorithmic bytes of that launch = 1.13e9 (packed emissions read once)",
                              "peak_source": "DFMA loop measured on this GPU in this run (MEASURED_PEAKS.json has no FP64 entry)",
                              "launches": int(n_dom), "ms_per_launch": ms_dom / max(n_dom, 1),
                              "flop_model": {"estep": "48 flop/(read,group)/pass", "mstep": "200 flop/group/sweep"},
