@@ -49,6 +49,68 @@ __global__ void __launch_bounds__(128, BLOCKS) k_chain(int steps, double seed, d
     if (s.fp + s.gap + s.gbm + s.gcp == 123.456) out[tid] = s.fm + s.gam + s.gbp + s.gcm;
 }
 
+// Variant with the real operand path: per step three 16-byte broadcast loads of the group's potentials and one 8-byte per-lane load of
+// the emission weight, all from shared memory (filled once), 64-group tile walked round and round.
+struct Tile { double2 w[64], tn[64], bd[64]; };
+template <int BLOCKS>
+__global__ void __launch_bounds__(128, BLOCKS) k_chain_smem(int steps, double seed, double* out) {
+    __shared__ Tile tiles[4];
+    __shared__ double ring[4][8][32];
+    const int tid = blockIdx.x * blockDim.x + threadIdx.x, w = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    for (int j = lane; j < 64; j += 32) {
+        tiles[w].w[j] = make_double2(0.7 + 1e-3 * (j & 7), 1.0);
+        tiles[w].tn[j] = make_double2(0.3 + seed, 2.0);
+        tiles[w].bd[j] = make_double2(0.05, 0.02);
+    }
+    for (int u = 0; u < 8; ++u) ring[w][u][lane] = 0.9 + 1e-4 * lane + 0.2 * (u & 1);
+    __syncwarp();
+    EState s{1.0, 1.0, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0};
+    double sc = 1.0;
+    const Tile& st = tiles[w];
+    for (int i = 0; i < steps; i += 8) {
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+            const int j = (i + u) & 63;
+            const double2 ww = st.w[j], tn = st.tn[j], bd = st.bd[j];
+            site(s, ww.x, ww.y, tn.x, tn.y, bd.x, bd.y, ring[w][u][lane], sc);
+            if (u & 1) sc = inv_pow2_of(s.fp + s.fm); else sc = 1.0;
+        }
+    }
+    if (s.fp + s.gap + s.gbm + s.gcp == 123.456) out[tid] = s.fm + s.gam + s.gbp + s.gcm;
+}
+
+// Variant V2: 40 instead of 48 bytes of warp-uniform operands per step — {e, t} and {nb, sinvd} as two 16-byte loads, N_l as one
+// 8-byte load whose sign bit says which potential is the 1.0 (w = (e, 1) or (1, e)).
+struct Tile2 { double2 et[64], bd[64]; double na[64]; };
+template <int BLOCKS>
+__global__ void __launch_bounds__(128, BLOCKS) k_chain_smem2(int steps, double seed, double* out) {
+    __shared__ Tile2 tiles[4];
+    __shared__ double ring[4][8][32];
+    const int tid = blockIdx.x * blockDim.x + threadIdx.x, w = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    for (int j = lane; j < 64; j += 32) {
+        tiles[w].et[j] = make_double2(0.7 + 1e-3 * (j & 7), 0.3 + seed);
+        tiles[w].bd[j] = make_double2(0.05, 0.02);
+        tiles[w].na[j] = (j & 1) ? 2.0 : -2.0;
+    }
+    for (int u = 0; u < 8; ++u) ring[w][u][lane] = 0.9 + 1e-4 * lane + 0.2 * (u & 1);
+    __syncwarp();
+    EState s{1.0, 1.0, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0};
+    double sc = 1.0;
+    const Tile2& st = tiles[w];
+    for (int i = 0; i < steps; i += 8) {
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+            const int j = (i + u) & 63;
+            const double2 et = st.et[j], bd = st.bd[j];
+            const double nas = st.na[j];
+            const bool pos = __double2hiint(nas) >= 0;
+            site(s, pos ? et.x : 1.0, pos ? 1.0 : et.x, et.y, fabs(nas), bd.x, bd.y, ring[w][u][lane], sc);
+            if (u & 1) sc = inv_pow2_of(s.fp + s.fm); else sc = 1.0;
+        }
+    }
+    if (s.fp + s.gap + s.gbm + s.gcp == 123.456) out[tid] = s.fm + s.gam + s.gbp + s.gcm;
+}
+
 template <int BLOCKS>
 __global__ void __launch_bounds__(128, BLOCKS) k_dfma(int iters, double seed, double* out) {
     const int tid = blockIdx.x * blockDim.x + threadIdx.x;
@@ -91,12 +153,14 @@ static void run(int sms, double* out) {
     const double lanes = (double)grid * 128;
     float t_chain = time_ms([&] { k_chain<BLOCKS><<<grid, 128>>>(steps, 0.0, out); });
     float t_dfma = time_ms([&] { k_dfma<BLOCKS><<<grid, 128>>>(iters, 1.0, out); });
+    float t_smem = time_ms([&] { k_chain_smem<BLOCKS><<<grid, 128>>>(steps, 0.0, out); });
+    float t_smem2 = time_ms([&] { k_chain_smem2<BLOCKS><<<grid, 128>>>(steps, 0.0, out); });
     // FP64 instructions per lane: chain step = 27 (+1 add for the rescale every second step, 1 multiply dropped when sc == 1: 26.5)
     const double chain_inst = lanes * steps * 26.5, dfma_inst = lanes * (double)iters * 8;
     printf("{\"blocks_per_sm\": %d, \"warps_per_sm\": %d, \"chain_step_Ginst_per_s\": %.1f, \"dfma_Ginst_per_s\": %.1f, \"chain_over_dfma\": %.3f, "
-           "\"dfma_TFLOPs\": %.2f}\n",
+           "\"dfma_TFLOPs\": %.2f, \"chain_step_smem_operands_Ginst_per_s\": %.1f, \"smem_over_dfma\": %.3f, \"smem40B_over_dfma\": %.3f}\n",
            BLOCKS, BLOCKS * 4, chain_inst / t_chain / 1e6, dfma_inst / t_dfma / 1e6, (chain_inst / t_chain) / (dfma_inst / t_dfma),
-           2 * dfma_inst / t_dfma / 1e9);
+           2 * dfma_inst / t_dfma / 1e9, chain_inst / t_smem / 1e6, (chain_inst / t_smem) / (dfma_inst / t_dfma), (chain_inst / t_smem2) / (dfma_inst / t_dfma));
 }
 
 int main() {
