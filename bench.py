@@ -259,7 +259,7 @@ def main():
     clocks = sampler.summary()
 
     # end-to-end timing through the host-pointer ABI
-    for _ in range(min(args.warmup, 2)):
+    for _ in range(args.warmup):
         run_step(lib, R, p_host_in, p_host_out, args.n_init, args.max_em_iters, mode, False, local_rank)
     barrier()
     t0 = time.perf_counter()
