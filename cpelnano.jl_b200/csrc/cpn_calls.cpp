@@ -81,6 +81,10 @@ void parse_slice(const char* buf, size_t b, size_t e, Slice& out) {
     const char* p = buf + b;
     const char* end = buf + e;
     out.recs.reserve((e - b) / 90 + 16);
+    struct RCache { std::string_view name; int32_t id = -1; };
+    RCache cache[256];
+    std::string_view last_chr;
+    int32_t last_chr_id = -1;
     while (p < end) {
         const char* nl = (const char*)memchr(p, '\n', end - p);
         const char* le = nl ? nl : end;
@@ -105,11 +109,23 @@ void parse_slice(const char* buf, size_t b, size_t e, Slice& out) {
             continue;
         }
         std::string_view cn(f[0], fe(0) - f[0]), rn(f[4], fe(4) - f[4]);
-        auto ci = out.chr_ix.find(cn);
-        if (ci == out.chr_ix.end()) { ci = out.chr_ix.emplace(cn, (int32_t)out.chr_names.size()).first; out.chr_names.push_back(cn); }
-        auto ri = out.read_ix.find(rn);
-        if (ri == out.read_ix.end()) { ri = out.read_ix.emplace(rn, (int32_t)out.read_names.size()).first; out.read_names.push_back(rn); }
-        r.chr = ci->second; r.read = ri->second;
+        // consecutive lines share the chromosome, and the ~coverage reads that span a position keep alternating: a last-value
+        // check and a small direct-mapped cache (keyed by 8 bytes of the name, verified by a full compare) answer almost every
+        // line without touching the hash maps
+        if (cn != last_chr) {
+            auto ci = out.chr_ix.find(cn);
+            if (ci == out.chr_ix.end()) { ci = out.chr_ix.emplace(cn, (int32_t)out.chr_names.size()).first; out.chr_names.push_back(cn); }
+            last_chr = ci->first; last_chr_id = ci->second;
+        }
+        uint64_t key = 0;
+        memcpy(&key, rn.data() + (rn.size() > 16 ? 8 : 0), std::min<size_t>(8, rn.size() > 16 ? rn.size() - 8 : rn.size()));
+        RCache& rc = cache[(key * 0x9E3779B97F4A7C15ull) >> 56];
+        if (rc.id < 0 || rc.name != rn) {
+            auto ri = out.read_ix.find(rn);
+            if (ri == out.read_ix.end()) { ri = out.read_ix.emplace(rn, (int32_t)out.read_names.size()).first; out.read_names.push_back(rn); }
+            rc.name = ri->first; rc.id = ri->second;
+        }
+        r.chr = last_chr_id; r.read = rc.id;
         out.recs.push_back(r);
     }
 }
