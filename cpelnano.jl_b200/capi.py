@@ -18,7 +18,8 @@ SYMBOLS = ["cpn_create", "cpn_destroy", "cpn_last_error", "cpn_version", "cpn_la
            "cpn_calls_open", "cpn_calls_close", "cpn_calls_open_error", "cpn_calls_error", "cpn_calls_num_lines", "cpn_calls_num_reads", "cpn_calls_num_chr",
            "cpn_calls_chr_name", "cpn_calls_chr_lines", "cpn_calls_read_name", "cpn_calls_count_reads", "cpn_calls_fill",
            "cpn_cpg_scan", "cpn_chr_part", "cpn_grp_info_count", "cpn_grp_info_fill", "cpn_format_f64", "cpn_write_rows", "cpn_write_theta", "cpn_nls_reg_info_batch", "cpn_calls_coverage", "cpn_fasta_open", "cpn_fasta_close", "cpn_fasta_open_error",
-           "cpn_fasta_num_records", "cpn_fasta_name", "cpn_fasta_length", "cpn_fasta_seq", "cpn_add_qvalues"]
+           "cpn_fasta_num_records", "cpn_fasta_name", "cpn_fasta_length", "cpn_fasta_seq", "cpn_add_qvalues", "cpn_theta_open", "cpn_theta_close", "cpn_theta_open_error",
+           "cpn_theta_num_rows", "cpn_theta_num_chr", "cpn_theta_chr_name", "cpn_theta_copy"]
 
 
 class CpnError(RuntimeError):
@@ -473,6 +474,36 @@ def write_rows(lib, path, chrom, a, b, v, digits=-1, clamp0=False, w=None):
                                 _ptr(w))
     if rc != 0:
         raise CpnError(f"cpn_write_rows({path}) failed with code {rc}")
+
+
+def read_theta(lib, path):
+    """{chr: (chrst[n], chrend[n], phi[n, 3])} of a model file, rows in file order (cpn_theta_*)."""
+    d = lib.dll
+    d.cpn_theta_open.argtypes = [C.c_char_p, C.POINTER(C.c_void_p)]
+    d.cpn_theta_close.argtypes = [C.c_void_p]
+    d.cpn_theta_open_error.restype = C.c_char_p
+    d.cpn_theta_num_rows.restype = d.cpn_theta_num_chr.restype = C.c_int64
+    d.cpn_theta_num_rows.argtypes = d.cpn_theta_num_chr.argtypes = [C.c_void_p]
+    d.cpn_theta_chr_name.restype = C.c_char_p
+    d.cpn_theta_chr_name.argtypes = [C.c_void_p, C.c_int64]
+    d.cpn_theta_copy.argtypes = [C.c_void_p] * 5
+    h = C.c_void_p()
+    rc = d.cpn_theta_open(str(path).encode(), C.byref(h))
+    if rc != 0 or not h.value:
+        raise CpnError(f"cpn_theta_open failed with code {rc}: {d.cpn_theta_open_error().decode()}")
+    try:
+        n = int(d.cpn_theta_num_rows(h))
+        names = [d.cpn_theta_chr_name(h, i).decode() for i in range(int(d.cpn_theta_num_chr(h)))]
+        cid, st, en, phi = np.empty(n, dtype=np.int32), np.empty(n, dtype=np.int64), np.empty(n, dtype=np.int64), np.empty((n, 3))
+        if d.cpn_theta_copy(h, _ptr(cid), _ptr(st), _ptr(en), _ptr(phi)) != 0:
+            raise CpnError("cpn_theta_copy failed")
+    finally:
+        d.cpn_theta_close(h)
+    out = {}
+    for i, name in enumerate(names):
+        m = cid == i
+        out[name] = (st[m], en[m], phi[m])
+    return out
 
 
 def add_qvalues(lib, path):

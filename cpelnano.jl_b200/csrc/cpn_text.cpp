@@ -17,6 +17,7 @@
 #include <cstring>
 #include <string>
 #include <string_view>
+#include <unordered_map>
 #include <thread>
 #include <vector>
 
@@ -237,6 +238,94 @@ int cpn_add_qvalues(const char* path) {
     const bool ok = fwrite(out.data(), 1, out.size(), g) == out.size();
     if (fclose(g) != 0 || !ok) return CPN_ERR_ARG;
     return rename(tmp.c_str(), path) == 0 ? CPN_OK : CPN_ERR_ARG;
+}
+
+// Model (theta) files: chr \t chrst \t chrend \t a,b,c [\t α list \t β list] — read_mod_file_chr (src/input_output.jl:581-630) only
+// uses the first four fields (everything else is recomputed from ϕ̂), and the α / β lists are kilobytes per line: fields 1-4 are
+// parsed, the rest of the line is skipped with one memchr.  Rows keep file order; chr_id indexes the table of names in order of
+// first appearance.
+struct cpn_theta {
+    std::vector<std::string> chr_names;
+    std::vector<int32_t> chr_id;
+    std::vector<int64_t> st, en;
+    std::vector<double> phi;     // [n][3]
+};
+static thread_local std::string g_theta_err;
+const char* cpn_theta_open_error(void) { return g_theta_err.c_str(); }
+
+int cpn_theta_open(const char* path, cpn_theta** out) {
+    if (!path || !out) { g_theta_err = "null argument"; return CPN_ERR_ARG; }
+    *out = nullptr;
+    FILE* f = fopen(path, "rb");
+    if (!f) { g_theta_err = std::string("cannot open ") + path; return CPN_ERR_ARG; }
+    std::string buf;
+    {
+        std::vector<char> tmp(1 << 22);
+        size_t k;
+        while ((k = fread(tmp.data(), 1, tmp.size(), f)) > 0) buf.append(tmp.data(), k);
+    }
+    fclose(f);
+    cpn_theta* t = new cpn_theta();
+    std::unordered_map<std::string, int32_t> ix;
+    const char* p = buf.data();
+    const char* end = p + buf.size();
+    int64_t line_no = 0;
+    auto bad = [&]() { g_theta_err = "malformed line " + std::to_string(line_no) + " in " + path; delete t; return CPN_ERR_ARG; };
+    while (p < end) {
+        ++line_no;
+        const char* nl = (const char*)memchr(p, '\n', end - p);
+        const char* le = nl ? nl : end;
+        const char* line = p;
+        p = nl ? nl + 1 : end;
+        if (le > line && le[-1] == '\r') --le;
+        if (le == line) continue;
+        const char* t1 = (const char*)memchr(line, '\t', le - line);
+        if (!t1) return bad();
+        const char* t2 = (const char*)memchr(t1 + 1, '\t', le - t1 - 1);
+        if (!t2) return bad();
+        const char* t3 = (const char*)memchr(t2 + 1, '\t', le - t2 - 1);
+        if (!t3) return bad();
+        const char* t4 = (const char*)memchr(t3 + 1, '\t', le - t3 - 1);
+        const char* pe = t4 ? t4 : le;
+        int64_t a, b;
+        if (std::from_chars(t1 + 1, t2, a).ptr != t2 || std::from_chars(t2 + 1, t3, b).ptr != t3) return bad();
+        double ph[3];
+        const char* q = t3 + 1;
+        for (int k = 0; k < 3; ++k) {
+            const char* c = (k < 2) ? (const char*)memchr(q, ',', pe - q) : pe;
+            if (!c) return bad();
+            std::string_view sv(q, c - q);
+            if (sv == "NaN") ph[k] = std::nan("");
+            else {
+                auto r = std::from_chars(q, c, ph[k]);
+                if (r.ec != std::errc() || r.ptr != c) return bad();
+            }
+            q = c + 1;
+        }
+        std::string name(line, t1 - line);
+        auto it = ix.find(name);
+        if (it == ix.end()) { it = ix.emplace(name, (int32_t)t->chr_names.size()).first; t->chr_names.push_back(name); }
+        t->chr_id.push_back(it->second);
+        t->st.push_back(a); t->en.push_back(b);
+        t->phi.push_back(ph[0]); t->phi.push_back(ph[1]); t->phi.push_back(ph[2]);
+    }
+    *out = t;
+    return CPN_OK;
+}
+void cpn_theta_close(cpn_theta* t) { delete t; }
+int64_t cpn_theta_num_rows(const cpn_theta* t) { return t ? (int64_t)t->st.size() : 0; }
+int64_t cpn_theta_num_chr(const cpn_theta* t) { return t ? (int64_t)t->chr_names.size() : 0; }
+const char* cpn_theta_chr_name(const cpn_theta* t, int64_t i) { return (t && i >= 0 && i < (int64_t)t->chr_names.size()) ? t->chr_names[i].c_str() : ""; }
+int cpn_theta_copy(const cpn_theta* t, int32_t* chr_id, int64_t* chrst, int64_t* chrend, double* phi) {
+    if (!t) return CPN_ERR_ARG;
+    const size_t n = t->st.size();
+    if (n == 0) return CPN_OK;
+    if (!chr_id || !chrst || !chrend || !phi) return CPN_ERR_ARG;
+    memcpy(chr_id, t->chr_id.data(), n * sizeof(int32_t));
+    memcpy(chrst, t->st.data(), n * sizeof(int64_t));
+    memcpy(chrend, t->en.data(), n * sizeof(int64_t));
+    memcpy(phi, t->phi.data(), 3 * n * sizeof(double));
+    return CPN_OK;
 }
 
 }  // extern "C"

@@ -312,7 +312,7 @@ def diff_grp_comp_csr(mod_fls_g1, mod_fls_g2, fasta, config, out_dir, out_prefix
         return None
     for f in files.all():
         open(f, "a").close()
-    cols = [[_read_theta_columns(f) for f in grp] for grp in (mod_fls_g1, mod_fls_g2)]
+    cols = [[capi.read_theta(lib, f) for f in grp] for grp in (mod_fls_g1, mod_fls_g2)]        # native; _read_theta_columns is the Python statement
     t = lap("read_model_files_s", t)
     matched = bool(config.matched)
     for name, chrom in chroms.items():

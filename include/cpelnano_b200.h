@@ -311,6 +311,16 @@ int cpn_write_rows(const char* path, const char* chr, int64_t n, const int64_t* 
 /*   cpn_add_qvalues  add_qvalues_to_path (src/multiple_hypothesis.jl:14-49): appends the Benjamini-Hochberg q-value of the p column
  *                   (NaN where p is NaN) to every row of a tmml / tnme / tcmd file, re-printing the float fields as writedlm does     */
 int cpn_add_qvalues(const char* path);
+/*   cpn_theta_*      model (theta) files as read_mod_file_chr uses them (src/input_output.jl:581-630): chromosome, chrst, chrend and
+ *                   phi = (a, b, c) of every line, in file order; the alpha / beta lists that may follow are skipped                 */
+typedef struct cpn_theta cpn_theta;
+int  cpn_theta_open(const char* path, cpn_theta** out);
+void cpn_theta_close(cpn_theta* th);
+const char* cpn_theta_open_error(void);
+int64_t cpn_theta_num_rows(const cpn_theta* th);
+int64_t cpn_theta_num_chr(const cpn_theta* th);
+const char* cpn_theta_chr_name(const cpn_theta* th, int64_t i);
+int cpn_theta_copy(const cpn_theta* th, int32_t* chr_id, int64_t* chrst, int64_t* chrend, double* phi);
 int cpn_write_theta(const char* path, const char* chr, int64_t R, const int64_t* chrst, const int64_t* chrend, const double* phi,
                     const int64_t* grp_off, const double* Nl, const double* rho_l, const double* d_l);
 

@@ -222,3 +222,28 @@ def test_native_qvalues_equal_python_and_golden(golden, tmp_path):
     empty.write_text("")
     capi.add_qvalues(lib, str(empty)); capi.add_qvalues(lib, str(tmp_path / "missing.txt"))
     assert empty.read_text() == "" and not (tmp_path / "missing.txt").exists()
+
+
+def test_native_theta_reader_equals_python_reader(golden, tmp_path):
+    from cpelnano_b200 import capi, pipeline
+    lib = cpn.Library()
+    for name in ("full_example/cpelnano/full_example_mod_nse_true_theta.txt", "grp_comp_example/mod_files/g1_rep3.txt",
+                 "targeted_example/cpelnano/targeted_example_theta.txt"):
+        p = tmp_path / "t.txt"
+        p.write_text(golden[name])
+        a, b = pipeline._read_theta_columns(str(p)), capi.read_theta(lib, str(p))
+        assert list(a) == list(b)
+        for k in a:
+            assert all(np.array_equal(x, y) for x, y in zip(a[k], b[k]))
+    # two chromosomes interleaved, 4-column lines, NaN, CRLF, blank line
+    p = tmp_path / "m.txt"
+    p.write_bytes(b"chr2\t10\t20\t0.5,-1.25,3.0\r\nchr1\t1\t5\tNaN,NaN,NaN\talpha\tbeta\n\nchr2\t21\t30\t1e-3,2,3\n")
+    b = capi.read_theta(lib, str(p))
+    assert list(b) == ["chr2", "chr1"] and b["chr2"][0].tolist() == [10, 21] and b["chr2"][2].tolist() == [[0.5, -1.25, 3.0], [1e-3, 2.0, 3.0]]
+    assert np.isnan(b["chr1"][2]).all()
+    bad = tmp_path / "bad.txt"
+    bad.write_text("chr1\t1\t5\t0.5,0.1\n")
+    with pytest.raises(cpn.CpnError, match="malformed line 1"):
+        capi.read_theta(lib, str(bad))
+    with pytest.raises(cpn.CpnError, match="cannot open"):
+        capi.read_theta(lib, str(tmp_path / "missing.txt"))
