@@ -548,6 +548,9 @@ __device__ void eval_grad_hess(const SweepSite* __restrict__ tbl, int L, double 
     }
     SitePot pot = site_pot(raw, 1, neg, a, b, cabs);
     if (!RING) raw = load_site(tbl + (L > 2 ? 2 : 0));
+    // unrolled by two: the 20 doubles of loop-carried state ping-pong between two register sets instead of being copied back
+    // (34 register moves per group otherwise, each an issue slot next to the 2-cycle FP64 issues)
+#pragma unroll 2
     for (int l = 1; l < L; ++l) {
         const SitePot p = pot;
         SweepSite rnext;
