@@ -10,11 +10,12 @@ import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 MSTEP_FD, MSTEP_ANALYTIC = 0, 1
+FIT_NONE, FIT_NUMERICAL, FIT_FILTERED = -1, -2, -16        # status words (include/cpelnano_b200.h)
 
 # every exported symbol of include/cpelnano_b200.h (tests check the library exports exactly these)
-SYMBOLS = ["cpn_create", "cpn_destroy", "cpn_last_error", "cpn_version", "cpn_last_device_ms", "cpn_last_launches",
-           "cpn_measure_fp64_peak", "cpn_set_profile", "cpn_get_profile", "cpn_analyze_batch", "cpn_analyze_batch_device", "cpn_fit_batch", "cpn_fit_batch_device", "cpn_estep_batch", "cpn_mstep_batch",
-           "cpn_stat_sums_batch", "cpn_nls_reg_info", "cpn_cmd_batch", "cpn_grp_unmat_sweep", "cpn_grp_mat_sweep", "cpn_two_samp_pvals", "cpn_two_samp_null_batch", "cpn_grp_test_batch",
+SYMBOLS = ["cpn_create", "cpn_destroy", "cpn_last_error", "cpn_version", "cpn_last_device_ms", "cpn_last_launches", "cpn_last_work",
+           "cpn_measure_fp64_peak", "cpn_set_seed", "cpn_rng_phi0", "cpn_rng_perm", "cpn_set_profile", "cpn_get_profile", "cpn_analyze_batch", "cpn_analyze_batch_device", "cpn_fit_batch", "cpn_fit_batch_device", "cpn_estep_batch", "cpn_mstep_batch",
+           "cpn_stat_sums_batch", "cpn_nls_reg_info", "cpn_cmd_batch", "cpn_grp_unmat_sweep", "cpn_grp_mat_sweep", "cpn_two_samp_pvals", "cpn_two_samp_null_batch", "cpn_two_samp_test_batch", "cpn_grp_test_batch", "cpn_region_filter",
            "cpn_calls_open", "cpn_calls_close", "cpn_calls_open_error", "cpn_calls_error", "cpn_calls_num_lines", "cpn_calls_num_reads", "cpn_calls_num_chr",
            "cpn_calls_chr_name", "cpn_calls_chr_lines", "cpn_calls_read_name", "cpn_calls_count_reads", "cpn_calls_fill",
            "cpn_cpg_scan", "cpn_chr_part", "cpn_grp_info_count", "cpn_grp_info_fill", "cpn_format_f64", "cpn_write_rows", "cpn_write_theta", "cpn_nls_reg_info_batch", "cpn_calls_coverage", "cpn_fasta_open", "cpn_fasta_close", "cpn_fasta_open_error",
@@ -110,11 +111,23 @@ class Library:
     def last_launches(self, device=0):
         return self.dll.cpn_last_launches(self.ctx(device))
 
+    def last_work(self, device=0):
+        """(E-step read·groups, M-step sweep·groups, score read·groups, EM instances) of the last fit call (cpn_last_work)."""
+        w = np.zeros(4)
+        ctx = self.ctx(device)
+        self._check(self.dll.cpn_last_work(ctx, _ptr(w)), ctx)
+        return w
+
     def measure_fp64_peak(self, device=0):
         v = C.c_double()
         ctx = self.ctx(device)
         self._check(self.dll.cpn_measure_fp64_peak(ctx, C.byref(v)), ctx)
         return v.value
+
+    def set_seed(self, seed, device=0):
+        """Seed of the on-device start / permutation stream used wherever phi0 / perm_ids are None (cpn_set_seed)."""
+        ctx = self.ctx(device)
+        self._check(self.dll.cpn_set_seed(ctx, C.c_uint64(int(seed) & 0xFFFFFFFFFFFFFFFF)), ctx)
 
     KERNEL_CLASSES = ("prep", "estep", "mstep", "score", "pick", "statsum", "cmd", "sweep")
 
@@ -158,9 +171,11 @@ class Library:
     def fit_batch(self, grp_off, Nl, rho_l, d_l, read_off, log_pyx_u, log_pyx_m, phi0, n_init, max_em_iters=20,
                   box=(20.0, 150.0, 50.0), mstep_mode=MSTEP_ANALYTIC, per_start=False, device=0):
         grp_off, read_off = _i64(grp_off), _i64(read_off)
-        Nl, rho_l, d_l, lu, lm, phi0 = _f64(Nl), _f64(rho_l), _f64(d_l), _f64(log_pyx_u), _f64(log_pyx_m), _f64(phi0)
+        Nl, rho_l, d_l, lu, lm = _f64(Nl), _f64(rho_l), _f64(d_l), _f64(log_pyx_u), _f64(log_pyx_m)
         R = len(grp_off) - 1
-        assert phi0.size == R * n_init * 3, "phi0 must be [R, n_init, 3]"
+        if phi0 is not None:                       # None: starts drawn on the device from the context's seed (set_seed)
+            phi0 = _f64(phi0)
+            assert phi0.size == R * n_init * 3, "phi0 must be [R, n_init, 3]"
         phi_hat, Q = np.empty((R, 3)), np.empty(R)
         status = np.empty(R, dtype=np.int32)
         counters = np.empty((R, 4), dtype=np.int64)
@@ -309,8 +324,9 @@ class Library:
                             sub_off, sub_p, sub_q, max_em_iters=20, box=(20.0, 150.0, 50.0), mstep_mode=MSTEP_ANALYTIC, device=0):
         """cpn_two_samp_null_batch: returns (T_null flat [Σ P_r·3·K_r], fit_status [Σ P_r·2])."""
         grp_off, read_off, perm_off, n1 = _i64(grp_off), _i64(read_off), _i64(perm_off), _i64(n1)
-        Nl, rho_l, d_l, lu, lm, phi0 = _f64(Nl), _f64(rho_l), _f64(d_l), _f64(lu), _f64(lm), _f64(phi0)
-        perm_ids = _i32(perm_ids)
+        Nl, rho_l, d_l, lu, lm = _f64(Nl), _f64(rho_l), _f64(d_l), _f64(lu), _f64(lm)
+        phi0 = None if phi0 is None else _f64(phi0)
+        perm_ids = None if perm_ids is None else _i32(perm_ids)
         cpg_off, sub_off, sub_p, sub_q, rho_n, d_n = _i64(cpg_off), _i64(sub_off), _i64(sub_p), _i64(sub_q), _f64(rho_n), _f64(d_n)
         R = len(grp_off) - 1
         P_r = np.diff(perm_off)
@@ -324,6 +340,35 @@ class Library:
         self._check(rc, ctx)
         return T, status
 
+    def two_samp_test_batch(self, grp_off, Nl, rho_l, d_l, read_off, lu, lm, n1, phi_s1, phi_s2, perm_off, perm_ids, exact, phi0, n_init,
+                            cpg_off, rho_n, d_n, sub_off, sub_p, sub_q, max_em_iters=20, box=(20.0, 150.0, 50.0), mstep_mode=MSTEP_ANALYTIC,
+                            want_null=False, device=0):
+        """cpn_two_samp_test_batch: the whole two-sample test of R regions.  perm_ids / phi0 may be None (drawn on the device from
+        the context's seed).  Returns dict(T, cnt, n_valid, pval [ΣK·3], optionally T_null and fit_status)."""
+        grp_off, read_off, perm_off, n1 = _i64(grp_off), _i64(read_off), _i64(perm_off), _i64(n1)
+        Nl, rho_l, d_l, lu, lm = _f64(Nl), _f64(rho_l), _f64(d_l), _f64(lu), _f64(lm)
+        phi_s1, phi_s2 = _f64(phi_s1), _f64(phi_s2)
+        perm_ids = None if perm_ids is None else _i32(perm_ids)
+        phi0 = None if phi0 is None else _f64(phi0)
+        exact = None if exact is None else _i32(exact)
+        cpg_off, sub_off, sub_p, sub_q, rho_n, d_n = _i64(cpg_off), _i64(sub_off), _i64(sub_p), _i64(sub_q), _f64(rho_n), _f64(d_n)
+        R, sK = len(grp_off) - 1, int(sub_off[-1])
+        out = dict(T=np.empty(3 * sK), cnt=np.empty(3 * sK, dtype=np.int64), n_valid=np.empty(3 * sK, dtype=np.int64), pval=np.empty(3 * sK))
+        T_null = status = None
+        if want_null:
+            T_null = np.empty(int((3 * np.diff(perm_off) * np.diff(sub_off)).sum()))
+            status = np.empty(int(2 * perm_off[-1]), dtype=np.int32)
+            out.update(T_null=T_null, fit_status=status)
+        ctx = self.ctx(device)
+        rc = self.dll.cpn_two_samp_test_batch(ctx, C.c_int64(R), _ptr(grp_off), _ptr(Nl), _ptr(rho_l), _ptr(d_l), _ptr(read_off), _ptr(lu), _ptr(lm),
+                                              _ptr(n1), _ptr(phi_s1), _ptr(phi_s2), _ptr(perm_off), _ptr(perm_ids), _ptr(exact), _ptr(phi0),
+                                              C.c_int32(n_init), C.c_int32(max_em_iters), C.c_double(box[0]), C.c_double(box[1]),
+                                              C.c_double(box[2]), C.c_int32(mstep_mode), _ptr(cpg_off), _ptr(rho_n), _ptr(d_n), _ptr(sub_off),
+                                              _ptr(sub_p), _ptr(sub_q), _ptr(out["T"]), _ptr(out["cnt"]), _ptr(out["n_valid"]), _ptr(out["pval"]),
+                                              _ptr(T_null), _ptr(status))
+        self._check(rc, ctx)
+        return out
+
     def two_samp_pvals(self, tbl_off, P, T_obs, T_null, exact, device=0):
         tbl_off = _i64(tbl_off)
         T_obs, T_null = _f64(T_obs), _f64(T_null)
@@ -335,6 +380,32 @@ class Library:
                                          _ptr(nv), _ptr(p))
         self._check(rc, ctx)
         return cnt, nv, p
+
+
+def rng_phi0(lib, seed, region, n_init, perm=-1, half=0):
+    """The starts the device draws for one EM unit when phi0 is None (cpn_rng_phi0)."""
+    out = np.empty((n_init, 3))
+    if lib.dll.cpn_rng_phi0(C.c_uint64(int(seed) & 0xFFFFFFFFFFFFFFFF), C.c_int64(region), C.c_int64(perm), C.c_int32(half), C.c_int32(n_init), _ptr(out)) != 0:
+        raise CpnError("cpn_rng_phi0: bad arguments")
+    return out
+
+
+def rng_perm(lib, seed, region, perm, n, n1):
+    """The ascending 1-based sample-1 indices the device draws for a permutation when perm_ids is None (cpn_rng_perm)."""
+    out = np.empty(n1, dtype=np.int32)
+    if lib.dll.cpn_rng_perm(C.c_uint64(int(seed) & 0xFFFFFFFFFFFFFFFF), C.c_int64(region), C.c_int64(perm), C.c_int32(n), C.c_int32(n1), _ptr(out)) != 0:
+        raise CpnError("cpn_rng_perm: bad arguments")
+    return out
+
+
+def region_filter(lib, n_cpg, grp_off, read_off, log_pyx_u, min_cov, n_threads=0):
+    """Status words of pmap_analyze_reg's data filters (cpn_region_filter): 0 = fit the region, else FIT_FILTERED − reasons."""
+    n_cpg, grp_off, read_off, lu = _i64(n_cpg), _i64(grp_off), _i64(read_off), _f64(log_pyx_u)
+    st = np.empty(len(n_cpg), dtype=np.int32)
+    if lib.dll.cpn_region_filter(C.c_int64(len(n_cpg)), _ptr(n_cpg), _ptr(grp_off), _ptr(read_off), _ptr(lu), C.c_double(min_cov),
+                                 C.c_int32(n_threads), _ptr(st)) != 0:
+        raise CpnError("cpn_region_filter: bad arguments")
+    return st
 
 
 def calls_coverage(lib, grp_off, read_off, log_pyx_u, n_threads=0):

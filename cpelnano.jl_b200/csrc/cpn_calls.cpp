@@ -104,7 +104,10 @@ void parse_slice(const char* buf, size_t b, size_t e, Slice& out) {
         if (nf < 8) { if (out.bad_line < 0) out.bad_line = line - buf; continue; }
         auto fe = [&](int i) { return (i + 1 < nf) ? f[i + 1] - 1 : le; };
         Rec r;
-        if (!parse_num(f[2], fe(2), r.start) || !parse_num(f[3], fe(3), r.end) || !parse_f64(f[6], fe(6), r.lm) || !parse_f64(f[7], fe(7), r.lu)) {
+        // A non-finite log-likelihood is a malformed line: NaN is the "group not observed" marker of the emission layout, so a NaN
+        // call would silently turn into an unobserved group (the reference would carry the NaN into the EM and skip the region).
+        if (!parse_num(f[2], fe(2), r.start) || !parse_num(f[3], fe(3), r.end) || !parse_f64(f[6], fe(6), r.lm) || !parse_f64(f[7], fe(7), r.lu) ||
+            !std::isfinite(r.lm) || !std::isfinite(r.lu)) {
             if (out.bad_line < 0) out.bad_line = line - buf;
             continue;
         }
@@ -277,9 +280,9 @@ int cpn_calls_open(const char* path, int32_t n_threads, cpn_calls** out) {
     for (ChrCols& cc : c->chrs) {
         const size_t n = cc.start.size();
         if (!std::is_sorted(cc.start.begin(), cc.start.end())) {
-            std::vector<uint32_t> ord(n);
-            for (size_t i = 0; i < n; ++i) ord[i] = (uint32_t)i;
-            std::stable_sort(ord.begin(), ord.end(), [&](uint32_t a, uint32_t b) { return cc.start[a] < cc.start[b]; });
+            std::vector<size_t> ord(n);                 // size_t: a chromosome may hold more than 2^32 lines
+            for (size_t i = 0; i < n; ++i) ord[i] = i;
+            std::stable_sort(ord.begin(), ord.end(), [&](size_t a, size_t b) { return cc.start[a] < cc.start[b]; });
             auto perm = [&](auto& v) { auto w = v; for (size_t i = 0; i < n; ++i) v[i] = w[ord[i]]; };
             perm(cc.start); perm(cc.end); perm(cc.read); perm(cc.lm); perm(cc.lu);
         }
@@ -299,6 +302,7 @@ int64_t cpn_calls_chr_lines(const cpn_calls* c, int64_t i) { return (c && i >= 0
 const char* cpn_calls_read_name(const cpn_calls* c, int64_t id) {
     return (c && id >= 0 && id < (int64_t)c->read_names.size()) ? c->read_names[id].c_str() : "";
 }
+
 
 }  // extern "C"
 
@@ -458,6 +462,33 @@ int cpn_calls_coverage(int64_t R, const int64_t* grp_off, const int64_t* read_of
         n_obs[r] = cells;
         n_grp_obs[r] = groups;
     });
+    return CPN_OK;
+}
+
+
+// The data filters of pmap_analyze_reg (src/nanopore.jl:309, 322-326) for every region of an emission batch, as status words:
+// 0 = the region goes on to the EM; otherwise CPN_FIT_FILTERED − (OR of the CPN_FILTER_* reasons).  n_cpg[r] = number of CpG
+// sites of region r (length(rs.cpg_pos)); get_ave_depth = observed cells / L, perc_gprs_obs = observed groups / L
+// (src/structures.jl:200-203), both compared in double precision as the reference does.
+int cpn_region_filter(int64_t R, const int64_t* n_cpg, const int64_t* grp_off, const int64_t* read_off, const double* log_pyx_u, double min_cov,
+                      int32_t n_threads, int32_t* status) {
+    if (R < 0 || (R > 0 && (!n_cpg || !grp_off || !read_off || !status))) return CPN_ERR_ARG;
+    if (R == 0) return CPN_OK;
+    std::vector<int64_t> n_obs(R), n_grp(R);
+    int rc = cpn_calls_coverage(R, grp_off, read_off, log_pyx_u, n_threads, n_obs.data(), n_grp.data());
+    if (rc != CPN_OK) return rc;
+    for (int64_t r = 0; r < R; ++r) {
+        const int64_t L = grp_off[r + 1] - grp_off[r], m = read_off[r + 1] - read_off[r];
+        int why = 0;
+        if (!(n_cpg[r] > 9)) why |= CPN_FILTER_FEW_CPGS;
+        if (m <= 0) why |= CPN_FILTER_NO_READS;
+        if (L > 0) {
+            if (!((double)n_obs[r] / (double)L >= min_cov)) why |= CPN_FILTER_LOW_DEPTH;
+            if (!((double)n_grp[r] / (double)L >= 0.66)) why |= CPN_FILTER_FEW_GROUPS_OBS;
+        }
+        if (!(L > 1)) why |= CPN_FILTER_ONE_GROUP;
+        status[r] = why ? CPN_FIT_FILTERED - why : 0;
+    }
     return CPN_OK;
 }
 

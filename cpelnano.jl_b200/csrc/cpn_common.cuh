@@ -87,6 +87,10 @@ struct cpn_ctx {
     std::string err;
     double last_ms = 0.0;
     int64_t last_launches = 0;
+    // algorithmic work of the last fit call, for roofline accounting: Σ E-step passes·M·L, Σ derivative sweeps (or log Z
+    // evaluations)·L, Σ score passes·M·L, EM instances
+    double last_work[4] = {0, 0, 0, 0};
+    uint64_t seed = 0;                       // cpn_set_seed: key of the counter-based start / permutation stream (cpn_philox.h)
     // profiler: when enabled every launch is bracketed by events on `stream`
     bool profile = false;
     std::vector<cudaEvent_t> pev;            // event pool
@@ -253,9 +257,13 @@ int cpn_cmd_launch(cpn_ctx* ctx, int64_t P, const int64_t* pair_a, const int64_t
                    const int64_t* cpg_off, const double* rho_n, const double* d_n, const int64_t* sub_off, const int64_t* sub_p,
                    const int64_t* sub_q, int64_t Nmax, const int64_t* cmd_off, double* cmd);
 
+// Launch-only entry of the two-sample p-value counting kernel (all pointers on the device); defined in cpn_sweeps.cu.
+int cpn_two_samp_pvals_launch(cpn_ctx* ctx, int64_t R, int Kmax, const int64_t* tbl_off, const int64_t* perm_off, const int64_t* nul_off,
+                              const int32_t* exact_r, const double* T_obs, const double* T_null, int64_t* cnt, int64_t* n_valid, double* pval);
+
 struct LaunchCounter {
     cpn_ctx* ctx;
-    explicit LaunchCounter(cpn_ctx* c) : ctx(c) { ctx->last_launches = 0; }
+    explicit LaunchCounter(cpn_ctx* c) : ctx(c) { ctx->last_launches = 0; for (double& w : ctx->last_work) w = 0; }
 };
 
 // ---- device helpers -------------------------------------------------------------------------------

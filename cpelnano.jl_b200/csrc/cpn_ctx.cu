@@ -4,18 +4,28 @@
 #include <vector>
 
 #include "cpn_common.cuh"
+#include "cpn_philox.h"
 
 namespace {
 
-// 8 independent DFMA chains per thread: enough ILP to saturate the FP64 pipe at full occupancy.
-__global__ void __launch_bounds__(256) k_dfma_peak(double* out, int iters, double seed) {
-    double a0 = seed + threadIdx.x, a1 = a0 + 1, a2 = a0 + 2, a3 = a0 + 3, a4 = a0 + 4, a5 = a0 + 5, a6 = a0 + 6, a7 = a0 + 7;
-    const double m = 0.999999, c = 1e-9;
+// 8 independent DFMA chains per thread, 128 threads per block, 8 blocks per SM: the configuration of tools/micro/fp64_mix.cu,
+// which reads 36.7 TFLOP/s on a B200 (nominal 148 SM x 64 FMA/clk x 2 x 1.965 GHz = 37.2).  The loop body is fully unrolled
+// DFMAs; the launch is long (>= 10 ms) so that clock ramp-up and the launch's head and tail do not weigh on the figure
+// (the round-1 probe ran 2.6 ms launches and under-read by about 6 %).
+__global__ void __launch_bounds__(128, 8) k_dfma_peak(double* out, int iters, double seed) {
+    const int tid = blockIdx.x * blockDim.x + threadIdx.x;
+    double a[8];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) a[k] = seed + k + tid * 1e-9;
+    const double m = 1.0000001, c = 1e-9;
     for (int i = 0; i < iters; ++i) {
-        a0 = fma(a0, m, c); a1 = fma(a1, m, c); a2 = fma(a2, m, c); a3 = fma(a3, m, c);
-        a4 = fma(a4, m, c); a5 = fma(a5, m, c); a6 = fma(a6, m, c); a7 = fma(a7, m, c);
+#pragma unroll
+        for (int k = 0; k < 8; ++k) a[k] = fma(a[k], m, c);
     }
-    out[blockIdx.x * (size_t)blockDim.x + threadIdx.x] = ((a0 + a1) + (a2 + a3)) + ((a4 + a5) + (a6 + a7));
+    double z = 0;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) z += a[k];
+    if (z == 123.456) out[tid] = z;          // never true: keeps the chains alive without a store on the timed path
 }
 
 }  // namespace
@@ -70,6 +80,35 @@ void cpn_destroy(cpn_ctx* ctx) {
 const char* cpn_last_error(const cpn_ctx* ctx) { return ctx ? ctx->err.c_str() : "null context"; }
 double cpn_last_device_ms(const cpn_ctx* ctx) { return ctx ? ctx->last_ms : 0.0; }
 int64_t cpn_last_launches(const cpn_ctx* ctx) { return ctx ? ctx->last_launches : 0; }
+int cpn_last_work(const cpn_ctx* ctx, double* work) {
+    if (!ctx || !work) return CPN_ERR_ARG;
+    for (int k = 0; k < 4; ++k) work[k] = ctx->last_work[k];
+    return CPN_OK;
+}
+
+int cpn_set_seed(cpn_ctx* ctx, uint64_t seed) {
+    if (!ctx) return CPN_ERR_ARG;
+    ctx->seed = seed;
+    return CPN_OK;
+}
+
+// Host-side evaluation of the same stream (no GPU needed): what the device generates for phi0 == NULL / perm_ids == NULL.
+int cpn_rng_phi0(uint64_t seed, int64_t region, int64_t perm, int32_t half, int32_t n_init, double* phi0) {
+    if (!phi0 || n_init < 0 || region < 0 || half < 0 || half > 1) return CPN_ERR_ARG;
+    const uint32_t p = perm < 0 ? CPN_RNG_NO_PERM : (uint32_t)perm;
+    for (int32_t s = 0; s < n_init; ++s) cpn_gen_phi0(seed, (uint32_t)region, p, (uint32_t)half, (uint32_t)s, phi0 + 3 * s);
+    return CPN_OK;
+}
+int cpn_rng_perm(uint64_t seed, int64_t region, int64_t perm, int32_t n, int32_t n1, int32_t* ids) {
+    if (!ids || n < 1 || n1 < 0 || n1 > n || region < 0 || perm < 0) return CPN_ERR_ARG;
+    int need = n1, k = 0;
+    CpnPhilox4 blk{};
+    for (int q = 0; q < n; ++q) {
+        if ((q & 3) == 0) blk = cpn_philox4x32_10(seed, (uint32_t)region, (uint32_t)perm, (uint32_t)(q >> 2), 1u);
+        if ((int)cpn_mulhi32(blk.x[q & 3], (uint32_t)(n - q)) < need) { ids[k++] = q + 1; --need; }
+    }
+    return CPN_OK;
+}
 
 int cpn_set_profile(cpn_ctx* ctx, int enable) {
     if (!ctx) return CPN_ERR_ARG;
@@ -87,11 +126,11 @@ int cpn_get_profile(const cpn_ctx* ctx, double* ms, int64_t* launches) {
 int cpn_measure_fp64_peak(cpn_ctx* ctx, double* tflops) {
     if (!ctx || !tflops) return CPN_ERR_ARG;
     CPN_CUDA(ctx, cudaSetDevice(ctx->device));
-    const int blocks = ctx->sm_count * 8, threads = 256, iters = 20000;
+    const int blocks = ctx->sm_count * 8, threads = 128, iters = 200000;
     DevBuf<double> out;
     CPN_CUDA(ctx, out.alloc((size_t)blocks * threads, ctx->stream));
     double best = 0.0;
-    for (int rep = 0; rep < 4; ++rep) {
+    for (int rep = 0; rep < 5; ++rep) {                      // rep 0 warms the clocks up; best of the next four
         CPN_CUDA(ctx, cudaEventRecord(ctx->ev0, ctx->stream));
         k_dfma_peak<<<blocks, threads, 0, ctx->stream>>>(out.p, iters, 1.0 + rep);
         CPN_CUDA(ctx, cudaEventRecord(ctx->ev1, ctx->stream));

@@ -18,6 +18,7 @@
 //     restatement of NLsolve's trust-region dogleg.
 //   * The EM loop is a sequence of batched launches over a compacted list of still-active instances.
 #include <algorithm>
+#include <array>
 #include <condition_variable>
 #include <memory>
 #include <mutex>
@@ -30,6 +31,7 @@
 #include <numeric>
 
 #include "cpn_common.cuh"
+#include "cpn_philox.h"
 
 namespace {
 
@@ -830,6 +832,8 @@ struct EmState {
     int64_t NI;
     double* gh;                 // [9][NI] ∇logZ (3) and its Hessian (6) at the instance's CURRENT ϕ, when gh_valid
     unsigned char* gh_valid;    // [NI]
+    unsigned char* numerr;      // [NI] 1 once an M-step of the instance met a non-finite residual or iterate (the reference
+                                //      catches the exception and keeps ϕ, em_algorithm.jl:160-172); feeds CPN_FIT_NUMERICAL
 };
 
 // One em_iter M-step + the em_inst bookkeeping (em_algorithm.jl:152-183, :317-341) for every active
@@ -856,6 +860,7 @@ __global__ void __launch_bounds__(M_THREADS) k_mstep(int n_items, const int* __r
         double x0[3] = {st.phi[inst], st.phi[NI + inst], st.phi[2 * NI + inst]}, sol[3];
         int nit; bool threw;
         bool conv = trust_region_solve(pb, x0, sol, &nit, &threw);
+        if (threw || !allfinite3(sol)) st.numerr[inst] = 1;
         double nx[3];
         if (threw || !conv) { nx[0] = x0[0]; nx[1] = x0[1]; nx[2] = x0[2]; }
         else {
@@ -1087,6 +1092,7 @@ __global__ void __launch_bounds__(M_THREADS, WS_BLOCKS) k_mstep_ws(int n_items, 
                     // em_iter tail (:172-181) + em_inst bookkeeping (:327-341)
                     double x0[3] = {CS(C_X0), CS(C_X0 + 1), CS(C_X0 + 2)}, nx[3];
                     bool gh_ok;
+                    if (threw || stopped) st.numerr[inst] = 1;
                     if (code == 2) {
                         nx[0] = x0[0]; nx[1] = x0[1]; nx[2] = x0[2];
                         gh_ok = init && !threw;               // ϕ stays at x0: gh still describes it only if no step was accepted
@@ -1213,12 +1219,26 @@ __global__ void k_mstep_once(int64_t R, RegionTables rt, const int64_t* __restri
     if (counters) { counters[2 * r] = nit; counters[2 * r + 1] = pb.evals; }
 }
 
-__global__ void k_init_state(int64_t NI, int n_init, const double* __restrict__ phi0 /*[NI][3]*/, EmState st, int* __restrict__ items,
+// EM starts: phi0 [NI][3] from the caller (the host RNG owns gen_ϕ0s), or — phi0 == null — regenerated from the seed with the
+// counter-based stream of cpn_philox.h: unit u is region unit_base + u of the call's batch (plain fit), or the (region,
+// permutation, half) its key names (two-sample refits).
+__global__ void k_init_state(int64_t NI, int n_init, const double* __restrict__ phi0 /*[NI][3] or null*/, uint64_t seed, int64_t unit_base,
+                             const int2* __restrict__ ukey /*[U] (region, 2·perm + half) or null*/, EmState st, int* __restrict__ items,
                              const int* __restrict__ order /*[R] region order or null*/) {
     int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
     if (i >= NI) return;
-    st.phi[i] = phi0[3 * i]; st.phi[st.NI + i] = phi0[3 * i + 1]; st.phi[2 * st.NI + i] = phi0[3 * i + 2];
+    if (phi0) {
+        st.phi[i] = phi0[3 * i]; st.phi[st.NI + i] = phi0[3 * i + 1]; st.phi[2 * st.NI + i] = phi0[3 * i + 2];
+    } else {
+        const int64_t u = i / n_init;
+        const uint32_t sidx = (uint32_t)(i - u * n_init);
+        double p[3];
+        if (ukey) { const int2 k = ukey[u]; cpn_gen_phi0(seed, (uint32_t)k.x, (uint32_t)k.y >> 1, (uint32_t)k.y & 1u, sidx, p); }
+        else cpn_gen_phi0(seed, (uint32_t)(unit_base + u), CPN_RNG_NO_PERM, 0u, sidx, p);
+        st.phi[i] = p[0]; st.phi[st.NI + i] = p[1]; st.phi[2 * st.NI + i] = p[2];
+    }
     st.iter[i] = 1; st.status[i] = 0; st.cnt_em[i] = 0; st.cnt_sol[i] = 0; st.cnt_eval[i] = 0;
+    st.gh_valid[i] = 0; st.numerr[i] = 0;
     if (order) {
         int64_t slot = i / n_init, s = i % n_init;
         items[i] = (int)((int64_t)order[slot] * n_init + s);
@@ -1234,10 +1254,12 @@ __global__ void k_pick(int64_t R, int n_init, EmState st, const double* __restri
     double best = -cpn_inf();
     int bi = -1;
     int64_t ce = 0, cs = 0, cv = 0;
+    bool numerr = false;
     for (int s = 0; s < n_init; ++s) {
         int64_t i = r * n_init + s;
         double q = Qs[i];
         if (q > best) { best = q; bi = s; }
+        numerr = numerr || st.numerr[i] != 0;
         ce += st.cnt_em[i]; cs += st.cnt_sol[i]; cv += st.cnt_eval[i];
         if (phi_starts) {
             phi_starts[3 * i] = st.phi[i]; phi_starts[3 * i + 1] = st.phi[st.NI + i]; phi_starts[3 * i + 2] = st.phi[2 * st.NI + i];
@@ -1251,8 +1273,21 @@ __global__ void k_pick(int64_t R, int n_init, EmState st, const double* __restri
         phi_hat[3 * r] = phi_hat[3 * r + 1] = phi_hat[3 * r + 2] = cpn_nan();
     }
     Q[r] = best;
-    if (status) status[r] = bi;
+    if (status) status[r] = bi >= 0 ? bi : (numerr ? CPN_FIT_NUMERICAL : CPN_FIT_NONE);
     if (counters) { counters[4 * r] = ce; counters[4 * r + 1] = cs; counters[4 * r + 2] = cv; counters[4 * r + 3] = ce; }
+}
+
+// Algorithmic work done by the EM loop (roofline accounting): Σ_i passes_i·M·L, Σ_i sweeps_i·L, Σ_converged M·L, instance count.
+__global__ void k_work_sum(int64_t NI, int n_init, const RegionDesc* __restrict__ rdesc, EmState st, double* __restrict__ out /*[4]*/) {
+    int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    double w0 = 0, w1 = 0, w2 = 0, w3 = 0;
+    if (i < NI) {
+        const RegionDesc rd = rdesc[i / n_init];
+        const double ml = (double)rd.M * (double)rd.L;
+        w0 = st.cnt_em[i] * ml; w1 = (double)st.cnt_eval[i] * rd.L; w2 = st.status[i] == 1 ? ml : 0.0; w3 = 1.0;
+    }
+    w0 = cpn_warp_sum(w0); w1 = cpn_warp_sum(w1); w2 = cpn_warp_sum(w2); w3 = cpn_warp_sum(w3);
+    if ((threadIdx.x & 31) == 0) { atomicAdd(out, w0); atomicAdd(out + 1, w1); atomicAdd(out + 2, w2); atomicAdd(out + 3, w3); }
 }
 
 __global__ void k_pack_phi(int64_t R, const double* __restrict__ phi /*[R][3]*/, double* __restrict__ out /*[3][R]*/) {
@@ -1414,6 +1449,12 @@ struct StagedBatch {
     DevBuf<RegionDesc> vdesc;    // [V]
     DevBuf<int32_t> ridx;        // read-id rows
     std::vector<int32_t> h_vL;   // chain length per view (ordering)
+    // EM starts regenerated on the device (phi0 == null): seed and, for plain fits, the position of unit 0 in the call's
+    // batch; views carry their (region, 2·perm + half) key
+    bool seeded = false;
+    uint64_t seed = 0;
+    int64_t unit_base = 0;
+    DevBuf<int2> vkey;           // [V]
 };
 
 int fit_stage(cpn_ctx* ctx, StagedBatch& sb, bool on_device, int64_t R, const int64_t* grp_off, const double* Nl, const double* rho_l,
@@ -1422,7 +1463,8 @@ int fit_stage(cpn_ctx* ctx, StagedBatch& sb, bool on_device, int64_t R, const in
     CPN_CUDA(ctx, cudaSetDevice(ctx->device));
     CpnArenaScope scope(sb.arena);
     // ϕ0 first: the raw emissions must stay on top of the workspace stack
-    CPN_CUDA(ctx, sb.phi0.bind(phi0, (n_units < 0 ? R : n_units) * n_init * 3, on_device, ctx->stream));
+    sb.seeded = phi0 == nullptr;
+    if (!sb.seeded) CPN_CUDA(ctx, sb.phi0.bind(phi0, (n_units < 0 ? R : n_units) * n_init * 3, on_device, ctx->stream));
     return pack_regions(ctx, sb.pk, on_device, true, R, grp_off, Nl, rho_l, d_l, read_off, lu, lm, offs_mode);
 }
 
@@ -1433,7 +1475,7 @@ int fit_impl(cpn_ctx* ctx, bool on_device, int64_t R, const int64_t* grp_off, co
              double* phi_starts, double* Q_starts, const SummaryArgs* sa = nullptr, StagedBatch* pre = nullptr, int offs_mode = -1) {
     const bool offs_dev = offs_mode < 0 ? on_device : offs_mode != 0;
     CPN_ARG(ctx, R >= 0 && n_init >= 1 && max_em_iters >= 1, "R >= 0, n_init >= 1, max_em_iters >= 1");
-    CPN_ARG(ctx, pre || (grp_off && Nl && rho_l && d_l && read_off && lu && lm && phi0), "null pointer");
+    CPN_ARG(ctx, pre || (grp_off && Nl && rho_l && d_l && read_off && lu && lm), "null pointer");
     CPN_ARG(ctx, phi_hat && Q, "null pointer");
     CPN_ARG(ctx, mstep_mode == CPN_MSTEP_FD || mstep_mode == CPN_MSTEP_ANALYTIC, "mstep_mode");
     CPN_ARG(ctx, R * (int64_t)n_init < (int64_t)2147483647, "R*n_init must fit in int32");
@@ -1450,6 +1492,7 @@ int fit_impl(cpn_ctx* ctx, bool on_device, int64_t R, const int64_t* grp_off, co
         if (!pre) {
             CPN_CUDA(ctx, ctx->stage_arena.reset());
             local.arena = &ctx->stage_arena;
+            local.seed = ctx->seed;
             int rc = fit_stage(ctx, local, on_device, R, grp_off, Nl, rho_l, d_l, read_off, lu, lm, phi0, n_init);
             if (rc) return rc;
         }
@@ -1498,13 +1541,14 @@ int fit_impl(cpn_ctx* ctx, bool on_device, int64_t R, const int64_t* grp_off, co
         }
         CPN_CUDA(ctx, order.upload(h_order.data(), U, s));
         DevBuf<double> gh;
-        DevBuf<unsigned char> gh_valid;
+        DevBuf<unsigned char> gh_valid, numerr;
         CPN_CUDA(ctx, gh.alloc(9 * NI, s));
         CPN_CUDA(ctx, gh_valid.alloc(NI, s));
-        CPN_CUDA(ctx, cudaMemsetAsync(gh_valid.p, 0, NI, s));
-        EmState st{phi.p, ES.p, iter.p, stat.p, c_em.p, c_sol.p, c_ev.p, NI, gh.p, gh_valid.p};
+        CPN_CUDA(ctx, numerr.alloc(NI, s));
+        EmState st{phi.p, ES.p, iter.p, stat.p, c_em.p, c_sol.p, c_ev.p, NI, gh.p, gh_valid.p, numerr.p};
         { KTimer kt(ctx, CPN_K_PREP);
-          k_init_state<<<blocks_for(NI, 256), 256, 0, s>>>(NI, n_init, d_phi0.p, st, items_a.p, order.p); }
+          k_init_state<<<blocks_for(NI, 256), 256, 0, s>>>(NI, n_init, sb->seeded ? nullptr : d_phi0.p, sb->seed, sb->unit_base,
+                                                           views ? sb->vkey.p : nullptr, st, items_a.p, order.p); }
         trace(ctx, "em-start");
         // The host never waits for the device inside the EM loop.  The number of instances still active after iteration i
         // lives in counts[i+1] on the device (kernels of iteration i+1 read it there); the host sizes its grids from the
@@ -1553,6 +1597,12 @@ int fit_impl(cpn_ctx* ctx, bool on_device, int64_t R, const int64_t* grp_off, co
             std::swap(cur, nxt);
         }
         trace(ctx, "em-done");
+        DevBuf<double> work;
+        CPN_CUDA(ctx, work.alloc(4, s));
+        CPN_CUDA(ctx, cudaMemsetAsync(work.p, 0, 4 * sizeof(double), s));
+        { KTimer kt(ctx, CPN_K_PREP); k_work_sum<<<blocks_for(NI, 256), 256, 0, s>>>(NI, n_init, rt.rdesc, st, work.p); }
+        double h_work[4] = {0, 0, 0, 0};
+        CPN_CUDA(ctx, cudaMemcpyAsync(h_work, work.p, sizeof(h_work), cudaMemcpyDeviceToHost, s));     // read after the final wait below
         // score converged instances (em_algorithm.jl:344), then pick per region
         { KTimer kt(ctx, CPN_K_SCORE);
           k_score<<<blocks_for(NI, E_WARPS), E_WARPS * 32, 0, s>>>((int)NI, nullptr, n_init, rt, phi.p, NI, stat.p, 1, Qs.p); }
@@ -1610,6 +1660,7 @@ int fit_impl(cpn_ctx* ctx, bool on_device, int64_t R, const int64_t* grp_off, co
             CPN_CUDA(ctx, cudaEventRecord(ctx->ev1, s));
             CPN_CUDA(ctx, cpn_wait_stream(ctx, s));
         }
+        for (int k = 0; k < 4; ++k) ctx->last_work[k] += h_work[k];
     }
     trace(ctx, "end");
     if (!pre) {
@@ -1638,6 +1689,131 @@ __global__ void k_two_samp_T(int64_t P, const int64_t* __restrict__ k_off /*[2P+
         T[3 * c0 + K + k] = bad ? nan : nme[ka + k] - nme[kb + k];
         T[3 * c0 + 2 * K + k] = bad ? nan : cmd[c0 + k];
     }
+}
+
+
+// ---- two-sample test: views of the pooled reads, built on the device --------------------------------------------------------
+// One entry per region of a chunk: where its views, read-index rows and summary tables start, and its sizes.
+struct TsRegion { int64_t v0, row0, ex0, k0, c0, pid0, gr; int32_t P, n, n1, N, K, rows1, rows2, pad; };
+
+// Thread = (region blockIdx.y, permutation i).  Splits the region's n pooled reads into sample 1 (perm_ids' ascending 1-based
+// indices, two_samp_perm_tests.jl:50-59; or — perm_ids == null — the selection-sampling draw of cpn_philox.h) and the rest, in
+// order, and writes the two views (descriptor, read-index rows padded with read 0, RNG key) plus the index tables the summaries
+// and CMD kernels take for these 2·ΣP models.
+__global__ void k_two_samp_views(const TsRegion* __restrict__ regs, const RegionDesc* __restrict__ base, const int32_t* __restrict__ perm_ids,
+                                 uint64_t seed, int64_t V, int64_t Pt, int64_t sN, int64_t sK, int64_t sC, RegionDesc* __restrict__ vdesc,
+                                 int32_t* __restrict__ ridx, int2* __restrict__ vkey, int64_t* __restrict__ reg_of, int64_t* __restrict__ ex_off,
+                                 int64_t* __restrict__ k_off, int64_t* __restrict__ cmd_off, int64_t* __restrict__ pa, int64_t* __restrict__ pb) {
+    const int r = blockIdx.y;
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (r == 0 && i == 0) { ex_off[V] = sN; k_off[V] = sK; cmd_off[Pt] = sC; }
+    const TsRegion t = regs[r];
+    if (i >= t.P) return;
+    const RegionDesc b = base[r];
+    const int64_t v = t.v0 + 2 * (int64_t)i;
+    const int64_t row = t.row0 + (int64_t)i * (t.rows1 + t.rows2);
+    int32_t* r1 = ridx + row * 32;
+    int32_t* r2 = r1 + (int64_t)t.rows1 * 32;
+    int c1 = 0, c2 = 0;
+    if (perm_ids) {
+        const int32_t* ids = perm_ids + t.pid0 + (int64_t)i * t.n1;
+        int j = 0;
+        for (int q = 0; q < t.n; ++q) {
+            const bool in1 = j < t.n1 && ids[j] - 1 == q;
+            if (in1) { r1[c1++] = q; ++j; } else r2[c2++] = q;
+        }
+    } else {
+        int need = t.n1;
+        uint32_t x0 = 0, x1 = 0, x2 = 0, x3 = 0;
+        for (int q = 0; q < t.n; ++q) {
+            if ((q & 3) == 0) {
+                const CpnPhilox4 blk = cpn_philox4x32_10(seed, (uint32_t)t.gr, (uint32_t)i, (uint32_t)(q >> 2), 1u);
+                x0 = blk.x[0]; x1 = blk.x[1]; x2 = blk.x[2]; x3 = blk.x[3];
+            }
+            const uint32_t x = (q & 2) ? ((q & 1) ? x3 : x2) : ((q & 1) ? x1 : x0);
+            const bool in1 = (int)cpn_mulhi32(x, (uint32_t)(t.n - q)) < need;
+            if (in1) { r1[c1++] = q; --need; } else r2[c2++] = q;
+        }
+    }
+    for (; c1 < t.rows1 * 32; ++c1) r1[c1] = 0;
+    for (; c2 < t.rows2 * 32; ++c2) r2[c2] = 0;
+    RegionDesc d;
+    d.g0 = b.g0; d.ew_off = b.ew_off; d.rb_off = b.rb_off; d.L = b.L; d.pad = 0;
+    d.M = t.n1; d.ridx = (int32_t)row;
+    vdesc[v] = d;
+    d.M = t.n - t.n1; d.ridx = (int32_t)(row + t.rows1);
+    vdesc[v + 1] = d;
+    vkey[v] = make_int2((int)t.gr, 2 * i); vkey[v + 1] = make_int2((int)t.gr, 2 * i + 1);
+    reg_of[v] = r; reg_of[v + 1] = r;
+    ex_off[v] = t.ex0 + 2 * (int64_t)i * t.N; ex_off[v + 1] = t.ex0 + (2 * (int64_t)i + 1) * t.N;
+    k_off[v] = t.k0 + 2 * (int64_t)i * t.K; k_off[v + 1] = t.k0 + (2 * (int64_t)i + 1) * t.K;
+    const int64_t pi = (t.v0 >> 1) + i;
+    pa[pi] = v; pb[pi] = v + 1; cmd_off[pi] = t.c0 + (int64_t)i * t.K;
+}
+
+// Observed statistics of the two-sample test (two_samp_perm_tests.jl:165-167) from the summaries of the two fitted models
+// (models 2r and 2r+1) and their CMD, in the [region][statistic][K] layout the counting kernel reads.
+__global__ void k_two_samp_Tobs(int64_t R, const int64_t* __restrict__ sub_off, const double* __restrict__ mml, const double* __restrict__ nme,
+                                const double* __restrict__ cmd, double* __restrict__ T) {
+    int64_t r = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5;
+    int lane = threadIdx.x & 31;
+    if (r >= R) return;
+    const int64_t k0 = sub_off[r], K = sub_off[r + 1] - k0;
+    for (int64_t k = lane; k < K; k += 32) {
+        T[3 * k0 + k] = mml[2 * k0 + k] - mml[2 * k0 + K + k];
+        T[3 * k0 + K + k] = nme[2 * k0 + k] - nme[2 * k0 + K + k];
+        T[3 * k0 + 2 * K + k] = cmd[k0 + k];
+    }
+}
+
+// Observed statistics and, when null statistics are given, the permutation p-values of Rc regions (host outputs).
+static int two_samp_observed(cpn_ctx* ctx, int64_t Rc, const double* phi_s1, const double* phi_s2, const int64_t* po, const int64_t* tn,
+                             const int32_t* exact, const int64_t* cp, const int64_t* so, int Kmax, int64_t Nmax, const int64_t* d_cpg,
+                             const double* d_rho, const double* d_dn, const int64_t* d_so, const int64_t* d_sp, const int64_t* d_sq,
+                             const double* d_Tnull, double* T_obs, int64_t* cnt, int64_t* n_valid, double* pval) {
+    cudaStream_t s = ctx->stream;
+    const int64_t T2 = 2 * Rc, sumN = cp[Rc], sumK = so[Rc];
+    std::vector<double> h_phi(3 * T2);
+    std::vector<int64_t> h_reg(T2), h_exo(T2 + 1), h_ko(T2 + 1), h_pa(Rc), h_pb(Rc), h_nul(Rc);
+    std::vector<int32_t> h_exact(Rc, 0);
+    for (int64_t r = 0; r < Rc; ++r) {
+        for (int k = 0; k < 3; ++k) { h_phi[6 * r + k] = phi_s1[3 * r + k]; h_phi[6 * r + 3 + k] = phi_s2[3 * r + k]; }
+        const int64_t N = cp[r + 1] - cp[r], K = so[r + 1] - so[r];
+        h_reg[2 * r] = h_reg[2 * r + 1] = r;
+        h_exo[2 * r] = 2 * cp[r]; h_exo[2 * r + 1] = 2 * cp[r] + N;
+        h_ko[2 * r] = 2 * so[r]; h_ko[2 * r + 1] = 2 * so[r] + K;
+        h_pa[r] = 2 * r; h_pb[r] = 2 * r + 1;
+        h_nul[r] = tn[r] - tn[0];
+        if (exact) h_exact[r] = exact[r];
+    }
+    h_exo[T2] = 2 * sumN; h_ko[T2] = 2 * sumK;
+    DevBuf<double> d_phi, logZ, ex, exx, lg, e1, e2, mml, nme, cmd, d_T, o_p;
+    DevBuf<int64_t> d_reg, d_exo, d_ko, d_pa, d_pb, d_po, d_nul, o_cnt, o_nv;
+    DevBuf<int32_t> d_exact;
+    CpnArenaScope scope(&ctx->stage_arena);
+    CPN_CUDA(ctx, d_phi.upload(h_phi.data(), 3 * T2, s)); CPN_CUDA(ctx, d_reg.upload(h_reg.data(), T2, s));
+    CPN_CUDA(ctx, d_exo.upload(h_exo.data(), T2 + 1, s)); CPN_CUDA(ctx, d_ko.upload(h_ko.data(), T2 + 1, s));
+    CPN_CUDA(ctx, d_pa.upload(h_pa.data(), Rc, s)); CPN_CUDA(ctx, d_pb.upload(h_pb.data(), Rc, s));
+    CPN_CUDA(ctx, d_po.upload(po, Rc + 1, s)); CPN_CUDA(ctx, d_nul.upload(h_nul.data(), Rc, s)); CPN_CUDA(ctx, d_exact.upload(h_exact.data(), Rc, s));
+    CPN_CUDA(ctx, logZ.alloc(T2, s)); CPN_CUDA(ctx, ex.alloc(2 * sumN, s)); CPN_CUDA(ctx, exx.alloc(2 * sumN - T2, s)); CPN_CUDA(ctx, lg.alloc(8 * sumK, s));
+    CPN_CUDA(ctx, e1.alloc(2 * sumK, s)); CPN_CUDA(ctx, e2.alloc(2 * sumK, s)); CPN_CUDA(ctx, mml.alloc(2 * sumK, s)); CPN_CUDA(ctx, nme.alloc(2 * sumK, s));
+    CPN_CUDA(ctx, cmd.alloc(sumK, s)); CPN_CUDA(ctx, d_T.alloc(3 * sumK, s));
+    CPN_CUDA(ctx, o_cnt.alloc(3 * sumK, s)); CPN_CUDA(ctx, o_nv.alloc(3 * sumK, s)); CPN_CUDA(ctx, o_p.alloc(3 * sumK, s));
+    int rc = cpn_stat_sums_launch(ctx, T2, d_phi.p, d_reg.p, d_exo.p, d_ko.p, d_cpg, d_rho, d_dn, d_so, d_sp, d_sq, Nmax, logZ.p, ex.p, exx.p, lg.p,
+                                  e1.p, e2.p, mml.p, nme.p);
+    if (rc) return rc;
+    rc = cpn_cmd_launch(ctx, Rc, d_pa.p, d_pb.p, d_phi.p, d_reg.p, d_exo.p, ex.p, exx.p, d_ko.p, nme.p, d_cpg, d_rho, d_dn, d_so, d_sp, d_sq, Nmax,
+                        d_so, cmd.p);
+    if (rc) return rc;
+    { KTimer kt(ctx, CPN_K_SWEEP); k_two_samp_Tobs<<<blocks_for(Rc * 32, 256), 256, 0, s>>>(Rc, d_so, mml.p, nme.p, cmd.p, d_T.p); }
+    CPN_CUDA(ctx, cudaGetLastError());
+    // with no null statistics (P = 0 everywhere) the counting kernel still runs: zero counts, NaN p-values (n_valid ≤ 20)
+    rc = cpn_two_samp_pvals_launch(ctx, Rc, Kmax, d_so, d_po.p, d_nul.p, d_exact.p, d_T.p, d_Tnull ? d_Tnull : d_T.p, o_cnt.p, o_nv.p, o_p.p);
+    if (rc) return rc;
+    CPN_CUDA(ctx, d_T.download(T_obs, 3 * sumK, s)); CPN_CUDA(ctx, o_cnt.download(cnt, 3 * sumK, s));
+    CPN_CUDA(ctx, o_nv.download(n_valid, 3 * sumK, s)); CPN_CUDA(ctx, o_p.download(pval, 3 * sumK, s));
+    CPN_CUDA(ctx, cpn_wait_stream(ctx, s));                       // host staging vectors and the DevBufs go out of scope
+    return CPN_OK;
 }
 
 }  // namespace
@@ -1669,7 +1845,7 @@ static int fit_chunked(cpn_ctx* ctx, bool on_device, int64_t R, const int64_t* g
     if (C <= 1)
         return fit_impl(ctx, on_device, R, grp_off_in, Nl, rho_l, d_l, read_off_in, lu, lm, phi0, n_init, max_em_iters, amax, bmax, cmax,
                         mstep_mode, phi_hat, Q, status, counters, phi_starts, Q_starts, sa_in);
-    CPN_ARG(ctx, Nl && rho_l && d_l && lu && lm && phi0 && phi_hat && Q, "null pointer");
+    CPN_ARG(ctx, Nl && rho_l && d_l && lu && lm && phi_hat && Q, "null pointer");
     CPN_ARG(ctx, n_init >= 1, "n_init >= 1");
     CPN_CUDA(ctx, cudaSetDevice(ctx->device));
     auto t0 = std::chrono::steady_clock::now();
@@ -1751,6 +1927,7 @@ static int fit_chunked(cpn_ctx* ctx, bool on_device, int64_t R, const int64_t* g
     std::vector<int> state(C, 0);          // 0 pending, 1 staged, -1 failed
     std::vector<int> rc(W + 1, CPN_OK);
     std::vector<int64_t> launches(W + 1, 0);
+    std::vector<std::array<double, 4>> work(W + 1, std::array<double, 4>{0, 0, 0, 0});
     std::mutex mu;
     std::condition_variable cv;
     int taken = 0;
@@ -1778,9 +1955,11 @@ static int fit_chunked(cpn_ctx* ctx, bool on_device, int64_t R, const int64_t* g
                 const int64_t g0 = grp_off[r0];
                 slot[c].reset(new StagedBatch());
                 slot[c]->arena = ar;
+                slot[c]->seed = ctx->seed;
+                slot[c]->unit_base = r0;               // seeded starts are keyed by the region's position in the whole batch
                 trace(u, "stage");
                 r = fit_stage(u, *slot[c], on_device, Rc, g.data(), Nl + g0, rho_l + g0, d_l + (g0 - r0), rd.data(), lu + obs[r0], lm + obs[r0],
-                              phi0 + r0 * n_init * 3, n_init, 0);
+                              phi0 ? phi0 + r0 * n_init * 3 : nullptr, n_init, 0);
                 if (r == CPN_OK && cpn_wait_stream(u, u->stream) != cudaSuccess) { u->err = "stream synchronize failed"; r = CPN_ERR_CUDA; }
                 launches[0] = u->last_launches;
                 trace(u, "staged");
@@ -1823,6 +2002,9 @@ static int fit_chunked(cpn_ctx* ctx, bool on_device, int64_t R, const int64_t* g
                                  counters ? counters + 4 * r0 : nullptr, phi_starts ? phi_starts + r0 * n_init * 3 : nullptr,
                                  Q_starts ? Q_starts + r0 * n_init : nullptr, sa ? &sc : nullptr, slot[c].get(), 0);
                 launches[wi] += w->last_launches;
+                for (int k = 0; k < 4; ++k) work[wi][k] += w->last_work[k];
+                // an error return may have left kernels that read the slot's tables in flight: drain the stream first
+                if (r != CPN_OK) cudaStreamSynchronize(w->stream);
                 {   // the worker's stream is idle: the staging slot can be reused
                     CpnArena* ar = slot[c]->arena;
                     slot[c].reset();
@@ -1842,10 +2024,12 @@ static int fit_chunked(cpn_ctx* ctx, bool on_device, int64_t R, const int64_t* g
     for (auto& t : th) t.join();
     slot.clear();
     ctx->last_launches = 0;
+    for (double& w : ctx->last_work) w = 0;
     int ret = CPN_OK;
     for (int wi = 0; wi <= W; ++wi) {
         cpn_ctx* w = ctx->children[wi];
         ctx->last_launches += launches[wi];
+        for (int k = 0; k < 4; ++k) { ctx->last_work[k] += work[wi][k]; }
         for (int k = 0; k < CPN_K_NCLASS; ++k) {
             ctx->prof_ms[k] += w->prof_ms[k]; ctx->prof_launches[k] += w->prof_launches[k];
             w->prof_ms[k] = 0; w->prof_launches[k] = 0;
@@ -2002,6 +2186,188 @@ int cpn_mstep_batch(cpn_ctx* ctx, int64_t R, const int64_t* grp_off, const doubl
     return CPN_OK;
 }
 
+// Two-sample permutation test for R regions, cut into chunks of regions whose refits (views) fit a bounded workspace.
+// T_obs / cnt / n_valid / pval are produced when the two observed models are given; T_null and fit_status are optional.
+static int two_samp_impl(cpn_ctx* ctx, int64_t R, const int64_t* grp_off, const double* Nl, const double* rho_l, const double* d_l,
+                         const int64_t* read_off, const double* lu, const double* lm, const int64_t* n1, const double* phi_s1,
+                         const double* phi_s2, const int64_t* perm_off, const int32_t* perm_ids, const int32_t* exact, const double* phi0,
+                         int32_t n_init, int32_t max_em_iters, double amax, double bmax, double cmax, int32_t mstep_mode,
+                         const int64_t* cpg_off, const double* rho_n, const double* d_n, const int64_t* sub_off, const int64_t* sub_p,
+                         const int64_t* sub_q, double* T_obs, int64_t* cnt, int64_t* n_valid, double* pval, double* T_null,
+                         int32_t* fit_status) {
+    CPN_ARG(ctx, R >= 0 && n_init >= 1 && max_em_iters >= 1, "R >= 0, n_init >= 1, max_em_iters >= 1");
+    CPN_ARG(ctx, grp_off && Nl && rho_l && d_l && read_off && lu && lm && perm_off && n1, "null pointer");
+    CPN_ARG(ctx, cpg_off && rho_n && d_n && sub_off && sub_p && sub_q, "null pointer");
+    const bool observed = phi_s1 != nullptr;
+    CPN_ARG(ctx, !observed || (phi_s2 && T_obs && cnt && n_valid && pval), "the test needs both observed models and the four output tables");
+    CPN_ARG(ctx, observed || T_null, "nothing to compute: neither observed models nor a T_null output");
+    CPN_CUDA(ctx, cudaSetDevice(ctx->device));
+    ctx->last_launches = 0;
+    ctx->last_ms = 0;
+    if (R == 0) return CPN_OK;
+    cudaStream_t s = ctx->stream;
+    // ---- host: validation, cumulative tables, chunk plan ----------------------------------------------------------------
+    std::vector<int64_t> obs(R + 1), pid(R + 1), tn(R + 1);     // emissions, perm_ids elements, T_null rows·K before region r
+    obs[0] = pid[0] = tn[0] = 0;
+    int64_t Nmax = 0, Kmax = 1;
+    for (int64_t r = 0; r < R; ++r) {
+        const int64_t L = grp_off[r + 1] - grp_off[r], n = read_off[r + 1] - read_off[r], P = perm_off[r + 1] - perm_off[r];
+        const int64_t N = cpg_off[r + 1] - cpg_off[r], K = sub_off[r + 1] - sub_off[r];
+        CPN_ARG(ctx, P >= 0, "perm_off must be non-decreasing");
+        CPN_ARG(ctx, n1[r] >= 1 && n1[r] < n, "each sample needs at least one read");
+        CPN_ARG(ctx, N >= 2, "every region needs N >= 2 CpG sites");
+        Nmax = std::max(Nmax, N); Kmax = std::max(Kmax, K);
+        obs[r + 1] = obs[r] + L * n; pid[r + 1] = pid[r] + P * n1[r]; tn[r + 1] = tn[r] + P * K;
+    }
+    if (perm_ids)
+        for (int64_t r = 0; r < R; ++r) {
+            const int64_t n = read_off[r + 1] - read_off[r], m1 = n1[r];
+            const int32_t* ids = perm_ids + pid[r];
+            for (int64_t i = 0; i < perm_off[r + 1] - perm_off[r]; ++i, ids += m1) {
+                int32_t prev = 0;
+                for (int64_t j = 0; j < m1; ++j) {
+                    CPN_ARG(ctx, ids[j] > prev && ids[j] <= n, "perm_ids must be ascending 1-based read indices");
+                    prev = ids[j];
+                }
+            }
+        }
+    const int64_t max_views = std::max<int64_t>(2, env_int("CPN_TWO_SAMP_MAX_VIEWS", 1 << 20));
+    std::vector<int64_t> bnd{0};
+    {
+        int64_t v = 0;
+        for (int64_t r = 0; r < R; ++r) {
+            const int64_t vr = 2 * (perm_off[r + 1] - perm_off[r]);
+            CPN_ARG(ctx, vr * (int64_t)n_init < (int64_t)2147483647, "2·P·n_init of one region must fit in int32");
+            if (v > 0 && v + vr > max_views) { bnd.push_back(r); v = 0; }
+            v += vr;
+        }
+        bnd.push_back(R);
+    }
+    CPN_CUDA(ctx, cudaEventRecord(ctx->ev0, s));
+    int64_t launches = 0;
+    double work_acc[4] = {0, 0, 0, 0};
+    std::vector<int64_t> g, rd, cp, so, po;
+    for (size_t c = 0; c + 1 < bnd.size(); ++c) {
+        const int64_t r0 = bnd[c], Rc = bnd[c + 1] - r0;
+        const int64_t Pt = perm_off[r0 + Rc] - perm_off[r0], V = 2 * Pt;
+        g.resize(Rc + 1); rd.resize(Rc + 1); cp.resize(Rc + 1); so.resize(Rc + 1); po.resize(Rc + 1);
+        for (int64_t i = 0; i <= Rc; ++i) {
+            g[i] = grp_off[r0 + i] - grp_off[r0]; rd[i] = read_off[r0 + i] - read_off[r0]; cp[i] = cpg_off[r0 + i] - cpg_off[r0];
+            so[i] = sub_off[r0 + i] - sub_off[r0]; po[i] = perm_off[r0 + i] - perm_off[r0];
+        }
+        const int64_t g0 = grp_off[r0], n0 = cpg_off[r0], k0 = sub_off[r0];
+        const int64_t sumN = cp[Rc], sumK = so[Rc];
+        // per-region layout of the chunk's views
+        std::vector<TsRegion> h_regs(Rc);
+        int64_t rows = 0, exo = 0, ko = 0, co = 0;
+        int Pmax = 0;
+        for (int64_t i = 0; i < Rc; ++i) {
+            TsRegion& t = h_regs[i];
+            const int64_t n = rd[i + 1] - rd[i], P = po[i + 1] - po[i];
+            t.v0 = 2 * po[i]; t.row0 = rows; t.ex0 = exo; t.k0 = ko; t.c0 = co; t.pid0 = pid[r0 + i] - pid[r0]; t.gr = r0 + i;
+            t.P = (int32_t)P; t.n = (int32_t)n; t.n1 = (int32_t)n1[r0 + i]; t.N = (int32_t)(cp[i + 1] - cp[i]); t.K = (int32_t)(so[i + 1] - so[i]);
+            t.rows1 = (int32_t)((t.n1 + 31) / 32); t.rows2 = (int32_t)((n - t.n1 + 31) / 32); t.pad = 0;
+            rows += P * (t.rows1 + t.rows2); exo += 2 * P * t.N; ko += 2 * P * t.K; co += P * t.K;
+            Pmax = std::max<int>(Pmax, (int)P);
+        }
+        CPN_ARG(ctx, rows < (int64_t)2147483647, "too many read-index rows in one chunk (lower CPN_TWO_SAMP_MAX_VIEWS)");
+        const int64_t sN = exo, sK = ko, sC = co;
+        int rc = CPN_OK;
+        if (V > 0) {
+            CPN_CUDA(ctx, ctx->stage_arena.reset());
+            StagedBatch sb;
+            sb.arena = &ctx->stage_arena;
+            sb.seed = ctx->seed;
+            rc = fit_stage(ctx, sb, false, Rc, g.data(), Nl + g0, rho_l + g0, d_l + (g0 - r0), rd.data(), lu + obs[r0], lm + obs[r0],
+                           phi0 ? phi0 + 2 * perm_off[r0] * n_init * 3 : nullptr, n_init, -1, V);
+            if (rc) return rc;
+            launches += ctx->last_launches;
+            DevBuf<int64_t> d_reg, d_exo, d_ko, d_co, d_pa, d_pb, d_cpg, d_so, d_sp, d_sq;
+            DevBuf<double> d_rho, d_dn, d_phi, d_Q, logZ, ex, exx, lg, e1, e2, mml, nme, cmd, T;
+            DevBuf<int32_t> d_stat, d_pid;
+            DevBuf<TsRegion> d_regs;
+            {
+                CpnArenaScope scope(&ctx->stage_arena);
+                sb.V = V;
+                sb.h_vL.resize(V);
+                for (int64_t i = 0; i < Rc; ++i) std::fill(sb.h_vL.begin() + 2 * po[i], sb.h_vL.begin() + 2 * po[i + 1], (int32_t)(g[i + 1] - g[i]));
+                CPN_CUDA(ctx, sb.vdesc.alloc(V, s)); CPN_CUDA(ctx, sb.ridx.alloc(rows * 32, s)); CPN_CUDA(ctx, sb.vkey.alloc(V, s));
+                CPN_CUDA(ctx, d_regs.upload(h_regs.data(), Rc, s));
+                if (perm_ids) CPN_CUDA(ctx, d_pid.upload(perm_ids + pid[r0], pid[r0 + Rc] - pid[r0], s));
+                CPN_CUDA(ctx, d_reg.alloc(V, s)); CPN_CUDA(ctx, d_exo.alloc(V + 1, s)); CPN_CUDA(ctx, d_ko.alloc(V + 1, s));
+                CPN_CUDA(ctx, d_co.alloc(Pt + 1, s)); CPN_CUDA(ctx, d_pa.alloc(Pt, s)); CPN_CUDA(ctx, d_pb.alloc(Pt, s));
+                CPN_CUDA(ctx, d_cpg.upload(cp.data(), Rc + 1, s)); CPN_CUDA(ctx, d_so.upload(so.data(), Rc + 1, s));
+                CPN_CUDA(ctx, d_sp.upload(sub_p + k0, sumK, s)); CPN_CUDA(ctx, d_sq.upload(sub_q + k0, sumK, s));
+                CPN_CUDA(ctx, d_rho.upload(rho_n + n0, sumN, s)); CPN_CUDA(ctx, d_dn.upload(d_n + (n0 - r0), sumN - Rc, s));
+                CPN_CUDA(ctx, d_phi.alloc(3 * V, s)); CPN_CUDA(ctx, d_Q.alloc(V, s)); CPN_CUDA(ctx, d_stat.alloc(V, s));
+                CPN_CUDA(ctx, logZ.alloc(V, s)); CPN_CUDA(ctx, ex.alloc(sN, s)); CPN_CUDA(ctx, exx.alloc(sN - V, s)); CPN_CUDA(ctx, lg.alloc(4 * sK, s));
+                CPN_CUDA(ctx, e1.alloc(sK, s)); CPN_CUDA(ctx, e2.alloc(sK, s)); CPN_CUDA(ctx, mml.alloc(sK, s)); CPN_CUDA(ctx, nme.alloc(sK, s));
+                CPN_CUDA(ctx, cmd.alloc(sC, s)); CPN_CUDA(ctx, T.alloc(3 * sC, s));
+                // the views: read-index rows, descriptors, RNG keys and the index tables of the summaries, built on the device
+                { KTimer kt(ctx, CPN_K_PREP);
+                  k_two_samp_views<<<dim3(blocks_for(std::max(Pmax, 1), 128), (unsigned)Rc), 128, 0, s>>>(
+                      d_regs.p, sb.pk.rdesc.p, perm_ids ? d_pid.p : nullptr, ctx->seed, V, Pt, sN, sK, sC, sb.vdesc.p, sb.ridx.p, sb.vkey.p,
+                      d_reg.p, d_exo.p, d_ko.p, d_co.p, d_pa.p, d_pb.p); }
+                CPN_CUDA(ctx, cudaGetLastError());
+                CPN_CUDA(ctx, cpn_wait_stream(ctx, s));               // the host staging vectors may go
+                launches += 1;
+            }
+            // 2·ΣP multi-start EM fits over the views; results stay on the device
+            rc = fit_impl(ctx, true, Rc, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, n_init, max_em_iters, amax, bmax,
+                          cmax, mstep_mode, d_phi.p, d_Q.p, d_stat.p, nullptr, nullptr, nullptr, nullptr, &sb);
+            if (rc) return rc;
+            launches += ctx->last_launches;
+            ctx->last_launches = 0;
+            for (int k = 0; k < 4; ++k) work_acc[k] += ctx->last_work[k];
+            // per-CpG summaries of every refit, CMD of the two halves of every permutation, then the three statistics
+            rc = cpn_stat_sums_launch(ctx, V, d_phi.p, d_reg.p, d_exo.p, d_ko.p, d_cpg.p, d_rho.p, d_dn.p, d_so.p, d_sp.p, d_sq.p, Nmax, logZ.p,
+                                      ex.p, exx.p, lg.p, e1.p, e2.p, mml.p, nme.p);
+            if (rc) return rc;
+            rc = cpn_cmd_launch(ctx, Pt, d_pa.p, d_pb.p, d_phi.p, d_reg.p, d_exo.p, ex.p, exx.p, d_ko.p, nme.p, d_cpg.p, d_rho.p, d_dn.p, d_so.p,
+                                d_sp.p, d_sq.p, Nmax, d_co.p, cmd.p);
+            if (rc) return rc;
+            { KTimer kt(ctx, CPN_K_SWEEP);
+              k_two_samp_T<<<blocks_for(Pt * 32, 256), 256, 0, s>>>(Pt, d_ko.p, d_co.p, mml.p, nme.p, cmd.p, d_stat.p, T.p); }
+            CPN_CUDA(ctx, cudaGetLastError());
+            if (T_null) CPN_CUDA(ctx, T.download(T_null + 3 * tn[r0], 3 * sC, s));
+            if (fit_status) CPN_CUDA(ctx, d_stat.download(fit_status + 2 * perm_off[r0], V, s));
+            if (observed) {
+                rc = two_samp_observed(ctx, Rc, phi_s1 + 3 * r0, phi_s2 + 3 * r0, po.data(), tn.data() + r0, exact ? exact + r0 : nullptr, cp.data(),
+                                       so.data(), (int)Kmax, Nmax, d_cpg.p, d_rho.p, d_dn.p, d_so.p, d_sp.p, d_sq.p, T.p, T_obs + 3 * k0, cnt + 3 * k0,
+                                       n_valid + 3 * k0, pval + 3 * k0);
+                if (rc) return rc;
+            }
+            CPN_CUDA(ctx, cpn_wait_stream(ctx, s));
+            launches += ctx->last_launches;
+        } else if (observed) {
+            // no permutations at all in this chunk (binomial ≤ 20 or pval_comp off): observed statistics only, p-values NaN
+            CPN_CUDA(ctx, ctx->stage_arena.reset());
+            CpnArenaScope scope(&ctx->stage_arena);
+            DevBuf<int64_t> d_cpg, d_so, d_sp, d_sq;
+            DevBuf<double> d_rho, d_dn;
+            CPN_CUDA(ctx, d_cpg.upload(cp.data(), Rc + 1, s)); CPN_CUDA(ctx, d_so.upload(so.data(), Rc + 1, s));
+            CPN_CUDA(ctx, d_sp.upload(sub_p + k0, sumK, s)); CPN_CUDA(ctx, d_sq.upload(sub_q + k0, sumK, s));
+            CPN_CUDA(ctx, d_rho.upload(rho_n + n0, sumN, s)); CPN_CUDA(ctx, d_dn.upload(d_n + (n0 - r0), sumN - Rc, s));
+            ctx->last_launches = 0;
+            rc = two_samp_observed(ctx, Rc, phi_s1 + 3 * r0, phi_s2 + 3 * r0, po.data(), tn.data() + r0, exact ? exact + r0 : nullptr, cp.data(),
+                                   so.data(), (int)Kmax, Nmax, d_cpg.p, d_rho.p, d_dn.p, d_so.p, d_sp.p, d_sq.p, nullptr, T_obs + 3 * k0, cnt + 3 * k0,
+                                   n_valid + 3 * k0, pval + 3 * k0);
+            if (rc) return rc;
+            CPN_CUDA(ctx, cpn_wait_stream(ctx, s));
+            launches += ctx->last_launches;
+        }
+    }
+    CPN_CUDA(ctx, cudaEventRecord(ctx->ev1, s));
+    CPN_CUDA(ctx, cpn_wait_stream(ctx, s));
+    float ms = 0;
+    CPN_CUDA(ctx, cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1));
+    ctx->last_ms = ms;
+    ctx->last_launches = launches;
+    for (int k = 0; k < 4; ++k) ctx->last_work[k] = work_acc[k];
+    if (ctx->profile) cpn_profile_collect(ctx);
+    return CPN_OK;
+}
+
 int cpn_two_samp_null_batch(cpn_ctx* ctx, int64_t R, const int64_t* grp_off, const double* Nl, const double* rho_l, const double* d_l,
                             const int64_t* read_off, const double* log_pyx_u, const double* log_pyx_m, const int64_t* perm_off,
                             const int64_t* n1, const int32_t* perm_ids, const double* phi0, int32_t n_init, int32_t max_em_iters,
@@ -2009,120 +2375,24 @@ int cpn_two_samp_null_batch(cpn_ctx* ctx, int64_t R, const int64_t* grp_off, con
                             const double* d_n, const int64_t* sub_off, const int64_t* sub_p, const int64_t* sub_q, double* T_null,
                             int32_t* fit_status) {
     if (!ctx) return CPN_ERR_ARG;
-    CPN_ARG(ctx, R >= 0 && n_init >= 1 && max_em_iters >= 1, "R >= 0, n_init >= 1, max_em_iters >= 1");
-    CPN_ARG(ctx, grp_off && Nl && rho_l && d_l && read_off && log_pyx_u && log_pyx_m && perm_off && n1 && perm_ids && phi0, "null pointer");
-    CPN_ARG(ctx, cpg_off && rho_n && d_n && sub_off && sub_p && sub_q && T_null, "null pointer");
-    CPN_CUDA(ctx, cudaSetDevice(ctx->device));
-    ctx->last_launches = 0;
-    if (R == 0 || perm_off[R] == 0) { ctx->last_ms = 0; return CPN_OK; }
-    cudaStream_t s = ctx->stream;
-    const int64_t Pt = perm_off[R], V = 2 * Pt;
-    CPN_ARG(ctx, V * (int64_t)n_init < (int64_t)2147483647, "2·ΣP·n_init must fit in int32");
-    // ---- host: the views.  View 2i is sample 1 of permutation i (the reads perm_ids names), view 2i+1 the rest, in order
-    // (deleteat!, two_samp_perm_tests.jl:57-59).  Row layout of ridx: 32 read ids per chunk, padding lanes point at read 0.
-    std::vector<RegionDesc> vd(V);
-    std::vector<int32_t> ridx;
-    std::vector<int64_t> reg_of(V), ex_off(V + 1), k_off(V + 1), cmd_off(Pt + 1), pa(Pt), pb(Pt);
-    std::vector<int64_t> h_ew(R + 1), h_rb(R + 1);
-    h_ew[0] = h_rb[0] = 0;
-    int64_t Nmax = 0;
-    for (int64_t r = 0; r < R; ++r) {
-        const int64_t L = grp_off[r + 1] - grp_off[r], n = read_off[r + 1] - read_off[r], nch = (n + 31) / 32;
-        h_ew[r + 1] = h_ew[r] + nch * L * 32;                      // same arithmetic as pack_regions
-        h_rb[r + 1] = h_rb[r] + nch * 32;
-        CPN_ARG(ctx, n1[r] >= 1 && n1[r] < n, "each sample needs at least one read");
-        CPN_ARG(ctx, cpg_off[r + 1] - cpg_off[r] >= 2, "every region needs N >= 2 CpG sites");
-        Nmax = std::max(Nmax, cpg_off[r + 1] - cpg_off[r]);
-    }
-    ex_off[0] = k_off[0] = cmd_off[0] = 0;
-    {
-        std::vector<char> in1;
-        int64_t ip = 0;                                            // cursor in perm_ids
-        for (int64_t r = 0; r < R; ++r) {
-            const int64_t L = grp_off[r + 1] - grp_off[r], n = read_off[r + 1] - read_off[r], m1 = n1[r], m2 = n - m1;
-            const int64_t N = cpg_off[r + 1] - cpg_off[r], K = sub_off[r + 1] - sub_off[r];
-            in1.assign(n, 0);
-            for (int64_t i = perm_off[r]; i < perm_off[r + 1]; ++i, ip += m1) {
-                std::fill(in1.begin(), in1.end(), 0);
-                int32_t prev = 0;
-                for (int64_t j = 0; j < m1; ++j) {
-                    int32_t id = perm_ids[ip + j];
-                    CPN_ARG(ctx, id > prev && id <= n, "perm_ids must be ascending 1-based read indices");
-                    prev = id; in1[id - 1] = 1;
-                }
-                for (int h = 0; h < 2; ++h) {
-                    const int64_t v = 2 * i + h, mv = h ? m2 : m1, rows = (mv + 31) / 32;
-                    RegionDesc& d = vd[v];
-                    d.g0 = grp_off[r]; d.ew_off = h_ew[r]; d.rb_off = h_rb[r]; d.L = (int32_t)L; d.M = (int32_t)mv;
-                    d.ridx = (int32_t)(ridx.size() / 32); d.pad = 0;
-                    size_t base = ridx.size();
-                    ridx.resize(base + rows * 32, 0);
-                    int64_t c = 0;
-                    if (h == 0) for (int64_t j = 0; j < m1; ++j) ridx[base + c++] = perm_ids[ip + j] - 1;
-                    else for (int64_t q = 0; q < n; ++q) if (!in1[q]) ridx[base + c++] = (int32_t)q;
-                    reg_of[v] = r; ex_off[v + 1] = ex_off[v] + N; k_off[v + 1] = k_off[v] + K;
-                }
-                pa[i] = 2 * i; pb[i] = 2 * i + 1; cmd_off[i + 1] = cmd_off[i] + K;
-            }
-        }
-    }
-    CPN_CUDA(ctx, cudaEventRecord(ctx->ev0, s));
-    int rc = CPN_OK;
-    {
-        CPN_CUDA(ctx, ctx->stage_arena.reset());
-        StagedBatch sb;
-        sb.arena = &ctx->stage_arena;
-        rc = fit_stage(ctx, sb, false, R, grp_off, Nl, rho_l, d_l, read_off, log_pyx_u, log_pyx_m, phi0, n_init, -1, V);
-        if (rc) return rc;
-        const int64_t sumN = cpg_off[R], sumK = sub_off[R], sK = k_off[V], sN = ex_off[V];
-        DevBuf<int64_t> d_reg, d_exo, d_ko, d_co, d_pa, d_pb, d_cpg, d_so, d_sp, d_sq;
-        DevBuf<double> d_rho, d_dn, d_phi, d_Q, logZ, ex, exx, lg, e1, e2, mml, nme, cmd, T;
-        DevBuf<int32_t> d_stat;
-        {
-            CpnArenaScope scope(&ctx->stage_arena);
-            sb.V = V;
-            sb.h_vL.resize(V);
-            for (int64_t v = 0; v < V; ++v) sb.h_vL[v] = vd[v].L;
-            CPN_CUDA(ctx, sb.vdesc.upload(vd.data(), V, s));
-            CPN_CUDA(ctx, sb.ridx.upload(ridx.data(), ridx.size(), s));
-            CPN_CUDA(ctx, d_reg.upload(reg_of.data(), V, s)); CPN_CUDA(ctx, d_exo.upload(ex_off.data(), V + 1, s));
-            CPN_CUDA(ctx, d_ko.upload(k_off.data(), V + 1, s)); CPN_CUDA(ctx, d_co.upload(cmd_off.data(), Pt + 1, s));
-            CPN_CUDA(ctx, d_pa.upload(pa.data(), Pt, s)); CPN_CUDA(ctx, d_pb.upload(pb.data(), Pt, s));
-            CPN_CUDA(ctx, d_cpg.upload(cpg_off, R + 1, s)); CPN_CUDA(ctx, d_so.upload(sub_off, R + 1, s));
-            CPN_CUDA(ctx, d_sp.upload(sub_p, sumK, s)); CPN_CUDA(ctx, d_sq.upload(sub_q, sumK, s));
-            CPN_CUDA(ctx, d_rho.upload(rho_n, sumN, s)); CPN_CUDA(ctx, d_dn.upload(d_n, sumN - R, s));
-            CPN_CUDA(ctx, d_phi.alloc(3 * V, s)); CPN_CUDA(ctx, d_Q.alloc(V, s)); CPN_CUDA(ctx, d_stat.alloc(V, s));
-            CPN_CUDA(ctx, logZ.alloc(V, s)); CPN_CUDA(ctx, ex.alloc(sN, s)); CPN_CUDA(ctx, exx.alloc(sN - V, s)); CPN_CUDA(ctx, lg.alloc(4 * sK, s));
-            CPN_CUDA(ctx, e1.alloc(sK, s)); CPN_CUDA(ctx, e2.alloc(sK, s)); CPN_CUDA(ctx, mml.alloc(sK, s)); CPN_CUDA(ctx, nme.alloc(sK, s));
-            CPN_CUDA(ctx, cmd.alloc(cmd_off[Pt], s)); CPN_CUDA(ctx, T.alloc(3 * cmd_off[Pt], s));
-            CPN_CUDA(ctx, cpn_wait_stream(ctx, s));               // the host staging vectors may go
-        }
-        // 2·ΣP multi-start EM fits over the views; results stay on the device
-        const int64_t keep_launches = ctx->last_launches;
-        rc = fit_impl(ctx, true, R, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, n_init, max_em_iters, amax, bmax, cmax,
-                      mstep_mode, d_phi.p, d_Q.p, d_stat.p, nullptr, nullptr, nullptr, nullptr, &sb);
-        if (rc) return rc;
-        ctx->last_launches += keep_launches;
-        // per-CpG summaries of every refit, CMD of the two halves of every permutation, then the three statistics
-        rc = cpn_stat_sums_launch(ctx, V, d_phi.p, d_reg.p, d_exo.p, d_ko.p, d_cpg.p, d_rho.p, d_dn.p, d_so.p, d_sp.p, d_sq.p, Nmax, logZ.p, ex.p,
-                                  exx.p, lg.p, e1.p, e2.p, mml.p, nme.p);
-        if (rc) return rc;
-        rc = cpn_cmd_launch(ctx, Pt, d_pa.p, d_pb.p, d_phi.p, d_reg.p, d_exo.p, ex.p, exx.p, d_ko.p, nme.p, d_cpg.p, d_rho.p, d_dn.p, d_so.p, d_sp.p,
-                            d_sq.p, Nmax, d_co.p, cmd.p);
-        if (rc) return rc;
-        { KTimer kt(ctx, CPN_K_SWEEP);
-          k_two_samp_T<<<blocks_for(Pt * 32, 256), 256, 0, s>>>(Pt, d_ko.p, d_co.p, mml.p, nme.p, cmd.p, d_stat.p, T.p); }
-        CPN_CUDA(ctx, cudaGetLastError());
-        CPN_CUDA(ctx, T.download(T_null, 3 * cmd_off[Pt], s));
-        if (fit_status) CPN_CUDA(ctx, d_stat.download(fit_status, V, s));
-        CPN_CUDA(ctx, cudaEventRecord(ctx->ev1, s));
-        CPN_CUDA(ctx, cpn_wait_stream(ctx, s));
-    }
-    float ms = 0;
-    CPN_CUDA(ctx, cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1));
-    ctx->last_ms = ms;
-    if (ctx->profile) cpn_profile_collect(ctx);
-    return CPN_OK;
+    CPN_ARG(ctx, T_null, "null pointer");
+    return two_samp_impl(ctx, R, grp_off, Nl, rho_l, d_l, read_off, log_pyx_u, log_pyx_m, n1, nullptr, nullptr, perm_off, perm_ids, nullptr, phi0,
+                         n_init, max_em_iters, amax, bmax, cmax, mstep_mode, cpg_off, rho_n, d_n, sub_off, sub_p, sub_q, nullptr, nullptr, nullptr,
+                         nullptr, T_null, fit_status);
+}
+
+int cpn_two_samp_test_batch(cpn_ctx* ctx, int64_t R, const int64_t* grp_off, const double* Nl, const double* rho_l, const double* d_l,
+                            const int64_t* read_off, const double* log_pyx_u, const double* log_pyx_m, const int64_t* n1, const double* phi_s1,
+                            const double* phi_s2, const int64_t* perm_off, const int32_t* perm_ids, const int32_t* exact, const double* phi0,
+                            int32_t n_init, int32_t max_em_iters, double amax, double bmax, double cmax, int32_t mstep_mode,
+                            const int64_t* cpg_off, const double* rho_n, const double* d_n, const int64_t* sub_off, const int64_t* sub_p,
+                            const int64_t* sub_q, double* T_obs, int64_t* cnt, int64_t* n_valid, double* pval, double* T_null,
+                            int32_t* fit_status) {
+    if (!ctx) return CPN_ERR_ARG;
+    CPN_ARG(ctx, phi_s1 && phi_s2, "null pointer");
+    return two_samp_impl(ctx, R, grp_off, Nl, rho_l, d_l, read_off, log_pyx_u, log_pyx_m, n1, phi_s1, phi_s2, perm_off, perm_ids, exact, phi0, n_init,
+                         max_em_iters, amax, bmax, cmax, mstep_mode, cpg_off, rho_n, d_n, sub_off, sub_p, sub_q, T_obs, cnt, n_valid, pval, T_null,
+                         fit_status);
 }
 
 }  // extern "C"

@@ -225,9 +225,13 @@ __global__ void __launch_bounds__(SW_THREADS) k_mat_sweep(int n, int Kmax, const
     }
 }
 
+// P permutations for every region (perm_off == null), or region r's own count perm_off[r+1] − perm_off[r] with its null
+// statistics at T_null + 3·nul_off[r]; exact_r (optional) overrides `exact` per region.
 __global__ void __launch_bounds__(SW_THREADS) k_two_samp_pvals(int Kmax, const int64_t* __restrict__ tbl_off, int64_t P,
                                                                 const double* __restrict__ T_obs, const double* __restrict__ T_null, int exact,
-                                                                int64_t* __restrict__ cnt, int64_t* __restrict__ n_valid, double* __restrict__ pval) {
+                                                                int64_t* __restrict__ cnt, int64_t* __restrict__ n_valid, double* __restrict__ pval,
+                                                                const int64_t* __restrict__ perm_off, const int64_t* __restrict__ nul_off,
+                                                                const int32_t* __restrict__ exact_r) {
     extern __shared__ double sm[];
     int64_t r = blockIdx.x;
     int64_t k0 = tbl_off[r];
@@ -237,7 +241,9 @@ __global__ void __launch_bounds__(SW_THREADS) k_two_samp_pvals(int Kmax, const i
     int* s_nv = s_cnt + 3 * Kmax;                // [3][K]
     for (int i = threadIdx.x; i < 3 * K; i += blockDim.x) { s_T[i] = T_obs[3 * k0 + i]; s_cnt[i] = 0; s_nv[i] = 0; }
     __syncthreads();
-    const double* nul = T_null + 3 * k0 * P;
+    const double* nul = T_null + (perm_off ? 3 * nul_off[r] : 3 * k0 * P);
+    if (perm_off) P = perm_off[r + 1] - perm_off[r];
+    if (exact_r) exact = exact_r[r];
     for (int64_t i = threadIdx.x; i < P * 3 * K; i += blockDim.x) {
         int64_t rem = i % (3 * K);
         int t = (int)(rem / K), k = (int)(rem % K);
@@ -307,6 +313,18 @@ int kmax_of(const int64_t* tbl_off, int64_t R) {
 }
 
 }  // namespace
+
+// Launch-only entry of the two-sample counting kernel (all pointers on the device), for the fused two-sample test.
+int cpn_two_samp_pvals_launch(cpn_ctx* ctx, int64_t R, int Kmax, const int64_t* tbl_off, const int64_t* perm_off, const int64_t* nul_off,
+                              const int32_t* exact_r, const double* T_obs, const double* T_null, int64_t* cnt, int64_t* n_valid, double* pval) {
+    size_t smem = (size_t)3 * Kmax * sizeof(double) + (size_t)6 * Kmax * sizeof(int);
+    {
+        KTimer kt(ctx, CPN_K_SWEEP);
+        k_two_samp_pvals<<<(unsigned)R, SW_THREADS, smem, ctx->stream>>>(Kmax, tbl_off, 0, T_obs, T_null, 0, cnt, n_valid, pval, perm_off, nul_off, exact_r);
+    }
+    CPN_CUDA(ctx, cudaGetLastError());
+    return CPN_OK;
+}
 
 extern "C" {
 
@@ -401,7 +419,7 @@ int cpn_two_samp_pvals(cpn_ctx* ctx, int64_t R, const int64_t* tbl_off, int64_t 
         CPN_CUDA(ctx, d_off.upload(tbl_off, R + 1, s)); CPN_CUDA(ctx, d_T.upload(T_obs, 3 * sumK, s));
         CPN_CUDA(ctx, d_null.upload(T_null, 3 * sumK * P, s));
         CPN_CUDA(ctx, o_cnt.alloc(3 * sumK, s)); CPN_CUDA(ctx, o_nv.alloc(3 * sumK, s)); CPN_CUDA(ctx, o_p.alloc(3 * sumK, s));
-        { KTimer kt(ctx, CPN_K_SWEEP); k_two_samp_pvals<<<(unsigned)R, SW_THREADS, smem, s>>>(Kmax, d_off.p, P, d_T.p, d_null.p, exact, o_cnt.p, o_nv.p, o_p.p); }
+        { KTimer kt(ctx, CPN_K_SWEEP); k_two_samp_pvals<<<(unsigned)R, SW_THREADS, smem, s>>>(Kmax, d_off.p, P, d_T.p, d_null.p, exact, o_cnt.p, o_nv.p, o_p.p, nullptr, nullptr, nullptr); }
         CPN_CUDA(ctx, cudaGetLastError());
         CPN_CUDA(ctx, o_cnt.download(cnt, 3 * sumK, s)); CPN_CUDA(ctx, o_nv.download(n_valid, 3 * sumK, s)); CPN_CUDA(ctx, o_p.download(pval, 3 * sumK, s));
         CPN_CUDA(ctx, cudaEventRecord(ctx->ev1, s));

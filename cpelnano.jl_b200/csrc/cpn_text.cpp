@@ -207,15 +207,15 @@ int cpn_add_qvalues(const char* path) {
         p0 = nl ? nl + 1 : end;
     }
     const size_t n_all = rows.size();
-    std::vector<uint32_t> ord;
+    std::vector<size_t> ord;
     ord.reserve(n_all);
     for (size_t i = 0; i < n_all; ++i)
-        if (rows[i].p == rows[i].p) ord.push_back((uint32_t)i);
+        if (rows[i].p == rows[i].p) ord.push_back(i);
     std::vector<double> q(n_all, std::nan(""));
     const size_t n = ord.size();
     if (n == 1) q[ord[0]] = rows[ord[0]].p;
     if (n > 1) {
-        std::stable_sort(ord.begin(), ord.end(), [&](uint32_t a, uint32_t b) { return rows[a].p < rows[b].p; });
+        std::stable_sort(ord.begin(), ord.end(), [&](size_t a, size_t b) { return rows[a].p < rows[b].p; });
         double run = INFINITY;
         for (size_t k = n; k-- > 0;) {
             const double v = rows[ord[k]].p * ((double)n / (double)(k + 1));

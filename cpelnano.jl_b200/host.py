@@ -405,89 +405,97 @@ class Engine:
             t0 += n
         return out
 
-    def diff_two_samp_comp_region(self, mod_s1, mod_s2, calls_s1, calls_s2, config, rng=None, perms=None, phi0s=None):
+    def diff_two_samp_comp_region(self, mod_s1, mod_s2, calls_s1, calls_s2, config, rng=None, perms=None, phi0s=None, seed=None):
         """pmap_diff_two_samp_comp (src/two_samp_perm_tests.jl:157-273) for one region: observed statistics from the two fitted
-        models (per-CpG scale, with summaries), null statistics from refits of permuted reads (group scale features are taken
-        from `calls`' owner mod_s1: Nl, rho_l, dl must describe the CpG groups), p-values by counting."""
-        K = mod_s1.nls_rgs.num
-        T_obs = np.stack([mod_s1.mml - mod_s2.mml, mod_s1.nme - mod_s2.nme, self.comp_cmd_pairs([mod_s1, mod_s2], [(0, 1)])[0]])
-        pval = np.full((3, K), np.nan)
-        out = dict(T=T_obs, pval=pval, cnt=None, n_valid=None, exact=None)
-        if not config.pval_comp:
-            return out
-        n1, n2 = calls_s1[0].shape[0], calls_s2[0].shape[0]
-        Lc = math.comb(n1 + n2, n1)
-        if Lc <= 20:
-            return out
-        exact = Lc < config.LMAX_TWO_SAMP
-        if perms is None:
-            if exact:
-                perms = np.array(list(combinations(range(1, n1 + n2 + 1), n1)), dtype=np.int64)
-            else:    # sort!(StatsBase.sample(1:n, n1; replace=false)) LMAX_TWO_SAMP times (:211-214)
-                rng = rng or np.random.default_rng()
-                perms = np.stack([np.sort(rng.choice(np.arange(1, n1 + n2 + 1), n1, replace=False)) for _ in range(config.LMAX_TWO_SAMP)])
-        import copy
-        ref = copy.copy(mod_s1.group_view if mod_s1.group_view is not None else mod_s1)    # "back to group scale" (:198-199)
-        ref.nls_rgs, ref.rho_n, ref.dn, ref.N = mod_s1.nls_rgs, mod_s1.rho_n, mod_s1.dn, mod_s1.N
-        T_null = self.two_samp_null_stats_device([(ref, calls_s1, calls_s2, perms)], config, None if phi0s is None else [phi0s], rng)[0]
-        cnt, nv, p = self.lib.two_samp_pvals(np.array([0, K]), len(perms), T_obs.reshape(-1), T_null.reshape(-1), exact, device=self.device)
-        out.update(pval=p.reshape(3, K), cnt=cnt.reshape(3, K), n_valid=nv.reshape(3, K), exact=exact, T_null=T_null)
-        return out
+        models, null statistics from refits of permuted reads, p-values by counting.  Returns T_null too."""
+        return self.diff_two_samp_comp_batch([(mod_s1, mod_s2, calls_s1, calls_s2)], config, rng=rng, perms=None if perms is None else [perms],
+                                             phi0s=None if phi0s is None else [phi0s], seed=seed, want_null=True)[0]
 
-    def diff_two_samp_comp_batch(self, items, config, rng=None, perms=None, phi0s=None):
-        """pmap_diff_two_samp_comp for many regions: items = [(mod_s1, mod_s2, calls_s1, calls_s2)], models at per-CpG scale with
-        summaries.  Observed CMDs in one call, the null refits of ALL regions in one cpn_two_samp_null_batch call, p-value counts
-        in one cpn_two_samp_pvals call per distinct (number of permutations, exact) pair.  perms / phi0s: optional per-region
-        lists (tests); default: all C(n, n1) splits when fewer than config.LMAX_TWO_SAMP, else LMAX_TWO_SAMP sorted samples."""
+    def diff_two_samp_comp_batch(self, items, config, rng=None, perms=None, phi0s=None, seed=None, want_null=False):
+        """pmap_diff_two_samp_comp for many regions through cpn_two_samp_test_batch: items = [(mod_s1, mod_s2, calls_s1, calls_s2)],
+        models with ϕ̂ and the per-CpG features (summaries are recomputed on the device).  Observed statistics, the null refits of
+        ALL regions, NaN filter and counting happen in one device call per group of regions; only (T, cnt, n_valid, p) come back
+        (plus T_null when want_null).  Permutations: `perms[i]` if given; all C(n, n1) splits when fewer than
+        config.LMAX_TWO_SAMP (exact, :195); else LMAX_TWO_SAMP sorted samples (:211-214) drawn on the host from `rng` — or, when
+        `seed` is given, drawn on the device together with the EM starts (nothing random crosses PCIe)."""
         import copy
         R = len(items)
         if R == 0:
             return []
-        models, pairs = [], []
-        for (m1, m2, _, _) in items:
-            pairs.append((len(models), len(models) + 1)); models.extend([m1, m2])
-        cmds = self.comp_cmd_pairs(models, pairs)
-        outs, todo = [], []
+        outs = [None] * R
+        todo = {False: [], True: []}            # regions whose index sets are explicit / drawn on the device
         for i, (m1, m2, c1, c2) in enumerate(items):
-            K = m1.nls_rgs.num
-            T_obs = np.stack([m1.mml - m2.mml, m1.nme - m2.nme, cmds[i]])
-            outs.append(dict(T=T_obs, pval=np.full((3, K), np.nan), cnt=None, n_valid=None, exact=None, coords=m1.nls_rgs))
-            if not config.pval_comp:
-                continue
             n1, n2 = c1[0].shape[0], c2[0].shape[0]
-            if n1 == 0 or n2 == 0:
+            P, exact, pr = 0, False, None
+            if config.pval_comp and n1 > 0 and n2 > 0:
+                Lc = math.comb(n1 + n2, n1)
+                if Lc > 20:                                                   # :192
+                    exact = Lc < config.LMAX_TWO_SAMP
+                    if perms is not None and perms[i] is not None:
+                        pr = np.asarray(perms[i], dtype=np.int32)
+                    elif exact:
+                        pr = np.array(list(combinations(range(1, n1 + n2 + 1), n1)), dtype=np.int32)
+                    elif seed is None:    # sort!(StatsBase.sample(1:n, n1; replace=false)) LMAX_TWO_SAMP times (:211-214)
+                        rng = rng or np.random.default_rng()
+                        pr = np.stack([np.sort(rng.choice(np.arange(1, n1 + n2 + 1), n1, replace=False)) for _ in range(config.LMAX_TWO_SAMP)]).astype(np.int32)
+                    P = config.LMAX_TWO_SAMP if pr is None else len(pr)
+            todo[pr is None and P > 0].append((i, P, exact, pr))
+        for on_device, grp in todo.items():
+            if not grp:
                 continue
-            Lc = math.comb(n1 + n2, n1)
-            if Lc <= 20:
-                continue
-            exact = Lc < config.LMAX_TWO_SAMP
-            if perms is not None and perms[i] is not None:
-                pr = np.asarray(perms[i], dtype=np.int64)
-            elif exact:
-                pr = np.array(list(combinations(range(1, n1 + n2 + 1), n1)), dtype=np.int64)
-            else:    # sort!(StatsBase.sample(1:n, n1; replace=false)) LMAX_TWO_SAMP times (:211-214)
-                rng = rng or np.random.default_rng()
-                pr = np.stack([np.sort(rng.choice(np.arange(1, n1 + n2 + 1), n1, replace=False)) for _ in range(config.LMAX_TWO_SAMP)])
-            ref = copy.copy(m1.group_view if m1.group_view is not None else m1)    # "back to group scale" (:198-199)
-            ref.nls_rgs, ref.rho_n, ref.dn, ref.N = m1.nls_rgs, m1.rho_n, m1.dn, m1.N
-            todo.append((i, ref, pr, exact))
-        if not todo:
-            return outs
-        T_nulls = self.two_samp_null_stats_device([(ref, items[i][2], items[i][3], pr) for (i, ref, pr, _) in todo], config,
-                                                  None if phi0s is None else [phi0s[i] for (i, _, _, _) in todo], rng)
-        groups = {}
-        for j, (i, ref, pr, exact) in enumerate(todo):
-            groups.setdefault((len(pr), exact), []).append(j)
-        for (P, exact), js in groups.items():
-            Ks = [outs[todo[j][0]]["T"].shape[1] for j in js]
-            tbl_off = np.concatenate([[0], np.cumsum(Ks)]).astype(np.int64)
-            T_obs = np.concatenate([outs[todo[j][0]]["T"].reshape(-1) for j in js])
-            T_null = np.concatenate([T_nulls[j].reshape(-1) for j in js])
-            cnt, nv, p = self.lib.two_samp_pvals(tbl_off, P, T_obs, T_null, exact, device=self.device)
-            for a, j in enumerate(js):
-                i, K = todo[j][0], Ks[a]
-                sl = slice(3 * tbl_off[a], 3 * tbl_off[a + 1])
-                outs[i].update(pval=p[sl].reshape(3, K), cnt=cnt[sl].reshape(3, K), n_valid=nv[sl].reshape(3, K), exact=exact, T_null=T_nulls[j])
+            idx = [g[0] for g in grp]
+            refs = []
+            for i in idx:
+                m1 = items[i][0]
+                ref = copy.copy(m1.group_view if m1.group_view is not None else m1)    # "back to group scale" (:198-199)
+                ref.nls_rgs, ref.rho_n, ref.dn, ref.N = m1.nls_rgs, m1.rho_n, m1.dn, m1.N
+                if ref.nls_rgs.num == 0:
+                    self.get_nls_reg_info(ref, config)
+                refs.append(ref)
+            has_reads = [items[i][2][0].shape[0] + items[i][3][0].shape[0] > 0 for i in idx]
+            # regions without reads (pval_comp off) still need a well-formed pooled sample for the ABI: one blank read per sample
+            pooled = []
+            for i, ref, hr in zip(idx, refs, has_reads):
+                if hr:
+                    pooled.append((np.concatenate([items[i][2][0], items[i][3][0]]), np.concatenate([items[i][2][1], items[i][3][1]]), items[i][2][0].shape[0]))
+                else:
+                    blank = np.full((2, len(ref.Nl)), np.nan)
+                    pooled.append((blank, blank, 1))
+            grp_off = np.concatenate([[0], np.cumsum([len(r.Nl) for r in refs])]).astype(np.int64)
+            Nl = np.concatenate([np.asarray(r.Nl, dtype=np.float64) for r in refs]); rho_l = np.concatenate([np.asarray(r.rho_l, dtype=np.float64) for r in refs])
+            d_l = np.concatenate([np.asarray(r.dl, dtype=np.float64) for r in refs])
+            lu = np.concatenate([p[0].reshape(-1) for p in pooled]); lm = np.concatenate([p[1].reshape(-1) for p in pooled])
+            read_off = np.concatenate([[0], np.cumsum([p[0].shape[0] for p in pooled])]).astype(np.int64)
+            n1 = np.array([p[2] for p in pooled], dtype=np.int64)
+            perm_off = np.concatenate([[0], np.cumsum([g[1] for g in grp])]).astype(np.int64)
+            exact = np.array([int(g[2]) for g in grp], dtype=np.int32)
+            perm_ids = None if on_device else (np.concatenate([g[3].reshape(-1) for g in grp if g[1] > 0]) if perm_off[-1] > 0 else np.zeros(0, dtype=np.int32))
+            if phi0s is not None and perm_off[-1] > 0:
+                phi0 = np.concatenate([np.asarray(phi0s[i]).reshape(-1, config.max_em_init, 3) for i, P, _, _ in grp if P > 0])
+            elif on_device or perm_off[-1] == 0:
+                phi0 = None
+            else:
+                from .simulations import gen_phi0s
+                phi0 = gen_phi0s(rng or np.random.default_rng(), 2 * int(perm_off[-1]), config.max_em_init)
+            if on_device or (phi0 is None and perm_off[-1] > 0):
+                self.lib.set_seed(0 if seed is None else seed, self.device)
+            cpg_off, rho_n, d_n, sub_off, sub_p, sub_q = self.pack_cpgs(refs)
+            phi1 = np.array([items[i][0].phihat for i in idx]); phi2 = np.array([items[i][1].phihat for i in idx])
+            res = self.lib.two_samp_test_batch(grp_off, Nl, rho_l, d_l, read_off, lu, lm, n1, phi1, phi2, perm_off, perm_ids, exact, phi0,
+                                               config.max_em_init, cpg_off, rho_n, d_n, sub_off, sub_p, sub_q, config.max_em_iters,
+                                               (AMAX, BMAX, CMAX), config.mstep_mode, want_null=want_null, device=self.device)
+            t0 = 0
+            for a, (i, P, ex, pr) in enumerate(grp):
+                K = int(sub_off[a + 1] - sub_off[a])
+                sl = slice(3 * sub_off[a], 3 * sub_off[a + 1])
+                o = dict(T=res["T"][sl].reshape(3, K), pval=res["pval"][sl].reshape(3, K), cnt=None, n_valid=None, exact=None, coords=refs[a].nls_rgs)
+                if P > 0:
+                    o.update(cnt=res["cnt"][sl].reshape(3, K), n_valid=res["n_valid"][sl].reshape(3, K), exact=bool(ex))
+                    if want_null:
+                        o["T_null"] = res["T_null"][t0:t0 + P * 3 * K].reshape(P, 3, K)
+                        o["fit_status"] = res["fit_status"][2 * perm_off[a]:2 * perm_off[a + 1]].reshape(P, 2)
+                t0 += P * 3 * K
+                outs[i] = o
         return outs
 
 

@@ -19,8 +19,9 @@ MASTER_SEED = 20211111
 
 
 def load_layouts(path=None):
-    """Real 3 kb CpG layouts (N>9, L>1) of the bundled hg38 chr17 window (tests/golden/layouts_targeted.npz)."""
-    path = path or os.path.join(_REPO, "tests", "golden", "layouts_targeted.npz")
+    """Real 3 kb CpG layouts (N>9, L>1) of the bundled hg38 chr17 window: package data (data/layouts_targeted.npz, written by
+    tests/golden/make_fixtures.py from the reference's targeted-example FASTA)."""
+    path = path or os.path.join(_HERE, "data", "layouts_targeted.npz")
     z = np.load(path)
     return {k: z[k] for k in z.files}
 

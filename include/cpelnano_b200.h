@@ -41,8 +41,17 @@ enum {
  *                       FiniteDiff central Jacobian), same step sizes and evaluation order            */
 enum { CPN_MSTEP_FD = 0, CPN_MSTEP_ANALYTIC = 1 };
 
-/* per-start / per-region status of the EM fit (src/em_algorithm.jl:341-344,385) */
-enum { CPN_FIT_NONE = -1 /* all starts ended with Q=-Inf: rs.ϕhat = [] */ };
+/* Per-region status word of the EM fit (`status` outputs; SURVEY.md §5 failure handling).  The reference "logs and skips": a
+ * region without a fit gets rs.ϕhat = [] (src/em_algorithm.jl:385), rs.proc stays false and the writers skip it.
+ *   >= 0                   index (0-based) of the picked start: ok
+ *   CPN_FIT_NONE           every start ended with Q = -Inf (stopped in its first iteration or hit max_em_iters, :341-344)
+ *   CPN_FIT_NUMERICAL      as CPN_FIT_NONE, and at least one M-step of the region met a non-finite residual or iterate (the
+ *                          exception the reference catches and logs, :160-172)
+ *   <= CPN_FIT_FILTERED    the region never reached the EM: it failed a data filter of pmap_analyze_reg (src/nanopore.jl:309,
+ *                          322-326).  Written by cpn_region_filter as CPN_FIT_FILTERED - (OR of the CPN_FILTER_* reasons).      */
+enum { CPN_FIT_NONE = -1, CPN_FIT_NUMERICAL = -2, CPN_FIT_FILTERED = -16 };
+enum { CPN_FILTER_FEW_CPGS = 1 /* N <= 9, :309 */, CPN_FILTER_NO_READS = 2 /* rs.m == 0 */, CPN_FILTER_LOW_DEPTH = 4 /* get_ave_depth <
+       min_cov, :322 */, CPN_FILTER_FEW_GROUPS_OBS = 8 /* perc_gprs_obs < 0.66, :323 */, CPN_FILTER_ONE_GROUP = 16 /* L <= 1, :326 */ };
 
 /* ---- context ------------------------------------------------------------------------------- */
 int  cpn_create(int device_id, cpn_ctx** out);
@@ -53,9 +62,24 @@ const char* cpn_version(void);
  * it launched (for bench.py's gpu_launches). */
 double  cpn_last_device_ms(const cpn_ctx* ctx);
 int64_t cpn_last_launches(const cpn_ctx* ctx);
+/* Algorithmic work of the EM fits of the last call, for roofline accounting (bench.py): work[0] = sum over EM instances of
+ * E-step passes x reads x groups, work[1] = sum of derivative sweeps (analytic mode) or log Z evaluations (FD mode) x groups,
+ * work[2] = reads x groups of the final log p(y) pass over converged instances, work[3] = number of EM instances.            */
+int cpn_last_work(const cpn_ctx* ctx, double* work /*[4]*/);
 /* Measured FP64 FMA peak of this device (dependent-chain-free DFMA loop), TFLOP/s; and a DRAM copy
  * bandwidth figure GB/s.  Used as roofline denominators when MEASURED_PEAKS.json has no FP64 entry. */
 int cpn_measure_fp64_peak(cpn_ctx* ctx, double* tflops);
+/* Seed of the counter-based stream (Philox-4x32-10, csrc/cpn_philox.h) that replaces the host RNG wherever an entry point is
+ * given phi0 == NULL (EM starts, gen_ϕ0s src/em_algorithm.jl:65-78) or perm_ids == NULL (read-label permutations,
+ * src/two_samp_perm_tests.jl:211-214).  Starts are keyed by (seed, position of the region in the call's batch, start), so a
+ * result does not depend on how the library chunks or shards the batch.  Default seed 0.                                     */
+int cpn_set_seed(cpn_ctx* ctx, uint64_t seed);
+/* The same stream evaluated on the host (no GPU needed), for callers that want the arrays the device would draw:
+ *   cpn_rng_phi0   the n_init starts [n_init*3] of one EM unit: region = position in the batch; perm < 0 for the plain fit, else the
+ *                  permutation index with half = 0 / 1 for the two refits of that permutation
+ *   cpn_rng_perm   the n1 ascending 1-based indices of sample 1 for permutation `perm` of `region` with n pooled reads           */
+int cpn_rng_phi0(uint64_t seed, int64_t region, int64_t perm, int32_t half, int32_t n_init, double* phi0);
+int cpn_rng_perm(uint64_t seed, int64_t region, int64_t perm, int32_t n, int32_t n1, int32_t* ids);
 /* Optional per-launch profiler: when enabled, every kernel launch is bracketed by CUDA events on the
  * launching stream and its time accumulated per kernel class (8 classes: 0 prep, 1 E-step, 2 M-step,
  * 3 score, 4 pick, 5 summaries, 6 CMD, 7 sweeps).  cpn_set_profile resets the accumulators.          */
@@ -66,10 +90,10 @@ int cpn_get_profile(const cpn_ctx* ctx, double* ms /*[8]*/, int64_t* launches /*
  * For every region r: run n_init EM instances (em_inst, :304-350) from the given starts phi0 (the host
  * RNG owns gen_ϕ0s, :65-78), keep the first start with maximal Q = mean_m log p(y_m; ϕ) (pick_ϕ, :35-53).
  * Inputs are HOST pointers (copied to the device inside the call).
- *   phi0        [R * n_init * 3]
+ *   phi0        [R * n_init * 3], or NULL: drawn on the device from the context's seed (cpn_set_seed)
  *   phi_hat     [R * 3]   NaN when no start converged
  *   Q           [R]       -Inf when no start converged
- *   status      [R]       index of the picked start (0-based) or CPN_FIT_NONE
+ *   status      [R]       index of the picked start (0-based), or CPN_FIT_NONE / CPN_FIT_NUMERICAL (status word above)
  *   counters    [R * 4]   (em_iters, solver_iters, logZ_evals, estep_passes) summed over starts; may be NULL
  *   phi_starts  [R * n_init * 3], Q_starts [R * n_init]  per-start results; may be NULL              */
 int cpn_fit_batch(cpn_ctx* ctx, int64_t R,
@@ -203,8 +227,8 @@ int cpn_grp_test_batch(cpn_ctx* ctx, int64_t R, int32_t n1, int32_t n2, int32_t 
  *   grp_off ... log_pyx_m  as in cpn_fit_batch; the reads of region r are vcat(calls_s1, calls_s2) (:54)
  *   perm_off [R+1]         permutations per region;  n1 [R] reads of sample 1
  *   perm_ids               for region r, P_r rows of n1[r] ascending 1-based indices into the pooled reads = sample 1 (:57);
- *                          sample 2 is the rest, in order (deleteat!, :58-59)
- *   phi0 [sum P_r*2*n_init*3]  EM starts, ordered region, permutation, half, start
+ *                          sample 2 is the rest, in order (deleteat!, :58-59); or NULL: drawn on the device (cpn_set_seed)
+ *   phi0 [sum P_r*2*n_init*3]  EM starts, ordered region, permutation, half, start; or NULL: drawn on the device (cpn_set_seed)
  *   cpg_off ... sub_q      per-CpG tables as in cpn_stat_sums_batch
  *   T_null [sum_r P_r*3*K_r]   region-major, then permutation, statistic (mml, nme, cmd), sub-region: the layout
  *                          cpn_two_samp_pvals reads; NaN for a permutation when either refit has no optimum (:65)
@@ -215,6 +239,28 @@ int cpn_two_samp_null_batch(cpn_ctx* ctx, int64_t R, const int64_t* grp_off, con
                             int32_t n_init, int32_t max_em_iters, double amax, double bmax, double cmax, int32_t mstep_mode,
                             const int64_t* cpg_off, const double* rho_n, const double* d_n, const int64_t* sub_off,
                             const int64_t* sub_p, const int64_t* sub_q, double* T_null, int32_t* fit_status);
+/* The whole two-sample test of a batch of regions in one call  src/two_samp_perm_tests.jl:157-273 (pmap_diff_two_samp_comp) over the
+ * serial map of :445: observed statistics from the two fitted models (:165-167: get_stat_sums! of both, comp_cmd), null statistics
+ * from the refits of every permutation (cpn_two_samp_null_batch's computation), NaN filter, ">20 valid" rule and counting (:230-258).
+ * Only the pooled reads and the two models' ϕ̂ go in and only (T, cnt, n_valid, p) come out: T_null (216 KB per region at 1000
+ * permutations) never crosses PCIe unless asked for.  Regions are processed in chunks of bounded workspace
+ * (CPN_TWO_SAMP_MAX_VIEWS refits per chunk, default 2^20), so the batch may be a whole chromosome.
+ *   phi_s1, phi_s2 [R*3]   ϕ̂ of the two samples (from their model files)
+ *   perm_ids               as in cpn_two_samp_null_batch, or NULL: perm_off[r+1]-perm_off[r] index sets per region are drawn on the
+ *                          device from the context's seed (ascending, uniform over the C(n, n1) subsets: the law of
+ *                          sort!(sample(1:n, n1; replace=false)), :211-214)
+ *   exact [R] or NULL      1: p = cnt/n_valid (all C(n,n1) splits were enumerated, :254), 0: p = (1+cnt)/(1+n_valid) (:256)
+ *   phi0                   as in cpn_two_samp_null_batch, or NULL: drawn on the device from the context's seed
+ *   T_obs, cnt, n_valid, pval [sumK*3]  region-major, (tmml, tnme, tcmd) blocks of K_r; p is NaN for empty sub-regions and where
+ *                          at most 20 permutations gave a finite statistic
+ *   T_null, fit_status     optional (NULL: not returned), layouts of cpn_two_samp_null_batch                                         */
+int cpn_two_samp_test_batch(cpn_ctx* ctx, int64_t R, const int64_t* grp_off, const double* Nl, const double* rho_l, const double* d_l,
+                            const int64_t* read_off, const double* log_pyx_u, const double* log_pyx_m, const int64_t* n1,
+                            const double* phi_s1, const double* phi_s2, const int64_t* perm_off, const int32_t* perm_ids,
+                            const int32_t* exact, const double* phi0, int32_t n_init, int32_t max_em_iters, double amax, double bmax,
+                            double cmax, int32_t mstep_mode, const int64_t* cpg_off, const double* rho_n, const double* d_n,
+                            const int64_t* sub_off, const int64_t* sub_p, const int64_t* sub_q, double* T_obs, int64_t* cnt,
+                            int64_t* n_valid, double* pval, double* T_null, int32_t* fit_status);
 /* two-sample p-value counting  src/two_samp_perm_tests.jl:230-258: T_obs [ΣK*3] region-major (tmml,tnme,tcmd
  * blocks of K_r), T_null [Σ_r P*3*K_r] permutation-major per region; NaN nulls are dropped, >20 valid needed. */
 int cpn_two_samp_pvals(cpn_ctx* ctx, int64_t R, const int64_t* tbl_off, int64_t P, const double* T_obs,
@@ -254,6 +300,10 @@ int cpn_calls_count_reads(const cpn_calls* calls, const char* chr, int64_t R, co
  *                          n_obs[r] observed (read, group) cells, n_grp_obs[r] groups observed in at least one read               */
 int cpn_calls_coverage(int64_t R, const int64_t* grp_off, const int64_t* read_off, const double* log_pyx_u, int32_t n_threads,
                        int64_t* n_obs, int64_t* n_grp_obs);
+/*   cpn_region_filter     the data filters of pmap_analyze_reg (src/nanopore.jl:309, 322-326) as status words: 0 = the region goes on to
+ *                          the EM, else CPN_FIT_FILTERED - (OR of CPN_FILTER_* reasons); n_cpg[r] = CpG sites of region r                 */
+int cpn_region_filter(int64_t R, const int64_t* n_cpg, const int64_t* grp_off, const int64_t* read_off, const double* log_pyx_u,
+                      double min_cov, int32_t n_threads, int32_t* status);
 int cpn_calls_fill(const cpn_calls* calls, const char* chr, int64_t R, const int64_t* chrst, const int64_t* chrend,
                    const int64_t* grp_off, const int64_t* grp_st, const int64_t* grp_end, int32_t mod_nse,
                    const int64_t* read_off, int32_t n_threads, double* log_pyx_u, double* log_pyx_m, int64_t* read_ids);

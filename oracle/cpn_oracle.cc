@@ -914,6 +914,49 @@ void orc_two_samp_pvals(int64_t K, int64_t P, const double* T_obs, const double*
     }
 }
 
+// ---- counter-based stream of EM starts and read-label permutations ----------------------
+// Independent restatement of the stream the library defines in cpelnano.jl_b200/csrc/cpn_philox.h, from the published
+// Philox-4x32-10 algorithm (Salmon, Moraes, Dror, Shaw: "Parallel random numbers: as easy as 1, 2, 3", SC'11; known-answer
+// vectors of the Random123 distribution are checked in tests/test_oracle_kats.py).  The reference itself draws from Julia's
+// global MersenneTwister (gen_ϕ0s em_algorithm.jl:65-78; sort!(sample(1:n, n1; replace=false)) two_samp_perm_tests.jl:211-214):
+// that stream cannot be reproduced without Julia and is not claimed.
+static void philox_round(uint32_t ctr[4], const uint32_t key[2]) {
+    const uint64_t prod_a = 0xD2511F53ull * ctr[0];
+    const uint64_t prod_b = 0xCD9E8D57ull * ctr[2];
+    const uint32_t hi_a = (uint32_t)(prod_a >> 32), lo_a = (uint32_t)(prod_a & 0xffffffffull);
+    const uint32_t hi_b = (uint32_t)(prod_b >> 32), lo_b = (uint32_t)(prod_b & 0xffffffffull);
+    const uint32_t out[4] = {hi_b ^ ctr[1] ^ key[0], lo_b, hi_a ^ ctr[3] ^ key[1], lo_a};
+    for (int i = 0; i < 4; ++i) ctr[i] = out[i];
+}
+void orc_philox4x32_10(uint64_t seed, uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, uint32_t* out4) {
+    uint32_t ctr[4] = {c0, c1, c2, c3};
+    uint32_t key[2] = {(uint32_t)(seed & 0xffffffffull), (uint32_t)(seed >> 32)};
+    philox_round(ctr, key);
+    for (int r = 1; r < 10; ++r) {
+        key[0] += 0x9E3779B9u; key[1] += 0xBB67AE85u;            // Weyl sequence key schedule
+        philox_round(ctr, key);
+    }
+    for (int i = 0; i < 4; ++i) out4[i] = ctr[i];
+}
+static uint32_t scale_u32(uint32_t x, uint32_t m) { return (uint32_t)(((uint64_t)x * m) / 4294967296ull); }   // ⌊x·m / 2^32⌋ ∈ 0..m−1
+// start `start` of unit (region, perm, half): the grid of gen_ϕ0s (em_algorithm.jl:72): a ∈ −5:0.01:5, b ∈ −50:0.01:50, c ∈ 0:0.01:10
+void orc_gen_phi0(uint64_t seed, uint32_t region, uint32_t perm, uint32_t half, uint32_t start, double* phi0) {
+    uint32_t w[4];
+    orc_philox4x32_10(seed, region, perm, half * 65536u + start, 0u, w);
+    phi0[0] = ((double)scale_u32(w[0], 1001u) - 500.0) / 100.0;
+    phi0[1] = ((double)scale_u32(w[1], 10001u) - 5000.0) / 100.0;
+    phi0[2] = (double)scale_u32(w[2], 1001u) / 100.0;
+}
+// ascending 1-based indices of sample 1 for permutation `perm` of `region` (n pooled reads, n1 in sample 1): selection sampling
+void orc_gen_perm(uint64_t seed, uint32_t region, uint32_t perm, int32_t n, int32_t n1, int32_t* ids) {
+    int32_t need = n1, k = 0;
+    uint32_t w[4] = {0, 0, 0, 0};
+    for (int32_t q = 0; q < n; ++q) {
+        if (q % 4 == 0) orc_philox4x32_10(seed, region, perm, (uint32_t)(q / 4), 1u, w);
+        if ((int32_t)scale_u32(w[q % 4], (uint32_t)(n - q)) < need) { ids[k++] = q + 1; --need; }
+    }
+}
+
 // ---- legacy non-log primitives: only to pin test/runtests.jl:9-25,46-59 --------------
 static void mm2(const double* A, const double* B, double* C) {
     C[0] = A[0] * B[0] + A[1] * B[2]; C[1] = A[0] * B[1] + A[1] * B[3];

@@ -262,3 +262,30 @@ def nonlog_chain(al, be, lu=None, lm=None):
         lu, lm = _f(lu), _f(lm)
     lib().orc_nonlog_chain(C.c_int64(L), _p(al), _p(be), _p(lu), _p(lm), C.byref(Z), _p(ex), _p(exx))
     return Z.value, ex, exx
+
+
+# ---- counter-based stream of starts / permutations (restatement of csrc/cpn_philox.h's specification) -----------------------
+NO_PERM = 0xFFFFFFFF
+
+
+def philox4x32_10(seed, c0, c1, c2, c3):
+    out = np.zeros(4, dtype=np.uint32)
+    lib().orc_philox4x32_10(C.c_uint64(seed), C.c_uint32(c0), C.c_uint32(c1), C.c_uint32(c2), C.c_uint32(c3), _p(out))
+    return out
+
+
+def gen_phi0(seed, region, perm, half, start):
+    out = np.zeros(3)
+    lib().orc_gen_phi0(C.c_uint64(seed), C.c_uint32(region), C.c_uint32(perm), C.c_uint32(half), C.c_uint32(start), _p(out))
+    return out
+
+
+def gen_phi0s(seed, regions, n_init, perm=NO_PERM, half=0):
+    """[len(regions), n_init, 3] starts of plain fits (perm = NO_PERM) or of one (perm, half) refit per region."""
+    return np.array([[gen_phi0(seed, int(r), perm, half, s) for s in range(n_init)] for r in regions])
+
+
+def gen_perm(seed, region, perm, n, n1):
+    ids = np.zeros(n1, dtype=np.int32)
+    lib().orc_gen_perm(C.c_uint64(seed), C.c_uint32(region), C.c_uint32(perm), C.c_int32(n), C.c_int32(n1), _p(ids))
+    return ids

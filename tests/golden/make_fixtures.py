@@ -213,7 +213,7 @@ def main():
         for k in ("cpg_pos", "rho_n", "d_n", "Nl", "rho_l", "d_l"):
             lay[k].append(gi[k])
         cpg_off.append(cpg_off[-1] + gi["N"]); grp_off.append(grp_off[-1] + len(gi["Nl"]))
-    np.savez_compressed(f"{OUT}/layouts_targeted.npz", chrst=np.array(lay["chrst"], dtype=np.int64), chrend=np.array(lay["chrend"], dtype=np.int64),
+    np.savez_compressed(f"{OUT}/../../cpelnano.jl_b200/data/layouts_targeted.npz", chrst=np.array(lay["chrst"], dtype=np.int64), chrend=np.array(lay["chrend"], dtype=np.int64),
                         cpg_off=np.array(cpg_off, dtype=np.int64), grp_off=np.array(grp_off, dtype=np.int64),
                         **{k: np.concatenate(lay[k]) for k in ("cpg_pos", "rho_n", "d_n", "Nl", "rho_l", "d_l")})
     Ls = np.diff(grp_off); Ns = np.diff(cpg_off)

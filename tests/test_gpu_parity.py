@@ -399,36 +399,8 @@ def test_two_samp_pvals_bit_exact(engine, orc):
         assert np.all(np.isnan(p[3 * K * 3:3 * K * 4]))
 
 
-def test_two_sample_null_stats_pipeline(engine, orc, cpn):
-    """pmap_two_samp_null_stats (two_samp_perm_tests.jl:41-87): split pooled reads, refit both halves, summaries, CMD —
-    same composition on the oracle; statistics agree within the EM's own reproducibility (see module docstring)."""
-    nb = cpn.simulations.make_nano_batch(1, M=24, seed=31)
-    rg = nb.region(0)
-    cfg = cpn.CpelNanoConfig(max_em_init=3)
-    ref = cpn.RegStruct(chr="c", chrst=int(nb.chrst[0]), chrend=int(nb.chrend[0]), N=int(nb.cpg_off[1]), L=rg["L"], Nl=rg["Nl"], rho_l=rg["rho_l"],
-                        dl=rg["d_l"], rho_n=nb.rho_n, dn=nb.d_n, cpg_pos=nb.cpg_pos)
-    engine.get_nls_reg_info(ref, cfg)
-    rng = np.random.default_rng(6)
-    phi0 = cpn.simulations.gen_phi0s(rng, 2, 3)
-    perm = np.sort(rng.choice(np.arange(1, 25), 12, replace=False))
-    s1, s2 = (rg["lu"][:12], rg["lm"][:12]), (rg["lu"][12:], rg["lm"][12:])
-    tm, tn, tc = cpn.pmap_two_samp_null_stats(ref, s1, s2, perm, cfg, phi0s=phi0, engine=engine)
-    # oracle composition
-    idx = perm - 1
-    rest = np.setdiff1d(np.arange(24), idx)
-    K = ref.nls_rgs.num
-    fits = []
-    for sel, p0 in ((idx, phi0[0]), (rest, phi0[1])):
-        o = orc.fit_batch(np.array([0, rg["L"]]), rg["Nl"], rg["rho_l"], rg["d_l"], np.array([0, 12]), rg["lu"][sel].reshape(-1),
-                          rg["lm"][sel].reshape(-1), p0[None], 3)
-        fits.append(o)
-    if fits[0]["pick"][0] < 0 or fits[1]["pick"][0] < 0:
-        assert np.all(np.isnan(tm)) and len(tm) == K
-        return
-    ss = [orc.get_stat_sums(f["phi_hat"][0], nb.rho_n, nb.d_n, ref.nls_rgs.cpg_p, ref.nls_rgs.cpg_q) for f in fits]
-    assert np.allclose(tm, ss[0]["mml"] - ss[1]["mml"], atol=5e-3, equal_nan=True)
-    assert np.allclose(tn, ss[0]["nme"] - ss[1]["nme"], atol=5e-3, equal_nan=True)
-    assert np.all((np.isnan(tc)) | ((tc > -1e-6) & (tc < 1.0)))
+# pmap_two_samp_null_stats against the oracle's composition (8 regions x 50 permutations, Tmml / Tnme / Tcmd):
+# tests/test_em_output_parity.py::test_two_sample_null_stats_vs_oracle_composition
 
 
 def test_two_sample_batched_permutations(engine, orc, cpn):

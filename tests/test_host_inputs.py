@@ -16,6 +16,7 @@ import cpelnano_b200 as cpn
 from cpelnano_b200 import genome, nanopolish
 
 GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 INP = os.path.join(GOLD, "inputs")
 
 
@@ -75,7 +76,7 @@ def test_partition_bed_contains_golden_regions(chr_targeted):
 def test_partition_whole_chromosome_matches_layout_fixture(chr_targeted):
     """Whole-chromosome partition (genome_analysis.jl:327-390) + the N>9, L>1 filters of pmap_analyze_reg reproduce the
     137 layouts the synthetic workload cycles through."""
-    lay = np.load(os.path.join(GOLD, "layouts_targeted.npz"))
+    lay = np.load(os.path.join(ROOT, "cpelnano.jl_b200", "data", "layouts_targeted.npz"))
     part = chr_targeted.chr_part(3000, 10)
     keep = []
     for a, b in part:

@@ -121,3 +121,33 @@ def test_logpy_matches_bruteforce(orc):
     ll = np.where(xs == 1, np.nan_to_num(lm), np.nan_to_num(lu)).sum(1)
     ref = np.log(np.exp(logw + ll).sum()) - np.log(np.exp(logw).sum())
     assert abs(orc.get_logpy(al, be, lu, lm) - ref) < 1e-12
+
+
+def test_philox_known_answers_and_product_stream(orc, cpn):
+    """Philox-4x32-10 known-answer vectors of the Random123 distribution (kat_vectors: zero, all-ones, digits of pi) pin the
+    oracle's restatement; the library's host-side evaluation of the stream (cpn_rng_*, the same header the device kernels
+    include) must then agree with the oracle's independent restatement on starts and permutations."""
+    assert [hex(x) for x in orc.philox4x32_10(0, 0, 0, 0, 0)] == ["0x6627e8d5", "0xe169c58d", "0xbc57ac4c", "0x9b00dbd8"]
+    assert [hex(x) for x in orc.philox4x32_10(0xFFFFFFFFFFFFFFFF, 0xFFFFFFFF, 0xFFFFFFFF, 0xFFFFFFFF, 0xFFFFFFFF)] == \
+        ["0x408f276d", "0x41c83b0e", "0xa20bc7c6", "0x6d5451fd"]
+    assert [hex(x) for x in orc.philox4x32_10((0x299f31d0 << 32) | 0xa4093822, 0x243f6a88, 0x85a308d3, 0x13198a2e, 0x03707344)] == \
+        ["0xd16cfe09", "0x94fdcceb", "0x5001e420", "0x24126ea1"]
+    lib = cpn.Library()
+    rng = np.random.default_rng(1)
+    for _ in range(200):
+        seed, region, perm = int(rng.integers(0, 2**63)), int(rng.integers(0, 3_000_000)), int(rng.integers(0, 1000))
+        a = cpn.capi.rng_phi0(lib, seed, region, 10)
+        assert np.array_equal(a, orc.gen_phi0s(seed, [region], 10)[0])
+        assert np.all((a[:, 0] >= -5) & (a[:, 0] <= 5) & (a[:, 1] >= -50) & (a[:, 1] <= 50) & (a[:, 2] >= 0) & (a[:, 2] <= 10))
+        assert np.allclose(a * 100, np.rint(a * 100), atol=1e-9)                                    # on the 0.01 grid of gen_ϕ0s
+        h = int(rng.integers(0, 2))
+        assert np.array_equal(cpn.capi.rng_phi0(lib, seed, region, 4, perm, h), np.array([orc.gen_phi0(seed, region, perm, h, s) for s in range(4)]))
+        n = int(rng.integers(2, 130)); n1 = int(rng.integers(1, n))
+        ids = cpn.capi.rng_perm(lib, seed, region, perm, n, n1)
+        assert np.array_equal(ids, orc.gen_perm(seed, region, perm, n, n1))
+        assert len(ids) == n1 and np.all(np.diff(ids) > 0) and ids[0] >= 1 and ids[-1] <= n
+    # uniformity of the subset draw: every read is in sample 1 with probability n1/n
+    hits = np.zeros(12)
+    for i in range(4000):
+        hits[cpn.capi.rng_perm(lib, 5, 0, i, 12, 5) - 1] += 1
+    assert np.all(np.abs(hits / 4000 - 5 / 12) < 0.04)
