@@ -15,7 +15,7 @@ FIT_NONE, FIT_NUMERICAL, FIT_FILTERED = -1, -2, -16        # status words (inclu
 # every exported symbol of include/cpelnano_b200.h (tests check the library exports exactly these)
 SYMBOLS = ["cpn_create", "cpn_destroy", "cpn_last_error", "cpn_version", "cpn_last_device_ms", "cpn_last_launches", "cpn_last_work",
            "cpn_measure_fp64_peak", "cpn_set_seed", "cpn_rng_phi0", "cpn_rng_perm", "cpn_set_profile", "cpn_get_profile", "cpn_analyze_batch", "cpn_analyze_batch_device", "cpn_fit_batch", "cpn_fit_batch_device", "cpn_estep_batch", "cpn_mstep_batch",
-           "cpn_stat_sums_batch", "cpn_nls_reg_info", "cpn_cmd_batch", "cpn_grp_unmat_sweep", "cpn_grp_mat_sweep", "cpn_two_samp_pvals", "cpn_two_samp_null_batch", "cpn_two_samp_test_batch", "cpn_grp_test_batch", "cpn_region_filter",
+           "cpn_stat_sums_batch", "cpn_nls_reg_info", "cpn_cmd_batch", "cpn_grp_unmat_sweep", "cpn_grp_mat_sweep", "cpn_two_samp_pvals", "cpn_two_samp_null_batch", "cpn_two_samp_test_batch", "cpn_grp_test_batch", "cpn_grp_test_batch_device", "cpn_region_filter",
            "cpn_calls_open", "cpn_calls_close", "cpn_calls_open_error", "cpn_calls_error", "cpn_calls_num_lines", "cpn_calls_num_reads", "cpn_calls_num_chr",
            "cpn_calls_chr_name", "cpn_calls_chr_lines", "cpn_calls_read_name", "cpn_calls_count_reads", "cpn_calls_fill",
            "cpn_cpg_scan", "cpn_chr_part", "cpn_grp_info_count", "cpn_grp_info_fill", "cpn_format_f64", "cpn_write_rows", "cpn_write_theta", "cpn_nls_reg_info_batch", "cpn_calls_coverage", "cpn_fasta_open", "cpn_fasta_close", "cpn_fasta_open_error",
@@ -319,6 +319,16 @@ class Library:
                                          C.c_int32(int(exact)), _ptr(T), _ptr(cnt), _ptr(p), _ptr(tcmd))
         self._check(rc, ctx)
         return (T, cnt, p, tcmd) if matched else (T, cnt, p)
+
+    def grp_test_batch_raw(self, R, n1, n2, matched, phi, cpg_off, rho_n, d_n, sub_off, sub_p, sub_q, labelings, P, exact, T, cnt, pval, tcmd,
+                           on_device, device=0):
+        """Pointer-level cpn_grp_test_batch[_device]: ints = raw addresses (pinned host or device), numpy arrays = host; cpg_off,
+        sub_off and labelings are always host numpy arrays."""
+        ctx = self.ctx(device)
+        fn = self.dll.cpn_grp_test_batch_device if on_device else self.dll.cpn_grp_test_batch
+        rc = fn(ctx, C.c_int64(R), C.c_int32(n1), C.c_int32(n2), C.c_int32(int(matched)), _ptr(phi), _ptr(cpg_off), _ptr(rho_n), _ptr(d_n),
+                _ptr(sub_off), _ptr(sub_p), _ptr(sub_q), _ptr(labelings), C.c_int64(P), C.c_int32(int(exact)), _ptr(T), _ptr(cnt), _ptr(pval), _ptr(tcmd))
+        self._check(rc, ctx)
 
     def two_samp_null_batch(self, grp_off, Nl, rho_l, d_l, read_off, lu, lm, perm_off, n1, perm_ids, phi0, n_init, cpg_off, rho_n, d_n,
                             sub_off, sub_p, sub_q, max_em_iters=20, box=(20.0, 150.0, 50.0), mstep_mode=MSTEP_ANALYTIC, device=0):

@@ -248,8 +248,19 @@ struct DevOut {
 // Launch-only entry of the summaries kernel (all pointers on the device); defined in cpn_summaries.cu.
 int cpn_stat_sums_launch(cpn_ctx* ctx, int64_t T, const double* phi, const int64_t* reg_of, const int64_t* ex_off, const int64_t* k_off,
                          const int64_t* cpg_off, const double* rho_n, const double* d_n, const int64_t* sub_off, const int64_t* sub_p,
-                         const int64_t* sub_q, int64_t Nmax, double* logZ, double* ex, double* exx, double* log_g, double* e_log_g1,
-                         double* e_log_g2, double* mml, double* nme);
+                         const int64_t* sub_q, int64_t Nmax, double* logZ, double* ex /*null: not written*/, double* exx, double* log_g,
+                         double* e_log_g1, double* e_log_g2, double* mml, double* nme, double* msum /*[k_off[T]][5] or null*/);
+// Host check: sub-regions of every region ascending, disjoint and at most 32 (what get_nls_reg_info! produces) — the condition
+// for the lane-per-pair CMD kernel.
+bool cpn_subregions_ordered(int64_t R, const int64_t* sub_off, const int64_t* sub_p, const int64_t* sub_q, const int64_t* cpg_off);
+int cpn_subregions_ordered_device(cpn_ctx* ctx, int64_t R, const int64_t* sub_off, const int64_t* sub_p, const int64_t* sub_q, const int64_t* cpg_off,
+                                  bool* ordered);
+// get_stat_sums! of T models + comp_cmd of P pairs of them (device pointers; scratch from the calling thread's arena / pool).
+int cpn_summaries_and_cmd(cpn_ctx* ctx, bool ordered, int64_t T, const double* phi, const int64_t* reg_of, const int64_t* ex_off,
+                          const int64_t* k_off, int64_t sN, int64_t sK, int64_t R, int64_t sumN, const int64_t* cpg_off, const double* rho_n,
+                          const double* d_n, const int64_t* sub_off, const int64_t* sub_p, const int64_t* sub_q, int64_t Nmax, int64_t P,
+                          const int64_t* pair_a, const int64_t* pair_b, const int64_t* cmd_off, double* logZ, double* log_g, double* e_log_g1,
+                          double* e_log_g2, double* mml, double* nme, double* cmd);
 
 // Launch-only entry of the CMD kernel (all pointers on the device); defined in cpn_summaries.cu.
 int cpn_cmd_launch(cpn_ctx* ctx, int64_t P, const int64_t* pair_a, const int64_t* pair_b, const double* phi_tbl, const int64_t* reg_of,

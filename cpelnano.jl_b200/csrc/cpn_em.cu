@@ -1650,7 +1650,7 @@ int fit_impl(cpn_ctx* ctx, bool on_device, int64_t R, const int64_t* grp_off, co
             CPN_CUDA(ctx, s_e1.bind(sa->e_log_g1, sumK, on_device, s)); CPN_CUDA(ctx, s_e2.bind(sa->e_log_g2, sumK, on_device, s));
             CPN_CUDA(ctx, s_mml.bind(sa->mml, sumK, on_device, s)); CPN_CUDA(ctx, s_nme.bind(sa->nme, sumK, on_device, s));
             int rc2 = cpn_stat_sums_launch(ctx, R, o_phi.p, nullptr, i_cpg.p, i_sub.p, i_cpg.p, i_rho.p, i_dn.p, i_sub.p, i_sp.p, i_sq.p, Nmax,
-                                           s_logZ.p, s_ex.p, s_exx.p, s_lg.p, s_e1.p, s_e2.p, s_mml.p, s_nme.p);
+                                           s_logZ.p, s_ex.p, s_exx.p, s_lg.p, s_e1.p, s_e2.p, s_mml.p, s_nme.p, nullptr);
             if (rc2) return rc2;
             CPN_CUDA(ctx, s_logZ.finish(s)); CPN_CUDA(ctx, s_ex.finish(s)); CPN_CUDA(ctx, s_exx.finish(s)); CPN_CUDA(ctx, s_lg.finish(s));
             CPN_CUDA(ctx, s_e1.finish(s)); CPN_CUDA(ctx, s_e2.finish(s)); CPN_CUDA(ctx, s_mml.finish(s)); CPN_CUDA(ctx, s_nme.finish(s));
@@ -1770,7 +1770,7 @@ __global__ void k_two_samp_Tobs(int64_t R, const int64_t* __restrict__ sub_off, 
 static int two_samp_observed(cpn_ctx* ctx, int64_t Rc, const double* phi_s1, const double* phi_s2, const int64_t* po, const int64_t* tn,
                              const int32_t* exact, const int64_t* cp, const int64_t* so, int Kmax, int64_t Nmax, const int64_t* d_cpg,
                              const double* d_rho, const double* d_dn, const int64_t* d_so, const int64_t* d_sp, const int64_t* d_sq,
-                             const double* d_Tnull, double* T_obs, int64_t* cnt, int64_t* n_valid, double* pval) {
+                             const double* d_Tnull, double* T_obs, int64_t* cnt, int64_t* n_valid, double* pval, bool ordered) {
     cudaStream_t s = ctx->stream;
     const int64_t T2 = 2 * Rc, sumN = cp[Rc], sumK = so[Rc];
     std::vector<double> h_phi(3 * T2);
@@ -1787,7 +1787,7 @@ static int two_samp_observed(cpn_ctx* ctx, int64_t Rc, const double* phi_s1, con
         if (exact) h_exact[r] = exact[r];
     }
     h_exo[T2] = 2 * sumN; h_ko[T2] = 2 * sumK;
-    DevBuf<double> d_phi, logZ, ex, exx, lg, e1, e2, mml, nme, cmd, d_T, o_p;
+    DevBuf<double> d_phi, logZ, lg, e1, e2, mml, nme, cmd, d_T, o_p;
     DevBuf<int64_t> d_reg, d_exo, d_ko, d_pa, d_pb, d_po, d_nul, o_cnt, o_nv;
     DevBuf<int32_t> d_exact;
     CpnArenaScope scope(&ctx->stage_arena);
@@ -1795,15 +1795,12 @@ static int two_samp_observed(cpn_ctx* ctx, int64_t Rc, const double* phi_s1, con
     CPN_CUDA(ctx, d_exo.upload(h_exo.data(), T2 + 1, s)); CPN_CUDA(ctx, d_ko.upload(h_ko.data(), T2 + 1, s));
     CPN_CUDA(ctx, d_pa.upload(h_pa.data(), Rc, s)); CPN_CUDA(ctx, d_pb.upload(h_pb.data(), Rc, s));
     CPN_CUDA(ctx, d_po.upload(po, Rc + 1, s)); CPN_CUDA(ctx, d_nul.upload(h_nul.data(), Rc, s)); CPN_CUDA(ctx, d_exact.upload(h_exact.data(), Rc, s));
-    CPN_CUDA(ctx, logZ.alloc(T2, s)); CPN_CUDA(ctx, ex.alloc(2 * sumN, s)); CPN_CUDA(ctx, exx.alloc(2 * sumN - T2, s)); CPN_CUDA(ctx, lg.alloc(8 * sumK, s));
+    CPN_CUDA(ctx, logZ.alloc(T2, s)); CPN_CUDA(ctx, lg.alloc(8 * sumK, s));
     CPN_CUDA(ctx, e1.alloc(2 * sumK, s)); CPN_CUDA(ctx, e2.alloc(2 * sumK, s)); CPN_CUDA(ctx, mml.alloc(2 * sumK, s)); CPN_CUDA(ctx, nme.alloc(2 * sumK, s));
     CPN_CUDA(ctx, cmd.alloc(sumK, s)); CPN_CUDA(ctx, d_T.alloc(3 * sumK, s));
     CPN_CUDA(ctx, o_cnt.alloc(3 * sumK, s)); CPN_CUDA(ctx, o_nv.alloc(3 * sumK, s)); CPN_CUDA(ctx, o_p.alloc(3 * sumK, s));
-    int rc = cpn_stat_sums_launch(ctx, T2, d_phi.p, d_reg.p, d_exo.p, d_ko.p, d_cpg, d_rho, d_dn, d_so, d_sp, d_sq, Nmax, logZ.p, ex.p, exx.p, lg.p,
-                                  e1.p, e2.p, mml.p, nme.p);
-    if (rc) return rc;
-    rc = cpn_cmd_launch(ctx, Rc, d_pa.p, d_pb.p, d_phi.p, d_reg.p, d_exo.p, ex.p, exx.p, d_ko.p, nme.p, d_cpg, d_rho, d_dn, d_so, d_sp, d_sq, Nmax,
-                        d_so, cmd.p);
+    int rc = cpn_summaries_and_cmd(ctx, ordered, T2, d_phi.p, d_reg.p, d_exo.p, d_ko.p, 2 * sumN, 2 * sumK, Rc, sumN, d_cpg, d_rho, d_dn, d_so, d_sp, d_sq,
+                                   Nmax, Rc, d_pa.p, d_pb.p, d_so, logZ.p, lg.p, e1.p, e2.p, mml.p, nme.p, cmd.p);
     if (rc) return rc;
     { KTimer kt(ctx, CPN_K_SWEEP); k_two_samp_Tobs<<<blocks_for(Rc * 32, 256), 256, 0, s>>>(Rc, d_so, mml.p, nme.p, cmd.p, d_T.p); }
     CPN_CUDA(ctx, cudaGetLastError());
@@ -2231,6 +2228,7 @@ static int two_samp_impl(cpn_ctx* ctx, int64_t R, const int64_t* grp_off, const 
                 }
             }
         }
+    const bool ordered = cpn_subregions_ordered(R, sub_off, sub_p, sub_q, cpg_off) && env_int("CPN_CMD_LANE", 1) != 0;
     const int64_t max_views = std::max<int64_t>(2, env_int("CPN_TWO_SAMP_MAX_VIEWS", 1 << 20));
     std::vector<int64_t> bnd{0};
     {
@@ -2283,7 +2281,7 @@ static int two_samp_impl(cpn_ctx* ctx, int64_t R, const int64_t* grp_off, const 
             if (rc) return rc;
             launches += ctx->last_launches;
             DevBuf<int64_t> d_reg, d_exo, d_ko, d_co, d_pa, d_pb, d_cpg, d_so, d_sp, d_sq;
-            DevBuf<double> d_rho, d_dn, d_phi, d_Q, logZ, ex, exx, lg, e1, e2, mml, nme, cmd, T;
+            DevBuf<double> d_rho, d_dn, d_phi, d_Q, logZ, lg, e1, e2, mml, nme, cmd, T;
             DevBuf<int32_t> d_stat, d_pid;
             DevBuf<TsRegion> d_regs;
             {
@@ -2300,7 +2298,7 @@ static int two_samp_impl(cpn_ctx* ctx, int64_t R, const int64_t* grp_off, const 
                 CPN_CUDA(ctx, d_sp.upload(sub_p + k0, sumK, s)); CPN_CUDA(ctx, d_sq.upload(sub_q + k0, sumK, s));
                 CPN_CUDA(ctx, d_rho.upload(rho_n + n0, sumN, s)); CPN_CUDA(ctx, d_dn.upload(d_n + (n0 - r0), sumN - Rc, s));
                 CPN_CUDA(ctx, d_phi.alloc(3 * V, s)); CPN_CUDA(ctx, d_Q.alloc(V, s)); CPN_CUDA(ctx, d_stat.alloc(V, s));
-                CPN_CUDA(ctx, logZ.alloc(V, s)); CPN_CUDA(ctx, ex.alloc(sN, s)); CPN_CUDA(ctx, exx.alloc(sN - V, s)); CPN_CUDA(ctx, lg.alloc(4 * sK, s));
+                CPN_CUDA(ctx, logZ.alloc(V, s)); CPN_CUDA(ctx, lg.alloc(4 * sK, s));
                 CPN_CUDA(ctx, e1.alloc(sK, s)); CPN_CUDA(ctx, e2.alloc(sK, s)); CPN_CUDA(ctx, mml.alloc(sK, s)); CPN_CUDA(ctx, nme.alloc(sK, s));
                 CPN_CUDA(ctx, cmd.alloc(sC, s)); CPN_CUDA(ctx, T.alloc(3 * sC, s));
                 // the views: read-index rows, descriptors, RNG keys and the index tables of the summaries, built on the device
@@ -2320,12 +2318,12 @@ static int two_samp_impl(cpn_ctx* ctx, int64_t R, const int64_t* grp_off, const 
             ctx->last_launches = 0;
             for (int k = 0; k < 4; ++k) work_acc[k] += ctx->last_work[k];
             // per-CpG summaries of every refit, CMD of the two halves of every permutation, then the three statistics
-            rc = cpn_stat_sums_launch(ctx, V, d_phi.p, d_reg.p, d_exo.p, d_ko.p, d_cpg.p, d_rho.p, d_dn.p, d_so.p, d_sp.p, d_sq.p, Nmax, logZ.p,
-                                      ex.p, exx.p, lg.p, e1.p, e2.p, mml.p, nme.p);
-            if (rc) return rc;
-            rc = cpn_cmd_launch(ctx, Pt, d_pa.p, d_pb.p, d_phi.p, d_reg.p, d_exo.p, ex.p, exx.p, d_ko.p, nme.p, d_cpg.p, d_rho.p, d_dn.p, d_so.p,
-                                d_sp.p, d_sq.p, Nmax, d_co.p, cmd.p);
-            if (rc) return rc;
+            {
+                CpnArenaScope scope(&ctx->stage_arena);
+                rc = cpn_summaries_and_cmd(ctx, ordered, V, d_phi.p, d_reg.p, d_exo.p, d_ko.p, sN, sK, Rc, sumN, d_cpg.p, d_rho.p, d_dn.p, d_so.p, d_sp.p,
+                                           d_sq.p, Nmax, Pt, d_pa.p, d_pb.p, d_co.p, logZ.p, lg.p, e1.p, e2.p, mml.p, nme.p, cmd.p);
+                if (rc) return rc;
+            }
             { KTimer kt(ctx, CPN_K_SWEEP);
               k_two_samp_T<<<blocks_for(Pt * 32, 256), 256, 0, s>>>(Pt, d_ko.p, d_co.p, mml.p, nme.p, cmd.p, d_stat.p, T.p); }
             CPN_CUDA(ctx, cudaGetLastError());
@@ -2334,7 +2332,7 @@ static int two_samp_impl(cpn_ctx* ctx, int64_t R, const int64_t* grp_off, const 
             if (observed) {
                 rc = two_samp_observed(ctx, Rc, phi_s1 + 3 * r0, phi_s2 + 3 * r0, po.data(), tn.data() + r0, exact ? exact + r0 : nullptr, cp.data(),
                                        so.data(), (int)Kmax, Nmax, d_cpg.p, d_rho.p, d_dn.p, d_so.p, d_sp.p, d_sq.p, T.p, T_obs + 3 * k0, cnt + 3 * k0,
-                                       n_valid + 3 * k0, pval + 3 * k0);
+                                       n_valid + 3 * k0, pval + 3 * k0, ordered);
                 if (rc) return rc;
             }
             CPN_CUDA(ctx, cpn_wait_stream(ctx, s));
@@ -2351,7 +2349,7 @@ static int two_samp_impl(cpn_ctx* ctx, int64_t R, const int64_t* grp_off, const 
             ctx->last_launches = 0;
             rc = two_samp_observed(ctx, Rc, phi_s1 + 3 * r0, phi_s2 + 3 * r0, po.data(), tn.data() + r0, exact ? exact + r0 : nullptr, cp.data(),
                                    so.data(), (int)Kmax, Nmax, d_cpg.p, d_rho.p, d_dn.p, d_so.p, d_sp.p, d_sq.p, nullptr, T_obs + 3 * k0, cnt + 3 * k0,
-                                   n_valid + 3 * k0, pval + 3 * k0);
+                                   n_valid + 3 * k0, pval + 3 * k0, ordered);
             if (rc) return rc;
             CPN_CUDA(ctx, cpn_wait_stream(ctx, s));
             launches += ctx->last_launches;

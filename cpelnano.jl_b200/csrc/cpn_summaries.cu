@@ -16,6 +16,7 @@
 // so the O(N) pass is overflow-free and replaces the reference's O(N²) log-domain re-multiplication.
 // Every array a region needs is staged in shared memory; global reads/writes are lane-contiguous.
 #include <cmath>
+#include <cstdlib>
 
 #include "cpn_common.cuh"
 
@@ -24,6 +25,7 @@ namespace {
 constexpr int S_WARPS = 4;
 constexpr int S_ARR = 11;                      // doubles of shared memory per site
 constexpr double LN2 = 0.6931471805599453;
+constexpr int CMD_MAXK = 32;                  // most sub-regions per region the lane-per-pair CMD kernel keeps in local memory
 
 struct Mat2e { double m00, m01, m10, m11; int e; };   // value = m · 2^e, all entries ≥ 0
 
@@ -193,6 +195,18 @@ __device__ __forceinline__ void log_g_at(const ChainSmem& cs, int N, int p, int 
     else { lg[2] = log(cs.B0[q - 1]) + cs.LSb[q - 1]; lg[3] = log(cs.B1[q - 1]) + cs.LSb[q - 1]; }
 }
 
+// What comp_crs_ent (statistical_summaries.jl:427-459) needs from model i for sub-region [p, q] (1-based): the sums
+// Σ E_i[X_n], Σ ρ_n E_i[X_n], Σ E_i[X_n X_n+1]/d_n — so that α̃·E_i[X] + β̃·E_i[XX] = ã·S0 + b̃·S1 + c̃·S2 for any mixture
+// parameters ϕ̃ — and the boundary marginals E_i[X_p], E_i[X_q].  Pair-independent: computed once per model, shared by every
+// pair the model is in (11 in a 6-vs-6 comparison).
+__device__ __forceinline__ void model_sums(const double* ex, const double* exx, const double* __restrict__ rho, const double* __restrict__ dn,
+                                           int p, int q, double ms[5]) {
+    double s0 = 0.0, s1 = 0.0, s2 = 0.0;
+    for (int n = p; n <= q; ++n) { const double e = ex[n - 1]; s0 += e; s1 = fma(rho[n - 1], e, s1); }
+    for (int n = p; n <= q - 1; ++n) s2 += exx[n - 1] / dn[n - 1];
+    ms[0] = s0; ms[1] = s1; ms[2] = s2; ms[3] = ex[p - 1]; ms[4] = ex[q - 1];
+}
+
 __global__ void __launch_bounds__(S_WARPS * 32) k_stat_sums(int64_t T, int stride, const double* __restrict__ phi,
                                                              const int64_t* __restrict__ reg_of, const int64_t* __restrict__ ex_off,
                                                              const int64_t* __restrict__ k_off,
@@ -202,7 +216,8 @@ __global__ void __launch_bounds__(S_WARPS * 32) k_stat_sums(int64_t T, int strid
                                                              double* __restrict__ logZ_out, double* __restrict__ ex_out,
                                                              double* __restrict__ exx_out, double* __restrict__ log_g_out,
                                                              double* __restrict__ elg1_out, double* __restrict__ elg2_out,
-                                                             double* __restrict__ mml_out, double* __restrict__ nme_out) {
+                                                             double* __restrict__ mml_out, double* __restrict__ nme_out,
+                                                             double* __restrict__ msum_out /*[k_off[T]][5] or null*/) {
     extern __shared__ double smem[];
     int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
     int64_t tm = blockIdx.x * (int64_t)S_WARPS + w;
@@ -216,10 +231,12 @@ __global__ void __launch_bounds__(S_WARPS * 32) k_stat_sums(int64_t T, int strid
     double a = phi[3 * tm], b = phi[3 * tm + 1], c = phi[3 * tm + 2];
     double logZ = build_chain(cs, N, lane, rho, dn, a, b, c);
     if (lane == 0) logZ_out[tm] = logZ;
-    int64_t e0 = ex_off[tm];
-    for (int n = lane; n < N; n += 32) {
-        ex_out[e0 + n] = cs.ex[n];
-        if (n + 1 < N) exx_out[e0 - tm + n] = cs.exx[n];
+    if (ex_out) {                                        // the fused comparison paths keep E[X], E[XX] on chip (msum is all they need)
+        int64_t e0 = ex_off[tm];
+        for (int n = lane; n < N; n += 32) {
+            ex_out[e0 + n] = cs.ex[n];
+            if (n + 1 < N) exx_out[e0 - tm + n] = cs.exx[n];
+        }
     }
     int64_t ks = sub_off[r];
     int K = (int)(sub_off[r + 1] - ks);
@@ -228,7 +245,9 @@ __global__ void __launch_bounds__(S_WARPS * 32) k_stat_sums(int64_t T, int strid
         int p = (int)sub_p[ks + k], q = (int)sub_q[ks + k];
         double lg[4] = {cpn_nan(), cpn_nan(), cpn_nan(), cpn_nan()};
         double e1 = cpn_nan(), e2 = cpn_nan(), mml = cpn_nan(), nme = cpn_nan();
+        double ms[5] = {0.0, 0.0, 0.0, 0.0, 0.0};
         if (p != 0 && q != 0) {
+            if (msum_out) model_sums(cs.ex, cs.exx, rho, dn, p, q, ms);
             log_g_at(cs, N, p, q, lg);
             double pp_p = 0.5 * (1.0 + cs.ex[p - 1]), pp_q = 0.5 * (1.0 + cs.ex[q - 1]);
             e1 = (p == 1) ? 0.0 : fma(pp_p, lg[1], (1.0 - pp_p) * lg[0]);        // E[log g1(X_p)]  (:212-236)
@@ -249,6 +268,10 @@ __global__ void __launch_bounds__(S_WARPS * 32) k_stat_sums(int64_t T, int strid
         log_g_out[4 * (k0 + k) + 0] = lg[0]; log_g_out[4 * (k0 + k) + 1] = lg[1];
         log_g_out[4 * (k0 + k) + 2] = lg[2]; log_g_out[4 * (k0 + k) + 3] = lg[3];
         elg1_out[k0 + k] = e1; elg2_out[k0 + k] = e2; mml_out[k0 + k] = mml; nme_out[k0 + k] = nme;
+        if (msum_out) {
+#pragma unroll
+            for (int j = 0; j < 5; ++j) msum_out[5 * (k0 + k) + j] = ms[j];
+        }
     }
 }
 
@@ -313,6 +336,169 @@ __global__ void __launch_bounds__(S_WARPS * 32) k_cmd(int64_t P, int stride, con
     }
 }
 
+
+// model_sums for models whose E[X], E[XX] tables came from the caller (cpn_cmd_batch): thread per (model, sub-region).
+__global__ void k_msum_from_ex(int64_t T, const int64_t* __restrict__ reg_of, const int64_t* __restrict__ ex_off, const double* __restrict__ ex_tbl,
+                               const double* __restrict__ exx_tbl, const int64_t* __restrict__ k_off, const int64_t* __restrict__ cpg_off,
+                               const double* __restrict__ rho_n, const double* __restrict__ d_n, const int64_t* __restrict__ sub_off,
+                               const int64_t* __restrict__ sub_p, const int64_t* __restrict__ sub_q, double* __restrict__ msum) {
+    int64_t t = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5;
+    int lane = threadIdx.x & 31;
+    if (t >= T) return;
+    const int64_t r = reg_of[t], n0 = cpg_off[r], ks = sub_off[r];
+    const int K = (int)(sub_off[r + 1] - ks);
+    for (int k = lane; k < K; k += 32) {
+        const int p = (int)sub_p[ks + k], q = (int)sub_q[ks + k];
+        double ms[5] = {0.0, 0.0, 0.0, 0.0, 0.0};
+        if (p != 0 && q != 0) model_sums(ex_tbl + ex_off[t], exx_tbl + (ex_off[t] - t), rho_n + n0, d_n + (n0 - r), p, q, ms);
+#pragma unroll
+        for (int j = 0; j < 5; ++j) msum[5 * (k_off[t] + k) + j] = ms[j];
+    }
+}
+
+__global__ void k_check_ordered(int64_t R, const int64_t* __restrict__ sub_off, const int64_t* __restrict__ sub_p, const int64_t* __restrict__ sub_q,
+                                const int64_t* __restrict__ cpg_off, int* __restrict__ bad) {
+    int64_t r = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (r >= R) return;
+    bool ok = sub_off[r + 1] - sub_off[r] <= CMD_MAXK;
+    int64_t last = 0;
+    const int64_t N = cpg_off[r + 1] - cpg_off[r];
+    for (int64_t k = sub_off[r]; k < sub_off[r + 1]; ++k) {
+        const int64_t p = sub_p[k], q = sub_q[k];
+        if (p == 0 || q == 0) continue;
+        if (p <= last || q < p || q > N) ok = false;
+        last = q;
+    }
+    if (!ok) *bad = 1;
+}
+
+// (ρ_n, 1/d_{n-1}) per CpG site, 16 bytes: what a chain step of k_cmd_lane loads (one broadcast LDG.128 per warp and site).
+__global__ void k_region_tables(int64_t R, const int64_t* __restrict__ cpg_off, const double* __restrict__ rho_n, const double* __restrict__ d_n,
+                                double2* __restrict__ rd) {
+    int64_t r = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5;
+    int lane = threadIdx.x & 31;
+    if (r >= R) return;
+    const int64_t n0 = cpg_off[r];
+    const int N = (int)(cpg_off[r + 1] - n0);
+    for (int n = lane; n < N; n += 32) rd[n0 + n] = make_double2(rho_n[n0 + n], n > 0 ? 1.0 / d_n[n0 - r + n - 1] : 0.0);
+}
+
+// comp_cmd (statistical_summaries.jl:512-570), ONE LANE PER PAIR.  The warp-per-pair kernel above spends most of its time in
+// shuffle scans and shared-memory staging for chains of ≈ 60 sites; here a lane walks the mixture chain (ϕ̃ = (ϕa+ϕb)/2, :517-527)
+// once, left to right, carrying the forward message F and the 2×2 product G of the transfer matrices since the last
+// sub-region end.  That is all comp_crs_ent (:427-459) needs when the sub-regions are ordered and disjoint, as
+// get_nls_reg_info! makes them:  log g̃1(x_p) comes from F just before site p; log g̃2(x_q) = log[(G_{k+1}⋯G_last·1)(x_q)] from a
+// backward pass over the ≤ K stored products; α̃·E_i[X] + β̃·E_i[XX] = ã·S0 + b̃·S1 + c̃·S2 with the per-model sums of model_sums.
+// Messages are linear-space doubles relative to the larger potential, rescaled by exact powers of two.
+__global__ void __launch_bounds__(128) k_cmd_lane(int64_t P, const int64_t* __restrict__ pair_a, const int64_t* __restrict__ pair_b,
+                                                  const double* __restrict__ phi_tbl, const int64_t* __restrict__ reg_of,
+                                                  const int64_t* __restrict__ k_off, const double* __restrict__ msum,
+                                                  const double* __restrict__ nme_tbl, const int64_t* __restrict__ cpg_off,
+                                                  const double2* __restrict__ rd, const int64_t* __restrict__ sub_off,
+                                                  const int64_t* __restrict__ sub_p, const int64_t* __restrict__ sub_q,
+                                                  const int64_t* __restrict__ cmd_off, double* __restrict__ cmd) {
+    const int64_t pi = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (pi >= P) return;
+    const int64_t ma = pair_a[pi], mb = pair_b[pi], r = reg_of[ma];
+    const int64_t n0 = cpg_off[r];
+    const int N = (int)(cpg_off[r + 1] - n0);
+    const double2* rdr = rd + n0;
+    const double a = 0.5 * (phi_tbl[3 * ma] + phi_tbl[3 * mb]), b = 0.5 * (phi_tbl[3 * ma + 1] + phi_tbl[3 * mb + 1]),
+                 c = 0.5 * (phi_tbl[3 * ma + 2] + phi_tbl[3 * mb + 2]);
+    const bool bpos = c >= 0.0;
+    const double cabs2 = -2.0 * fabs(c);
+    const int64_t ks = sub_off[r];
+    const int K = (int)(sub_off[r + 1] - ks);
+    // per sub-region: log g̃1(∓) at p, the product G since the previous sub-region end (4 entries, exponent, offset)
+    double lg1m[CMD_MAXK], lg1p[CMD_MAXK], g00[CMD_MAXK], g01[CMD_MAXK], g10[CMD_MAXK], g11[CMD_MAXK], goff[CMD_MAXK];
+    int gexp[CMD_MAXK];
+    int k = 0;                                            // next non-empty sub-region whose p or q lies ahead
+    while (k < K && (sub_p[ks + k] == 0 || sub_q[ks + k] == 0)) ++k;
+    int pk = k < K ? (int)sub_p[ks + k] : 0, qk = k < K ? (int)sub_q[ks + k] : 0;
+    double f0 = 1.0, f1 = 1.0, offF = 0.0;               // forward message through site n-1 (incl. φ), value = f·2^eF·e^offF
+    int eF = 0;
+    double G00 = 1.0, G01 = 0.0, G10 = 0.0, G11 = 1.0, offG = 0.0;
+    int eG = 0;
+    for (int n = 0; n < N; ++n) {
+        const double2 x = __ldg(rdr + n);
+        const double alpha = fma(b, x.x, a);
+        const double absa = fabs(alpha);
+        const double e = cpn_exp_neg(-2.0 * absa);
+        const bool pos = alpha >= 0.0;
+        const double wm = pos ? e : 1.0, wp = pos ? 1.0 : e;
+        double a0, a1, absb = 0.0;
+        if (n == 0) { a0 = 1.0; a1 = 1.0; }
+        else {
+            const double bt = cabs2 * x.y;                  // -2|β|, β = c/d_{n-1}
+            absb = -0.5 * bt;
+            const double t = cpn_exp_neg(bt);
+            const double same = bpos ? 1.0 : t, diff = bpos ? t : 1.0;
+            a0 = fma(diff, f1, same * f0); a1 = fma(diff, f0, same * f1);
+            // G ← G·Ψ
+            const double h00 = fma(G01, diff, G00 * same), h01 = fma(G01, same, G00 * diff);
+            const double h10 = fma(G11, diff, G10 * same), h11 = fma(G11, same, G10 * diff);
+            G00 = h00; G01 = h01; G10 = h10; G11 = h11;
+        }
+        offF += absb;                                       // the coupling into n belongs to A_n (everything left of n)
+        if (n + 1 == pk) {                                  // comp_log_g_p(p, ∓1) :94-122; 0 at the chain start
+            const double ls = (double)eF * LN2 + offF;
+            lg1m[k] = (n == 0) ? 0.0 : log(a0) + ls;
+            lg1p[k] = (n == 0) ? 0.0 : log(a1) + ls;
+        }
+        offF += absa; offG += absb + absa;
+        f0 = a0 * wm; f1 = a1 * wp;
+        if (n == 0) { G00 = wm; G11 = wp; }                 // T_0 = diag(φ_0)
+        else { G00 *= wm; G10 *= wm; G01 *= wp; G11 *= wp; }
+        if (n & 1) {                                        // rescale every second site (entries ≤ 1 per step, ≥ e^-2|·| ... safe)
+            int de;
+            double sc = cpn_inv_pow2_of(f0 + f1, &de);
+            f0 *= sc; f1 *= sc; eF += de;
+            sc = cpn_inv_pow2_of((G00 + G01) + (G10 + G11), &de);
+            G00 *= sc; G01 *= sc; G10 *= sc; G11 *= sc; eG += de;
+        }
+        if (n + 1 == qk) {                                  // close the segment that ends at q_k
+            g00[k] = G00; g01[k] = G01; g10[k] = G10; g11[k] = G11; gexp[k] = eG; goff[k] = offG;
+            G00 = 1.0; G01 = 0.0; G10 = 0.0; G11 = 1.0; eG = 0; offG = 0.0;
+            ++k;
+            while (k < K && (sub_p[ks + k] == 0 || sub_q[ks + k] == 0)) ++k;
+            pk = k < K ? (int)sub_p[ks + k] : 0; qk = k < K ? (int)sub_q[ks + k] : 0;
+        }
+    }
+    const double logZm = log(f0 + f1) + (double)eF * LN2 + offF;
+    // backward over the sub-regions: B = (product of everything right of q_k)·1, starting from the tail after the last q
+    double b0 = G00 + G01, b1 = G10 + G11, offB = offG;
+    int eB = eG;
+    const double* msa = msum + 5 * k_off[ma];
+    const double* msb = msum + 5 * k_off[mb];
+    const double* nmea = nme_tbl + k_off[ma];
+    const double* nmeb = nme_tbl + k_off[mb];
+    double* out = cmd + cmd_off[pi];
+    for (int kk = K - 1; kk >= 0; --kk) {
+        const int p = (int)sub_p[ks + kk], q = (int)sub_q[ks + kk];
+        if (p == 0 || q == 0) { out[kk] = cpn_nan(); continue; }
+        const double lsb = (double)eB * LN2 + offB;
+        const double lg2m = (q == N) ? 0.0 : log(b0) + lsb, lg2p = (q == N) ? 0.0 : log(b1) + lsb;   // comp_log_g_q :133-161
+        double ce[2];
+#pragma unroll
+        for (int i = 0; i < 2; ++i) {
+            const double* ms = (i ? msb : msa) + 5 * kk;
+            const double pp_p = 0.5 * (1.0 + ms[3]), pp_q = 0.5 * (1.0 + ms[4]);
+            const double e1 = (p == 1) ? 0.0 : fma(pp_p, lg1p[kk], (1.0 - pp_p) * lg1m[kk]);       // E_i[log g̃1(X_p)] :248-275
+            const double e2 = (q == N) ? 0.0 : fma(pp_q, lg2p, (1.0 - pp_q) * lg2m);             // E_i[log g̃2(X_q)] :320-347
+            const double dot1 = fma(b, ms[1], a * ms[0]), dot2 = c * ms[2];
+            ce[i] = logZm - dot1 - e1 - e2 - dot2;                                                  // comp_crs_ent :448-449
+        }
+        const double len = (double)(q - p + 1);
+        const double ent1 = nmea[kk] * len * LN2, ent2 = nmeb[kk] * len * LN2;                    // :554-555
+        out[kk] = (ce[0] == 0.0 && ce[1] == 0.0) ? cpn_nan() : 1.0 - (ent1 + ent2) / (ce[0] + ce[1]);   // :560-563
+        // B ← G_kk·B: everything right of q_{kk-1}
+        const double c0 = fma(g01[kk], b1, g00[kk] * b0), c1 = fma(g11[kk], b1, g10[kk] * b0);
+        int de;
+        const double sc = cpn_inv_pow2_of(c0 + c1, &de);
+        b0 = c0 * sc; b1 = c1 * sc; eB += gexp[kk] + de; offB += goff[kk];
+    }
+}
+
 inline unsigned blocks_for(int64_t n, int per_block) { return (unsigned)((n + per_block - 1) / per_block); }
 
 }  // namespace
@@ -320,7 +506,7 @@ inline unsigned blocks_for(int64_t n, int per_block) { return (unsigned)((n + pe
 int cpn_stat_sums_launch(cpn_ctx* ctx, int64_t T, const double* phi, const int64_t* reg_of, const int64_t* ex_off, const int64_t* k_off,
                          const int64_t* cpg_off, const double* rho_n, const double* d_n, const int64_t* sub_off, const int64_t* sub_p,
                          const int64_t* sub_q, int64_t Nmax, double* logZ, double* ex, double* exx, double* log_g, double* e_log_g1,
-                         double* e_log_g2, double* mml, double* nme) {
+                         double* e_log_g2, double* mml, double* nme, double* msum) {
     int stride = (int)((Nmax + 1) | 1);                              // odd stride: fewer shared-memory bank conflicts
     size_t smem = (size_t)S_WARPS * S_ARR * stride * sizeof(double);
     CPN_ARG(ctx, smem <= 200 * 1024, "region with too many CpG sites for the shared-memory staging (N > ~500)");
@@ -328,10 +514,82 @@ int cpn_stat_sums_launch(cpn_ctx* ctx, int64_t T, const double* phi, const int64
     {
         KTimer kt(ctx, CPN_K_STATSUM);
         k_stat_sums<<<blocks_for(T, S_WARPS), S_WARPS * 32, smem, ctx->stream>>>(T, stride, phi, reg_of, ex_off, k_off, cpg_off, rho_n, d_n, sub_off,
-                                                                                  sub_p, sub_q, logZ, ex, exx, log_g, e_log_g1, e_log_g2, mml, nme);
+                                                                                  sub_p, sub_q, logZ, ex, exx, log_g, e_log_g1, e_log_g2, mml, nme, msum);
     }
     CPN_CUDA(ctx, cudaGetLastError());
     return CPN_OK;
+}
+
+bool cpn_subregions_ordered(int64_t R, const int64_t* sub_off, const int64_t* sub_p, const int64_t* sub_q, const int64_t* cpg_off) {
+    for (int64_t r = 0; r < R; ++r) {
+        if (sub_off[r + 1] - sub_off[r] > CMD_MAXK) return false;
+        int64_t last = 0;
+        const int64_t N = cpg_off[r + 1] - cpg_off[r];
+        for (int64_t k = sub_off[r]; k < sub_off[r + 1]; ++k) {
+            const int64_t p = sub_p[k], q = sub_q[k];
+            if (p == 0 || q == 0) continue;
+            if (p <= last || q < p || q > N) return false;
+            last = q;
+        }
+    }
+    return true;
+}
+
+// The same check with the tables on the device (one flag comes back).
+int cpn_subregions_ordered_device(cpn_ctx* ctx, int64_t R, const int64_t* sub_off, const int64_t* sub_p, const int64_t* sub_q, const int64_t* cpg_off,
+                                  bool* ordered) {
+    DevBuf<int> flag;
+    CPN_CUDA(ctx, flag.alloc(1, ctx->stream));
+    CPN_CUDA(ctx, cudaMemsetAsync(flag.p, 0, sizeof(int), ctx->stream));
+    { KTimer kt(ctx, CPN_K_PREP); k_check_ordered<<<blocks_for(R, 256), 256, 0, ctx->stream>>>(R, sub_off, sub_p, sub_q, cpg_off, flag.p); }
+    int h = 1;
+    CPN_CUDA(ctx, cudaMemcpyAsync(&h, flag.p, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+    CPN_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    *ordered = h == 0;
+    return CPN_OK;
+}
+
+int cpn_cmd_lane_launch(cpn_ctx* ctx, int64_t P, const int64_t* pair_a, const int64_t* pair_b, const double* phi_tbl, const int64_t* reg_of,
+                        const int64_t* k_off, const double* msum, const double* nme_tbl, int64_t R, const int64_t* cpg_off, const double* rho_n,
+                        const double* d_n, double2* rd_scratch /*[sumN]*/, const int64_t* sub_off, const int64_t* sub_p, const int64_t* sub_q,
+                        const int64_t* cmd_off, double* cmd) {
+    { KTimer kt(ctx, CPN_K_PREP);
+      k_region_tables<<<blocks_for(R * 32, 256), 256, 0, ctx->stream>>>(R, cpg_off, rho_n, d_n, rd_scratch); }
+    { KTimer kt(ctx, CPN_K_CMD);
+      k_cmd_lane<<<blocks_for(P, 128), 128, 0, ctx->stream>>>(P, pair_a, pair_b, phi_tbl, reg_of, k_off, msum, nme_tbl, cpg_off, rd_scratch, sub_off,
+                                                              sub_p, sub_q, cmd_off, cmd); }
+    CPN_CUDA(ctx, cudaGetLastError());
+    return CPN_OK;
+}
+
+// get_stat_sums! of T models followed by comp_cmd of P pairs of them, everything on the device.  With ordered sub-regions (the
+// get_nls_reg_info! case) the lane-per-pair kernel runs and E[X], E[XX] are never written to memory; otherwise the general
+// warp-per-pair kernel reads them back from a scratch table.
+int cpn_summaries_and_cmd(cpn_ctx* ctx, bool ordered, int64_t T, const double* phi, const int64_t* reg_of, const int64_t* ex_off,
+                          const int64_t* k_off, int64_t sN /*ex_off[T]*/, int64_t sK /*k_off[T]*/, int64_t R, int64_t sumN, const int64_t* cpg_off,
+                          const double* rho_n, const double* d_n, const int64_t* sub_off, const int64_t* sub_p, const int64_t* sub_q, int64_t Nmax,
+                          int64_t P, const int64_t* pair_a, const int64_t* pair_b, const int64_t* cmd_off, double* logZ, double* log_g,
+                          double* e_log_g1, double* e_log_g2, double* mml, double* nme, double* cmd) {
+    cudaStream_t s = ctx->stream;
+    if (ordered) {
+        DevBuf<double> msum;
+        DevBuf<double2> rd;
+        CPN_CUDA(ctx, msum.alloc(5 * sK, s));
+        CPN_CUDA(ctx, rd.alloc(sumN, s));
+        int rc = cpn_stat_sums_launch(ctx, T, phi, reg_of, ex_off, k_off, cpg_off, rho_n, d_n, sub_off, sub_p, sub_q, Nmax, logZ, nullptr, nullptr, log_g,
+                                      e_log_g1, e_log_g2, mml, nme, msum.p);
+        if (rc) return rc;
+        return cpn_cmd_lane_launch(ctx, P, pair_a, pair_b, phi, reg_of, k_off, msum.p, nme, R, cpg_off, rho_n, d_n, rd.p, sub_off, sub_p, sub_q, cmd_off,
+                                   cmd);
+    }
+    DevBuf<double> ex, exx;
+    CPN_CUDA(ctx, ex.alloc(sN, s));
+    CPN_CUDA(ctx, exx.alloc(sN - T, s));
+    int rc = cpn_stat_sums_launch(ctx, T, phi, reg_of, ex_off, k_off, cpg_off, rho_n, d_n, sub_off, sub_p, sub_q, Nmax, logZ, ex.p, exx.p, log_g, e_log_g1,
+                                  e_log_g2, mml, nme, nullptr);
+    if (rc) return rc;
+    return cpn_cmd_launch(ctx, P, pair_a, pair_b, phi, reg_of, ex_off, ex.p, exx.p, k_off, nme, cpg_off, rho_n, d_n, sub_off, sub_p, sub_q, Nmax, cmd_off,
+                          cmd);
 }
 
 int cpn_cmd_launch(cpn_ctx* ctx, int64_t P, const int64_t* pair_a, const int64_t* pair_b, const double* phi_tbl, const int64_t* reg_of,
@@ -395,7 +653,7 @@ int cpn_stat_sums_batch(cpn_ctx* ctx, int64_t T, const double* phi, const int64_
         CPN_CUDA(ctx, o_mml.alloc(outK, s)); CPN_CUDA(ctx, o_nme.alloc(outK, s));
         int rc = cpn_stat_sums_launch(ctx, T, d_phi.p, reg_of ? d_reg.p : nullptr, reg_of ? d_exo.p : d_cpg.p, reg_of ? d_ko.p : d_so.p, d_cpg.p,
                                       d_rho.p, d_dn.p, d_so.p, d_sp.p, d_sq.p, Nmax, o_logZ.p, o_ex.p, o_exx.p, o_lg.p, o_e1.p, o_e2.p, o_mml.p,
-                                      o_nme.p);
+                                      o_nme.p, nullptr);
         if (rc) return rc;
         CPN_CUDA(ctx, o_logZ.download(logZ, T, s)); CPN_CUDA(ctx, o_ex.download(ex, outN, s)); CPN_CUDA(ctx, o_exx.download(exx, outN - T, s));
         CPN_CUDA(ctx, o_lg.download(log_g, 4 * outK, s)); CPN_CUDA(ctx, o_e1.download(e_log_g1, outK, s));
@@ -443,9 +701,24 @@ int cpn_cmd_batch(cpn_ctx* ctx, int64_t P, const int64_t* pair_a, const int64_t*
         CPN_CUDA(ctx, d_cpg.upload(cpg_off, R + 1, s)); CPN_CUDA(ctx, d_rho.upload(rho_n, sumN, s)); CPN_CUDA(ctx, d_dn.upload(d_n, sumN - R, s));
         CPN_CUDA(ctx, d_so.upload(sub_off, R + 1, s)); CPN_CUDA(ctx, d_sp.upload(sub_p, sumK, s)); CPN_CUDA(ctx, d_sq.upload(sub_q, sumK, s));
         CPN_CUDA(ctx, d_co.upload(cmd_off, P + 1, s)); CPN_CUDA(ctx, o_cmd.alloc(cmd_off[P], s));
-        { KTimer kt(ctx, CPN_K_CMD);
-          k_cmd<<<blocks_for(P, S_WARPS), S_WARPS * 32, smem, s>>>(P, stride, d_pa.p, d_pb.p, d_phi.p, d_reg.p, d_exo.p, d_ex.p, d_exx.p, d_nmo.p,
-                                                                    d_nme.p, d_cpg.p, d_rho.p, d_dn.p, d_so.p, d_sp.p, d_sq.p, d_co.p, o_cmd.p); }
+        const char* e_lane = getenv("CPN_CMD_LANE");
+        if (!(e_lane && atoi(e_lane) == 0) && cpn_subregions_ordered(R, sub_off, sub_p, sub_q, cpg_off)) {
+            // per-model sums from the caller's E[X], E[XX] tables (the arithmetic cpn_stat_sums_launch uses when it produces them
+            // itself, so the staged and the fused routes agree bit for bit), then one lane per pair
+            DevBuf<double> msum;
+            DevBuf<double2> rd;
+            CPN_CUDA(ctx, msum.alloc(5 * nme_off[T], s)); CPN_CUDA(ctx, rd.alloc(sumN, s));
+            { KTimer kt(ctx, CPN_K_PREP);
+              k_msum_from_ex<<<blocks_for(T * 32, 256), 256, 0, s>>>(T, d_reg.p, d_exo.p, d_ex.p, d_exx.p, d_nmo.p, d_cpg.p, d_rho.p, d_dn.p, d_so.p,
+                                                                     d_sp.p, d_sq.p, msum.p); }
+            int rc = cpn_cmd_lane_launch(ctx, P, d_pa.p, d_pb.p, d_phi.p, d_reg.p, d_nmo.p, msum.p, d_nme.p, R, d_cpg.p, d_rho.p, d_dn.p, rd.p, d_so.p,
+                                         d_sp.p, d_sq.p, d_co.p, o_cmd.p);
+            if (rc) return rc;
+        } else {
+            KTimer kt(ctx, CPN_K_CMD);
+            k_cmd<<<blocks_for(P, S_WARPS), S_WARPS * 32, smem, s>>>(P, stride, d_pa.p, d_pb.p, d_phi.p, d_reg.p, d_exo.p, d_ex.p, d_exx.p, d_nmo.p,
+                                                                      d_nme.p, d_cpg.p, d_rho.p, d_dn.p, d_so.p, d_sp.p, d_sq.p, d_co.p, o_cmd.p);
+        }
         CPN_CUDA(ctx, cudaGetLastError());
         CPN_CUDA(ctx, o_cmd.download(cmd, cmd_off[P], s));
         CPN_CUDA(ctx, cudaEventRecord(ctx->ev1, s));

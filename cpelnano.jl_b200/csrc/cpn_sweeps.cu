@@ -432,10 +432,13 @@ int cpn_two_samp_pvals(cpn_ctx* ctx, int64_t R, const int64_t* tbl_off, int64_t 
     return CPN_OK;
 }
 
-int cpn_grp_test_batch(cpn_ctx* ctx, int64_t R, int32_t n1, int32_t n2, int32_t matched, const double* phi, const int64_t* cpg_off,
-                       const double* rho_n, const double* d_n, const int64_t* sub_off, const int64_t* sub_p, const int64_t* sub_q,
-                       const void* labelings, int64_t P, int32_t exact, double* T, int64_t* cnt, double* pval, double* tcmd) {
-    if (!ctx) return CPN_ERR_ARG;
+// Group comparison of R regions, in chunks of regions so that the workspace (≈ 25 KB per region at 6 vs 6, 9 sub-regions)
+// does not grow with the batch: a whole genome (3·10⁶ regions) goes through the same few GB.  on_device: phi, the per-CpG tables
+// and the outputs are device pointers; the CSR offsets and the labelings are host arrays either way (they size the launches).
+static int grp_test_impl(cpn_ctx* ctx, bool on_device, int64_t R, int32_t n1, int32_t n2, int32_t matched, const double* phi,
+                         const int64_t* cpg_off, const double* rho_n, const double* d_n, const int64_t* sub_off, const int64_t* sub_p,
+                         const int64_t* sub_q, const void* labelings, int64_t P, int32_t exact, double* T, int64_t* cnt, double* pval,
+                         double* tcmd) {
     CPN_ARG(ctx, R >= 0 && n1 >= 1 && n2 >= 1 && n1 <= 32 && n2 <= 32 && P >= 0, "sizes (n1,n2 in 1..32)");
     CPN_ARG(ctx, !matched || n1 == n2, "the matched test needs n1 == n2");
     CPN_ARG(ctx, phi && cpg_off && rho_n && d_n && sub_off && sub_p && sub_q && (labelings || P == 0) && T && cnt && pval, "null pointer");
@@ -444,7 +447,6 @@ int cpn_grp_test_batch(cpn_ctx* ctx, int64_t R, int32_t n1, int32_t n2, int32_t 
     LaunchCounter lc(ctx);
     if (R == 0) return CPN_OK;
     const int S = n1 + n2, n = n1;
-    const int64_t Tm = R * S, sumN = cpg_off[R], sumK = sub_off[R];
     const int Kmax = kmax_of(sub_off, R);
     int64_t Nmax = 0;
     for (int64_t r = 0; r < R; ++r) {
@@ -466,60 +468,99 @@ int cpn_grp_test_batch(cpn_ctx* ctx, int64_t R, int32_t n1, int32_t n2, int32_t 
     if (matched) CPN_CUDA(ctx, cudaFuncSetAttribute(k_mat_sweep, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     unmat_kernel_t kern = unmat_kernel_for(Kmax);
     if (!matched) CPN_CUDA(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    const char* e_chunk = getenv("CPN_GRP_CHUNK_REGIONS");
+    const int64_t chunk = std::max<int64_t>(1, e_chunk ? atoll(e_chunk) : 65536);
+    const char* e_lane = getenv("CPN_CMD_LANE");
+    const bool lane_ok = !(e_lane && atoi(e_lane) == 0);
     CPN_CUDA(ctx, cudaEventRecord(ctx->ev0, s));
+    int64_t launches = 0;
     {
-        DevBuf<double> d_phi, d_rho, d_dn, logZ, ex, exx, lg, e1, e2, mml, nme, cmd, o_T, o_p, o_tc;
-        DevBuf<int64_t> d_cpg, d_so, d_sp, d_sq, reg_of, ex_off, k_off, pa, pb, cmd_off, d_js, o_cnt;
+        // labelings and the pair list are shared by every chunk
+        DevBuf<int64_t> d_js;
         DevBuf<int32_t> d_lab;
         DevBuf<int> d_pi, d_pj;
-        CPN_CUDA(ctx, d_phi.upload(phi, 3 * Tm, s));
-        CPN_CUDA(ctx, d_cpg.upload(cpg_off, R + 1, s)); CPN_CUDA(ctx, d_rho.upload(rho_n, sumN, s)); CPN_CUDA(ctx, d_dn.upload(d_n, sumN - R, s));
-        CPN_CUDA(ctx, d_so.upload(sub_off, R + 1, s)); CPN_CUDA(ctx, d_sp.upload(sub_p, sumK, s)); CPN_CUDA(ctx, d_sq.upload(sub_q, sumK, s));
         CPN_CUDA(ctx, d_pi.upload(pi.data(), npair, s)); CPN_CUDA(ctx, d_pj.upload(pj.data(), npair, s));
         if (matched) CPN_CUDA(ctx, d_js.upload((const int64_t*)labelings, P, s));
         else CPN_CUDA(ctx, d_lab.upload((const int32_t*)labelings, P * n1, s));
-        CPN_CUDA(ctx, reg_of.alloc(Tm, s)); CPN_CUDA(ctx, ex_off.alloc(Tm + 1, s)); CPN_CUDA(ctx, k_off.alloc(Tm + 1, s));
-        CPN_CUDA(ctx, logZ.alloc(Tm, s)); CPN_CUDA(ctx, ex.alloc(S * sumN, s)); CPN_CUDA(ctx, exx.alloc(S * (sumN - R), s));
-        CPN_CUDA(ctx, lg.alloc(4 * S * sumK, s)); CPN_CUDA(ctx, e1.alloc(S * sumK, s)); CPN_CUDA(ctx, e2.alloc(S * sumK, s));
-        CPN_CUDA(ctx, mml.alloc(S * sumK, s)); CPN_CUDA(ctx, nme.alloc(S * sumK, s));
-        const int64_t ncmd = matched ? (int64_t)n * sumK : (int64_t)S * S * sumK;
-        CPN_CUDA(ctx, cmd.alloc(ncmd, s));
-        CPN_CUDA(ctx, pa.alloc(R * npair, s)); CPN_CUDA(ctx, pb.alloc(R * npair, s)); CPN_CUDA(ctx, cmd_off.alloc(R * npair, s));
-        CPN_CUDA(ctx, o_T.alloc(nstat * sumK, s)); CPN_CUDA(ctx, o_cnt.alloc(nstat * sumK, s)); CPN_CUDA(ctx, o_p.alloc(nstat * sumK, s));
-        if (matched) CPN_CUDA(ctx, o_tc.alloc(sumK, s));
-        CPN_CUDA(ctx, cudaMemsetAsync(cmd.p, 0xFF, ncmd * sizeof(double), s));        // NaN outside the pairs that exist
-        { KTimer kt(ctx, CPN_K_PREP);
-          k_grp_models<<<blocks_for(Tm + 1, 256), 256, 0, s>>>(Tm, S, d_cpg.p, d_so.p, reg_of.p, ex_off.p, k_off.p); }
-        { KTimer kt(ctx, CPN_K_PREP);
-          k_grp_pairs<<<blocks_for(R * npair, 256), 256, 0, s>>>(R, S, npair, d_pi.p, d_pj.p, matched, d_so.p, pa.p, pb.p, cmd_off.p); }
-        // get_stat_sums! of every sample's model, comp_cmd of every pair, then the labelings
-        int rc = cpn_stat_sums_launch(ctx, Tm, d_phi.p, reg_of.p, ex_off.p, k_off.p, d_cpg.p, d_rho.p, d_dn.p, d_so.p, d_sp.p, d_sq.p, Nmax, logZ.p,
-                                      ex.p, exx.p, lg.p, e1.p, e2.p, mml.p, nme.p);
-        if (rc) return rc;
-        rc = cpn_cmd_launch(ctx, R * npair, pa.p, pb.p, d_phi.p, reg_of.p, ex_off.p, ex.p, exx.p, k_off.p, nme.p, d_cpg.p, d_rho.p, d_dn.p, d_so.p,
-                            d_sp.p, d_sq.p, Nmax, cmd_off.p, cmd.p);
-        if (rc) return rc;
-        if (matched) {
-            { KTimer kt(ctx, CPN_K_SWEEP); k_mat_tcmd<<<(unsigned)R, 32, 0, s>>>(R, n, d_so.p, cmd.p, o_tc.p); }
-            { KTimer kt(ctx, CPN_K_SWEEP);
-              k_mat_sweep<<<(unsigned)R, SW_THREADS, smem, s>>>(n, Kmax, d_so.p, mml.p, mml.p, nme.p, nme.p, d_js.p, P, exact, o_T.p, o_cnt.p, o_p.p,
-                                                                S, n); }
-            CPN_CUDA(ctx, o_tc.download(tcmd, sumK, s));
-        } else {
-            KTimer kt(ctx, CPN_K_SWEEP);
-            kern<<<(unsigned)R, SW_THREADS, smem, s>>>(n1, n2, Kmax, d_so.p, mml.p, nme.p, cmd.p, d_lab.p, P, exact, o_T.p, o_cnt.p, o_p.p);
+        std::vector<int64_t> cp, so;
+        for (int64_t r0 = 0; r0 < R; r0 += chunk) {
+            const int64_t Rc = std::min(chunk, R - r0), Tm = Rc * S;
+            cp.resize(Rc + 1); so.resize(Rc + 1);
+            for (int64_t i = 0; i <= Rc; ++i) { cp[i] = cpg_off[r0 + i] - cpg_off[r0]; so[i] = sub_off[r0 + i] - sub_off[r0]; }
+            const int64_t n0 = cpg_off[r0], k0 = sub_off[r0], sumN = cp[Rc], sumK = so[Rc];
+            CPN_CUDA(ctx, ctx->stage_arena.reset());
+            CpnArenaScope scope(&ctx->stage_arena);
+            DevIn<double> i_phi, i_rho, i_dn;
+            DevIn<int64_t> i_sp, i_sq;
+            DevOut<double> o_T, o_p, o_tc;
+            DevOut<int64_t> o_cnt;
+            DevBuf<double> logZ, lg, e1, e2, mml, nme, cmd;
+            DevBuf<int64_t> d_cpg, d_so, reg_of, ex_off, k_off, pa, pb, cmd_off;
+            CPN_CUDA(ctx, i_phi.bind(phi + 3 * r0 * S, 3 * Tm, on_device, s));
+            CPN_CUDA(ctx, d_cpg.upload(cp.data(), Rc + 1, s)); CPN_CUDA(ctx, d_so.upload(so.data(), Rc + 1, s));
+            CPN_CUDA(ctx, i_rho.bind(rho_n + n0, sumN, on_device, s)); CPN_CUDA(ctx, i_dn.bind(d_n + (n0 - r0), sumN - Rc, on_device, s));
+            CPN_CUDA(ctx, i_sp.bind(sub_p + k0, sumK, on_device, s)); CPN_CUDA(ctx, i_sq.bind(sub_q + k0, sumK, on_device, s));
+            CPN_CUDA(ctx, o_T.bind(T + nstat * k0, nstat * sumK, on_device, s)); CPN_CUDA(ctx, o_cnt.bind(cnt + nstat * k0, nstat * sumK, on_device, s));
+            CPN_CUDA(ctx, o_p.bind(pval + nstat * k0, nstat * sumK, on_device, s));
+            if (matched) CPN_CUDA(ctx, o_tc.bind(tcmd + k0, sumK, on_device, s));
+            CPN_CUDA(ctx, reg_of.alloc(Tm, s)); CPN_CUDA(ctx, ex_off.alloc(Tm + 1, s)); CPN_CUDA(ctx, k_off.alloc(Tm + 1, s));
+            CPN_CUDA(ctx, logZ.alloc(Tm, s)); CPN_CUDA(ctx, lg.alloc(4 * S * sumK, s)); CPN_CUDA(ctx, e1.alloc(S * sumK, s));
+            CPN_CUDA(ctx, e2.alloc(S * sumK, s)); CPN_CUDA(ctx, mml.alloc(S * sumK, s)); CPN_CUDA(ctx, nme.alloc(S * sumK, s));
+            const int64_t ncmd = matched ? (int64_t)n * sumK : (int64_t)S * S * sumK;
+            CPN_CUDA(ctx, cmd.alloc(ncmd, s));
+            CPN_CUDA(ctx, pa.alloc(Rc * npair, s)); CPN_CUDA(ctx, pb.alloc(Rc * npair, s)); CPN_CUDA(ctx, cmd_off.alloc(Rc * npair, s));
+            CPN_CUDA(ctx, cudaMemsetAsync(cmd.p, 0xFF, ncmd * sizeof(double), s));        // NaN outside the pairs that exist
+            { KTimer kt(ctx, CPN_K_PREP);
+              k_grp_models<<<blocks_for(Tm + 1, 256), 256, 0, s>>>(Tm, S, d_cpg.p, d_so.p, reg_of.p, ex_off.p, k_off.p); }
+            { KTimer kt(ctx, CPN_K_PREP);
+              k_grp_pairs<<<blocks_for(Rc * npair, 256), 256, 0, s>>>(Rc, S, npair, d_pi.p, d_pj.p, matched, d_so.p, pa.p, pb.p, cmd_off.p); }
+            // get_stat_sums! of every sample's model, comp_cmd of every pair, then the labelings
+            bool ordered = false;
+            if (lane_ok) {
+                if (on_device) { int rc0 = cpn_subregions_ordered_device(ctx, Rc, d_so.p, i_sp.p, i_sq.p, d_cpg.p, &ordered); if (rc0) return rc0; }
+                else ordered = cpn_subregions_ordered(Rc, so.data(), sub_p + k0, sub_q + k0, cp.data());
+            }
+            int rc = cpn_summaries_and_cmd(ctx, ordered, Tm, i_phi.p, reg_of.p, ex_off.p, k_off.p, S * sumN, S * sumK, Rc, sumN, d_cpg.p, i_rho.p, i_dn.p,
+                                           d_so.p, i_sp.p, i_sq.p, Nmax, Rc * npair, pa.p, pb.p, cmd_off.p, logZ.p, lg.p, e1.p, e2.p, mml.p, nme.p, cmd.p);
+            if (rc) return rc;
+            if (matched) {
+                { KTimer kt(ctx, CPN_K_SWEEP); k_mat_tcmd<<<(unsigned)Rc, 32, 0, s>>>(Rc, n, d_so.p, cmd.p, o_tc.p); }
+                { KTimer kt(ctx, CPN_K_SWEEP);
+                  k_mat_sweep<<<(unsigned)Rc, SW_THREADS, smem, s>>>(n, Kmax, d_so.p, mml.p, mml.p, nme.p, nme.p, d_js.p, P, exact, o_T.p, o_cnt.p, o_p.p,
+                                                                     S, n); }
+                CPN_CUDA(ctx, o_tc.finish(s));
+            } else {
+                KTimer kt(ctx, CPN_K_SWEEP);
+                kern<<<(unsigned)Rc, SW_THREADS, smem, s>>>(n1, n2, Kmax, d_so.p, mml.p, nme.p, cmd.p, d_lab.p, P, exact, o_T.p, o_cnt.p, o_p.p);
+            }
+            CPN_CUDA(ctx, cudaGetLastError());
+            CPN_CUDA(ctx, o_T.finish(s)); CPN_CUDA(ctx, o_cnt.finish(s)); CPN_CUDA(ctx, o_p.finish(s));
+            CPN_CUDA(ctx, cpn_wait_stream(ctx, s));                       // the chunk's workspace is reused by the next one
+            launches += ctx->last_launches;
+            ctx->last_launches = 0;
         }
-        CPN_CUDA(ctx, cudaGetLastError());
-        CPN_CUDA(ctx, o_T.download(T, nstat * sumK, s)); CPN_CUDA(ctx, o_cnt.download(cnt, nstat * sumK, s));
-        CPN_CUDA(ctx, o_p.download(pval, nstat * sumK, s));
         CPN_CUDA(ctx, cudaEventRecord(ctx->ev1, s));
-        CPN_CUDA(ctx, cudaStreamSynchronize(s));
+        CPN_CUDA(ctx, cpn_wait_stream(ctx, s));
     }
+    ctx->last_launches = launches;
     float ms = 0;
     CPN_CUDA(ctx, cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1));
     ctx->last_ms = ms;
     if (ctx->profile) cpn_profile_collect(ctx);
     return CPN_OK;
+}
+
+int cpn_grp_test_batch(cpn_ctx* ctx, int64_t R, int32_t n1, int32_t n2, int32_t matched, const double* phi, const int64_t* cpg_off,
+                       const double* rho_n, const double* d_n, const int64_t* sub_off, const int64_t* sub_p, const int64_t* sub_q,
+                       const void* labelings, int64_t P, int32_t exact, double* T, int64_t* cnt, double* pval, double* tcmd) {
+    if (!ctx) return CPN_ERR_ARG;
+    return grp_test_impl(ctx, false, R, n1, n2, matched, phi, cpg_off, rho_n, d_n, sub_off, sub_p, sub_q, labelings, P, exact, T, cnt, pval, tcmd);
+}
+int cpn_grp_test_batch_device(cpn_ctx* ctx, int64_t R, int32_t n1, int32_t n2, int32_t matched, const double* phi, const int64_t* cpg_off,
+                              const double* rho_n, const double* d_n, const int64_t* sub_off, const int64_t* sub_p, const int64_t* sub_q,
+                              const void* labelings, int64_t P, int32_t exact, double* T, int64_t* cnt, double* pval, double* tcmd) {
+    if (!ctx) return CPN_ERR_ARG;
+    return grp_test_impl(ctx, true, R, n1, n2, matched, phi, cpg_off, rho_n, d_n, sub_off, sub_p, sub_q, labelings, P, exact, T, cnt, pval, tcmd);
 }
 
 }  // extern "C"

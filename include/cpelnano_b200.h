@@ -219,6 +219,13 @@ int cpn_grp_test_batch(cpn_ctx* ctx, int64_t R, int32_t n1, int32_t n2, int32_t 
                        const int64_t* cpg_off, const double* rho_n, const double* d_n, const int64_t* sub_off,
                        const int64_t* sub_p, const int64_t* sub_q, const void* labelings, int64_t P, int32_t exact,
                        double* T, int64_t* cnt, double* pval, double* tcmd);
+/* The same with phi, rho_n, d_n, sub_p, sub_q and the outputs resident in device memory; cpg_off, sub_off and the labelings stay
+ * host arrays (they size the launches).  Both variants process the regions in chunks of CPN_GRP_CHUNK_REGIONS (default 65536)
+ * regions, so the workspace (about 25 KB per region at 6 vs 6) does not grow with the batch.                                     */
+int cpn_grp_test_batch_device(cpn_ctx* ctx, int64_t R, int32_t n1, int32_t n2, int32_t matched, const double* phi,
+                              const int64_t* cpg_off, const double* rho_n, const double* d_n, const int64_t* sub_off,
+                              const int64_t* sub_p, const int64_t* sub_q, const void* labelings, int64_t P, int32_t exact,
+                              double* T, int64_t* cnt, double* pval, double* tcmd);
 /* two-sample null statistics, all on the device  src/two_samp_perm_tests.jl:41-87 (pmap_two_samp_null_stats) over the
  * pmap of :220: for every region r and every permutation i of its pooled reads, refit both halves (multi-start EM),
  * summarise both fits (rscle_grp_mod! + get_stat_sums!) and return Tmml = mml1-mml2, Tnme = nme1-nme2, Tcmd = comp_cmd.
