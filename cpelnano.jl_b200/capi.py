@@ -13,7 +13,7 @@ MSTEP_FD, MSTEP_ANALYTIC = 0, 1
 FIT_NONE, FIT_NUMERICAL, FIT_FILTERED = -1, -2, -16        # status words (include/cpelnano_b200.h)
 
 # every exported symbol of include/cpelnano_b200.h (tests check the library exports exactly these)
-SYMBOLS = ["cpn_create", "cpn_destroy", "cpn_last_error", "cpn_version", "cpn_last_device_ms", "cpn_last_launches", "cpn_last_work",
+SYMBOLS = ["cpn_create", "cpn_create_multi", "cpn_num_devices", "cpn_destroy", "cpn_last_error", "cpn_version", "cpn_last_device_ms", "cpn_last_launches", "cpn_last_work",
            "cpn_measure_fp64_peak", "cpn_set_seed", "cpn_rng_phi0", "cpn_rng_perm", "cpn_set_profile", "cpn_get_profile", "cpn_analyze_batch", "cpn_analyze_batch_device", "cpn_fit_batch", "cpn_fit_batch_device", "cpn_estep_batch", "cpn_mstep_batch",
            "cpn_stat_sums_batch", "cpn_nls_reg_info", "cpn_cmd_batch", "cpn_grp_unmat_sweep", "cpn_grp_mat_sweep", "cpn_two_samp_pvals", "cpn_two_samp_null_batch", "cpn_two_samp_test_batch", "cpn_grp_test_batch", "cpn_grp_test_batch_device", "cpn_region_filter",
            "cpn_calls_open", "cpn_calls_close", "cpn_calls_open_error", "cpn_calls_error", "cpn_calls_num_lines", "cpn_calls_num_reads", "cpn_calls_num_chr",
@@ -70,6 +70,7 @@ class Library:
         d.cpn_last_launches.restype = C.c_int64
         d.cpn_last_launches.argtypes = [C.c_void_p]
         d.cpn_create.argtypes = [C.c_int, C.POINTER(C.c_void_p)]
+        d.cpn_create_multi.argtypes = [C.POINTER(C.c_int), C.c_int, C.POINTER(C.c_void_p)]
         d.cpn_destroy.argtypes = [C.c_void_p]
         d.cpn_nls_reg_info.restype = C.c_int64
         for f in ("cpn_calls_open_error", "cpn_calls_error", "cpn_calls_chr_name", "cpn_calls_read_name"):
@@ -88,9 +89,17 @@ class Library:
         return self.dll.cpn_version().decode()
 
     def ctx(self, device=0):
+        """The context of one device (int) or ONE context spanning several devices (tuple / list of ints: cpn_create_multi — the
+        host-pointer batch entry points then shard every call over those GPUs from this single process)."""
+        if isinstance(device, (list, tuple)):
+            device = tuple(int(d) for d in device)
         if device not in self._ctx:
             h = C.c_void_p()
-            rc = self.dll.cpn_create(int(device), C.byref(h))
+            if isinstance(device, tuple):
+                ids = (C.c_int * len(device))(*device)
+                rc = self.dll.cpn_create_multi(ids, C.c_int(len(device)), C.byref(h))
+            else:
+                rc = self.dll.cpn_create(int(device), C.byref(h))
             if rc != 0 or not h.value:
                 raise CpnError(f"cpn_create(device={device}) failed with code {rc}: no usable sm_100 GPU (there is no CPU fallback)")
             self._ctx[device] = h

@@ -100,6 +100,11 @@ struct cpn_ctx {
     int64_t prof_launches[CPN_K_NCLASS] = {0};
     // worker sub-contexts (own stream/events) used by the host-pointer entry points to run chunks of a batch concurrently
     std::vector<cpn_ctx*> children;
+    // cpn_create_multi: one context per device, devs[0] == this.  Host-pointer entry points shard the regions of a call over
+    // them (one host thread per device); region_base = position of a shard's first region in the caller's batch (seeded starts
+    // and permutations are keyed by the global position, so sharding does not change a result)
+    std::vector<cpn_ctx*> devs;
+    int64_t region_base = 0;
     // EM loop: pinned mailbox for the per-iteration active counts and the events that say when each has arrived
     int* h_counts = nullptr;
     int h_counts_cap = 0;

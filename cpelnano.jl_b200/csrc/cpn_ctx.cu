@@ -60,8 +60,32 @@ int cpn_create(int device_id, cpn_ctx** out) {
     return CPN_OK;
 }
 
+int cpn_create_multi(const int* device_ids, int n_dev, cpn_ctx** out) {
+    if (!out || !device_ids || n_dev < 1) return CPN_ERR_ARG;
+    *out = nullptr;
+    for (int i = 0; i < n_dev; ++i)
+        for (int j = 0; j < i; ++j)
+            if (device_ids[i] == device_ids[j]) return CPN_ERR_ARG;
+    cpn_ctx* head = nullptr;
+    int rc = cpn_create(device_ids[0], &head);
+    if (rc != CPN_OK) return rc;
+    head->devs.push_back(head);
+    for (int i = 1; i < n_dev; ++i) {
+        cpn_ctx* c = nullptr;
+        rc = cpn_create(device_ids[i], &c);
+        if (rc != CPN_OK) { cpn_destroy(head); return rc; }
+        head->devs.push_back(c);
+    }
+    cudaSetDevice(device_ids[0]);
+    *out = head;
+    return CPN_OK;
+}
+int cpn_num_devices(const cpn_ctx* ctx) { return ctx ? (ctx->devs.empty() ? 1 : (int)ctx->devs.size()) : 0; }
+
 void cpn_destroy(cpn_ctx* ctx) {
     if (!ctx) return;
+    for (size_t i = 1; i < ctx->devs.size(); ++i) cpn_destroy(ctx->devs[i]);
+    ctx->devs.clear();
     cudaSetDevice(ctx->device);
     if (ctx->stream) { cudaStreamSynchronize(ctx->stream); cudaStreamDestroy(ctx->stream); }
     if (ctx->ev0) cudaEventDestroy(ctx->ev0);

@@ -1493,6 +1493,7 @@ int fit_impl(cpn_ctx* ctx, bool on_device, int64_t R, const int64_t* grp_off, co
             CPN_CUDA(ctx, ctx->stage_arena.reset());
             local.arena = &ctx->stage_arena;
             local.seed = ctx->seed;
+            local.unit_base = ctx->region_base;
             int rc = fit_stage(ctx, local, on_device, R, grp_off, Nl, rho_l, d_l, read_off, lu, lm, phi0, n_init);
             if (rc) return rc;
         }
@@ -1953,7 +1954,7 @@ static int fit_chunked(cpn_ctx* ctx, bool on_device, int64_t R, const int64_t* g
                 slot[c].reset(new StagedBatch());
                 slot[c]->arena = ar;
                 slot[c]->seed = ctx->seed;
-                slot[c]->unit_base = r0;               // seeded starts are keyed by the region's position in the whole batch
+                slot[c]->unit_base = ctx->region_base + r0;   // seeded starts are keyed by the region's position in the whole batch
                 trace(u, "stage");
                 r = fit_stage(u, *slot[c], on_device, Rc, g.data(), Nl + g0, rho_l + g0, d_l + (g0 - r0), rd.data(), lu + obs[r0], lm + obs[r0],
                               phi0 ? phi0 + r0 * n_init * 3 : nullptr, n_init, 0);
@@ -2048,11 +2049,83 @@ static int fit_chunked(cpn_ctx* ctx, bool on_device, int64_t R, const int64_t* g
     return ret;
 }
 
+// cpn_create_multi contexts: the regions of a host-pointer call are cut into one contiguous shard per device, balanced by
+// reads x groups, and every device runs fit_chunked on its shard from its own host thread, writing into the caller's arrays at the
+// shard's offset.  Per-region arithmetic does not depend on the shard (seeded starts are keyed by the global position).
+static int multi_fit(cpn_ctx* ctx, int64_t R, const int64_t* grp_off, const double* Nl, const double* rho_l, const double* d_l,
+                     const int64_t* read_off, const double* lu, const double* lm, const double* phi0, int32_t n_init, int32_t max_em_iters,
+                     double amax, double bmax, double cmax, int32_t mstep_mode, double* phi_hat, double* Q, int32_t* status, int64_t* counters,
+                     double* phi_starts, double* Q_starts, const SummaryArgs* sa) {
+    CPN_ARG(ctx, R >= 0 && grp_off && read_off, "null pointer");
+    const int nd = (int)ctx->devs.size();
+    std::vector<int64_t> obs(R + 1);
+    obs[0] = 0;
+    for (int64_t r = 0; r < R; ++r) obs[r + 1] = obs[r] + (grp_off[r + 1] - grp_off[r]) * (read_off[r + 1] - read_off[r]);
+    std::vector<int64_t> bnd(nd + 1, R);
+    bnd[0] = 0;
+    for (int d = 1; d < nd; ++d) {
+        const int64_t target = (int64_t)((double)obs[R] * d / nd);
+        bnd[d] = std::max<int64_t>(bnd[d - 1], std::lower_bound(obs.begin(), obs.end(), target) - obs.begin());
+        bnd[d] = std::min(bnd[d], R);
+    }
+    std::vector<int> rc(nd, CPN_OK);
+    std::vector<std::thread> th;
+    for (int d = 0; d < nd; ++d) {
+        th.emplace_back([&, d]() {
+            cpn_ctx* c = ctx->devs[d];
+            const int64_t r0 = bnd[d], Rd = bnd[d + 1] - r0;
+            c->last_ms = 0; c->last_launches = 0;
+            for (double& w : c->last_work) w = 0;
+            if (Rd <= 0) return;
+            c->seed = ctx->seed; c->region_base = ctx->region_base + r0;
+            if (d > 0) cpn_set_profile(c, ctx->profile ? 1 : 0);
+            std::vector<int64_t> g(Rd + 1), rd(Rd + 1), cp, sb;
+            for (int64_t i = 0; i <= Rd; ++i) { g[i] = grp_off[r0 + i] - grp_off[r0]; rd[i] = read_off[r0 + i] - read_off[r0]; }
+            const int64_t g0 = grp_off[r0];
+            SummaryArgs sc{};
+            if (sa) {
+                cp.resize(Rd + 1); sb.resize(Rd + 1);
+                for (int64_t i = 0; i <= Rd; ++i) { cp[i] = sa->cpg_off[r0 + i] - sa->cpg_off[r0]; sb[i] = sa->sub_off[r0 + i] - sa->sub_off[r0]; }
+                const int64_t n0 = sa->cpg_off[r0], k0 = sa->sub_off[r0];
+                sc = SummaryArgs{cp.data(), sb.data(), sa->sub_p + k0, sa->sub_q + k0, sa->rho_n + n0, sa->d_n + (n0 - r0), sa->logZ + r0, sa->ex + n0,
+                                 sa->exx + (n0 - r0), sa->log_g + 4 * k0, sa->e_log_g1 + k0, sa->e_log_g2 + k0, sa->mml + k0, sa->nme + k0};
+            }
+            rc[d] = fit_chunked(c, false, Rd, g.data(), Nl + g0, rho_l + g0, d_l + (g0 - r0), rd.data(), lu + obs[r0], lm + obs[r0],
+                                phi0 ? phi0 + r0 * n_init * 3 : nullptr, n_init, max_em_iters, amax, bmax, cmax, mstep_mode, phi_hat + 3 * r0, Q + r0,
+                                status ? status + r0 : nullptr, counters ? counters + 4 * r0 : nullptr,
+                                phi_starts ? phi_starts + r0 * n_init * 3 : nullptr, Q_starts ? Q_starts + r0 * n_init : nullptr, sa ? &sc : nullptr);
+            c->region_base = 0;
+        });
+    }
+    for (auto& t : th) t.join();
+    cudaSetDevice(ctx->device);
+    int ret = CPN_OK;
+    double ms = 0, work[4] = {0, 0, 0, 0};
+    int64_t launches = 0;
+    for (int d = 0; d < nd; ++d) {
+        cpn_ctx* c = ctx->devs[d];
+        if (rc[d] != CPN_OK && ret == CPN_OK) { ret = rc[d]; if (d > 0) ctx->err = c->err; }
+        ms = std::max(ms, c->last_ms); launches += c->last_launches;
+        for (int k = 0; k < 4; ++k) work[k] += c->last_work[k];
+        if (d > 0)
+            for (int k = 0; k < CPN_K_NCLASS; ++k) {
+                ctx->prof_ms[k] += c->prof_ms[k]; ctx->prof_launches[k] += c->prof_launches[k];
+                c->prof_ms[k] = 0; c->prof_launches[k] = 0;
+            }
+    }
+    ctx->last_ms = ms; ctx->last_launches = launches;
+    for (int k = 0; k < 4; ++k) ctx->last_work[k] = work[k];
+    return ret;
+}
+
 int cpn_fit_batch(cpn_ctx* ctx, int64_t R, const int64_t* grp_off, const double* Nl, const double* rho_l, const double* d_l,
                   const int64_t* read_off, const double* log_pyx_u, const double* log_pyx_m, const double* phi0, int32_t n_init,
                   int32_t max_em_iters, double amax, double bmax, double cmax, int32_t mstep_mode, double* phi_hat, double* Q,
                   int32_t* status, int64_t* counters, double* phi_starts, double* Q_starts) {
     if (!ctx) return CPN_ERR_ARG;
+    if (ctx->devs.size() > 1)
+        return multi_fit(ctx, R, grp_off, Nl, rho_l, d_l, read_off, log_pyx_u, log_pyx_m, phi0, n_init, max_em_iters, amax, bmax, cmax, mstep_mode,
+                         phi_hat, Q, status, counters, phi_starts, Q_starts, nullptr);
     return fit_chunked(ctx, false, R, grp_off, Nl, rho_l, d_l, read_off, log_pyx_u, log_pyx_m, phi0, n_init, max_em_iters, amax, bmax, cmax,
                             mstep_mode, phi_hat, Q, status, counters, phi_starts, Q_starts, nullptr);
 }
@@ -2076,6 +2149,9 @@ static int analyze_common(cpn_ctx* ctx, bool dev, int64_t R, const int64_t* grp_
     SummaryArgs sa{cpg_off, sub_off, sub_p, sub_q, rho_n, d_n, logZ, ex, exx, log_g, e_log_g1, e_log_g2, mml, nme};
     if (!dev) {
         CPN_ARG(ctx, logZ && ex && exx && log_g && e_log_g1 && e_log_g2 && mml && nme, "null output pointer");
+        if (ctx->devs.size() > 1)
+            return multi_fit(ctx, R, grp_off, Nl, rho_l, d_l, read_off, lu, lm, phi0, n_init, max_em_iters, amax, bmax, cmax, mstep_mode, phi_hat, Q,
+                             status, counters, nullptr, nullptr, &sa);
         return fit_chunked(ctx, false, R, grp_off, Nl, rho_l, d_l, read_off, lu, lm, phi0, n_init, max_em_iters, amax, bmax, cmax, mstep_mode,
                                 phi_hat, Q, status, counters, nullptr, nullptr, &sa);
     }
@@ -2262,7 +2338,7 @@ static int two_samp_impl(cpn_ctx* ctx, int64_t R, const int64_t* grp_off, const 
         for (int64_t i = 0; i < Rc; ++i) {
             TsRegion& t = h_regs[i];
             const int64_t n = rd[i + 1] - rd[i], P = po[i + 1] - po[i];
-            t.v0 = 2 * po[i]; t.row0 = rows; t.ex0 = exo; t.k0 = ko; t.c0 = co; t.pid0 = pid[r0 + i] - pid[r0]; t.gr = r0 + i;
+            t.v0 = 2 * po[i]; t.row0 = rows; t.ex0 = exo; t.k0 = ko; t.c0 = co; t.pid0 = pid[r0 + i] - pid[r0]; t.gr = ctx->region_base + r0 + i;
             t.P = (int32_t)P; t.n = (int32_t)n; t.n1 = (int32_t)n1[r0 + i]; t.N = (int32_t)(cp[i + 1] - cp[i]); t.K = (int32_t)(so[i + 1] - so[i]);
             t.rows1 = (int32_t)((t.n1 + 31) / 32); t.rows2 = (int32_t)((n - t.n1 + 31) / 32); t.pad = 0;
             rows += P * (t.rows1 + t.rows2); exo += 2 * P * t.N; ko += 2 * P * t.K; co += P * t.K;
@@ -2388,9 +2464,71 @@ int cpn_two_samp_test_batch(cpn_ctx* ctx, int64_t R, const int64_t* grp_off, con
                             int32_t* fit_status) {
     if (!ctx) return CPN_ERR_ARG;
     CPN_ARG(ctx, phi_s1 && phi_s2, "null pointer");
-    return two_samp_impl(ctx, R, grp_off, Nl, rho_l, d_l, read_off, log_pyx_u, log_pyx_m, n1, phi_s1, phi_s2, perm_off, perm_ids, exact, phi0, n_init,
-                         max_em_iters, amax, bmax, cmax, mstep_mode, cpg_off, rho_n, d_n, sub_off, sub_p, sub_q, T_obs, cnt, n_valid, pval, T_null,
-                         fit_status);
+    if (ctx->devs.size() <= 1 || R < 2)
+        return two_samp_impl(ctx, R, grp_off, Nl, rho_l, d_l, read_off, log_pyx_u, log_pyx_m, n1, phi_s1, phi_s2, perm_off, perm_ids, exact, phi0,
+                             n_init, max_em_iters, amax, bmax, cmax, mstep_mode, cpg_off, rho_n, d_n, sub_off, sub_p, sub_q, T_obs, cnt, n_valid, pval,
+                             T_null, fit_status);
+    // cpn_create_multi: contiguous shards of regions balanced by permutations x reads x groups, one host thread per device
+    CPN_ARG(ctx, grp_off && read_off && perm_off && n1 && cpg_off && sub_off, "null pointer");
+    const int nd = (int)ctx->devs.size();
+    std::vector<int64_t> obs(R + 1), pid(R + 1), tn(R + 1);
+    std::vector<double> cost(R + 1);
+    obs[0] = pid[0] = tn[0] = 0; cost[0] = 0;
+    for (int64_t r = 0; r < R; ++r) {
+        const int64_t L = grp_off[r + 1] - grp_off[r], n = read_off[r + 1] - read_off[r], P = perm_off[r + 1] - perm_off[r];
+        obs[r + 1] = obs[r] + L * n; pid[r + 1] = pid[r] + P * n1[r]; tn[r + 1] = tn[r] + P * (sub_off[r + 1] - sub_off[r]);
+        cost[r + 1] = cost[r] + (double)(P + 1) * (double)(L * n);
+    }
+    std::vector<int64_t> bnd(nd + 1, R);
+    bnd[0] = 0;
+    for (int d = 1; d < nd; ++d) {
+        bnd[d] = std::lower_bound(cost.begin(), cost.end(), cost[R] * d / nd) - cost.begin();
+        bnd[d] = std::min(std::max(bnd[d], bnd[d - 1]), R);
+    }
+    std::vector<int> rc(nd, CPN_OK);
+    std::vector<std::thread> th;
+    for (int d = 0; d < nd; ++d) {
+        th.emplace_back([&, d]() {
+            cpn_ctx* c = ctx->devs[d];
+            const int64_t r0 = bnd[d], Rd = bnd[d + 1] - r0;
+            c->last_ms = 0; c->last_launches = 0;
+            for (double& w : c->last_work) w = 0;
+            if (Rd <= 0) return;
+            c->seed = ctx->seed; c->region_base = ctx->region_base + r0;
+            if (d > 0) cpn_set_profile(c, ctx->profile ? 1 : 0);
+            std::vector<int64_t> g(Rd + 1), rd(Rd + 1), cp(Rd + 1), so(Rd + 1), po(Rd + 1);
+            for (int64_t i = 0; i <= Rd; ++i) {
+                g[i] = grp_off[r0 + i] - grp_off[r0]; rd[i] = read_off[r0 + i] - read_off[r0]; cp[i] = cpg_off[r0 + i] - cpg_off[r0];
+                so[i] = sub_off[r0 + i] - sub_off[r0]; po[i] = perm_off[r0 + i] - perm_off[r0];
+            }
+            const int64_t g0 = grp_off[r0], n0 = cpg_off[r0], k0 = sub_off[r0], p0 = perm_off[r0];
+            rc[d] = two_samp_impl(c, Rd, g.data(), Nl + g0, rho_l + g0, d_l + (g0 - r0), rd.data(), log_pyx_u + obs[r0], log_pyx_m + obs[r0], n1 + r0,
+                                  phi_s1 + 3 * r0, phi_s2 + 3 * r0, po.data(), perm_ids ? perm_ids + pid[r0] : nullptr, exact ? exact + r0 : nullptr,
+                                  phi0 ? phi0 + 2 * p0 * n_init * 3 : nullptr, n_init, max_em_iters, amax, bmax, cmax, mstep_mode, cp.data(), rho_n + n0,
+                                  d_n + (n0 - r0), so.data(), sub_p + k0, sub_q + k0, T_obs + 3 * k0, cnt + 3 * k0, n_valid + 3 * k0, pval + 3 * k0,
+                                  T_null ? T_null + 3 * tn[r0] : nullptr, fit_status ? fit_status + 2 * p0 : nullptr);
+            c->region_base = 0;
+        });
+    }
+    for (auto& t : th) t.join();
+    cudaSetDevice(ctx->device);
+    int ret = CPN_OK;
+    double ms = 0, work[4] = {0, 0, 0, 0};
+    int64_t launches = 0;
+    for (int d = 0; d < nd; ++d) {
+        cpn_ctx* c = ctx->devs[d];
+        if (rc[d] != CPN_OK && ret == CPN_OK) { ret = rc[d]; if (d > 0) ctx->err = c->err; }
+        ms = std::max(ms, c->last_ms); launches += c->last_launches;
+        for (int k = 0; k < 4; ++k) work[k] += c->last_work[k];
+        if (d > 0)
+            for (int k = 0; k < CPN_K_NCLASS; ++k) {
+                ctx->prof_ms[k] += c->prof_ms[k]; ctx->prof_launches[k] += c->prof_launches[k];
+                c->prof_ms[k] = 0; c->prof_launches[k] = 0;
+            }
+    }
+    ctx->last_ms = ms; ctx->last_launches = launches;
+    for (int k = 0; k < 4; ++k) ctx->last_work[k] = work[k];
+    return ret;
 }
 
 }  // extern "C"

@@ -14,6 +14,7 @@
 #include <algorithm>
 #include <cmath>
 #include <cstdlib>
+#include <thread>
 #include <vector>
 
 #include "cpn_common.cuh"
@@ -554,7 +555,44 @@ int cpn_grp_test_batch(cpn_ctx* ctx, int64_t R, int32_t n1, int32_t n2, int32_t 
                        const double* rho_n, const double* d_n, const int64_t* sub_off, const int64_t* sub_p, const int64_t* sub_q,
                        const void* labelings, int64_t P, int32_t exact, double* T, int64_t* cnt, double* pval, double* tcmd) {
     if (!ctx) return CPN_ERR_ARG;
-    return grp_test_impl(ctx, false, R, n1, n2, matched, phi, cpg_off, rho_n, d_n, sub_off, sub_p, sub_q, labelings, P, exact, T, cnt, pval, tcmd);
+    if (ctx->devs.size() <= 1 || R < 2)
+        return grp_test_impl(ctx, false, R, n1, n2, matched, phi, cpg_off, rho_n, d_n, sub_off, sub_p, sub_q, labelings, P, exact, T, cnt, pval, tcmd);
+    // cpn_create_multi: equal contiguous blocks of regions (a region's cost is its CpG count, nearly uniform), one host thread per device
+    CPN_ARG(ctx, cpg_off && sub_off, "null pointer");
+    const int nd = (int)ctx->devs.size(), S = n1 + n2, nstat = matched ? 2 : 3;
+    std::vector<int> rc(nd, CPN_OK);
+    std::vector<std::thread> th;
+    for (int d = 0; d < nd; ++d) {
+        th.emplace_back([&, d]() {
+            cpn_ctx* c = ctx->devs[d];
+            const int64_t r0 = R * d / nd, Rd = R * (d + 1) / nd - r0;
+            c->last_ms = 0; c->last_launches = 0;
+            if (Rd <= 0) return;
+            if (d > 0) cpn_set_profile(c, ctx->profile ? 1 : 0);
+            std::vector<int64_t> cp(Rd + 1), so(Rd + 1);
+            for (int64_t i = 0; i <= Rd; ++i) { cp[i] = cpg_off[r0 + i] - cpg_off[r0]; so[i] = sub_off[r0 + i] - sub_off[r0]; }
+            const int64_t n0 = cpg_off[r0], k0 = sub_off[r0];
+            rc[d] = grp_test_impl(c, false, Rd, n1, n2, matched, phi + 3 * S * r0, cp.data(), rho_n + n0, d_n + (n0 - r0), so.data(), sub_p + k0, sub_q + k0,
+                                  labelings, P, exact, T + nstat * k0, cnt + nstat * k0, pval + nstat * k0, tcmd ? tcmd + k0 : nullptr);
+        });
+    }
+    for (auto& t : th) t.join();
+    cudaSetDevice(ctx->device);
+    int ret = CPN_OK;
+    double ms = 0;
+    int64_t launches = 0;
+    for (int d = 0; d < nd; ++d) {
+        cpn_ctx* c = ctx->devs[d];
+        if (rc[d] != CPN_OK && ret == CPN_OK) { ret = rc[d]; if (d > 0) ctx->err = c->err; }
+        ms = std::max(ms, c->last_ms); launches += c->last_launches;
+        if (d > 0)
+            for (int k = 0; k < CPN_K_NCLASS; ++k) {
+                ctx->prof_ms[k] += c->prof_ms[k]; ctx->prof_launches[k] += c->prof_launches[k];
+                c->prof_ms[k] = 0; c->prof_launches[k] = 0;
+            }
+    }
+    ctx->last_ms = ms; ctx->last_launches = launches;
+    return ret;
 }
 int cpn_grp_test_batch_device(cpn_ctx* ctx, int64_t R, int32_t n1, int32_t n2, int32_t matched, const double* phi, const int64_t* cpg_off,
                               const double* rho_n, const double* d_n, const int64_t* sub_off, const int64_t* sub_p, const int64_t* sub_q,

@@ -55,6 +55,14 @@ enum { CPN_FILTER_FEW_CPGS = 1 /* N <= 9, :309 */, CPN_FILTER_NO_READS = 2 /* rs
 
 /* ---- context ------------------------------------------------------------------------------- */
 int  cpn_create(int device_id, cpn_ctx** out);
+/* One context spanning several GPUs of the box, for a single host process (the reference is one master process,
+ * src/nanopore.jl:362-416).  The host-pointer entry points cpn_fit_batch, cpn_analyze_batch, cpn_grp_test_batch and
+ * cpn_two_samp_test_batch then shard the regions of a call over the devices — contiguous blocks balanced by the cost proxy
+ * reads x groups, one host thread per device, each device copying its results straight into the caller's arrays at
+ * the shard's offset: no collective, outputs in input order, bit-identical to the single-device call.  Every other entry point
+ * runs on device_ids[0].  cpn_last_device_ms = the slowest device's time.                                                       */
+int  cpn_create_multi(const int* device_ids, int n_dev, cpn_ctx** out);
+int  cpn_num_devices(const cpn_ctx* ctx);
 void cpn_destroy(cpn_ctx* ctx);
 const char* cpn_last_error(const cpn_ctx* ctx);           /* NUL-terminated, library-owned */
 const char* cpn_version(void);

@@ -146,7 +146,8 @@ def test_two_sample_null_stats_vs_oracle_composition(engine, orc, cpn):
         out = {"nan_pattern_flip_rate": float(np.mean(nan_a != nan_b)), "entries": int(both.sum())}
         for t, name in enumerate(("tmml", "tnme", "tcmd")):
             d = np.abs(A - B)[both & (stat == t)]
-            out[name] = {"median": float(np.median(d)), "p90": float(np.percentile(d, 90)), "p99": float(np.percentile(d, 99))}
+            out[name] = {"median": float(np.median(d)), "p90": float(np.percentile(d, 90)), "p99": float(np.percentile(d, 99)),
+                         "frac_gt_1e-2": float(np.mean(d > 1e-2))}
         return out
 
     got, slf = cmp(T_dev, T_ref), cmp(T_per, T_ref)
@@ -157,8 +158,9 @@ def test_two_sample_null_stats_vs_oracle_composition(engine, orc, cpn):
         # same distribution as the oracle against itself: typical entry equal to 1e-6, tails within the EM stopping slack
         assert got[name]["median"] <= max(1e-6, 3 * slf[name]["median"]), (name, got, slf)
         assert got[name]["p90"] <= max(1e-4, 3 * slf[name]["p90"]), (name, got, slf)
-        # the p99 of ≈ 1500 entries is a handful of refits that ended in another optimum (a pick flip): bounded, not tight
-        assert got[name]["p99"] <= max(5e-2, 3 * slf[name]["p99"]), (name, got, slf)
+        # the tail is made of the few refits that ended in another optimum (a pick flip moves all 9 sub-regions of a permutation at
+        # once, so a p99 over ≈ 2400 entries is 2-3 permutations): bounded as a rate, like the flip rates of the single-sample test
+        assert got[name]["frac_gt_1e-2"] <= slf[name]["frac_gt_1e-2"] + 0.03, (name, got, slf)
     ok = ~np.isnan(T_dev) & (stat == 2)
     assert np.all((T_dev[ok] > -1e-6) & (T_dev[ok] < 1.0))
 

@@ -655,6 +655,56 @@ def test_second_device_worker_threads(engine, cpn, monkeypatch):
         assert np.array_equal(np.asarray(outs[1][k]), np.asarray(outs[2][k]), equal_nan=True), k
 
 
+def test_multi_device_context_is_bit_identical(engine, cpn):
+    """cpn_create_multi: one context spanning two GPUs (the single Julia master of the reference drives all devices): the host-pointer
+    batch calls shard their regions over the devices and must return exactly what one device returns — fit + summaries (explicit
+    and seeded starts), the group test and the two-sample test."""
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs two GPUs")
+    lib = engine.lib
+    multi = (0, 1)
+    nb = cpn.simulations.make_nano_batch(70, M=20, seed=41)
+    n_init = 3
+    phi0 = cpn.simulations.gen_phi0s(np.random.default_rng(6), nb.R, n_init)
+    sub_off, _, _, sub_p, sub_q = cpn.capi.nls_reg_info_batch(lib, nb.chrst, nb.chrend, 350, nb.cpg_off, nb.cpg_pos)
+    for p0 in (phi0, None):
+        for d in (0, multi):
+            lib.set_seed(99, d)
+        a = lib.analyze_batch(nb.grp_off, nb.Nl, nb.rho_l, nb.d_l, nb.read_off, nb.log_pyx_u, nb.log_pyx_m, p0, n_init, nb.cpg_off, nb.rho_n, nb.d_n,
+                              sub_off, sub_p, sub_q, device=0)
+        b = lib.analyze_batch(nb.grp_off, nb.Nl, nb.rho_l, nb.d_l, nb.read_off, nb.log_pyx_u, nb.log_pyx_m, p0, n_init, nb.cpg_off, nb.rho_n, nb.d_n,
+                              sub_off, sub_p, sub_q, device=multi)
+        for k in a:
+            assert np.array_equal(np.asarray(a[k]), np.asarray(b[k]), equal_nan=True), (k, p0 is None)
+        fa = lib.fit_batch(nb.grp_off, nb.Nl, nb.rho_l, nb.d_l, nb.read_off, nb.log_pyx_u, nb.log_pyx_m, p0, n_init, per_start=True, device=0)
+        fb = lib.fit_batch(nb.grp_off, nb.Nl, nb.rho_l, nb.d_l, nb.read_off, nb.log_pyx_u, nb.log_pyx_m, p0, n_init, per_start=True, device=multi)
+        for k in fa:
+            assert np.array_equal(np.asarray(fa[k]), np.asarray(fb[k]), equal_nan=True), (k, p0 is None)
+    assert (a["pick"] >= 0).sum() > nb.R // 2
+    # group test
+    rng = np.random.default_rng(2)
+    S = 8
+    phi = np.stack([rng.uniform(-1, 1, (nb.R, S)), rng.uniform(-20, 20, (nb.R, S)), rng.uniform(0, 5, (nb.R, S))], axis=2)
+    from itertools import combinations
+    labs = np.array(list(combinations(range(1, S + 1), 4)), dtype=np.int32)
+    ga = lib.grp_test_batch(4, 4, False, phi, nb.cpg_off, nb.rho_n, nb.d_n, sub_off, sub_p, sub_q, labs, True, device=0)
+    gb = lib.grp_test_batch(4, 4, False, phi, nb.cpg_off, nb.rho_n, nb.d_n, sub_off, sub_p, sub_q, labs, True, device=multi)
+    for x, y in zip(ga, gb):
+        assert np.array_equal(x, y, equal_nan=True)
+    # two-sample test, everything random drawn on the device
+    P, n1 = 25, 8
+    perm_off = np.arange(nb.R + 1, dtype=np.int64) * P
+    phi2 = phi[:, 1] * 0.9
+    outs = []
+    for d in (0, multi):
+        lib.set_seed(5, d)
+        outs.append(lib.two_samp_test_batch(nb.grp_off, nb.Nl, nb.rho_l, nb.d_l, nb.read_off, nb.log_pyx_u, nb.log_pyx_m, np.full(nb.R, n1), phi[:, 0], phi2,
+                                            perm_off, None, None, None, 2, nb.cpg_off, nb.rho_n, nb.d_n, sub_off, sub_p, sub_q, want_null=True, device=d))
+    for k in outs[0]:
+        assert np.array_equal(outs[0][k], outs[1][k], equal_nan=True), k
+
+
 def test_analyze_regions_filters(engine, cpn):
     """pmap_analyze_reg's data filters (nanopore.jl:309,322-326): regions failing them keep proc == false."""
     nb = cpn.simulations.make_nano_batch(5, M=30, seed=3)
