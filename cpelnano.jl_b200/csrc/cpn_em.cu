@@ -58,7 +58,12 @@ struct __align__(32) ItemDesc { int inst, L, M, ridx; int64_t g0, ew_off; };
 // A "region" of the EM kernels.  Normally one estimation region with its own reads.  A VIEW (two-sample permutation
 // refits) shares the group tables and the packed emissions of a base region and names its reads through an index table:
 // ridx ≥ 0 is the first row (32 int32 read ids, one per lane and chunk) of the view in RegionTables::ridx; −1 = all reads.
-struct __align__(16) RegionDesc { int64_t g0, ew_off, rb_off; int32_t L, M, ridx, pad; };
+// llrmax = largest |log-likelihood ratio| among the region's emissions (after the clamp), idmax = largest 1/d_l: together with |c|
+// they bound how fast an E-step message can grow or shrink per group, i.e. how many groups may pass between two rescalings.
+struct __align__(16) RegionDesc { int64_t g0, ew_off, rb_off; int32_t L, M, ridx; float llrmax, idmax; int32_t pad; };
+static_assert(sizeof(RegionDesc) == 48, "RegionDesc layout");
+constexpr int ITEM_SLOW_BIT = 30;  // ItemDesc::M bit: this instance must rescale every group (k_make_desc decides)
+constexpr int EW_ROW = 64;         // doubles per emission row: 32 lanes x (r, 1/r)
 
 struct RegionTables {
     // per group (offsets grp_off): N_l, N_l·ρ_l and 1/d_l (coupling l→l+1; entry L-1 unused)
@@ -108,39 +113,55 @@ __global__ void k_prep_sites(int64_t R, const int64_t* __restrict__ grp_off, con
     }
 }
 
-// Packs emissions (structures.jl:121-128: obs, log_pyx_u, log_pyx_m) as likelihood ratios, lanes = reads.
+// Packs emissions (structures.jl:121-128: obs, log_pyx_u, log_pyx_m) as likelihood ratios, lanes = reads: per (group, read) the
+// pair (r, 1/r), r = exp(log p(y|+1) − log p(y|−1)) — the E-step multiplies by whichever of the two keeps the heavier state of the
+// group at weight 1 — and per region the bounds RegionDesc::llrmax / idmax.
 // |LLR| is clamped at 300 with the dropped mass (< e^-300 relative) moved into the per-read base term.
 __global__ void k_prep_emis(int64_t R, const int64_t* __restrict__ grp_off, const int64_t* __restrict__ read_off,
                             const int64_t* __restrict__ obs_off, const double* __restrict__ lu, const double* __restrict__ lm,
-                            const int64_t* __restrict__ ew_off, const int64_t* __restrict__ rb_off, double* __restrict__ ew,
-                            double* __restrict__ rb) {
+                            const int64_t* __restrict__ ew_off, const int64_t* __restrict__ rb_off, const double* __restrict__ invd,
+                            double* __restrict__ ew, double* __restrict__ rb, RegionDesc* __restrict__ rdesc) {
     int64_t warp = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5;
     int lane = threadIdx.x & 31;
     if (warp >= R) return;
-    int64_t L = grp_off[warp + 1] - grp_off[warp];
+    const int64_t g0 = grp_off[warp];
+    int64_t L = grp_off[warp + 1] - g0;
     int64_t M = read_off[warp + 1] - read_off[warp];
     int64_t nchunk = (M + 31) >> 5;
     const double* lu_r = lu + obs_off[warp];
     const double* lm_r = lm + obs_off[warp];
+    double dmax = 0.0;
     for (int64_t ch = 0; ch < nchunk; ++ch) {
         int64_t m = ch * 32 + lane;
         double base = 0.0;
-        double* dst = ew + ew_off[warp] + ch * L * 32 + lane;
+        double2* dst = reinterpret_cast<double2*>(ew + ew_off[warp] + ch * L * EW_ROW) + lane;
         for (int64_t l = 0; l < L; ++l) {
-            double r = 1.0;
+            double r = 1.0, ri = 1.0;
             if (m < M) {
                 double u = lu_r[m * L + l], v = lm_r[m * L + l];
                 if (u == u) {   // observed
                     double d = v - u;
                     if (d > LLR_CLAMP) { u = v - LLR_CLAMP; d = LLR_CLAMP; }
                     else if (d < -LLR_CLAMP) { d = -LLR_CLAMP; }
-                    r = exp(d);
+                    r = exp(d); ri = exp(-d);
                     base += u;
+                    dmax = fmax(dmax, fabs(d));          // a NaN likelihood leaves dmax alone; the NaN itself poisons the fit
                 }
             }
-            dst[l * 32] = r;
+            dst[l * 32] = make_double2(r, ri);
         }
         rb[rb_off[warp] + ch * 32 + lane] = base;
+    }
+    double idm = 0.0;
+    for (int64_t l = lane; l < L - 1; l += 32) idm = fmax(idm, invd[g0 + l]);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        dmax = fmax(dmax, __shfl_xor_sync(0xffffffffu, dmax, o));
+        idm = fmax(idm, __shfl_xor_sync(0xffffffffu, idm, o));
+    }
+    if (lane == 0) {
+        rdesc[warp].llrmax = __double2float_ru(dmax);
+        rdesc[warp].idmax = __double2float_ru(idm);
     }
 }
 
@@ -179,22 +200,71 @@ __device__ __forceinline__ void fill_tile(SiteTile& st, int l0, int n, int lane,
 // ---------------------------------------------------------------------------------------------------
 // E-step: ES = Σ_m ∇_ϕ log Zc_m(ϕ)   (≡ get_ess ∘ get_cond_exs_log)
 // ---------------------------------------------------------------------------------------------------
-// One forward sweep for the 32 reads of a chunk.  BPOS = (c ≥ 0).  (u,v) below are the source states that
-// enter x'=+1 with weight 1 and t respectively; for c<0 the roles of same/opposite swap.
+// The statistics are RATIOS of the tangent sums to the message sum, so a chain step may be normalised by anything that is
+// common to the eight state values.  Each step is normalised by the potential of the group's HEAVIER state (α_l ≥ 0: x=+1,
+// weight e^{α}·r; α_l < 0: x=−1, weight e^{−α}): that state's four values take no multiplication at all, the other four
+// are multiplied by κ = e^{−2|α_l|}·r^{∓1} ≤ e^{|LLR|}.  21 FP64 instructions per (read, group) instead of 26.5, and the
+// power-of-two rescale moves out of the step: the heavier component never shrinks by more than t = e^{−2|β|} per group and
+// nothing grows by more than 2·max(1, κ), so with |LLR| ≤ 80 and |β| ≤ 40 eight groups fit between two rescalings with 60
+// binary orders of magnitude to spare on either side; instances outside those bounds (RegionDesc::llrmax/idmax, |c|) take
+// estep_chunk_slow, which rescales after every group.
 #ifndef E_PF_N
 #define E_PF_N 8
 #endif
-constexpr int E_PF = E_PF_N;       // emission weights prefetched per lane (register double buffer)
+constexpr int E_PF = E_PF_N;       // groups per block of emission rows (ring slot) = groups between two rescalings
+constexpr float E_FAST_LLR = 80.0f, E_FAST_BETA = 40.0f;
+static_assert(TILE % E_PF == 0 && E_PF <= 32 && (E_PF & (E_PF - 1)) == 0, "blocks of groups must tile a shared-memory tile");
 
 struct EState { double fp, fm, gap, gam, gbp, gbm, gcp, gcm; };
 
-// One chain step for one read.  (u,v) are the source states entering x'=+1 with weight 1 and t; for c<0 the roles of
-// aligned/opposite swap (BPOS=false).  `sc` is the power-of-two rescale computed from an earlier message.
-template <bool BPOS>
-__device__ __forceinline__ void estep_site(EState& s, const SiteTile& st, int j, double r, double sc) {
-    const double2 w = st.w[j], tn = st.tn[j], bd = st.bd[j];
-    const double t = tn.x, na = tn.y, nb = bd.x, sinvd = bd.y;
-    double phiP = (w.y * r) * sc, phiM = w.x * sc;
+// Per-group potentials of one EM instance for the E-step: (e^{−2|α|}, t), (N_l, N_lρ_l), ±1/d_l — two LDS.128 and one
+// LDS.64 per chain step, all lanes reading the same address (broadcast).  The sign of α_l travels as a bit mask.
+struct SiteTileK {
+    double2 et[TILE];
+    double2 nn[TILE];
+    double sd[TILE];
+};
+
+// Stages groups [l0, l0+n) (lanes strided over the groups; all loads of a lane are issued before any exponential) and returns
+// the mask of groups with α_l ≥ 0 (bit j of m[j / 32]).
+__device__ __forceinline__ void fill_tile_k(SiteTileK& st, int l0, int n, int lane, const double* __restrict__ na_g,
+                                            const double* __restrict__ nb_g, const double* __restrict__ invd_g, double a, double b,
+                                            double cabs, bool bpos, unsigned& m0, unsigned& m1) {
+    constexpr int K = TILE / 32;
+    static_assert(K == 2, "two mask words");
+    double na[K], nb[K], id[K];
+#pragma unroll
+    for (int k = 0; k < K; ++k) {
+        const int j = lane + 32 * k, l = l0 + j;
+        const bool in = j < n;
+        na[k] = in ? na_g[l] : 0.0;
+        nb[k] = in ? nb_g[l] : 0.0;
+        id[k] = (in && l > 0) ? invd_g[l - 1] : 0.0;
+    }
+#pragma unroll
+    for (int k = 0; k < K; ++k) {
+        const int j = lane + 32 * k, l = l0 + j;
+        const bool in = j < n;
+        double alpha = fma(b, nb[k], a * na[k]);
+        const unsigned mk = __ballot_sync(0xffffffffu, in && __double2hiint(alpha) >= 0);
+        if (k == 0) m0 = mk; else m1 = mk;
+        if (in) {
+            // group 0 has no incoming coupling: t = 0 makes the generic step reproduce f = φ_0 from the all-ones message
+            st.et[j] = make_double2(cpn_exp_neg(-2.0 * fabs(alpha)), (l > 0) ? cpn_exp_neg(-2.0 * (cabs * id[k])) : 0.0);
+            st.nn[j] = make_double2(na[k], nb[k]);
+            st.sd[j] = bpos ? id[k] : -id[k];
+        }
+    }
+}
+
+// One chain step for one read.  BPOS = (c ≥ 0): (u,v) are the source states entering x'=+1 with weight 1 and t (for c<0 the
+// roles of aligned/opposite swap).  APOS = (α_l ≥ 0): x'=+1 is the heavier state and stays unmultiplied; `rsel` is 1/r then,
+// r otherwise.
+template <bool BPOS, bool APOS>
+__device__ __forceinline__ void estep_site(EState& s, const SiteTileK& st, int j, double rsel) {
+    const double2 et = st.et[j], nn = st.nn[j];
+    const double sinvd = st.sd[j];
+    const double k = et.x * rsel, t = et.y, na = nn.x, nb = nn.y;
     double u = BPOS ? s.fp : s.fm, v = BPOS ? s.fm : s.fp;
     double Gp = fma(t, v, u), Gm = fma(t, u, v);
     double ua = BPOS ? s.gap : s.gam, va = BPOS ? s.gam : s.gap;
@@ -204,80 +274,134 @@ __device__ __forceinline__ void estep_site(EState& s, const SiteTile& st, int j,
     double Hbp = fma(t, vb, ub), Hbm = fma(t, ub, vb);
     double Hcp = fma(t, vc, uc), Hcm = fma(t, uc, vc);
     double Dp = fma(2.0, u, -Gp), Dm = fma(2.0, v, -Gm);          // Σ_x (x x') ψ f, up to the sign carried by sinvd
-    s.gap = phiP * fma(na, Gp, Hap);
-    s.gam = phiM * fma(-na, Gm, Ham);
-    s.gbp = phiP * fma(nb, Gp, Hbp);
-    s.gbm = phiM * fma(-nb, Gm, Hbm);
-    s.gcp = phiP * fma(sinvd, Dp, Hcp);
-    s.gcm = phiM * fma(sinvd, Dm, Hcm);
-    s.fp = phiP * Gp;
-    s.fm = phiM * Gm;
+    if (APOS) {
+        s.gap = fma(na, Gp, Hap);        s.gam = k * fma(-na, Gm, Ham);
+        s.gbp = fma(nb, Gp, Hbp);        s.gbm = k * fma(-nb, Gm, Hbm);
+        s.gcp = fma(sinvd, Dp, Hcp);     s.gcm = k * fma(sinvd, Dm, Hcm);
+        s.fp = Gp;                       s.fm = k * Gm;
+    } else {
+        s.gap = k * fma(na, Gp, Hap);    s.gam = fma(-na, Gm, Ham);
+        s.gbp = k * fma(nb, Gp, Hbp);    s.gbm = fma(-nb, Gm, Hbm);
+        s.gcp = k * fma(sinvd, Dp, Hcp); s.gcm = fma(sinvd, Dm, Hcm);
+        s.fp = k * Gp;                   s.fm = Gm;
+    }
+}
+__device__ __forceinline__ void estep_rescale(EState& s) {
+    const double sc = cpn_inv_pow2_of(s.fp + s.fm);
+    s.fp *= sc; s.fm *= sc; s.gap *= sc; s.gam *= sc; s.gbp *= sc; s.gbm *= sc; s.gcp *= sc; s.gcm *= sc;
 }
 
-// Emission weights of a warp travel global → shared memory with cp.async (8 bytes per lane and group) into a private
-// ring: two slots of E_PF groups plus one slot for the chain tail.  A lane only ever reads what it copied itself, so no
-// warp synchronisation is needed; and because an asynchronous copy has no destination register, the deep prefetch costs
-// no registers (the register file is what limits the number of resident E-step warps).
-struct EmisRing { double r[3][E_PF][32]; };
+// Emission pairs of a warp travel global → shared memory with cp.async into a private ring of two blocks of E_PF groups,
+// as two planes (r and 1/r, 8 bytes per lane each) so that a step's LDS.64 of either is conflict-free.  A lane only ever
+// reads what it copied itself, so no warp synchronisation is needed; and because an asynchronous copy has no destination
+// register, the deep prefetch costs no registers (the register file is what limits the number of resident E-step warps).
+#ifndef E_RING_PLANAR
+#define E_RING_PLANAR 1
+#endif
+#if E_RING_PLANAR
+struct EmisRing { double r[2][E_PF][2][32]; };
+#define ERING_R(ring, slot, u, lane) (ring).r[slot][u][0][lane]
+#define ERING_RI(ring, slot, u, lane) (ring).r[slot][u][1][lane]
+#else
+struct EmisRing { double2 r[2][E_PF][32]; };
+#define ERING_R(ring, slot, u, lane) (ring).r[slot][u][lane].x
+#define ERING_RI(ring, slot, u, lane) (ring).r[slot][u][lane].y
+#endif
 
-__device__ __forceinline__ void ering_issue(EmisRing& ring, int slot, const double* __restrict__ src /*row 0, this lane*/, int nrows, int lane) {
+template <bool FULL>
+__device__ __forceinline__ void ering_issue(EmisRing& ring, int slot, const double2* __restrict__ src /*row 0, this lane*/, int nrows, int lane) {
+#if E_RING_PLANAR
+    const unsigned d = (unsigned)__cvta_generic_to_shared(&ring.r[slot][0][0][lane]);
+    const double* s8 = reinterpret_cast<const double*>(src);
 #pragma unroll
     for (int u = 0; u < E_PF; ++u) {
-        if (u < nrows) {
-            unsigned d = (unsigned)__cvta_generic_to_shared(&ring.r[slot][u][lane]);
-            asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(d), "l"(src + u * 32));
+        if (FULL || u < nrows) {
+            asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(d + u * 512), "l"(s8 + u * EW_ROW));
+            asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(d + u * 512 + 256), "l"(s8 + u * EW_ROW + 1));
         }
     }
+#else
+    const unsigned d = (unsigned)__cvta_generic_to_shared(&ring.r[slot][0][lane]);
+#pragma unroll
+    for (int u = 0; u < E_PF; ++u) {
+        if (FULL || u < nrows) asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" ::"r"(d + u * 512), "l"(src + u * 32));
+    }
+#endif
     asm volatile("cp.async.commit_group;");
 }
 
 // Forward sweep of the conditional chain for the 32 reads of a chunk, carrying the tangents (∂a,∂b,∂c).
 // Groups are processed E_PF at a time: while one block of E_PF emission rows is consumed from the ring the next one is in
-// flight; the message is rescaled every second group (|LLR| ≤ 300 keeps two steps inside the double range).
+// flight; the state is rescaled by a power of two between blocks.
 template <bool BPOS>
-__device__ __forceinline__ void estep_chunk(SiteTile& st, EmisRing& ring, int L, int lane, const double* __restrict__ na_g,
+__device__ __forceinline__ void estep_chunk(SiteTileK& st, EmisRing& ring, int L, int lane, const double* __restrict__ na_g,
                                             const double* __restrict__ nb_g, const double* __restrict__ invd_g,
-                                            const double* __restrict__ p /*emission weight of (group l, this lane's read) at p[l*32]*/,
+                                            const double2* __restrict__ p /*(r, 1/r) of (group l, this lane's read) at p[l*32]*/,
                                             double a, double b, double cabs, double out[3]) {
     EState s{1.0, 1.0, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0};
-    double sc = 1.0;
-    const int Lfull = L & ~(E_PF - 1);
-    const int ngrp = Lfull / E_PF;
-    // in flight from the start: the first block of rows (slot 0) and the chain tail (slot 2)
-    ering_issue(ring, 0, p, Lfull > 0 ? E_PF : 0, lane);
-    ering_issue(ring, 2, p + (size_t)Lfull * 32, L - Lfull, lane);
+    if (L >= E_PF) ering_issue<true>(ring, 0, p, E_PF, lane); else ering_issue<false>(ring, 0, p, L, lane);
     int g = 0;                                          // index of the block of E_PF groups being consumed
     for (int l0 = 0; l0 < L; l0 += TILE) {
         const int n = min(TILE, L - l0);
+        unsigned m0, m1;
         __syncwarp();
-        fill_tile(st, l0, n, lane, na_g, nb_g, invd_g, a, b, cabs, BPOS);
+        fill_tile_k(st, l0, n, lane, na_g, nb_g, invd_g, a, b, cabs, BPOS, m0, m1);
         __syncwarp();
-        const int nfull = n & ~(E_PF - 1);
-        for (int j0 = 0; j0 < nfull; j0 += E_PF, ++g) {
-            // next block in flight, then wait until at most that one is pending: block g (and the tail) have landed
-            ering_issue(ring, (g + 1) & 1, p + (size_t)(g + 1) * E_PF * 32, (g + 1 < ngrp) ? E_PF : 0, lane);
+#pragma unroll 1
+        for (int j0 = 0; j0 < n; j0 += E_PF, ++g) {
+            // next block in flight, then wait until at most that one is pending: block g has landed
+            const int left = L - (g + 1) * E_PF;        // groups after this block
+            const double2* nxt = p + (size_t)(g + 1) * E_PF * 32;
+            if (left >= E_PF) ering_issue<true>(ring, (g + 1) & 1, nxt, E_PF, lane); else ering_issue<false>(ring, (g + 1) & 1, nxt, left, lane);
             asm volatile("cp.async.wait_group 1;");
+            if (g > 0) estep_rescale(s);
+            // (read back from lane 0: a value the compiler can see is warp-uniform, so the per-group branches below are plain
+            // uniform branches without reconvergence barriers)
+            const unsigned bits = __shfl_sync(0xffffffffu, ((j0 & 32) ? m1 : m0) >> (j0 & 31), 0);
             const int slot = g & 1;
+            if (n - j0 >= E_PF) {
 #pragma unroll
-            for (int u = 0; u < E_PF; ++u) {
-                estep_site<BPOS>(s, st, j0 + u, ring.r[slot][u][lane], sc);
-                if (u & 1) sc = cpn_inv_pow2_of(s.fp + s.fm); else sc = 1.0;
-            }
-        }
-        // tail of the chain (fewer than E_PF groups left; only the last tile has one)
-        if (nfull < n) {
-            asm volatile("cp.async.wait_group 0;");
-#pragma unroll
-            for (int u = 0; u < E_PF - 1; ++u) {
-                const int j = nfull + u;
-                if (j < n) {
-                    estep_site<BPOS>(s, st, j, ring.r[2][u][lane], sc);
-                    sc = cpn_inv_pow2_of(s.fp + s.fm);
+                for (int u = 0; u < E_PF; ++u) {
+                    if (bits & (1u << u)) estep_site<BPOS, true>(s, st, j0 + u, ERING_RI(ring, slot, u, lane));
+                    else estep_site<BPOS, false>(s, st, j0 + u, ERING_R(ring, slot, u, lane));
+                }
+            } else {                                    // last block of the chain, fewer than E_PF groups
+#pragma unroll 1
+                for (int u = 0; u < n - j0; ++u) {
+                    if ((bits >> u) & 1u) estep_site<BPOS, true>(s, st, j0 + u, ERING_RI(ring, slot, u, lane));
+                    else estep_site<BPOS, false>(s, st, j0 + u, ERING_R(ring, slot, u, lane));
                 }
             }
         }
     }
     asm volatile("cp.async.wait_group 0;");
+    double inv = 1.0 / (s.fp + s.fm);
+    out[0] = (s.gap + s.gam) * inv;
+    out[1] = (s.gbp + s.gbm) * inv;
+    out[2] = (s.gcp + s.gcm) * inv;
+}
+
+// The same sweep with a rescale after every group and plain loads: for instances whose |LLR| or |β| bound is too large for
+// E_PF unscaled groups (rare: real and simulated log-likelihood ratios are a few tens at most).
+template <bool BPOS>
+__device__ __noinline__ void estep_chunk_slow(SiteTileK& st, int L, int lane, const double* __restrict__ na_g,
+                                              const double* __restrict__ nb_g, const double* __restrict__ invd_g,
+                                              const double2* __restrict__ p, double a, double b, double cabs, double out[3]) {
+    EState s{1.0, 1.0, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0};
+    for (int l0 = 0; l0 < L; l0 += TILE) {
+        const int n = min(TILE, L - l0);
+        unsigned m0, m1;
+        __syncwarp();
+        fill_tile_k(st, l0, n, lane, na_g, nb_g, invd_g, a, b, cabs, BPOS, m0, m1);
+        __syncwarp();
+#pragma unroll 1
+        for (int j = 0; j < n; ++j) {
+            const double2 rr = __ldg(p + (size_t)(l0 + j) * 32);
+            if ((((j & 32) ? m1 : m0) >> (j & 31)) & 1u) estep_site<BPOS, true>(s, st, j, rr.y);
+            else estep_site<BPOS, false>(s, st, j, rr.x);
+            estep_rescale(s);
+        }
+    }
     double inv = 1.0 / (s.fp + s.fm);
     out[0] = (s.gap + s.gam) * inv;
     out[1] = (s.gbp + s.gbm) * inv;
@@ -291,7 +415,7 @@ __global__ void __launch_bounds__(E_WARPS * 32, E_BLOCKS) k_estep(int n_items, c
                                                                    const double* __restrict__ phil /*[3][cap] by list position*/, int64_t cap,
                                                                    RegionTables rt, int64_t NI, double* __restrict__ ES /*[3][NI]*/,
                                                                    const int* __restrict__ n_dev /*null, or the true item count*/) {
-    __shared__ SiteTile tiles[E_WARPS];
+    __shared__ SiteTileK tiles[E_WARPS];
     __shared__ EmisRing rings[E_WARPS];
     int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
     int item = blockIdx.x * E_WARPS + w;
@@ -302,11 +426,15 @@ __global__ void __launch_bounds__(E_WARPS * 32, E_BLOCKS) k_estep(int n_items, c
     const int4 d0 = __ldg(dq);
     const longlong2 d1 = __ldg(reinterpret_cast<const longlong2*>(dq + 1));
     double a = phil[item], b = phil[cap + item], c = phil[2 * cap + item];
-    const int inst = d0.x, L = d0.y, M = d0.z, ridx = d0.w;
+    // L, M and the path flag are the same in every lane; reading them back from lane 0 lets the compiler see that (loop
+    // counters and the per-group branch then live in uniform registers and the branches need no reconvergence barriers)
+    const int inst = d0.x, L = __shfl_sync(0xffffffffu, d0.y, 0), Mw = __shfl_sync(0xffffffffu, d0.z, 0), ridx = d0.w;
+    const int M = Mw & ((1 << ITEM_SLOW_BIT) - 1);
+    const bool slow = (Mw >> ITEM_SLOW_BIT) & 1;
     const int64_t g0 = d1.x;
     bool bpos = __double2hiint(c) >= 0;
     double cabs = fabs(c);
-    const double* ew_r = rt.ew + d1.y;
+    const double2* ew_r = reinterpret_cast<const double2*>(rt.ew + d1.y);
     double acc0 = 0, acc1 = 0, acc2 = 0;
     int nchunk = (M + 31) >> 5;
     for (int ch = 0; ch < nchunk; ++ch) {
@@ -314,9 +442,14 @@ __global__ void __launch_bounds__(E_WARPS * 32, E_BLOCKS) k_estep(int n_items, c
         // this lane's read: lane of chunk ch, or — in a view — the pooled read the view's index row names
         int q = ch * 32 + lane;
         if (ridx >= 0) q = __ldg(rt.ridx + ((size_t)(ridx + ch) << 5) + lane);
-        const double* p = ew_r + (size_t)(q >> 5) * L * 32 + (q & 31);
-        if (bpos) estep_chunk<true>(tiles[w], rings[w], L, lane, rt.na + g0, rt.nb + g0, rt.invd + g0, p, a, b, cabs, o);
-        else estep_chunk<false>(tiles[w], rings[w], L, lane, rt.na + g0, rt.nb + g0, rt.invd + g0, p, a, b, cabs, o);
+        const double2* p = ew_r + (size_t)(q >> 5) * L * 32 + (q & 31);
+        if (!slow) {
+            if (bpos) estep_chunk<true>(tiles[w], rings[w], L, lane, rt.na + g0, rt.nb + g0, rt.invd + g0, p, a, b, cabs, o);
+            else estep_chunk<false>(tiles[w], rings[w], L, lane, rt.na + g0, rt.nb + g0, rt.invd + g0, p, a, b, cabs, o);
+        } else {
+            if (bpos) estep_chunk_slow<true>(tiles[w], L, lane, rt.na + g0, rt.nb + g0, rt.invd + g0, p, a, b, cabs, o);
+            else estep_chunk_slow<false>(tiles[w], L, lane, rt.na + g0, rt.nb + g0, rt.invd + g0, p, a, b, cabs, o);
+        }
         bool live = ch * 32 + lane < M;
         acc0 += cpn_warp_sum(live ? o[0] : 0.0);
         acc1 += cpn_warp_sum(live ? o[1] : 0.0);
@@ -337,9 +470,12 @@ __global__ void k_make_desc(int n_items, const int* __restrict__ items, int n_in
     int inst = items ? items[i] : i;
     RegionDesc rd = rdesc[inst / n_init];
     ItemDesc d;
-    d.inst = inst; d.L = rd.L; d.M = rd.M; d.ridx = rd.ridx; d.g0 = rd.g0; d.ew_off = rd.ew_off;
+    const double c = phi[2 * NI + inst];
+    // rescale policy of the E-step for this instance (see estep_site): negated comparisons, so NaN bounds or a NaN c choose slow
+    const bool fast = (rd.llrmax <= E_FAST_LLR) && (fabs(c) * (double)rd.idmax <= (double)E_FAST_BETA);
+    d.inst = inst; d.L = rd.L; d.M = rd.M | (fast ? 0 : (1 << ITEM_SLOW_BIT)); d.ridx = rd.ridx; d.g0 = rd.g0; d.ew_off = rd.ew_off;
     desc[i] = d;
-    phil[i] = phi[inst]; phil[cap + i] = phi[NI + inst]; phil[2 * cap + i] = phi[2 * NI + inst];
+    phil[i] = phi[inst]; phil[cap + i] = phi[NI + inst]; phil[2 * cap + i] = c;
 }
 
 // ---------------------------------------------------------------------------------------------------
@@ -349,7 +485,7 @@ __global__ void k_make_desc(int n_items, const int* __restrict__ items, int n_in
 template <bool BPOS>
 __device__ __forceinline__ double logz_chunk(SiteTile& st, int L, int lane, const double* __restrict__ na_g,
                                              const double* __restrict__ nb_g, const double* __restrict__ invd_g,
-                                             const double* __restrict__ p /*this lane's read, row stride 32; null → r = 1*/, double a,
+                                             const double* __restrict__ p /*r of this lane's read, row stride EW_ROW; null → r = 1*/, double a,
                                              double b, double cabs) {
     double fp = 1.0, fm = 1.0, sc = 1.0;           // all-ones message; group 0 carries t = 0 (see fill_tile)
     int esum = 0, e;
@@ -363,7 +499,7 @@ __device__ __forceinline__ double logz_chunk(SiteTile& st, int L, int lane, cons
         for (int j0 = 0; j0 < n; j0 += 8) {
             double rr[8];
 #pragma unroll
-            for (int k = 0; k < 8; ++k) rr[k] = (p && j0 + k < n) ? __ldg(p + (size_t)(l0 + j0 + k) * 32) : 1.0;
+            for (int k = 0; k < 8; ++k) rr[k] = (p && j0 + k < n) ? __ldg(p + (size_t)(l0 + j0 + k) * EW_ROW) : 1.0;
 #pragma unroll
             for (int k = 0; k < 8; ++k) {
                 const int j = j0 + k;
@@ -414,7 +550,7 @@ __global__ void __launch_bounds__(E_WARPS * 32) k_score(int n_items, const int* 
         int q = ch * 32 + lane;
         const bool live = (int64_t)ch * 32 + lane < M;
         if (rd.ridx >= 0) q = __ldg(rt.ridx + ((size_t)(rd.ridx + ch) << 5) + lane);
-        const double* p = ew_r + (size_t)(q >> 5) * L * 32 + (q & 31);
+        const double* p = ew_r + (size_t)(q >> 5) * L * EW_ROW + 2 * (q & 31);
         if (spare && ch == nchunk - 1 && lane == 31) p = nullptr;
         double lz = bpos ? logz_chunk<true>(tiles[w], L, lane, rt.na + g0, rt.nb + g0, rt.invd + g0, p, a, b, cabs)
                          : logz_chunk<false>(tiles[w], L, lane, rt.na + g0, rt.nb + g0, rt.invd + g0, p, a, b, cabs);
@@ -1304,6 +1440,12 @@ __global__ void k_unpack3(int64_t R, const double* __restrict__ in /*[3][R]*/, d
 // ---------------------------------------------------------------------------------------------------
 // host side
 // ---------------------------------------------------------------------------------------------------
+// k_estep keeps E_BLOCKS blocks of 42 KB of shared memory resident per SM: ask for the shared-memory carveout that allows it
+// (per device; the call is cheap and idempotent).
+static cudaError_t estep_prepare() {
+    return cudaFuncSetAttribute(k_estep, cudaFuncAttributePreferredSharedMemoryCarveout, (int)cudaSharedmemCarveoutMaxShared);
+}
+
 struct PackedRegions {
     DevIn<int64_t> grp_off, read_off;
     DevIn<double> Nl, rho, dl, lu, lm;
@@ -1363,7 +1505,7 @@ int pack_regions(cpn_ctx* ctx, PackedRegions& pk, bool on_device, bool with_read
         CPN_ARG(ctx, !with_reads || M >= 1, "every region needs at least one read");
         int64_t nch = (M + 31) / 32;
         h_obs[r + 1] = h_obs[r] + M * L;
-        h_ew[r + 1] = h_ew[r] + nch * L * 32;
+        h_ew[r + 1] = h_ew[r] + nch * L * EW_ROW;
         h_rb[r + 1] = h_rb[r] + nch * 32;
     }
     pk.sumL = pk.h_grp_off[R];
@@ -1387,7 +1529,7 @@ int pack_regions(cpn_ctx* ctx, PackedRegions& pk, bool on_device, bool with_read
         for (int64_t r = 0; r < R; ++r) {
             h_desc[r].g0 = pk.h_grp_off[r]; h_desc[r].ew_off = h_ew[r]; h_desc[r].rb_off = h_rb[r];
             h_desc[r].L = (int32_t)(pk.h_grp_off[r + 1] - pk.h_grp_off[r]); h_desc[r].M = (int32_t)(pk.h_read_off[r + 1] - pk.h_read_off[r]);
-            h_desc[r].ridx = -1; h_desc[r].pad = 0;
+            h_desc[r].ridx = -1; h_desc[r].pad = 0; h_desc[r].llrmax = 0.f; h_desc[r].idmax = 0.f;
         }
         CPN_CUDA(ctx, pk.read_off.bind(read_off, R + 1, offs_dev, s));
         CPN_CUDA(ctx, pk.obs_off.upload(h_obs.data(), R + 1, s));
@@ -1403,7 +1545,7 @@ int pack_regions(cpn_ctx* ctx, PackedRegions& pk, bool on_device, bool with_read
         trace(ctx, "pk-lm");
         { KTimer kt(ctx, CPN_K_PREP);
           k_prep_emis<<<blocks_for(R * 32, 128), 128, 0, s>>>(R, pk.grp_off.p, pk.read_off.p, pk.obs_off.p, pk.lu.p, pk.lm.p, pk.ew_off.p,
-                                                              pk.rb_off.p, pk.ew.p, pk.rb.p); }
+                                                              pk.rb_off.p, pk.invd.p, pk.ew.p, pk.rb.p, pk.rdesc.p); }
         // the raw emissions are not needed once packed: hand the memory back (stream-ordered) before the EM loop
         pk.lm.own.release();
         pk.lu.own.release();
@@ -1483,7 +1625,7 @@ int fit_impl(cpn_ctx* ctx, bool on_device, int64_t R, const int64_t* grp_off, co
     LaunchCounter lc(ctx);
     if (R == 0) { ctx->last_ms = 0; return CPN_OK; }
     cudaStream_t s = ctx->stream;
-    CPN_CUDA(ctx, cudaEventRecord(ctx->ev0, s));
+    if (!pre) CPN_CUDA(ctx, cudaEventRecord(ctx->ev0, s));      // with `pre` the caller owns the timing events
     {
         StagedBatch local;
         StagedBatch* sb = pre ? pre : &local;
@@ -1522,6 +1664,7 @@ int fit_impl(cpn_ctx* ctx, bool on_device, int64_t R, const int64_t* grp_off, co
         CPN_CUDA(ctx, alive.alloc(NI, s));
         CPN_CUDA(ctx, blk_cnt.alloc((NI + CP_TILE - 1) / CP_TILE, s));
         int ws_blocks_per_sm = 1;
+        CPN_CUDA(ctx, estep_prepare());
         CPN_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ws_blocks_per_sm, k_mstep_ws, M_THREADS, 0));
         if (ws_blocks_per_sm < 1) ws_blocks_per_sm = 1;
         // Regions ordered by group count (counting sort) so the 32 lanes of an M-step warp walk chains of
@@ -1739,7 +1882,7 @@ __global__ void k_two_samp_views(const TsRegion* __restrict__ regs, const Region
     for (; c1 < t.rows1 * 32; ++c1) r1[c1] = 0;
     for (; c2 < t.rows2 * 32; ++c2) r2[c2] = 0;
     RegionDesc d;
-    d.g0 = b.g0; d.ew_off = b.ew_off; d.rb_off = b.rb_off; d.L = b.L; d.pad = 0;
+    d.g0 = b.g0; d.ew_off = b.ew_off; d.rb_off = b.rb_off; d.L = b.L; d.pad = 0; d.llrmax = b.llrmax; d.idmax = b.idmax;
     d.M = t.n1; d.ridx = (int32_t)row;
     vdesc[v] = d;
     d.M = t.n - t.n1; d.ridx = (int32_t)(row + t.rows1);
@@ -2201,6 +2344,7 @@ int cpn_estep_batch(cpn_ctx* ctx, int64_t R, const int64_t* grp_off, const doubl
         { KTimer kt(ctx, CPN_K_PREP); k_pack_phi<<<blocks_for(R, 256), 256, 0, s>>>(R, d_phi_in.p, d_phi.p); }
         DevBuf<ItemDesc> idesc;
         DevBuf<double> phil;
+        CPN_CUDA(ctx, estep_prepare());
         CPN_CUDA(ctx, idesc.alloc(R, s)); CPN_CUDA(ctx, phil.alloc(3 * R, s));
         { KTimer kt(ctx, CPN_K_PREP);
           k_make_desc<<<blocks_for(R, 256), 256, 0, s>>>((int)R, nullptr, 1, pk.rt.rdesc, d_phi.p, R, idesc.p, phil.p, R, nullptr); }
