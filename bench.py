@@ -50,6 +50,9 @@ C_S, C_G = 60.0, 30.0   # summaries: per CpG, per (sub-region, CpG)  (SURVEY.md 
 C_CMD = 90.0        # per CpG of one mixture chain of comp_cmd (k_cmd_lane: 2 exp × 20 + forward message 8 + 2×2 product 24 + offsets/rescale 18)
 HBM_PEAK = 6551.7   # GB/s, MEASURED_PEAKS.json
 BOX = (20.0, 150.0, 50.0)
+CPU_REGIONS_PER_THREAD = 16   # CPU legs of the fit workloads: regions per host thread and step (one region ≈ 1 s of one core; 16 per
+                              # thread keeps the end-of-step imbalance of the dynamic schedule near 1/16 for both the cpu_baseline
+                              # block and the --impl reference arm, which therefore time the same sample the same way)
 WORKLOADS = ("chr22", "targeted", "whole-genome", "two-sample", "group")
 
 
@@ -531,10 +534,7 @@ def bench_fit(env):
         import oracle_py as orc
         import parity_report as pr
         threads = os.cpu_count() or 1
-        probe = min(nb.R, threads)
-        t1 = cpu_fit_step(orc, nb, arrays, np.arange(probe), n_init, max_iters, threads)[0]
-        n_s = args.cpu_sample or int(max(8 * threads, min(4096, threads * round(12.0 / max(t1, 1e-3)))))
-        n_s = min(n_s, nb.R)
+        n_s = min(args.cpu_sample or CPU_REGIONS_PER_THREAD * threads, nb.R)      # the same sample rule as the --impl reference arm
         idx = np.arange(n_s)
         tc, fit_c, rows_c, so_c = cpu_fit_step(orc, nb, arrays, idx, n_init, max_iters, threads)
         line["cpu_baseline"] = {"value": n_s / tc, "unit": UNIT, "cores": threads, "kind": "port", "mstep": "finite differences of finite differences (the reference's NLsolve path)",
@@ -906,7 +906,7 @@ def reference_arm(args):
             nb, arrays = build_workload(cpn, orc, len(phi_true), args.reads, n_init, cpn.simulations.MASTER_SEED, subreg=351, layouts=lay, phi_true=phi_true)
             n_s = nb.R
         else:
-            n_s = args.cpu_sample or 8 * threads
+            n_s = args.cpu_sample or CPU_REGIONS_PER_THREAD * threads
             nb, arrays = build_workload(cpn, orc, max(n_s, 64), args.reads, n_init, cpn.simulations.MASTER_SEED)
         idx = np.arange(n_s)
         run = lambda n: cpu_fit_step(orc, nb, arrays, idx[:n], n_init, max_iters, threads)[0]      # noqa: E731

@@ -62,8 +62,7 @@ struct __align__(32) ItemDesc { int inst, L, M, ridx; int64_t g0, ew_off; };
 // they bound how fast an E-step message can grow or shrink per group, i.e. how many groups may pass between two rescalings.
 struct __align__(16) RegionDesc { int64_t g0, ew_off, rb_off; int32_t L, M, ridx; float llrmax, idmax; int32_t pad; };
 static_assert(sizeof(RegionDesc) == 48, "RegionDesc layout");
-constexpr int ITEM_SLOW_BIT = 30;  // ItemDesc::M bit: this instance must rescale every group (k_make_desc decides)
-constexpr int EW_ROW = 64;         // doubles per emission row: 32 lanes x (r, 1/r)
+constexpr int EW_ROW = 32;         // doubles per emission row: one likelihood ratio per lane
 
 struct RegionTables {
     // per group (offsets grp_off): N_l, N_l·ρ_l and 1/d_l (coupling l→l+1; entry L-1 unused)
@@ -76,6 +75,7 @@ struct RegionTables {
     const int64_t* ew_off;     // [R] start of the region's block: [chunk][l][32]
     const int64_t* rb_off;     // [R] start of the per-read base (Σ_obs log p(y|−1)) block: [chunk][32]
     const double *ew, *rb;
+    const double* ewi;         // 1/r, same layout as ew (the E-step reads it for blocks of groups whose heavier state is x=+1)
     const int32_t* ridx;       // read-id rows of views (null when there are none)
 };
 
@@ -113,14 +113,14 @@ __global__ void k_prep_sites(int64_t R, const int64_t* __restrict__ grp_off, con
     }
 }
 
-// Packs emissions (structures.jl:121-128: obs, log_pyx_u, log_pyx_m) as likelihood ratios, lanes = reads: per (group, read) the
-// pair (r, 1/r), r = exp(log p(y|+1) − log p(y|−1)) — the E-step multiplies by whichever of the two keeps the heavier state of the
-// group at weight 1 — and per region the bounds RegionDesc::llrmax / idmax.
+// Packs emissions (structures.jl:121-128: obs, log_pyx_u, log_pyx_m) as likelihood ratios r = exp(log p(y|+1) − log p(y|−1))
+// and their reciprocals (two planes of the same layout), lanes = reads, and records per region the bounds
+// RegionDesc::llrmax / idmax.
 // |LLR| is clamped at 300 with the dropped mass (< e^-300 relative) moved into the per-read base term.
 __global__ void k_prep_emis(int64_t R, const int64_t* __restrict__ grp_off, const int64_t* __restrict__ read_off,
                             const int64_t* __restrict__ obs_off, const double* __restrict__ lu, const double* __restrict__ lm,
                             const int64_t* __restrict__ ew_off, const int64_t* __restrict__ rb_off, const double* __restrict__ invd,
-                            double* __restrict__ ew, double* __restrict__ rb, RegionDesc* __restrict__ rdesc) {
+                            double* __restrict__ ew, double* __restrict__ ewi, double* __restrict__ rb, RegionDesc* __restrict__ rdesc) {
     int64_t warp = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5;
     int lane = threadIdx.x & 31;
     if (warp >= R) return;
@@ -134,7 +134,8 @@ __global__ void k_prep_emis(int64_t R, const int64_t* __restrict__ grp_off, cons
     for (int64_t ch = 0; ch < nchunk; ++ch) {
         int64_t m = ch * 32 + lane;
         double base = 0.0;
-        double2* dst = reinterpret_cast<double2*>(ew + ew_off[warp] + ch * L * EW_ROW) + lane;
+        double* dst = ew + ew_off[warp] + ch * L * 32 + lane;
+        double* dsti = ewi + ew_off[warp] + ch * L * 32 + lane;
         for (int64_t l = 0; l < L; ++l) {
             double r = 1.0, ri = 1.0;
             if (m < M) {
@@ -148,7 +149,8 @@ __global__ void k_prep_emis(int64_t R, const int64_t* __restrict__ grp_off, cons
                     dmax = fmax(dmax, fabs(d));          // a NaN likelihood leaves dmax alone; the NaN itself poisons the fit
                 }
             }
-            dst[l * 32] = make_double2(r, ri);
+            dst[l * 32] = r;
+            dsti[l * 32] = ri;
         }
         rb[rb_off[warp] + ch * 32 + lane] = base;
     }
@@ -168,103 +170,85 @@ __global__ void k_prep_emis(int64_t R, const int64_t* __restrict__ grp_off, cons
 // ---------------------------------------------------------------------------------------------------
 // shared: stage the per-group potentials of one instance for groups [l0, l0+n)
 // ---------------------------------------------------------------------------------------------------
-__device__ __forceinline__ void fill_tile(SiteTile& st, int l0, int n, int lane, const double* __restrict__ na_g,
+struct TileRegs { double na[TILE / 32], nb[TILE / 32], id[TILE / 32], alpha[TILE / 32]; };
+// first half: the loads of a tile (lanes strided over its groups) and the mask of groups with α_l ≥ 0 (bit j of m[j / 32])
+__device__ __forceinline__ void tile_load(TileRegs& tr, int l0, int n, int lane, const double* __restrict__ na_g,
                                           const double* __restrict__ nb_g, const double* __restrict__ invd_g, double a, double b,
-                                          double cabs, bool bpos) {
-    // lanes are strided over the groups of the tile; all loads of a lane are issued before any exponential
+                                          unsigned& m0, unsigned& m1) {
     constexpr int K = TILE / 32;
-    double na[K], nb[K], id[K];
+    static_assert(K == 2, "two mask words");
 #pragma unroll
     for (int k = 0; k < K; ++k) {
         const int j = lane + 32 * k, l = l0 + j;
         const bool in = j < n;
-        na[k] = in ? na_g[l] : 0.0;
-        nb[k] = in ? nb_g[l] : 0.0;
-        id[k] = (in && l > 0) ? invd_g[l - 1] : 0.0;
+        tr.na[k] = in ? na_g[l] : 0.0;
+        tr.nb[k] = in ? nb_g[l] : 0.0;
+        tr.id[k] = (in && l > 0) ? invd_g[l - 1] : 0.0;
     }
+#pragma unroll
+    for (int k = 0; k < K; ++k) {
+        const int j = lane + 32 * k;
+        tr.alpha[k] = fma(b, tr.nb[k], a * tr.na[k]);
+        const unsigned mk = __ballot_sync(0xffffffffu, j < n && __double2hiint(tr.alpha[k]) >= 0);
+        if (k == 0) m0 = mk; else m1 = mk;
+    }
+}
+// second half: the exponentials, and the potentials into shared memory
+__device__ __forceinline__ void tile_store(SiteTile& st, const TileRegs& tr, int l0, int n, int lane, double cabs, bool bpos) {
+    constexpr int K = TILE / 32;
 #pragma unroll
     for (int k = 0; k < K; ++k) {
         const int j = lane + 32 * k, l = l0 + j;
         if (j < n) {
-            double alpha = fma(b, nb[k], a * na[k]);
-            double e = cpn_exp_neg(-2.0 * fabs(alpha));
-            bool pos = __double2hiint(alpha) >= 0;
+            double e = cpn_exp_neg(-2.0 * fabs(tr.alpha[k]));
+            bool pos = __double2hiint(tr.alpha[k]) >= 0;
             st.w[j] = make_double2(pos ? e : 1.0, pos ? 1.0 : e);
             // group 0 has no incoming coupling: t = 0 makes the generic step reproduce f = φ_0 from the all-ones message
-            st.tn[j] = make_double2((l > 0) ? cpn_exp_neg(-2.0 * (cabs * id[k])) : 0.0, na[k]);
-            st.bd[j] = make_double2(nb[k], bpos ? id[k] : -id[k]);
+            st.tn[j] = make_double2((l > 0) ? cpn_exp_neg(-2.0 * (cabs * tr.id[k])) : 0.0, tr.na[k]);
+            st.bd[j] = make_double2(tr.nb[k], bpos ? tr.id[k] : -tr.id[k]);
         }
     }
+}
+__device__ __forceinline__ void fill_tile(SiteTile& st, int l0, int n, int lane, const double* __restrict__ na_g,
+                                          const double* __restrict__ nb_g, const double* __restrict__ invd_g, double a, double b,
+                                          double cabs, bool bpos) {
+    TileRegs tr;
+    unsigned m0, m1;
+    tile_load(tr, l0, n, lane, na_g, nb_g, invd_g, a, b, m0, m1);
+    tile_store(st, tr, l0, n, lane, cabs, bpos);
 }
 
 // ---------------------------------------------------------------------------------------------------
 // E-step: ES = Σ_m ∇_ϕ log Zc_m(ϕ)   (≡ get_ess ∘ get_cond_exs_log)
 // ---------------------------------------------------------------------------------------------------
-// The statistics are RATIOS of the tangent sums to the message sum, so a chain step may be normalised by anything that is
-// common to the eight state values.  Each step is normalised by the potential of the group's HEAVIER state (α_l ≥ 0: x=+1,
-// weight e^{α}·r; α_l < 0: x=−1, weight e^{−α}): that state's four values take no multiplication at all, the other four
-// are multiplied by κ = e^{−2|α_l|}·r^{∓1} ≤ e^{|LLR|}.  21 FP64 instructions per (read, group) instead of 26.5, and the
-// power-of-two rescale moves out of the step: the heavier component never shrinks by more than t = e^{−2|β|} per group and
-// nothing grows by more than 2·max(1, κ), so with |LLR| ≤ 80 and |β| ≤ 40 eight groups fit between two rescalings with 60
-// binary orders of magnitude to spare on either side; instances outside those bounds (RegionDesc::llrmax/idmax, |c|) take
-// estep_chunk_slow, which rescales after every group.
+// One forward sweep for the 32 reads of a chunk.  BPOS = (c ≥ 0).  (u,v) below are the source states that
+// enter x'=+1 with weight 1 and t respectively; for c<0 the roles of same/opposite swap.
+//
+// The statistics are RATIOS of the tangent sums to the message sum, so the common scale of the eight state values is free.
+// With potentials relative to their larger entry a step multiplies the larger state value by at most 2·max(1, r) and by at
+// least t·min(1, r) (r = e^{LLR}, t = e^{−2|β|}): with B = max|LLR| + 2·max|β| the scale moves by at most e^{±(B + ln 2)} per
+// group.  k_make_desc turns the region's bounds (RegionDesc::llrmax / idmax) and the instance's |c| into a rescale period:
+// every second block of E_PF groups (B ≤ 40), every block (B ≤ 80) — 16 resp. 8 groups stay within e^{±650} — or, for anything
+// wilder, the plain loop estep_chunk_slow with a rescale after every group.  Real and simulated nanopolish LLRs are a few
+// tens at most, so the chain step itself carries no rescale arithmetic: 24 FP64 instructions per (read, group).
 #ifndef E_PF_N
 #define E_PF_N 8
 #endif
-constexpr int E_PF = E_PF_N;       // groups per block of emission rows (ring slot) = groups between two rescalings
-constexpr float E_FAST_LLR = 80.0f, E_FAST_BETA = 40.0f;
-static_assert(TILE % E_PF == 0 && E_PF <= 32 && (E_PF & (E_PF - 1)) == 0, "blocks of groups must tile a shared-memory tile");
+constexpr int E_PF = E_PF_N;       // groups per block of emission rows (ring slot)
+constexpr float E_BOUND_1 = 80.0f, E_BOUND_2 = 40.0f;     // bound on B for a rescale every block / every second block
+constexpr int ITEM_MODE_SHIFT = 28;                       // ItemDesc::M bits 28-29: 0 slow path, 1 every block, 2 every second block
+constexpr int ITEM_M_MASK = (1 << ITEM_MODE_SHIFT) - 1;
 
 struct EState { double fp, fm, gap, gam, gbp, gbm, gcp, gcm; };
 
-// Per-group potentials of one EM instance for the E-step: (e^{−2|α|}, t), (N_l, N_lρ_l), ±1/d_l — two LDS.128 and one
-// LDS.64 per chain step, all lanes reading the same address (broadcast).  The sign of α_l travels as a bit mask.
-struct SiteTileK {
-    double2 et[TILE];
-    double2 nn[TILE];
-    double sd[TILE];
-};
-
-// Stages groups [l0, l0+n) (lanes strided over the groups; all loads of a lane are issued before any exponential) and returns
-// the mask of groups with α_l ≥ 0 (bit j of m[j / 32]).
-__device__ __forceinline__ void fill_tile_k(SiteTileK& st, int l0, int n, int lane, const double* __restrict__ na_g,
-                                            const double* __restrict__ nb_g, const double* __restrict__ invd_g, double a, double b,
-                                            double cabs, bool bpos, unsigned& m0, unsigned& m1) {
-    constexpr int K = TILE / 32;
-    static_assert(K == 2, "two mask words");
-    double na[K], nb[K], id[K];
-#pragma unroll
-    for (int k = 0; k < K; ++k) {
-        const int j = lane + 32 * k, l = l0 + j;
-        const bool in = j < n;
-        na[k] = in ? na_g[l] : 0.0;
-        nb[k] = in ? nb_g[l] : 0.0;
-        id[k] = (in && l > 0) ? invd_g[l - 1] : 0.0;
-    }
-#pragma unroll
-    for (int k = 0; k < K; ++k) {
-        const int j = lane + 32 * k, l = l0 + j;
-        const bool in = j < n;
-        double alpha = fma(b, nb[k], a * na[k]);
-        const unsigned mk = __ballot_sync(0xffffffffu, in && __double2hiint(alpha) >= 0);
-        if (k == 0) m0 = mk; else m1 = mk;
-        if (in) {
-            // group 0 has no incoming coupling: t = 0 makes the generic step reproduce f = φ_0 from the all-ones message
-            st.et[j] = make_double2(cpn_exp_neg(-2.0 * fabs(alpha)), (l > 0) ? cpn_exp_neg(-2.0 * (cabs * id[k])) : 0.0);
-            st.nn[j] = make_double2(na[k], nb[k]);
-            st.sd[j] = bpos ? id[k] : -id[k];
-        }
-    }
-}
-
-// One chain step for one read.  BPOS = (c ≥ 0): (u,v) are the source states entering x'=+1 with weight 1 and t (for c<0 the
-// roles of aligned/opposite swap).  APOS = (α_l ≥ 0): x'=+1 is the heavier state and stays unmultiplied; `rsel` is 1/r then,
-// r otherwise.
-template <bool BPOS, bool APOS>
-__device__ __forceinline__ void estep_site(EState& s, const SiteTileK& st, int j, double rsel) {
-    const double2 et = st.et[j], nn = st.nn[j];
-    const double sinvd = st.sd[j];
-    const double k = et.x * rsel, t = et.y, na = nn.x, nb = nn.y;
+// One chain step for one read.  (u,v) are the source states entering x'=+1 with weight 1 and t; for c<0 the roles of
+// aligned/opposite swap (BPOS=false).  SGN = 0: any α_l, both states multiplied by their relative potential (r rides on
+// x'=+1).  SGN = +1 / −1: α_l ≥ 0 / α_l < 0 is known, the step is normalised by the potential of the heavier state, which
+// therefore takes no multiplication at all; the other one is multiplied by κ = e^{−2|α_l|}·r^{∓1} (`r` is 1/r for SGN = +1).
+template <bool BPOS, int SGN>
+__device__ __forceinline__ void estep_site(EState& s, const SiteTile& st, int j, double r) {
+    const double2 w = st.w[j], tn = st.tn[j], bd = st.bd[j];
+    const double t = tn.x, na = tn.y, nb = bd.x, sinvd = bd.y;
     double u = BPOS ? s.fp : s.fm, v = BPOS ? s.fm : s.fp;
     double Gp = fma(t, v, u), Gm = fma(t, u, v);
     double ua = BPOS ? s.gap : s.gam, va = BPOS ? s.gam : s.gap;
@@ -274,16 +258,24 @@ __device__ __forceinline__ void estep_site(EState& s, const SiteTileK& st, int j
     double Hbp = fma(t, vb, ub), Hbm = fma(t, ub, vb);
     double Hcp = fma(t, vc, uc), Hcm = fma(t, uc, vc);
     double Dp = fma(2.0, u, -Gp), Dm = fma(2.0, v, -Gm);          // Σ_x (x x') ψ f, up to the sign carried by sinvd
-    if (APOS) {
-        s.gap = fma(na, Gp, Hap);        s.gam = k * fma(-na, Gm, Ham);
-        s.gbp = fma(nb, Gp, Hbp);        s.gbm = k * fma(-nb, Gm, Hbm);
-        s.gcp = fma(sinvd, Dp, Hcp);     s.gcm = k * fma(sinvd, Dm, Hcm);
-        s.fp = Gp;                       s.fm = k * Gm;
+    if (SGN == 0) {
+        const double phiP = w.y * r, phiM = w.x;
+        s.gap = phiP * fma(na, Gp, Hap);     s.gam = phiM * fma(-na, Gm, Ham);
+        s.gbp = phiP * fma(nb, Gp, Hbp);     s.gbm = phiM * fma(-nb, Gm, Hbm);
+        s.gcp = phiP * fma(sinvd, Dp, Hcp);  s.gcm = phiM * fma(sinvd, Dm, Hcm);
+        s.fp = phiP * Gp;                    s.fm = phiM * Gm;
+    } else if (SGN > 0) {
+        const double k = w.x * r;
+        s.gap = fma(na, Gp, Hap);            s.gam = k * fma(-na, Gm, Ham);
+        s.gbp = fma(nb, Gp, Hbp);            s.gbm = k * fma(-nb, Gm, Hbm);
+        s.gcp = fma(sinvd, Dp, Hcp);         s.gcm = k * fma(sinvd, Dm, Hcm);
+        s.fp = Gp;                           s.fm = k * Gm;
     } else {
-        s.gap = k * fma(na, Gp, Hap);    s.gam = fma(-na, Gm, Ham);
-        s.gbp = k * fma(nb, Gp, Hbp);    s.gbm = fma(-nb, Gm, Hbm);
-        s.gcp = k * fma(sinvd, Dp, Hcp); s.gcm = fma(sinvd, Dm, Hcm);
-        s.fp = k * Gp;                   s.fm = Gm;
+        const double k = w.y * r;
+        s.gap = k * fma(na, Gp, Hap);        s.gam = fma(-na, Gm, Ham);
+        s.gbp = k * fma(nb, Gp, Hbp);        s.gbm = fma(-nb, Gm, Hbm);
+        s.gcp = k * fma(sinvd, Dp, Hcp);     s.gcm = fma(sinvd, Dm, Hcm);
+        s.fp = k * Gp;                       s.fm = Gm;
     }
 }
 __device__ __forceinline__ void estep_rescale(EState& s) {
@@ -291,87 +283,77 @@ __device__ __forceinline__ void estep_rescale(EState& s) {
     s.fp *= sc; s.fm *= sc; s.gap *= sc; s.gam *= sc; s.gbp *= sc; s.gbm *= sc; s.gcp *= sc; s.gcm *= sc;
 }
 
-// Emission pairs of a warp travel global → shared memory with cp.async into a private ring of two blocks of E_PF groups,
-// as two planes (r and 1/r, 8 bytes per lane each) so that a step's LDS.64 of either is conflict-free.  A lane only ever
-// reads what it copied itself, so no warp synchronisation is needed; and because an asynchronous copy has no destination
-// register, the deep prefetch costs no registers (the register file is what limits the number of resident E-step warps).
-#ifndef E_RING_PLANAR
-#define E_RING_PLANAR 1
-#endif
-#if E_RING_PLANAR
-struct EmisRing { double r[2][E_PF][2][32]; };
-#define ERING_R(ring, slot, u, lane) (ring).r[slot][u][0][lane]
-#define ERING_RI(ring, slot, u, lane) (ring).r[slot][u][1][lane]
-#else
-struct EmisRing { double2 r[2][E_PF][32]; };
-#define ERING_R(ring, slot, u, lane) (ring).r[slot][u][lane].x
-#define ERING_RI(ring, slot, u, lane) (ring).r[slot][u][lane].y
-#endif
+// Emission weights of a warp travel global → shared memory with cp.async (8 bytes per lane and group) into a private
+// ring: two slots of E_PF groups plus one slot for the chain tail.  A lane only ever reads what it copied itself, so no
+// warp synchronisation is needed; and because an asynchronous copy has no destination register, the deep prefetch costs
+// no registers (the register file is what limits the number of resident E-step warps).
+struct EmisRing { double r[3][E_PF][32]; };
 
-template <bool FULL>
-__device__ __forceinline__ void ering_issue(EmisRing& ring, int slot, const double2* __restrict__ src /*row 0, this lane*/, int nrows, int lane) {
-#if E_RING_PLANAR
-    const unsigned d = (unsigned)__cvta_generic_to_shared(&ring.r[slot][0][0][lane]);
-    const double* s8 = reinterpret_cast<const double*>(src);
+__device__ __forceinline__ void ering_issue(EmisRing& ring, int slot, const double* __restrict__ src /*row 0, this lane*/, int nrows, int lane) {
 #pragma unroll
     for (int u = 0; u < E_PF; ++u) {
-        if (FULL || u < nrows) {
-            asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(d + u * 512), "l"(s8 + u * EW_ROW));
-            asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(d + u * 512 + 256), "l"(s8 + u * EW_ROW + 1));
+        if (u < nrows) {
+            unsigned d = (unsigned)__cvta_generic_to_shared(&ring.r[slot][u][lane]);
+            asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(d), "l"(src + u * 32));
         }
     }
-#else
-    const unsigned d = (unsigned)__cvta_generic_to_shared(&ring.r[slot][0][lane]);
-#pragma unroll
-    for (int u = 0; u < E_PF; ++u) {
-        if (FULL || u < nrows) asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" ::"r"(d + u * 512), "l"(src + u * 32));
-    }
-#endif
     asm volatile("cp.async.commit_group;");
 }
 
 // Forward sweep of the conditional chain for the 32 reads of a chunk, carrying the tangents (∂a,∂b,∂c).
-// Groups are processed E_PF at a time: while one block of E_PF emission rows is consumed from the ring the next one is in
-// flight; the state is rescaled by a power of two between blocks.
+// Groups are processed in blocks of E_PF: while one block of emission rows is consumed from the ring the next one is in
+// flight.  A block whose groups all have α_l ≥ 0 (or all α_l < 0; 97 % of the blocks of the simulated genome, because ρ_l is
+// small and a decides the sign) runs the matching specialised steps and reads 1/r (or r); a mixed block runs the general step.
+// The state is rescaled by a power of two between blocks (rmask = 0: before every block, 1: before every second one).
 template <bool BPOS>
-__device__ __forceinline__ void estep_chunk(SiteTileK& st, EmisRing& ring, int L, int lane, const double* __restrict__ na_g,
+__device__ __forceinline__ void estep_chunk(SiteTile& st, EmisRing& ring, int L, int lane, const double* __restrict__ na_g,
                                             const double* __restrict__ nb_g, const double* __restrict__ invd_g,
-                                            const double2* __restrict__ p /*(r, 1/r) of (group l, this lane's read) at p[l*32]*/,
-                                            double a, double b, double cabs, double out[3]) {
+                                            const double* __restrict__ p /*r of (group l, this lane's read) at p[l*32]*/,
+                                            const double* __restrict__ pi /*1/r, same indexing*/,
+                                            double a, double b, double cabs, int rmask, double out[3]) {
     EState s{1.0, 1.0, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0};
-    if (L >= E_PF) ering_issue<true>(ring, 0, p, E_PF, lane); else ering_issue<false>(ring, 0, p, L, lane);
+    const int Lfull = L & ~(E_PF - 1);
+    // the chain tail (always the general step, so always r) is in flight from the start
+    ering_issue(ring, 2, p + (size_t)Lfull * 32, L - Lfull, lane);
     int g = 0;                                          // index of the block of E_PF groups being consumed
     for (int l0 = 0; l0 < L; l0 += TILE) {
         const int n = min(TILE, L - l0);
+        const int nfull = n & ~(E_PF - 1);
+        TileRegs tr;
         unsigned m0, m1;
+        tile_load(tr, l0, n, lane, na_g, nb_g, invd_g, a, b, m0, m1);
+        // first block of the tile: its plane is known as soon as the signs are; the copy overlaps the exponentials below
+        ering_issue(ring, g & 1, ((m0 & 0xffu) == 0xffu ? pi : p) + (size_t)g * E_PF * 32, nfull > 0 ? E_PF : 0, lane);
         __syncwarp();
-        fill_tile_k(st, l0, n, lane, na_g, nb_g, invd_g, a, b, cabs, BPOS, m0, m1);
+        tile_store(st, tr, l0, n, lane, cabs, BPOS);
         __syncwarp();
 #pragma unroll 1
-        for (int j0 = 0; j0 < n; j0 += E_PF, ++g) {
-            // next block in flight, then wait until at most that one is pending: block g has landed
-            const int left = L - (g + 1) * E_PF;        // groups after this block
-            const double2* nxt = p + (size_t)(g + 1) * E_PF * 32;
-            if (left >= E_PF) ering_issue<true>(ring, (g + 1) & 1, nxt, E_PF, lane); else ering_issue<false>(ring, (g + 1) & 1, nxt, left, lane);
+        for (int j0 = 0; j0 < nfull; j0 += E_PF, ++g) {
+            const unsigned bits = (((j0 & 32) ? m1 : m0) >> (j0 & 31)) & ((1u << E_PF) - 1);
+            // next block of this tile in flight, then wait until at most that one is pending: block g (and the tail) have landed
+            const int j1 = j0 + E_PF;
+            const unsigned bits1 = (((j1 & 32) ? m1 : m0) >> (j1 & 31)) & ((1u << E_PF) - 1);
+            ering_issue(ring, (g + 1) & 1, (bits1 == (1u << E_PF) - 1 ? pi : p) + (size_t)(g + 1) * E_PF * 32, (j1 < nfull) ? E_PF : 0, lane);
             asm volatile("cp.async.wait_group 1;");
-            if (g > 0) estep_rescale(s);
-            // (read back from lane 0: a value the compiler can see is warp-uniform, so the per-group branches below are plain
-            // uniform branches without reconvergence barriers)
-            const unsigned bits = __shfl_sync(0xffffffffu, ((j0 & 32) ? m1 : m0) >> (j0 & 31), 0);
+            if (g > 0 && (g & rmask) == 0) estep_rescale(s);
             const int slot = g & 1;
-            if (n - j0 >= E_PF) {
+            if (bits == (1u << E_PF) - 1) {
 #pragma unroll
-                for (int u = 0; u < E_PF; ++u) {
-                    if (bits & (1u << u)) estep_site<BPOS, true>(s, st, j0 + u, ERING_RI(ring, slot, u, lane));
-                    else estep_site<BPOS, false>(s, st, j0 + u, ERING_R(ring, slot, u, lane));
-                }
-            } else {                                    // last block of the chain, fewer than E_PF groups
-#pragma unroll 1
-                for (int u = 0; u < n - j0; ++u) {
-                    if ((bits >> u) & 1u) estep_site<BPOS, true>(s, st, j0 + u, ERING_RI(ring, slot, u, lane));
-                    else estep_site<BPOS, false>(s, st, j0 + u, ERING_R(ring, slot, u, lane));
-                }
+                for (int u = 0; u < E_PF; ++u) estep_site<BPOS, 1>(s, st, j0 + u, ring.r[slot][u][lane]);
+            } else if (bits == 0u) {
+#pragma unroll
+                for (int u = 0; u < E_PF; ++u) estep_site<BPOS, -1>(s, st, j0 + u, ring.r[slot][u][lane]);
+            } else {
+#pragma unroll
+                for (int u = 0; u < E_PF; ++u) estep_site<BPOS, 0>(s, st, j0 + u, ring.r[slot][u][lane]);
             }
+        }
+        // tail of the chain (fewer than E_PF groups left; only the last tile has one)
+        if (nfull < n) {
+            asm volatile("cp.async.wait_group 0;");
+            if (g > 0) estep_rescale(s);
+#pragma unroll 1
+            for (int u = 0; u < n - nfull; ++u) estep_site<BPOS, 0>(s, st, nfull + u, ring.r[2][u][lane]);
         }
     }
     asm volatile("cp.async.wait_group 0;");
@@ -381,24 +363,21 @@ __device__ __forceinline__ void estep_chunk(SiteTileK& st, EmisRing& ring, int L
     out[2] = (s.gcp + s.gcm) * inv;
 }
 
-// The same sweep with a rescale after every group and plain loads: for instances whose |LLR| or |β| bound is too large for
-// E_PF unscaled groups (rare: real and simulated log-likelihood ratios are a few tens at most).
+// The same sweep with a rescale after every group and plain loads: for instances whose |LLR| / |β| bound allows no unscaled
+// run of groups (|LLR| is clamped at 300, so one group always fits the double range).
 template <bool BPOS>
-__device__ __noinline__ void estep_chunk_slow(SiteTileK& st, int L, int lane, const double* __restrict__ na_g,
+__device__ __noinline__ void estep_chunk_slow(SiteTile& st, int L, int lane, const double* __restrict__ na_g,
                                               const double* __restrict__ nb_g, const double* __restrict__ invd_g,
-                                              const double2* __restrict__ p, double a, double b, double cabs, double out[3]) {
+                                              const double* __restrict__ p, double a, double b, double cabs, double out[3]) {
     EState s{1.0, 1.0, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0};
     for (int l0 = 0; l0 < L; l0 += TILE) {
         const int n = min(TILE, L - l0);
-        unsigned m0, m1;
         __syncwarp();
-        fill_tile_k(st, l0, n, lane, na_g, nb_g, invd_g, a, b, cabs, BPOS, m0, m1);
+        fill_tile(st, l0, n, lane, na_g, nb_g, invd_g, a, b, cabs, BPOS);
         __syncwarp();
 #pragma unroll 1
         for (int j = 0; j < n; ++j) {
-            const double2 rr = __ldg(p + (size_t)(l0 + j) * 32);
-            if ((((j & 32) ? m1 : m0) >> (j & 31)) & 1u) estep_site<BPOS, true>(s, st, j, rr.y);
-            else estep_site<BPOS, false>(s, st, j, rr.x);
+            estep_site<BPOS, 0>(s, st, j, __ldg(p + (size_t)(l0 + j) * 32));
             estep_rescale(s);
         }
     }
@@ -415,7 +394,7 @@ __global__ void __launch_bounds__(E_WARPS * 32, E_BLOCKS) k_estep(int n_items, c
                                                                    const double* __restrict__ phil /*[3][cap] by list position*/, int64_t cap,
                                                                    RegionTables rt, int64_t NI, double* __restrict__ ES /*[3][NI]*/,
                                                                    const int* __restrict__ n_dev /*null, or the true item count*/) {
-    __shared__ SiteTileK tiles[E_WARPS];
+    __shared__ SiteTile tiles[E_WARPS];
     __shared__ EmisRing rings[E_WARPS];
     int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
     int item = blockIdx.x * E_WARPS + w;
@@ -426,15 +405,11 @@ __global__ void __launch_bounds__(E_WARPS * 32, E_BLOCKS) k_estep(int n_items, c
     const int4 d0 = __ldg(dq);
     const longlong2 d1 = __ldg(reinterpret_cast<const longlong2*>(dq + 1));
     double a = phil[item], b = phil[cap + item], c = phil[2 * cap + item];
-    // L, M and the path flag are the same in every lane; reading them back from lane 0 lets the compiler see that (loop
-    // counters and the per-group branch then live in uniform registers and the branches need no reconvergence barriers)
-    const int inst = d0.x, L = __shfl_sync(0xffffffffu, d0.y, 0), Mw = __shfl_sync(0xffffffffu, d0.z, 0), ridx = d0.w;
-    const int M = Mw & ((1 << ITEM_SLOW_BIT) - 1);
-    const bool slow = (Mw >> ITEM_SLOW_BIT) & 1;
+    const int inst = d0.x, L = d0.y, M = d0.z & ITEM_M_MASK, ridx = d0.w, mode = (d0.z >> ITEM_MODE_SHIFT) & 3;
     const int64_t g0 = d1.x;
     bool bpos = __double2hiint(c) >= 0;
     double cabs = fabs(c);
-    const double2* ew_r = reinterpret_cast<const double2*>(rt.ew + d1.y);
+    const double* ew_r = rt.ew + d1.y;
     double acc0 = 0, acc1 = 0, acc2 = 0;
     int nchunk = (M + 31) >> 5;
     for (int ch = 0; ch < nchunk; ++ch) {
@@ -442,10 +417,12 @@ __global__ void __launch_bounds__(E_WARPS * 32, E_BLOCKS) k_estep(int n_items, c
         // this lane's read: lane of chunk ch, or — in a view — the pooled read the view's index row names
         int q = ch * 32 + lane;
         if (ridx >= 0) q = __ldg(rt.ridx + ((size_t)(ridx + ch) << 5) + lane);
-        const double2* p = ew_r + (size_t)(q >> 5) * L * 32 + (q & 31);
-        if (!slow) {
-            if (bpos) estep_chunk<true>(tiles[w], rings[w], L, lane, rt.na + g0, rt.nb + g0, rt.invd + g0, p, a, b, cabs, o);
-            else estep_chunk<false>(tiles[w], rings[w], L, lane, rt.na + g0, rt.nb + g0, rt.invd + g0, p, a, b, cabs, o);
+        const size_t po = (size_t)(q >> 5) * L * 32 + (q & 31);
+        const double* p = ew_r + po;
+        if (mode != 0) {
+            const double* pi = rt.ewi + d1.y + po;
+            if (bpos) estep_chunk<true>(tiles[w], rings[w], L, lane, rt.na + g0, rt.nb + g0, rt.invd + g0, p, pi, a, b, cabs, mode - 1, o);
+            else estep_chunk<false>(tiles[w], rings[w], L, lane, rt.na + g0, rt.nb + g0, rt.invd + g0, p, pi, a, b, cabs, mode - 1, o);
         } else {
             if (bpos) estep_chunk_slow<true>(tiles[w], L, lane, rt.na + g0, rt.nb + g0, rt.invd + g0, p, a, b, cabs, o);
             else estep_chunk_slow<false>(tiles[w], L, lane, rt.na + g0, rt.nb + g0, rt.invd + g0, p, a, b, cabs, o);
@@ -471,9 +448,10 @@ __global__ void k_make_desc(int n_items, const int* __restrict__ items, int n_in
     RegionDesc rd = rdesc[inst / n_init];
     ItemDesc d;
     const double c = phi[2 * NI + inst];
-    // rescale policy of the E-step for this instance (see estep_site): negated comparisons, so NaN bounds or a NaN c choose slow
-    const bool fast = (rd.llrmax <= E_FAST_LLR) && (fabs(c) * (double)rd.idmax <= (double)E_FAST_BETA);
-    d.inst = inst; d.L = rd.L; d.M = rd.M | (fast ? 0 : (1 << ITEM_SLOW_BIT)); d.ridx = rd.ridx; d.g0 = rd.g0; d.ew_off = rd.ew_off;
+    // rescale policy of the E-step for this instance (see estep_site); comparisons written so that NaN bounds or a NaN c choose slow
+    const double B = (double)rd.llrmax + 2.0 * fabs(c) * (double)rd.idmax;
+    const int mode = (B <= (double)E_BOUND_2) ? 2 : ((B <= (double)E_BOUND_1) ? 1 : 0);
+    d.inst = inst; d.L = rd.L; d.M = rd.M | (mode << ITEM_MODE_SHIFT); d.ridx = rd.ridx; d.g0 = rd.g0; d.ew_off = rd.ew_off;
     desc[i] = d;
     phil[i] = phi[inst]; phil[cap + i] = phi[NI + inst]; phil[2 * cap + i] = c;
 }
@@ -550,7 +528,7 @@ __global__ void __launch_bounds__(E_WARPS * 32) k_score(int n_items, const int* 
         int q = ch * 32 + lane;
         const bool live = (int64_t)ch * 32 + lane < M;
         if (rd.ridx >= 0) q = __ldg(rt.ridx + ((size_t)(rd.ridx + ch) << 5) + lane);
-        const double* p = ew_r + (size_t)(q >> 5) * L * EW_ROW + 2 * (q & 31);
+        const double* p = ew_r + (size_t)(q >> 5) * L * EW_ROW + (q & 31);
         if (spare && ch == nchunk - 1 && lane == 31) p = nullptr;
         double lz = bpos ? logz_chunk<true>(tiles[w], L, lane, rt.na + g0, rt.nb + g0, rt.invd + g0, p, a, b, cabs)
                          : logz_chunk<false>(tiles[w], L, lane, rt.na + g0, rt.nb + g0, rt.invd + g0, p, a, b, cabs);
@@ -1440,17 +1418,11 @@ __global__ void k_unpack3(int64_t R, const double* __restrict__ in /*[3][R]*/, d
 // ---------------------------------------------------------------------------------------------------
 // host side
 // ---------------------------------------------------------------------------------------------------
-// k_estep keeps E_BLOCKS blocks of 42 KB of shared memory resident per SM: ask for the shared-memory carveout that allows it
-// (per device; the call is cheap and idempotent).
-static cudaError_t estep_prepare() {
-    return cudaFuncSetAttribute(k_estep, cudaFuncAttributePreferredSharedMemoryCarveout, (int)cudaSharedmemCarveoutMaxShared);
-}
-
 struct PackedRegions {
     DevIn<int64_t> grp_off, read_off;
     DevIn<double> Nl, rho, dl, lu, lm;
     DevBuf<int64_t> obs_off, ew_off, rb_off;
-    DevBuf<double> na, nb, invd, ew, rb;
+    DevBuf<double> na, nb, invd, ew, ewi, rb;
     DevBuf<SweepSite> sq;
     DevBuf<RegionDesc> rdesc;
     std::vector<int64_t> h_grp_off, h_read_off;
@@ -1538,6 +1510,7 @@ int pack_regions(cpn_ctx* ctx, PackedRegions& pk, bool on_device, bool with_read
         CPN_CUDA(ctx, pk.rdesc.upload(h_desc.data(), R, s));
         pk.rt.rdesc = pk.rdesc.p;
         CPN_CUDA(ctx, pk.ew.alloc(h_ew[R], s));
+        CPN_CUDA(ctx, pk.ewi.alloc(h_ew[R], s));
         CPN_CUDA(ctx, pk.rb.alloc(h_rb[R], s));
         CPN_CUDA(ctx, pk.lu.bind(lu, pk.n_obs, on_device, s));
         trace(ctx, "pk-lu");
@@ -1545,14 +1518,14 @@ int pack_regions(cpn_ctx* ctx, PackedRegions& pk, bool on_device, bool with_read
         trace(ctx, "pk-lm");
         { KTimer kt(ctx, CPN_K_PREP);
           k_prep_emis<<<blocks_for(R * 32, 128), 128, 0, s>>>(R, pk.grp_off.p, pk.read_off.p, pk.obs_off.p, pk.lu.p, pk.lm.p, pk.ew_off.p,
-                                                              pk.rb_off.p, pk.invd.p, pk.ew.p, pk.rb.p, pk.rdesc.p); }
+                                                              pk.rb_off.p, pk.invd.p, pk.ew.p, pk.ewi.p, pk.rb.p, pk.rdesc.p); }
         // the raw emissions are not needed once packed: hand the memory back (stream-ordered) before the EM loop
         pk.lm.own.release();
         pk.lu.own.release();
         trace(ctx, "pk-enq");
         CPN_CUDA(ctx, cpn_wait_stream(ctx, s));   // h_* staging vectors go out of scope
         trace(ctx, "pk-sync");
-        pk.rt.read_off = pk.read_off.p; pk.rt.ew_off = pk.ew_off.p; pk.rt.rb_off = pk.rb_off.p; pk.rt.ew = pk.ew.p; pk.rt.rb = pk.rb.p;
+        pk.rt.read_off = pk.read_off.p; pk.rt.ew_off = pk.ew_off.p; pk.rt.rb_off = pk.rb_off.p; pk.rt.ew = pk.ew.p; pk.rt.ewi = pk.ewi.p; pk.rt.rb = pk.rb.p;
     }
     CPN_CUDA(ctx, cudaGetLastError());
     return CPN_OK;
@@ -1664,8 +1637,7 @@ int fit_impl(cpn_ctx* ctx, bool on_device, int64_t R, const int64_t* grp_off, co
         CPN_CUDA(ctx, alive.alloc(NI, s));
         CPN_CUDA(ctx, blk_cnt.alloc((NI + CP_TILE - 1) / CP_TILE, s));
         int ws_blocks_per_sm = 1;
-        CPN_CUDA(ctx, estep_prepare());
-        CPN_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ws_blocks_per_sm, k_mstep_ws, M_THREADS, 0));
+                CPN_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ws_blocks_per_sm, k_mstep_ws, M_THREADS, 0));
         if (ws_blocks_per_sm < 1) ws_blocks_per_sm = 1;
         // Regions ordered by group count (counting sort) so the 32 lanes of an M-step warp walk chains of
         // similar length.
@@ -2344,8 +2316,7 @@ int cpn_estep_batch(cpn_ctx* ctx, int64_t R, const int64_t* grp_off, const doubl
         { KTimer kt(ctx, CPN_K_PREP); k_pack_phi<<<blocks_for(R, 256), 256, 0, s>>>(R, d_phi_in.p, d_phi.p); }
         DevBuf<ItemDesc> idesc;
         DevBuf<double> phil;
-        CPN_CUDA(ctx, estep_prepare());
-        CPN_CUDA(ctx, idesc.alloc(R, s)); CPN_CUDA(ctx, phil.alloc(3 * R, s));
+                CPN_CUDA(ctx, idesc.alloc(R, s)); CPN_CUDA(ctx, phil.alloc(3 * R, s));
         { KTimer kt(ctx, CPN_K_PREP);
           k_make_desc<<<blocks_for(R, 256), 256, 0, s>>>((int)R, nullptr, 1, pk.rt.rdesc, d_phi.p, R, idesc.p, phil.p, R, nullptr); }
         { KTimer kt(ctx, CPN_K_ESTEP); k_estep<<<blocks_for(R, E_WARPS), E_WARPS * 32, 0, s>>>((int)R, idesc.p, phil.p, R, pk.rt, R, d_ES.p, nullptr); }
