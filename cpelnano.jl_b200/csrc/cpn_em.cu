@@ -390,51 +390,90 @@ __device__ __noinline__ void estep_chunk_slow(SiteTile& st, int L, int lane, con
 #ifndef E_BLOCKS
 #define E_BLOCKS 5
 #endif
+#ifndef E_PERSIST
+#define E_PERSIST 1                 // 1: resident grid, every warp walks the list with a block stride and prefetches its next instance
+#endif
+__device__ __forceinline__ void pf_l1(const void* p) { asm volatile("prefetch.global.L1 [%0];" ::"l"(p)); }
+
+// One warp per (region, start) instance, lanes = reads.  The head of an instance is a chain of dependent loads (descriptor and ϕ →
+// group tables → first rows of emissions) that the chain loop cannot start without; a warp therefore pulls the lines its NEXT
+// instance will need into L1 while it still works on the current one — descriptor and ϕ at the start, the group tables and the
+// first block of emission rows (both planes) when its chain ends, so that they travel during the reduction over reads.
 __global__ void __launch_bounds__(E_WARPS * 32, E_BLOCKS) k_estep(int n_items, const ItemDesc* __restrict__ desc,
                                                                    const double* __restrict__ phil /*[3][cap] by list position*/, int64_t cap,
                                                                    RegionTables rt, int64_t NI, double* __restrict__ ES /*[3][NI]*/,
                                                                    const int* __restrict__ n_dev /*null, or the true item count*/) {
     __shared__ SiteTile tiles[E_WARPS];
     __shared__ EmisRing rings[E_WARPS];
-    int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    int item = blockIdx.x * E_WARPS + w;
+    const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
     if (n_dev) n_items = __ldg(n_dev);
-    if (item >= n_items) return;
-    // one round of independent loads: descriptor (two 16-byte vectors) and ϕ
-    const int4* dq = reinterpret_cast<const int4*>(desc + item);
-    const int4 d0 = __ldg(dq);
-    const longlong2 d1 = __ldg(reinterpret_cast<const longlong2*>(dq + 1));
-    double a = phil[item], b = phil[cap + item], c = phil[2 * cap + item];
-    const int inst = d0.x, L = d0.y, M = d0.z & ITEM_M_MASK, ridx = d0.w, mode = (d0.z >> ITEM_MODE_SHIFT) & 3;
-    const int64_t g0 = d1.x;
-    bool bpos = __double2hiint(c) >= 0;
-    double cabs = fabs(c);
-    const double* ew_r = rt.ew + d1.y;
-    double acc0 = 0, acc1 = 0, acc2 = 0;
-    int nchunk = (M + 31) >> 5;
-    for (int ch = 0; ch < nchunk; ++ch) {
-        double o[3];
-        // this lane's read: lane of chunk ch, or — in a view — the pooled read the view's index row names
-        int q = ch * 32 + lane;
-        if (ridx >= 0) q = __ldg(rt.ridx + ((size_t)(ridx + ch) << 5) + lane);
-        const size_t po = (size_t)(q >> 5) * L * 32 + (q & 31);
-        const double* p = ew_r + po;
-        if (mode != 0) {
-            const double* pi = rt.ewi + d1.y + po;
-            if (bpos) estep_chunk<true>(tiles[w], rings[w], L, lane, rt.na + g0, rt.nb + g0, rt.invd + g0, p, pi, a, b, cabs, mode - 1, o);
-            else estep_chunk<false>(tiles[w], rings[w], L, lane, rt.na + g0, rt.nb + g0, rt.invd + g0, p, pi, a, b, cabs, mode - 1, o);
-        } else {
-            if (bpos) estep_chunk_slow<true>(tiles[w], L, lane, rt.na + g0, rt.nb + g0, rt.invd + g0, p, a, b, cabs, o);
-            else estep_chunk_slow<false>(tiles[w], L, lane, rt.na + g0, rt.nb + g0, rt.invd + g0, p, a, b, cabs, o);
+    const int stride = gridDim.x * E_WARPS;
+#pragma unroll 1
+    for (int item = blockIdx.x * E_WARPS + w; item < n_items; item += stride) {
+        const int next = item + stride;
+        const bool has_next = E_PERSIST && next < n_items;
+        if (has_next && lane < 4) pf_l1(lane == 0 ? (const void*)(desc + next) : (const void*)(phil + (size_t)(lane - 1) * cap + next));
+        // one round of independent loads: descriptor (two 16-byte vectors) and ϕ
+        const int4* dq = reinterpret_cast<const int4*>(desc + item);
+        const int4 d0 = __ldg(dq);
+        const longlong2 d1 = __ldg(reinterpret_cast<const longlong2*>(dq + 1));
+        double a = phil[item], b = phil[cap + item], c = phil[2 * cap + item];
+        const int inst = d0.x, L = d0.y, M = d0.z & ITEM_M_MASK, ridx = d0.w, mode = (d0.z >> ITEM_MODE_SHIFT) & 3;
+        const int64_t g0 = d1.x;
+        bool bpos = __double2hiint(c) >= 0;
+        double cabs = fabs(c);
+        const double* ew_r = rt.ew + d1.y;
+        double acc0 = 0, acc1 = 0, acc2 = 0;
+        int nchunk = (M + 31) >> 5;
+        for (int ch = 0; ch < nchunk; ++ch) {
+            double o[3];
+            // this lane's read: lane of chunk ch, or — in a view — the pooled read the view's index row names
+            int q = ch * 32 + lane;
+            if (ridx >= 0) q = __ldg(rt.ridx + ((size_t)(ridx + ch) << 5) + lane);
+            const size_t po = (size_t)(q >> 5) * L * 32 + (q & 31);
+            const double* p = ew_r + po;
+            if (mode != 0) {
+                const double* pi = rt.ewi + d1.y + po;
+                if (bpos) estep_chunk<true>(tiles[w], rings[w], L, lane, rt.na + g0, rt.nb + g0, rt.invd + g0, p, pi, a, b, cabs, mode - 1, o);
+                else estep_chunk<false>(tiles[w], rings[w], L, lane, rt.na + g0, rt.nb + g0, rt.invd + g0, p, pi, a, b, cabs, mode - 1, o);
+            } else {
+                if (bpos) estep_chunk_slow<true>(tiles[w], L, lane, rt.na + g0, rt.nb + g0, rt.invd + g0, p, a, b, cabs, o);
+                else estep_chunk_slow<false>(tiles[w], L, lane, rt.na + g0, rt.nb + g0, rt.invd + g0, p, a, b, cabs, o);
+            }
+            if (has_next && ch == nchunk - 1) {
+                // the next instance's group tables (lanes 0-14: five 128-byte lines of each of na, nb, 1/d) and the first E_PF rows
+                // of both emission planes (32 lines, one per lane)
+                const int4* nq = reinterpret_cast<const int4*>(desc + next);
+                const int Ln = __ldg(nq).y;
+                const longlong2 n1 = __ldg(reinterpret_cast<const longlong2*>(nq + 1));
+                if (lane < 15) {
+                    const int tb = lane / 5, ln = lane - 5 * tb;
+                    const double* base = (tb == 0 ? rt.na : (tb == 1 ? rt.nb : rt.invd)) + n1.x;
+                    if (ln * 16 < Ln + 16) pf_l1(base + ln * 16);
+                }
+                const double* pl = ((lane & 16) ? rt.ewi : rt.ew) + n1.y + (size_t)((lane >> 1) & 7) * 32 + (lane & 1) * 16;
+                if (((lane >> 1) & 7) < Ln) pf_l1(pl);
+            }
+            bool live = ch * 32 + lane < M;
+            acc0 += cpn_warp_sum(live ? o[0] : 0.0);
+            acc1 += cpn_warp_sum(live ? o[1] : 0.0);
+            acc2 += cpn_warp_sum(live ? o[2] : 0.0);
         }
-        bool live = ch * 32 + lane < M;
-        acc0 += cpn_warp_sum(live ? o[0] : 0.0);
-        acc1 += cpn_warp_sum(live ? o[1] : 0.0);
-        acc2 += cpn_warp_sum(live ? o[2] : 0.0);
+        if (lane == 0) {
+            ES[inst] = acc0; ES[NI + inst] = acc1; ES[2 * NI + inst] = acc2;
+        }
     }
-    if (lane == 0) {
-        ES[inst] = acc0; ES[NI + inst] = acc1; ES[2 * NI + inst] = acc2;
+}
+// grid of an E-step launch over n items
+static unsigned estep_grid(cpn_ctx* ctx, int64_t n) {
+    const unsigned full = (unsigned)((n + E_WARPS - 1) / E_WARPS);
+    if (!E_PERSIST) return full;
+    if (ctx->estep_blocks <= 0) {          // what the device really keeps resident (registers, shared-memory carveout), not what was asked for
+        int nb = 0;
+        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k_estep, E_WARPS * 32, 0) != cudaSuccess || nb < 1) nb = 1;
+        ctx->estep_blocks = nb;
     }
+    return std::min<unsigned>(full, (unsigned)(ctx->sm_count * ctx->estep_blocks));
 }
 
 // Builds the position-indexed descriptors for a list of instances (items == null: identity list).
@@ -1694,7 +1733,7 @@ int fit_impl(cpn_ctx* ctx, bool on_device, int64_t R, const int64_t* grp_off, co
             { KTimer kt(ctx, CPN_K_PREP);
               k_make_desc<<<blocks_for(ub, 256), 256, 0, s>>>(ub, cur, n_init, rt.rdesc, phi.p, NI, idesc.p, phil.p, NI, n_dev); }
             { KTimer kt(ctx, CPN_K_ESTEP);
-              k_estep<<<blocks_for(ub, E_WARPS), E_WARPS * 32, 0, s>>>(ub, idesc.p, phil.p, NI, rt, NI, ES.p, n_dev); }
+              k_estep<<<estep_grid(ctx, ub), E_WARPS * 32, 0, s>>>(ub, idesc.p, phil.p, NI, rt, NI, ES.p, n_dev); }
             if (mstep_mode == CPN_MSTEP_ANALYTIC) {
                 unsigned grid = std::min<unsigned>(blocks_for(ub, M_THREADS), (unsigned)(ctx->sm_count * ws_blocks_per_sm));
                 { KTimer kt(ctx, CPN_K_MSTEP);
@@ -2319,7 +2358,7 @@ int cpn_estep_batch(cpn_ctx* ctx, int64_t R, const int64_t* grp_off, const doubl
                 CPN_CUDA(ctx, idesc.alloc(R, s)); CPN_CUDA(ctx, phil.alloc(3 * R, s));
         { KTimer kt(ctx, CPN_K_PREP);
           k_make_desc<<<blocks_for(R, 256), 256, 0, s>>>((int)R, nullptr, 1, pk.rt.rdesc, d_phi.p, R, idesc.p, phil.p, R, nullptr); }
-        { KTimer kt(ctx, CPN_K_ESTEP); k_estep<<<blocks_for(R, E_WARPS), E_WARPS * 32, 0, s>>>((int)R, idesc.p, phil.p, R, pk.rt, R, d_ES.p, nullptr); }
+        { KTimer kt(ctx, CPN_K_ESTEP); k_estep<<<estep_grid(ctx, R), E_WARPS * 32, 0, s>>>((int)R, idesc.p, phil.p, R, pk.rt, R, d_ES.p, nullptr); }
         { KTimer kt(ctx, CPN_K_PREP); k_unpack3<<<blocks_for(R, 256), 256, 0, s>>>(R, d_ES.p, d_ESo.p); }
         CPN_CUDA(ctx, d_ESo.download(ES, 3 * R, s));
         if (ave_logpy) {
