@@ -14,7 +14,7 @@ FIT_NONE, FIT_NUMERICAL, FIT_FILTERED = -1, -2, -16        # status words (inclu
 
 # every exported symbol of include/cpelnano_b200.h (tests check the library exports exactly these)
 SYMBOLS = ["cpn_create", "cpn_create_multi", "cpn_num_devices", "cpn_destroy", "cpn_last_error", "cpn_version", "cpn_last_device_ms", "cpn_last_launches", "cpn_last_work",
-           "cpn_measure_fp64_peak", "cpn_set_seed", "cpn_rng_phi0", "cpn_rng_perm", "cpn_set_profile", "cpn_get_profile", "cpn_analyze_batch", "cpn_analyze_batch_device", "cpn_fit_batch", "cpn_fit_batch_device", "cpn_estep_batch", "cpn_mstep_batch",
+           "cpn_measure_fp64_peak", "cpn_set_seed", "cpn_rng_phi0", "cpn_rng_perm", "cpn_set_profile", "cpn_get_profile", "cpn_analyze_batch", "cpn_analyze_batch_device", "cpn_fit_batch", "cpn_fit_batch_device", "cpn_pack_emissions", "cpn_fit_batch_packed", "cpn_analyze_batch_packed", "cpn_estep_batch", "cpn_mstep_batch",
            "cpn_stat_sums_batch", "cpn_nls_reg_info", "cpn_cmd_batch", "cpn_grp_unmat_sweep", "cpn_grp_mat_sweep", "cpn_two_samp_pvals", "cpn_two_samp_null_batch", "cpn_two_samp_test_batch", "cpn_grp_test_batch", "cpn_grp_test_batch_device", "cpn_region_filter",
            "cpn_calls_open", "cpn_calls_close", "cpn_calls_open_error", "cpn_calls_error", "cpn_calls_num_lines", "cpn_calls_num_reads", "cpn_calls_num_chr",
            "cpn_calls_chr_name", "cpn_calls_chr_lines", "cpn_calls_read_name", "cpn_calls_count_reads", "cpn_calls_fill",
@@ -151,11 +151,50 @@ class Library:
         self._check(self.dll.cpn_get_profile(ctx, _ptr(ms), _ptr(n)), ctx)
         return {k: (float(ms[i]), int(n[i])) for i, k in enumerate(self.KERNEL_CLASSES)}
 
-    def analyze_batch_raw(self, R, grp_off, Nl, rho_l, d_l, read_off, lu, lm, phi0, n_init, max_em_iters, box, mstep_mode, cpg_off, rho_n,
-                          d_n, sub_off, sub_p, sub_q, phi_hat, Q, status, counters, logZ, ex, exx, log_g, e1, e2, mml, nme, on_device, device=0):
-        """Pointer-level cpn_analyze_batch[_device] (ints = raw addresses, or numpy arrays)."""
+    def pack_emissions(self, grp_off, read_off, log_pyx_u, log_pyx_m, n_threads=0, out=None):
+        """cpn_pack_emissions: (llr [Σ M·L], read_base [Σ M]) from the two log-likelihood tables (host, no CUDA)."""
+        grp_off, read_off = _i64(grp_off), _i64(read_off)
+        lu, lm = _f64(log_pyx_u), _f64(log_pyx_m)
+        R = len(grp_off) - 1
+        llr, base = out if out is not None else (np.empty(lu.size), np.empty(int(read_off[-1])))
+        rc = self.dll.cpn_pack_emissions(C.c_int64(R), _ptr(grp_off), _ptr(read_off), _ptr(lu), _ptr(lm), _ptr(llr), _ptr(base), C.c_int32(n_threads))
+        if rc != 0:
+            raise CpnError(f"cpn_pack_emissions failed with code {rc} (null pointer, negative extent, or an observed cell without a finite log p(y|+1))")
+        return llr, base
+
+    def fit_batch_packed(self, grp_off, Nl, rho_l, d_l, read_off, llr, read_base, phi0, n_init, max_em_iters=20,
+                         box=(20.0, 150.0, 50.0), mstep_mode=MSTEP_ANALYTIC, per_start=False, device=0):
+        """cpn_fit_batch_packed: cpn_fit_batch on packed emissions (pack_emissions)."""
+        grp_off, read_off = _i64(grp_off), _i64(read_off)
+        Nl, rho_l, d_l, llr, read_base = _f64(Nl), _f64(rho_l), _f64(d_l), _f64(llr), _f64(read_base)
+        R = len(grp_off) - 1
+        if phi0 is not None:
+            phi0 = _f64(phi0)
+            assert phi0.size == R * n_init * 3, "phi0 must be [R, n_init, 3]"
+        phi_hat, Q = np.empty((R, 3)), np.empty(R)
+        status = np.empty(R, dtype=np.int32)
+        counters = np.empty((R, 4), dtype=np.int64)
+        ps = np.empty((R, n_init, 3)) if per_start else None
+        qs = np.empty((R, n_init)) if per_start else None
         ctx = self.ctx(device)
-        fn = self.dll.cpn_analyze_batch_device if on_device else self.dll.cpn_analyze_batch
+        rc = self.dll.cpn_fit_batch_packed(ctx, C.c_int64(R), _ptr(grp_off), _ptr(Nl), _ptr(rho_l), _ptr(d_l), _ptr(read_off), _ptr(llr),
+                                           _ptr(read_base), _ptr(phi0), C.c_int32(n_init), C.c_int32(max_em_iters), C.c_double(box[0]),
+                                           C.c_double(box[1]), C.c_double(box[2]), C.c_int32(mstep_mode), _ptr(phi_hat), _ptr(Q), _ptr(status),
+                                           _ptr(counters), _ptr(ps), _ptr(qs))
+        self._check(rc, ctx)
+        out = dict(phi_hat=phi_hat, Q=Q, pick=status, counters=counters)
+        if per_start:
+            out.update(phi_starts=ps, Q_starts=qs)
+        return out
+
+    def analyze_batch_raw(self, R, grp_off, Nl, rho_l, d_l, read_off, lu, lm, phi0, n_init, max_em_iters, box, mstep_mode, cpg_off, rho_n,
+                          d_n, sub_off, sub_p, sub_q, phi_hat, Q, status, counters, logZ, ex, exx, log_g, e1, e2, mml, nme, on_device, device=0,
+                          packed=False):
+        """Pointer-level cpn_analyze_batch[_device] (ints = raw addresses, or numpy arrays).  packed=True: cpn_analyze_batch_packed —
+        `lu` holds the log-likelihood ratios and `lm` the per-read base terms of pack_emissions (host pointers only)."""
+        ctx = self.ctx(device)
+        assert not (packed and on_device), "the packed entry point takes host pointers"
+        fn = self.dll.cpn_analyze_batch_packed if packed else (self.dll.cpn_analyze_batch_device if on_device else self.dll.cpn_analyze_batch)
         rc = fn(ctx, C.c_int64(R), _ptr(grp_off), _ptr(Nl), _ptr(rho_l), _ptr(d_l), _ptr(read_off), _ptr(lu), _ptr(lm), _ptr(phi0),
                 C.c_int32(n_init), C.c_int32(max_em_iters), C.c_double(box[0]), C.c_double(box[1]), C.c_double(box[2]), C.c_int32(mstep_mode),
                 _ptr(cpg_off), _ptr(rho_n), _ptr(d_n), _ptr(sub_off), _ptr(sub_p), _ptr(sub_q), _ptr(phi_hat), _ptr(Q), _ptr(status),

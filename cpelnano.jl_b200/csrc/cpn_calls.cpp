@@ -492,4 +492,52 @@ int cpn_region_filter(int64_t R, const int64_t* n_cpg, const int64_t* grp_off, c
     return CPN_OK;
 }
 
+// Packed form of an emission batch (see the header): llr = log_pyx_m − log_pyx_u per cell (NaN where unobserved),
+// read_base = Σ_obs log_pyx_u per read, accumulated left to right exactly as the device's packing kernel does (compiled with
+// -ffp-contract=off: plain IEEE subtraction and addition), so both routes into the EM give the same bits.  Regions are spread
+// over n_threads host threads in contiguous blocks of equal cell count.
+int cpn_pack_emissions(int64_t R, const int64_t* grp_off, const int64_t* read_off, const double* log_pyx_u, const double* log_pyx_m,
+                       double* llr, double* read_base, int32_t n_threads) {
+    if (R < 0 || (R > 0 && (!grp_off || !read_off || !log_pyx_u || !log_pyx_m || !llr || !read_base))) return CPN_ERR_ARG;
+    if (R == 0) return CPN_OK;
+    std::vector<int64_t> obs(R + 1);
+    obs[0] = 0;
+    for (int64_t r = 0; r < R; ++r) {
+        const int64_t L = grp_off[r + 1] - grp_off[r], M = read_off[r + 1] - read_off[r];
+        if (L < 0 || M < 0) return CPN_ERR_ARG;
+        obs[r + 1] = obs[r] + L * M;
+    }
+    const int nt = (int)std::max<int64_t>(1, std::min<int64_t>(n_threads > 0 ? n_threads : (int)std::thread::hardware_concurrency(), R));
+    std::atomic<int> bad{0};
+    auto work = [&](int t) {
+        const int64_t lo = std::lower_bound(obs.begin(), obs.end(), obs[R] / nt * t) - obs.begin();
+        const int64_t hi = t + 1 == nt ? R : std::lower_bound(obs.begin(), obs.end(), obs[R] / nt * (t + 1)) - obs.begin();
+        for (int64_t r = std::min(lo, R); r < std::min(hi, R); ++r) {
+            const int64_t L = grp_off[r + 1] - grp_off[r], M = read_off[r + 1] - read_off[r];
+            const double *u = log_pyx_u + obs[r], *m = log_pyx_m + obs[r];
+            double* d = llr + obs[r];
+            for (int64_t i = 0; i < M; ++i) {
+                double base = 0.0;
+                for (int64_t l = 0; l < L; ++l) {
+                    const double uu = u[i * L + l];
+                    if (uu == uu) {
+                        const double mm = m[i * L + l];
+                        if (mm != mm) bad.store(1);          // NaN marks "unobserved" in the packed table: an observed cell needs a number
+                        d[i * L + l] = mm - uu; base += uu;
+                    }
+                    else d[i * L + l] = std::numeric_limits<double>::quiet_NaN();
+                }
+                read_base[read_off[r] + i] = base;
+            }
+        }
+    };
+    if (nt == 1) work(0);
+    else {
+        std::vector<std::thread> th;
+        for (int t = 0; t < nt; ++t) th.emplace_back(work, t);
+        for (auto& x : th) x.join();
+    }
+    return bad.load() ? CPN_ERR_ARG : CPN_OK;
+}
+
 }  // extern "C"

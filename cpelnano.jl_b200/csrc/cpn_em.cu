@@ -36,7 +36,10 @@
 namespace {
 
 constexpr int TILE = 64;           // groups staged per shared-memory tile
-constexpr int E_WARPS = 4;         // warps (EM instances) per E-step block
+#ifndef E_WARPS_N
+#define E_WARPS_N 4
+#endif
+constexpr int E_WARPS = E_WARPS_N; // warps (EM instances) per E-step block
 constexpr int M_THREADS = 128;     // lanes (EM instances) per M-step block
 #ifndef WS_BLOCKS
 #define WS_BLOCKS 4                 // resident M-step blocks per SM the register budget is tuned for
@@ -118,7 +121,7 @@ __global__ void k_prep_sites(int64_t R, const int64_t* __restrict__ grp_off, con
 // RegionDesc::llrmax / idmax.
 // |LLR| is clamped at 300 with the dropped mass (< e^-300 relative) moved into the per-read base term.
 __global__ void k_prep_emis(int64_t R, const int64_t* __restrict__ grp_off, const int64_t* __restrict__ read_off,
-                            const int64_t* __restrict__ obs_off, const double* __restrict__ lu, const double* __restrict__ lm,
+                            const int64_t* __restrict__ obs_off, const double* __restrict__ lu, const double* __restrict__ lm, bool packed,
                             const int64_t* __restrict__ ew_off, const int64_t* __restrict__ rb_off, const double* __restrict__ invd,
                             double* __restrict__ ew, double* __restrict__ ewi, double* __restrict__ rb, RegionDesc* __restrict__ rdesc) {
     int64_t warp = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5;
@@ -129,7 +132,7 @@ __global__ void k_prep_emis(int64_t R, const int64_t* __restrict__ grp_off, cons
     int64_t M = read_off[warp + 1] - read_off[warp];
     int64_t nchunk = (M + 31) >> 5;
     const double* lu_r = lu + obs_off[warp];
-    const double* lm_r = lm + obs_off[warp];
+    const double* lm_r = packed ? lm + read_off[warp] : lm + obs_off[warp];      // packed: one base per read
     double dmax = 0.0;
     for (int64_t ch = 0; ch < nchunk; ++ch) {
         int64_t m = ch * 32 + lane;
@@ -139,10 +142,13 @@ __global__ void k_prep_emis(int64_t R, const int64_t* __restrict__ grp_off, cons
         for (int64_t l = 0; l < L; ++l) {
             double r = 1.0, ri = 1.0;
             if (m < M) {
-                double u = lu_r[m * L + l], v = lm_r[m * L + l];
+                // packed: u is the log-likelihood ratio itself and the read's Σ log p(y|−1) arrives ready-made; only what the
+                // clamp moves out of the ratio is added to it
+                double u = lu_r[m * L + l], v = packed ? 0.0 : lm_r[m * L + l];
                 if (u == u) {   // observed
-                    double d = v - u;
-                    if (d > LLR_CLAMP) { u = v - LLR_CLAMP; d = LLR_CLAMP; }
+                    double d = packed ? u : v - u;
+                    if (packed) u = 0.0;
+                    if (d > LLR_CLAMP) { u = packed ? d - LLR_CLAMP : v - LLR_CLAMP; d = LLR_CLAMP; }
                     else if (d < -LLR_CLAMP) { d = -LLR_CLAMP; }
                     r = exp(d); ri = exp(-d);
                     base += u;
@@ -152,7 +158,7 @@ __global__ void k_prep_emis(int64_t R, const int64_t* __restrict__ grp_off, cons
             dst[l * 32] = r;
             dsti[l * 32] = ri;
         }
-        rb[rb_off[warp] + ch * 32 + lane] = base;
+        rb[rb_off[warp] + ch * 32 + lane] = (packed && m < M) ? lm_r[m] + base : base;
     }
     double idm = 0.0;
     for (int64_t l = lane; l < L - 1; l += 32) idm = fmax(idm, invd[g0 + l]);
@@ -283,13 +289,62 @@ __device__ __forceinline__ void estep_rescale(EState& s) {
     s.fp *= sc; s.fm *= sc; s.gap *= sc; s.gam *= sc; s.gbp *= sc; s.gbm *= sc; s.gcp *= sc; s.gcm *= sc;
 }
 
-// Emission weights of a warp travel global → shared memory with cp.async (8 bytes per lane and group) into a private
-// ring: two slots of E_PF groups plus one slot for the chain tail.  A lane only ever reads what it copied itself, so no
-// warp synchronisation is needed; and because an asynchronous copy has no destination register, the deep prefetch costs
-// no registers (the register file is what limits the number of resident E-step warps).
+// Emission weights of a warp travel global → shared memory into a private ring: two slots of E_PF groups plus one slot for
+// the chain tail.  Two transports:
+//  * TMA (plain regions): the E_PF rows of a block are 2 KB contiguous in global memory, so lane 0 issues ONE bulk copy per
+//    block (cp.async.bulk, completion on an mbarrier of the warp).  ncu showed the L1/shared-memory data pipe, not the FP64 pipe,
+//    to be the busiest unit of this kernel (71 % vs 59 %): with per-lane cp.async every emission crossed it three times (L1
+//    read, shared-memory write, shared-memory read); the bulk copy goes L2 → shared memory past it and leaves the one LDS.64.
+//  * per-lane cp.async (views of the two-sample test, whose lanes read arbitrary pooled reads): 8 bytes per lane and group; a
+//    lane only ever reads what it copied itself, so no warp synchronisation is needed.
+// Either way the deep prefetch costs no registers (the register file is what limits the number of resident E-step warps).
 struct EmisRing { double r[3][E_PF][32]; };
 
-__device__ __forceinline__ void ering_issue(EmisRing& ring, int slot, const double* __restrict__ src /*row 0, this lane*/, int nrows, int lane) {
+__device__ __forceinline__ void mbar_init(unsigned mbar, unsigned count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(mbar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(unsigned mbar, unsigned parity) {
+    asm volatile(
+        "{\n"
+        ".reg .pred P1;\n"
+        "LAB_WAIT:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n"
+        "@P1 bra DONE;\n"
+        "bra LAB_WAIT;\n"
+        "DONE:\n"
+        "}" ::"r"(mbar), "r"(parity) : "memory");
+}
+// lane 0 only: arm the barrier with the byte count and start the bulk copy of `bytes` (multiple of 16) contiguous bytes
+__device__ __forceinline__ void tma_rows(unsigned dst, const double* __restrict__ src, unsigned bytes, unsigned mbar) {
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");       // the slot's earlier reads (generic proxy) precede the refill
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(mbar), "r"(bytes) : "memory");
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst), "l"(src), "r"(bytes),
+                 "r"(mbar) : "memory");
+}
+
+// What the two transports need to know about the chunk of reads a warp is working on.
+template <bool VIEW> struct EmisSrc;
+template <> struct EmisSrc<false> {
+    const double *p, *pi;      // row 0 of the chunk (lane 0) in the r and the 1/r plane
+    unsigned mbar;             // shared-memory address of the warp's three barriers (8 bytes apart), one per ring slot
+    unsigned ring;             // shared-memory address of the warp's ring
+    unsigned phase;            // bit s: parity the next completion of slot s will have
+};
+template <> struct EmisSrc<true> {
+    const double *p, *pi;      // this lane's read: its element of row 0 in either plane
+};
+
+// start the copy of rows [row0, row0 + nrows) of the plane chosen by `inv` into `slot` (nrows may be ≤ 0: nothing happens)
+__device__ __forceinline__ void ering_issue(EmisRing& ring, int slot, EmisSrc<false>& es, bool inv, int row0, int nrows, int lane) {
+    if (nrows > 0) {
+        __syncwarp();                                    // every lane is done with what the slot held
+        if (lane == 0)
+            tma_rows(es.ring + (unsigned)slot * (unsigned)(E_PF * 256), (inv ? es.pi : es.p) + row0 * 32, (unsigned)nrows * 256u,
+                     es.mbar + 8u * (unsigned)slot);
+    }
+}
+__device__ __forceinline__ void ering_issue(EmisRing& ring, int slot, EmisSrc<true>& es, bool inv, int row0, int nrows, int lane) {
+    const double* src = (inv ? es.pi : es.p) + (size_t)row0 * 32;
 #pragma unroll
     for (int u = 0; u < E_PF; ++u) {
         if (u < nrows) {
@@ -299,22 +354,32 @@ __device__ __forceinline__ void ering_issue(EmisRing& ring, int slot, const doub
     }
     asm volatile("cp.async.commit_group;");
 }
+// wait until the copy into `slot` has landed; `pending_after`: copies issued after it that may still be in flight (views)
+template <int PENDING_AFTER>
+__device__ __forceinline__ void ering_wait(EmisSrc<false>& es, int slot) {
+    mbar_wait(es.mbar + 8u * (unsigned)slot, (es.phase >> slot) & 1u);
+    es.phase ^= 1u << slot;
+}
+template <int PENDING_AFTER>
+__device__ __forceinline__ void ering_wait(EmisSrc<true>&, int) {
+    if (PENDING_AFTER == 0) asm volatile("cp.async.wait_group 0;");
+    else asm volatile("cp.async.wait_group 1;");
+}
 
 // Forward sweep of the conditional chain for the 32 reads of a chunk, carrying the tangents (∂a,∂b,∂c).
 // Groups are processed in blocks of E_PF: while one block of emission rows is consumed from the ring the next one is in
 // flight.  A block whose groups all have α_l ≥ 0 (or all α_l < 0; 97 % of the blocks of the simulated genome, because ρ_l is
 // small and a decides the sign) runs the matching specialised steps and reads 1/r (or r); a mixed block runs the general step.
 // The state is rescaled by a power of two between blocks (rmask = 0: before every block, 1: before every second one).
-template <bool BPOS>
+template <bool BPOS, bool VIEW>
 __device__ __forceinline__ void estep_chunk(SiteTile& st, EmisRing& ring, int L, int lane, const double* __restrict__ na_g,
-                                            const double* __restrict__ nb_g, const double* __restrict__ invd_g,
-                                            const double* __restrict__ p /*r of (group l, this lane's read) at p[l*32]*/,
-                                            const double* __restrict__ pi /*1/r, same indexing*/,
+                                            const double* __restrict__ nb_g, const double* __restrict__ invd_g, EmisSrc<VIEW>& es,
                                             double a, double b, double cabs, int rmask, double out[3]) {
     EState s{1.0, 1.0, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0};
     const int Lfull = L & ~(E_PF - 1);
+    constexpr unsigned ALL = (1u << E_PF) - 1;
     // the chain tail (always the general step, so always r) is in flight from the start
-    ering_issue(ring, 2, p + (size_t)Lfull * 32, L - Lfull, lane);
+    ering_issue(ring, 2, es, false, Lfull, L - Lfull, lane);
     int g = 0;                                          // index of the block of E_PF groups being consumed
     for (int l0 = 0; l0 < L; l0 += TILE) {
         const int n = min(TILE, L - l0);
@@ -323,21 +388,21 @@ __device__ __forceinline__ void estep_chunk(SiteTile& st, EmisRing& ring, int L,
         unsigned m0, m1;
         tile_load(tr, l0, n, lane, na_g, nb_g, invd_g, a, b, m0, m1);
         // first block of the tile: its plane is known as soon as the signs are; the copy overlaps the exponentials below
-        ering_issue(ring, g & 1, ((m0 & 0xffu) == 0xffu ? pi : p) + (size_t)g * E_PF * 32, nfull > 0 ? E_PF : 0, lane);
+        ering_issue(ring, g & 1, es, (m0 & ALL) == ALL, g * E_PF, nfull > 0 ? E_PF : 0, lane);
         __syncwarp();
         tile_store(st, tr, l0, n, lane, cabs, BPOS);
         __syncwarp();
 #pragma unroll 1
         for (int j0 = 0; j0 < nfull; j0 += E_PF, ++g) {
-            const unsigned bits = (((j0 & 32) ? m1 : m0) >> (j0 & 31)) & ((1u << E_PF) - 1);
-            // next block of this tile in flight, then wait until at most that one is pending: block g (and the tail) have landed
+            const unsigned bits = (((j0 & 32) ? m1 : m0) >> (j0 & 31)) & ALL;
+            // next block of this tile in flight, then wait for block g
             const int j1 = j0 + E_PF;
-            const unsigned bits1 = (((j1 & 32) ? m1 : m0) >> (j1 & 31)) & ((1u << E_PF) - 1);
-            ering_issue(ring, (g + 1) & 1, (bits1 == (1u << E_PF) - 1 ? pi : p) + (size_t)(g + 1) * E_PF * 32, (j1 < nfull) ? E_PF : 0, lane);
-            asm volatile("cp.async.wait_group 1;");
-            if (g > 0 && (g & rmask) == 0) estep_rescale(s);
+            const unsigned bits1 = (((j1 & 32) ? m1 : m0) >> (j1 & 31)) & ALL;
+            ering_issue(ring, (g + 1) & 1, es, bits1 == ALL, (g + 1) * E_PF, (j1 < nfull) ? E_PF : 0, lane);
             const int slot = g & 1;
-            if (bits == (1u << E_PF) - 1) {
+            ering_wait<1>(es, slot);
+            if (g > 0 && (g & rmask) == 0) estep_rescale(s);
+            if (bits == ALL) {
 #pragma unroll
                 for (int u = 0; u < E_PF; ++u) estep_site<BPOS, 1>(s, st, j0 + u, ring.r[slot][u][lane]);
             } else if (bits == 0u) {
@@ -350,13 +415,13 @@ __device__ __forceinline__ void estep_chunk(SiteTile& st, EmisRing& ring, int L,
         }
         // tail of the chain (fewer than E_PF groups left; only the last tile has one)
         if (nfull < n) {
-            asm volatile("cp.async.wait_group 0;");
+            ering_wait<0>(es, 2);
             if (g > 0) estep_rescale(s);
 #pragma unroll 1
             for (int u = 0; u < n - nfull; ++u) estep_site<BPOS, 0>(s, st, nfull + u, ring.r[2][u][lane]);
         }
     }
-    asm volatile("cp.async.wait_group 0;");
+    if (VIEW) asm volatile("cp.async.wait_group 0;");
     double inv = 1.0 / (s.fp + s.fm);
     out[0] = (s.gap + s.gam) * inv;
     out[1] = (s.gbp + s.gbm) * inv;
@@ -391,7 +456,14 @@ __device__ __noinline__ void estep_chunk_slow(SiteTile& st, int L, int lane, con
 #define E_BLOCKS 5
 #endif
 #ifndef E_PERSIST
-#define E_PERSIST 1                 // 1: resident grid, every warp walks the list with a block stride and prefetches its next instance
+#define E_PERSIST 0                 // 1: resident grid, every warp walks the list with a block stride and prefetches its next instance
+                                    // (measured 58-60 ms against 51 ms per 1e5 regions for one block per four instances: kept for experiments)
+#endif
+#ifndef E_PREFETCH
+#define E_PREFETCH 1
+#endif
+#ifndef E_CARVEOUT
+#define E_CARVEOUT 0
 #endif
 __device__ __forceinline__ void pf_l1(const void* p) { asm volatile("prefetch.global.L1 [%0];" ::"l"(p)); }
 
@@ -399,25 +471,54 @@ __device__ __forceinline__ void pf_l1(const void* p) { asm volatile("prefetch.gl
 // group tables → first rows of emissions) that the chain loop cannot start without; a warp therefore pulls the lines its NEXT
 // instance will need into L1 while it still works on the current one — descriptor and ϕ at the start, the group tables and the
 // first block of emission rows (both planes) when its chain ends, so that they travel during the reduction over reads.
+template <bool VIEW>
 __global__ void __launch_bounds__(E_WARPS * 32, E_BLOCKS) k_estep(int n_items, const ItemDesc* __restrict__ desc,
                                                                    const double* __restrict__ phil /*[3][cap] by list position*/, int64_t cap,
                                                                    RegionTables rt, int64_t NI, double* __restrict__ ES /*[3][NI]*/,
                                                                    const int* __restrict__ n_dev /*null, or the true item count*/) {
     __shared__ SiteTile tiles[E_WARPS];
     __shared__ EmisRing rings[E_WARPS];
+    __shared__ longlong4 nextd[E_WARPS];          // {L, first group, first emission} of the warp's next instance
+    __shared__ unsigned long long mbars[E_WARPS][4];   // per warp: one completion barrier per ring slot (TMA transport)
     const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    EmisSrc<VIEW> es;
+    if constexpr (!VIEW) {
+        es.mbar = (unsigned)__cvta_generic_to_shared(&mbars[w][0]);
+        es.ring = (unsigned)__cvta_generic_to_shared(&rings[w].r[0][0][0]);
+        es.phase = 0u;
+        if (lane == 0) {
+            mbar_init(es.mbar, 1u); mbar_init(es.mbar + 8u, 1u); mbar_init(es.mbar + 16u, 1u);
+            asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        }
+        __syncwarp();
+    }
     if (n_dev) n_items = __ldg(n_dev);
     const int stride = gridDim.x * E_WARPS;
+    // Every block walks its own items (list positions ≡ 4·blockIdx + w mod stride) starting from a different round, so that the
+    // blocks resident on an SM sit at different places of the length-sorted list: their instances then differ in length and the
+    // latency-bound heads of some overlap the pipe-bound chain loops of the others instead of all 20 warps marching in step.
+    const int rounds = E_PERSIST ? (n_items + stride - 1) / stride : 1;
+    const int k0 = E_PERSIST ? (int)(((unsigned)blockIdx.x * 7919u) % (unsigned)max(rounds, 1)) : 0;
 #pragma unroll 1
-    for (int item = blockIdx.x * E_WARPS + w; item < n_items; item += stride) {
-        const int next = item + stride;
-        const bool has_next = E_PERSIST && next < n_items;
-        if (has_next && lane < 4) pf_l1(lane == 0 ? (const void*)(desc + next) : (const void*)(phil + (size_t)(lane - 1) * cap + next));
-        // one round of independent loads: descriptor (two 16-byte vectors) and ϕ
+    for (int j = 0; j < rounds; ++j) {
+        int k = k0 + j; if (k >= rounds) k -= rounds;
+        const int item = k * stride + blockIdx.x * E_WARPS + w;
+        if (item >= n_items) continue;
+        int kn = k + 1; if (kn >= rounds) kn -= rounds;
+        const int next = kn * stride + blockIdx.x * E_WARPS + w;
+        const bool has_next = E_PERSIST && E_PREFETCH && j + 1 < rounds && next < n_items;
+        // one round of independent loads: descriptor (two 16-byte vectors) and ϕ; and, for later, the next instance's descriptor
         const int4* dq = reinterpret_cast<const int4*>(desc + item);
         const int4 d0 = __ldg(dq);
         const longlong2 d1 = __ldg(reinterpret_cast<const longlong2*>(dq + 1));
         double a = phil[item], b = phil[cap + item], c = phil[2 * cap + item];
+        if (has_next) {
+            const int4* nq = reinterpret_cast<const int4*>(desc + next);
+            const int4 n0 = __ldg(nq);
+            const longlong2 n1 = __ldg(reinterpret_cast<const longlong2*>(nq + 1));
+            if (lane < 3) pf_l1(phil + (size_t)lane * cap + next);
+            if (lane == 0) nextd[w] = make_longlong4((long long)n0.y, n1.x, n1.y, 0);
+        }
         const int inst = d0.x, L = d0.y, M = d0.z & ITEM_M_MASK, ridx = d0.w, mode = (d0.z >> ITEM_MODE_SHIFT) & 3;
         const int64_t g0 = d1.x;
         bool bpos = __double2hiint(c) >= 0;
@@ -429,29 +530,32 @@ __global__ void __launch_bounds__(E_WARPS * 32, E_BLOCKS) k_estep(int n_items, c
             double o[3];
             // this lane's read: lane of chunk ch, or — in a view — the pooled read the view's index row names
             int q = ch * 32 + lane;
-            if (ridx >= 0) q = __ldg(rt.ridx + ((size_t)(ridx + ch) << 5) + lane);
+            if (VIEW && ridx >= 0) q = __ldg(rt.ridx + ((size_t)(ridx + ch) << 5) + lane);
             const size_t po = (size_t)(q >> 5) * L * 32 + (q & 31);
             const double* p = ew_r + po;
             if (mode != 0) {
-                const double* pi = rt.ewi + d1.y + po;
-                if (bpos) estep_chunk<true>(tiles[w], rings[w], L, lane, rt.na + g0, rt.nb + g0, rt.invd + g0, p, pi, a, b, cabs, mode - 1, o);
-                else estep_chunk<false>(tiles[w], rings[w], L, lane, rt.na + g0, rt.nb + g0, rt.invd + g0, p, pi, a, b, cabs, mode - 1, o);
+                // plain regions: row 0 of the chunk (the bulk copy moves whole rows); views: this lane's pooled read
+                const size_t eo = VIEW ? po : (size_t)ch * L * 32;
+                es.p = ew_r + eo;
+                es.pi = rt.ewi + d1.y + eo;
+                if (bpos) estep_chunk<true, VIEW>(tiles[w], rings[w], L, lane, rt.na + g0, rt.nb + g0, rt.invd + g0, es, a, b, cabs, mode - 1, o);
+                else estep_chunk<false, VIEW>(tiles[w], rings[w], L, lane, rt.na + g0, rt.nb + g0, rt.invd + g0, es, a, b, cabs, mode - 1, o);
             } else {
                 if (bpos) estep_chunk_slow<true>(tiles[w], L, lane, rt.na + g0, rt.nb + g0, rt.invd + g0, p, a, b, cabs, o);
                 else estep_chunk_slow<false>(tiles[w], L, lane, rt.na + g0, rt.nb + g0, rt.invd + g0, p, a, b, cabs, o);
             }
             if (has_next && ch == nchunk - 1) {
                 // the next instance's group tables (lanes 0-14: five 128-byte lines of each of na, nb, 1/d) and the first E_PF rows
-                // of both emission planes (32 lines, one per lane)
-                const int4* nq = reinterpret_cast<const int4*>(desc + next);
-                const int Ln = __ldg(nq).y;
-                const longlong2 n1 = __ldg(reinterpret_cast<const longlong2*>(nq + 1));
+                // of both emission planes (32 lines, one per lane) travel while this instance's reads are reduced
+                __syncwarp();
+                const longlong4 nd = nextd[w];
+                const int Ln = (int)nd.x;
                 if (lane < 15) {
                     const int tb = lane / 5, ln = lane - 5 * tb;
-                    const double* base = (tb == 0 ? rt.na : (tb == 1 ? rt.nb : rt.invd)) + n1.x;
+                    const double* base = (tb == 0 ? rt.na : (tb == 1 ? rt.nb : rt.invd)) + nd.y;
                     if (ln * 16 < Ln + 16) pf_l1(base + ln * 16);
                 }
-                const double* pl = ((lane & 16) ? rt.ewi : rt.ew) + n1.y + (size_t)((lane >> 1) & 7) * 32 + (lane & 1) * 16;
+                const double* pl = ((lane & 16) ? rt.ewi : rt.ew) + nd.z + (size_t)((lane >> 1) & 7) * 32 + (lane & 1) * 16;
                 if (((lane >> 1) & 7) < Ln) pf_l1(pl);
             }
             bool live = ch * 32 + lane < M;
@@ -470,7 +574,8 @@ static unsigned estep_grid(cpn_ctx* ctx, int64_t n) {
     if (!E_PERSIST) return full;
     if (ctx->estep_blocks <= 0) {          // what the device really keeps resident (registers, shared-memory carveout), not what was asked for
         int nb = 0;
-        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k_estep, E_WARPS * 32, 0) != cudaSuccess || nb < 1) nb = 1;
+        if (E_CARVEOUT) cudaFuncSetAttribute(k_estep<false>, cudaFuncAttributePreferredSharedMemoryCarveout, (int)cudaSharedmemCarveoutMaxShared);
+        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k_estep<false>, E_WARPS * 32, 0) != cudaSuccess || nb < 1) nb = 1;
         ctx->estep_blocks = nb;
     }
     return std::min<unsigned>(full, (unsigned)(ctx->sm_count * ctx->estep_blocks));
@@ -1492,7 +1597,8 @@ static void trace(const cpn_ctx* ctx, const char* what) {
 // Uploads (or borrows) the CSR inputs and builds the per-group and per-read device tables.
 int pack_regions(cpn_ctx* ctx, PackedRegions& pk, bool on_device, bool with_reads, int64_t R, const int64_t* grp_off,
                  const double* Nl, const double* rho_l, const double* d_l, const int64_t* read_off, const double* lu, const double* lm,
-                 int offs_mode = -1 /*-1: offsets live where the data lives; 0: offsets on the host, data per on_device*/) {
+                 int offs_mode = -1 /*-1: offsets live where the data lives; 0: offsets on the host, data per on_device*/,
+                 bool packed = false /*lu = log-likelihood ratios, lm = per-read Σ_obs log p(y|−1) (cpn_pack_emissions)*/) {
     cudaStream_t s = ctx->stream;
     const bool offs_dev = offs_mode < 0 ? on_device : offs_mode != 0;
     pk.R = R;
@@ -1553,10 +1659,10 @@ int pack_regions(cpn_ctx* ctx, PackedRegions& pk, bool on_device, bool with_read
         CPN_CUDA(ctx, pk.rb.alloc(h_rb[R], s));
         CPN_CUDA(ctx, pk.lu.bind(lu, pk.n_obs, on_device, s));
         trace(ctx, "pk-lu");
-        CPN_CUDA(ctx, pk.lm.bind(lm, pk.n_obs, on_device, s));
+        CPN_CUDA(ctx, pk.lm.bind(lm, packed ? pk.h_read_off[R] : pk.n_obs, on_device, s));
         trace(ctx, "pk-lm");
         { KTimer kt(ctx, CPN_K_PREP);
-          k_prep_emis<<<blocks_for(R * 32, 128), 128, 0, s>>>(R, pk.grp_off.p, pk.read_off.p, pk.obs_off.p, pk.lu.p, pk.lm.p, pk.ew_off.p,
+          k_prep_emis<<<blocks_for(R * 32, 128), 128, 0, s>>>(R, pk.grp_off.p, pk.read_off.p, pk.obs_off.p, pk.lu.p, pk.lm.p, packed, pk.ew_off.p,
                                                               pk.rb_off.p, pk.invd.p, pk.ew.p, pk.ewi.p, pk.rb.p, pk.rdesc.p); }
         // the raw emissions are not needed once packed: hand the memory back (stream-ordered) before the EM loop
         pk.lm.own.release();
@@ -1613,20 +1719,21 @@ struct StagedBatch {
 
 int fit_stage(cpn_ctx* ctx, StagedBatch& sb, bool on_device, int64_t R, const int64_t* grp_off, const double* Nl, const double* rho_l,
               const double* d_l, const int64_t* read_off, const double* lu, const double* lm, const double* phi0, int32_t n_init,
-              int offs_mode = -1, int64_t n_units = -1 /*EM units the starts are for; default: the R regions*/) {
+              int offs_mode = -1, int64_t n_units = -1 /*EM units the starts are for; default: the R regions*/, bool packed = false) {
     CPN_CUDA(ctx, cudaSetDevice(ctx->device));
     CpnArenaScope scope(sb.arena);
     // ϕ0 first: the raw emissions must stay on top of the workspace stack
     sb.seeded = phi0 == nullptr;
     if (!sb.seeded) CPN_CUDA(ctx, sb.phi0.bind(phi0, (n_units < 0 ? R : n_units) * n_init * 3, on_device, ctx->stream));
-    return pack_regions(ctx, sb.pk, on_device, true, R, grp_off, Nl, rho_l, d_l, read_off, lu, lm, offs_mode);
+    return pack_regions(ctx, sb.pk, on_device, true, R, grp_off, Nl, rho_l, d_l, read_off, lu, lm, offs_mode, packed);
 }
 
 // `pre` = inputs staged earlier (possibly on another context's stream, already synchronised); the input pointers are then unused.
 int fit_impl(cpn_ctx* ctx, bool on_device, int64_t R, const int64_t* grp_off, const double* Nl, const double* rho_l, const double* d_l,
              const int64_t* read_off, const double* lu, const double* lm, const double* phi0, int32_t n_init, int32_t max_em_iters,
              double amax, double bmax, double cmax, int32_t mstep_mode, double* phi_hat, double* Q, int32_t* status, int64_t* counters,
-             double* phi_starts, double* Q_starts, const SummaryArgs* sa = nullptr, StagedBatch* pre = nullptr, int offs_mode = -1) {
+             double* phi_starts, double* Q_starts, const SummaryArgs* sa = nullptr, StagedBatch* pre = nullptr, int offs_mode = -1,
+             bool packed = false) {
     const bool offs_dev = offs_mode < 0 ? on_device : offs_mode != 0;
     CPN_ARG(ctx, R >= 0 && n_init >= 1 && max_em_iters >= 1, "R >= 0, n_init >= 1, max_em_iters >= 1");
     CPN_ARG(ctx, pre || (grp_off && Nl && rho_l && d_l && read_off && lu && lm), "null pointer");
@@ -1648,7 +1755,7 @@ int fit_impl(cpn_ctx* ctx, bool on_device, int64_t R, const int64_t* grp_off, co
             local.arena = &ctx->stage_arena;
             local.seed = ctx->seed;
             local.unit_base = ctx->region_base;
-            int rc = fit_stage(ctx, local, on_device, R, grp_off, Nl, rho_l, d_l, read_off, lu, lm, phi0, n_init);
+            int rc = fit_stage(ctx, local, on_device, R, grp_off, Nl, rho_l, d_l, read_off, lu, lm, phi0, n_init, -1, -1, packed);
             if (rc) return rc;
         }
         PackedRegions& pk = sb->pk;
@@ -1733,7 +1840,8 @@ int fit_impl(cpn_ctx* ctx, bool on_device, int64_t R, const int64_t* grp_off, co
             { KTimer kt(ctx, CPN_K_PREP);
               k_make_desc<<<blocks_for(ub, 256), 256, 0, s>>>(ub, cur, n_init, rt.rdesc, phi.p, NI, idesc.p, phil.p, NI, n_dev); }
             { KTimer kt(ctx, CPN_K_ESTEP);
-              k_estep<<<estep_grid(ctx, ub), E_WARPS * 32, 0, s>>>(ub, idesc.p, phil.p, NI, rt, NI, ES.p, n_dev); }
+              if (views) k_estep<true><<<estep_grid(ctx, ub), E_WARPS * 32, 0, s>>>(ub, idesc.p, phil.p, NI, rt, NI, ES.p, n_dev);
+              else k_estep<false><<<estep_grid(ctx, ub), E_WARPS * 32, 0, s>>>(ub, idesc.p, phil.p, NI, rt, NI, ES.p, n_dev); }
             if (mstep_mode == CPN_MSTEP_ANALYTIC) {
                 unsigned grid = std::min<unsigned>(blocks_for(ub, M_THREADS), (unsigned)(ctx->sm_count * ws_blocks_per_sm));
                 { KTimer kt(ctx, CPN_K_MSTEP);
@@ -1979,7 +2087,7 @@ extern "C" {
 static int fit_chunked(cpn_ctx* ctx, bool on_device, int64_t R, const int64_t* grp_off_in, const double* Nl, const double* rho_l,
                        const double* d_l, const int64_t* read_off_in, const double* lu, const double* lm, const double* phi0, int32_t n_init,
                        int32_t max_em_iters, double amax, double bmax, double cmax, int32_t mstep_mode, double* phi_hat, double* Q,
-                       int32_t* status, int64_t* counters, double* phi_starts, double* Q_starts, const SummaryArgs* sa_in) {
+                       int32_t* status, int64_t* counters, double* phi_starts, double* Q_starts, const SummaryArgs* sa_in, bool packed = false) {
     // Chunk plan: K chunks whose costs (M·L summed over regions) grow geometrically, so the first upload — the only one that
     // nothing overlaps — is short, while later chunks are big enough to keep the EM kernels' late, sparsely populated
     // iterations amortised.  Device-resident inputs have nothing to upload and run as one batch unless CPN_DEVICE_CHUNKS asks
@@ -1996,7 +2104,7 @@ static int fit_chunked(cpn_ctx* ctx, bool on_device, int64_t R, const int64_t* g
     if (R / chunk_regions > 1 && n_workers >= 1 && getenv(cvar)) C = (int)std::min<int64_t>(std::max(1, env_int(cvar, C)), R);
     if (C <= 1)
         return fit_impl(ctx, on_device, R, grp_off_in, Nl, rho_l, d_l, read_off_in, lu, lm, phi0, n_init, max_em_iters, amax, bmax, cmax,
-                        mstep_mode, phi_hat, Q, status, counters, phi_starts, Q_starts, sa_in);
+                        mstep_mode, phi_hat, Q, status, counters, phi_starts, Q_starts, sa_in, nullptr, -1, packed);
     CPN_ARG(ctx, Nl && rho_l && d_l && lu && lm && phi_hat && Q, "null pointer");
     CPN_ARG(ctx, n_init >= 1, "n_init >= 1");
     CPN_CUDA(ctx, cudaSetDevice(ctx->device));
@@ -2110,8 +2218,8 @@ static int fit_chunked(cpn_ctx* ctx, bool on_device, int64_t R, const int64_t* g
                 slot[c]->seed = ctx->seed;
                 slot[c]->unit_base = ctx->region_base + r0;   // seeded starts are keyed by the region's position in the whole batch
                 trace(u, "stage");
-                r = fit_stage(u, *slot[c], on_device, Rc, g.data(), Nl + g0, rho_l + g0, d_l + (g0 - r0), rd.data(), lu + obs[r0], lm + obs[r0],
-                              phi0 ? phi0 + r0 * n_init * 3 : nullptr, n_init, 0);
+                r = fit_stage(u, *slot[c], on_device, Rc, g.data(), Nl + g0, rho_l + g0, d_l + (g0 - r0), rd.data(), lu + obs[r0],
+                              lm + (packed ? read_off[r0] : obs[r0]), phi0 ? phi0 + r0 * n_init * 3 : nullptr, n_init, 0, -1, packed);
                 if (r == CPN_OK && cpn_wait_stream(u, u->stream) != cudaSuccess) { u->err = "stream synchronize failed"; r = CPN_ERR_CUDA; }
                 launches[0] = u->last_launches;
                 trace(u, "staged");
@@ -2209,7 +2317,7 @@ static int fit_chunked(cpn_ctx* ctx, bool on_device, int64_t R, const int64_t* g
 static int multi_fit(cpn_ctx* ctx, int64_t R, const int64_t* grp_off, const double* Nl, const double* rho_l, const double* d_l,
                      const int64_t* read_off, const double* lu, const double* lm, const double* phi0, int32_t n_init, int32_t max_em_iters,
                      double amax, double bmax, double cmax, int32_t mstep_mode, double* phi_hat, double* Q, int32_t* status, int64_t* counters,
-                     double* phi_starts, double* Q_starts, const SummaryArgs* sa) {
+                     double* phi_starts, double* Q_starts, const SummaryArgs* sa, bool packed = false) {
     CPN_ARG(ctx, R >= 0 && grp_off && read_off, "null pointer");
     const int nd = (int)ctx->devs.size();
     std::vector<int64_t> obs(R + 1);
@@ -2244,10 +2352,11 @@ static int multi_fit(cpn_ctx* ctx, int64_t R, const int64_t* grp_off, const doub
                 sc = SummaryArgs{cp.data(), sb.data(), sa->sub_p + k0, sa->sub_q + k0, sa->rho_n + n0, sa->d_n + (n0 - r0), sa->logZ + r0, sa->ex + n0,
                                  sa->exx + (n0 - r0), sa->log_g + 4 * k0, sa->e_log_g1 + k0, sa->e_log_g2 + k0, sa->mml + k0, sa->nme + k0};
             }
-            rc[d] = fit_chunked(c, false, Rd, g.data(), Nl + g0, rho_l + g0, d_l + (g0 - r0), rd.data(), lu + obs[r0], lm + obs[r0],
+            rc[d] = fit_chunked(c, false, Rd, g.data(), Nl + g0, rho_l + g0, d_l + (g0 - r0), rd.data(), lu + obs[r0],
+                                lm + (packed ? read_off[r0] : obs[r0]),
                                 phi0 ? phi0 + r0 * n_init * 3 : nullptr, n_init, max_em_iters, amax, bmax, cmax, mstep_mode, phi_hat + 3 * r0, Q + r0,
                                 status ? status + r0 : nullptr, counters ? counters + 4 * r0 : nullptr,
-                                phi_starts ? phi_starts + r0 * n_init * 3 : nullptr, Q_starts ? Q_starts + r0 * n_init : nullptr, sa ? &sc : nullptr);
+                                phi_starts ? phi_starts + r0 * n_init * 3 : nullptr, Q_starts ? Q_starts + r0 * n_init : nullptr, sa ? &sc : nullptr, packed);
             c->region_base = 0;
         });
     }
@@ -2297,7 +2406,7 @@ static int analyze_common(cpn_ctx* ctx, bool dev, int64_t R, const int64_t* grp_
                           double amax, double bmax, double cmax, int32_t mstep_mode, const int64_t* cpg_off, const double* rho_n,
                           const double* d_n, const int64_t* sub_off, const int64_t* sub_p, const int64_t* sub_q, double* phi_hat, double* Q,
                           int32_t* status, int64_t* counters, double* logZ, double* ex, double* exx, double* log_g, double* e_log_g1,
-                          double* e_log_g2, double* mml, double* nme) {
+                          double* e_log_g2, double* mml, double* nme, bool packed = false) {
     if (!ctx) return CPN_ERR_ARG;
     CPN_ARG(ctx, cpg_off && rho_n && d_n && sub_off && sub_p && sub_q, "null per-CpG input pointer");
     SummaryArgs sa{cpg_off, sub_off, sub_p, sub_q, rho_n, d_n, logZ, ex, exx, log_g, e_log_g1, e_log_g2, mml, nme};
@@ -2305,12 +2414,12 @@ static int analyze_common(cpn_ctx* ctx, bool dev, int64_t R, const int64_t* grp_
         CPN_ARG(ctx, logZ && ex && exx && log_g && e_log_g1 && e_log_g2 && mml && nme, "null output pointer");
         if (ctx->devs.size() > 1)
             return multi_fit(ctx, R, grp_off, Nl, rho_l, d_l, read_off, lu, lm, phi0, n_init, max_em_iters, amax, bmax, cmax, mstep_mode, phi_hat, Q,
-                             status, counters, nullptr, nullptr, &sa);
+                             status, counters, nullptr, nullptr, &sa, packed);
         return fit_chunked(ctx, false, R, grp_off, Nl, rho_l, d_l, read_off, lu, lm, phi0, n_init, max_em_iters, amax, bmax, cmax, mstep_mode,
-                                phi_hat, Q, status, counters, nullptr, nullptr, &sa);
+                                phi_hat, Q, status, counters, nullptr, nullptr, &sa, packed);
     }
     return fit_chunked(ctx, true, R, grp_off, Nl, rho_l, d_l, read_off, lu, lm, phi0, n_init, max_em_iters, amax, bmax, cmax, mstep_mode,
-                       phi_hat, Q, status, counters, nullptr, nullptr, &sa);
+                       phi_hat, Q, status, counters, nullptr, nullptr, &sa, packed);
 }
 
 int cpn_analyze_batch(cpn_ctx* ctx, int64_t R, const int64_t* grp_off, const double* Nl, const double* rho_l, const double* d_l,
@@ -2332,6 +2441,30 @@ int cpn_analyze_batch_device(cpn_ctx* ctx, int64_t R, const int64_t* grp_off, co
     return analyze_common(ctx, true, R, grp_off, Nl, rho_l, d_l, read_off, log_pyx_u, log_pyx_m, phi0, n_init, max_em_iters, amax, bmax, cmax,
                           mstep_mode, cpg_off, rho_n, d_n, sub_off, sub_p, sub_q, phi_hat, Q, status, counters, logZ, ex, exx, log_g, e_log_g1,
                           e_log_g2, mml, nme);
+}
+
+// Packed emissions (cpn_pack_emissions): one log-likelihood ratio per (read, group) and one Σ_obs log p(y|−1) per read — what
+// the kernels consume, and half the bytes of the two log-likelihood tables on the way to the device.
+int cpn_fit_batch_packed(cpn_ctx* ctx, int64_t R, const int64_t* grp_off, const double* Nl, const double* rho_l, const double* d_l,
+                         const int64_t* read_off, const double* llr, const double* read_base, const double* phi0, int32_t n_init,
+                         int32_t max_em_iters, double amax, double bmax, double cmax, int32_t mstep_mode, double* phi_hat, double* Q,
+                         int32_t* status, int64_t* counters, double* phi_starts, double* Q_starts) {
+    if (!ctx) return CPN_ERR_ARG;
+    if (ctx->devs.size() > 1)
+        return multi_fit(ctx, R, grp_off, Nl, rho_l, d_l, read_off, llr, read_base, phi0, n_init, max_em_iters, amax, bmax, cmax, mstep_mode,
+                         phi_hat, Q, status, counters, phi_starts, Q_starts, nullptr, true);
+    return fit_chunked(ctx, false, R, grp_off, Nl, rho_l, d_l, read_off, llr, read_base, phi0, n_init, max_em_iters, amax, bmax, cmax, mstep_mode,
+                       phi_hat, Q, status, counters, phi_starts, Q_starts, nullptr, true);
+}
+int cpn_analyze_batch_packed(cpn_ctx* ctx, int64_t R, const int64_t* grp_off, const double* Nl, const double* rho_l, const double* d_l,
+                             const int64_t* read_off, const double* llr, const double* read_base, const double* phi0, int32_t n_init,
+                             int32_t max_em_iters, double amax, double bmax, double cmax, int32_t mstep_mode, const int64_t* cpg_off,
+                             const double* rho_n, const double* d_n, const int64_t* sub_off, const int64_t* sub_p, const int64_t* sub_q,
+                             double* phi_hat, double* Q, int32_t* status, int64_t* counters, double* logZ, double* ex, double* exx,
+                             double* log_g, double* e_log_g1, double* e_log_g2, double* mml, double* nme) {
+    return analyze_common(ctx, false, R, grp_off, Nl, rho_l, d_l, read_off, llr, read_base, phi0, n_init, max_em_iters, amax, bmax, cmax,
+                          mstep_mode, cpg_off, rho_n, d_n, sub_off, sub_p, sub_q, phi_hat, Q, status, counters, logZ, ex, exx, log_g, e_log_g1,
+                          e_log_g2, mml, nme, true);
 }
 
 int cpn_estep_batch(cpn_ctx* ctx, int64_t R, const int64_t* grp_off, const double* Nl, const double* rho_l, const double* d_l,
@@ -2358,7 +2491,7 @@ int cpn_estep_batch(cpn_ctx* ctx, int64_t R, const int64_t* grp_off, const doubl
                 CPN_CUDA(ctx, idesc.alloc(R, s)); CPN_CUDA(ctx, phil.alloc(3 * R, s));
         { KTimer kt(ctx, CPN_K_PREP);
           k_make_desc<<<blocks_for(R, 256), 256, 0, s>>>((int)R, nullptr, 1, pk.rt.rdesc, d_phi.p, R, idesc.p, phil.p, R, nullptr); }
-        { KTimer kt(ctx, CPN_K_ESTEP); k_estep<<<estep_grid(ctx, R), E_WARPS * 32, 0, s>>>((int)R, idesc.p, phil.p, R, pk.rt, R, d_ES.p, nullptr); }
+        { KTimer kt(ctx, CPN_K_ESTEP); k_estep<false><<<estep_grid(ctx, R), E_WARPS * 32, 0, s>>>((int)R, idesc.p, phil.p, R, pk.rt, R, d_ES.p, nullptr); }
         { KTimer kt(ctx, CPN_K_PREP); k_unpack3<<<blocks_for(R, 256), 256, 0, s>>>(R, d_ES.p, d_ESo.p); }
         CPN_CUDA(ctx, d_ESo.download(ES, 3 * R, s));
         if (ave_logpy) {

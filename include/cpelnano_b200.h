@@ -148,6 +148,36 @@ int cpn_analyze_batch_device(cpn_ctx* ctx, int64_t R,
                   double* logZ, double* ex, double* exx, double* log_g,
                   double* e_log_g1, double* e_log_g2, double* mml, double* nme);
 
+/* ---- packed emissions -------------------------------------------------------------------------------------------
+ * The emissions of a read enter the model only through the log-likelihood ratio of every observed group and through the
+ * read's Σ_obs log p(y|−1) (transfer_matrix.jl:632-643, :843-870: γ_l(x) and log p(y_m) − SURVEY.md A.3), so the two
+ * tables of structures.jl:121-128 can be handed over as
+ *   llr        [Σ_r M_r·L_r]  log_pyx_m − log_pyx_u per (read, group), NaN = unobserved (same order as log_pyx_*)
+ *   read_base  [Σ_r M_r]      Σ over the observed groups of the read of log_pyx_u, added left to right
+ * — half the bytes on PCIe.  cpn_pack_emissions (host, multi-threaded, no CUDA) computes both from the two tables with the
+ * arithmetic of the device's own packing kernel, so the *_packed entry points return bit-identical results to their
+ * two-table twins (as long as no |LLR| exceeds the clamp at 300).  All other arguments as in cpn_fit_batch /
+ * cpn_analyze_batch (host pointers).                                                                                   */
+int cpn_pack_emissions(int64_t R, const int64_t* grp_off, const int64_t* read_off, const double* log_pyx_u,
+                       const double* log_pyx_m, double* llr, double* read_base, int32_t n_threads);
+int cpn_fit_batch_packed(cpn_ctx* ctx, int64_t R,
+                  const int64_t* grp_off, const double* Nl, const double* rho_l, const double* d_l,
+                  const int64_t* read_off, const double* llr, const double* read_base,
+                  const double* phi0, int32_t n_init, int32_t max_em_iters,
+                  double amax, double bmax, double cmax, int32_t mstep_mode,
+                  double* phi_hat, double* Q, int32_t* status, int64_t* counters,
+                  double* phi_starts, double* Q_starts);
+int cpn_analyze_batch_packed(cpn_ctx* ctx, int64_t R,
+                  const int64_t* grp_off, const double* Nl, const double* rho_l, const double* d_l,
+                  const int64_t* read_off, const double* llr, const double* read_base,
+                  const double* phi0, int32_t n_init, int32_t max_em_iters,
+                  double amax, double bmax, double cmax, int32_t mstep_mode,
+                  const int64_t* cpg_off, const double* rho_n, const double* d_n,
+                  const int64_t* sub_off, const int64_t* sub_p, const int64_t* sub_q,
+                  double* phi_hat, double* Q, int32_t* status, int64_t* counters,
+                  double* logZ, double* ex, double* exx, double* log_g,
+                  double* e_log_g1, double* e_log_g2, double* mml, double* nme);
+
 /* Building blocks of em_iter exposed for parity tests (host pointers):
  *   cpn_estep_batch   ES[r] = get_ess(map(get_cond_exs_log))  src/em_algorithm.jl:142-146 at phi[r]
  *                     and ave_logpy[r] = comp_ave_log_py (:263-288) at the same phi (may be NULL)

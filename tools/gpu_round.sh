@@ -34,7 +34,7 @@ for st in "$@"; do
                  python bench.py --workload group --regions 200000 --no-cpu --steps 1 --warmup 1 > $O/${TAG}_ncu_group.out 2>&1; echo "ncu_group rc=$?" ;;
     ncu_two)   timeout 900 $NCU --set full --import-source on -k regex:'k_two_samp_pvals|k_two_samp_views|k_score' -c 3 -o $O/${TAG}_ncu_two -f \
                  python bench.py --workload two-sample --regions 64 --no-cpu --steps 1 --warmup 1 > $O/${TAG}_ncu_two.out 2>&1; echo "ncu_two rc=$?" ;;
-    parity)    timeout 900 python -m pytest tests/test_gpu_parity.py tests/test_pipeline_gpu.py -m gpu -x -q > $O/${TAG}_parity.log 2>&1; echo "parity rc=$?"; tail -3 $O/${TAG}_parity.log ;;
+    parity)    timeout 180 python -m pytest tests/test_gpu_parity.py tests/test_pipeline_gpu.py -m gpu -x -q > $O/${TAG}_parity.log 2>&1; echo "parity rc=$?"; tail -3 $O/${TAG}_parity.log ;;
     ab)        bash tools/ab.sh 100000 $AB_LIBS > $O/${TAG}_ab.txt 2>&1; cat $O/${TAG}_ab.txt ;;
     trace)     CPN_TRACE=1 timeout 600 python bench.py --no-cpu --steps 1 --warmup 2 > $O/${TAG}_trace.json 2> $O/${TAG}_trace.err; echo "trace rc=$?" ;;
     *) echo "unknown stage $st" ;;
