@@ -12,6 +12,7 @@ is the host-side mirror of the reference's Julia interface for that path (same n
     unmat_est_reg_test / mat_est_reg_test          src/grp_perm_tests.jl:200 / :432
     pmap_two_samp_null_stats                       src/two_samp_perm_tests.jl:41
     analyze_regions (batched pmap_analyze_reg)     src/nanopore.jl:292,406
+    analyze_regions_wgbs (pmap_analyze_reg_bam)    src/wgbs.jl:335, get_ϕhat_wgbs! src/em_algorithm.jl:556
 
 There is no CPU fallback: importing works anywhere, but every compute call needs the CUDA library and a
 B200; a missing library raises at first use.
@@ -21,7 +22,7 @@ The directory name contains a dot, so it is loaded through `cpelnano_b200.py` at
 """
 from .capi import Library, CpnError, lib_path, MSTEP_FD, MSTEP_ANALYTIC   # noqa: F401
 from .host import (CpelNanoConfig, RegStruct, Engine, get_phihat, rscle_grp_mod, get_nls_reg_info, get_stat_sums,   # noqa: F401
-                   comp_cmd, unmat_est_reg_test, mat_est_reg_test, pmap_two_samp_null_stats, analyze_regions, default_engine)
+                   comp_cmd, unmat_est_reg_test, mat_est_reg_test, pmap_two_samp_null_stats, analyze_regions, analyze_regions_wgbs, default_engine)
 from . import simulations   # noqa: F401
 from . import sharding      # noqa: F401
 from . import genome        # noqa: F401
@@ -31,5 +32,5 @@ from . import pipeline      # noqa: F401
 from .pipeline import analyze_nano, analyze_nano_csr, merge_shards, diff_grp_comp, diff_grp_comp_csr, diff_two_samp_comp   # noqa: F401
 
 __all__ = ["Library", "CpnError", "Engine", "CpelNanoConfig", "RegStruct", "get_phihat", "rscle_grp_mod", "get_nls_reg_info",
-           "get_stat_sums", "comp_cmd", "unmat_est_reg_test", "mat_est_reg_test", "pmap_two_samp_null_stats", "analyze_regions",
+           "get_stat_sums", "comp_cmd", "unmat_est_reg_test", "mat_est_reg_test", "pmap_two_samp_null_stats", "analyze_regions", "analyze_regions_wgbs",
            "simulations", "sharding", "genome", "nanopolish", "outputs", "pipeline", "analyze_nano", "analyze_nano_csr", "merge_shards", "diff_grp_comp_csr", "diff_grp_comp", "diff_two_samp_comp", "default_engine", "MSTEP_FD", "MSTEP_ANALYTIC"]

@@ -14,7 +14,7 @@ FIT_NONE, FIT_NUMERICAL, FIT_FILTERED = -1, -2, -16        # status words (inclu
 
 # every exported symbol of include/cpelnano_b200.h (tests check the library exports exactly these)
 SYMBOLS = ["cpn_create", "cpn_create_multi", "cpn_num_devices", "cpn_destroy", "cpn_last_error", "cpn_version", "cpn_last_device_ms", "cpn_last_launches", "cpn_last_work",
-           "cpn_measure_fp64_peak", "cpn_set_seed", "cpn_rng_phi0", "cpn_rng_perm", "cpn_set_profile", "cpn_get_profile", "cpn_analyze_batch", "cpn_analyze_batch_device", "cpn_fit_batch", "cpn_fit_batch_device", "cpn_pack_emissions", "cpn_fit_batch_packed", "cpn_analyze_batch_packed", "cpn_estep_batch", "cpn_mstep_batch",
+           "cpn_measure_fp64_peak", "cpn_set_seed", "cpn_rng_phi0", "cpn_rng_perm", "cpn_set_profile", "cpn_get_profile", "cpn_analyze_batch", "cpn_analyze_batch_device", "cpn_fit_batch", "cpn_fit_batch_device", "cpn_pack_emissions", "cpn_fit_batch_packed", "cpn_analyze_batch_packed", "cpn_wgbs_pack", "cpn_analyze_wgbs_batch", "cpn_estep_batch", "cpn_mstep_batch",
            "cpn_stat_sums_batch", "cpn_nls_reg_info", "cpn_cmd_batch", "cpn_grp_unmat_sweep", "cpn_grp_mat_sweep", "cpn_two_samp_pvals", "cpn_two_samp_null_batch", "cpn_two_samp_test_batch", "cpn_grp_test_batch", "cpn_grp_test_batch_device", "cpn_region_filter",
            "cpn_calls_open", "cpn_calls_close", "cpn_calls_open_error", "cpn_calls_error", "cpn_calls_num_lines", "cpn_calls_num_reads", "cpn_calls_num_chr",
            "cpn_calls_chr_name", "cpn_calls_chr_lines", "cpn_calls_read_name", "cpn_calls_count_reads", "cpn_calls_fill",
@@ -185,6 +185,40 @@ class Library:
         out = dict(phi_hat=phi_hat, Q=Q, pick=status, counters=counters)
         if per_start:
             out.update(phi_starts=ps, Q_starts=qs)
+        return out
+
+    def wgbs_pack(self, cpg_off, read_off, calls, n_threads=0):
+        """cpn_wgbs_pack: WGBS calls (int8 −1/0/+1 per read and CpG) → packed hard emissions (llr, read_base)."""
+        cpg_off, read_off = _i64(cpg_off), _i64(read_off)
+        calls = np.ascontiguousarray(calls, dtype=np.int8)
+        R = len(cpg_off) - 1
+        llr, base = np.empty(calls.size), np.empty(int(read_off[-1]))
+        rc = self.dll.cpn_wgbs_pack(C.c_int64(R), _ptr(cpg_off), _ptr(read_off), _ptr(calls), _ptr(llr), _ptr(base), C.c_int32(n_threads))
+        if rc != 0:
+            raise CpnError(f"cpn_wgbs_pack failed with code {rc} (calls must be -1, 0 or +1)")
+        return llr, base
+
+    def analyze_wgbs_batch(self, cpg_off, rho_n, d_n, read_off, calls, phi0, n_init, sub_off, sub_p, sub_q, max_em_iters=20,
+                           box=(20.0, 150.0, 50.0), mstep_mode=MSTEP_ANALYTIC, device=0):
+        """cpn_analyze_wgbs_batch: batched pmap_analyze_reg_bam (get_ϕhat_wgbs! + get_stat_sums!) from per-CpG calls."""
+        cpg_off, read_off, sub_off, sub_p, sub_q = (_i64(a) for a in (cpg_off, read_off, sub_off, sub_p, sub_q))
+        rho_n, d_n = _f64(rho_n), _f64(d_n)
+        calls = np.ascontiguousarray(calls, dtype=np.int8)
+        R = len(cpg_off) - 1
+        if phi0 is not None:
+            phi0 = _f64(phi0)
+            assert phi0.size == R * n_init * 3
+        sN, sK = int(cpg_off[-1]), int(sub_off[-1])
+        out = dict(phi_hat=np.empty((R, 3)), Q=np.empty(R), pick=np.empty(R, dtype=np.int32), counters=np.empty((R, 4), dtype=np.int64),
+                   logZ=np.empty(R), ex=np.empty(sN), exx=np.empty(sN - R), log_g=np.empty((sK, 4)), e_log_g1=np.empty(sK),
+                   e_log_g2=np.empty(sK), mml=np.empty(sK), nme=np.empty(sK))
+        ctx = self.ctx(device)
+        rc = self.dll.cpn_analyze_wgbs_batch(ctx, C.c_int64(R), _ptr(cpg_off), _ptr(rho_n), _ptr(d_n), _ptr(read_off), _ptr(calls), _ptr(phi0),
+                                             C.c_int32(n_init), C.c_int32(max_em_iters), C.c_double(box[0]), C.c_double(box[1]), C.c_double(box[2]),
+                                             C.c_int32(mstep_mode), _ptr(sub_off), _ptr(sub_p), _ptr(sub_q), _ptr(out["phi_hat"]), _ptr(out["Q"]),
+                                             _ptr(out["pick"]), _ptr(out["counters"]), _ptr(out["logZ"]), _ptr(out["ex"]), _ptr(out["exx"]),
+                                             _ptr(out["log_g"]), _ptr(out["e_log_g1"]), _ptr(out["e_log_g2"]), _ptr(out["mml"]), _ptr(out["nme"]))
+        self._check(rc, ctx)
         return out
 
     def analyze_batch_raw(self, R, grp_off, Nl, rho_l, d_l, read_off, lu, lm, phi0, n_init, max_em_iters, box, mstep_mode, cpg_off, rho_n,

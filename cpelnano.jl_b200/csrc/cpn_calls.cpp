@@ -540,4 +540,50 @@ int cpn_pack_emissions(int64_t R, const int64_t* grp_off, const int64_t* read_of
     return bad.load() ? CPN_ERR_ARG : CPN_OK;
 }
 
+// WGBS front-end (wgbs.jl:222-323 turns the XM tags of a BAM into per-CpG calls x ∈ {−1 unmethylated, +1 methylated, 0 not
+// covered}; that parser is out of scope, its output is the input here).  A call is a hard emission (wgbs.jl:294-304 with
+// CpelNano.jl:32-33: log p(y|x) = 0 if the call agrees with x, −50 otherwise), so in packed form: llr = ∓50 and every methylated
+// call adds −50 to the read's Σ_obs log p(y|−1).  calls: [Σ_r M_r·N_r] int8, read-major per region.
+int cpn_wgbs_pack(int64_t R, const int64_t* cpg_off, const int64_t* read_off, const int8_t* calls, double* llr, double* read_base,
+                  int32_t n_threads) {
+    if (R < 0 || (R > 0 && (!cpg_off || !read_off || !calls || !llr || !read_base))) return CPN_ERR_ARG;
+    if (R == 0) return CPN_OK;
+    std::vector<int64_t> obs(R + 1);
+    obs[0] = 0;
+    for (int64_t r = 0; r < R; ++r) {
+        const int64_t N = cpg_off[r + 1] - cpg_off[r], M = read_off[r + 1] - read_off[r];
+        if (N < 0 || M < 0) return CPN_ERR_ARG;
+        obs[r + 1] = obs[r] + N * M;
+    }
+    const double right = 0.0, wrong = -50.0;                 // log_pyx_right_x, log_pyx_wrong_x
+    const int nt = (int)std::max<int64_t>(1, std::min<int64_t>(n_threads > 0 ? n_threads : (int)std::thread::hardware_concurrency(), R));
+    std::atomic<int> bad{0};
+    auto work = [&](int t) {
+        const int64_t lo = std::lower_bound(obs.begin(), obs.end(), obs[R] / nt * t) - obs.begin();
+        const int64_t hi = t + 1 == nt ? R : std::lower_bound(obs.begin(), obs.end(), obs[R] / nt * (t + 1)) - obs.begin();
+        for (int64_t r = std::min(lo, R); r < std::min(hi, R); ++r) {
+            const int64_t N = cpg_off[r + 1] - cpg_off[r], M = read_off[r + 1] - read_off[r];
+            const int8_t* x = calls + obs[r];
+            double* d = llr + obs[r];
+            for (int64_t i = 0; i < M; ++i) {
+                double base = 0.0;
+                for (int64_t n = 0; n < N; ++n) {
+                    const int8_t c = x[i * N + n];
+                    if (c == 1) { d[i * N + n] = right - wrong; base += wrong; }        // log_pyx_m = right, log_pyx_u = wrong
+                    else if (c == -1) { d[i * N + n] = wrong - right; base += right; }  // log_pyx_m = wrong, log_pyx_u = right
+                    else { d[i * N + n] = std::numeric_limits<double>::quiet_NaN(); if (c != 0) bad.store(1); }
+                }
+                read_base[read_off[r] + i] = base;
+            }
+        }
+    };
+    if (nt == 1) work(0);
+    else {
+        std::vector<std::thread> th;
+        for (int t = 0; t < nt; ++t) th.emplace_back(work, t);
+        for (auto& x : th) x.join();
+    }
+    return bad.load() ? CPN_ERR_ARG : CPN_OK;
+}
+
 }  // extern "C"

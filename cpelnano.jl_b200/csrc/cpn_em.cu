@@ -2467,6 +2467,28 @@ int cpn_analyze_batch_packed(cpn_ctx* ctx, int64_t R, const int64_t* grp_off, co
                           e_log_g2, mml, nme, true);
 }
 
+// Batched pmap_analyze_reg_bam (wgbs.jl:335-389): per region get_ϕhat_wgbs! (em_algorithm.jl:556-575: the same multi-start EM,
+// em_iter_wgbs :412-470 being em_iter with the hard emissions of the calls) and get_stat_sums!.  WGBS regions are modelled at
+// CpG resolution (get_grp_info! with min_grp_dist = 1, wgbs.jl:351: every CpG site is its own group, N_l = 1, ρ_l = ρ_n,
+// d_l = d_n), so there is no rscle_grp_mod! step and the fit and the summaries share the per-CpG tables.
+int cpn_analyze_wgbs_batch(cpn_ctx* ctx, int64_t R, const int64_t* cpg_off, const double* rho_n, const double* d_n, const int64_t* read_off,
+                           const int8_t* calls, const double* phi0, int32_t n_init, int32_t max_em_iters, double amax, double bmax,
+                           double cmax, int32_t mstep_mode, const int64_t* sub_off, const int64_t* sub_p, const int64_t* sub_q,
+                           double* phi_hat, double* Q, int32_t* status, int64_t* counters, double* logZ, double* ex, double* exx,
+                           double* log_g, double* e_log_g1, double* e_log_g2, double* mml, double* nme) {
+    if (!ctx) return CPN_ERR_ARG;
+    CPN_ARG(ctx, R >= 0 && (R == 0 || (cpg_off && rho_n && d_n && read_off && calls)), "null pointer");
+    if (R == 0) return CPN_OK;
+    int64_t cells = 0;
+    for (int64_t r = 0; r < R; ++r) cells += (cpg_off[r + 1] - cpg_off[r]) * (read_off[r + 1] - read_off[r]);
+    std::vector<double> llr((size_t)cells), base((size_t)read_off[R]), ones((size_t)cpg_off[R], 1.0);
+    int rc = cpn_wgbs_pack(R, cpg_off, read_off, calls, llr.data(), base.data(), 0);
+    CPN_ARG(ctx, rc == CPN_OK, "calls must be -1, 0 or +1");
+    return analyze_common(ctx, false, R, cpg_off, ones.data(), rho_n, d_n, read_off, llr.data(), base.data(), phi0, n_init, max_em_iters, amax, bmax,
+                          cmax, mstep_mode, cpg_off, rho_n, d_n, sub_off, sub_p, sub_q, phi_hat, Q, status, counters, logZ, ex, exx, log_g,
+                          e_log_g1, e_log_g2, mml, nme, true);
+}
+
 int cpn_estep_batch(cpn_ctx* ctx, int64_t R, const int64_t* grp_off, const double* Nl, const double* rho_l, const double* d_l,
                     const int64_t* read_off, const double* log_pyx_u, const double* log_pyx_m, const double* phi, double* ES,
                     double* ave_logpy) {

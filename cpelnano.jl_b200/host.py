@@ -10,6 +10,7 @@ from itertools import combinations
 
 import numpy as np
 
+from . import sharding
 from .capi import Library, MSTEP_ANALYTIC
 
 LMAX = 1000                      # src/CpelNano.jl:50
@@ -210,14 +211,8 @@ class Engine:
         L = math.comb(S, n1)
         if L > 20:
             exact = L < LMAX
-            if labelings is None:
-                allc = np.array(list(combinations(range(1, S + 1), n1)), dtype=np.int32)
-                if exact:
-                    labelings = allc
-                else:   # rand(1:L, LMAX) then keep the enumerated combinations whose index was drawn (:242-245)
-                    rng = rng or np.random.default_rng()
-                    idx = np.unique(rng.integers(0, L, size=LMAX))
-                    labelings = allc[idx]
+            if labelings is None:   # all of them, or rand(1:L, LMAX) de-duplicated (:242-245), unranked instead of enumerated
+                labelings, exact = sharding.labelings_for(S, n1, LMAX, rng)
         else:
             exact, labelings = True, np.zeros((0, n1), dtype=np.int32)
         models, pairs, tbl_off = [], [], [0]
@@ -271,8 +266,7 @@ class Engine:
         if L > 20:
             exact = L < LMAX
             if labelings is None:
-                allc = np.array(list(combinations(range(1, S + 1), n1)), dtype=np.int32)
-                labelings = allc if exact else allc[np.unique((rng or np.random.default_rng()).integers(0, L, size=LMAX))]
+                labelings, exact = sharding.labelings_for(S, n1, LMAX, rng)
         else:
             exact, labelings = True, np.zeros((0, n1), dtype=np.int32)
         T, cnt, p = self.lib.grp_test_batch(n1, n2, False, phi, cpg_off, rho_n, d_n, sub_off, sub_p, sub_q, labelings, exact, device=self.device)
@@ -575,6 +569,54 @@ def pmap_two_samp_null_stats(rs_ref, calls_s1, calls_s2, perm_ids, config, phi0s
     rscle_grp_mod(a1); rscle_grp_mod(a2)
     eng.get_stat_sums_batch([a1, a2], config)
     return a1.mml - a2.mml, a1.nme - a2.nme, eng.comp_cmd_pairs([a1, a2], [(0, 1)])[0]
+
+
+def analyze_regions_wgbs(regs, calls, config, phi0s=None, rng=None, engine=None):
+    """The body of pmap_analyze_reg_bam (src/wgbs.jl:335-389) for a batch of regions: `regs` carry the per-CpG features of
+    get_grp_info!(rs, fa_rec, 1) (every CpG its own group), `calls[i]` is the int8 [M_i, N_i] table of the region's reads
+    (−1 unmethylated, +1 methylated, 0 not covered — what get_calls_bam extracts from the XM tags; the BAM parser itself is not
+    part of this package).  Filters of :363-367, then get_ϕhat_wgbs! and get_stat_sums! in one cpn_analyze_wgbs_batch call."""
+    eng = engine or default_engine()
+    keep = []
+    for i, (rs, x) in enumerate(zip(regs, calls)):
+        x = np.asarray(x, dtype=np.int8)
+        N = len(rs.cpg_pos)
+        rs.m = x.shape[0]
+        if not (N > 9 and rs.m > 0 and x.shape[1] == N and N > 1):
+            continue
+        depth = np.count_nonzero(x) / N                       # get_ave_depth: observed cells / L
+        frac = np.count_nonzero(np.any(x != 0, axis=0)) / N   # perc_gprs_obs: observed groups / L
+        if depth >= config.min_cov and frac >= 0.66:
+            keep.append(i)
+    if not keep:
+        return regs
+    sel = [regs[i] for i in keep]
+    cpg_off = np.concatenate([[0], np.cumsum([len(rs.cpg_pos) for rs in sel])]).astype(np.int64)
+    read_off = np.concatenate([[0], np.cumsum([np.asarray(calls[i]).shape[0] for i in keep])]).astype(np.int64)
+    flat = np.concatenate([np.asarray(calls[i], dtype=np.int8).reshape(-1) for i in keep])
+    rho_n = np.concatenate([rs.rho_n for rs in sel]); d_n = np.concatenate([rs.dn for rs in sel])
+    for rs in sel:
+        eng.get_nls_reg_info(rs, config)
+    sub_off = np.concatenate([[0], np.cumsum([rs.nls_rgs.num for rs in sel])]).astype(np.int64)
+    sub_p = np.concatenate([rs.nls_rgs.cpg_p for rs in sel]); sub_q = np.concatenate([rs.nls_rgs.cpg_q for rs in sel])
+    n_init = config.max_em_init
+    if phi0s is None and rng is not None:
+        from . import simulations
+        phi0s = simulations.gen_phi0s(rng, len(sel), n_init)
+    elif phi0s is not None:
+        phi0s = np.asarray(phi0s)[keep]
+    out = eng.lib.analyze_wgbs_batch(cpg_off, rho_n, d_n, read_off, flat, phi0s, n_init, sub_off, sub_p, sub_q, config.max_em_iters,
+                                     mstep_mode=config.mstep_mode, device=eng.device)
+    for k, rs in enumerate(sel):
+        if out["pick"][k] < 0:
+            continue
+        a, b, k0, k1 = cpg_off[k], cpg_off[k + 1], sub_off[k], sub_off[k + 1]
+        rs.phihat = out["phi_hat"][k].copy(); rs.Q = float(out["Q"][k])
+        rs.logZ = float(out["logZ"][k]); rs.ex = out["ex"][a:b].copy(); rs.exx = out["exx"][a - k:b - k - 1].copy()
+        rs.log_gs = out["log_g"][k0:k1].copy(); rs.log_g1 = out["e_log_g1"][k0:k1].copy(); rs.log_g2 = out["e_log_g2"][k0:k1].copy()
+        rs.mml = out["mml"][k0:k1].copy(); rs.nme = out["nme"][k0:k1].copy()
+        rs.proc = True
+    return regs
 
 
 def analyze_regions(regs, config, phi0s=None, rng=None, engine=None):

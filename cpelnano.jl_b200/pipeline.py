@@ -8,14 +8,17 @@ per chromosome (SURVEY.md §8b "batch points"):
 Same arguments, same output files (outputs.py restates Julia's number formatting).  Two documented differences, both about
 ORDER only: the reference iterates Julia `Dict`s (reads of a region in get_calls_nanopolish!, common regions in
 find_comm_regs), whose order depends on the Julia build; here reads follow their first appearance in the calls file and
-common regions are written in coordinate order.  Host work is native and batched per chromosome: CpG index, partition and region features (csrc/cpn_genome.cpp), calls
+common regions are written in coordinate order.  One difference about RANDOMNESS, only when a comparison has too many labelings to
+enumerate (≥ 1000: more than 6 vs 6 unmatched, or ≥ 10 matched pairs): the reference draws its random subset of labelings inside
+every region's test, here one subset is drawn per (n1, n2) batch and shared by the regions of the batch — each region's p-value
+has the same distribution, but their Monte-Carlo errors are correlated across regions (exact tests are unaffected).  Host work is native and batched per chromosome: CpG index, partition and region features (csrc/cpn_genome.cpp), calls
 parsing and binning (csrc/cpn_calls.cpp); every number comes from libcpelnano_b200.so.
 """
 import os
 
 import numpy as np
 
-from . import genome, outputs
+from . import genome, outputs, sharding
 from .host import default_engine, analyze_regions
 from .nanopolish import NativeCalls
 
@@ -357,9 +360,7 @@ def diff_grp_comp_csr(mod_fls_g1, mod_fls_g2, fasta, config, out_dir, out_prefix
             else:
                 Lc = math.comb(S, n1)
                 if Lc > 20:
-                    exact = Lc < LMAX
-                    allc = np.array(list(combinations(range(1, S + 1), n1)), dtype=np.int32)
-                    lab = allc if exact else allc[np.unique((rng or np.random.default_rng()).integers(0, Lc, size=LMAX))]
+                    lab, exact = sharding.labelings_for(S, n1, LMAX, rng)
                 else:
                     exact, lab = True, np.zeros((0, n1), dtype=np.int32)
             for b0 in range(0, len(ridx_all), block_regions):

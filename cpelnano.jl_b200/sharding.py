@@ -118,3 +118,39 @@ class ResultGather:
 
     def bytes_moved(self):
         return self.sizes[self.rank], (sum(self.sizes) if self.rank == self.dst else 0)
+
+
+def labelings_for(S, n1, LMAX, rng=None):
+    """Group labelings of the unmatched test (src/grp_perm_tests.jl:236-247): all C(S, n1) combinations in lexicographic order
+    when there are fewer than LMAX, otherwise the distinct members of LMAX uniform draws from 1:C(S, n1) — the drawn INDICES are
+    turned into combinations by unranking (combinatorial number system), so nothing is enumerated when C(S, n1) is astronomically
+    large (the reference collects the iterator lazily; 32 samples would be 6·10⁸ rows).  Returns (labelings [n, n1] int32 with
+    1-based sample ids, exact)."""
+    import math
+    from itertools import combinations
+    import numpy as np
+    Lc = math.comb(S, n1)
+    if Lc < LMAX:
+        return np.array(list(combinations(range(1, S + 1), n1)), dtype=np.int32).reshape(-1, n1), True
+    rng = rng or np.random.default_rng()
+    # rand(1:L, LMAX): Python integers, because C(S, n1) may not fit in 64 bits
+    def draw():
+        if Lc < 2 ** 62:
+            return int(rng.integers(0, Lc))
+        return ((int(rng.integers(0, 2 ** 62)) << 62) | int(rng.integers(0, 2 ** 62))) % Lc      # 124 random bits, bias < 2^-60
+    idx = sorted({draw() for _ in range(LMAX)})
+    out = np.empty((len(idx), n1), dtype=np.int32)
+    for row, rank in enumerate(idx):
+        # lexicographic unranking: choose the smallest first element whose block of C(S - x, n1 - 1) combinations contains `rank`
+        x, k = 1, n1
+        for j in range(n1):
+            while True:
+                c = math.comb(S - x, k - 1)
+                if rank < c:
+                    break
+                rank -= c
+                x += 1
+            out[row, j] = x
+            x += 1
+            k -= 1
+    return out, False

@@ -166,6 +166,56 @@ def make_nano_batch(R, M=30, seed=MASTER_SEED, pobs=0.9, mu_m=84.0, sigma_m=2.0,
                      d_n=d_n, cpg_pos=cpg_pos, log_pyx_u=lu, log_pyx_m=lm, chrst=chrst, chrend=chrend, phi_true=phi_true)
 
 
+def wgbs_obs_pattern(rng, M, L, pobs):
+    """Which groups a WGBS read observes, as cpel_samp_wgbs draws it (simulations.jl:737-763): walking along the chain a new
+    fragment starts with probability pobs whenever at least 15 groups have passed since the last start, and a fragment covers its
+    first 9 groups (obs_count 1..9)."""
+    obs = np.zeros((M, L), dtype=bool)
+    for m in range(M):
+        cnt = 15
+        for l in range(L):
+            if rng.random() < pobs and cnt >= 15:
+                cnt = 0
+            cnt += 1
+            obs[m, l] = cnt < 10
+    return obs
+
+
+def make_wgbs_batch(R, M=40, seed=MASTER_SEED, pobs=0.25, layouts=None, phi_true=None):
+    """WGBS analogue of make_nano_batch at CpG resolution (every CpG site its own group: N_l = 1, ρ_l = ρ_n, d_l = d_n, as
+    pmap_analyze_reg_bam builds its regions, wgbs.jl:351): exact samples of the chain, hard calls x ∈ {−1, 0, +1} (int8, 0 = not
+    covered by the read) with cpel_samp_wgbs's coverage pattern.  Returns a NanoBatch whose group arrays are the per-CpG ones, with
+    `calls` [Σ M·N] and the equivalent emission tables log_pyx_u / log_pyx_m (0 / −50, NaN where not covered)."""
+    lay = layouts or load_layouts()
+    nlay = len(lay["cpg_off"]) - 1
+    rng = np.random.default_rng(seed)
+    which = np.arange(R) % nlay
+    Ns = np.diff(lay["cpg_off"])[which]
+    cpg_off = np.concatenate([[0], np.cumsum(Ns)]).astype(np.int64)
+    rho_n = np.concatenate([lay["rho_n"][lay["cpg_off"][w]:lay["cpg_off"][w + 1]] for w in which])
+    d_n = np.concatenate([lay["d_n"][lay["cpg_off"][w] - w:lay["cpg_off"][w + 1] - w - 1] for w in which])
+    cpg_pos = np.concatenate([lay["cpg_pos"][lay["cpg_off"][w]:lay["cpg_off"][w + 1]] for w in which])
+    if phi_true is None:
+        phi_true = np.stack([rng.uniform(-1, 1, R), rng.uniform(-20, 20, R), rng.uniform(0, 5, R)], axis=1)
+    read_off = (np.arange(R + 1) * M).astype(np.int64)
+    obs_off = np.concatenate([[0], np.cumsum(Ns * M)]).astype(np.int64)
+    calls = np.zeros(obs_off[-1], dtype=np.int8)
+    for r in range(R):
+        N = int(Ns[r])
+        rho = rho_n[cpg_off[r]:cpg_off[r + 1]]
+        dn = d_n[cpg_off[r] - r:cpg_off[r + 1] - r - 1]
+        alpha = (phi_true[r, 0] + phi_true[r, 1] * rho)[None, :]
+        beta = (phi_true[r, 2] / dn)[None, :]
+        x = sample_chain(rng, alpha, beta, np.array([N]), M)[0]          # [M, N]
+        obs = wgbs_obs_pattern(rng, M, N, pobs)
+        calls[obs_off[r]:obs_off[r + 1]] = np.where(obs, x, 0).reshape(-1)
+    lu = np.where(calls == 1, -50.0, np.where(calls == -1, 0.0, np.nan))
+    lm = np.where(calls == 1, 0.0, np.where(calls == -1, -50.0, np.nan))
+    return NanoBatch(grp_off=cpg_off, cpg_off=cpg_off, read_off=read_off, obs_off=obs_off, Nl=np.ones(int(cpg_off[-1])), rho_l=rho_n, d_l=d_n,
+                     rho_n=rho_n, d_n=d_n, cpg_pos=cpg_pos, log_pyx_u=lu, log_pyx_m=lm, calls=calls, chrst=lay["chrst"][which],
+                     chrend=lay["chrend"][which], phi_true=phi_true)
+
+
 def gen_grp_phis(rng, phi1, phi2, s1, s2, nse_sc=1.0):
     """simulations.jl:608,631 — ϕ_s = ϕ_g + nse_sc·[U{-0.1:0.01:0.1}, U{-0.5:0.01:0.5}, U{0:0.01:0.2}]; phi1,phi2 [R,3]."""
     R = phi1.shape[0]

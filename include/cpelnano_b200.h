@@ -178,6 +178,24 @@ int cpn_analyze_batch_packed(cpn_ctx* ctx, int64_t R,
                   double* logZ, double* ex, double* exx, double* log_g,
                   double* e_log_g1, double* e_log_g2, double* mml, double* nme);
 
+/* ---- WGBS front-end: pmap_analyze_reg_bam  src/wgbs.jl:335-389, get_ϕhat_wgbs!  src/em_algorithm.jl:556-575 ---------------
+ * Input = what get_calls_bam (wgbs.jl:222-323; the BAM/XM-tag parser itself is not part of this library) produces: per read and
+ * CpG site a call x ∈ {-1 unmethylated, +1 methylated, 0 not covered}, int8, [Σ_r M_r·N_r] read-major per region.  The calls
+ * are hard emissions (log p(y|x) ∈ {0, -50}, CpelNano.jl:32-33), the regions are modelled at CpG resolution (every CpG its own
+ * group), and em_iter_wgbs (em_algorithm.jl:412-470) is em_iter on those emissions: the call packs them (cpn_wgbs_pack, one byte
+ * per cell in, host) and runs the same kernels as cpn_analyze_batch_packed.  Outputs as cpn_analyze_batch.                    */
+int cpn_wgbs_pack(int64_t R, const int64_t* cpg_off, const int64_t* read_off, const int8_t* calls,
+                  double* llr, double* read_base, int32_t n_threads);
+int cpn_analyze_wgbs_batch(cpn_ctx* ctx, int64_t R,
+                  const int64_t* cpg_off, const double* rho_n, const double* d_n,
+                  const int64_t* read_off, const int8_t* calls,
+                  const double* phi0, int32_t n_init, int32_t max_em_iters,
+                  double amax, double bmax, double cmax, int32_t mstep_mode,
+                  const int64_t* sub_off, const int64_t* sub_p, const int64_t* sub_q,
+                  double* phi_hat, double* Q, int32_t* status, int64_t* counters,
+                  double* logZ, double* ex, double* exx, double* log_g,
+                  double* e_log_g1, double* e_log_g2, double* mml, double* nme);
+
 /* Building blocks of em_iter exposed for parity tests (host pointers):
  *   cpn_estep_batch   ES[r] = get_ess(map(get_cond_exs_log))  src/em_algorithm.jl:142-146 at phi[r]
  *                     and ave_logpy[r] = comp_ave_log_py (:263-288) at the same phi (may be NULL)

@@ -1002,4 +1002,54 @@ void orc_nonlog_chain(int64_t L, const double* al, const double* be, const doubl
     }
 }
 
+// ---- WGBS E-step: em_iter_wgbs (em_algorithm.jl:412-424) = get_ess ∘ get_cond_exs (transfer_matrix.jl:191-217) ---------------
+// get_cond_exs is the NON-log conditional chain: get_uc :19, get_Wc :43-66, the matrices scaled by 1/max entry (:202:
+// UniformScaling(1.0/maximum(maximum.(Ws))) * Ws), then get_Zc :73, get_Ec_X :102-126, get_Ec_XX :150-174 with D_EX = [-1 0;0 1] and
+// Ws[l] .* D_EXX.  WGBS calls are hard (log p ∈ {0, −50}, CpelNano.jl:32-33).  Same left-to-right products as orc_nonlog_chain.
+void orc_e_step_wgbs(int64_t L, int64_t M, const double* Nl, const double* rho, const double* dl, const double* lu, const double* lm,
+                     const double* phi, double* ES) {
+    std::vector<double> al, be;
+    get_ab_from_phi(phi, L, Nl, rho, dl, al, be);
+    std::vector<double> W(4 * (L - 1)), ex(L), exx(L - 1);
+    ES[0] = ES[1] = ES[2] = 0.0;
+    for (int64_t m = 0; m < M; ++m) {
+        const double *u = lu + m * L, *v = lm + m * L;
+        auto g = [&](bool x, int64_t l) { return std::exp(get_gc(x, al[l], !(u[l] != u[l]), u[l], v[l])); };
+        const double u1[2] = {g(false, 0), g(true, 0)}, uL[2] = {g(false, L - 1), g(true, L - 1)};
+        double wmax = -std::numeric_limits<double>::infinity();
+        for (int64_t l = 0; l + 1 < L; ++l) {
+            double f1 = g(false, l), t1 = g(true, l), f2 = g(false, l + 1), t2 = g(true, l + 1), eb = std::exp(be[l]);
+            W[4 * l + 0] = f1 * f2 * eb; W[4 * l + 2] = t1 * f2 / eb; W[4 * l + 1] = f1 * t2 / eb; W[4 * l + 3] = t1 * t2 * eb;
+            for (int k = 0; k < 4; ++k) wmax = std::max(wmax, W[4 * l + k]);
+        }
+        const double sc = 1.0 / wmax;
+        for (auto& w : W) w = sc * w;
+        auto prod = [&](int64_t a, int64_t b, double* P) {
+            P[0] = 1; P[1] = 0; P[2] = 0; P[3] = 1; bool first = true;
+            for (int64_t l = a; l < b; ++l) { if (first) { std::memcpy(P, &W[4 * l], 32); first = false; } else { double T[4]; mm2(P, &W[4 * l], T); std::memcpy(P, T, 32); } }
+        };
+        auto bil = [&](const double* P) { return (u1[0] * P[0] + u1[1] * P[2]) * uL[0] + (u1[0] * P[1] + u1[1] * P[3]) * uL[1]; };
+        double P[4]; prod(0, L - 1, P);
+        const double Zc = bil(P);
+        const double DEX[4] = {-1, 0, 0, 1};
+        for (int64_t l = 0; l < L; ++l) {
+            double A[4], B[4], T1[4], T2[4];
+            prod(0, l, A); prod(l, L - 1, B);
+            mm2(A, DEX, T1); mm2(T1, B, T2);
+            ex[l] = bil(T2) / Zc;
+        }
+        for (int64_t l = 0; l + 1 < L; ++l) {
+            double A[4], B[4], Wd[4] = {W[4 * l], -W[4 * l + 1], -W[4 * l + 2], W[4 * l + 3]}, T1[4], T2[4];
+            prod(0, l, A); prod(l + 1, L - 1, B);
+            mm2(A, Wd, T1); mm2(T1, B, T2);
+            exx[l] = bil(T2) / Zc;
+        }
+        double d1 = 0.0, d2 = 0.0, d3 = 0.0;                 // get_ess, em_algorithm.jl:99-113
+        for (int64_t l = 0; l < L; ++l) d1 += Nl[l] * ex[l];
+        for (int64_t l = 0; l < L; ++l) d2 += (Nl[l] * rho[l]) * ex[l];
+        for (int64_t l = 0; l + 1 < L; ++l) d3 += (1.0 / dl[l]) * exx[l];
+        ES[0] += d1; ES[1] += d2; ES[2] += d3;
+    }
+}
+
 }  // extern "C"

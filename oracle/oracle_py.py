@@ -138,6 +138,15 @@ def e_step(Nl, rho, dl, lu, lm, phi):
     return ES
 
 
+def e_step_wgbs(Nl, rho, dl, lu, lm, phi):
+    """em_iter_wgbs's E-step: get_ess(map(get_cond_exs)) — the non-log chain of transfer_matrix.jl:191-217, em_algorithm.jl:421-424."""
+    Nl, rho, dl, lu, lm, phi = _f(Nl), _f(rho), _f(dl), _f(lu), _f(lm), _f(phi)
+    M, L = lu.shape
+    ES = np.zeros(3)
+    lib().orc_e_step_wgbs(C.c_int64(L), C.c_int64(M), _p(Nl), _p(rho), _p(dl), _p(lu), _p(lm), _p(phi), _p(ES))
+    return ES
+
+
 def m_step(Nl, rho, dl, M, ES, phi_init):
     Nl, rho, dl, ES, phi_init = _f(Nl), _f(rho), _f(dl), _f(ES), _f(phi_init)
     sol = np.zeros(3)
