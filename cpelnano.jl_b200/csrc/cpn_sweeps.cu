@@ -40,7 +40,14 @@ __device__ __forceinline__ double div_small(double a, double n, double y) {
 // worth of running sums in registers, so the index arithmetic of a sample (or pair of samples) is paid once per KB
 // sub-regions and the inner loops are LDS + DADD.  Sums run over ascending sample ids — the order of the reference's id
 // vectors (grp_perm_tests.jl:121-125, :86-107; combinations are ascending, and so is their complement).
-template <int KB>
+constexpr int SW_PK_MAX = 1024;   // labelings whose packed member lists fit the kernel's shared-memory table
+
+// PACKED (n1 + n2 ≤ 16 samples and at most SW_PK_MAX labelings — every exact test and the reference's LMAX = 1000 sample): a
+// labeling is held as one 64-bit word of 4-bit sample ids, group 1 ascending then group 2 ascending, built once per block; the
+// sweep then walks members with a shift and a mask instead of a find-first-set chain over two bit masks, runs over sub-region
+// passes in the OUTER loop so that a thread counts its exceedances in registers, and touches the shared counters once per warp
+// and pass (a ballot-free shuffle sum) instead of once per (labeling, sub-region, statistic).  Same additions in the same order.
+template <int KB, bool PACKED>
 __global__ void __launch_bounds__(SW_THREADS) k_unmat_sweep(int n1, int n2, int Kmax, const int64_t* __restrict__ tbl_off,
                                                              const double* __restrict__ mml, const double* __restrict__ nme,
                                                              const double* __restrict__ cmd_tbl, const int32_t* __restrict__ labelings,
@@ -56,7 +63,22 @@ __global__ void __launch_bounds__(SW_THREADS) k_unmat_sweep(int n1, int n2, int 
     double* s_cmd = s_nme + S * Kmax;            // [S*S][K]
     double* s_T = s_cmd + S * S * Kmax;          // [3][K]
     int* s_cnt = (int*)(s_T + 3 * Kmax);         // [3][K]  (+ 16 doubles of slack: row tails are read unguarded below)
+    unsigned long long* s_pk = (unsigned long long*)(sm + (2 * S + S * S + 3) * Kmax + 16 + (3 * Kmax + 1) / 2);   // [P] (PACKED)
     for (int i = threadIdx.x; i < S * K; i += blockDim.x) { s_mml[i] = mml[k0 * S + i]; s_nme[i] = nme[k0 * S + i]; }
+    if (PACKED) {
+        for (int64_t pi = threadIdx.x; pi < P; pi += blockDim.x) {
+            const int32_t* lab = labelings + pi * n1;
+            unsigned m1 = 0;
+            unsigned long long pk = 0;
+            for (int i = 0; i < n1; ++i) m1 |= 1u << (lab[i] - 1);
+            int pos1 = 0, pos2 = n1;                     // both groups in ascending id order, whatever the order of the row
+            for (int id = 0; id < S; ++id) {
+                if ((m1 >> id) & 1u) { pk |= (unsigned long long)id << (4 * pos1); ++pos1; }
+                else { pk |= (unsigned long long)id << (4 * pos2); ++pos2; }
+            }
+            s_pk[pi] = pk;
+        }
+    }
     for (int i = threadIdx.x; i < S * S * K; i += blockDim.x) s_cmd[i] = cmd_tbl[k0 * S * S + i];
     for (int i = threadIdx.x; i < 3 * K; i += blockDim.x) s_cnt[i] = 0;
     __syncthreads();
@@ -78,6 +100,78 @@ __global__ void __launch_bounds__(SW_THREADS) k_unmat_sweep(int n1, int n2, int 
     const unsigned long long all = (S >= 64) ? ~0ull : ((1ull << S) - 1ull);
     const double d1 = (double)n1, d2 = (double)n2, d12 = (double)(n1 * n2);
     const double y1 = __ddiv_rn(1.0, d1), y2 = __ddiv_rn(1.0, d2), y12 = __ddiv_rn(1.0, d12);
+    if (PACKED) {
+        const int lane = threadIdx.x & 31;
+        for (int kb = 0; kb < K; kb += KB) {
+            int cm[KB], cn[KB], cc[KB];
+#pragma unroll
+            for (int u = 0; u < KB; ++u) { cm[u] = 0; cn[u] = 0; cc[u] = 0; }
+            for (int64_t pi = threadIdx.x; pi < P; pi += blockDim.x) {
+                const unsigned long long pk = s_pk[pi];
+                double tm[KB], tn[KB], tc[KB];
+                {   // Tmml, Tnme: mean over group 1 − mean over group 2, members in ascending id order
+                    double a[KB], b[KB];
+                    int o = (int)(pk & 15ull) * K + kb;
+#pragma unroll
+                    for (int u = 0; u < KB; ++u) { a[u] = s_mml[o + u]; b[u] = s_nme[o + u]; }
+                    for (int i = 1; i < n1; ++i) {
+                        o = (int)((pk >> (4 * i)) & 15ull) * K + kb;
+#pragma unroll
+                        for (int u = 0; u < KB; ++u) { a[u] = __dadd_rn(a[u], s_mml[o + u]); b[u] = __dadd_rn(b[u], s_nme[o + u]); }
+                    }
+#pragma unroll
+                    for (int u = 0; u < KB; ++u) { tm[u] = div_small(a[u], d1, y1); tn[u] = div_small(b[u], d1, y1); }
+                    o = (int)((pk >> (4 * n1)) & 15ull) * K + kb;
+#pragma unroll
+                    for (int u = 0; u < KB; ++u) { a[u] = s_mml[o + u]; b[u] = s_nme[o + u]; }
+                    for (int i = n1 + 1; i < S; ++i) {
+                        o = (int)((pk >> (4 * i)) & 15ull) * K + kb;
+#pragma unroll
+                        for (int u = 0; u < KB; ++u) { a[u] = __dadd_rn(a[u], s_mml[o + u]); b[u] = __dadd_rn(b[u], s_nme[o + u]); }
+                    }
+#pragma unroll
+                    for (int u = 0; u < KB; ++u) {
+                        tm[u] = __dsub_rn(tm[u], div_small(a[u], d2, y2));
+                        tn[u] = __dsub_rn(tn[u], div_small(b[u], d2, y2));
+                    }
+                }
+#pragma unroll
+                for (int u = 0; u < KB; ++u) tc[u] = 0.0;                        // comp_unmat_perm_stat_cmd :86-107
+                for (int i = 0; i < n1; ++i) {
+                    const int ii = (int)((pk >> (4 * i)) & 15ull);
+                    for (int j = n1; j < S; ++j) {
+                        const int jj = (int)((pk >> (4 * j)) & 15ull);
+                        const int o = (min(ii, jj) * S + max(ii, jj)) * K + kb;
+#pragma unroll
+                        for (int u = 0; u < KB; ++u) tc[u] = __dadd_rn(tc[u], s_cmd[o + u]);
+                    }
+                }
+#pragma unroll
+                for (int u = 0; u < KB; ++u) {
+                    const int k = kb + u;
+                    if (k < K) {
+                        const double tobs = s_T[k];
+                        if (tobs == tobs) {                                      // isnan(tmml_obs[k]) && continue (:260)
+                            cm[u] += fabs(tm[u]) >= fabs(tobs);                  // :268-270
+                            cn[u] += fabs(tn[u]) >= fabs(s_T[K + k]);
+                            cc[u] += div_small(tc[u], d12, y12) >= s_T[2 * K + k];
+                        }
+                    }
+                }
+            }
+#pragma unroll
+            for (int u = 0; u < KB; ++u) {
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1) {
+                    cm[u] += __shfl_xor_sync(0xffffffffu, cm[u], o);
+                    cn[u] += __shfl_xor_sync(0xffffffffu, cn[u], o);
+                    cc[u] += __shfl_xor_sync(0xffffffffu, cc[u], o);
+                }
+                const int k = kb + u;
+                if (lane == 0 && k < K) { atomicAdd(&s_cnt[k], cm[u]); atomicAdd(&s_cnt[K + k], cn[u]); atomicAdd(&s_cnt[2 * K + k], cc[u]); }
+            }
+        }
+    } else
     for (int64_t pi = threadIdx.x; pi < P; pi += blockDim.x) {
         const int32_t* lab = labelings + pi * n1;
         unsigned long long m1 = 0;
@@ -156,14 +250,23 @@ typedef void (*unmat_kernel_t)(int, int, int, const int64_t*, const double*, con
                                int64_t*, double*);
 // Sub-regions per pass: the fewest passes of at most 8, split evenly (K = 9 → 5 + 4), so the accumulators stay in ≈ 100
 // registers and two blocks fit on an SM.  CPN_SWEEP_KB overrides (4, 5, 6, 8, 12, 16) for experiments.
-inline unmat_kernel_t unmat_kernel_for(int Kmax) {
+inline bool unmat_packed(int S, int64_t P) {
+    const char* e = getenv("CPN_SWEEP_PACKED");
+    return S <= 16 && P <= SW_PK_MAX && !(e && atoi(e) == 0);
+}
+inline unmat_kernel_t unmat_kernel_for(int Kmax, int S, int64_t P) {
     int chunks = (Kmax + 7) / 8, kb = (Kmax + chunks - 1) / chunks;
     if (const char* e = getenv("CPN_SWEEP_KB")) kb = atoi(e);
-    return kb <= 4 ? k_unmat_sweep<4> : kb == 5 ? k_unmat_sweep<5> : kb == 6 ? k_unmat_sweep<6> : kb <= 8 ? k_unmat_sweep<8>
-         : kb <= 12 ? k_unmat_sweep<12> : k_unmat_sweep<16>;
+    if (unmat_packed(S, P))
+        return kb <= 4 ? k_unmat_sweep<4, true> : kb == 5 ? k_unmat_sweep<5, true> : kb == 6 ? k_unmat_sweep<6, true>
+             : kb <= 8 ? k_unmat_sweep<8, true> : kb <= 12 ? k_unmat_sweep<12, true> : k_unmat_sweep<16, true>;
+    return kb <= 4 ? k_unmat_sweep<4, false> : kb == 5 ? k_unmat_sweep<5, false> : kb == 6 ? k_unmat_sweep<6, false>
+         : kb <= 8 ? k_unmat_sweep<8, false> : kb <= 12 ? k_unmat_sweep<12, false> : k_unmat_sweep<16, false>;
 }
-inline size_t unmat_smem(int S, int Kmax) {
-    return (size_t)(2 * S + S * S + 3) * Kmax * sizeof(double) + (size_t)3 * Kmax * sizeof(int) + 16 * sizeof(double);
+inline size_t unmat_smem(int S, int Kmax, int64_t P) {
+    size_t doubles = (size_t)(2 * S + S * S + 3) * Kmax + 16 + (size_t)(3 * Kmax + 1) / 2;
+    if (unmat_packed(S, P)) doubles += (size_t)P;
+    return doubles * sizeof(double);
 }
 
 __global__ void __launch_bounds__(SW_THREADS) k_mat_sweep(int n, int Kmax, const int64_t* __restrict__ tbl_off, const double* __restrict__ mml1,
@@ -340,11 +443,11 @@ int cpn_grp_unmat_sweep(cpn_ctx* ctx, int64_t R, int32_t n1, int32_t n2, const i
     const int S = n1 + n2;
     const int Kmax = kmax_of(tbl_off, R);
     const int64_t sumK = tbl_off[R];
-    size_t smem = unmat_smem(S, Kmax);
+    size_t smem = unmat_smem(S, Kmax, P);
     CPN_ARG(ctx, smem <= 200 * 1024, "statistic tables of one region do not fit in shared memory");
     for (int64_t i = 0; i < P * n1; ++i) CPN_ARG(ctx, labelings[i] >= 1 && labelings[i] <= S, "labeling id out of range");
     cudaStream_t s = ctx->stream;
-    unmat_kernel_t kern = unmat_kernel_for(Kmax);
+    unmat_kernel_t kern = unmat_kernel_for(Kmax, S, P);
     CPN_CUDA(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     CPN_CUDA(ctx, cudaEventRecord(ctx->ev0, s));
     {
@@ -459,7 +562,7 @@ static int grp_test_impl(cpn_ctx* ctx, bool on_device, int64_t R, int32_t n1, in
     else for (int i = 0; i < S; ++i) for (int j = i + 1; j < S; ++j) { pi.push_back(i); pj.push_back(j); }
     const int npair = (int)pi.size();
     const int nstat = matched ? 2 : 3;
-    size_t smem = matched ? (size_t)(2 * n + 2) * Kmax * sizeof(double) + (size_t)2 * Kmax * sizeof(int) : unmat_smem(S, Kmax);
+    size_t smem = matched ? (size_t)(2 * n + 2) * Kmax * sizeof(double) + (size_t)2 * Kmax * sizeof(int) : unmat_smem(S, Kmax, P);
     CPN_ARG(ctx, smem <= 200 * 1024, "statistic tables of one region do not fit in shared memory");
     if (!matched) {
         const int32_t* lab = (const int32_t*)labelings;
@@ -467,7 +570,7 @@ static int grp_test_impl(cpn_ctx* ctx, bool on_device, int64_t R, int32_t n1, in
     }
     cudaStream_t s = ctx->stream;
     if (matched) CPN_CUDA(ctx, cudaFuncSetAttribute(k_mat_sweep, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    unmat_kernel_t kern = unmat_kernel_for(Kmax);
+    unmat_kernel_t kern = unmat_kernel_for(Kmax, S, P);
     if (!matched) CPN_CUDA(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     const char* e_chunk = getenv("CPN_GRP_CHUNK_REGIONS");
     const int64_t chunk = std::max<int64_t>(1, e_chunk ? atoll(e_chunk) : 65536);
