@@ -114,6 +114,7 @@ __global__ void __launch_bounds__(SW_THREADS) k_unmat_sweep(int n1, int n2, int 
                     int o = (int)(pk & 15ull) * K + kb;
 #pragma unroll
                     for (int u = 0; u < KB; ++u) { a[u] = s_mml[o + u]; b[u] = s_nme[o + u]; }
+#pragma unroll 4
                     for (int i = 1; i < n1; ++i) {
                         o = (int)((pk >> (4 * i)) & 15ull) * K + kb;
 #pragma unroll
@@ -124,6 +125,7 @@ __global__ void __launch_bounds__(SW_THREADS) k_unmat_sweep(int n1, int n2, int 
                     o = (int)((pk >> (4 * n1)) & 15ull) * K + kb;
 #pragma unroll
                     for (int u = 0; u < KB; ++u) { a[u] = s_mml[o + u]; b[u] = s_nme[o + u]; }
+#pragma unroll 4
                     for (int i = n1 + 1; i < S; ++i) {
                         o = (int)((pk >> (4 * i)) & 15ull) * K + kb;
 #pragma unroll
@@ -139,6 +141,7 @@ __global__ void __launch_bounds__(SW_THREADS) k_unmat_sweep(int n1, int n2, int 
                 for (int u = 0; u < KB; ++u) tc[u] = 0.0;                        // comp_unmat_perm_stat_cmd :86-107
                 for (int i = 0; i < n1; ++i) {
                     const int ii = (int)((pk >> (4 * i)) & 15ull);
+#pragma unroll 6
                     for (int j = n1; j < S; ++j) {
                         const int jj = (int)((pk >> (4 * j)) & 15ull);
                         const int o = (min(ii, jj) * S + max(ii, jj)) * K + kb;
