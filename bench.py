@@ -312,8 +312,9 @@ def main():
     dist = None
     if world > 1:
         import torch.distributed as dist
-        if os.environ.get("NCCL_DEBUG", "").upper() in ("", "VERSION"):
-            os.environ["NCCL_DEBUG"] = "WARN"        # keep NCCL's version banner off stdout: rank 0 prints exactly one JSON line
+        # rank 0 prints exactly one JSON line on stdout: whatever NCCL logs (its version banner appears from NCCL_DEBUG=VERSION up,
+        # WARN included) goes to stderr
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     import cpelnano_b200 as cpn
     lib = cpn.Library()

@@ -37,6 +37,13 @@ for st in "$@"; do
     parity)    timeout 180 python -m pytest tests/test_gpu_parity.py tests/test_pipeline_gpu.py -m gpu -x -q > $O/${TAG}_parity.log 2>&1; echo "parity rc=$?"; tail -3 $O/${TAG}_parity.log ;;
     ab)        bash tools/ab.sh 100000 $AB_LIBS > $O/${TAG}_ab.txt 2>&1; cat $O/${TAG}_ab.txt ;;
     trace)     CPN_TRACE=1 timeout 600 python bench.py --no-cpu --steps 1 --warmup 2 > $O/${TAG}_trace.json 2> $O/${TAG}_trace.err; echo "trace rc=$?" ;;
+    multi)     # NG GPUs, the driver's launch line; one JSON line per workload
+               TR="python -m torch.distributed.run --nnodes=1 --nproc-per-node $NG --master-addr 127.0.0.1 --master-port 29511"
+               for wl in chr22 whole-genome group two-sample; do
+                 extra=""; [ "$wl" = "two-sample" ] && extra="--steps 2 --warmup 1"; [ "$wl" = "whole-genome" ] && extra="--steps 2 --warmup 1"
+                 timeout 900 $TR bench.py --gpus $NG --workload $wl --no-cpu $extra > $O/${TAG}_bench_${wl}_${NG}gpu.json 2> $O/${TAG}_bench_${wl}_${NG}gpu.err; echo "multi $wl rc=$?"
+               done ;;
+    tests2)    timeout 900 python -m pytest tests -m gpu -x -q -k "device or multi or second" > $O/${TAG}_pytest_2gpu.log 2>&1; echo "tests2 rc=$?"; tail -3 $O/${TAG}_pytest_2gpu.log ;;
     *) echo "unknown stage $st" ;;
   esac
   echo "  stage $st: $(( $(date +%s) - t0 )) s"
