@@ -14,7 +14,7 @@ FIT_NONE, FIT_NUMERICAL, FIT_FILTERED = -1, -2, -16        # status words (inclu
 
 # every exported symbol of include/cpelnano_b200.h (tests check the library exports exactly these)
 SYMBOLS = ["cpn_create", "cpn_create_multi", "cpn_num_devices", "cpn_destroy", "cpn_last_error", "cpn_version", "cpn_last_device_ms", "cpn_last_launches", "cpn_last_work",
-           "cpn_measure_fp64_peak", "cpn_set_seed", "cpn_rng_phi0", "cpn_rng_perm", "cpn_set_profile", "cpn_get_profile", "cpn_analyze_batch", "cpn_analyze_batch_device", "cpn_fit_batch", "cpn_fit_batch_device", "cpn_pack_emissions", "cpn_fit_batch_packed", "cpn_analyze_batch_packed", "cpn_wgbs_pack", "cpn_analyze_wgbs_batch", "cpn_estep_batch", "cpn_mstep_batch",
+           "cpn_measure_fp64_peak", "cpn_set_seed", "cpn_rng_phi0", "cpn_rng_perm", "cpn_set_profile", "cpn_get_profile", "cpn_analyze_batch", "cpn_analyze_batch_device", "cpn_fit_batch", "cpn_fit_batch_device", "cpn_pack_emissions", "cpn_fit_batch_packed", "cpn_analyze_batch_packed", "cpn_wgbs_pack", "cpn_analyze_wgbs_batch", "cpn_estep_batch", "cpn_estep_batch_starts", "cpn_mstep_batch",
            "cpn_stat_sums_batch", "cpn_nls_reg_info", "cpn_cmd_batch", "cpn_grp_unmat_sweep", "cpn_grp_mat_sweep", "cpn_two_samp_pvals", "cpn_two_samp_null_batch", "cpn_two_samp_test_batch", "cpn_grp_test_batch", "cpn_grp_test_batch_device", "cpn_region_filter",
            "cpn_calls_open", "cpn_calls_close", "cpn_calls_open_error", "cpn_calls_error", "cpn_calls_num_lines", "cpn_calls_num_reads", "cpn_calls_num_chr",
            "cpn_calls_chr_name", "cpn_calls_chr_lines", "cpn_calls_read_name", "cpn_calls_count_reads", "cpn_calls_fill",
@@ -295,6 +295,20 @@ class Library:
                                       _ptr(phi), _ptr(ES), _ptr(lp))
         self._check(rc, ctx)
         return ES, lp
+
+    def estep_batch_starts(self, grp_off, Nl, rho_l, d_l, read_off, log_pyx_u, log_pyx_m, phi, device=0):
+        """phi [R, n_init, 3] → ES [R, n_init, 3] through the paired E-step (k_make_pairs → k_estep_pair)."""
+        grp_off, read_off = _i64(grp_off), _i64(read_off)
+        Nl, rho_l, d_l, lu, lm, phi = _f64(Nl), _f64(rho_l), _f64(d_l), _f64(log_pyx_u), _f64(log_pyx_m), _f64(phi)
+        R = len(grp_off) - 1
+        assert phi.ndim == 3 and phi.shape[0] == R and phi.shape[2] == 3
+        n_init = phi.shape[1]
+        ES = np.empty((R, n_init, 3))
+        ctx = self.ctx(device)
+        rc = self.dll.cpn_estep_batch_starts(ctx, C.c_int64(R), _ptr(grp_off), _ptr(Nl), _ptr(rho_l), _ptr(d_l), _ptr(read_off), _ptr(lu),
+                                             _ptr(lm), C.c_int32(n_init), _ptr(phi), _ptr(ES))
+        self._check(rc, ctx)
+        return ES
 
     def mstep_batch(self, grp_off, Nl, rho_l, d_l, n_reads, ES, phi_init, mstep_mode=MSTEP_ANALYTIC, device=0):
         grp_off, n_reads = _i64(grp_off), _i64(n_reads)

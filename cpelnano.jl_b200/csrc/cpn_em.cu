@@ -601,6 +601,395 @@ __global__ void k_make_desc(int n_items, const int* __restrict__ items, int n_in
 }
 
 // ---------------------------------------------------------------------------------------------------
+// E-step, two EM instances per warp (the default for the analytic M-step; k_estep above stays as the one-instance form)
+// ---------------------------------------------------------------------------------------------------
+// k_estep's time follows its executed issue slots, and a third of them are not chain arithmetic: the head and tail of an
+// instance (descriptor, group potentials, reductions), the per-block emission transport and three warp-uniform LDS.128 per
+// chain step.  All of that is per WARP, so the pair form halves it per instance: lanes 0-15 work for one start of a region and
+// lanes 16-31 for another start of the SAME region, every lane carrying two reads (slots i and i+16 of the 32-read chunk).  The
+// two instances share the region's emission rows (one bulk copy per block for both), the block bookkeeping and the loop; the
+// potentials of a step are one LDS.128 triple per lane for two chain steps.  Both halves run one instruction stream, so
+//  * only starts whose coupling c has the same sign are paired (the BPOS specialisation is per warp);
+//  * a block of E_PF groups runs a sign-specialised body only when BOTH instances have that sign of α_l on all its groups,
+//    otherwise the general body (25 instead of 21 FP64 instructions per step, r plane).
+// Pairs are rebuilt every EM iteration from the active list (k_make_pairs): within a region's run of active starts, starts of
+// one sign class are paired in list order; an odd one out runs with its second half idle.  Pairing only looks at the region's
+// own starts, so results do not depend on how a batch is chunked or sharded.  The sum over reads is the same tree as
+// cpn_warp_sum (first i with i+16, then the xor butterfly 8,4,2,1).
+struct __align__(16) PairDesc { int instA, instB, L, M; int64_t g0, ew_off; int ridx, pad0, pad1, pad2; };
+static_assert(sizeof(PairDesc) == 48, "PairDesc layout");
+#ifndef EP_BLOCKS
+#define EP_BLOCKS 4
+#endif
+#ifndef EP_UNROLL
+#define EP_UNROLL 2                 // groups per trip of a block body (see estep_pair_chunk)
+#endif
+constexpr int EP_UNR = EP_UNROLL;
+
+// potentials of the two instances of a pair; rows padded by one entry so that the two halves' broadcast reads of the same group
+// fall into different banks
+struct PairTile { double2 w[2][TILE + 1], tn[2][TILE + 1], bd[2][TILE + 1]; };
+#ifdef EP_STATS          // diagnostic build: how many blocks run each body, how many pairs are singletons
+__device__ unsigned long long ep_stats[8];
+#define EP_COUNT(k) do { if (lane == 0) atomicAdd(&ep_stats[k], 1ull); } while (0)
+#else
+#define EP_COUNT(k) do { } while (0)
+#endif
+constexpr size_t EP_SMEM = (size_t)E_WARPS * (sizeof(PairTile) + sizeof(EmisRing)) + (size_t)E_WARPS * 4 * sizeof(unsigned long long);
+
+// estep_site on explicit operands (same arithmetic, same order)
+template <bool BPOS, int SGN>
+__device__ __forceinline__ void estep_core(EState& s, const double2 w, const double2 tn, const double2 bd, double r) {
+    const double t = tn.x, na = tn.y, nb = bd.x, sinvd = bd.y;
+    double u = BPOS ? s.fp : s.fm, v = BPOS ? s.fm : s.fp;
+    double Gp = fma(t, v, u), Gm = fma(t, u, v);
+    double ua = BPOS ? s.gap : s.gam, va = BPOS ? s.gam : s.gap;
+    double ub = BPOS ? s.gbp : s.gbm, vb = BPOS ? s.gbm : s.gbp;
+    double uc = BPOS ? s.gcp : s.gcm, vc = BPOS ? s.gcm : s.gcp;
+    double Hap = fma(t, va, ua), Ham = fma(t, ua, va);
+    double Hbp = fma(t, vb, ub), Hbm = fma(t, ub, vb);
+    double Hcp = fma(t, vc, uc), Hcm = fma(t, uc, vc);
+    double Dp = fma(2.0, u, -Gp), Dm = fma(2.0, v, -Gm);
+    if (SGN == 0) {
+        const double phiP = w.y * r, phiM = w.x;
+        s.gap = phiP * fma(na, Gp, Hap);     s.gam = phiM * fma(-na, Gm, Ham);
+        s.gbp = phiP * fma(nb, Gp, Hbp);     s.gbm = phiM * fma(-nb, Gm, Hbm);
+        s.gcp = phiP * fma(sinvd, Dp, Hcp);  s.gcm = phiM * fma(sinvd, Dm, Hcm);
+        s.fp = phiP * Gp;                    s.fm = phiM * Gm;
+    } else if (SGN > 0) {
+        const double k = w.x * r;
+        s.gap = fma(na, Gp, Hap);            s.gam = k * fma(-na, Gm, Ham);
+        s.gbp = fma(nb, Gp, Hbp);            s.gbm = k * fma(-nb, Gm, Hbm);
+        s.gcp = fma(sinvd, Dp, Hcp);         s.gcm = k * fma(sinvd, Dm, Hcm);
+        s.fp = Gp;                           s.fm = k * Gm;
+    } else {
+        const double k = w.y * r;
+        s.gap = k * fma(na, Gp, Hap);        s.gam = fma(-na, Gm, Ham);
+        s.gbp = k * fma(nb, Gp, Hbp);        s.gbm = fma(-nb, Gm, Hbm);
+        s.gcp = k * fma(sinvd, Dp, Hcp);     s.gcm = fma(sinvd, Dm, Hcm);
+        s.fp = k * Gp;                       s.fm = Gm;
+    }
+}
+
+// Potentials of groups [l0, l0+n) for both instances: half h of the warp (16 lanes strided over the groups) fills its own rows.
+// mP / mN: bit j set when BOTH instances have α ≥ 0 / α < 0 at group l0 + j.
+struct PairTileRegs { double na[TILE / 16], nb[TILE / 16], id[TILE / 16], alpha[TILE / 16]; };
+__device__ __forceinline__ void ptile_load(PairTileRegs& tr, int l0, int n, int i, const double* __restrict__ na_g,
+                                           const double* __restrict__ nb_g, const double* __restrict__ invd_g, double a, double b,
+                                           unsigned long long& mP, unsigned long long& mN) {
+    constexpr int K = TILE / 16;
+#pragma unroll
+    for (int k = 0; k < K; ++k) {
+        const int j = i + 16 * k, l = l0 + j;
+        const bool in = j < n;
+        tr.na[k] = in ? na_g[l] : 0.0;
+        tr.nb[k] = in ? nb_g[l] : 0.0;
+        tr.id[k] = (in && l > 0) ? invd_g[l - 1] : 0.0;
+    }
+    mP = 0ull; mN = 0ull;
+#pragma unroll
+    for (int k = 0; k < K; ++k) {
+        const int j = i + 16 * k;
+        tr.alpha[k] = fma(b, tr.nb[k], a * tr.na[k]);
+        const unsigned bal = __ballot_sync(0xffffffffu, j < n && __double2hiint(tr.alpha[k]) >= 0);
+        mP |= (unsigned long long)(bal & (bal >> 16) & 0xffffu) << (16 * k);
+        mN |= (unsigned long long)(~(bal | (bal >> 16)) & 0xffffu) << (16 * k);
+    }
+}
+__device__ __forceinline__ void ptile_store(PairTile& pt, const PairTileRegs& tr, int l0, int n, int h, int i, double cabs, bool bpos) {
+    constexpr int K = TILE / 16;
+#pragma unroll
+    for (int k = 0; k < K; ++k) {
+        const int j = i + 16 * k, l = l0 + j;
+        if (j < n) {
+            const double e = cpn_exp_neg(-2.0 * fabs(tr.alpha[k]));
+            const bool pos = __double2hiint(tr.alpha[k]) >= 0;
+            pt.w[h][j] = make_double2(pos ? e : 1.0, pos ? 1.0 : e);
+            pt.tn[h][j] = make_double2((l > 0) ? cpn_exp_neg(-2.0 * (cabs * tr.id[k])) : 0.0, tr.na[k]);
+            pt.bd[h][j] = make_double2(tr.nb[k], bpos ? tr.id[k] : -tr.id[k]);
+        }
+    }
+}
+
+// ring transport for a pair: with the per-lane copies of a view a lane reads what ANOTHER lane copied (slot i+16, or i from the
+// upper half), so the warp synchronises before a slot is refilled and after a copy has landed; the bulk-copy path already does
+template <bool VIEW>
+__device__ __forceinline__ void pring_issue(EmisRing& ring, int slot, EmisSrc<VIEW>& es, bool inv, int row0, int nrows, int lane) {
+    if (VIEW) __syncwarp();
+    ering_issue(ring, slot, es, inv, row0, nrows, lane);
+}
+template <int PENDING_AFTER, bool VIEW>
+__device__ __forceinline__ void pring_wait(EmisSrc<VIEW>& es, int slot) {
+    ering_wait<PENDING_AFTER>(es, slot);
+    if (VIEW) __syncwarp();
+}
+
+// EP_UNR groups × 2 reads per trip of a block body.  The bodies are NOT unrolled over the whole block: six of them (three sign
+// cases × the sign of c) are live on an SM at once, and fully unrolled (8 groups × 2 reads ≈ 6 KB each, next to two copies of the
+// head) they fell out of the 32 KB instruction cache as soon as both signs of c were present — ncu: 75-85 % of the warp-stall
+// samples of the bodies were "no instruction", 6.3 instead of 2.9 ms per launch.  For the same reason everything but the bodies
+// exists once, with the sign of c as a run-time value.
+template <bool BPOS, int SGN>
+__device__ __forceinline__ void pair_block(EState& s0, EState& s1, const double2* __restrict__ W, const double2* __restrict__ TN,
+                                           const double2* __restrict__ BD, const double* __restrict__ r /*this lane's first read, row 0*/,
+                                           int rows) {
+#pragma unroll EP_UNR
+    for (int u = 0; u < rows; ++u) {
+        const double2 w = W[u], tn = TN[u], bd = BD[u];
+        estep_core<BPOS, SGN>(s0, w, tn, bd, r[u * 32]);
+        estep_core<BPOS, SGN>(s1, w, tn, bd, r[u * 32 + 16]);
+    }
+}
+
+template <bool VIEW>
+__device__ __forceinline__ void estep_pair_chunk(PairTile& pt, EmisRing& ring, int L, int lane, const double* __restrict__ na_g,
+                                                 const double* __restrict__ nb_g, const double* __restrict__ invd_g, EmisSrc<VIEW>& es,
+                                                 double a, double b, double cabs, bool bpos, int rmask, double out0[3], double out1[3]) {
+    const int h = lane >> 4, i = lane & 15;
+    const double2* __restrict__ W = pt.w[h];
+    const double2* __restrict__ TN = pt.tn[h];
+    const double2* __restrict__ BD = pt.bd[h];
+    EState s0{1.0, 1.0, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0};
+    EState s1 = s0;
+    const int Lfull = L & ~(E_PF - 1);
+    constexpr unsigned ALL = (1u << E_PF) - 1;
+    pring_issue<VIEW>(ring, 2, es, false, Lfull, L - Lfull, lane);
+    int g = 0;
+    for (int l0 = 0; l0 < L; l0 += TILE) {
+        const int n = min(TILE, L - l0);
+        const int nfull = n & ~(E_PF - 1);
+        PairTileRegs tr;
+        unsigned long long mP, mN;
+        ptile_load(tr, l0, n, i, na_g, nb_g, invd_g, a, b, mP, mN);
+        pring_issue<VIEW>(ring, g & 1, es, ((unsigned)mP & ALL) == ALL, g * E_PF, nfull > 0 ? E_PF : 0, lane);
+        __syncwarp();
+        ptile_store(pt, tr, l0, n, h, i, cabs, bpos);
+        __syncwarp();
+#pragma unroll 1
+        for (int j0 = 0; j0 < nfull; j0 += E_PF, ++g) {
+            const unsigned bp = (unsigned)(mP >> j0) & ALL, bn = (unsigned)(mN >> j0) & ALL;
+            const int j1 = j0 + E_PF;
+            const unsigned bp1 = (unsigned)(mP >> (j1 & (TILE - 1))) & ALL;
+            pring_issue<VIEW>(ring, (g + 1) & 1, es, bp1 == ALL, (g + 1) * E_PF, (j1 < nfull) ? E_PF : 0, lane);
+            const int slot = g & 1;
+            pring_wait<1, VIEW>(es, slot);
+            if (g > 0 && (g & rmask) == 0) { estep_rescale(s0); estep_rescale(s1); }
+            EP_COUNT(bp == ALL ? 0 : (bn == ALL ? 1 : 2));
+            const double* r = &ring.r[slot][0][i];
+            if (bpos) {
+                if (bp == ALL) pair_block<true, 1>(s0, s1, W + j0, TN + j0, BD + j0, r, E_PF);
+                else if (bn == ALL) pair_block<true, -1>(s0, s1, W + j0, TN + j0, BD + j0, r, E_PF);
+                else pair_block<true, 0>(s0, s1, W + j0, TN + j0, BD + j0, r, E_PF);
+            } else {
+                if (bp == ALL) pair_block<false, 1>(s0, s1, W + j0, TN + j0, BD + j0, r, E_PF);
+                else if (bn == ALL) pair_block<false, -1>(s0, s1, W + j0, TN + j0, BD + j0, r, E_PF);
+                else pair_block<false, 0>(s0, s1, W + j0, TN + j0, BD + j0, r, E_PF);
+            }
+        }
+        if (nfull < n) {
+            pring_wait<0, VIEW>(es, 2);
+            if (g > 0) { estep_rescale(s0); estep_rescale(s1); }
+            const double* r = &ring.r[2][0][i];
+#pragma unroll 1
+            for (int u = 0; u < n - nfull; ++u) {
+                const double2 w = W[nfull + u], tn = TN[nfull + u], bd = BD[nfull + u];
+                if (bpos) { estep_core<true, 0>(s0, w, tn, bd, r[u * 32]); estep_core<true, 0>(s1, w, tn, bd, r[u * 32 + 16]); }
+                else { estep_core<false, 0>(s0, w, tn, bd, r[u * 32]); estep_core<false, 0>(s1, w, tn, bd, r[u * 32 + 16]); }
+            }
+        }
+    }
+    if (VIEW) asm volatile("cp.async.wait_group 0;");
+    const double inv0 = 1.0 / (s0.fp + s0.fm), inv1 = 1.0 / (s1.fp + s1.fm);
+    out0[0] = (s0.gap + s0.gam) * inv0; out0[1] = (s0.gbp + s0.gbm) * inv0; out0[2] = (s0.gcp + s0.gcm) * inv0;
+    out1[0] = (s1.gap + s1.gam) * inv1; out1[1] = (s1.gbp + s1.gbm) * inv1; out1[2] = (s1.gcp + s1.gcm) * inv1;
+}
+
+// rescale after every group, plain loads (pairs whose |LLR| / |β| bound allows no unscaled run of groups)
+template <bool BPOS>
+__device__ __noinline__ void estep_pair_slow(PairTile& pt, int L, int lane, const double* __restrict__ na_g, const double* __restrict__ nb_g,
+                                             const double* __restrict__ invd_g, const double* __restrict__ p0, const double* __restrict__ p1,
+                                             double a, double b, double cabs, double out0[3], double out1[3]) {
+    const int h = lane >> 4, i = lane & 15;
+    EState s0{1.0, 1.0, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0};
+    EState s1 = s0;
+    for (int l0 = 0; l0 < L; l0 += TILE) {
+        const int n = min(TILE, L - l0);
+        PairTileRegs tr;
+        unsigned long long mP, mN;
+        __syncwarp();
+        ptile_load(tr, l0, n, i, na_g, nb_g, invd_g, a, b, mP, mN);
+        ptile_store(pt, tr, l0, n, h, i, cabs, BPOS);
+        __syncwarp();
+#pragma unroll 1
+        for (int j = 0; j < n; ++j) {
+            const double2 w = pt.w[h][j], tn = pt.tn[h][j], bd = pt.bd[h][j];
+            estep_core<BPOS, 0>(s0, w, tn, bd, __ldg(p0 + (size_t)(l0 + j) * 32));
+            estep_rescale(s0);
+            estep_core<BPOS, 0>(s1, w, tn, bd, __ldg(p1 + (size_t)(l0 + j) * 32));
+            estep_rescale(s1);
+        }
+    }
+    const double inv0 = 1.0 / (s0.fp + s0.fm), inv1 = 1.0 / (s1.fp + s1.fm);
+    out0[0] = (s0.gap + s0.gam) * inv0; out0[1] = (s0.gbp + s0.gbm) * inv0; out0[2] = (s0.gcp + s0.gcm) * inv0;
+    out1[0] = (s1.gap + s1.gam) * inv1; out1[1] = (s1.gbp + s1.gbm) * inv1; out1[2] = (s1.gcp + s1.gcm) * inv1;
+}
+
+template <bool VIEW>
+__global__ void __launch_bounds__(E_WARPS * 32, EP_BLOCKS) k_estep_pair(const int* __restrict__ n_pairs_dev, const PairDesc* __restrict__ pdesc,
+                                                                         const double* __restrict__ phil2 /*[6][cap] by pair position*/,
+                                                                         int64_t cap, RegionTables rt, int64_t NI, double* __restrict__ ES) {
+    extern __shared__ __align__(128) unsigned char ep_smem[];
+    PairTile* tiles = reinterpret_cast<PairTile*>(ep_smem);
+    EmisRing* rings = reinterpret_cast<EmisRing*>(ep_smem + (size_t)E_WARPS * sizeof(PairTile));
+    unsigned long long* mbars = reinterpret_cast<unsigned long long*>(ep_smem + (size_t)E_WARPS * (sizeof(PairTile) + sizeof(EmisRing)));
+    const int w = threadIdx.x >> 5, lane = threadIdx.x & 31, h = lane >> 4, i = lane & 15;
+    EmisSrc<VIEW> es;
+    if constexpr (!VIEW) {
+        es.mbar = (unsigned)__cvta_generic_to_shared(&mbars[4 * w]);
+        es.ring = (unsigned)__cvta_generic_to_shared(&rings[w].r[0][0][0]);
+        es.phase = 0u;
+        if (lane == 0) {
+            mbar_init(es.mbar, 1u); mbar_init(es.mbar + 8u, 1u); mbar_init(es.mbar + 16u, 1u);
+            asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        }
+        __syncwarp();
+    }
+    // pairs with c ≥ 0 fill the list from the front, pairs with c < 0 from the back (k_make_pairs): the launch runs the former
+    // first and the latter together at its end, so that an SM mostly executes the bodies of ONE sign of c at a time
+    const int n_pos = __ldg(n_pairs_dev), n_pairs = n_pos + __ldg(n_pairs_dev + 1);
+#pragma unroll 1
+    for (int pq = blockIdx.x * E_WARPS + w; pq < n_pairs; pq += gridDim.x * E_WARPS) {
+        const int p = pq < n_pos ? pq : (int)cap - 1 - (pq - n_pos);
+        const int4* dq = reinterpret_cast<const int4*>(pdesc + p);
+        const int4 d0 = __ldg(dq);
+        const longlong2 d1 = __ldg(reinterpret_cast<const longlong2*>(dq + 1));
+        const int ridx = __ldg(reinterpret_cast<const int*>(dq + 2));
+        const double a = phil2[(size_t)(3 * h) * cap + p], b = phil2[(size_t)(3 * h + 1) * cap + p], c = phil2[(size_t)(3 * h + 2) * cap + p];
+        const int L = d0.z, M = d0.w & ITEM_M_MASK, mode = (d0.w >> ITEM_MODE_SHIFT) & 3;
+        const int64_t g0 = d1.x;
+        // both starts of a pair have the same sign of c (k_make_pairs); lane 0's copy decides for the warp
+        const bool bpos = __shfl_sync(0xffffffffu, (int)(__double2hiint(c) >= 0), 0) != 0;
+        const double cabs = fabs(c);
+        const double* ew_r = rt.ew + d1.y;
+        double acc0 = 0, acc1 = 0, acc2 = 0;
+        const int nchunk = (M + 31) >> 5;
+        for (int ch = 0; ch < nchunk; ++ch) {
+            double o0[3], o1[3];
+            int q = ch * 32 + lane;
+            if (VIEW && ridx >= 0) q = __ldg(rt.ridx + ((size_t)(ridx + ch) << 5) + lane);
+            const size_t po = (size_t)(q >> 5) * L * 32 + (q & 31);
+            if (mode != 0) {
+                const size_t eo = VIEW ? po : (size_t)ch * L * 32;
+                es.p = ew_r + eo;
+                es.pi = rt.ewi + d1.y + eo;
+                estep_pair_chunk<VIEW>(tiles[w], rings[w], L, lane, rt.na + g0, rt.nb + g0, rt.invd + g0, es, a, b, cabs, bpos, mode - 1, o0, o1);
+            } else {
+                const int q0 = __shfl_sync(0xffffffffu, q, i), q1 = __shfl_sync(0xffffffffu, q, i + 16);
+                const double* p0 = ew_r + (size_t)(q0 >> 5) * L * 32 + (q0 & 31);
+                const double* p1 = ew_r + (size_t)(q1 >> 5) * L * 32 + (q1 & 31);
+                if (bpos) estep_pair_slow<true>(tiles[w], L, lane, rt.na + g0, rt.nb + g0, rt.invd + g0, p0, p1, a, b, cabs, o0, o1);
+                else estep_pair_slow<false>(tiles[w], L, lane, rt.na + g0, rt.nb + g0, rt.invd + g0, p0, p1, a, b, cabs, o0, o1);
+            }
+            const bool live0 = ch * 32 + i < M, live1 = ch * 32 + 16 + i < M;
+            double v0 = (live0 ? o0[0] : 0.0) + (live1 ? o1[0] : 0.0);
+            double v1 = (live0 ? o0[1] : 0.0) + (live1 ? o1[1] : 0.0);
+            double v2 = (live0 ? o0[2] : 0.0) + (live1 ? o1[2] : 0.0);
+#pragma unroll
+            for (int o = 8; o > 0; o >>= 1) {
+                v0 += __shfl_xor_sync(0xffffffffu, v0, o);
+                v1 += __shfl_xor_sync(0xffffffffu, v1, o);
+                v2 += __shfl_xor_sync(0xffffffffu, v2, o);
+            }
+            acc0 += v0; acc1 += v1; acc2 += v2;
+        }
+        EP_COUNT(d0.y < 0 ? 3 : 4);
+        if (mode == 0) EP_COUNT(5);
+        const int inst = h ? d0.y : d0.x;
+        if (i == 0 && inst >= 0) { ES[inst] = acc0; ES[NI + inst] = acc1; ES[2 * NI + inst] = acc2; }
+    }
+}
+
+// Pairs of the active list (see above).  Thread per list position; leaders (even rank within their region's run and sign class)
+// append one pair each through a warp-aggregated counter — the order of the pair list follows the active list only roughly,
+// which changes scheduling, never results.
+__global__ void k_make_pairs(int n_items, const int* __restrict__ items, int n_init, const RegionDesc* __restrict__ rdesc,
+                             const double* __restrict__ phi /*[3][NI]*/, int64_t NI, PairDesc* __restrict__ pdesc, double* __restrict__ phil2,
+                             int64_t cap, const int* __restrict__ n_dev, int* __restrict__ n_pairs) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (n_dev) n_items = __ldg(n_dev);
+    bool leader = false;
+    int inst = 0, partner = -1, u = 0;
+    double c = 0.0;
+    if (i < n_items) {
+        inst = items ? items[i] : i;
+        u = inst / n_init;
+        c = phi[2 * NI + inst];
+        const bool cneg = __double2hiint(c) < 0, aneg = __double2hiint(phi[inst]) < 0;
+        // Pairing order within the region's run and the sign class of c: starts with a ≥ 0 in list order, then starts with a < 0
+        // — two starts that agree on the sign of a mostly agree on the sign of α_l = N_l (a + b ρ_l), i.e. on the block body.
+        int pos_before = 0, neg_before = 0, pos_after = 0;
+        int next_pos = -1, next_neg = -1;                  // first classmates after this one
+        for (int j = 1; j < n_init && i - j >= 0; ++j) {
+            const int o = items ? items[i - j] : i - j;
+            if (o / n_init != u) break;
+            if ((__double2hiint(phi[2 * NI + o]) < 0) != cneg) continue;
+            if (__double2hiint(phi[o]) < 0) ++neg_before; else ++pos_before;
+        }
+        for (int j = 1; j < n_init && i + j < n_items; ++j) {
+            const int o = items ? items[i + j] : i + j;
+            if (o / n_init != u) break;
+            if ((__double2hiint(phi[2 * NI + o]) < 0) != cneg) continue;
+            if (__double2hiint(phi[o]) < 0) { if (next_neg < 0) next_neg = o; }
+            else { ++pos_after; if (next_pos < 0) next_pos = o; }
+        }
+        // first a < 0 classmate of the whole run (needed by the last a ≥ 0 start when their number is odd)
+        int first_neg = next_neg;
+        if (neg_before > 0) {
+            for (int j = 1; j < n_init && i - j >= 0; ++j) {
+                const int o = items ? items[i - j] : i - j;
+                if (o / n_init != u) break;
+                if ((__double2hiint(phi[2 * NI + o]) < 0) == cneg && __double2hiint(phi[o]) < 0) first_neg = o;
+            }
+        }
+        const int rank = aneg ? pos_before + pos_after + neg_before : pos_before;
+        leader = (rank & 1) == 0;
+        if (leader) partner = aneg ? next_neg : (next_pos >= 0 ? next_pos : first_neg);
+    }
+    const bool lneg = leader && __double2hiint(c) < 0;
+    const unsigned mask_p = __ballot_sync(0xffffffffu, leader && !lneg), mask_n = __ballot_sync(0xffffffffu, lneg);
+    if ((mask_p | mask_n) == 0u) return;
+    const int lane = threadIdx.x & 31;
+    int base_p = 0, base_n = 0;
+    if (mask_p) {
+        const int first = __ffs(mask_p) - 1;
+        if (lane == first) base_p = atomicAdd(n_pairs, __popc(mask_p));
+        base_p = __shfl_sync(0xffffffffu, base_p, first);
+    }
+    if (mask_n) {
+        const int first = __ffs(mask_n) - 1;
+        if (lane == first) base_n = atomicAdd(n_pairs + 1, __popc(mask_n));
+        base_n = __shfl_sync(0xffffffffu, base_n, first);
+    }
+    if (!leader) return;
+    const unsigned below = (1u << lane) - 1u;
+    // c ≥ 0: k-th pair at position k; c < 0: k-th pair at position cap − 1 − k (k_estep_pair reads them in the same order)
+    const int p = lneg ? (int)cap - 1 - (base_n + __popc(mask_n & below)) : base_p + __popc(mask_p & below);
+    const RegionDesc rd = rdesc[u];
+    const int ib = partner >= 0 ? partner : inst;
+    const double cB = phi[2 * NI + ib];
+    // rescale policy: the more careful of the two instances' (see k_make_desc); NaN bounds or a NaN c choose the slow path
+    const double B = (double)rd.llrmax + 2.0 * fmax(fabs(c), fabs(cB)) * (double)rd.idmax;
+    int mode = (B <= (double)E_BOUND_2) ? 2 : ((B <= (double)E_BOUND_1) ? 1 : 0);
+    if (c != c || cB != cB) mode = 0;
+    PairDesc d;
+    d.instA = inst; d.instB = partner; d.L = rd.L; d.M = rd.M | (mode << ITEM_MODE_SHIFT); d.g0 = rd.g0; d.ew_off = rd.ew_off;
+    d.ridx = rd.ridx; d.pad0 = d.pad1 = d.pad2 = 0;
+    pdesc[p] = d;
+    phil2[p] = phi[inst]; phil2[cap + p] = phi[NI + inst]; phil2[2 * cap + p] = c;
+    phil2[3 * cap + p] = phi[ib]; phil2[4 * cap + p] = phi[NI + ib]; phil2[5 * cap + p] = cB;
+}
+
+// ---------------------------------------------------------------------------------------------------
 // score: Q = (1/M) Σ_m log p(y_m; ϕ) = (1/M) Σ_m [base_m + log Zc_m,rel] − log Z_rel
 // (the |α|,|β| offsets of the relative potentials are identical in Zc and Z and cancel)
 // ---------------------------------------------------------------------------------------------------
@@ -1577,6 +1966,27 @@ struct PackedRegions {
 inline unsigned blocks_for(int64_t n, int per_block) { return (unsigned)((n + per_block - 1) / per_block); }
 
 static int env_int(const char* name, int dflt) { const char* e = getenv(name); return e ? atoi(e) : dflt; }
+// Once per device: k_estep_pair asks for more than the 48 KB static shared-memory limit, and EP_BLOCKS of its blocks only fit an SM
+// when the L1/shared split is at its shared-memory end (left to itself the driver may pick a smaller carveout and keep fewer
+// blocks resident).  CPN_EP_CARVEOUT: percent of the maximum, -1 = the driver's choice.
+static cudaError_t ep_prepare(cpn_ctx* ctx) {
+    if (ctx->ep_attr_set) return cudaSuccess;
+    cudaError_t e;
+    const int carve = env_int("CPN_EP_CARVEOUT", 100);
+    if ((e = cudaFuncSetAttribute(k_estep_pair<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)EP_SMEM)) != cudaSuccess) return e;
+    if ((e = cudaFuncSetAttribute(k_estep_pair<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)EP_SMEM)) != cudaSuccess) return e;
+    if (carve >= 0) {
+        if ((e = cudaFuncSetAttribute(k_estep_pair<false>, cudaFuncAttributePreferredSharedMemoryCarveout, carve)) != cudaSuccess) return e;
+        if ((e = cudaFuncSetAttribute(k_estep_pair<true>, cudaFuncAttributePreferredSharedMemoryCarveout, carve)) != cudaSuccess) return e;
+    }
+    if (env_int("CPN_TRACE", 0)) {
+        int nb = 0;
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k_estep_pair<false>, E_WARPS * 32, EP_SMEM);
+        fprintf(stderr, "[cpn] k_estep_pair: %zu B shared memory per block, %d blocks per SM possible, carveout %d\n", (size_t)EP_SMEM, nb, carve);
+    }
+    ctx->ep_attr_set = true;
+    return cudaSuccess;
+}
 
 // CPN_TRACE=1 prints host-side phase timestamps (ms since the first traced event) to stderr.
 static void trace(const cpn_ctx* ctx, const char* what) {
@@ -1777,9 +2187,22 @@ int fit_impl(cpn_ctx* ctx, bool on_device, int64_t R, const int64_t* grp_off, co
         DevBuf<unsigned char> alive;
         DevBuf<int> blk_cnt;
         DevBuf<ItemDesc> idesc;
+        DevBuf<PairDesc> pdesc;
         DevBuf<double> phil;
-        CPN_CUDA(ctx, idesc.alloc(NI, s));
-        CPN_CUDA(ctx, phil.alloc(3 * NI, s));
+        DevBuf<int> pair_cnt;
+        // two instances per E-step warp (k_estep_pair) whenever the active list keeps a region's starts together, i.e. with the
+        // order-preserving compaction of the analytic M-step; CPN_ESTEP_PAIRS=0 selects the one-instance kernel
+        const bool pairs = mstep_mode == CPN_MSTEP_ANALYTIC && env_int("CPN_ESTEP_PAIRS", 1) != 0;
+        if (pairs) {
+            CPN_CUDA(ctx, ep_prepare(ctx));
+            CPN_CUDA(ctx, pdesc.alloc(NI, s));
+            CPN_CUDA(ctx, phil.alloc(6 * NI, s));
+            CPN_CUDA(ctx, pair_cnt.alloc(2 * (size_t)max_em_iters, s));          // per iteration: pairs with c ≥ 0, pairs with c < 0
+            CPN_CUDA(ctx, cudaMemsetAsync(pair_cnt.p, 0, 2 * (size_t)max_em_iters * sizeof(int), s));
+        } else {
+            CPN_CUDA(ctx, idesc.alloc(NI, s));
+            CPN_CUDA(ctx, phil.alloc(3 * NI, s));
+        }
         CPN_CUDA(ctx, alive.alloc(NI, s));
         CPN_CUDA(ctx, blk_cnt.alloc((NI + CP_TILE - 1) / CP_TILE, s));
         int ws_blocks_per_sm = 1;
@@ -1837,11 +2260,22 @@ int fit_impl(cpn_ctx* ctx, bool on_device, int64_t R, const int64_t* grp_off, co
             const int* n_dev = counts.p + 2 * it;
             int* queue = counts.p + 2 * it + 1;
             int* n_out = counts.p + 2 * (it + 1);
+            if (pairs) {
+                // at most ub pairs; ≈ ub/2 unless many regions are down to one active start — the grid covers 5/8·ub, warps stride
+                const unsigned pgrid = (unsigned)(((int64_t)ub * 5 / 8 + E_WARPS - 1) / E_WARPS + 1);
+                { KTimer kt(ctx, CPN_K_PREP);
+                  k_make_pairs<<<blocks_for(ub, 256), 256, 0, s>>>(ub, cur, n_init, rt.rdesc, phi.p, NI, pdesc.p, phil.p, NI, n_dev,
+                                                                   pair_cnt.p + 2 * it); }
+                { KTimer kt(ctx, CPN_K_ESTEP);
+                  if (views) k_estep_pair<true><<<pgrid, E_WARPS * 32, EP_SMEM, s>>>(pair_cnt.p + 2 * it, pdesc.p, phil.p, NI, rt, NI, ES.p);
+                  else k_estep_pair<false><<<pgrid, E_WARPS * 32, EP_SMEM, s>>>(pair_cnt.p + 2 * it, pdesc.p, phil.p, NI, rt, NI, ES.p); }
+            } else {
             { KTimer kt(ctx, CPN_K_PREP);
               k_make_desc<<<blocks_for(ub, 256), 256, 0, s>>>(ub, cur, n_init, rt.rdesc, phi.p, NI, idesc.p, phil.p, NI, n_dev); }
             { KTimer kt(ctx, CPN_K_ESTEP);
               if (views) k_estep<true><<<estep_grid(ctx, ub), E_WARPS * 32, 0, s>>>(ub, idesc.p, phil.p, NI, rt, NI, ES.p, n_dev);
               else k_estep<false><<<estep_grid(ctx, ub), E_WARPS * 32, 0, s>>>(ub, idesc.p, phil.p, NI, rt, NI, ES.p, n_dev); }
+            }
             if (mstep_mode == CPN_MSTEP_ANALYTIC) {
                 unsigned grid = std::min<unsigned>(blocks_for(ub, M_THREADS), (unsigned)(ctx->sm_count * ws_blocks_per_sm));
                 { KTimer kt(ctx, CPN_K_MSTEP);
@@ -1860,6 +2294,19 @@ int fit_impl(cpn_ctx* ctx, bool on_device, int64_t R, const int64_t* grp_off, co
             std::swap(cur, nxt);
         }
         trace(ctx, "em-done");
+#ifdef EP_STATS
+        if (pairs) {
+            CPN_CUDA(ctx, cpn_wait_stream(ctx, s));
+            std::vector<int> h_pc(2 * max_em_iters), h_ct(2 * (max_em_iters + 1));
+            unsigned long long h_st[8];
+            cudaMemcpy(h_pc.data(), pair_cnt.p, 2 * max_em_iters * sizeof(int), cudaMemcpyDeviceToHost);
+            cudaMemcpy(h_ct.data(), counts.p, h_ct.size() * sizeof(int), cudaMemcpyDeviceToHost);
+            cudaMemcpyFromSymbol(h_st, ep_stats, sizeof(h_st));
+            fprintf(stderr, "[ep_stats] blocks + %llu  - %llu  general %llu | singleton pairs %llu  full pairs %llu  slow %llu\n", h_st[0], h_st[1],
+                    h_st[2], h_st[3], h_st[4], h_st[5]);
+            for (int it = 0; it < max_em_iters; ++it) fprintf(stderr, "[ep_stats] it %d active %d pairs c>=0 %d c<0 %d\n", it, h_ct[2 * it], h_pc[2 * it], h_pc[2 * it + 1]);
+        }
+#endif
         DevBuf<double> work;
         CPN_CUDA(ctx, work.alloc(4, s));
         CPN_CUDA(ctx, cudaMemsetAsync(work.p, 0, 4 * sizeof(double), s));
@@ -2528,6 +2975,47 @@ int cpn_estep_batch(cpn_ctx* ctx, int64_t R, const int64_t* grp_off, const doubl
     float ms = 0;
     CPN_CUDA(ctx, cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1));
     ctx->last_ms = ms;
+    if (ctx->profile) cpn_profile_collect(ctx);
+    return CPN_OK;
+}
+
+// Test hook for the paired E-step: n_init parameter vectors per region (phi [R·n_init][3]), paired and evaluated exactly as one EM
+// iteration of cpn_fit_batch does (k_make_pairs → k_estep_pair); ES [R·n_init][3].
+int cpn_estep_batch_starts(cpn_ctx* ctx, int64_t R, const int64_t* grp_off, const double* Nl, const double* rho_l, const double* d_l,
+                           const int64_t* read_off, const double* log_pyx_u, const double* log_pyx_m, int32_t n_init, const double* phi,
+                           double* ES) {
+    if (!ctx) return CPN_ERR_ARG;
+    CPN_ARG(ctx, R >= 0 && n_init >= 1 && grp_off && Nl && rho_l && d_l && read_off && log_pyx_u && log_pyx_m && phi && ES, "null pointer");
+    CPN_ARG(ctx, R * (int64_t)n_init < (int64_t)2147483647, "R*n_init must fit in int32");
+    CPN_CUDA(ctx, cudaSetDevice(ctx->device));
+    LaunchCounter lc(ctx);
+    if (R == 0) return CPN_OK;
+    cudaStream_t s = ctx->stream;
+    {
+        PackedRegions pk;
+        int rc = pack_regions(ctx, pk, false, true, R, grp_off, Nl, rho_l, d_l, read_off, log_pyx_u, log_pyx_m);
+        if (rc) return rc;
+        const int64_t NI = R * n_init;
+        DevBuf<double> d_phi_in, d_phi, d_ES, d_ESo, phil;
+        DevBuf<PairDesc> pdesc;
+        DevBuf<int> pair_cnt;
+        CPN_CUDA(ctx, d_phi_in.upload(phi, 3 * NI, s));
+        CPN_CUDA(ctx, d_phi.alloc(3 * NI, s)); CPN_CUDA(ctx, d_ES.alloc(3 * NI, s)); CPN_CUDA(ctx, d_ESo.alloc(3 * NI, s));
+        CPN_CUDA(ctx, pdesc.alloc(NI, s)); CPN_CUDA(ctx, phil.alloc(6 * NI, s)); CPN_CUDA(ctx, pair_cnt.alloc(2, s));
+        CPN_CUDA(ctx, cudaMemsetAsync(pair_cnt.p, 0, 2 * sizeof(int), s));
+        CPN_CUDA(ctx, cudaMemsetAsync(d_ES.p, 0xff, 3 * NI * sizeof(double), s));       // NaN: an instance no pair covers would show
+        CPN_CUDA(ctx, ep_prepare(ctx));
+        { KTimer kt(ctx, CPN_K_PREP); k_pack_phi<<<blocks_for(NI, 256), 256, 0, s>>>(NI, d_phi_in.p, d_phi.p); }
+        { KTimer kt(ctx, CPN_K_PREP);
+          k_make_pairs<<<blocks_for(NI, 256), 256, 0, s>>>((int)NI, nullptr, n_init, pk.rt.rdesc, d_phi.p, NI, pdesc.p, phil.p, NI, nullptr, pair_cnt.p); }
+        const unsigned pgrid = (unsigned)((NI * 5 / 8 + E_WARPS - 1) / E_WARPS + 1);
+        { KTimer kt(ctx, CPN_K_ESTEP);
+          k_estep_pair<false><<<pgrid, E_WARPS * 32, EP_SMEM, s>>>(pair_cnt.p, pdesc.p, phil.p, NI, pk.rt, NI, d_ES.p); }
+        { KTimer kt(ctx, CPN_K_PREP); k_unpack3<<<blocks_for(NI, 256), 256, 0, s>>>(NI, d_ES.p, d_ESo.p); }
+        CPN_CUDA(ctx, d_ESo.download(ES, 3 * NI, s));
+        CPN_CUDA(ctx, cudaGetLastError());
+        CPN_CUDA(ctx, cpn_wait_stream(ctx, s));
+    }
     if (ctx->profile) cpn_profile_collect(ctx);
     return CPN_OK;
 }

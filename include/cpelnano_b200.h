@@ -204,6 +204,13 @@ int cpn_analyze_wgbs_batch(cpn_ctx* ctx, int64_t R,
 int cpn_estep_batch(cpn_ctx* ctx, int64_t R, const int64_t* grp_off, const double* Nl, const double* rho_l,
                     const double* d_l, const int64_t* read_off, const double* log_pyx_u, const double* log_pyx_m,
                     const double* phi /*[R*3]*/, double* ES /*[R*3]*/, double* ave_logpy /*[R] or NULL*/);
+/*   cpn_estep_batch_starts   the same statistics for n_init parameter vectors per region (phi [R*n_init*3], start-major within
+ *                     a region), evaluated the way an EM iteration of cpn_fit_batch evaluates them: the starts of a region are
+ *                     paired (two per warp, sharing the region's emission rows) — get_ϕhat!'s inner E-step over all starts,
+ *                     src/em_algorithm.jl:142-146 inside :374-383                                                   */
+int cpn_estep_batch_starts(cpn_ctx* ctx, int64_t R, const int64_t* grp_off, const double* Nl, const double* rho_l,
+                           const double* d_l, const int64_t* read_off, const double* log_pyx_u, const double* log_pyx_m,
+                           int32_t n_init, const double* phi /*[R*n_init*3]*/, double* ES /*[R*n_init*3]*/);
 int cpn_mstep_batch(cpn_ctx* ctx, int64_t R, const int64_t* grp_off, const double* Nl, const double* rho_l,
                     const double* d_l, const int64_t* n_reads /*[R]*/, const double* ES /*[R*3]*/,
                     const double* phi_init /*[R*3]*/, int32_t mstep_mode, double* sol /*[R*3]*/,

@@ -74,6 +74,56 @@ def test_estep_ragged_and_extreme(engine, orc):
         assert close(lp[r], lp_o, 1e-10), (r, lp[r], lp_o)
 
 
+def test_estep_pairs_vs_oracle_and_single(engine, orc, cpn, batch):
+    """The paired E-step (two starts of a region per warp, two reads per lane — what every EM iteration of cpn_fit_batch runs)
+    against the oracle and against the one-instance kernel: odd and even numbers of starts, both signs of c in one region
+    (only equal signs are paired, the rest run as singletons), starts that disagree on the sign of α_l (general block body),
+    ragged read counts over one and several 32-read chunks, chains shorter than a block and longer than a tile, LLRs beyond
+    the unscaled-run bound (per-group rescale path)."""
+    rng = np.random.default_rng(17)
+    # (1) the simulated nanopore batch, 5 starts per region
+    n_init = 5
+    phis = cpn.simulations.gen_phi0s(rng, batch.R, n_init)
+    phis[::2, 1, 2] *= -1.0; phis[::3, 3, 2] *= -1.0; phis[1::4, :, 0] *= -1.0
+    ES = engine.lib.estep_batch_starts(batch.grp_off, batch.Nl, batch.rho_l, batch.d_l, batch.read_off, batch.log_pyx_u, batch.log_pyx_m, phis)
+    assert np.all(np.isfinite(ES))
+    for k in range(n_init):
+        ES1, _ = engine.lib.estep_batch(batch.grp_off, batch.Nl, batch.rho_l, batch.d_l, batch.read_off, batch.log_pyx_u, batch.log_pyx_m,
+                                        np.ascontiguousarray(phis[:, k]), with_logpy=False)
+        assert close(ES[:, k], ES1, 1e-12), k
+    for r in range(0, batch.R, 3):
+        rg = batch.region(r)
+        for k in range(n_init):
+            es_o = orc.e_step(rg["Nl"], rg["rho_l"], rg["d_l"], rg["lu"], rg["lm"], phis[r, k])
+            assert close(ES[r, k], es_o, 1e-10), (r, k, ES[r, k], es_o)
+    # (2) ragged and extreme shapes, 4 starts per region
+    Ls = [2, 3, 7, 8, 17, 64, 65, 129, 150]
+    Ms = [1, 31, 16, 17, 32, 33, 70, 5, 64]
+    grp_off = np.concatenate([[0], np.cumsum(Ls)])
+    read_off = np.concatenate([[0], np.cumsum(Ms)])
+    Nl = rng.integers(1, 6, grp_off[-1]).astype(float)
+    rho = rng.uniform(0.001, 0.1, grp_off[-1])
+    dl = rng.integers(11, 300, grp_off[-1] - len(Ls)).astype(float)
+    lus, lms = [], []
+    for r, (L, M) in enumerate(zip(Ls, Ms)):
+        spread = 15 if r % 2 == 0 else 3          # every other region stays within the unscaled-run bound
+        lu = rng.normal(-100, 40, (M, L)); lm = lu + rng.normal(0, spread, (M, L))
+        mask = rng.random((M, L)) < 0.3
+        lu[mask] = np.nan; lm[mask] = np.nan
+        if M > 2:
+            lu[1] = np.nan; lm[1] = np.nan
+        lus.append(lu.reshape(-1)); lms.append(lm.reshape(-1))
+    base = np.array([[4.9, -50.0, 9.9], [-5.0, 50.0, 0.0], [0.3, 10.0, -7.5], [-0.2, -3.0, 2.0], [1.0, 20.0, 5.0], [0.0, 0.0, 0.0],
+                     [0.05, -1.0, 0.3], [-0.4, 8.0, -0.2], [0.7, 2.0, 1.5]])
+    phis2 = np.stack([base, base * np.array([-1.0, 1.0, 1.0]), base * np.array([0.5, -0.5, 1.0]), base * np.array([1.0, 1.0, -1.0])], axis=1)
+    ES2 = engine.lib.estep_batch_starts(grp_off, Nl, rho, dl, read_off, np.concatenate(lus), np.concatenate(lms), phis2)
+    for r, (L, M) in enumerate(zip(Ls, Ms)):
+        g0 = grp_off[r]
+        for k in range(4):
+            es_o = orc.e_step(Nl[g0:g0 + L], rho[g0:g0 + L], dl[g0 - r:g0 - r + L - 1], lus[r].reshape(M, L), lms[r].reshape(M, L), phis2[r, k])
+            assert close(ES2[r, k], es_o, 1e-9), (r, k, ES2[r, k], es_o)
+
+
 # ---- (c): M-step ------------------------------------------------------------------------------------------
 def test_grad_logZ_analytic_vs_fd_oracle(engine, orc, batch):
     """With ES = 0 and ϕ_init = ϕ the initial residual of the solve is ∇logZ(ϕ); a converged 0-iteration solve is not
