@@ -82,6 +82,7 @@ struct cpn_ctx {
     int device = 0;
     int sm_count = 148;
     bool ep_attr_set = false;                // k_estep_pair's dynamic shared-memory limit raised on this device
+    int epw_blocks = 1;                      // resident k_estep_pair_ws blocks per SM (occupancy query, ep_prepare)
     int estep_blocks = 0;                    // resident k_estep blocks per SM (occupancy query, cached by the first E-step launch)
     cudaStream_t stream = nullptr;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;

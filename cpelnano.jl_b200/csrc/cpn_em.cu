@@ -909,6 +909,231 @@ __global__ void __launch_bounds__(E_WARPS * 32, EP_BLOCKS) k_estep_pair(const in
     }
 }
 
+// ---------------------------------------------------------------------------------------------------
+// The paired E-step as a resident grid with a work queue and a head that is prefetched (plain regions)
+// ---------------------------------------------------------------------------------------------------
+// ncu (source page) on k_estep_pair: about a third of a warp's life is the HEAD of a pair — three dependent round trips to L2
+// (descriptor and ϕ → group tables → first emission rows) during which it issues nothing — and with 16 warps per SM the FP64 pipe
+// idles 37 % of the time.  Here every warp takes pairs from a queue (one atomic per pair: whoever is free takes the next one, so
+// the warps of an SM may progress at different rates without idling, which the static walk of E_PERSIST could not offer) and
+// brings its NEXT pair's descriptor, ϕ and group tables into shared memory with cp.async while it works on the current one:
+//   loop top        descriptor and ϕ of the current pair: shared memory → registers; take the next pair from the queue, start the
+//                   copy of its descriptor and ϕ (group A)
+//   tile 0          potentials from the staged tables (shared memory, not global); first emission rows by TMA as before
+//   after tile 0    wait for A, start the copy of the next pair's group tables (group B) — it lands during the chain loop
+//   chain, epilogue as k_estep_pair
+// What is left exposed per pair is one round trip (the first emission rows), overlapped with the exponentials of the tile.
+struct __align__(16) PairStage { int4 d[3]; double phi[6]; double pad[2]; double na[TILE], nb[TILE], id[TILE]; };
+constexpr size_t EPW_SMEM = (size_t)E_WARPS * (sizeof(PairTile) + sizeof(EmisRing) + sizeof(PairStage)) + (size_t)E_WARPS * 4 * sizeof(unsigned long long);
+
+__device__ __forceinline__ void cp_async8(void* dst_smem, const void* src) {
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"((unsigned)__cvta_generic_to_shared(dst_smem)), "l"(src) : "memory");
+}
+__device__ __forceinline__ void cp_async16(void* dst_smem, const void* src) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((unsigned)__cvta_generic_to_shared(dst_smem)), "l"(src) : "memory");
+}
+// descriptor (three 16-byte parts, lanes 0-2) and ϕ of both instances (lanes 3-8) of the pair at list position p
+__device__ __forceinline__ void stage_desc(PairStage& st, const PairDesc* __restrict__ pdesc, const double* __restrict__ phil2, int64_t cap,
+                                           int p, int lane) {
+    if (lane < 3) cp_async16(&st.d[lane], reinterpret_cast<const int4*>(pdesc + p) + lane);
+    else if (lane < 9) cp_async8(&st.phi[lane - 3], phil2 + (size_t)(lane - 3) * cap + p);
+    asm volatile("cp.async.commit_group;" ::: "memory");
+}
+// group tables of the first tile of a region: N_l, N_l ρ_l, and 1/d of the coupling INTO group l (0 for l = 0)
+__device__ __forceinline__ void stage_tables(PairStage& st, const RegionTables& rt, int64_t g0, int L, int lane) {
+    const int n = min(L, TILE);
+    for (int j = lane; j < n; j += 32) {
+        cp_async8(&st.na[j], rt.na + g0 + j);
+        cp_async8(&st.nb[j], rt.nb + g0 + j);
+        if (j > 0) cp_async8(&st.id[j], rt.invd + g0 + j - 1);
+    }
+    asm volatile("cp.async.commit_group;" ::: "memory");
+}
+__device__ __forceinline__ void ptile_load_staged(PairTileRegs& tr, const PairStage& st, int n, int i, double a, double b,
+                                                  unsigned long long& mP, unsigned long long& mN) {
+    constexpr int K = TILE / 16;
+#pragma unroll
+    for (int k = 0; k < K; ++k) {
+        const int j = i + 16 * k;
+        const bool in = j < n;
+        tr.na[k] = in ? st.na[j] : 0.0;
+        tr.nb[k] = in ? st.nb[j] : 0.0;
+        tr.id[k] = (in && j > 0) ? st.id[j] : 0.0;
+    }
+    mP = 0ull; mN = 0ull;
+#pragma unroll
+    for (int k = 0; k < K; ++k) {
+        const int j = i + 16 * k;
+        tr.alpha[k] = fma(b, tr.nb[k], a * tr.na[k]);
+        const unsigned bal = __ballot_sync(0xffffffffu, j < n && __double2hiint(tr.alpha[k]) >= 0);
+        mP |= (unsigned long long)(bal & (bal >> 16) & 0xffffu) << (16 * k);
+        mN |= (unsigned long long)(~(bal | (bal >> 16)) & 0xffffu) << (16 * k);
+    }
+}
+
+// estep_pair_chunk for plain regions with the first tile's tables taken from the stage when `staged`; `next` ≥ 0: once the first
+// tile has been consumed, the next pair's descriptor (group A, in flight since the loop top) is awaited and its tables are requested
+__device__ __forceinline__ void estep_pair_chunk_ws(PairTile& pt, EmisRing& ring, PairStage& stg, const RegionTables& rt, int L, int lane,
+                                                    const double* __restrict__ na_g, const double* __restrict__ nb_g,
+                                                    const double* __restrict__ invd_g, EmisSrc<false>& es, double a, double b, double cabs,
+                                                    bool bpos, int rmask, bool staged, bool fetch_next, double out0[3], double out1[3]) {
+    const int h = lane >> 4, i = lane & 15;
+    const double2* __restrict__ W = pt.w[h];
+    const double2* __restrict__ TN = pt.tn[h];
+    const double2* __restrict__ BD = pt.bd[h];
+    EState s0{1.0, 1.0, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0};
+    EState s1 = s0;
+    const int Lfull = L & ~(E_PF - 1);
+    constexpr unsigned ALL = (1u << E_PF) - 1;
+    ering_issue(ring, 2, es, false, Lfull, L - Lfull, lane);
+    int g = 0;
+    for (int l0 = 0; l0 < L; l0 += TILE) {
+        const int n = min(TILE, L - l0);
+        const int nfull = n & ~(E_PF - 1);
+        PairTileRegs tr;
+        unsigned long long mP, mN;
+        if (staged && l0 == 0) ptile_load_staged(tr, stg, n, i, a, b, mP, mN);
+        else ptile_load(tr, l0, n, i, na_g, nb_g, invd_g, a, b, mP, mN);
+        ering_issue(ring, g & 1, es, ((unsigned)mP & ALL) == ALL, g * E_PF, nfull > 0 ? E_PF : 0, lane);
+        __syncwarp();
+        ptile_store(pt, tr, l0, n, h, i, cabs, bpos);
+        __syncwarp();
+        if (fetch_next && l0 == 0) {
+            // the staged tables are in registers and in the tile now: the stage may take the next pair's
+            asm volatile("cp.async.wait_group 0;" ::: "memory");
+            __syncwarp();
+            const int4 nd0 = stg.d[0];
+            const longlong2 nd1 = *reinterpret_cast<const longlong2*>(&stg.d[1]);
+            stage_tables(stg, rt, nd1.x, nd0.z, lane);
+        }
+#pragma unroll 1
+        for (int j0 = 0; j0 < nfull; j0 += E_PF, ++g) {
+            const unsigned bp = (unsigned)(mP >> j0) & ALL, bn = (unsigned)(mN >> j0) & ALL;
+            const int j1 = j0 + E_PF;
+            const unsigned bp1 = (unsigned)(mP >> (j1 & (TILE - 1))) & ALL;
+            ering_issue(ring, (g + 1) & 1, es, bp1 == ALL, (g + 1) * E_PF, (j1 < nfull) ? E_PF : 0, lane);
+            const int slot = g & 1;
+            ering_wait<1>(es, slot);
+            if (g > 0 && (g & rmask) == 0) { estep_rescale(s0); estep_rescale(s1); }
+            const double* r = &ring.r[slot][0][i];
+            if (bpos) {
+                if (bp == ALL) pair_block<true, 1>(s0, s1, W + j0, TN + j0, BD + j0, r, E_PF);
+                else if (bn == ALL) pair_block<true, -1>(s0, s1, W + j0, TN + j0, BD + j0, r, E_PF);
+                else pair_block<true, 0>(s0, s1, W + j0, TN + j0, BD + j0, r, E_PF);
+            } else {
+                if (bp == ALL) pair_block<false, 1>(s0, s1, W + j0, TN + j0, BD + j0, r, E_PF);
+                else if (bn == ALL) pair_block<false, -1>(s0, s1, W + j0, TN + j0, BD + j0, r, E_PF);
+                else pair_block<false, 0>(s0, s1, W + j0, TN + j0, BD + j0, r, E_PF);
+            }
+        }
+        if (nfull < n) {
+            ering_wait<0>(es, 2);
+            if (g > 0) { estep_rescale(s0); estep_rescale(s1); }
+            const double* r = &ring.r[2][0][i];
+#pragma unroll 1
+            for (int u = 0; u < n - nfull; ++u) {
+                const double2 w = W[nfull + u], tn = TN[nfull + u], bd = BD[nfull + u];
+                if (bpos) { estep_core<true, 0>(s0, w, tn, bd, r[u * 32]); estep_core<true, 0>(s1, w, tn, bd, r[u * 32 + 16]); }
+                else { estep_core<false, 0>(s0, w, tn, bd, r[u * 32]); estep_core<false, 0>(s1, w, tn, bd, r[u * 32 + 16]); }
+            }
+        }
+    }
+    const double inv0 = 1.0 / (s0.fp + s0.fm), inv1 = 1.0 / (s1.fp + s1.fm);
+    out0[0] = (s0.gap + s0.gam) * inv0; out0[1] = (s0.gbp + s0.gbm) * inv0; out0[2] = (s0.gcp + s0.gcm) * inv0;
+    out1[0] = (s1.gap + s1.gam) * inv1; out1[1] = (s1.gbp + s1.gbm) * inv1; out1[2] = (s1.gcp + s1.gcm) * inv1;
+}
+
+// cnt: {pairs with c ≥ 0, pairs with c < 0, queue head (zero at launch), unused}
+__global__ void __launch_bounds__(E_WARPS * 32, EP_BLOCKS) k_estep_pair_ws(int* __restrict__ cnt, const PairDesc* __restrict__ pdesc,
+                                                                            const double* __restrict__ phil2 /*[6][cap] by pair position*/,
+                                                                            int64_t cap, RegionTables rt, int64_t NI, double* __restrict__ ES) {
+    extern __shared__ __align__(128) unsigned char ep_smem[];
+    PairTile* tiles = reinterpret_cast<PairTile*>(ep_smem);
+    EmisRing* rings = reinterpret_cast<EmisRing*>(ep_smem + (size_t)E_WARPS * sizeof(PairTile));
+    PairStage* stages = reinterpret_cast<PairStage*>(ep_smem + (size_t)E_WARPS * (sizeof(PairTile) + sizeof(EmisRing)));
+    unsigned long long* mbars = reinterpret_cast<unsigned long long*>(ep_smem + (size_t)E_WARPS * (sizeof(PairTile) + sizeof(EmisRing) + sizeof(PairStage)));
+    const int w = threadIdx.x >> 5, lane = threadIdx.x & 31, h = lane >> 4, i = lane & 15;
+    PairStage& stg = stages[w];
+    EmisSrc<false> es;
+    es.mbar = (unsigned)__cvta_generic_to_shared(&mbars[4 * w]);
+    es.ring = (unsigned)__cvta_generic_to_shared(&rings[w].r[0][0][0]);
+    es.phase = 0u;
+    if (lane == 0) {
+        mbar_init(es.mbar, 1u); mbar_init(es.mbar + 8u, 1u); mbar_init(es.mbar + 16u, 1u);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncwarp();
+    const int n_pos = __ldg(cnt), n_pairs = n_pos + __ldg(cnt + 1);
+    auto take = [&]() -> int {
+        int q = 0;
+        if (lane == 0) q = atomicAdd(cnt + 2, 1);
+        return __shfl_sync(0xffffffffu, q, 0);
+    };
+    auto position = [&](int pq) -> int { return pq < n_pos ? pq : (int)cap - 1 - (pq - n_pos); };
+    int pq = take();
+    if (pq >= n_pairs) return;
+    // the first pair of this warp: nothing to overlap with
+    stage_desc(stg, pdesc, phil2, cap, position(pq), lane);
+    asm volatile("cp.async.wait_group 0;" ::: "memory");
+    __syncwarp();
+    stage_tables(stg, rt, reinterpret_cast<const longlong2*>(&stg.d[1])->x, stg.d[0].z, lane);
+    asm volatile("cp.async.wait_group 0;" ::: "memory");
+    __syncwarp();
+#pragma unroll 1
+    while (true) {
+        const int4 d0 = stg.d[0];
+        const longlong2 d1 = *reinterpret_cast<const longlong2*>(&stg.d[1]);
+        const double a = stg.phi[3 * h], b = stg.phi[3 * h + 1], c = stg.phi[3 * h + 2];
+        const int L = d0.z, M = d0.w & ITEM_M_MASK, mode = (d0.w >> ITEM_MODE_SHIFT) & 3;
+        const int64_t g0 = d1.x;
+        const bool bpos = __shfl_sync(0xffffffffu, (int)(__double2hiint(c) >= 0), 0) != 0;   // also orders the reads above before the refill
+        const double cabs = fabs(c);
+        const double* ew_r = rt.ew + d1.y;
+        const int nq = take();
+        const bool has_next = nq < n_pairs;
+        if (has_next) stage_desc(stg, pdesc, phil2, cap, position(nq), lane);
+        double acc0 = 0, acc1 = 0, acc2 = 0;
+        const int nchunk = (M + 31) >> 5;
+        for (int ch = 0; ch < nchunk; ++ch) {
+            double o0[3], o1[3];
+            // the next pair's tables replace the staged ones after the LAST chunk's first tile; earlier chunks leave them in place
+            const bool last = ch == nchunk - 1;
+            if (mode != 0) {
+                const size_t eo = (size_t)ch * L * 32;
+                es.p = ew_r + eo;
+                es.pi = rt.ewi + d1.y + eo;
+                estep_pair_chunk_ws(tiles[w], rings[w], stg, rt, L, lane, rt.na + g0, rt.nb + g0, rt.invd + g0, es, a, b, cabs, bpos, mode - 1,
+                                    true, has_next && last, o0, o1);
+            } else {
+                const double* p0 = ew_r + (size_t)ch * L * 32 + i;
+                if (bpos) estep_pair_slow<true>(tiles[w], L, lane, rt.na + g0, rt.nb + g0, rt.invd + g0, p0, p0 + 16, a, b, cabs, o0, o1);
+                else estep_pair_slow<false>(tiles[w], L, lane, rt.na + g0, rt.nb + g0, rt.invd + g0, p0, p0 + 16, a, b, cabs, o0, o1);
+                if (has_next && last) {
+                    asm volatile("cp.async.wait_group 0;" ::: "memory");
+                    __syncwarp();
+                    stage_tables(stg, rt, reinterpret_cast<const longlong2*>(&stg.d[1])->x, stg.d[0].z, lane);
+                }
+            }
+            const bool live0 = ch * 32 + i < M, live1 = ch * 32 + 16 + i < M;
+            double v0 = (live0 ? o0[0] : 0.0) + (live1 ? o1[0] : 0.0);
+            double v1 = (live0 ? o0[1] : 0.0) + (live1 ? o1[1] : 0.0);
+            double v2 = (live0 ? o0[2] : 0.0) + (live1 ? o1[2] : 0.0);
+#pragma unroll
+            for (int o = 8; o > 0; o >>= 1) {
+                v0 += __shfl_xor_sync(0xffffffffu, v0, o);
+                v1 += __shfl_xor_sync(0xffffffffu, v1, o);
+                v2 += __shfl_xor_sync(0xffffffffu, v2, o);
+            }
+            acc0 += v0; acc1 += v1; acc2 += v2;
+        }
+        const int inst = h ? d0.y : d0.x;
+        if (i == 0 && inst >= 0) { ES[inst] = acc0; ES[NI + inst] = acc1; ES[2 * NI + inst] = acc2; }
+        if (!has_next) break;
+        asm volatile("cp.async.wait_group 0;" ::: "memory");      // the next pair's tables (group B)
+        __syncwarp();
+    }
+}
+
 // Pairs of the active list (see above).  Thread per list position; leaders (even rank within their region's run and sign class)
 // append one pair each through a warp-aggregated counter — the order of the pair list follows the active list only roughly,
 // which changes scheduling, never results.
@@ -1975,9 +2200,16 @@ static cudaError_t ep_prepare(cpn_ctx* ctx) {
     const int carve = env_int("CPN_EP_CARVEOUT", 100);
     if ((e = cudaFuncSetAttribute(k_estep_pair<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)EP_SMEM)) != cudaSuccess) return e;
     if ((e = cudaFuncSetAttribute(k_estep_pair<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)EP_SMEM)) != cudaSuccess) return e;
+    if ((e = cudaFuncSetAttribute(k_estep_pair_ws, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)EPW_SMEM)) != cudaSuccess) return e;
     if (carve >= 0) {
         if ((e = cudaFuncSetAttribute(k_estep_pair<false>, cudaFuncAttributePreferredSharedMemoryCarveout, carve)) != cudaSuccess) return e;
         if ((e = cudaFuncSetAttribute(k_estep_pair<true>, cudaFuncAttributePreferredSharedMemoryCarveout, carve)) != cudaSuccess) return e;
+        if ((e = cudaFuncSetAttribute(k_estep_pair_ws, cudaFuncAttributePreferredSharedMemoryCarveout, carve)) != cudaSuccess) return e;
+    }
+    {
+        int nb = 0;
+        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k_estep_pair_ws, E_WARPS * 32, EPW_SMEM) != cudaSuccess || nb < 1) nb = 1;
+        ctx->epw_blocks = nb;
     }
     if (env_int("CPN_TRACE", 0)) {
         int nb = 0;
@@ -2193,12 +2425,13 @@ int fit_impl(cpn_ctx* ctx, bool on_device, int64_t R, const int64_t* grp_off, co
         // two instances per E-step warp (k_estep_pair) whenever the active list keeps a region's starts together, i.e. with the
         // order-preserving compaction of the analytic M-step; CPN_ESTEP_PAIRS=0 selects the one-instance kernel
         const bool pairs = mstep_mode == CPN_MSTEP_ANALYTIC && env_int("CPN_ESTEP_PAIRS", 1) != 0;
+        const bool pair_ws = env_int("CPN_ESTEP_WS", 1) != 0;      // resident grid + work queue + prefetched head (plain regions)
         if (pairs) {
             CPN_CUDA(ctx, ep_prepare(ctx));
             CPN_CUDA(ctx, pdesc.alloc(NI, s));
             CPN_CUDA(ctx, phil.alloc(6 * NI, s));
-            CPN_CUDA(ctx, pair_cnt.alloc(2 * (size_t)max_em_iters, s));          // per iteration: pairs with c ≥ 0, pairs with c < 0
-            CPN_CUDA(ctx, cudaMemsetAsync(pair_cnt.p, 0, 2 * (size_t)max_em_iters * sizeof(int), s));
+            CPN_CUDA(ctx, pair_cnt.alloc(4 * (size_t)max_em_iters, s));          // per iteration: pairs with c ≥ 0, pairs with c < 0, queue head of k_estep_pair_ws
+            CPN_CUDA(ctx, cudaMemsetAsync(pair_cnt.p, 0, 4 * (size_t)max_em_iters * sizeof(int), s));
         } else {
             CPN_CUDA(ctx, idesc.alloc(NI, s));
             CPN_CUDA(ctx, phil.alloc(3 * NI, s));
@@ -2265,10 +2498,12 @@ int fit_impl(cpn_ctx* ctx, bool on_device, int64_t R, const int64_t* grp_off, co
                 const unsigned pgrid = (unsigned)(((int64_t)ub * 5 / 8 + E_WARPS - 1) / E_WARPS + 1);
                 { KTimer kt(ctx, CPN_K_PREP);
                   k_make_pairs<<<blocks_for(ub, 256), 256, 0, s>>>(ub, cur, n_init, rt.rdesc, phi.p, NI, pdesc.p, phil.p, NI, n_dev,
-                                                                   pair_cnt.p + 2 * it); }
+                                                                   pair_cnt.p + 4 * it); }
                 { KTimer kt(ctx, CPN_K_ESTEP);
-                  if (views) k_estep_pair<true><<<pgrid, E_WARPS * 32, EP_SMEM, s>>>(pair_cnt.p + 2 * it, pdesc.p, phil.p, NI, rt, NI, ES.p);
-                  else k_estep_pair<false><<<pgrid, E_WARPS * 32, EP_SMEM, s>>>(pair_cnt.p + 2 * it, pdesc.p, phil.p, NI, rt, NI, ES.p); }
+                  if (views) k_estep_pair<true><<<pgrid, E_WARPS * 32, EP_SMEM, s>>>(pair_cnt.p + 4 * it, pdesc.p, phil.p, NI, rt, NI, ES.p);
+                  else if (pair_ws) k_estep_pair_ws<<<std::min<unsigned>(pgrid, (unsigned)(ctx->sm_count * ctx->epw_blocks)), E_WARPS * 32, EPW_SMEM, s>>>(
+                                        pair_cnt.p + 4 * it, pdesc.p, phil.p, NI, rt, NI, ES.p);
+                  else k_estep_pair<false><<<pgrid, E_WARPS * 32, EP_SMEM, s>>>(pair_cnt.p + 4 * it, pdesc.p, phil.p, NI, rt, NI, ES.p); }
             } else {
             { KTimer kt(ctx, CPN_K_PREP);
               k_make_desc<<<blocks_for(ub, 256), 256, 0, s>>>(ub, cur, n_init, rt.rdesc, phi.p, NI, idesc.p, phil.p, NI, n_dev); }
@@ -3001,8 +3236,8 @@ int cpn_estep_batch_starts(cpn_ctx* ctx, int64_t R, const int64_t* grp_off, cons
         DevBuf<int> pair_cnt;
         CPN_CUDA(ctx, d_phi_in.upload(phi, 3 * NI, s));
         CPN_CUDA(ctx, d_phi.alloc(3 * NI, s)); CPN_CUDA(ctx, d_ES.alloc(3 * NI, s)); CPN_CUDA(ctx, d_ESo.alloc(3 * NI, s));
-        CPN_CUDA(ctx, pdesc.alloc(NI, s)); CPN_CUDA(ctx, phil.alloc(6 * NI, s)); CPN_CUDA(ctx, pair_cnt.alloc(2, s));
-        CPN_CUDA(ctx, cudaMemsetAsync(pair_cnt.p, 0, 2 * sizeof(int), s));
+        CPN_CUDA(ctx, pdesc.alloc(NI, s)); CPN_CUDA(ctx, phil.alloc(6 * NI, s)); CPN_CUDA(ctx, pair_cnt.alloc(4, s));
+        CPN_CUDA(ctx, cudaMemsetAsync(pair_cnt.p, 0, 4 * sizeof(int), s));
         CPN_CUDA(ctx, cudaMemsetAsync(d_ES.p, 0xff, 3 * NI * sizeof(double), s));       // NaN: an instance no pair covers would show
         CPN_CUDA(ctx, ep_prepare(ctx));
         { KTimer kt(ctx, CPN_K_PREP); k_pack_phi<<<blocks_for(NI, 256), 256, 0, s>>>(NI, d_phi_in.p, d_phi.p); }
@@ -3010,7 +3245,10 @@ int cpn_estep_batch_starts(cpn_ctx* ctx, int64_t R, const int64_t* grp_off, cons
           k_make_pairs<<<blocks_for(NI, 256), 256, 0, s>>>((int)NI, nullptr, n_init, pk.rt.rdesc, d_phi.p, NI, pdesc.p, phil.p, NI, nullptr, pair_cnt.p); }
         const unsigned pgrid = (unsigned)((NI * 5 / 8 + E_WARPS - 1) / E_WARPS + 1);
         { KTimer kt(ctx, CPN_K_ESTEP);
-          k_estep_pair<false><<<pgrid, E_WARPS * 32, EP_SMEM, s>>>(pair_cnt.p, pdesc.p, phil.p, NI, pk.rt, NI, d_ES.p); }
+          if (env_int("CPN_ESTEP_WS", 1) != 0)
+              k_estep_pair_ws<<<std::min<unsigned>(pgrid, (unsigned)(ctx->sm_count * ctx->epw_blocks)), E_WARPS * 32, EPW_SMEM, s>>>(
+                  pair_cnt.p, pdesc.p, phil.p, NI, pk.rt, NI, d_ES.p);
+          else k_estep_pair<false><<<pgrid, E_WARPS * 32, EP_SMEM, s>>>(pair_cnt.p, pdesc.p, phil.p, NI, pk.rt, NI, d_ES.p); }
         { KTimer kt(ctx, CPN_K_PREP); k_unpack3<<<blocks_for(NI, 256), 256, 0, s>>>(NI, d_ES.p, d_ESo.p); }
         CPN_CUDA(ctx, d_ESo.download(ES, 3 * NI, s));
         CPN_CUDA(ctx, cudaGetLastError());

@@ -74,19 +74,27 @@ def test_estep_ragged_and_extreme(engine, orc):
         assert close(lp[r], lp_o, 1e-10), (r, lp[r], lp_o)
 
 
-def test_estep_pairs_vs_oracle_and_single(engine, orc, cpn, batch):
-    """The paired E-step (two starts of a region per warp, two reads per lane — what every EM iteration of cpn_fit_batch runs)
+@pytest.mark.parametrize("ws", [0, 1])
+def test_estep_pairs_vs_oracle_and_single(engine, orc, cpn, batch, monkeypatch, ws):
+    """ws = 1: the same through k_estep_pair_ws (resident grid, pairs taken from a queue, next pair's head prefetched), which must
+    also be bit-identical to k_estep_pair.  The paired E-step (two starts of a region per warp, two reads per lane — what every EM iteration of cpn_fit_batch runs)
     against the oracle and against the one-instance kernel: odd and even numbers of starts, both signs of c in one region
     (only equal signs are paired, the rest run as singletons), starts that disagree on the sign of α_l (general block body),
     ragged read counts over one and several 32-read chunks, chains shorter than a block and longer than a tile, LLRs beyond
     the unscaled-run bound (per-group rescale path)."""
     rng = np.random.default_rng(17)
+    monkeypatch.setenv("CPN_ESTEP_WS", str(ws))
     # (1) the simulated nanopore batch, 5 starts per region
     n_init = 5
     phis = cpn.simulations.gen_phi0s(rng, batch.R, n_init)
     phis[::2, 1, 2] *= -1.0; phis[::3, 3, 2] *= -1.0; phis[1::4, :, 0] *= -1.0
     ES = engine.lib.estep_batch_starts(batch.grp_off, batch.Nl, batch.rho_l, batch.d_l, batch.read_off, batch.log_pyx_u, batch.log_pyx_m, phis)
     assert np.all(np.isfinite(ES))
+    if ws:
+        monkeypatch.setenv("CPN_ESTEP_WS", "0")
+        ES_plain = engine.lib.estep_batch_starts(batch.grp_off, batch.Nl, batch.rho_l, batch.d_l, batch.read_off, batch.log_pyx_u, batch.log_pyx_m, phis)
+        monkeypatch.setenv("CPN_ESTEP_WS", "1")
+        assert np.array_equal(ES, ES_plain)
     for k in range(n_init):
         ES1, _ = engine.lib.estep_batch(batch.grp_off, batch.Nl, batch.rho_l, batch.d_l, batch.read_off, batch.log_pyx_u, batch.log_pyx_m,
                                         np.ascontiguousarray(phis[:, k]), with_logpy=False)
