@@ -973,6 +973,14 @@ __device__ __forceinline__ void ptile_load_staged(PairTileRegs& tr, const PairSt
 
 // estep_pair_chunk for plain regions with the first tile's tables taken from the stage when `staged`; `next` ≥ 0: once the first
 // tile has been consumed, the next pair's descriptor (group A, in flight since the loop top) is awaited and its tables are requested
+#ifndef EP_RUNPTR
+#define EP_RUNPTR 1
+#endif
+// one full block of E_PF rows (E_PF · 256 contiguous bytes at src) into the ring slot at shared-memory address dst
+__device__ __forceinline__ void ering_issue_at(unsigned dst, unsigned mbar, const char* src, int lane) {
+    __syncwarp();                                        // every lane is done with what the slot held
+    if (lane == 0) tma_rows(dst, reinterpret_cast<const double*>(src), (unsigned)(E_PF * 256), mbar);
+}
 __device__ __forceinline__ void estep_pair_chunk_ws(PairTile& pt, EmisRing& ring, PairStage& stg, const RegionTables& rt, int L, int lane,
                                                     const double* __restrict__ na_g, const double* __restrict__ nb_g,
                                                     const double* __restrict__ invd_g, EmisSrc<false>& es, double a, double b, double cabs,
@@ -986,6 +994,12 @@ __device__ __forceinline__ void estep_pair_chunk_ws(PairTile& pt, EmisRing& ring
     const int Lfull = L & ~(E_PF - 1);
     constexpr unsigned ALL = (1u << E_PF) - 1;
     ering_issue(ring, 2, es, false, Lfull, L - Lfull, lane);
+    // the full blocks' rows: a running pointer into the r plane (the 1/r plane lies dpi bytes further) instead of addresses rebuilt
+    // from the chunk's offsets by the one issuing lane
+#if EP_RUNPTR
+    const char* nxt = reinterpret_cast<const char*>(es.p);
+    const long long dpi = reinterpret_cast<const char*>(rt.ewi) - reinterpret_cast<const char*>(rt.ew);
+#endif
     int g = 0;
     for (int l0 = 0; l0 < L; l0 += TILE) {
         const int n = min(TILE, L - l0);
@@ -994,7 +1008,15 @@ __device__ __forceinline__ void estep_pair_chunk_ws(PairTile& pt, EmisRing& ring
         unsigned long long mP, mN;
         if (staged && l0 == 0) ptile_load_staged(tr, stg, n, i, a, b, mP, mN);
         else ptile_load(tr, l0, n, i, na_g, nb_g, invd_g, a, b, mP, mN);
+#if EP_RUNPTR
+        if (nfull > 0) {
+            ering_issue_at(es.ring + (unsigned)(g & 1) * (unsigned)(E_PF * 256), es.mbar + 8u * (unsigned)(g & 1),
+                           nxt + ((((unsigned)mP & ALL) == ALL) ? dpi : 0ll), lane);
+            nxt += E_PF * 256;
+        }
+#else
         ering_issue(ring, g & 1, es, ((unsigned)mP & ALL) == ALL, g * E_PF, nfull > 0 ? E_PF : 0, lane);
+#endif
         __syncwarp();
         ptile_store(pt, tr, l0, n, h, i, cabs, bpos);
         __syncwarp();
@@ -1011,7 +1033,15 @@ __device__ __forceinline__ void estep_pair_chunk_ws(PairTile& pt, EmisRing& ring
             const unsigned bp = (unsigned)(mP >> j0) & ALL, bn = (unsigned)(mN >> j0) & ALL;
             const int j1 = j0 + E_PF;
             const unsigned bp1 = (unsigned)(mP >> (j1 & (TILE - 1))) & ALL;
+#if EP_RUNPTR
+            if (j1 < nfull) {
+                ering_issue_at(es.ring + (unsigned)((g + 1) & 1) * (unsigned)(E_PF * 256), es.mbar + 8u * (unsigned)((g + 1) & 1),
+                               nxt + (bp1 == ALL ? dpi : 0ll), lane);
+                nxt += E_PF * 256;
+            }
+#else
             ering_issue(ring, (g + 1) & 1, es, bp1 == ALL, (g + 1) * E_PF, (j1 < nfull) ? E_PF : 0, lane);
+#endif
             const int slot = g & 1;
             ering_wait<1>(es, slot);
             if (g > 0 && (g & rmask) == 0) { estep_rescale(s0); estep_rescale(s1); }
