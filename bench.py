@@ -64,6 +64,11 @@ def load_peaks():
         return {}
 
 
+# kernel behind each timing class of cpn_get_profile (the E-step of a fit is the paired kernel; plain regions go through its
+# resident work-queue form, views of the two-sample test through k_estep_pair<views>)
+KERNEL_NAME = {"estep": "k_estep_pair_ws", "mstep": "k_mstep_ws"}
+
+
 def ncu_traffic(kernel, workload):
     """dram__bytes_read.sum + dram__bytes_write.sum per launch of `kernel` from the committed ncu capture of this workload
     (profiles/r02_ncu_traffic.json, written from `ncu --set full` reports); None when no capture is committed."""
@@ -537,7 +542,7 @@ def bench_fit(env):
                          "two_table_entry": {"entry": "cpn_analyze_batch", "value": R_all * args.steps / t_e2e_two,
                                              "h2d_bytes_per_step": int(h2d_two_tables * world), "bit_identical_outputs_rank0": bool(same_bits)}},
                  "gpu_launches": int(launches_all), "clocks": clocks, "mstep": {"mode": args.mstep_mode},
-                 "roofline": {"bound": "fp64", "kernel": "k_" + dom, "achieved": achieved, "peak": fp64_peak, "unit": "TFLOP/s",
+                 "roofline": {"bound": "fp64", "kernel": KERNEL_NAME[dom], "achieved": achieved, "peak": fp64_peak, "unit": "TFLOP/s",
                               "frac": achieved / fp64_peak if fp64_peak else None,
                               "traffic": tr["bytes_per_launch"] if tr else None, "traffic_note": tr["note"] if tr else "no ncu capture committed for this workload",
                               "peak_source": "DFMA loop (8 independent chains per thread, 128x8 threads per SM, 5 launches of >= 10 ms, best) measured on this "
@@ -691,7 +696,8 @@ def bench_two_sample(env):
                          "ms_steps_rank0": steps_ms},
                  "refits_per_s": world * R * 2 * P * args.steps / (dev_ms * 1e-3), "em_instances_per_step": float(work[3] / args.steps),
                  "gpu_launches": int(tot.item()), "clocks": clocks, "mstep": {"mode": args.mstep_mode},
-                 "roofline": {"bound": "fp64", "kernel": "k_" + dom, "achieved": achieved, "peak": fp64_peak, "unit": "TFLOP/s",
+                 "roofline": {"bound": "fp64", "kernel": "k_estep_pair<views>" if dom == "estep" else KERNEL_NAME[dom], "achieved": achieved, "peak": fp64_peak,
+                              "unit": "TFLOP/s",
                               "frac": achieved / fp64_peak if fp64_peak else None, "traffic": tr["bytes_per_launch"] if tr else None,
                               "traffic_note": tr["note"] if tr else "no ncu capture committed for this workload",
                               "peak_source": "DFMA loop measured on this GPU in this run", "launches": int(n_dom), "ms_per_launch": ms_dom / max(n_dom, 1),

@@ -24,6 +24,7 @@ def main():
     ap.add_argument("--chunks", default="4,6,8,12")
     ap.add_argument("--ratios", default="1.0,1.3,1.6")
     ap.add_argument("--workers", default="2,3")
+    ap.add_argument("--two-tables", action="store_true", help="cpn_analyze_batch instead of the packed entry bench.py's e2e leg uses")
     args = ap.parse_args()
     import torch
     import cpelnano_b200 as cpn
@@ -36,12 +37,18 @@ def main():
     host_out = {k: torch.empty(n, dtype=torch.float64 if dt == np.float64 else (torch.int32 if dt == np.int32 else torch.int64)).pin_memory()
                 for k, (n, dt) in shapes.items()}
     pin = {k: v.data_ptr() for k, v in host_in.items()}
+    packed = not args.two_tables
+    if packed:
+        host_llr = torch.empty(host_in["lu"].numel(), dtype=torch.float64).pin_memory()
+        host_base = torch.empty(int(arrays["read_off"][-1]), dtype=torch.float64).pin_memory()
+        lib.pack_emissions(arrays["grp_off"], arrays["read_off"], host_in["lu"].numpy(), host_in["lm"].numpy(), out=(host_llr.numpy(), host_base.numpy()))
+        pin = dict(pin, lu=host_llr.data_ptr(), lm=host_base.data_ptr())
     pout = {k: v.data_ptr() for k, v in host_out.items()}
 
     def call():
         torch.cuda.synchronize()
         t = time.perf_counter()
-        bench.run_step(lib, R, pin, pout, 10, 20, cpn.MSTEP_ANALYTIC, False, 0)
+        bench.run_step(lib, R, pin, pout, 10, 20, cpn.MSTEP_ANALYTIC, False, 0, packed=packed)
         return (time.perf_counter() - t) * 1e3
 
     ref = None
