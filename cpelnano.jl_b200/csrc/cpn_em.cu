@@ -2562,14 +2562,14 @@ int fit_impl(cpn_ctx* ctx, bool on_device, int64_t R, const int64_t* grp_off, co
 #ifdef EP_STATS
         if (pairs) {
             CPN_CUDA(ctx, cpn_wait_stream(ctx, s));
-            std::vector<int> h_pc(2 * max_em_iters), h_ct(2 * (max_em_iters + 1));
+            std::vector<int> h_pc(4 * max_em_iters), h_ct(2 * (max_em_iters + 1));
             unsigned long long h_st[8];
-            cudaMemcpy(h_pc.data(), pair_cnt.p, 2 * max_em_iters * sizeof(int), cudaMemcpyDeviceToHost);
+            cudaMemcpy(h_pc.data(), pair_cnt.p, 4 * max_em_iters * sizeof(int), cudaMemcpyDeviceToHost);
             cudaMemcpy(h_ct.data(), counts.p, h_ct.size() * sizeof(int), cudaMemcpyDeviceToHost);
             cudaMemcpyFromSymbol(h_st, ep_stats, sizeof(h_st));
             fprintf(stderr, "[ep_stats] blocks + %llu  - %llu  general %llu | singleton pairs %llu  full pairs %llu  slow %llu\n", h_st[0], h_st[1],
                     h_st[2], h_st[3], h_st[4], h_st[5]);
-            for (int it = 0; it < max_em_iters; ++it) fprintf(stderr, "[ep_stats] it %d active %d pairs c>=0 %d c<0 %d\n", it, h_ct[2 * it], h_pc[2 * it], h_pc[2 * it + 1]);
+            for (int it = 0; it < max_em_iters; ++it) fprintf(stderr, "[ep_stats] it %d active %d pairs c>=0 %d c<0 %d\n", it, h_ct[2 * it], h_pc[4 * it], h_pc[4 * it + 1]);
         }
 #endif
         DevBuf<double> work;
