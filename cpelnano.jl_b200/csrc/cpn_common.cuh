@@ -331,6 +331,28 @@ __device__ __forceinline__ double cpn_exp_neg(double x) {
     }
     return (e < -1021) ? 0.0 : y;
 }
+// cpn_exp_neg for arguments that are known not to be NaN-carrying results the caller still needs (the M-step sweep: a non-finite
+// trial point is caught by the solver's own checks).  The argument's high word is clamped at −708 with one integer minimum
+// (for negative doubles a larger magnitude is a larger unsigned high word; −Inf and sign-carrying NaNs clamp too), so the exponent
+// patch never leaves the normal range and the range tests of cpn_exp_neg (7 instructions, a branch) disappear.  Same bits as
+// cpn_exp_neg for −708 ≤ x ≤ 0; below that e^{−708} ≈ 3·10⁻³⁰⁸ instead of 0.
+__device__ __forceinline__ double cpn_exp_neg_clamped(double x) {
+    const double MAGIC = 6755399441055744.0;
+    x = __hiloint2double((int)min((unsigned)__double2hiint(x), 0xC0862000u), __double2loint(x));
+    double kd = fma(x, 92.332482616893656, MAGIC);
+    int ki = __double2loint(kd);
+    kd -= MAGIC;
+    double r = fma(kd, -0.01083042469326756, x);
+    r = fma(kd, -2.9815858269852933e-12, r);
+    double q = fma(r, 8.3333333333333332e-03, 4.1666666666666664e-02);
+    q = fma(q, r, 1.6666666666666666e-01);
+    q = fma(q, r, 0.5);
+    q = fma(q, r, 1.0);
+    q = q * r;
+    double T = __ldg(&cpn_exp_tbl[ki & 63]);
+    double y = fma(T, q, T);
+    return __hiloint2double(__double2hiint(y) + ((ki >> 6) << 20), __double2loint(y));
+}
 __device__ __forceinline__ double cpn_nan() { return __longlong_as_double(0x7ff8000000000000LL); }
 __device__ __forceinline__ double cpn_inf() { return __longlong_as_double(0x7ff0000000000000LL); }
 #endif

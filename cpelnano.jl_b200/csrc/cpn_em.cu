@@ -696,16 +696,32 @@ __device__ __forceinline__ void ptile_load(PairTileRegs& tr, int l0, int n, int 
         mN |= (unsigned long long)(~(bal | (bal >> 16)) & 0xffffu) << (16 * k);
     }
 }
+// The tile's exponentials without the range tests of cpn_exp_neg (cpn_exp_neg_clamped: 7 instructions and a branch less per
+// exponential): a start with a non-finite ϕ, whose NaN the tests used to carry into ES, is caught by pair_poison instead.
+#ifndef EP_EXP_CLAMPED
+#define EP_EXP_CLAMPED 1
+#endif
+#if EP_EXP_CLAMPED
+#define EP_EXP cpn_exp_neg_clamped
+#else
+#define EP_EXP cpn_exp_neg
+#endif
+// ES of a start whose ϕ is not finite is NaN (the M-step then reports the numerical failure, em_algorithm.jl:160-172)
+__device__ __forceinline__ void pair_poison(double a, double b, double c, double& acc0, double& acc1, double& acc2) {
+#if EP_EXP_CLAMPED
+    if (!(isfinite(a) && isfinite(b) && isfinite(c))) { acc0 = cpn_nan(); acc1 = cpn_nan(); acc2 = cpn_nan(); }
+#endif
+}
 __device__ __forceinline__ void ptile_store(PairTile& pt, const PairTileRegs& tr, int l0, int n, int h, int i, double cabs, bool bpos) {
     constexpr int K = TILE / 16;
 #pragma unroll
     for (int k = 0; k < K; ++k) {
         const int j = i + 16 * k, l = l0 + j;
         if (j < n) {
-            const double e = cpn_exp_neg(-2.0 * fabs(tr.alpha[k]));
+            const double e = EP_EXP(-2.0 * fabs(tr.alpha[k]));
             const bool pos = __double2hiint(tr.alpha[k]) >= 0;
             pt.w[h][j] = make_double2(pos ? e : 1.0, pos ? 1.0 : e);
-            pt.tn[h][j] = make_double2((l > 0) ? cpn_exp_neg(-2.0 * (cabs * tr.id[k])) : 0.0, tr.na[k]);
+            pt.tn[h][j] = make_double2((l > 0) ? EP_EXP(-2.0 * (cabs * tr.id[k])) : 0.0, tr.na[k]);
             pt.bd[h][j] = make_double2(tr.nb[k], bpos ? tr.id[k] : -tr.id[k]);
         }
     }
@@ -905,6 +921,7 @@ __global__ void __launch_bounds__(E_WARPS * 32, EP_BLOCKS) k_estep_pair(const in
         EP_COUNT(d0.y < 0 ? 3 : 4);
         if (mode == 0) EP_COUNT(5);
         const int inst = h ? d0.y : d0.x;
+        pair_poison(a, b, c, acc0, acc1, acc2);
         if (i == 0 && inst >= 0) { ES[inst] = acc0; ES[NI + inst] = acc1; ES[2 * NI + inst] = acc2; }
     }
 }
@@ -1157,6 +1174,7 @@ __global__ void __launch_bounds__(E_WARPS * 32, EP_BLOCKS) k_estep_pair_ws(int* 
             acc0 += v0; acc1 += v1; acc2 += v2;
         }
         const int inst = h ? d0.y : d0.x;
+        pair_poison(a, b, c, acc0, acc1, acc2);
         if (i == 0 && inst >= 0) { ES[inst] = acc0; ES[NI + inst] = acc1; ES[2 * NI + inst] = acc2; }
         if (!has_next) break;
         asm volatile("cp.async.wait_group 0;" ::: "memory");      // the next pair's tables (group B)
@@ -1377,6 +1395,14 @@ __device__ __forceinline__ SweepSite load_site(const SweepSite* __restrict__ p) 
     r.na = x0.x; r.nb = x0.y; r.id = x1.x; r.id2 = x1.y;
     return r;
 }
+#ifndef MS_EXP_CLAMPED
+#define MS_EXP_CLAMPED 1
+#endif
+#if MS_EXP_CLAMPED
+#define MS_EXP cpn_exp_neg_clamped          // a non-finite trial point never reaches the caller's results: see `stopped` in the solvers
+#else
+#define MS_EXP cpn_exp_neg
+#endif
 // Potentials of group l at ϕ (gauge for c<0: sign flip of N_l, N_lρ_l on odd groups and of 1/d everywhere).
 __device__ __forceinline__ SitePot site_pot(const SweepSite& r, int l, bool neg, double a, double b, double cabs) {
     const int flipbit = (neg && (l & 1)) ? (int)0x80000000 : 0;
@@ -1387,10 +1413,10 @@ __device__ __forceinline__ SitePot site_pot(const SweepSite& r, int l, bool neg,
     p.invd = __hiloint2double(__double2hiint(r.id) ^ negbit, __double2loint(r.id));
     p.invd2 = r.id2; p.na2 = r.na * r.na; p.nanb = r.na * r.nb; p.nb2 = r.nb * r.nb;
     double alpha = fma(b, p.nb, a * p.na);
-    double ex = cpn_exp_neg(-2.0 * fabs(alpha));
+    double ex = MS_EXP(-2.0 * fabs(alpha));
     const bool pos = __double2hiint(alpha) >= 0;
     p.w0 = pos ? ex : 1.0; p.w1 = pos ? 1.0 : ex;
-    p.t = cpn_exp_neg(-2.0 * (cabs * r.id));
+    p.t = MS_EXP(-2.0 * (cabs * r.id));
     return p;
 }
 
@@ -1665,7 +1691,7 @@ __device__ bool trust_region_solve(MProblem& pb, const double* x0, double* x, in
     *n_iters = 0;
     if (!allfinite3(r)) { *threw = true; return false; }
     bool x_conv = false, f_conv = norminf3(fval) <= ftol;
-    bool stopped = anynan3(x) || anynan3(fval);
+    bool stopped = !allfinite3(x) || anynan3(fval);      // NLsolve stops on NaN; a non-finite x gives NaN at its next evaluation
     bool conv = f_conv;
     if (conv) return true;
 #pragma unroll
@@ -1717,7 +1743,7 @@ __device__ bool trust_region_solve(MProblem& pb, const double* x0, double* x, in
         if (rho < 0.1) delta = delta / 2;
         else if (rho >= 0.9) delta = 2 * wnorm3(d, p);
         else if (rho >= 0.5) delta = fmax(delta, 2 * wnorm3(d, p));
-        stopped = anynan3(x) || anynan3(fval);
+        stopped = !allfinite3(x) || anynan3(fval);      // NLsolve stops on NaN; a non-finite x gives NaN at its next evaluation
     }
     *n_iters = it;
     return x_conv || f_conv;
@@ -1974,7 +2000,7 @@ __global__ void __launch_bounds__(M_THREADS, WS_BLOCKS) k_mstep_ws(int n_items, 
                 }
                 const bool threw = init && !allfinite3(fval);
                 const bool conv = accept && !threw && (x_conv || norminf3(r) <= ftol);
-                const bool stopped = anynan3(x) || anynan3(fval);
+                const bool stopped = !allfinite3(x) || anynan3(fval);      // NLsolve stops on NaN; a non-finite x gives NaN at its next evaluation
                 int code = 0;
                 if (threw) code = 2;
                 else if (conv) code = 1;

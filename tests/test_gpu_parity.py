@@ -233,6 +233,34 @@ def test_em_failure_modes(engine, cpn):
         engine.lib.fit_batch(np.array([0, 1]), [1.0], [0.1], [], np.array([0, 1]), [0.0], [0.0], np.zeros((1, 1, 3)), 1)
 
 
+def test_non_finite_starts_are_numerical_failures(engine, cpn):
+    """A start whose ϕ0 is NaN or ±Inf never yields a fit: its E-step statistics are NaN (the tile's exponentials clamp their
+    argument, so the kernels poison ES explicitly), the M-step meets a non-finite residual — the exception the reference catches
+    and logs (em_algorithm.jl:160-172) — and the start ends with Q = −Inf.  The region's other starts are unaffected; a region
+    whose starts all fail that way reports CPN_FIT_NUMERICAL."""
+    nb = cpn.simulations.make_nano_batch(4, M=30, seed=19)
+    rng = np.random.default_rng(3)
+    n_init = 4
+    phi0 = cpn.simulations.gen_phi0s(rng, nb.R, n_init)
+    good = engine.lib.fit_batch(nb.grp_off, nb.Nl, nb.rho_l, nb.d_l, nb.read_off, nb.log_pyx_u, nb.log_pyx_m, phi0, n_init, 20, per_start=True)
+    bad = phi0.copy()
+    bad[0, :, :] = np.nan                    # region 0: every start
+    bad[1, 1, 0] = np.nan                    # region 1: start 1 (a)
+    bad[2, 2, 1] = np.inf                    # region 2: start 2 (b)
+    bad[3, 0, 2] = -np.inf                   # region 3: start 0 (c)
+    out = engine.lib.fit_batch(nb.grp_off, nb.Nl, nb.rho_l, nb.d_l, nb.read_off, nb.log_pyx_u, nb.log_pyx_m, bad, n_init, 20, per_start=True)
+    assert out["pick"][0] == -2 and np.all(np.isnan(out["phi_hat"][0])) and np.isneginf(out["Q"][0])
+    for r, k in ((1, 1), (2, 2), (3, 0)):
+        assert np.isneginf(out["Q_starts"][r, k]), (r, k, out["Q_starts"][r])
+        assert out["pick"][r] != k
+        others = [j for j in range(n_init) if j != k]
+        # the other starts of the region run their EM as usual (their pair partner differs from the clean run's, so the fits agree
+        # only up to the EM's own sensitivity to rounding, tests/test_em_sensitivity.py: no value comparison here)
+        assert np.all(np.isfinite(out["phi_starts"][r, others]))
+        assert (out["pick"][r] >= 0) == bool(np.any(np.isfinite(out["Q_starts"][r, others])))
+    assert np.all(np.isfinite(good["phi_starts"]))
+
+
 # ---- (a)+(d): summaries -------------------------------------------------------------------------------------------
 @pytest.mark.parametrize("name,rounded", [("full_example", False), ("targeted_example", True)])
 def test_stat_sums_vs_oracle_and_goldens(engine, orc, name, rounded):
