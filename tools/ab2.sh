@@ -7,5 +7,5 @@ for cfg in "$@"; do
     if [ "$L" != "-" ]; then export CPN_LIB=$PWD/$L; fi
     for kv in "${parts[@]:1}"; do export "$kv"; done
     python bench.py --steps 3 --warmup 2 --no-cpu 2>/dev/null | python -c "
-import json,sys; d=json.loads(sys.stdin.read().strip().splitlines()[-1]); print('$cfg', round(d['value']), round(d['ms_per_step'],2), d['kernel_ms_per_step'], 'e2e', d['e2e']['ms_steps_rank0'], 'conv', d['fit_stats']['converged_regions'], 'iters', d['fit_stats']['em_iters_per_region'], 'frac', d['roofline']['frac'])" )
+import json,sys; d=json.loads(sys.stdin.read().strip().splitlines()[-1]); print('$cfg', round(d['value']), round(d['ms_per_step'],2), d['kernel_ms_per_step'], 'e2e', d['e2e']['ms_steps_rank0'], 'stats', d['fit_stats'], 'frac', d['roofline']['frac'])" )
 done
