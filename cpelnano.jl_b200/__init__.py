@@ -29,8 +29,8 @@ from . import genome        # noqa: F401
 from . import nanopolish    # noqa: F401
 from . import outputs       # noqa: F401
 from . import pipeline      # noqa: F401
-from .pipeline import analyze_nano, analyze_nano_csr, merge_shards, diff_grp_comp, diff_grp_comp_csr, diff_two_samp_comp   # noqa: F401
+from .pipeline import analyze_nano, analyze_bam, analyze_nano_csr, merge_shards, diff_grp_comp, diff_grp_comp_csr, diff_two_samp_comp   # noqa: F401
 
 __all__ = ["Library", "CpnError", "Engine", "CpelNanoConfig", "RegStruct", "get_phihat", "rscle_grp_mod", "get_nls_reg_info",
            "get_stat_sums", "comp_cmd", "unmat_est_reg_test", "mat_est_reg_test", "pmap_two_samp_null_stats", "analyze_regions", "analyze_regions_wgbs",
-           "simulations", "sharding", "genome", "nanopolish", "outputs", "pipeline", "analyze_nano", "analyze_nano_csr", "merge_shards", "diff_grp_comp_csr", "diff_grp_comp", "diff_two_samp_comp", "default_engine", "MSTEP_FD", "MSTEP_ANALYTIC"]
+           "simulations", "sharding", "genome", "nanopolish", "outputs", "pipeline", "analyze_nano", "analyze_bam", "analyze_nano_csr", "merge_shards", "diff_grp_comp_csr", "diff_grp_comp", "diff_two_samp_comp", "default_engine", "MSTEP_FD", "MSTEP_ANALYTIC"]

@@ -20,7 +20,9 @@ SYMBOLS = ["cpn_create", "cpn_create_multi", "cpn_num_devices", "cpn_destroy", "
            "cpn_calls_chr_name", "cpn_calls_chr_lines", "cpn_calls_read_name", "cpn_calls_count_reads", "cpn_calls_fill",
            "cpn_cpg_scan", "cpn_chr_part", "cpn_grp_info_count", "cpn_grp_info_fill", "cpn_format_f64", "cpn_write_rows", "cpn_write_theta", "cpn_nls_reg_info_batch", "cpn_calls_coverage", "cpn_fasta_open", "cpn_fasta_close", "cpn_fasta_open_error",
            "cpn_fasta_num_records", "cpn_fasta_name", "cpn_fasta_length", "cpn_fasta_seq", "cpn_add_qvalues", "cpn_theta_open", "cpn_theta_close", "cpn_theta_open_error",
-           "cpn_theta_num_rows", "cpn_theta_num_chr", "cpn_theta_chr_name", "cpn_theta_copy"]
+           "cpn_theta_num_rows", "cpn_theta_num_chr", "cpn_theta_chr_name", "cpn_theta_copy",
+           "cpn_bam_open", "cpn_bam_close", "cpn_bam_open_error", "cpn_bam_error", "cpn_bam_num_records", "cpn_bam_num_refs", "cpn_bam_ref_name", "cpn_bam_ref_len",
+           "cpn_bam_record", "cpn_bam_count_reads", "cpn_bam_fill_calls"]
 
 
 class CpnError(RuntimeError):
@@ -752,3 +754,80 @@ class CallsHandle:
         if rc != 0:
             raise CpnError(f"cpn_calls_fill error {rc}: {self.lib.dll.cpn_calls_error(self.h).decode()}")
         return (read_off, lu, lm, ids) if want_ids else (read_off, lu, lm)
+
+
+class BamHandle:
+    """cpn_bam: a BAM file (Bismark / Arioc XM tags) inflated and indexed once by the native reader (csrc/cpn_bam.cpp).
+    Host-only — works without a GPU."""
+
+    def __init__(self, lib, path, n_threads=0):
+        self.lib = lib
+        d = lib.dll
+        d.cpn_bam_open.argtypes = [C.c_char_p, C.c_int32, C.POINTER(C.c_void_p)]
+        d.cpn_bam_close.argtypes = [C.c_void_p]
+        d.cpn_bam_open_error.restype = d.cpn_bam_error.restype = d.cpn_bam_ref_name.restype = C.c_char_p
+        d.cpn_bam_error.argtypes = d.cpn_bam_num_records.argtypes = d.cpn_bam_num_refs.argtypes = [C.c_void_p]
+        d.cpn_bam_num_records.restype = d.cpn_bam_num_refs.restype = d.cpn_bam_ref_len.restype = C.c_int64
+        d.cpn_bam_ref_name.argtypes = d.cpn_bam_ref_len.argtypes = [C.c_void_p, C.c_int64]
+        h = C.c_void_p()
+        rc = d.cpn_bam_open(str(path).encode(), C.c_int32(n_threads), C.byref(h))
+        if rc != 0 or not h.value:
+            raise CpnError(f"cpn_bam_open failed with code {rc}: {d.cpn_bam_open_error().decode()}")
+        self.h = h
+        self.n_records = int(d.cpn_bam_num_records(h))
+        self.refs = {d.cpn_bam_ref_name(h, C.c_int64(i)).decode(): int(d.cpn_bam_ref_len(h, C.c_int64(i))) for i in range(int(d.cpn_bam_num_refs(h)))}
+        self.ref_names = list(self.refs)
+
+    def close(self):
+        if self.h is not None:
+            self.lib.dll.cpn_bam_close(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def record(self, i):
+        """Fields of record i (file order) as the reference's BAM accessors give them: dict(ref, pos, rightpos, flag, mapq, has_xm,
+        has_xs, qname, xm)."""
+        ref, flag, mapq, hxm, hxs = C.c_int32(), C.c_int32(), C.c_int32(), C.c_int32(), C.c_int32()
+        pos, right, ql, xl = C.c_int64(), C.c_int64(), C.c_int64(), C.c_int64()
+        qn, xm = C.c_void_p(), C.c_void_p()
+        rc = self.lib.dll.cpn_bam_record(self.h, C.c_int64(int(i)), C.byref(ref), C.byref(pos), C.byref(right), C.byref(flag), C.byref(mapq),
+                                         C.byref(hxm), C.byref(hxs), C.byref(qn), C.byref(ql), C.byref(xm), C.byref(xl))
+        if rc != 0:
+            raise CpnError(f"cpn_bam_record({i}) failed with code {rc}")
+        return dict(ref=ref.value, pos=pos.value, rightpos=right.value, flag=flag.value, mapq=mapq.value, has_xm=bool(hxm.value),
+                    has_xs=bool(hxs.value), qname=C.string_at(qn.value, ql.value).decode(),
+                    xm=C.string_at(xm.value, xl.value).decode() if hxm.value and xl.value else "")
+
+    def _args(self, chrom, roi_st, roi_end, cpg_off, cpg_pos, pe, trim):
+        roi_st, roi_end, cpg_off, cpg_pos = _i64(roi_st), _i64(roi_end), _i64(cpg_off), _i64(cpg_pos)
+        trim = _i64(list(trim))
+        assert trim.size == 4 and len(cpg_off) == len(roi_st) + 1
+        return roi_st, roi_end, cpg_off, cpg_pos, trim
+
+    def count_reads(self, chrom, roi_st, roi_end, cpg_off, cpg_pos, pe=False, trim=(0, 0, 0, 0), n_threads=0):
+        roi_st, roi_end, cpg_off, cpg_pos, trim = self._args(chrom, roi_st, roi_end, cpg_off, cpg_pos, pe, trim)
+        n = np.zeros(len(roi_st), dtype=np.int64)
+        rc = self.lib.dll.cpn_bam_count_reads(self.h, chrom.encode(), C.c_int64(len(roi_st)), _ptr(roi_st), _ptr(roi_end), _ptr(cpg_off), _ptr(cpg_pos),
+                                              C.c_int32(int(bool(pe))), _ptr(trim), C.c_int32(n_threads), _ptr(n))
+        if rc != 0:
+            raise CpnError(f"cpn_bam_count_reads error {rc}: {self.lib.dll.cpn_bam_error(self.h).decode()}")
+        return n
+
+    def calls(self, chrom, roi_st, roi_end, cpg_off, cpg_pos, pe=False, trim=(0, 0, 0, 0), n_threads=0):
+        """get_calls_bam for every region of a chromosome → (read_off [R+1], calls int8 flat, read-major [m_r × N_r] per region)."""
+        roi_st, roi_end, cpg_off, cpg_pos, trim = self._args(chrom, roi_st, roi_end, cpg_off, cpg_pos, pe, trim)
+        n = self.count_reads(chrom, roi_st, roi_end, cpg_off, cpg_pos, pe, trim, n_threads)
+        read_off = np.concatenate([[0], np.cumsum(n)]).astype(np.int64)
+        cell_off = np.concatenate([[0], np.cumsum(n * np.diff(cpg_off))]).astype(np.int64)
+        out = np.zeros(int(cell_off[-1]), dtype=np.int8)
+        if len(roi_st):
+            rc = self.lib.dll.cpn_bam_fill_calls(self.h, chrom.encode(), C.c_int64(len(roi_st)), _ptr(roi_st), _ptr(roi_end), _ptr(cpg_off), _ptr(cpg_pos),
+                                                 C.c_int32(int(bool(pe))), _ptr(trim), C.c_int32(n_threads), _ptr(cell_off), _ptr(out))
+            if rc != 0:
+                raise CpnError(f"cpn_bam_fill_calls error {rc}: {self.lib.dll.cpn_bam_error(self.h).decode()}")
+        return read_off, out

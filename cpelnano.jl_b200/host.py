@@ -30,6 +30,8 @@ class CpelNanoConfig:
     verbose: bool = False
     LMAX_TWO_SAMP: int = 100
     pval_comp: bool = True
+    trim: tuple = (0, 0, 0, 0)            # WGBS: bases trimmed from the XM strings (R1 5', R1 3', R2 5', R2 3'), structures.jl:53
+    pe: bool = False                      # WGBS: paired-end BAM, structures.jl:54
     mstep_mode: int = MSTEP_ANALYTIC      # B200 extension: see include/cpelnano_b200.h
 
     @classmethod
@@ -574,9 +576,9 @@ def pmap_two_samp_null_stats(rs_ref, calls_s1, calls_s2, perm_ids, config, phi0s
 def analyze_regions_wgbs(regs, calls, config, phi0s=None, rng=None, engine=None):
     """The body of pmap_analyze_reg_bam (src/wgbs.jl:335-389) for a batch of regions: `regs` carry the per-CpG features of
     get_grp_info!(rs, fa_rec, 1) (every CpG its own group), `calls[i]` is the int8 [M_i, N_i] table of the region's reads
-    (−1 unmethylated, +1 methylated, 0 not covered — what get_calls_bam extracts from the XM tags; the BAM parser itself is not
-    part of this package).  Filters of :363-367, then get_ϕhat_wgbs! and get_stat_sums! in one cpn_analyze_wgbs_batch call."""
-    eng = engine or default_engine()
+    (−1 unmethylated, +1 methylated, 0 not covered — what get_calls_bam extracts from the XM tags: capi.BamHandle.calls,
+    csrc/cpn_bam.cpp).  Filters of :363-367, then get_ϕhat_wgbs! and get_stat_sums! in one cpn_analyze_wgbs_batch call.  `engine`
+    may be a callable returning the engine: it is only called when a region passes the filters."""
     keep = []
     for i, (rs, x) in enumerate(zip(regs, calls)):
         x = np.asarray(x, dtype=np.int8)
@@ -590,6 +592,7 @@ def analyze_regions_wgbs(regs, calls, config, phi0s=None, rng=None, engine=None)
             keep.append(i)
     if not keep:
         return regs
+    eng = engine() if callable(engine) else (engine or default_engine())
     sel = [regs[i] for i in keep]
     cpg_off = np.concatenate([[0], np.cumsum([len(rs.cpg_pos) for rs in sel])]).astype(np.int64)
     read_off = np.concatenate([[0], np.cumsum([np.asarray(calls[i]).shape[0] for i in keep])]).astype(np.int64)

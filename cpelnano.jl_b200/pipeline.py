@@ -84,6 +84,71 @@ def analyze_nano(nano, fasta, config, out_dir, out_prefix, bed_reg=None, mod_nse
     return done
 
 
+def analyze_bam(bam, fasta, config, out_dir, out_prefix, bed_reg=None, rng=None, phi0_fn=None, engine=None, lib=None, timings=None):
+    """analyze_bam (src/wgbs.jl:401-464): ϕ̂, MML and NME of every estimation region from a Bismark / Arioc BAM file.  Per
+    chromosome: partition (get_chr_part with config.min_grp_dist, :441), per-CpG features (get_grp_info!(rs, fa_rec, 1), :351),
+    the calls of ALL its regions in one pass over the BAM (capi.BamHandle.calls = get_calls_bam, :357), then the body of
+    pmap_analyze_reg_bam for the whole batch (host.analyze_regions_wgbs) and the writers.  config.pe / config.trim as in the
+    reference.  The library is used without a device context until a region passes the data filters, so a run in which none
+    does (the reference's own example: 7 CpG sites) needs no GPU.  Returns the list of processed RegStructs."""
+    import time
+    from . import capi
+    from .host import analyze_regions_wgbs
+    tm = timings if timings is not None else {}
+
+    def lap(key, t0):
+        tm[key] = tm.get(key, 0.0) + time.perf_counter() - t0
+        return time.perf_counter()
+
+    lib = lib or (engine.lib if engine is not None else capi.Library())
+    holder = {"eng": engine}
+
+    def get_engine():
+        if holder["eng"] is None:
+            holder["eng"] = default_engine()
+        return holder["eng"]
+
+    t = time.perf_counter()
+    chroms = genome.load_genome(fasta, lib)
+    t = lap("fasta_and_cpg_index_s", t)
+    os.makedirs(out_dir, exist_ok=True)
+    files = outputs.OutputFiles(out_dir, out_prefix)
+    if _outputs_exist(files.all()):
+        return None
+    targets = genome.read_bed(bed_reg) if bed_reg else None
+    t = time.perf_counter()
+    reads = capi.BamHandle(lib, bam)
+    t = lap("bam_inflate_and_index_s", t)
+    done = []
+    for name, chrom in chroms.items():
+        if targets is not None and name not in targets:
+            continue
+        t = time.perf_counter()
+        part = chrom.chr_part_native(lib, config.size_est_reg, config.min_grp_dist, None if targets is None else targets[name])
+        _print_log(config, f"chr {name}: {len(part)} estimation regions")
+        regs = chrom.region_structs(lib, part, 1)                 # every CpG its own group (:351)
+        t = lap("partition_and_features_s", t)
+        cand = [rs for rs in regs if len(rs.cpg_pos) > 9]          # pmap_analyze_reg_bam returns before get_calls_bam otherwise (:353)
+        calls = []
+        if cand:
+            cpg_off = np.concatenate([[0], np.cumsum([len(rs.cpg_pos) for rs in cand])]).astype(np.int64)
+            read_off, flat = reads.calls(name, [rs.chrst for rs in cand], [rs.chrend for rs in cand], cpg_off,
+                                         np.concatenate([rs.cpg_pos for rs in cand]), config.pe, config.trim)
+            cell = np.concatenate([[0], np.cumsum(np.diff(read_off) * np.diff(cpg_off))])
+            calls = [flat[cell[i]:cell[i + 1]].reshape(int(read_off[i + 1] - read_off[i]), int(cpg_off[i + 1] - cpg_off[i])) for i in range(len(cand))]
+        t = lap("calls_s", t)
+        phi0s = phi0_fn(len(cand)) if (phi0_fn is not None and cand) else None
+        if cand:
+            analyze_regions_wgbs(cand, calls, config, phi0s=phi0s, rng=rng, engine=get_engine)
+        t = lap("fit_and_summaries_s", t)
+        outputs.write_output(regs, files, lib)
+        t = lap("write_outputs_s", t)
+        done.extend(rs for rs in regs if rs.proc)
+        tm["regions"] = tm.get("regions", 0) + len(part)
+        tm["regions_fitted"] = tm.get("regions_fitted", 0) + sum(1 for rs in regs if rs.proc)
+    return done
+
+
 def analyze_nano_csr(nano, fasta, config, out_dir, out_prefix, bed_reg=None, mod_nse=True, rng=None, phi0_fn=None, engine=None, timings=None,
                      block_regions=50_000, rank=0, world=1, phi0_by_region=None):
     """analyze_nano without per-region Python objects: every stage works on the CSR arrays of a block of estimation regions —

@@ -179,7 +179,7 @@ int cpn_analyze_batch_packed(cpn_ctx* ctx, int64_t R,
                   double* e_log_g1, double* e_log_g2, double* mml, double* nme);
 
 /* ---- WGBS front-end: pmap_analyze_reg_bam  src/wgbs.jl:335-389, get_ϕhat_wgbs!  src/em_algorithm.jl:556-575 ---------------
- * Input = what get_calls_bam (wgbs.jl:222-323; the BAM/XM-tag parser itself is not part of this library) produces: per read and
+ * Input = what get_calls_bam (wgbs.jl:222-323; native reader: cpn_bam_* below) produces: per read and
  * CpG site a call x ∈ {-1 unmethylated, +1 methylated, 0 not covered}, int8, [Σ_r M_r·N_r] read-major per region.  The calls
  * are hard emissions (log p(y|x) ∈ {0, -50}, CpelNano.jl:32-33), the regions are modelled at CpG resolution (every CpG its own
  * group), and em_iter_wgbs (em_algorithm.jl:412-470) is em_iter on those emissions: the call packs them (cpn_wgbs_pack, one byte
@@ -443,6 +443,43 @@ const char* cpn_theta_chr_name(const cpn_theta* th, int64_t i);
 int cpn_theta_copy(const cpn_theta* th, int32_t* chr_id, int64_t* chrst, int64_t* chrend, double* phi);
 int cpn_write_theta(const char* path, const char* chr, int64_t R, const int64_t* chrst, const int64_t* chrend, const double* phi,
                     const int64_t* grp_off, const double* Nl, const double* rho_l, const double* d_l);
+
+/*   cpn_bam_*        get_calls_bam (src/wgbs.jl:222-323, with clean_records :93-118, order_bams :66-78, get_align_strand :23-55,
+ *                   try_olaps :129-139) for ALL estimation regions of a chromosome in two calls.  cpn_bam_open inflates a BAM file
+ *                   once (BGZF blocks in parallel, n_threads <= 0: all cores) and indexes its records by reference and position;
+ *                   no .bai is needed.  Host-only.
+ *   cpn_bam_record        fields of record i in file order, as the reference's accessors return them: position and rightposition
+ *                         1-based (BAM.position, BAM.rightposition), FLAG, MAPQ, presence of the XM / XS tags, template name and the
+ *                         XM:Z string (pointers into the handle, not NUL-terminated: use the lengths); any output may be NULL
+ *   cpn_bam_count_reads   n_reads[r] = templates of `chr` with at least one call on a CpG site of region r: records overlapping
+ *                         [roi_st[r], min(roi_end[r], chr_size - 151)], mapped, with XM, without XS, FLAG in {0,16,83,99,147,163},
+ *                         MAPQ > 39; single end (pe = 0): FLAG 0 / 16 only; paired end: names with exactly two such records,
+ *                         R1 = the mate that starts first, FLAG pairs (99,147) (83,163) (147,99) (163,83).  cpg_off [R+1] /
+ *                         cpg_pos: CSR of the regions' CpG positions (1-based, ascending).  trim[4] = (R1 5', R1 3', R2 5', R2 3')
+ *                         bases removed from the XM strings (config.trim).  A chromosome the BAM header does not know gives zeros.
+ *   cpn_bam_fill_calls    calls [sum_r n_reads[r] * N_r] int8, read-major per region (-1 unmethylated 'z', +1 methylated 'Z', 0 not
+ *                         covered): the layout cpn_wgbs_pack / cpn_analyze_wgbs_batch take; cell_off[r] = sum_{q<r} n_reads[q] * N_q.
+ *                         Rows follow the order of the reference's templates (first appearance among the region's records).
+ * Errors: cpn_bam_open returns non-zero and leaves the text in cpn_bam_open_error() (thread-local); an unexpected FLAG (the
+ * reference prints a message and exits, wgbs.jl:31-33, 45-47) makes the region calls return CPN_ERR_ARG with the text in
+ * cpn_bam_error().  One difference: a mate R2 that ends before R1's string does contributes nothing (the reference throws).       */
+typedef struct cpn_bam cpn_bam;
+int  cpn_bam_open(const char* path, int32_t n_threads, cpn_bam** out);
+void cpn_bam_close(cpn_bam* bam);
+const char* cpn_bam_open_error(void);
+const char* cpn_bam_error(const cpn_bam* bam);
+int64_t cpn_bam_num_records(const cpn_bam* bam);
+int64_t cpn_bam_num_refs(const cpn_bam* bam);
+const char* cpn_bam_ref_name(const cpn_bam* bam, int64_t i);
+int64_t cpn_bam_ref_len(const cpn_bam* bam, int64_t i);
+int cpn_bam_record(const cpn_bam* bam, int64_t i, int32_t* ref, int64_t* pos, int64_t* rightpos, int32_t* flag, int32_t* mapq,
+                   int32_t* has_xm, int32_t* has_xs, const char** qname, int64_t* qname_len, const char** xm, int64_t* xm_len);
+int cpn_bam_count_reads(const cpn_bam* bam, const char* chr, int64_t R, const int64_t* roi_st, const int64_t* roi_end,
+                        const int64_t* cpg_off, const int64_t* cpg_pos, int32_t pe, const int64_t* trim, int32_t n_threads,
+                        int64_t* n_reads);
+int cpn_bam_fill_calls(const cpn_bam* bam, const char* chr, int64_t R, const int64_t* roi_st, const int64_t* roi_end,
+                       const int64_t* cpg_off, const int64_t* cpg_pos, int32_t pe, const int64_t* trim, int32_t n_threads,
+                       const int64_t* cell_off, int8_t* calls);
 
 #ifdef __cplusplus
 }
