@@ -11,6 +11,7 @@
 #     analyze_nano(nano, fasta, config)                                     src/nanopore.jl:362
 #     diff_grp_comp(mod_fls_g1, mod_fls_g2, fasta, config)                   src/grp_perm_tests.jl:637
 #     diff_two_samp_comp(mods_s1, mods_s2, nano_s1, nano_s2, fasta, config)  src/two_samp_perm_tests.jl:408
+#     analyze_bam(bam, fasta, config)                                       src/wgbs.jl:401   (WGBS; get_calls_bam :222 too)
 # and so do the per-region functions they are built from:
 #     get_ϕhat!  get_stat_sums!  comp_cmd  unmat_est_reg_test  mat_est_reg_test  pmap_two_samp_null_stats
 # What changes is the batching: each `pmap` over regions (nanopore.jl:406, grp_perm_tests.jl:674) and the serial `map` over regions
@@ -22,7 +23,7 @@ using Combinatorics                                  # combinations(): the label
 using ..CpelNano: RegStruct, CpelNanoConfig, MethCallCpgGrp, AnalysisRegions, RegStatTestStruct, OutputFiles, OutputDiffFiles,
                   get_grp_info!, get_genome_info, get_chr_part, get_chr_fa_rec, read_bed_reg, check_output_exists, check_diff_output_exists,
                   read_mod_file_chr, read_in_grp_mods, find_comm_regs, write_output, write_diff_output, mult_hyp_corr, rscle_grp_mod!,
-                  gen_ϕ0s, print_log
+                  gen_ϕ0s, print_log, get_nls_reg_info!, log_pyx_right_x, log_pyx_wrong_x
 import ..CpelNano
 
 const LIB = Ref{String}("libcpelnano_b200")
@@ -322,6 +323,129 @@ function CpelNano.analyze_nano(nano::String, fasta::String, config::CpelNanoConf
         end
         fa_rec = get_chr_fa_rec(chr, fasta)
         write_output(analyze_chr(chr_part, chr, nano, fa_rec, config), config)      # was: pmap(pmap_analyze_reg, chr_part) :406
+    end
+    return nothing
+end
+
+# ---- WGBS: get_calls_bam (wgbs.jl:222-323) ↔ cpn_bam_*, analyze_bam (wgbs.jl:401-464) ↔ cpn_analyze_wgbs_batch ------------------
+# The BAM file is inflated and indexed once per path (no .bai needed); the calls of all regions of a chromosome come back as one
+# Int8 table (−1 unmethylated, +1 methylated, 0 not covered), which is also what cpn_analyze_wgbs_batch takes.
+const BAMS = Dict{String,Ptr{Cvoid}}()
+function bam_handle(bam::String)
+    get!(BAMS, bam) do
+        h = Ref{Ptr{Cvoid}}(C_NULL)
+        rc = ccall((:cpn_bam_open, LIB[]), Cint, (Cstring, Int32, Ref{Ptr{Cvoid}}), bam, 0, h)
+        rc == 0 || error("cpn_bam_open: " * unsafe_string(ccall((:cpn_bam_open_error, LIB[]), Cstring, ())))
+        h[]
+    end
+end
+bam_check(h, rc) = rc == 0 || error(unsafe_string(ccall((:cpn_bam_error, LIB[]), Cstring, (Ptr{Cvoid},), h)))
+# → (n_reads [R], cell_off [R+1], calls Int8 [Σ n_reads·N]) for regions (sts[r], ens[r]) with CpG sites cpg_pos[cpg_off[r]+1 : cpg_off[r+1]]
+function bam_calls(bam::String, chr::String, sts::Vector{Int64}, ens::Vector{Int64}, cpg_off::Vector{Int64}, cpg_pos::Vector{Int64},
+                   pe::Bool, trim::NTuple{4,Int64})
+    h = bam_handle(bam); R = length(sts); tr = Int64[trim...]
+    n = zeros(Int64, R)
+    GC.@preserve sts ens cpg_off cpg_pos tr n begin
+        bam_check(h, ccall((:cpn_bam_count_reads, LIB[]), Cint,
+            (Ptr{Cvoid}, Cstring, Int64, Ptr{Int64}, Ptr{Int64}, Ptr{Int64}, Ptr{Int64}, Int32, Ptr{Int64}, Int32, Ptr{Int64}),
+            h, chr, R, sts, ens, cpg_off, cpg_pos, pe, tr, 0, n))
+    end
+    cell_off = Int64[0; cumsum(n .* diff(cpg_off))]
+    calls = zeros(Int8, cell_off[end])
+    GC.@preserve sts ens cpg_off cpg_pos tr cell_off calls begin
+        bam_check(h, ccall((:cpn_bam_fill_calls, LIB[]), Cint,
+            (Ptr{Cvoid}, Cstring, Int64, Ptr{Int64}, Ptr{Int64}, Ptr{Int64}, Ptr{Int64}, Int32, Ptr{Int64}, Int32, Ptr{Int64}, Ptr{Int8}),
+            h, chr, R, sts, ens, cpg_off, cpg_pos, pe, tr, 0, cell_off, calls))
+    end
+    return n, cell_off, calls
+end
+# same signature and return value as the reference's (one region, boxed calls)
+function CpelNano.get_calls_bam(bam::String, chr::String, roi_st::Int64, roi_end::Int64, cpg_pos::Vector{Int64}, pe::Bool,
+                                trim::NTuple{4,Int64})::Tuple{Int64,Vector{Vector{MethCallCpgGrp}}}
+    N = length(cpg_pos)
+    n, _, x = bam_calls(bam, chr, [roi_st], [roi_end], Int64[0, N], cpg_pos, pe, trim)
+    calls = Vector{Vector{MethCallCpgGrp}}()
+    for m = 1:n[1]
+        call = Vector{MethCallCpgGrp}()
+        for k = 1:N
+            c = MethCallCpgGrp(); v = x[(m - 1) * N + k]
+            if v != 0                                          # wgbs.jl:296-307
+                c.obs = true
+                c.log_pyx_u = v < 0 ? log_pyx_right_x : log_pyx_wrong_x
+                c.log_pyx_m = v > 0 ? log_pyx_right_x : log_pyx_wrong_x
+            end
+            push!(call, c)
+        end
+        push!(calls, call)
+    end
+    return n[1], calls
+end
+function analyze_chr_bam(chr_part, chr, bam, fa_rec, config::CpelNanoConfig)
+    rss = RegStruct[]
+    for reg_int in chr_part                                   # host side of pmap_analyze_reg_bam (wgbs.jl:340-353), unchanged
+        rs = RegStruct(); rs.chr = chr; rs.chrst = minimum(reg_int); rs.chrend = maximum(reg_int)
+        get_grp_info!(rs, fa_rec, 1)                          # every CpG site its own group (:351)
+        push!(rss, rs)
+    end
+    cand = [rs for rs in rss if length(rs.cpg_pos) > 9]       # :353
+    isempty(cand) && return rss
+    cpg_off = Int64[0; cumsum([length(rs.cpg_pos) for rs in cand])]
+    n, cell_off, x = bam_calls(bam, chr, Int64[rs.chrst for rs in cand], Int64[rs.chrend for rs in cand], cpg_off,
+                               Int64.(vcat([rs.cpg_pos for rs in cand]...)), config.pe, config.trim)
+    keep = Int[]
+    for (i, rs) in enumerate(cand)                            # get_ave_depth ≥ min_cov, perc_gprs_obs ≥ 0.66, L > 1 (:363-367)
+        N = length(rs.cpg_pos); rs.m = n[i]
+        n[i] > 0 || continue
+        tbl = reshape(view(x, (cell_off[i] + 1):cell_off[i + 1]), N, n[i])       # column = read
+        depth = count(!=(0), tbl) / N
+        frac = count(k -> any(!=(0), view(tbl, k, :)), 1:N) / N
+        (depth >= config.min_cov && frac >= 0.66 && rs.L > 1) && push!(keep, i)
+    end
+    isempty(keep) && return rss
+    sel = cand[keep]; R = length(sel)
+    c_off, ρn, dn = pack_cpgs(sel)
+    r_off = Int64[0; cumsum(n[keep])]
+    xs = vcat([x[(cell_off[i] + 1):cell_off[i + 1]] for i in keep]...)
+    sub_off, sub_p, sub_q = pack_subregs(sel, config)
+    sN, sK = c_off[end], sub_off[end]
+    ϕ0 = starts(R, config)
+    ϕhat = Vector{Float64}(undef, 3R); Q = Vector{Float64}(undef, R); st = Vector{Int32}(undef, R)
+    logZ = Vector{Float64}(undef, R); ex = Vector{Float64}(undef, sN); exx = Vector{Float64}(undef, sN - R)
+    lg = Vector{Float64}(undef, 4sK); e1 = Vector{Float64}(undef, sK); e2 = similar(e1); mml = similar(e1); nme = similar(e1)
+    GC.@preserve c_off ρn dn r_off xs ϕ0 sub_off sub_p sub_q ϕhat Q st logZ ex exx lg e1 e2 mml nme begin
+        check(ccall((:cpn_analyze_wgbs_batch, LIB[]), Cint,
+            (Ptr{Cvoid}, Int64, Ptr{Int64}, Ptr{Float64}, Ptr{Float64}, Ptr{Int64}, Ptr{Int8}, Ptr{Float64}, Int32, Int32,
+             Float64, Float64, Float64, Int32, Ptr{Int64}, Ptr{Int64}, Ptr{Int64},
+             Ptr{Float64}, Ptr{Float64}, Ptr{Int32}, Ptr{Int64}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64},
+             Ptr{Float64}, Ptr{Float64}, Ptr{Float64}),
+            CTX[], R, c_off, ρn, dn, r_off, xs, ptr_or_null(ϕ0), config.max_em_init, config.max_em_iters,
+            CpelNano.AMAX, CpelNano.BMAX, CpelNano.CMAX, 1, sub_off, sub_p, sub_q,
+            ϕhat, Q, st, C_NULL, logZ, ex, exx, lg, e1, e2, mml, nme))
+    end
+    for (t, rs) in enumerate(sel)
+        st[t] >= 0 || continue                                # rs.ϕhat stays []: the writers skip the region (:376)
+        rs.ϕhat = ϕhat[(3t - 2):(3t)]
+        store_summaries!(rs, t, c_off, sub_off, logZ, ex, exx, lg, e1, e2, mml, nme)
+        rs.proc = true
+    end
+    return rss
+end
+function CpelNano.analyze_bam(bam::String, fasta::String, config::CpelNanoConfig)::Nothing
+    chr_names, chr_sizes = get_genome_info(fasta)
+    isdir(config.out_dir) || mkdir(config.out_dir)
+    config.out_files = OutputFiles(config.out_dir, config.out_prefix)
+    check_output_exists(config) && return nothing
+    targ_regs = isempty(config.bed_reg) ? nothing : read_bed_reg(config)
+    for i = 1:length(chr_names)
+        chr = chr_names[i]
+        if isnothing(targ_regs)
+            chr_part = get_chr_part(chr, config, fasta)
+        else
+            haskey(targ_regs, chr) || continue
+            chr_part = get_chr_part(chr, config, fasta, targ_regs[chr])
+        end
+        fa_rec = get_chr_fa_rec(chr, fasta)
+        write_output(analyze_chr_bam(chr_part, chr, bam, fa_rec, config), config)   # was: pmap(pmap_analyze_reg_bam, chr_part) :455
     end
     return nothing
 end
